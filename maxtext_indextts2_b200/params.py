@@ -1,0 +1,129 @@
+"""Parameter tree of the llama2-style decoder, with the reference's names and shapes.
+
+Tree (unscanned layout; SURVEY 5 "Checkpoint / resume", names from
+MaxText/layers/models.py:69, llama2.py:79,102,139, attentions.py:1865-1869,
+linears.py:347,373,388, decoders.py:544,573)::
+
+  params/token_embedder/embedding                       [V, E]
+  params/decoder/layers_{i}/pre_self_attention_layer_norm/scale   [E]
+  params/decoder/layers_{i}/self_attention/query/kernel  [E, Hq, D]
+  params/decoder/layers_{i}/self_attention/key/kernel    [E, Hkv, D]
+  params/decoder/layers_{i}/self_attention/value/kernel  [E, Hkv, D]
+  params/decoder/layers_{i}/self_attention/out/kernel    [Hq, D, E]
+  params/decoder/layers_{i}/mlp/mlp_layer_norm/scale     [E]
+  params/decoder/layers_{i}/mlp/wi_0/kernel              [E, M]
+  params/decoder/layers_{i}/mlp/wi_1/kernel              [E, M]
+  params/decoder/layers_{i}/mlp/wo/kernel                [M, E]
+  params/decoder/decoder_norm/scale                      [E]
+  params/decoder/logits_dense/kernel                     [E, V]   (absent if logits_via_embedding)
+
+Random init follows the reference's distributions (layers/initializers.py:31-43,
+models.py:68, linears.py:106, attentions.py:1510,1900-1904) but draws from
+numpy's PCG64 because JAX's bit streams are not reproducible outside JAX.
+"""
+
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+_TRUNC_STD = 0.87962566103423978  # std of a unit normal truncated to [-2, 2]
+
+
+def _normal(rng: np.random.Generator, shape, std: float, dtype: torch.dtype) -> torch.Tensor:
+  n = int(np.prod(shape))
+  out = torch.empty(n, dtype=dtype)
+  step = 1 << 24
+  for lo in range(0, n, step):
+    hi = min(n, lo + step)
+    chunk = rng.standard_normal(hi - lo, dtype=np.float32) * np.float32(std)
+    out[lo:hi] = torch.from_numpy(chunk).to(dtype)
+  return out.reshape(shape)
+
+
+def _truncated_normal(rng: np.random.Generator, shape, std: float, dtype: torch.dtype) -> torch.Tensor:
+  """variance_scaling(..., "truncated_normal"): unit normal cut at +-2, rescaled to `std`."""
+  n = int(np.prod(shape))
+  out = torch.empty(n, dtype=dtype)
+  step = 1 << 24
+  scale = np.float32(std / _TRUNC_STD)
+  for lo in range(0, n, step):
+    hi = min(n, lo + step)
+    chunk = rng.standard_normal(hi - lo, dtype=np.float32)
+    bad = np.abs(chunk) > 2.0
+    while bad.any():
+      chunk[bad] = rng.standard_normal(int(bad.sum()), dtype=np.float32)
+      bad = np.abs(chunk) > 2.0
+    out[lo:hi] = torch.from_numpy(chunk * scale).to(dtype)
+  return out.reshape(shape)
+
+
+def weight_torch_dtype(config) -> torch.dtype:
+  return torch.bfloat16 if config.weight_dtype == "bfloat16" else torch.float32
+
+
+def init_params(config, seed: int | None = None) -> dict:
+  """Random-init parameter tree on the CPU (reference: maxtext_utils.py:916-921)."""
+  seed = config.init_weights_seed if seed is None else seed
+  rng = np.random.Generator(np.random.PCG64(seed))
+  dt = weight_torch_dtype(config)
+  E, Hq, Hkv, D = config.emb_dim, config.num_query_heads, config.num_kv_heads, config.head_dim
+  M, V, L = config.mlp_dim, config.vocab_size, config.num_decoder_layers
+
+  params: dict = {"token_embedder": {"embedding": _normal(rng, (V, E), 1.0, dt)}}
+  dec: dict = {}
+  for i in range(L):
+    # attention kernels: variance_scaling(1.0, fan_in, normal); query additionally / sqrt(D)
+    q = _normal(rng, (E, Hq, D), 1.0 / math.sqrt(E), torch.float32) / math.sqrt(D)
+    k = _normal(rng, (E, Hkv, D), 1.0 / math.sqrt(E), dt)
+    v = _normal(rng, (E, Hkv, D), 1.0 / math.sqrt(E), dt)
+    o = _normal(rng, (Hq, D, E), 1.0 / math.sqrt(Hq * D), dt)
+    dec[f"layers_{i}"] = {
+        "pre_self_attention_layer_norm": {"scale": torch.ones(E, dtype=dt)},
+        "self_attention": {
+            "query": {"kernel": q.to(dt)},
+            "key": {"kernel": k},
+            "value": {"kernel": v},
+            "out": {"kernel": o},
+        },
+        "mlp": {
+            "mlp_layer_norm": {"scale": torch.ones(E, dtype=dt)},
+            "wi_0": {"kernel": _truncated_normal(rng, (E, M), 1.0 / math.sqrt(E), dt)},
+            "wi_1": {"kernel": _truncated_normal(rng, (E, M), 1.0 / math.sqrt(E), dt)},
+            "wo": {"kernel": _truncated_normal(rng, (M, E), 1.0 / math.sqrt(M), dt)},
+        },
+    }
+  dec["decoder_norm"] = {"scale": torch.ones(E, dtype=dt)}
+  if not config.logits_via_embedding:
+    dec["logits_dense"] = {"kernel": _truncated_normal(rng, (E, V), 1.0 / math.sqrt(E), dt)}
+  params["decoder"] = dec
+  return {"params": params}
+
+
+def perturb_norm_scales(params: dict, seed: int = 1) -> dict:
+  """Give the RMSNorm scales non-trivial values (tests only need them != 1)."""
+  rng = np.random.Generator(np.random.PCG64(seed))
+
+  def walk(node):
+    for k, v in node.items():
+      if isinstance(v, dict):
+        walk(v)
+      elif k == "scale":
+        node[k] = (1.0 + 0.1 * torch.from_numpy(rng.standard_normal(v.shape[0], dtype=np.float32))).to(v.dtype)
+
+  walk(params)
+  return params
+
+
+def param_count(config) -> dict:
+  E, Hq, Hkv, D = config.emb_dim, config.num_query_heads, config.num_kv_heads, config.head_dim
+  M, V, L = config.mlp_dim, config.vocab_size, config.num_decoder_layers
+  layer = E * Hq * D + 2 * E * Hkv * D + Hq * D * E + 3 * E * M + 2 * E
+  return {
+      "layers": L * layer,
+      "final_norm": E,
+      "logits": 0 if config.logits_via_embedding else E * V,
+      "embedding": V * E,
+  }
