@@ -1,0 +1,184 @@
+/*
+ * mtx_b200.h -- C ABI of the B200-native decode step for the IndexTTS2-on-MaxText
+ * text+audio-token transformer (HyperBlaze456/maxtext-indextts2).
+ *
+ * The reference has no FFI for this path: its decode step is one jax.jit executable
+ * (MaxText/maxengine.py:868-936).  Each entry point below names the reference function
+ * it replaces (file:line relative to the reference tree); INTEGRATION.md shows how a
+ * maintainer registers them as XLA custom calls with jax.ffi, or binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is DEVICE memory owned by the caller unless the comment says "host";
+ *   - matrices are row-major; activations and weights are bfloat16, statistics fp32,
+ *     indices int32;
+ *   - `stream` is a cudaStream_t; all work is enqueued on it, nothing synchronises;
+ *   - return value: 0 = ok, otherwise an MTX_ERR_* code; mtx_last_error() gives the text;
+ *   - no exceptions cross the ABI; functions are re-entrant per engine, an engine is
+ *     used from one host thread at a time (as MaxEngine is, SURVEY 8b "Threading");
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ *
+ * "rows": the independent sequences one call advances by one token -- the decode slots
+ * of a generate step, or the consecutive prompt positions of one prefill chunk.
+ */
+#ifndef MTX_B200_H_
+#define MTX_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTX_OK 0
+#define MTX_ERR_ARG 1         /* bad shape / null pointer / unsupported size           */
+#define MTX_ERR_CUDA 2        /* a CUDA runtime or driver call failed                  */
+#define MTX_ERR_UNSUPPORTED 3 /* config outside the hot path (e.g. head_dim not 64/128) */
+
+/* inference_utils.py:75-84 `sampling(..., algorithm)` */
+#define MTX_SAMPLE_GREEDY 0
+#define MTX_SAMPLE_WEIGHTED 1
+#define MTX_SAMPLE_NUCLEUS 2
+#define MTX_SAMPLE_TOPK 3
+
+typedef struct mtx_engine mtx_engine; /* opaque */
+typedef void* mtx_stream;             /* cudaStream_t */
+
+/* Model shape: the derived keys of MaxText/pyconfig.py:576-582 plus the numerics keys of
+ * configs/base.yml the step reads. */
+typedef struct {
+  int32_t num_layers;        /* num_decoder_layers */
+  int32_t emb_dim;           /* E */
+  int32_t num_q_heads;       /* Hq */
+  int32_t num_kv_heads;      /* Hkv */
+  int32_t head_dim;          /* D: 64 or 128 */
+  int32_t mlp_dim;           /* M */
+  int32_t vocab_size;        /* V rows of the logits matrix held by THIS process (a shard when vocab-parallel) */
+  int32_t vocab_offset;      /* global id of row 0 of that matrix */
+  int32_t max_prefill_len;   /* P = max_prefill_predict_length */
+  int32_t max_target_len;    /* T = max_target_length; the AR ring has T - P rows */
+  int32_t num_slots;         /* KV planes: decode slots plus any prefill staging planes */
+  int32_t max_rows;          /* most rows one call advances (<= 256) */
+  float rms_eps;             /* normalization_layer_epsilon */
+  float rope_min_timescale;  /* rope_min_timescale */
+  float rope_max_timescale;  /* rope_max_timescale */
+  float attn_softcap;        /* attn_logits_soft_cap, 0 = off */
+  float final_softcap;       /* final_logits_soft_cap, 0 = off */
+  float logits_scale;        /* 1, or 1/sqrt(E) when logits_via_embedding && normalize_embedding_logits */
+  int32_t logits_round_bf16; /* 1 unless logits_dot_in_fp32 (decoders.py:557,571) */
+} mtx_model_config;
+
+/* Weights, repacked once at load time for K-major streaming (see DESIGN.md "Data layout").
+ * All bfloat16.  Relation to the reference parameter tree ("Checkpoint / resume"):
+ *   wqkv[l]  [ (Hq+2Hkv)*D, E ]  rows = query|key|value kernels transposed (attentions.py:1894-2030)
+ *   wo[l]    [ E, Hq*D ]         out kernel transposed
+ *   w01[l]   [ 2*M, E ]          wi_0 / wi_1 transposed and interleaved in groups of 16 rows:
+ *                                rows 32g..32g+15 = wi_0[:, 16g..16g+15]^T, rows 32g+16..32g+31 = wi_1[...]^T
+ *   wout[l]  [ E, M ]            wo kernel transposed (linears.py:425-476)
+ *   logits   [ V, E ]            logits_dense kernel transposed, or the embedding table when tied
+ */
+typedef struct {
+  const void* embedding;  /* [V_full, E]   token_embedder/embedding as bf16 (embeddings.py:154) */
+  const void* attn_norm;  /* [L, E]        pre_self_attention_layer_norm/scale */
+  const void* wqkv;       /* [L, (Hq+2Hkv)*D, E] */
+  const void* wo;         /* [L, E, Hq*D] */
+  const void* mlp_norm;   /* [L, E]        mlp/mlp_layer_norm/scale */
+  const void* w01;        /* [L, 2*M, E] */
+  const void* wout;       /* [L, E, M] */
+  const void* final_norm; /* [E]           decoder_norm/scale */
+  const void* logits;     /* [V, E] */
+} mtx_weights;
+
+/* Decode state: the device-resident fields of the reference's decode_state dict
+ * (maxengine.py:930-936, 1415-1427) in this implementation's layout.
+ *   k_cache/v_cache  [L, num_slots, Hkv, T, D] bf16.  Rows [0,P) of a plane are the prefill
+ *                    segment (cached_prefill_key/value), rows [P,T) the AR ring
+ *                    (cached_ar_key/value); the reference's axis order keys select a layout,
+ *                    this is the one with the sequence contiguous per (slot, head).
+ *   prefill_len[s]   number of active prefill rows of slot s (== sum(cache_prefill_segment_id[s]))
+ *   ar_lengths[s]    cached_ar_lengths; ar_index[0] is the shared ring index cache_ar_index
+ */
+typedef struct {
+  void* k_cache;
+  void* v_cache;
+  int32_t* tokens;       /* [B]  decode_state["tokens"]           */
+  int32_t* next_pos;     /* [B]  decode_state["next_pos"]         */
+  int32_t* generated;    /* [B]  decode_state["generated_tokens"] */
+  int32_t* prefill_len;  /* [num_slots] */
+  int32_t* ar_lengths;   /* [num_slots] */
+  int32_t* ar_index;     /* [1] */
+  int32_t* result;       /* [B,3] ResultTokens.data: token, valid, length (maxengine.py:916-928) */
+  float* log_prob;       /* [B] or NULL (return_log_prob)         */
+  float* logits;         /* [B,V] fp32 or NULL: decode_state["logits"], only written when non-NULL */
+  uint32_t* rng_state;   /* [4] sampler stream: {step, seed_lo, seed_hi, 0}; step advances once per decode step */
+} mtx_decode_state;
+
+/* ---- engine ---------------------------------------------------------------------------- */
+
+/* Validates the shape and plans kernels (tile counts, split-K factors, workspace layout). */
+int mtx_engine_create(const mtx_model_config* cfg, mtx_engine** out);
+int mtx_engine_destroy(mtx_engine* e);
+
+/* Scratch the caller must provide to mtx_engine_bind (activations, split-K partials, ...). */
+size_t mtx_engine_workspace_bytes(const mtx_engine* e);
+
+/* Attach weights, state and scratch; builds the TMA descriptors.  Replaces
+ * MaxEngine.load_params + init_decode_state (maxengine.py:218, 1370) for the device side. */
+int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state* s, void* workspace, size_t workspace_bytes);
+
+/* inference_utils.py:66-84 arguments.  The random stream is keyed by decode_state.rng_state. */
+int mtx_engine_set_sampling(mtx_engine* e, int strategy, int top_k, float nucleus_p, float temperature);
+
+/* One autoregressive step for slots [0, rows): MaxEngine._generate_jit (maxengine.py:868-936).
+ * Reads tokens/next_pos, appends K/V at the shared ring index, attends over the valid rows
+ * of both cache segments, samples, and advances next_pos / generated / ar_index / ar_lengths. */
+int mtx_decode_step(mtx_engine* e, int rows, mtx_stream stream);
+
+/* Same step, replayed from a CUDA graph captured on first use (one graph per `rows`). */
+int mtx_decode_step_graph(mtx_engine* e, int rows, mtx_stream stream);
+
+/* `count` consecutive prompt positions [start_pos, start_pos+count) of one sequence into the
+ * prefill segment of plane `slot`: MaxEngine._prefill_jit (maxengine.py:400-530) with
+ * KVCache.kv_cache_prefill (kvcache.py:584-624), processed as rows of one step with causal
+ * lengths.  If `sample_last`, the last position's logits are sampled into first_token[0]
+ * (and copied to logits_out [V] fp32 when non-NULL). */
+int mtx_prefill_chunk(mtx_engine* e, const int32_t* tokens, int count, int start_pos, int slot, int sample_last,
+                      int32_t* first_token, float* logits_out, mtx_stream stream);
+
+/* ---- single fused ops (the same kernels the step uses) ------------------------------------ */
+
+/* RMSNorm (normalizations.py:57-69): out = bf16(bf16(x*rsqrt(mean(x^2)+eps)) * scale). x,out [rows,E]. */
+int mtx_rmsnorm(const void* x, const void* scale, void* out, int rows, int emb_dim, float eps, mtx_stream stream);
+
+/* DenseGeneral (linears.py:188-232): out[rows,N] = bf16(x[rows,K] . w[N,K]^T), fp32 accumulate on
+ * tcgen05 tensor cores.  x must be allocated with rows rounded up to 16/32/64/128/256 (zero
+ * padded).  splits > 1 cuts K over that many CTAs per 128-row weight tile; it needs `scratch`
+ * of mtx_linear_scratch_bytes(), zeroed once by the caller (it is left zeroed). */
+size_t mtx_linear_scratch_bytes(int rows, int n, int splits);
+int mtx_linear(const void* x, const void* w, void* out, int rows, int n, int k, int splits, void* scratch, mtx_stream stream);
+
+/* GQA decode attention over the valid rows of both cache segments: AttentionOp.__call__ in
+ * autoregressive mode (attentions.py:1399-1466: two apply_attention_dot calls merged by
+ * normalize_attention).  q,out [rows, Hq*D] bf16; k_cache/v_cache one layer [num_slots,Hkv,T,D];
+ * row i reads plane[i], its first len0[i] rows and ring_len[i] ring rows starting at ring
+ * offset ring_first[i] (ring base row P, ring length T-P).  `scratch` needs
+ * mtx_attention_scratch_bytes(); no initialisation required. */
+size_t mtx_attention_scratch_bytes(int rows, int num_kv_heads, int num_q_heads, int head_dim, int max_prefill_len,
+                                   int max_target_len);
+int mtx_decode_attention(const void* q, const void* k_cache, const void* v_cache, const int32_t* plane, const int32_t* len0,
+                         const int32_t* ring_first, const int32_t* ring_len, void* out, int rows, int num_slots,
+                         int num_q_heads, int num_kv_heads, int head_dim, int max_prefill_len, int max_target_len,
+                         float softcap, void* scratch, mtx_stream stream);
+
+/* ---- misc ---------------------------------------------------------------------------------- */
+
+const char* mtx_last_error(void);
+/* "sm_100a" build tag, so a caller can check what it loaded. */
+const char* mtx_build_info(void);
+/* Kernels launched by this library since load (all engines); used by bench.py's gpu_launches. */
+uint64_t mtx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTX_B200_H_ */

@@ -1,0 +1,345 @@
+// GQA decode attention over the valid rows of the two KV-cache segments.
+//
+// Replaces AttentionOp.__call__ in autoregressive mode (MaxText/layers/attentions.py:1399-1466):
+// two masked dot-product attentions (prefill segment, AR ring) merged by
+// normalize_attention (:1376-1397).  Mathematically that is one softmax over the rows whose
+// segment id is active; this kernel reads ONLY those rows (the reference reads every
+// allocated row and masks).
+//
+// Layout: one layer of the cache is [num_slots, Hkv, T, D] bf16 -- the sequence of a
+// (slot, kv-head) is contiguous, rows [0,P) prefill, rows [P,T) the AR ring.
+//
+// Work decomposition (split-KV): the valid rows of a (row, kv-head) are cut into 64-row
+// tiles that never straddle a segment boundary; 4 tiles = one work item = one CTA iteration
+// (one tile per warp).  A persistent grid walks a device-built work list, so ragged contexts
+// cost no empty CTAs and the launch is graph-capturable.  Each warp TMA-loads its K and V
+// tile (SWIZZLE_128B) into its own smem, computes S = Q K^T for the G query heads of the
+// group at once (so K/V are read once per group), an fp32 softmax with quad shuffles, and
+// O = P V.  Warps merge in smem; items merge through an L2 workspace, the last CTA to
+// arrive for a (row, kv-head) writing the bf16 result.
+#pragma once
+
+#include "common.cuh"
+
+namespace mtx {
+
+constexpr int kAttnThreads = 128;
+constexpr int kAttnTileRows = 64;   // kv rows per warp tile
+constexpr int kAttnWarps = 4;       // tiles per work item
+
+struct AttnParams {
+  const bf16* q;          // [rows, Hq*D]
+  bf16* out;              // [rows, Hq*D]
+  const int* plane;       // [rows]
+  const int* len0;        // [rows] valid rows of the prefill segment
+  const int* ring_first;  // [rows] ring offset of the first valid AR row
+  const int* ring_len;    // [rows] number of valid AR rows
+  const int* work_items;  // [work_count] (row << 16) | chunk
+  const int* work_count;  // [1]
+  float* part_o;          // [rows, Hkv, max_chunks, G, D]
+  float* part_ml;         // [rows, Hkv, max_chunks, G, 2]
+  int* tickets;           // [rows, Hkv], zero between launches
+  int rows, hq, hkv, P, T, max_chunks;
+  int plane_base;         // layer * num_slots (row coordinate base in the cache tensor map)
+  float softcap;
+};
+
+struct TileLoc { int p0, cnt; };
+
+__host__ __device__ inline int attn_num_tiles(int len0, int ring_first, int ring_len, int R) {
+  const int a = ring_len < R - ring_first ? ring_len : R - ring_first;
+  const int b = ring_len - a;
+  return (len0 + 63) / 64 + (a + 63) / 64 + (b + 63) / 64;
+}
+
+__host__ __device__ inline int attn_max_chunks(int P, int T) {
+  const int R = T - P;
+  return ((P + 63) / 64 + (R + 63) / 64 + 1 + kAttnWarps - 1) / kAttnWarps;
+}
+
+// Physical start row and valid count of 64-row tile t of a row's valid sequence.
+__device__ __forceinline__ TileLoc attn_tile(int t, int len0, int ring_first, int ring_len, int P, int R) {
+  const int a = min(ring_len, R - ring_first);
+  const int b = ring_len - a;
+  const int n0 = (len0 + 63) >> 6, na = (a + 63) >> 6, nb = (b + 63) >> 6;
+  TileLoc loc;
+  loc.cnt = 0;
+  loc.p0 = 0;
+  if (t < n0) {
+    loc.p0 = t * 64;
+    loc.cnt = min(64, len0 - t * 64);
+  } else if (t < n0 + na) {
+    const int u = t - n0;
+    loc.p0 = P + ring_first + u * 64;
+    loc.cnt = min(64, a - u * 64);
+  } else if (t < n0 + na + nb) {
+    const int u = t - n0 - na;
+    loc.p0 = P + u * 64;
+    loc.cnt = min(64, b - u * 64);
+  }
+  return loc;
+}
+
+// One block: per-row chunk counts -> prefix sum -> (row, chunk) list.
+__global__ void attn_build_worklist_kernel(const int* len0, const int* ring_first, const int* ring_len, int rows, int P, int T,
+                                           int* work_items, int* work_count) {
+  __shared__ int s_off[257];
+  griddep_launch_dependents();
+  griddep_wait();
+  const int R = T - P;
+  const int tid = threadIdx.x;
+  int chunks = 0;
+  if (tid < rows) chunks = (attn_num_tiles(len0[tid], ring_first[tid], ring_len[tid], R) + kAttnWarps - 1) / kAttnWarps;
+  s_off[tid + 1] = chunks;
+  if (tid == 0) s_off[0] = 0;
+  __syncthreads();
+  if (tid == 0)
+    for (int i = 1; i <= 256; ++i) s_off[i] += s_off[i - 1];
+  __syncthreads();
+  if (tid < rows) {
+    const int base = s_off[tid];
+    for (int c = 0; c < chunks; ++c) work_items[base + c] = (tid << 16) | c;
+  }
+  if (tid == 0) *work_count = s_off[rows];
+}
+
+template <int D>
+__global__ void __launch_bounds__(kAttnThreads)
+decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
+  constexpr int kSub = D / 64;                 // 64-wide (128-byte) sub-tiles per row
+  constexpr int kTileBytes = 64 * D * 2;       // one warp's K (or V) tile
+  constexpr float kLog2e = 1.4426950408889634f;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // [warp][K tile | V tile], then barriers and merge statistics
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAttnWarps * 2 * kTileBytes);
+  float* sm_m = reinterpret_cast<float*>(bars + 2 * kAttnWarps);  // [4][16]
+  float* sm_l = sm_m + kAttnWarps * 16;                            // [4][16]
+  __shared__ int s_last;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gid = lane >> 2, tid4 = lane & 3;
+  const int G = p.hq / p.hkv;
+  const int R = p.T - p.P;
+  uint8_t* k_tile = smem + warp * 2 * kTileBytes;
+  uint8_t* v_tile = k_tile + kTileBytes;
+  uint64_t* bar_k = bars + 2 * warp;
+  uint64_t* bar_v = bar_k + 1;
+
+  griddep_launch_dependents();
+  if (lane == 0) {
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  __syncthreads();
+  griddep_wait();
+
+  const int n_items = *p.work_count * p.hkv;
+  uint32_t phase = 0;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int packed = p.work_items[item / p.hkv];
+    const int h = item % p.hkv;
+    const int r = packed >> 16, chunk = packed & 0xffff;
+    const int len0 = p.len0[r], rf = p.ring_first[r], rl = p.ring_len[r];
+    const int n_chunks = (attn_num_tiles(len0, rf, rl, R) + kAttnWarps - 1) / kAttnWarps;
+    const TileLoc loc = attn_tile(chunk * kAttnWarps + warp, len0, rf, rl, p.P, R);
+    const bool active = loc.cnt > 0;
+
+    if (active && lane == 0) {
+      fence_proxy_async();  // order the previous iteration's generic reads before the async writes
+      const int row0 = ((p.plane_base + p.plane[r]) * p.hkv + h) * p.T + loc.p0;
+      mbar_expect_tx(bar_k, kTileBytes);
+#pragma unroll
+      for (int s = 0; s < kSub; ++s) tma_load_2d(k_tile + s * 8192, &tm_k, s * 64, row0, bar_k, kEvictFirst);
+      mbar_expect_tx(bar_v, kTileBytes);
+#pragma unroll
+      for (int s = 0; s < kSub; ++s) tma_load_2d(v_tile + s * 8192, &tm_v, s * 64, row0, bar_v, kEvictFirst);
+    }
+
+    // Q fragments (A operand, rows = query heads of the group, zero-padded to 16)
+    uint32_t qf[D / 16][4];
+    {
+      const bf16* qrow = p.q + (long long)r * p.hq * D + (long long)h * G * D;
+#pragma unroll
+      for (int t = 0; t < D / 16; ++t) {
+        const int d = t * 16 + tid4 * 2;
+        qf[t][0] = gid < G ? *reinterpret_cast<const uint32_t*>(qrow + gid * D + d) : 0u;
+        qf[t][1] = gid + 8 < G ? *reinterpret_cast<const uint32_t*>(qrow + (gid + 8) * D + d) : 0u;
+        qf[t][2] = gid < G ? *reinterpret_cast<const uint32_t*>(qrow + gid * D + d + 8) : 0u;
+        qf[t][3] = gid + 8 < G ? *reinterpret_cast<const uint32_t*>(qrow + (gid + 8) * D + d + 8) : 0u;
+      }
+    }
+
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+    float o[D / 8][4];
+#pragma unroll
+    for (int j = 0; j < D / 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.0f;
+
+    if (active) {
+      // ---- S = Q K^T over the 64 rows of the tile ----
+      float s[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
+      mbar_wait(bar_k, phase);
+      const uint32_t kb = smem_u32(k_tile);
+      const int mtx_i = lane >> 3, lrow = lane & 7;
+#pragma unroll
+      for (int t = 0; t < D / 16; ++t) {
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+          const int row = 8 * (2 * jp + (mtx_i >> 1)) + lrow;
+          const int c = 2 * t + (mtx_i & 1);
+          const uint32_t addr = kb + (c >> 3) * 8192 + row * 128 + (((c & 7) ^ (row & 7)) << 4);
+          uint32_t b00, b01, b10, b11;
+          ldmatrix_x4(addr, b00, b01, b10, b11);
+          mma_m16n8k16_bf16(s[2 * jp], qf[t], b00, b01);
+          mma_m16n8k16_bf16(s[2 * jp + 1], qf[t], b10, b11);
+        }
+      }
+      // ---- mask + softmax statistics (rows gid and gid+8 of the 16-row fragment) ----
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = 8 * j + tid4 * 2 + (e & 1);
+          float x = s[j][e];
+          if (p.softcap != 0.0f) x = tanhf(x / p.softcap) * p.softcap;
+          s[j][e] = col < loc.cnt ? x : -INFINITY;
+        }
+        m0 = fmaxf(m0, fmaxf(s[j][0], s[j][1]));
+        m1 = fmaxf(m1, fmaxf(s[j][2], s[j][3]));
+      }
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      uint32_t pa[4][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p0 = exp2f((s[j][0] - m0) * kLog2e), p1 = exp2f((s[j][1] - m0) * kLog2e);
+        const float p2 = exp2f((s[j][2] - m1) * kLog2e), p3 = exp2f((s[j][3] - m1) * kLog2e);
+        l0 += p0 + p1;
+        l1 += p2 + p3;
+        // probabilities are cast to the value dtype before the PV product
+        // (kernels/ragged_attention.py:156 `unnormalized.astype(v.dtype)`)
+        pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+        pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      }
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+
+      // ---- O = P V ----
+      mbar_wait(bar_v, phase);
+      if (loc.cnt < 64) {  // rows past the valid count may hold anything: zero them (0 * NaN != 0)
+        const int nvec = (64 - loc.cnt) * 8;
+        for (int i = lane; i < nvec * kSub; i += 32) {
+          const int sub = i / nvec, w = i % nvec;
+          *reinterpret_cast<uint4*>(v_tile + sub * 8192 + (loc.cnt + w / 8) * 128 + (w & 7) * 16) = make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();
+      }
+      const uint32_t vb = smem_u32(v_tile);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int jp = 0; jp < D / 16; ++jp) {
+          const int row = 16 * u + 8 * (mtx_i & 1) + lrow;
+          const int c = 2 * jp + (mtx_i >> 1);
+          const uint32_t addr = vb + (c >> 3) * 8192 + row * 128 + (((c & 7) ^ (row & 7)) << 4);
+          uint32_t b00, b01, b10, b11;
+          ldmatrix_x4_trans(addr, b00, b01, b10, b11);
+          mma_m16n8k16_bf16(o[2 * jp], pa[u], b00, b01);
+          mma_m16n8k16_bf16(o[2 * jp + 1], pa[u], b10, b11);
+        }
+      }
+      phase ^= 1;
+    }
+
+    // ---- merge the four warps of the item in shared memory ----
+    __syncwarp();
+    float* sm_o = reinterpret_cast<float*>(k_tile);  // [16][D] fp32, reuses this warp's K tile
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < D / 8; ++j) {
+        const int d = 8 * j + tid4 * 2;
+        if (gid < G) *reinterpret_cast<float2*>(sm_o + gid * D + d) = make_float2(o[j][0], o[j][1]);
+        if (gid + 8 < G) *reinterpret_cast<float2*>(sm_o + (gid + 8) * D + d) = make_float2(o[j][2], o[j][3]);
+      }
+    }
+    if (tid4 == 0) {
+      sm_m[warp * 16 + gid] = m0;
+      sm_m[warp * 16 + gid + 8] = m1;
+      sm_l[warp * 16 + gid] = l0;
+      sm_l[warp * 16 + gid + 8] = l1;
+    }
+    __syncthreads();
+
+    const long long out_base = (long long)r * p.hq * D + (long long)h * G * D;
+    const long long part_base = ((long long)(r * p.hkv + h) * p.max_chunks + chunk) * G;
+    for (int e = threadIdx.x; e < G * D; e += kAttnThreads) {
+      const int g = e / D, d = e - g * D;
+      float M = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < kAttnWarps; ++w) M = fmaxf(M, sm_m[w * 16 + g]);
+      float L = 0.0f, O = 0.0f;
+#pragma unroll
+      for (int w = 0; w < kAttnWarps; ++w) {
+        const float mw = sm_m[w * 16 + g];
+        if (mw > -INFINITY) {
+          const float sc = exp2f((mw - M) * kLog2e);
+          L += sm_l[w * 16 + g] * sc;
+          O += reinterpret_cast<const float*>(smem + w * 2 * kTileBytes)[g * D + d] * sc;
+        }
+      }
+      if (n_chunks == 1) {
+        p.out[out_base + e] = __float2bfloat16_rn(O / L);
+      } else {
+        __stcg(p.part_o + (part_base + g) * D + d, O);
+        if (d == 0) {
+          __stcg(p.part_ml + (part_base + g) * 2, M);
+          __stcg(p.part_ml + (part_base + g) * 2 + 1, L);
+        }
+      }
+    }
+    if (n_chunks > 1) {
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int old = atomicAdd(p.tickets + r * p.hkv + h, 1);
+        const int last = old == n_chunks - 1;
+        if (last) p.tickets[r * p.hkv + h] = 0;
+        s_last = last;
+      }
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        const long long pb = (long long)(r * p.hkv + h) * p.max_chunks * G;
+        for (int e = threadIdx.x; e < G * D; e += kAttnThreads) {
+          const int g = e / D, d = e - g * D;
+          float M = -INFINITY;
+          for (int c = 0; c < n_chunks; ++c) M = fmaxf(M, __ldcg(p.part_ml + (pb + c * G + g) * 2));
+          float L = 0.0f, O = 0.0f;
+          for (int c = 0; c < n_chunks; ++c) {
+            const float sc = exp2f((__ldcg(p.part_ml + (pb + c * G + g) * 2) - M) * kLog2e);
+            L += __ldcg(p.part_ml + (pb + c * G + g) * 2 + 1) * sc;
+            O += __ldcg(p.part_o + (pb + c * G + g) * D + d) * sc;
+          }
+          p.out[out_base + e] = __float2bfloat16_rn(O / L);
+        }
+      }
+    }
+    fence_proxy_async();  // this thread's generic smem accesses precede the next item's TMA writes
+    __syncthreads();
+  }
+}
+
+__host__ inline size_t attn_smem_bytes(int D) { return 1024 + size_t(kAttnWarps) * 2 * (64 * D * 2) + 2 * kAttnWarps * 8 + 2 * kAttnWarps * 16 * 4 + 16; }
+
+}  // namespace mtx

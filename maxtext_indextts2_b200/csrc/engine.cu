@@ -1,0 +1,742 @@
+// C ABI of the decode step (include/mtx_b200.h): engine object, TMA descriptors, kernel
+// launch plumbing (programmatic dependent launch, CUDA graphs).  Host code only; the kernels
+// live in the .cuh files next to this one.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mtx_b200.h"
+#include "attention.cuh"
+#include "gemm_umma.cuh"
+#include "step_kernels.cuh"
+
+using namespace mtx;
+
+#define MTX_STR2(x) #x
+#define MTX_STR(x) MTX_STR2(x)
+
+namespace {
+
+thread_local std::string g_error;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+
+#define MTX_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t err__ = (expr);                                                                 \
+    if (err__ != cudaSuccess) return fail(MTX_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(err__)); \
+  } while (0)
+
+#define MTX_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != MTX_OK) return rc__; \
+  } while (0)
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// ---- TMA descriptors ---------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 matrix [outer, inner] (inner contiguous), box [box_outer, 64] with the 128-byte swizzle.
+int make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint32_t box_outer) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return fail(MTX_ERR_CUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (inner * 2) % 16 != 0)
+    return fail(MTX_ERR_ARG, "TMA needs a 16-byte aligned base and row pitch");
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {inner * 2};
+  const cuuint32_t box[2] = {64, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return fail(MTX_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", int(rc));
+  return MTX_OK;
+}
+
+// ---- launch helper -------------------------------------------------------------------------
+
+bool use_pdl() {
+  static int v = env_int("MTX_PDL", 1);
+  return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+int launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  MTX_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return MTX_OK;
+}
+
+int round_rows(int rows) {
+  int t = 16;
+  while (t < rows) t *= 2;
+  return t;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct GemmPlan {
+  int n_tiles, splits, stages;
+  size_t smem;
+};
+
+GemmPlan plan_gemm(int n, int k, int r_tile, int num_sms, int forced_splits = 0) {
+  GemmPlan g;
+  g.n_tiles = (n + kTileN - 1) / kTileN;
+  const int kb = k / kBlockK;
+  int splits = forced_splits;
+  if (splits <= 0) {
+    const int target = env_int("MTX_GEMM_TARGET_CTAS", num_sms);
+    splits = target / g.n_tiles;
+  }
+  if (splits < 1) splits = 1;
+  if (splits > kb) splits = kb;
+  g.splits = splits;
+  const int stage_bytes = kWTileBytes + r_tile * kBlockK * 2;
+  const int budget = (r_tile <= 128 ? 100 : 200) * 1024;
+  int stages = budget / stage_bytes;
+  const int max_kb = (kb + splits - 1) / splits;
+  if (stages > max_kb) stages = max_kb;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 1) stages = 1;
+  g.stages = stages;
+  g.smem = gemm_smem_bytes(stages, r_tile);
+  return g;
+}
+
+template <int EPI>
+int launch_gemm(const CUtensorMap& tw, const CUtensorMap& tx, GemmParams p, const EpiArgs& e, const GemmPlan& g, cudaStream_t st) {
+  static bool attr_set = false;  // per template instance
+  if (!attr_set) {
+    MTX_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  p.splits = g.splits;
+  p.stages = g.stages;
+  return launch(gemm_umma_kernel<EPI>, dim3(g.n_tiles, g.splits), dim3(kGemmThreads), g.smem, st, tw, tx, p, e);
+}
+
+struct XMaps {
+  bool built = false;
+  CUtensorMap n, attn, act;
+};
+
+int log2_tile(int r_tile) {
+  int i = 0;
+  while ((16 << i) < r_tile) ++i;
+  return i;
+}
+
+}  // namespace
+
+// =============================================================================================
+
+struct mtx_engine {
+  mtx_model_config cfg;
+  int num_sms = 148;
+  int max_r_tile = 16;
+  int qkv_n = 0;
+  int attn_max_chunks = 0;
+  bool bound = false;
+  mtx_weights w{};
+  mtx_decode_state s{};
+  // workspace carve-up
+  size_t ws_bytes = 0;
+  bf16 *x = nullptr, *h = nullptr, *n = nullptr, *q = nullptr, *attn = nullptr, *act = nullptr;
+  float* gemm_ws = nullptr;
+  int* gemm_tickets = nullptr;
+  float *attn_part_o = nullptr, *attn_part_ml = nullptr;
+  int* attn_tickets = nullptr;
+  RowDesc rd{};
+  float* rope_timescale = nullptr;
+  float *part_score = nullptr, *part_raw = nullptr, *part_max = nullptr, *part_sum = nullptr;
+  int* part_idx = nullptr;
+  std::vector<float> rope_timescale_host;
+  // descriptors
+  std::vector<CUtensorMap> tm_wqkv, tm_wo, tm_w01, tm_wout;
+  CUtensorMap tm_logits, tm_k, tm_v;
+  XMaps xmaps[5];
+  // sampling
+  int strategy = MTX_SAMPLE_GREEDY, top_k = 0;
+  float nucleus_p = 0.f, temperature = 1.f;
+  // graphs
+  cudaStream_t cap_stream = nullptr;
+  std::map<int, cudaGraphExec_t> graphs;
+};
+
+namespace {
+
+struct WsLayout {
+  size_t x, h, n, q, attn, act, gemm_ws, gemm_tickets, attn_part_o, attn_part_ml, attn_tickets;
+  size_t token, pos, plane, write_row, len0, ring_first, ring_len, rope_cs, work_items, work_count, rope_timescale;
+  size_t part_score, part_idx, part_raw, part_max, part_sum;
+  size_t total;
+};
+
+WsLayout layout_workspace(const mtx_engine* e) {
+  const mtx_model_config& c = e->cfg;
+  const size_t rt = e->max_r_tile;
+  WsLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = off;
+    off = align_up(off + bytes, 1024);
+    return at;
+  };
+  const int G = c.num_q_heads / c.num_kv_heads;
+  L.x = take(rt * c.emb_dim * 2);
+  L.h = take(rt * c.emb_dim * 2);
+  L.n = take(rt * c.emb_dim * 2);
+  L.q = take(rt * c.num_q_heads * c.head_dim * 2);
+  L.attn = take(rt * c.num_q_heads * c.head_dim * 2);
+  L.act = take(rt * c.mlp_dim * 2);
+  // split-K partials: splits * n_tiles <= max(num_sms, n_tiles) tiles of [r_tile][128] fp32 for split GEMMs
+  const size_t max_split_tiles = size_t(e->num_sms) * 2 + 64;
+  L.gemm_ws = take(max_split_tiles * rt * kTileN * 4);
+  L.gemm_tickets = take(4096 * 4);
+  L.attn_part_o = take(size_t(c.max_rows) * c.num_kv_heads * e->attn_max_chunks * G * c.head_dim * 4);
+  L.attn_part_ml = take(size_t(c.max_rows) * c.num_kv_heads * e->attn_max_chunks * G * 2 * 4);
+  L.attn_tickets = take(size_t(c.max_rows) * c.num_kv_heads * 4);
+  L.token = take(rt * 4);
+  L.pos = take(rt * 4);
+  L.plane = take(rt * 4);
+  L.write_row = take(rt * 4);
+  L.len0 = take(rt * 4);
+  L.ring_first = take(rt * 4);
+  L.ring_len = take(rt * 4);
+  L.rope_cs = take(rt * (c.head_dim / 2) * 8);
+  L.work_items = take(size_t(c.max_rows) * e->attn_max_chunks * 4);
+  L.work_count = take(4);
+  L.rope_timescale = take((c.head_dim / 2) * 4);
+  const size_t vt = (c.vocab_size + kTileN - 1) / kTileN;
+  L.part_score = take(size_t(c.max_rows) * vt * 4);
+  L.part_idx = take(size_t(c.max_rows) * vt * 4);
+  L.part_raw = take(size_t(c.max_rows) * vt * 4);
+  L.part_max = take(size_t(c.max_rows) * vt * 4);
+  L.part_sum = take(size_t(c.max_rows) * vt * 4);
+  L.total = off;
+  return L;
+}
+
+int get_xmaps(mtx_engine* e, int r_tile, XMaps** out) {
+  XMaps& m = e->xmaps[log2_tile(r_tile)];
+  if (!m.built) {
+    const mtx_model_config& c = e->cfg;
+    MTX_TRY(make_map(&m.n, e->n, c.emb_dim, e->max_r_tile, r_tile));
+    MTX_TRY(make_map(&m.attn, e->attn, uint64_t(c.num_q_heads) * c.head_dim, e->max_r_tile, r_tile));
+    MTX_TRY(make_map(&m.act, e->act, c.mlp_dim, e->max_r_tile, r_tile));
+    m.built = true;
+  }
+  *out = &m;
+  return MTX_OK;
+}
+
+int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st) {
+  const mtx_model_config& c = e->cfg;
+  AttnParams p;
+  p.q = e->q;
+  p.out = e->attn;
+  p.plane = e->rd.plane;
+  p.len0 = e->rd.len0;
+  p.ring_first = e->rd.ring_first;
+  p.ring_len = e->rd.ring_len;
+  p.work_items = e->rd.work_items;
+  p.work_count = e->rd.work_count;
+  p.part_o = e->attn_part_o;
+  p.part_ml = e->attn_part_ml;
+  p.tickets = e->attn_tickets;
+  p.rows = rows;
+  p.hq = c.num_q_heads;
+  p.hkv = c.num_kv_heads;
+  p.P = c.max_prefill_len;
+  p.T = c.max_target_len;
+  p.max_chunks = e->attn_max_chunks;
+  p.plane_base = layer * c.num_slots;
+  p.softcap = c.attn_softcap;
+  const size_t smem = attn_smem_bytes(c.head_dim);
+  const int ctas_per_sm = c.head_dim == 64 ? 3 : 1;
+  int grid = rows * c.num_kv_heads * e->attn_max_chunks;
+  const int cap = e->num_sms * ctas_per_sm;
+  if (grid > cap) grid = cap;
+  if (c.head_dim == 64) return launch(decode_attn_kernel<64>, dim3(grid), dim3(kAttnThreads), smem, st, e->tm_k, e->tm_v, p);
+  return launch(decode_attn_kernel<128>, dim3(grid), dim3(kAttnThreads), smem, st, e->tm_k, e->tm_v, p);
+}
+
+// The kernels of one step, in stream order.  mode 0 = decode, 1 = prefill chunk.
+int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens, int start_pos, int slot, int want_logits,
+                 int32_t* first_token, float* prefill_logits, cudaStream_t st) {
+  const mtx_model_config& c = e->cfg;
+  const int r_tile = round_rows(rows);
+  XMaps* xm;
+  MTX_TRY(get_xmaps(e, r_tile, &xm));
+  const int E = c.emb_dim, HD = c.num_q_heads * c.head_dim, M = c.mlp_dim, L = c.num_layers;
+  const size_t kv_layer = size_t(c.num_slots) * c.num_kv_heads * c.max_target_len * c.head_dim;
+
+  PrepareArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  pa.tokens = e->s.tokens;
+  pa.next_pos = e->s.next_pos;
+  pa.prefill_len = e->s.prefill_len;
+  pa.ar_lengths = e->s.ar_lengths;
+  pa.ar_index = e->s.ar_index;
+  pa.chunk_tokens = chunk_tokens;
+  pa.start_pos = start_pos;
+  pa.slot = slot;
+  pa.mode = mode;
+  pa.rows = rows;
+  pa.P = c.max_prefill_len;
+  pa.T = c.max_target_len;
+  pa.D = c.head_dim;
+  pa.rope_timescale = e->rope_timescale;
+  MTX_TRY(launch(prepare_rows_kernel, dim3(1), dim3(256), 0, st, pa, e->rd));
+
+  const bf16* attn_norm = static_cast<const bf16*>(e->w.attn_norm);
+  const bf16* mlp_norm = static_cast<const bf16*>(e->w.mlp_norm);
+  MTX_TRY(launch(rmsnorm_kernel<true>, dim3(rows), dim3(128), 0, st, (const bf16*)nullptr, (const int*)e->rd.token,
+                 static_cast<const bf16*>(e->w.embedding), attn_norm, e->x, e->n, E, c.rms_eps));
+
+  GemmParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.rows = rows;
+  gp.r_tile = r_tile;
+  gp.ws = e->gemm_ws;
+  gp.tickets = e->gemm_tickets;
+  const GemmPlan plan_qkv = plan_gemm(e->qkv_n, E, r_tile, e->num_sms);
+  const GemmPlan plan_o = plan_gemm(E, HD, r_tile, e->num_sms);
+  const GemmPlan plan_up = plan_gemm(2 * M, E, r_tile, e->num_sms);
+  const GemmPlan plan_down = plan_gemm(E, M, r_tile, e->num_sms);
+  const GemmPlan plan_logits = plan_gemm(c.vocab_size, E, r_tile, e->num_sms, 1);
+
+  for (int l = 0; l < L; ++l) {
+    EpiArgs ea;
+    memset(&ea, 0, sizeof(ea));
+    ea.q_out = e->q;
+    ea.k_cache = static_cast<bf16*>(e->s.k_cache) + kv_layer * l;
+    ea.v_cache = static_cast<bf16*>(e->s.v_cache) + kv_layer * l;
+    ea.plane = e->rd.plane;
+    ea.write_row = e->rd.write_row;
+    ea.rope_cs = e->rd.rope_cs;
+    ea.hq = c.num_q_heads;
+    ea.hkv = c.num_kv_heads;
+    ea.d = c.head_dim;
+    ea.t_alloc = c.max_target_len;
+    gp.n = e->qkv_n;
+    gp.k = E;
+    MTX_TRY(launch_gemm<EPI_QKV_ROPE>(e->tm_wqkv[l], xm->n, gp, ea, plan_qkv, st));
+
+    MTX_TRY(launch_attention(e, l, rows, st));
+
+    memset(&ea, 0, sizeof(ea));
+    ea.out = e->h;
+    ea.resid = e->x;
+    ea.ld_out = E;
+    gp.n = E;
+    gp.k = HD;
+    MTX_TRY(launch_gemm<EPI_RESIDUAL>(e->tm_wo[l], xm->attn, gp, ea, plan_o, st));
+
+    MTX_TRY(launch(rmsnorm_kernel<false>, dim3(rows), dim3(128), 0, st, (const bf16*)e->h, (const int*)nullptr,
+                   (const bf16*)nullptr, mlp_norm + size_t(l) * E, (bf16*)nullptr, e->n, E, c.rms_eps));
+
+    memset(&ea, 0, sizeof(ea));
+    ea.out = e->act;
+    ea.ld_out = M;
+    gp.n = 2 * M;
+    gp.k = E;
+    MTX_TRY(launch_gemm<EPI_SWIGLU>(e->tm_w01[l], xm->n, gp, ea, plan_up, st));
+
+    memset(&ea, 0, sizeof(ea));
+    ea.out = e->x;
+    ea.resid = e->h;
+    ea.ld_out = E;
+    gp.n = E;
+    gp.k = M;
+    MTX_TRY(launch_gemm<EPI_RESIDUAL>(e->tm_wout[l], xm->act, gp, ea, plan_down, st));
+
+    const bf16* next_scale = l + 1 < L ? attn_norm + size_t(l + 1) * E : static_cast<const bf16*>(e->w.final_norm);
+    if (l + 1 < L || want_logits)
+      MTX_TRY(launch(rmsnorm_kernel<false>, dim3(rows), dim3(128), 0, st, (const bf16*)e->x, (const int*)nullptr,
+                     (const bf16*)nullptr, next_scale, (bf16*)nullptr, e->n, E, c.rms_eps));
+  }
+
+  if (want_logits) {
+    if (e->strategy == MTX_SAMPLE_NUCLEUS || e->strategy == MTX_SAMPLE_TOPK)
+      return fail(MTX_ERR_UNSUPPORTED, "nucleus / topk sampling are not fused yet: use the host sampler on materialised logits");
+    EpiArgs ea;
+    memset(&ea, 0, sizeof(ea));
+    ea.logits_out = mode == 0 ? e->s.logits : prefill_logits;
+    ea.ld_logits = c.vocab_size;
+    ea.logits_only_row = mode == 0 ? -1 : rows - 1;
+    ea.part_score = e->part_score;
+    ea.part_idx = e->part_idx;
+    ea.part_raw = e->part_raw;
+    ea.part_max = e->part_max;
+    ea.part_sum = e->part_sum;
+    ea.n_tiles = plan_logits.n_tiles;
+    ea.vocab_offset = c.vocab_offset;
+    ea.scale = c.logits_scale;
+    ea.softcap = c.final_softcap;
+    ea.inv_temp = 1.0f / e->temperature;
+    ea.round_bf16 = c.logits_round_bf16;
+    ea.gumbel = e->strategy == MTX_SAMPLE_WEIGHTED ? 1 : 0;
+    ea.rng_state = e->s.rng_state;
+    ea.row_offset = 0;
+    gp.n = c.vocab_size;
+    gp.k = E;
+    MTX_TRY(launch_gemm<EPI_LOGITS>(e->tm_logits, xm->n, gp, ea, plan_logits, st));
+
+    FinalizeArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.part_score = e->part_score;
+    fa.part_idx = e->part_idx;
+    fa.part_raw = e->part_raw;
+    fa.part_max = e->part_max;
+    fa.part_sum = e->part_sum;
+    fa.n_tiles = plan_logits.n_tiles;
+    fa.rows = rows;
+    fa.mode = mode;
+    fa.tokens = e->s.tokens;
+    fa.next_pos = e->s.next_pos;
+    fa.generated = e->s.generated;
+    fa.ar_lengths = e->s.ar_lengths;
+    fa.ar_index = e->s.ar_index;
+    fa.result = e->s.result;
+    fa.log_prob = e->s.log_prob;
+    fa.rng_state = e->s.rng_state;
+    fa.num_slots = c.num_slots;
+    fa.R = c.max_target_len - c.max_prefill_len;
+    fa.first_token = first_token;
+    MTX_TRY(launch(finalize_kernel, dim3(rows), dim3(128), 0, st, fa));
+  }
+  return MTX_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+
+extern "C" {
+
+const char* mtx_last_error(void) { return g_error.c_str(); }
+const char* mtx_build_info(void) { return "mtx_b200 sm_100a (tcgen05 + TMA + mbarrier), CUDA " MTX_STR(CUDART_VERSION); }
+uint64_t mtx_launch_count(void) { return g_launches.load(); }
+
+int mtx_engine_create(const mtx_model_config* cfg, mtx_engine** out) {
+  if (cfg == nullptr || out == nullptr) return fail(MTX_ERR_ARG, "null argument");
+  const mtx_model_config& c = *cfg;
+  if (c.head_dim != 64 && c.head_dim != 128) return fail(MTX_ERR_UNSUPPORTED, "head_dim %d: only 64 and 128", c.head_dim);
+  if (c.num_q_heads % c.num_kv_heads != 0 || c.num_q_heads / c.num_kv_heads > 16)
+    return fail(MTX_ERR_UNSUPPORTED, "query heads per kv head must divide evenly and be <= 16");
+  if (c.emb_dim % 64 != 0 || c.mlp_dim % 64 != 0 || (c.num_q_heads * c.head_dim) % 64 != 0)
+    return fail(MTX_ERR_UNSUPPORTED, "emb_dim, mlp_dim and Hq*D must be multiples of 64");
+  if (c.mlp_dim % 16 != 0) return fail(MTX_ERR_UNSUPPORTED, "mlp_dim must be a multiple of 16");
+  if (c.max_rows < 1 || c.max_rows > 256) return fail(MTX_ERR_ARG, "max_rows must be in [1, 256]");
+  if (c.max_target_len <= c.max_prefill_len) return fail(MTX_ERR_ARG, "max_target_len must exceed max_prefill_len");
+  if (c.num_layers < 1 || c.vocab_size < 1 || c.num_slots < 1) return fail(MTX_ERR_ARG, "bad layer / vocab / slot count");
+  mtx_engine* e = new mtx_engine();
+  e->cfg = c;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+    e->num_sms = sms;
+  cudaGetLastError();
+  e->max_r_tile = round_rows(c.max_rows);
+  e->qkv_n = (c.num_q_heads + 2 * c.num_kv_heads) * c.head_dim;
+  e->attn_max_chunks = attn_max_chunks(c.max_prefill_len, c.max_target_len);
+  e->rope_timescale_host.resize(c.head_dim / 2);
+  for (int i = 0; i < c.head_dim / 2; ++i) {
+    // embeddings.py:270-275, evaluated in fp64 and rounded once
+    const double fraction = 2.0 * double(i) / double(c.head_dim);
+    e->rope_timescale_host[i] = float(double(c.rope_min_timescale) * pow(double(c.rope_max_timescale) / double(c.rope_min_timescale), fraction));
+  }
+  e->ws_bytes = layout_workspace(e).total;
+  *out = e;
+  return MTX_OK;
+}
+
+int mtx_engine_destroy(mtx_engine* e) {
+  if (e == nullptr) return MTX_OK;
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  delete e;
+  return MTX_OK;
+}
+
+size_t mtx_engine_workspace_bytes(const mtx_engine* e) { return e ? e->ws_bytes : 0; }
+
+int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state* s, void* workspace, size_t workspace_bytes) {
+  if (!e || !w || !s || !workspace) return fail(MTX_ERR_ARG, "null argument");
+  if (workspace_bytes < e->ws_bytes) return fail(MTX_ERR_ARG, "workspace too small: %zu < %zu", workspace_bytes, e->ws_bytes);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return fail(MTX_ERR_ARG, "workspace must be 1024-byte aligned");
+  const mtx_model_config& c = e->cfg;
+  e->w = *w;
+  e->s = *s;
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  e->graphs.clear();
+  for (auto& m : e->xmaps) m.built = false;
+  MTX_CUDA(cudaMemset(workspace, 0, e->ws_bytes));
+  const WsLayout L = layout_workspace(e);
+  uint8_t* b = static_cast<uint8_t*>(workspace);
+  e->x = reinterpret_cast<bf16*>(b + L.x);
+  e->h = reinterpret_cast<bf16*>(b + L.h);
+  e->n = reinterpret_cast<bf16*>(b + L.n);
+  e->q = reinterpret_cast<bf16*>(b + L.q);
+  e->attn = reinterpret_cast<bf16*>(b + L.attn);
+  e->act = reinterpret_cast<bf16*>(b + L.act);
+  e->gemm_ws = reinterpret_cast<float*>(b + L.gemm_ws);
+  e->gemm_tickets = reinterpret_cast<int*>(b + L.gemm_tickets);
+  e->attn_part_o = reinterpret_cast<float*>(b + L.attn_part_o);
+  e->attn_part_ml = reinterpret_cast<float*>(b + L.attn_part_ml);
+  e->attn_tickets = reinterpret_cast<int*>(b + L.attn_tickets);
+  e->rd.token = reinterpret_cast<int*>(b + L.token);
+  e->rd.pos = reinterpret_cast<int*>(b + L.pos);
+  e->rd.plane = reinterpret_cast<int*>(b + L.plane);
+  e->rd.write_row = reinterpret_cast<int*>(b + L.write_row);
+  e->rd.len0 = reinterpret_cast<int*>(b + L.len0);
+  e->rd.ring_first = reinterpret_cast<int*>(b + L.ring_first);
+  e->rd.ring_len = reinterpret_cast<int*>(b + L.ring_len);
+  e->rd.rope_cs = reinterpret_cast<float2*>(b + L.rope_cs);
+  e->rd.work_items = reinterpret_cast<int*>(b + L.work_items);
+  e->rd.work_count = reinterpret_cast<int*>(b + L.work_count);
+  e->rope_timescale = reinterpret_cast<float*>(b + L.rope_timescale);
+  e->part_score = reinterpret_cast<float*>(b + L.part_score);
+  e->part_idx = reinterpret_cast<int*>(b + L.part_idx);
+  e->part_raw = reinterpret_cast<float*>(b + L.part_raw);
+  e->part_max = reinterpret_cast<float*>(b + L.part_max);
+  e->part_sum = reinterpret_cast<float*>(b + L.part_sum);
+  MTX_CUDA(cudaMemcpy(e->rope_timescale, e->rope_timescale_host.data(), e->rope_timescale_host.size() * 4, cudaMemcpyHostToDevice));
+
+  const int E = c.emb_dim, HD = c.num_q_heads * c.head_dim, M = c.mlp_dim, L_ = c.num_layers;
+  e->tm_wqkv.resize(L_);
+  e->tm_wo.resize(L_);
+  e->tm_w01.resize(L_);
+  e->tm_wout.resize(L_);
+  for (int l = 0; l < L_; ++l) {
+    MTX_TRY(make_map(&e->tm_wqkv[l], static_cast<const bf16*>(w->wqkv) + size_t(l) * e->qkv_n * E, E, e->qkv_n, kTileN));
+    MTX_TRY(make_map(&e->tm_wo[l], static_cast<const bf16*>(w->wo) + size_t(l) * E * HD, HD, E, kTileN));
+    MTX_TRY(make_map(&e->tm_w01[l], static_cast<const bf16*>(w->w01) + size_t(l) * 2 * M * E, E, 2 * M, kTileN));
+    MTX_TRY(make_map(&e->tm_wout[l], static_cast<const bf16*>(w->wout) + size_t(l) * E * M, M, E, kTileN));
+  }
+  MTX_TRY(make_map(&e->tm_logits, w->logits, E, c.vocab_size, kTileN));
+  const uint64_t kv_rows = uint64_t(L_) * c.num_slots * c.num_kv_heads * c.max_target_len;
+  if (kv_rows >= (1ull << 31)) return fail(MTX_ERR_UNSUPPORTED, "KV cache has too many rows for one tensor map");
+  MTX_TRY(make_map(&e->tm_k, s->k_cache, c.head_dim, kv_rows, kAttnTileRows));
+  MTX_TRY(make_map(&e->tm_v, s->v_cache, c.head_dim, kv_rows, kAttnTileRows));
+  if (c.head_dim == 64)
+    MTX_CUDA(cudaFuncSetAttribute(decode_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_smem_bytes(64))));
+  else
+    MTX_CUDA(cudaFuncSetAttribute(decode_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_smem_bytes(128))));
+  e->bound = true;
+  return MTX_OK;
+}
+
+int mtx_engine_set_sampling(mtx_engine* e, int strategy, int top_k, float nucleus_p, float temperature) {
+  if (!e) return fail(MTX_ERR_ARG, "null engine");
+  if (strategy < MTX_SAMPLE_GREEDY || strategy > MTX_SAMPLE_TOPK) return fail(MTX_ERR_ARG, "Sampling algorithm=%d not supported!", strategy);
+  if (strategy == MTX_SAMPLE_TOPK && top_k <= 0) return fail(MTX_ERR_ARG, "Can't apply algorithm topk with parameter topk=%d less than or equal to zero", top_k);
+  if (strategy == MTX_SAMPLE_NUCLEUS && nucleus_p < 0) return fail(MTX_ERR_ARG, "Can't apply nucleus with parameter nucleus_topp=%f less zero", nucleus_p);
+  if (!(temperature > 0.f)) return fail(MTX_ERR_ARG, "temperature must be positive");
+  e->strategy = strategy;
+  e->top_k = top_k;
+  e->nucleus_p = nucleus_p;
+  e->temperature = temperature;
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  e->graphs.clear();
+  return MTX_OK;
+}
+
+int mtx_decode_step(mtx_engine* e, int rows, mtx_stream stream) {
+  if (!e || !e->bound) return fail(MTX_ERR_ARG, "engine is not bound");
+  if (rows < 1 || rows > e->cfg.max_rows) return fail(MTX_ERR_ARG, "rows %d outside [1, %d]", rows, e->cfg.max_rows);
+  return enqueue_step(e, 0, rows, nullptr, 0, 0, 1, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int mtx_decode_step_graph(mtx_engine* e, int rows, mtx_stream stream) {
+  if (!e || !e->bound) return fail(MTX_ERR_ARG, "engine is not bound");
+  if (rows < 1 || rows > e->cfg.max_rows) return fail(MTX_ERR_ARG, "rows %d outside [1, %d]", rows, e->cfg.max_rows);
+  auto it = e->graphs.find(rows);
+  if (it == e->graphs.end()) {
+    if (!e->cap_stream) MTX_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    MTX_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_step(e, 0, rows, nullptr, 0, 0, 1, nullptr, nullptr, e->cap_stream);
+    const cudaError_t end = cudaStreamEndCapture(e->cap_stream, &graph);
+    if (rc != MTX_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (end != cudaSuccess) return fail(MTX_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(end));
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t inst = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (inst != cudaSuccess) return fail(MTX_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(inst));
+    it = e->graphs.emplace(rows, exec).first;
+  }
+  MTX_CUDA(cudaGraphLaunch(it->second, static_cast<cudaStream_t>(stream)));
+  return MTX_OK;
+}
+
+int mtx_prefill_chunk(mtx_engine* e, const int32_t* tokens, int count, int start_pos, int slot, int sample_last,
+                      int32_t* first_token, float* logits_out, mtx_stream stream) {
+  if (!e || !e->bound) return fail(MTX_ERR_ARG, "engine is not bound");
+  if (count < 1 || count > e->cfg.max_rows) return fail(MTX_ERR_ARG, "count %d outside [1, %d]", count, e->cfg.max_rows);
+  if (start_pos < 0 || start_pos + count > e->cfg.max_prefill_len) return fail(MTX_ERR_ARG, "prompt positions exceed max_prefill_len");
+  if (slot < 0 || slot >= e->cfg.num_slots) return fail(MTX_ERR_ARG, "slot out of range");
+  if (sample_last && first_token == nullptr) return fail(MTX_ERR_ARG, "first_token is null");
+  return enqueue_step(e, 1, count, tokens, start_pos, slot, sample_last, first_token, logits_out, static_cast<cudaStream_t>(stream));
+}
+
+// ---- single ops ------------------------------------------------------------------------------
+
+int mtx_rmsnorm(const void* x, const void* scale, void* out, int rows, int emb_dim, float eps, mtx_stream stream) {
+  if (!x || !scale || !out || rows < 1 || emb_dim % 8 != 0) return fail(MTX_ERR_ARG, "bad rmsnorm arguments");
+  return launch(rmsnorm_kernel<false>, dim3(rows), dim3(128), 0, static_cast<cudaStream_t>(stream), static_cast<const bf16*>(x),
+                (const int*)nullptr, (const bf16*)nullptr, static_cast<const bf16*>(scale), (bf16*)nullptr, static_cast<bf16*>(out),
+                emb_dim, eps);
+}
+
+size_t mtx_linear_scratch_bytes(int rows, int n, int splits) {
+  const size_t n_tiles = (n + kTileN - 1) / kTileN;
+  return align_up(n_tiles * 4, 1024) + n_tiles * size_t(splits < 1 ? 1 : splits) * round_rows(rows) * kTileN * 4;
+}
+
+int mtx_linear(const void* x, const void* w, void* out, int rows, int n, int k, int splits, void* scratch, mtx_stream stream) {
+  if (!x || !w || !out || rows < 1 || rows > 256 || n < 1 || k < 64 || k % 64 != 0) return fail(MTX_ERR_ARG, "bad linear arguments");
+  if (splits > 1 && scratch == nullptr) return fail(MTX_ERR_ARG, "split-K needs scratch");
+  const int r_tile = round_rows(rows);
+  CUtensorMap tw, tx;
+  MTX_TRY(make_map(&tw, w, k, n, kTileN));
+  MTX_TRY(make_map(&tx, x, k, r_tile, r_tile));
+  const GemmPlan g = plan_gemm(n, k, r_tile, 148, splits < 1 ? 1 : splits);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = n;
+  p.k = k;
+  p.rows = rows;
+  p.r_tile = r_tile;
+  p.tickets = static_cast<int*>(scratch);
+  p.ws = scratch ? reinterpret_cast<float*>(static_cast<uint8_t*>(scratch) + align_up(size_t(g.n_tiles) * 4, 1024)) : nullptr;
+  EpiArgs e;
+  memset(&e, 0, sizeof(e));
+  e.out = static_cast<bf16*>(out);
+  e.ld_out = n;
+  return launch_gemm<EPI_STORE_BF16>(tw, tx, p, e, g, static_cast<cudaStream_t>(stream));
+}
+
+size_t mtx_attention_scratch_bytes(int rows, int num_kv_heads, int num_q_heads, int head_dim, int max_prefill_len, int max_target_len) {
+  const size_t mc = attn_max_chunks(max_prefill_len, max_target_len);
+  const size_t G = num_q_heads / num_kv_heads;
+  size_t b = 0;
+  b += align_up(size_t(rows) * mc * 4, 1024);                           // work items
+  b += 1024;                                                            // work count
+  b += align_up(size_t(rows) * num_kv_heads * 4, 1024);                 // tickets
+  b += align_up(size_t(rows) * num_kv_heads * mc * G * 2 * 4, 1024);    // (max, sum)
+  b += align_up(size_t(rows) * num_kv_heads * mc * G * head_dim * 4, 1024);
+  return b;
+}
+
+int mtx_decode_attention(const void* q, const void* k_cache, const void* v_cache, const int32_t* plane, const int32_t* len0,
+                         const int32_t* ring_first, const int32_t* ring_len, void* out, int rows, int num_slots, int num_q_heads,
+                         int num_kv_heads, int head_dim, int max_prefill_len, int max_target_len, float softcap, void* scratch,
+                         mtx_stream stream) {
+  if (!q || !k_cache || !v_cache || !plane || !len0 || !ring_first || !ring_len || !out || !scratch) return fail(MTX_ERR_ARG, "null argument");
+  if (head_dim != 64 && head_dim != 128) return fail(MTX_ERR_UNSUPPORTED, "head_dim %d: only 64 and 128", head_dim);
+  if (rows < 1 || rows > 256) return fail(MTX_ERR_ARG, "rows must be in [1, 256]");
+  if (num_q_heads % num_kv_heads != 0 || num_q_heads / num_kv_heads > 16) return fail(MTX_ERR_UNSUPPORTED, "bad head grouping");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t mc = attn_max_chunks(max_prefill_len, max_target_len);
+  const size_t G = num_q_heads / num_kv_heads;
+  uint8_t* b = static_cast<uint8_t*>(scratch);
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  int* work_items = reinterpret_cast<int*>(b);
+  b += align_up(size_t(rows) * mc * 4, 1024);
+  int* work_count = reinterpret_cast<int*>(b);
+  b += 1024;
+  p.tickets = reinterpret_cast<int*>(b);
+  const size_t ticket_bytes = align_up(size_t(rows) * num_kv_heads * 4, 1024);
+  b += ticket_bytes;
+  p.part_ml = reinterpret_cast<float*>(b);
+  b += align_up(size_t(rows) * num_kv_heads * mc * G * 2 * 4, 1024);
+  p.part_o = reinterpret_cast<float*>(b);
+  MTX_CUDA(cudaMemsetAsync(p.tickets, 0, ticket_bytes, st));
+  MTX_TRY(launch(attn_build_worklist_kernel, dim3(1), dim3(256), 0, st, (const int*)len0, (const int*)ring_first, (const int*)ring_len,
+                 rows, max_prefill_len, max_target_len, work_items, work_count));
+  CUtensorMap tk, tv;
+  const uint64_t kv_rows = uint64_t(num_slots) * num_kv_heads * max_target_len;
+  MTX_TRY(make_map(&tk, k_cache, head_dim, kv_rows, kAttnTileRows));
+  MTX_TRY(make_map(&tv, v_cache, head_dim, kv_rows, kAttnTileRows));
+  p.q = static_cast<const bf16*>(q);
+  p.out = static_cast<bf16*>(out);
+  p.plane = plane;
+  p.len0 = len0;
+  p.ring_first = ring_first;
+  p.ring_len = ring_len;
+  p.work_items = work_items;
+  p.work_count = work_count;
+  p.rows = rows;
+  p.hq = num_q_heads;
+  p.hkv = num_kv_heads;
+  p.P = max_prefill_len;
+  p.T = max_target_len;
+  p.max_chunks = int(mc);
+  p.plane_base = 0;
+  p.softcap = softcap;
+  const size_t smem = attn_smem_bytes(head_dim);
+  int grid = rows * num_kv_heads * int(mc);
+  const int cap = 148 * (head_dim == 64 ? 3 : 1);
+  if (grid > cap) grid = cap;
+  if (head_dim == 64) {
+    MTX_CUDA(cudaFuncSetAttribute(decode_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    return launch(decode_attn_kernel<64>, dim3(grid), dim3(kAttnThreads), smem, st, tk, tv, p);
+  }
+  MTX_CUDA(cudaFuncSetAttribute(decode_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  return launch(decode_attn_kernel<128>, dim3(grid), dim3(kAttnThreads), smem, st, tk, tv, p);
+}
+
+}  // extern "C"

@@ -1,0 +1,230 @@
+// Small kernels around the GEMMs and attention of one step: row descriptors, embedding
+// gather + RMSNorm, sampler finalisation and the decode-state bookkeeping.
+#pragma once
+
+#include "attention.cuh"
+#include "common.cuh"
+
+namespace mtx {
+
+// Per-row descriptors consumed by the QKV epilogue and the attention kernel.
+struct RowDesc {
+  int* token;       // [max_rows] token id fed to the embedding
+  int* pos;         // [max_rows] RoPE position
+  int* plane;       // [max_rows] KV plane
+  int* write_row;   // [max_rows] cache row the new K/V go to
+  int* len0;        // [max_rows] valid prefill rows (including a row appended there this step)
+  int* ring_first;  // [max_rows]
+  int* ring_len;    // [max_rows] valid ring rows (including the row appended this step)
+  float2* rope_cs;  // [max_rows, D/2] (cos, sin), bf16-rounded
+  int* work_items;  // attention work list
+  int* work_count;
+};
+
+struct PrepareArgs {
+  // decode (mode 0): KVCache.kv_cache_autoregressive bookkeeping, inference/kvcache.py:738-795
+  const int* tokens;       // [B] decode_state["tokens"]
+  const int* next_pos;     // [B]
+  const int* prefill_len;  // [num_slots]
+  const int* ar_lengths;   // [num_slots]
+  const int* ar_index;     // [1]
+  // prefill chunk (mode 1): maxengine.py:444-458 positions / sequence indicator
+  const int* chunk_tokens;  // [count]
+  int start_pos, slot;
+  int mode, rows, P, T, D;
+  const float* rope_timescale;  // [D/2] min * (max/min)^(2i/D), embeddings.py:270-275
+};
+
+// One block of 256 threads.  Fills the row descriptors, the RoPE table
+// (embeddings.py:304-307: sin/cos of position / timescale, cast to bf16) and the attention work list.
+__global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
+  __shared__ int s_off[257];
+  griddep_launch_dependents();
+  griddep_wait();
+  const int tid = threadIdx.x;
+  const int R = a.T - a.P;
+  int chunks = 0;
+  if (tid < a.rows) {
+    int token, pos, plane, wr, l0, rf, rl;
+    if (a.mode == 0) {
+      const int idx = a.ar_index[0];
+      token = a.tokens[tid];
+      pos = a.next_pos[tid];
+      plane = tid;
+      wr = a.P + idx;  // all rows append at the shared ring index (kvcache.py:696-701)
+      l0 = a.prefill_len[tid];
+      const int n = a.ar_lengths[tid] + 1;  // rows marked active since insert, this one included
+      rl = n < R ? n : R;
+      rf = ((idx + 1 - rl) % R + R) % R;
+    } else {
+      token = a.chunk_tokens[tid];
+      pos = a.start_pos + tid;
+      plane = a.slot;
+      wr = a.start_pos + tid;
+      l0 = a.start_pos + tid + 1;  // causal: this position and everything before it
+      rf = 0;
+      rl = 0;
+    }
+    rd.token[tid] = token;
+    rd.pos[tid] = pos;
+    rd.plane[tid] = plane;
+    rd.write_row[tid] = wr;
+    rd.len0[tid] = l0;
+    rd.ring_first[tid] = rf;
+    rd.ring_len[tid] = rl;
+    chunks = (attn_num_tiles(l0, rf, rl, R) + kAttnWarps - 1) / kAttnWarps;
+    const int half = a.D / 2;
+    for (int i = 0; i < half; ++i) {
+      const float ang = float(pos) / a.rope_timescale[i];
+      rd.rope_cs[tid * half + i] = make_float2(bf16r(cosf(ang)), bf16r(sinf(ang)));
+    }
+  }
+  s_off[tid + 1] = chunks;
+  if (tid == 0) s_off[0] = 0;
+  __syncthreads();
+  if (tid == 0)
+    for (int i = 1; i <= 256; ++i) s_off[i] += s_off[i - 1];
+  __syncthreads();
+  if (tid < a.rows) {
+    const int base = s_off[tid];
+    for (int c = 0; c < chunks; ++c) rd.work_items[base + c] = (tid << 16) | c;
+  }
+  if (tid == 0) *rd.work_count = s_off[a.rows];
+}
+
+// RMSNorm (normalizations.py:57-69), optionally fused with the embedding gather
+// (embeddings.py:154: embedding.astype(bf16)[tokens]).  One CTA per row.
+//   y   = bf16(x32 * rsqrt(mean(x32^2) + eps));  out = bf16(y * bf16(scale))
+template <bool EMBED>
+__global__ void __launch_bounds__(128)
+rmsnorm_kernel(const bf16* __restrict__ x_in, const int* __restrict__ tokens, const bf16* __restrict__ embedding,
+               const bf16* __restrict__ scale, bf16* __restrict__ x_out, bf16* __restrict__ n_out, int E, float eps) {
+  __shared__ float s_part[4];
+  griddep_launch_dependents();
+  griddep_wait();
+  const int r = blockIdx.x;
+  const bf16* src = EMBED ? embedding + (long long)tokens[r] * E : x_in + (long long)r * E;
+  const int nvec = E / 8;
+  float ss = 0.0f;
+  for (int i = threadIdx.x; i < nvec; i += 128) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(src + i * 8);
+    if (EMBED) *reinterpret_cast<uint4*>(x_out + (long long)r * E + i * 8) = raw;
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = bf16_lo(w[j]), b = bf16_hi(w[j]);
+      ss += a * a + b * b;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  const float total = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+  const float rstd = 1.0f / sqrtf(total / float(E) + eps);
+  for (int i = threadIdx.x; i < nvec; i += 128) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(src + i * 8);
+    const uint4 sc = *reinterpret_cast<const uint4*>(scale + i * 8);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    const uint32_t s[4] = {sc.x, sc.y, sc.z, sc.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float y0 = bf16r(bf16_lo(w[j]) * rstd), y1 = bf16r(bf16_hi(w[j]) * rstd);
+      o[j] = pack_bf16x2(y0 * bf16_lo(s[j]), y1 * bf16_hi(s[j]));
+    }
+    *reinterpret_cast<uint4*>(n_out + (long long)r * E + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+struct FinalizeArgs {
+  const float* part_score;  // [rows, n_tiles]
+  const int* part_idx;
+  const float* part_raw;
+  const float* part_max;
+  const float* part_sum;
+  int n_tiles, rows;
+  int mode;  // 0 = decode step: advance the state; 1 = prefill: only emit the last row's token
+  // decode state (maxengine.py:913-936)
+  int* tokens;
+  int* next_pos;
+  int* generated;
+  int* ar_lengths;
+  int* ar_index;
+  int* result;        // [rows, 3]
+  float* log_prob;    // [rows] or null
+  uint32_t* rng_state;
+  int num_slots, R;
+  // prefill
+  int* first_token;
+};
+
+// One CTA (128 threads) per row: reduce the per-tile candidates (first maximum wins, as
+// jnp.argmax), compute log-softmax of the choice (inference_utils.py:55-63), then the
+// bookkeeping of maxengine.py:913-914 and kvcache.py:778-779.
+__global__ void __launch_bounds__(128) finalize_kernel(const FinalizeArgs a) {
+  __shared__ float s_score[4], s_raw[4], s_max[4], s_sum[4];
+  __shared__ int s_idx[4];
+  griddep_launch_dependents();
+  griddep_wait();
+  const int r = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float score = -INFINITY, raw = -INFINITY, mx = -INFINITY, sum = 0.0f;
+  int idx = 0x7fffffff;
+  for (int t = threadIdx.x; t < a.n_tiles; t += 128) {
+    const long long o = (long long)r * a.n_tiles + t;
+    const float s2 = a.part_score[o];
+    const int i2 = a.part_idx[o];
+    if (s2 > score || (s2 == score && i2 < idx)) { score = s2; idx = i2; raw = a.part_raw[o]; }
+    const float m2 = a.part_max[o];
+    const float mn = fmaxf(mx, m2);
+    if (mn > -INFINITY) sum = sum * expf(mx - mn) + a.part_sum[o] * expf(m2 - mn);
+    mx = mn;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float s2 = __shfl_xor_sync(0xffffffffu, score, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+    const float r2 = __shfl_xor_sync(0xffffffffu, raw, o);
+    if (s2 > score || (s2 == score && i2 < idx)) { score = s2; idx = i2; raw = r2; }
+    const float m2 = __shfl_xor_sync(0xffffffffu, mx, o);
+    const float u2 = __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mn = fmaxf(mx, m2);
+    if (mn > -INFINITY) sum = sum * expf(mx - mn) + u2 * expf(m2 - mn);
+    mx = mn;
+  }
+  if (lane == 0) { s_score[warp] = score; s_idx[warp] = idx; s_raw[warp] = raw; s_max[warp] = mx; s_sum[warp] = sum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 4; ++w) {
+      if (s_score[w] > score || (s_score[w] == score && s_idx[w] < idx)) { score = s_score[w]; idx = s_idx[w]; raw = s_raw[w]; }
+      const float mn = fmaxf(mx, s_max[w]);
+      if (mn > -INFINITY) sum = sum * expf(mx - mn) + s_sum[w] * expf(s_max[w] - mn);
+      mx = mn;
+    }
+    const float logp = raw - (mx + logf(sum));
+    if (a.mode == 0) {
+      const int gen = a.generated[r] + 1;
+      a.tokens[r] = idx;
+      a.next_pos[r] += 1;
+      a.generated[r] = gen;
+      a.result[r * 3 + 0] = idx;
+      a.result[r * 3 + 1] = 1;
+      a.result[r * 3 + 2] = gen;
+      if (a.log_prob != nullptr) a.log_prob[r] = logp;
+    } else if (r == a.rows - 1) {
+      a.first_token[0] = idx;
+      if (a.log_prob != nullptr) a.log_prob[0] = logp;
+    }
+  }
+  if (a.mode == 0 && blockIdx.x == 0) {
+    // every slot's counter advances, occupied or not (kvcache.py:779 `.at[:].add(1)`)
+    for (int s = threadIdx.x; s < a.num_slots; s += 128) a.ar_lengths[s] += 1;
+    if (threadIdx.x == 0) {
+      a.ar_index[0] = (a.ar_index[0] + 1) % a.R;
+      a.rng_state[0] += 1;
+    }
+  }
+}
+
+}  // namespace mtx

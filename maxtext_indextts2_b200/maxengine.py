@@ -1,0 +1,497 @@
+"""MaxEngine for the B200: the reference's engine API over the sm_100a decode kernels.
+
+Mirrors ``MaxText/maxengine.py`` (class ``MaxEngine``, :100) for the decode path:
+
+=====================  ==========================================  =====================
+method                 reference                                    here
+=====================  ==========================================  =====================
+``load_params``        maxengine.py:218                             repack for K-major streaming, upload
+``init_decode_state``  maxengine.py:1370-1453                       zero the device state
+``prefill``            maxengine.py:533-574 (``_prefill_jit`` :400)  ``mtx_prefill_chunk``
+``insert``             maxengine.py:1166-1192 (``_insert_jit`` :1045)  device copies
+``bulk_insert``        maxengine.py:946                              loop over ``insert``
+``generate``           maxengine.py:838-866 (``_generate_jit`` :868)  ``mtx_decode_step[_graph]``
+=====================  ==========================================  =====================
+
+Same signatures, state-dict keys (``logits, cache, next_pos, generated_tokens, tokens``),
+``ResultTokens`` layout and config keys.  ``decode_state`` is donated exactly as in the
+reference (``donate_argnums``, maxengine.py:868): it is updated in place and the returned
+dict is the one to keep using.
+
+Device memory, streams and (for the optional vocab-parallel mode) the process group come
+from PyTorch; all arithmetic is in ``libmtx_b200.so``.  Nothing here computes on the CPU.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+import math
+from typing import Any, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import params as params_lib
+from .common_types import DECODING_ACTIVE_SEQUENCE_INDICATOR
+
+
+@dataclasses.dataclass
+class SlotData:
+  tokens: Any
+  valid: Any
+  lengths: Any
+  log_prob: Any = None
+
+
+@dataclasses.dataclass
+class ResultTokens:
+  """Same fields as JetStream's ``engine_api.ResultTokens`` (built at maxengine.py:916-928)."""
+
+  data: Any  # [B, 3] int32: token, valid, length
+  tokens_idx: tuple = (0, 1)
+  valid_idx: tuple = (1, 2)
+  length_idx: tuple = (2, 3)
+  log_prob: Any = None
+  samples_per_slot: int = 1
+
+  def copy_to_host_async(self):
+    if isinstance(self.data, torch.Tensor) and self.data.is_cuda:
+      host = torch.empty(self.data.shape, dtype=self.data.dtype, pin_memory=True)
+      host.copy_(self.data, non_blocking=True)
+      self._host = host
+
+  def convert_to_numpy(self) -> "ResultTokens":
+    data = self.data.cpu().numpy() if isinstance(self.data, torch.Tensor) else np.asarray(self.data)
+    lp = self.log_prob
+    if isinstance(lp, torch.Tensor):
+      lp = lp.cpu().numpy()
+    return ResultTokens(data, self.tokens_idx, self.valid_idx, self.length_idx, lp, self.samples_per_slot)
+
+  def get_result_at_slot(self, slot: int) -> SlotData:
+    start, end = slot * self.samples_per_slot, (slot + 1) * self.samples_per_slot
+    d = self.data
+    return SlotData(
+        tokens=d[start:end, self.tokens_idx[0] : self.tokens_idx[1]],
+        valid=d[start:end, self.valid_idx[0] : self.valid_idx[1]],
+        lengths=d[start:end, self.length_idx[0] : self.length_idx[1]][:, 0],
+        log_prob=None if self.log_prob is None else self.log_prob[start:end],
+    )
+
+
+class DeviceParams:
+  """Weights in the layout of ``mtx_weights`` (include/mtx_b200.h), resident in HBM."""
+
+  def __init__(self, tensors: dict):
+    self.tensors = tensors
+    self.struct = _lib.Weights(**{k: v.data_ptr() for k, v in tensors.items()})
+
+  def nbytes(self) -> int:
+    seen, total = set(), 0
+    for t in self.tensors.values():
+      if t.data_ptr() not in seen:
+        seen.add(t.data_ptr())
+        total += t.numel() * t.element_size()
+    return total
+
+
+def pack_params(params: dict, config, device, vocab_shard: Optional[tuple] = None) -> DeviceParams:
+  """Reference parameter tree (params.py) -> K-major packed bf16 tensors on `device`.
+
+  Every projection is stored [out_features, in_features] so a 128-row weight tile is one
+  TMA box of contiguous 128-byte rows; wi_0 / wi_1 are interleaved 16 rows at a time so the
+  gate and the value of one MLP feature land in the same warp of the GEMM epilogue.
+  """
+  p = params["params"]
+  E, Hq, Hkv, D = config.emb_dim, config.num_query_heads, config.num_kv_heads, config.head_dim
+  M, L = config.mlp_dim, config.num_decoder_layers
+  bf = torch.bfloat16
+  dev = lambda t: t.to(device=device, dtype=bf)
+  wqkv, wo, w01, wout, an, mn = [], [], [], [], [], []
+  for i in range(L):
+    lp = p["decoder"][f"layers_{i}"]
+    sa = lp["self_attention"]
+    q = dev(sa["query"]["kernel"]).reshape(E, Hq * D).t()
+    k = dev(sa["key"]["kernel"]).reshape(E, Hkv * D).t()
+    v = dev(sa["value"]["kernel"]).reshape(E, Hkv * D).t()
+    wqkv.append(torch.cat([q, k, v], dim=0).contiguous())
+    wo.append(dev(sa["out"]["kernel"]).reshape(Hq * D, E).t().contiguous())
+    w0 = dev(lp["mlp"]["wi_0"]["kernel"]).t().reshape(M // 16, 16, E)
+    w1 = dev(lp["mlp"]["wi_1"]["kernel"]).t().reshape(M // 16, 16, E)
+    w01.append(torch.stack([w0, w1], dim=1).reshape(2 * M, E).contiguous())
+    wout.append(dev(lp["mlp"]["wo"]["kernel"]).t().contiguous())
+    an.append(dev(lp["pre_self_attention_layer_norm"]["scale"]))
+    mn.append(dev(lp["mlp"]["mlp_layer_norm"]["scale"]))
+  embedding = dev(p["token_embedder"]["embedding"]).contiguous()
+  if config.logits_via_embedding:
+    logits = embedding  # attend_on_embedding, embeddings.py:183-199
+  else:
+    logits = dev(p["decoder"]["logits_dense"]["kernel"]).t().contiguous()
+  if vocab_shard is not None:
+    lo, hi = vocab_shard
+    logits = logits[lo:hi].contiguous()
+  tensors = dict(
+      embedding=embedding,
+      attn_norm=torch.stack(an).contiguous(),
+      wqkv=torch.stack(wqkv).contiguous(),
+      wo=torch.stack(wo).contiguous(),
+      mlp_norm=torch.stack(mn).contiguous(),
+      w01=torch.stack(w01).contiguous(),
+      wout=torch.stack(wout).contiguous(),
+      final_norm=dev(p["decoder"]["decoder_norm"]["scale"]).contiguous(),
+      logits=logits,
+  )
+  return DeviceParams(tensors)
+
+
+def random_device_params(config, device, seed: int = 0) -> DeviceParams:
+  """Random-init weights generated directly in HBM (benchmarks; same distributions as params.py)."""
+  g = torch.Generator(device=device).manual_seed(seed)
+  E, Hq, Hkv, D = config.emb_dim, config.num_query_heads, config.num_kv_heads, config.head_dim
+  M, L, V = config.mlp_dim, config.num_decoder_layers, config.vocab_size
+  bf = torch.bfloat16
+
+  def rn(shape, std):
+    out = torch.empty(shape, device=device, dtype=bf)
+    flat = out.view(-1)
+    step = 1 << 26
+    for lo in range(0, flat.numel(), step):
+      n = min(step, flat.numel() - lo)
+      flat[lo : lo + n] = (torch.randn(n, device=device, generator=g) * std).to(bf)
+    return out
+
+  qkv_n = (Hq + 2 * Hkv) * D
+  wqkv = rn((L, qkv_n, E), 1.0 / math.sqrt(E))
+  wqkv[:, : Hq * D] /= math.sqrt(D)  # attentions.py:1900-1904
+  embedding = rn((V, E), 1.0)
+  tensors = dict(
+      embedding=embedding,
+      attn_norm=torch.ones(L, E, device=device, dtype=bf),
+      wqkv=wqkv,
+      wo=rn((L, E, Hq * D), 1.0 / math.sqrt(Hq * D)),
+      mlp_norm=torch.ones(L, E, device=device, dtype=bf),
+      w01=rn((L, 2 * M, E), 1.0 / math.sqrt(E)),
+      wout=rn((L, E, M), 1.0 / math.sqrt(M)),
+      final_norm=torch.ones(E, device=device, dtype=bf),
+      logits=embedding if config.logits_via_embedding else rn((V, E), 1.0 / math.sqrt(E)),
+  )
+  return DeviceParams(tensors)
+
+
+class MaxEngine:
+  """The reference's ``MaxEngine`` for one B200 (one process per GPU)."""
+
+  def __init__(self, config, devices: Any = None, use_cuda_graph: bool = True):
+    self.config = config
+    self.device = _lib.require_cuda()
+    self.lib = _lib.load()
+    self.use_cuda_graph = use_cuda_graph
+    self.rng = None
+    self._handle = ctypes.c_void_p()
+    self._params: Optional[DeviceParams] = None
+    self._bound_params = None
+    self._state = None
+    B = self.max_concurrent_decodes
+    if B < 1 or B > 256:
+      raise ValueError(f"per_device_batch_size={config.per_device_batch_size}: this engine holds 1..256 slots per GPU")
+    self._chunk = max(1, min(256, int(config.prefill_chunk_size), config.max_prefill_predict_length))
+    self._staging = B  # extra KV plane prefill writes into
+    self._num_slots = B + 1
+    scale = 1.0
+    if config.logits_via_embedding and config.normalize_embedding_logits:
+      scale = 1.0 / math.sqrt(config.emb_dim)  # decoders.py:560-562
+    self._cfg_struct = _lib.ModelConfig(
+        num_layers=config.num_decoder_layers,
+        emb_dim=config.emb_dim,
+        num_q_heads=config.num_query_heads,
+        num_kv_heads=config.num_kv_heads,
+        head_dim=config.head_dim,
+        mlp_dim=config.mlp_dim,
+        vocab_size=config.vocab_size,
+        vocab_offset=0,
+        max_prefill_len=config.max_prefill_predict_length,
+        max_target_len=config.max_target_length,
+        num_slots=self._num_slots,
+        max_rows=max(B, self._chunk),
+        rms_eps=config.normalization_layer_epsilon,
+        rope_min_timescale=float(config.rope_min_timescale),
+        rope_max_timescale=float(config.rope_max_timescale),
+        attn_softcap=float(config.attn_logits_soft_cap or 0.0),
+        final_softcap=float(config.final_logits_soft_cap or 0.0),
+        logits_scale=scale,
+        logits_round_bf16=0 if config.logits_dot_in_fp32 else 1,
+    )
+    _lib.check(self.lib.mtx_engine_create(ctypes.byref(self._cfg_struct), ctypes.byref(self._handle)))
+    ws = self.lib.mtx_engine_workspace_bytes(self._handle)
+    self._ws_raw = torch.empty(ws + 1024, dtype=torch.uint8, device=self.device)
+    self._ws_ptr = (self._ws_raw.data_ptr() + 1023) // 1024 * 1024
+    self._ws_bytes = ws
+    self._alloc_state()
+    self._apply_sampling()
+
+  def __del__(self):
+    try:
+      if self._handle:
+        self.lib.mtx_engine_destroy(self._handle)
+    except Exception:  # pragma: no cover - interpreter shutdown
+      pass
+
+  # -- properties (maxengine.py:1455-1487) -------------------------------------------------
+
+  @property
+  def max_concurrent_decodes(self) -> int:
+    return int(self.config.per_device_batch_size)  # x mesh.size; one process per GPU here
+
+  @property
+  def max_prefill_length(self) -> int:
+    return int(self.config.max_prefill_predict_length)
+
+  @property
+  def use_chunked_prefill(self) -> bool:
+    return bool(self.config.use_chunked_prefill)
+
+  @property
+  def prefill_chunk_size(self) -> int:
+    return int(self.config.prefill_chunk_size)
+
+  @property
+  def samples_per_slot(self) -> int:
+    return 1
+
+  # -- state --------------------------------------------------------------------------------
+
+  def _alloc_state(self) -> None:
+    cfg, dev = self.config, self.device
+    B, S = self.max_concurrent_decodes, self._num_slots
+    L, Hkv, T, D = cfg.num_decoder_layers, cfg.num_kv_heads, cfg.max_target_length, cfg.head_dim
+    i32 = torch.int32
+    z = lambda *shape, dtype=i32: torch.zeros(*shape, dtype=dtype, device=dev)
+    self._k = z(L, S, Hkv, T, D, dtype=torch.bfloat16)
+    self._v = z(L, S, Hkv, T, D, dtype=torch.bfloat16)
+    self._tokens, self._next_pos, self._generated = z(B, 1), z(B, 1), z(B, 1)
+    self._prefill_len, self._ar_lengths, self._ar_index = z(S), z(S), z(1)
+    self._result = z(B, 3)
+    self._log_prob = z(B, 1, dtype=torch.float32) if cfg.return_log_prob else None
+    self._logits = z(B, 1, cfg.vocab_size, dtype=torch.float32) if cfg.materialize_logits else None
+    self._rng_state = z(4)
+    self._first_token = z(1)
+    self._prefill_logits = z(cfg.vocab_size, dtype=torch.float32)
+    self._prefill_tokens = z(cfg.max_prefill_predict_length)
+    self._state_struct = _lib.DecodeState(
+        k_cache=self._k.data_ptr(),
+        v_cache=self._v.data_ptr(),
+        tokens=self._tokens.data_ptr(),
+        next_pos=self._next_pos.data_ptr(),
+        generated=self._generated.data_ptr(),
+        prefill_len=self._prefill_len.data_ptr(),
+        ar_lengths=self._ar_lengths.data_ptr(),
+        ar_index=self._ar_index.data_ptr(),
+        result=self._result.data_ptr(),
+        log_prob=self._log_prob.data_ptr() if self._log_prob is not None else None,
+        logits=self._logits.data_ptr() if self._logits is not None else None,
+        rng_state=self._rng_state.data_ptr(),
+    )
+
+  def _apply_sampling(self) -> None:
+    cfg = self.config
+    _lib.check(
+        self.lib.mtx_engine_set_sampling(
+            self._handle,
+            _lib.SAMPLING[cfg.decode_sampling_strategy],
+            int(cfg.decode_sampling_top_k),
+            float(cfg.decode_sampling_nucleus_p),
+            float(cfg.decode_sampling_temperature),
+        )
+    )
+
+  def _bind(self, params: DeviceParams) -> None:
+    if self._bound_params is params:
+      return
+    _lib.check(
+        self.lib.mtx_engine_bind(
+            self._handle, ctypes.byref(params.struct), ctypes.byref(self._state_struct), ctypes.c_void_p(self._ws_ptr), self._ws_bytes
+        )
+    )
+    self._bound_params = params
+
+  def _stream(self):
+    return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+  def _seed(self, rng) -> None:
+    """Key the sampler's Philox stream (the reference threads a jax PRNG key instead)."""
+    if rng is None:
+      return
+    seed = int(rng.sum().item()) if isinstance(rng, torch.Tensor) else int(np.asarray(rng).astype(np.uint64).sum())
+    vals = torch.tensor([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=torch.int64).to(torch.int32)
+    self._rng_state[1:3].copy_(vals.to(self.device), non_blocking=True)
+
+  # -- API -----------------------------------------------------------------------------------
+
+  def load_params(self, params: Optional[dict] = None, rng: Any = None, on_device_init: bool = False) -> DeviceParams:
+    """maxengine.py:218.  `params` is the reference-named tree (params.py); None = random init."""
+    if params is None:
+      if on_device_init:
+        dp = random_device_params(self.config, self.device, self.config.init_weights_seed)
+      else:
+        dp = pack_params(params_lib.init_params(self.config), self.config, self.device)
+    elif isinstance(params, DeviceParams):
+      dp = params
+    else:
+      dp = pack_params(params, self.config, self.device)
+    self._params = dp
+    self._bind(dp)
+    return dp
+
+  def init_decode_state(self, rng: Any = None) -> dict:
+    """maxengine.py:1370-1453: every field zero."""
+    for t in (self._k, self._v, self._tokens, self._next_pos, self._generated, self._prefill_len, self._ar_lengths,
+              self._ar_index, self._result):
+      t.zero_()
+    self._rng_state[0:1].zero_()
+    if self._logits is not None:
+      self._logits.zero_()
+    self._seed(rng)
+    self._state = {
+        "logits": self._logits,
+        "cache": {
+            "key": self._k,  # [L, slots, Hkv, T, D]: rows [0,P) = cached_prefill_key, [P,T) = cached_ar_key
+            "value": self._v,
+            "prefill_length": self._prefill_len,  # == cache_prefill_segment_id.sum(-1)
+            "cached_ar_lengths": self._ar_lengths,
+            "cache_ar_index": self._ar_index,
+        },
+        "next_pos": self._next_pos,
+        "generated_tokens": self._generated,
+        "tokens": self._tokens,
+    }
+    return self._state
+
+  def prefill(
+      self,
+      *,
+      params: DeviceParams,
+      padded_tokens: Any,
+      true_length: int,
+      existing_prefix: Any = None,
+      images: Any = None,
+      sampler: Any = None,
+      rng: Any = None,
+      request_id: Any = None,
+      slot: Optional[int] = None,
+      return_prompt_logp: bool = False,
+  ):
+    """maxengine.py:533-574.  Returns (prefix, ResultTokens) for one sequence."""
+    if existing_prefix is not None:
+      raise ValueError("Using chunked prefill is needed for existing_prefix.")  # maxengine.py:436-437
+    if return_prompt_logp:
+      raise NotImplementedError("return_prompt_logp is outside the decode path")
+    self._bind(params)
+    self._seed(rng)
+    cfg = self.config
+    true_length = int(true_length)
+    toks = torch.as_tensor(padded_tokens).reshape(-1)
+    if true_length < 1 or true_length > toks.numel() or toks.numel() > cfg.max_prefill_predict_length:
+      raise ValueError(f"true_length={true_length}, {toks.numel()} padded tokens, max_prefill_predict_length={cfg.max_prefill_predict_length}")
+    n = toks.numel()
+    self._prefill_tokens[:n].copy_(toks.to(torch.int32), non_blocking=True)
+    want_logits = self._logits is not None
+    for start in range(0, true_length, self._chunk):
+      count = min(self._chunk, true_length - start)
+      last = start + count == true_length
+      _lib.check(
+          self.lib.mtx_prefill_chunk(
+              self._handle,
+              ctypes.c_void_p(self._prefill_tokens.data_ptr() + 4 * start),
+              count,
+              start,
+              self._staging,
+              1 if last else 0,
+              ctypes.c_void_p(self._first_token.data_ptr()),
+              ctypes.c_void_p(self._prefill_logits.data_ptr()) if (want_logits and last) else None,
+              self._stream(),
+          )
+      )
+    first = self._first_token.clone().reshape(1, 1)
+    prefix = {
+        "logits": self._prefill_logits.clone().reshape(1, 1, -1) if want_logits else None,
+        "cache": {
+            "key": self._k[:, self._staging, :, :true_length].clone(),  # [L, Hkv, len, D]
+            "value": self._v[:, self._staging, :, :true_length].clone(),
+            "prefill_length": true_length,
+        },
+        "next_pos": torch.full((1, 1), true_length, dtype=torch.int32, device=self.device),
+        "generated_tokens": torch.zeros((1, 1), dtype=torch.int32, device=self.device),
+        "tokens": first,
+    }
+    data = torch.cat((first, torch.ones_like(first), torch.zeros_like(first)), dim=1)
+    return prefix, ResultTokens(data=data)
+
+  def insert(self, prefix: dict, decode_state: dict, slot: int, request_id: Any = None) -> dict:
+    """maxengine.py:1045-1164: copy the prefill segment into `slot`, reset the slot's AR bookkeeping,
+    leave the AR ring data and the shared ring index untouched."""
+    if decode_state is not self._state:
+      raise ValueError("decode_state must be the dict returned by this engine's init_decode_state (it is donated)")
+    B = self.max_concurrent_decodes
+    if not 0 <= int(slot) < B:
+      raise ValueError(f"slot {slot} outside [0, {B})")
+    n = int(prefix["cache"]["prefill_length"])
+    self._k[:, slot, :, :n].copy_(prefix["cache"]["key"])
+    self._v[:, slot, :, :n].copy_(prefix["cache"]["value"])
+    self._prefill_len[slot] = n
+    self._ar_lengths[slot] = 0
+    self._next_pos[slot].copy_(prefix["next_pos"][0])
+    self._generated[slot].copy_(prefix["generated_tokens"][0])
+    self._tokens[slot].copy_(prefix["tokens"][0])
+    if self._logits is not None and prefix["logits"] is not None:
+      self._logits[slot].copy_(prefix["logits"][0])
+    return decode_state
+
+  def bulk_insert(self, prefix: dict, decode_state: dict, slots: list) -> dict:
+    """maxengine.py:946-1043: the same prefix into several slots."""
+    for s in slots:
+      decode_state = self.insert(prefix, decode_state, s)
+    return decode_state
+
+  def generate(self, params: DeviceParams, decode_state: dict, sampler: Any = None, rng: Any = None):
+    """maxengine.py:838-936: one token for every slot.  Returns (decode_state, ResultTokens)."""
+    if decode_state is not self._state:
+      raise ValueError("decode_state must be the dict returned by this engine's init_decode_state (it is donated)")
+    self._bind(params)
+    self._seed(rng)
+    B = self.max_concurrent_decodes
+    fn = self.lib.mtx_decode_step_graph if self.use_cuda_graph else self.lib.mtx_decode_step
+    _lib.check(fn(self._handle, B, self._stream()))
+    result = ResultTokens(
+        data=self._result.clone(),
+        log_prob=self._log_prob.clone() if self._log_prob is not None else None,
+    )
+    return decode_state, result
+
+  # -- helpers for tests / benchmarks ----------------------------------------------------------
+
+  def fill_synthetic_context(self, prefill_lengths, ar_lengths, seed: int = 7) -> dict:
+    """Benchmark set-up: random-normal K/V and per-slot context lengths without running prefill
+    (SURVEY 8d "random-normal bf16 fill allowed for pure bandwidth runs")."""
+    cfg = self.config
+    B = self.max_concurrent_decodes
+    P, R = cfg.max_prefill_predict_length, cfg.max_target_length - cfg.max_prefill_predict_length
+    state = self.init_decode_state()
+    g = torch.Generator(device=self.device).manual_seed(seed)
+    for buf in (self._k, self._v):
+      flat = buf.view(-1)
+      step = 1 << 26
+      for lo in range(0, flat.numel(), step):
+        n = min(step, flat.numel() - lo)
+        flat[lo : lo + n] = torch.randn(n, device=self.device, generator=g).to(torch.bfloat16)
+    pl = torch.as_tensor(prefill_lengths, dtype=torch.int32)
+    al = torch.as_tensor(ar_lengths, dtype=torch.int32)
+    if pl.numel() != B or al.numel() != B or int(pl.max()) > P or int(al.max()) >= R:
+      raise ValueError("bad synthetic context lengths")
+    self._prefill_len[:B].copy_(pl)
+    self._ar_lengths[:B].copy_(al)
+    self._ar_index.fill_(int(al.max()))
+    self._next_pos.copy_((pl + al).reshape(B, 1))
+    self._generated.copy_(al.reshape(B, 1))
+    self._tokens.copy_(torch.randint(0, cfg.vocab_size, (B, 1), generator=torch.Generator().manual_seed(seed)).to(torch.int32))
+    return state

@@ -139,9 +139,11 @@ class DecodeOracle:
     """embeddings.py:270-315.  x [B,T,H,D]; pos [B,T] int."""
     D = x.shape[-1]
     half = D // 2
-    fraction = 2 * torch.arange(0, half, dtype=torch.float32) / D
+    # timescale = min * (max/min) ** (2i/D) (embeddings.py:270-275), evaluated in fp64 and
+    # rounded once to fp32 so that every libm gives the same table
+    fraction = 2 * torch.arange(0, half, dtype=torch.float64) / D
     lo, hi = float(self.cfg.rope_min_timescale), float(self.cfg.rope_max_timescale)
-    timescale = lo * (hi / lo) ** fraction
+    timescale = (lo * (hi / lo) ** fraction).to(torch.float32)
     sinusoid = pos.to(torch.float32)[:, :, None, None] / timescale
     sin = self.r(torch.sin(sinusoid))
     cos = self.r(torch.cos(sinusoid))

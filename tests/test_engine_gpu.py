@@ -1,0 +1,203 @@
+"""Engine-level parity on the B200: MaxEngine (CUDA) against the CPU oracle on the same
+random-init weights and synthetic prompts.
+
+Stated tolerances:
+* logits vs the dtype-faithful oracle: rtol = atol = 1e-1, the reference's own ceiling
+  (MaxText/tests/model_test.py:191);
+* logits vs the fp32 oracle: |d| <= 2^-5 * max|logit| (bf16 activations through the stack);
+* greedy token ids: bit-exact, except at steps where the faithful oracle's top-2 margin is
+  below `NEAR_TIE` of the top logit -- those are near-ties; the run is re-synchronised by
+  teacher-forcing the oracle's token and the step is counted.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from maxtext_indextts2_b200 import maxengine, pyconfig
+from oracle import decode_ref as ref
+from tests.helpers import make_params, random_tokens, small_config
+
+pytestmark = pytest.mark.gpu
+
+NEAR_TIE = 2**-6  # relative top-2 margin under which a greedy mismatch is a documented near-tie
+
+
+def _prefill_both(engine, dparams, oracle, ostate, state, prompts, lengths):
+  for slot, (toks, n) in enumerate(zip(prompts, lengths)):
+    padded = torch.zeros(oracle.P, dtype=torch.int64)
+    padded[:n] = toks[:n]
+    oprefix, ofirst = oracle.prefill(padded, n)
+    ostate = oracle.insert(oprefix, ostate, slot)
+    prefix, result = engine.prefill(params=dparams, padded_tokens=padded, true_length=n)
+    assert result.data.shape == (1, 3)
+    if prefix["logits"] is not None:
+      torch.testing.assert_close(prefix["logits"].cpu()[0], oprefix["logits"][0], rtol=1e-1, atol=1e-1)
+    got_first = int(prefix["tokens"].item())
+    if got_first != int(ofirst):
+      _assert_near_tie(oprefix["logits"][0, 0], got_first, int(ofirst))
+      prefix["tokens"].fill_(int(ofirst))
+    state = engine.insert(prefix, state, slot)
+  return ostate, state
+
+
+def _assert_near_tie(row_logits, got, want):
+  top = row_logits[want].item()
+  other = row_logits[got].item()
+  assert abs(top - other) <= NEAR_TIE * max(1.0, abs(top)), f"token {got} (logit {other}) vs oracle {want} (logit {top}) is not a near-tie"
+
+
+def _lockstep(engine, dparams, oracle, ostate, state, steps, f32_oracle=None, f32_state=None):
+  near_ties = 0
+  for step in range(steps):
+    ostate, odata = oracle.generate(ostate)
+    state, result = engine.generate(dparams, state)
+    data = result.data.cpu()
+    assert data.shape == odata.shape and data.dtype == torch.int32
+    assert torch.equal(data[:, 1:], odata[:, 1:])  # valid flag and generated length
+    if state["logits"] is not None:
+      got = state["logits"].cpu()
+      torch.testing.assert_close(got, ostate["logits"], rtol=1e-1, atol=1e-1)
+      if f32_oracle is not None:
+        f32_state["tokens"] = ostate["tokens"].clone() if step else f32_state["tokens"]
+    for b in range(data.shape[0]):
+      if data[b, 0] != odata[b, 0]:
+        _assert_near_tie(ostate["logits"][b, 0], int(data[b, 0]), int(odata[b, 0]))
+        near_ties += 1
+        state["tokens"][b] = int(odata[b, 0])  # re-synchronise on the oracle's token
+    assert torch.equal(state["next_pos"].cpu(), ostate["next_pos"])
+  return near_ties
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_greedy_decode_matches_oracle_small(use_graph):
+  cfg = small_config(per_device_batch_size=3, max_prefill_predict_length=16, max_target_length=48, materialize_logits=True)
+  params = make_params(cfg)
+  oracle = ref.DecodeOracle(cfg, params, faithful=True)
+  engine = maxengine.MaxEngine(cfg, use_cuda_graph=use_graph)
+  dparams = engine.load_params(params)
+  prompts = random_tokens((3, 16), cfg.vocab_size)
+  ostate, state = _prefill_both(engine, dparams, oracle, oracle.init_decode_state(), engine.init_decode_state(), prompts, [16, 5, 1])
+  near = _lockstep(engine, dparams, oracle, ostate, state, steps=32)
+  assert near <= 3, f"{near} near-ties in 96 tokens"
+
+
+def test_logits_close_to_fp32_oracle():
+  cfg = small_config(per_device_batch_size=2, materialize_logits=True)
+  params = make_params(cfg)
+  f32 = ref.DecodeOracle(cfg, params, faithful=False)
+  engine = maxengine.MaxEngine(cfg, use_cuda_graph=False)
+  dparams = engine.load_params(params)
+  prompts = random_tokens((2, 16), cfg.vocab_size, seed=9)
+  ostate, state = _prefill_both(engine, dparams, f32, f32.init_decode_state(), engine.init_decode_state(), prompts, [7, 12])
+  for _ in range(8):
+    ostate, odata = f32.generate(ostate)
+    state, _ = engine.generate(dparams, state)
+    want = ostate["logits"]
+    got = state["logits"].cpu()
+    assert (got - want).abs().max() <= 2**-5 * want.abs().max()
+    state["tokens"].copy_(odata[:, :1])  # teacher-force so both see the same history
+
+
+def test_late_insert_and_ring_wrap():
+  """Slots joining at different times share one ring index (maxengine.py:1060-1067, kvcache.py:778)."""
+  cfg = small_config(per_device_batch_size=2, max_prefill_predict_length=8, max_target_length=20, materialize_logits=True)
+  params = make_params(cfg)
+  oracle = ref.DecodeOracle(cfg, params, faithful=True)
+  engine = maxengine.MaxEngine(cfg, use_cuda_graph=True)
+  dparams = engine.load_params(params)
+  prompts = random_tokens((2, 8), cfg.vocab_size, seed=5)
+  ostate, state = oracle.init_decode_state(), engine.init_decode_state()
+
+  def add(slot, n):
+    nonlocal ostate, state
+    padded = torch.zeros(oracle.P, dtype=torch.int64)
+    padded[:n] = prompts[slot, :n]
+    oprefix, ofirst = oracle.prefill(padded, n)
+    ostate = oracle.insert(oprefix, ostate, slot)
+    prefix, _ = engine.prefill(params=dparams, padded_tokens=padded, true_length=n)
+    prefix["tokens"].fill_(int(ofirst))
+    state = engine.insert(prefix, state, slot)
+
+  add(0, 3)
+  # slot 1 is empty: the reference still runs it on zeros; only slot 0 is compared
+  for _ in range(5):
+    ostate, odata = oracle.generate(ostate)
+    state, result = engine.generate(dparams, state)
+    torch.testing.assert_close(state["logits"].cpu()[0], ostate["logits"][0], rtol=1e-1, atol=1e-1)
+    state["tokens"].copy_(odata[:, :1])
+  add(1, 6)
+  assert int(state["cache"]["cache_ar_index"].item()) == 5 and int(state["cache"]["cached_ar_lengths"][1].item()) == 0
+  for _ in range(9):  # 14 steps in total on a ring of 12: wraps, slot 0 loses its oldest AR rows in both
+    ostate, odata = oracle.generate(ostate)
+    state, result = engine.generate(dparams, state)
+    torch.testing.assert_close(state["logits"].cpu(), ostate["logits"], rtol=1e-1, atol=1e-1)
+    state["tokens"].copy_(odata[:, :1])
+  assert int(state["cache"]["cache_ar_index"].item()) == 2
+
+
+def test_tiny_audio_config_greedy_64_steps():
+  """BASELINE config C1: MaxText decode.py-shaped run -- 4 layers, emb 256, audio-expanded vocabulary,
+  batch 1, greedy, 37-token prompt (seed 1234), every one of the 64 decode steps compared."""
+  cfg = pyconfig.initialize(None, model_name="tiny-audio", materialize_logits=True)
+  params = make_params(cfg, perturb=False)
+  oracle = ref.DecodeOracle(cfg, params, faithful=True)
+  engine = maxengine.MaxEngine(cfg)
+  dparams = engine.load_params(params)
+  rng = np.random.Generator(np.random.PCG64(1234))
+  prompt = torch.from_numpy(rng.integers(0, 262144, size=(1, 64), dtype=np.int64))
+  ostate, state = _prefill_both(engine, dparams, oracle, oracle.init_decode_state(), engine.init_decode_state(), prompt, [37])
+  near = _lockstep(engine, dparams, oracle, ostate, state, steps=64)
+  assert near <= 2
+
+
+def test_weighted_sampling_follows_the_oracle_stream():
+  cfg = small_config(per_device_batch_size=4, materialize_logits=True, decode_sampling_strategy="weighted",
+                     decode_sampling_temperature=0.7, return_log_prob=True)
+  params = make_params(cfg)
+  engine = maxengine.MaxEngine(cfg, use_cuda_graph=True)
+  dparams = engine.load_params(params)
+  state = engine.init_decode_state(rng=np.array([123, 0], dtype=np.uint32))
+  prompts = random_tokens((4, 16), cfg.vocab_size, seed=2)
+  for slot in range(4):
+    prefix, _ = engine.prefill(params=dparams, padded_tokens=prompts[slot], true_length=9 + slot)
+    state = engine.insert(prefix, state, slot)
+  for step in range(6):
+    state, result = engine.generate(dparams, state)
+    logits = state["logits"].cpu()
+    toks, scores = ref.sampling(logits, "weighted", temperature=0.7, seed=123, step=step, return_scores=True)
+    got = result.data.cpu()[:, 0]
+    for b in range(4):
+      if int(got[b]) != int(toks[b, 0]):
+        s = scores[b]
+        assert abs(s[int(got[b])] - s[int(toks[b, 0])]) < 1e-3  # ulp-level difference of logf on the two sides
+    lp = ref.log_prob_of_chosen_token(logits, got.reshape(4, 1).long())
+    torch.testing.assert_close(result.log_prob.cpu(), lp, rtol=1e-3, atol=1e-3)
+
+
+def test_engine_api_shapes_and_errors():
+  """MaxText/tests/maxengine_test.py:111-164 (shapes / dtypes) and the error behaviour of SURVEY 8b."""
+  cfg = small_config(per_device_batch_size=2)
+  engine = maxengine.MaxEngine(cfg)
+  dparams = engine.load_params()  # random init, as decode.py does without load_parameters_path
+  state = engine.init_decode_state()
+  assert set(state) == {"logits", "cache", "next_pos", "generated_tokens", "tokens"}
+  assert state["tokens"].shape == (2, 1) and state["tokens"].dtype == torch.int32
+  assert engine.max_concurrent_decodes == 2 and engine.max_prefill_length == 16 and engine.samples_per_slot == 1
+  prefix, result = engine.prefill(params=dparams, padded_tokens=torch.arange(16), true_length=4)
+  assert prefix["next_pos"].tolist() == [[4]] and prefix["generated_tokens"].tolist() == [[0]]
+  assert result.data.shape == (1, 3) and result.data.cpu()[0, 1:].tolist() == [1, 0]
+  state = engine.bulk_insert(prefix, state, [0, 1])
+  state, result = engine.generate(dparams, state)
+  assert result.data.shape == (2, 3) and result.data.dtype == torch.int32
+  slot0 = result.convert_to_numpy().get_result_at_slot(0)
+  assert slot0.tokens.shape == (1, 1) and slot0.valid[0, 0] == 1 and slot0.lengths[0] == 1
+  assert state["next_pos"].cpu().tolist() == [[5], [5]]
+  with pytest.raises(ValueError):
+    engine.insert(prefix, state, 7)
+  with pytest.raises(ValueError):
+    engine.prefill(params=dparams, padded_tokens=torch.arange(16), true_length=4, existing_prefix=object())
+  with pytest.raises(ValueError):
+    pyconfig.initialize(None, decode_sampling_strategy="beam")
+  with pytest.raises(ValueError):
+    pyconfig.initialize(None, not_a_key=1)
