@@ -40,7 +40,8 @@ def test_rmsnorm(rows, E):
   x = (torch.randn(rows, E, generator=g) * 3).to(torch.bfloat16)
   scale = (1 + 0.1 * torch.randn(E, generator=g)).to(torch.bfloat16)
   out = torch.zeros(rows, E, dtype=torch.bfloat16, device="cuda")
-  _lib.check(lib.mtx_rmsnorm(_ptr(x.cuda()), _ptr(scale.cuda()), _ptr(out), rows, E, 1e-5, _stream()))
+  xd, sd = x.cuda(), scale.cuda()  # keep the device copies alive across the asynchronous launch
+  _lib.check(lib.mtx_rmsnorm(_ptr(xd), _ptr(sd), _ptr(out), rows, E, 1e-5, _stream()))
   torch.cuda.synchronize()
 
   class C:
