@@ -1,0 +1,442 @@
+#!/usr/bin/env python3
+"""Decode-step benchmark: audio tokens/s at batch 64 on the IndexTTS2-scale model (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...   # the reference decode arithmetic on the host CPU
+
+One "step" = one autoregressive decode step (MaxEngine.generate) for `batch` slots per GPU, i.e.
+`batch` audio tokens per GPU.  Work is partitioned by request batch: every rank owns `batch` slots
+and a full weight replica; there is no data-path collective (weak scaling).
+
+Workload: 24 layers, emb 1280, 20/4 heads x 64, mlp 5120, vocabulary 264,192
+(text + audio codec tokens), bf16, P = 1024, T = 3072, contexts uniform in [512, 1536] (seed 7),
+random-init weights, random-normal KV fill (synthetic).
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+KERNEL_CLASSES = ["prepare", "rmsnorm", "qkv_rope_append", "attention", "out_proj", "mlp_up", "mlp_down", "logits_sample", "finalize"]
+
+
+def parse_args():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=64)
+  ap.add_argument("--warmup", type=int, default=4)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--batch", type=int, default=64, help="decode slots per GPU")
+  ap.add_argument("--model", default="indextts2-t2s")
+  ap.add_argument("--context-min", type=int, default=512)
+  ap.add_argument("--context-max", type=int, default=1536)
+  ap.add_argument("--no-graph", action="store_true")
+  ap.add_argument("--skip-cpu-baseline", action="store_true")
+  ap.add_argument("--cpu-slots", type=int, default=8, help="slots in the CPU baseline sample")
+  ap.add_argument("--cpu-steps", type=int, default=3)
+  return ap.parse_args()
+
+
+def make_config(args):
+  from maxtext_indextts2_b200 import pyconfig
+
+  return pyconfig.initialize(None, model_name=args.model, per_device_batch_size=args.batch)
+
+
+def context_lengths(args, cfg, rank=0):
+  rng = np.random.Generator(np.random.PCG64(7 + rank))
+  P = cfg.max_prefill_predict_length
+  total = rng.integers(args.context_min, args.context_max + 1, size=args.batch)
+  prefill = np.minimum(total, P)
+  # part of the longer contexts was decoded, the rest prefetched; short ones are all prompt
+  ar = total - prefill
+  return prefill.astype(np.int64), ar.astype(np.int64)
+
+
+def algorithmic_bytes(cfg, batch, ctx_sum):
+  """weights once + valid KV rows + KV append + embedding rows + outputs."""
+  E, Hq, Hkv, D = cfg.emb_dim, cfg.num_query_heads, cfg.num_kv_heads, cfg.head_dim
+  M, V, L = cfg.mlp_dim, cfg.vocab_size, cfg.num_decoder_layers
+  w_layers = 2 * L * (E * Hq * D + 2 * E * Hkv * D + Hq * D * E + 3 * E * M)
+  w_norm = 2 * (2 * L + 1) * E
+  w_logits = 2 * E * V
+  kv_row = L * 2 * Hkv * D * 2
+  return {
+      "weights": w_layers + w_norm + w_logits,
+      "kv_read": int(ctx_sum) * kv_row,
+      "kv_write": batch * kv_row,
+      "misc": batch * E * 2 + batch * 8,
+      "logits_weights": w_logits,
+      "attention_per_layer": int(ctx_sum) * 2 * Hkv * D * 2,
+  }
+
+
+class ClockSampler:
+  """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+  QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+           "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index):
+    self.index = index
+    self.proc = None
+    self.lines = []
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except OSError:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.lines.append(line.strip())
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except subprocess.TimeoutExpired:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for line in self.lines:
+      parts = [p.strip() for p in line.split(",")]
+      if len(parts) < 7:
+        continue
+      try:
+        sm.append(float(parts[0]))
+        mx.append(float(parts[1]))
+      except ValueError:
+        continue
+      for name, val in zip(names, parts[3:7]):
+        if val.lower().startswith("active"):
+          reasons.add(name)
+    return {
+        "sm_mhz": statistics.median(sm) if sm else None,
+        "sm_max_mhz": max(mx) if mx else None,
+        "samples": len(sm),
+        "reasons": sorted(reasons),
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of the reference decode step, timed on the host cores
+# ---------------------------------------------------------------------------------------------
+
+
+def cpu_reference_run(args, cfg, slots, steps, warmup=1):
+  """Times oracle/decode_ref.py (dtype-faithful restatement of MaxEngine.generate) on `slots` slots.
+
+  The reference's own JAX path cannot run here (no jax in the image); BASELINE.md section 4.
+  """
+  from maxtext_indextts2_b200 import pyconfig
+  from oracle import decode_ref as ref
+
+  threads = os.cpu_count() or 1
+  torch.set_num_threads(threads)
+  keys = cfg.get_keys()
+  ccfg = pyconfig.HyperParameters({**keys, "per_device_batch_size": slots})
+  E, Hq, Hkv, D = cfg.emb_dim, cfg.num_query_heads, cfg.num_kv_heads, cfg.head_dim
+  M, V, L = cfg.mlp_dim, cfg.vocab_size, cfg.num_decoder_layers
+  g = torch.Generator().manual_seed(0)
+  bf = lambda t: t.to(torch.bfloat16).to(torch.float32)
+  rn = lambda shape, std: bf(torch.randn(shape, generator=g) * std)
+  layers = []
+  for _ in range(L):
+    layers.append(dict(
+        attn_scale=torch.ones(E), wq=rn((E, Hq * D), E**-0.5 / D**0.5), wk=rn((E, Hkv * D), E**-0.5), wv=rn((E, Hkv * D), E**-0.5),
+        wo=rn((Hq * D, E), (Hq * D) ** -0.5), mlp_scale=torch.ones(E), w0=rn((E, M), E**-0.5), w1=rn((E, M), E**-0.5),
+        wout=rn((M, E), M**-0.5)))
+  weights = ref.OracleWeights(embedding=rn((V, E), 1.0), layers=layers, final_scale=torch.ones(E), logits=rn((E, V), E**-0.5))
+  oracle = ref.DecodeOracle.__new__(ref.DecodeOracle)
+  oracle.cfg, oracle.faithful, oracle.w = ccfg, True, weights
+  oracle.B, oracle.P, oracle.T = slots, cfg.max_prefill_predict_length, cfg.max_target_length
+  oracle.R = oracle.T - oracle.P
+  oracle.scores_f32 = bool(cfg.float32_qk_product)
+  oracle.softmax_f32 = oracle.scores_f32 or bool(cfg.float32_logits)
+  state = oracle.init_decode_state()
+  prefill, ar = context_lengths(args, cfg)
+  prefill, ar = prefill[:slots], ar[:slots]
+  c = state["cache"]
+  for l in range(L):
+    for name in ("prefill_key", "prefill_value", "ar_key", "ar_value"):
+      c[name][l].copy_(bf(torch.randn(c[name][l].shape, generator=g)))
+  c["prefill_segment_id"] = (torch.arange(oracle.P)[None, :] < torch.from_numpy(prefill)[:, None]).to(torch.int32)
+  idx = int(ar.max())
+  c["ar_segment_id"] = ((torch.arange(oracle.R)[None, :] >= idx - torch.from_numpy(ar)[:, None]) & (torch.arange(oracle.R)[None, :] < idx)).to(torch.int32)
+  c["ar_index"] = idx
+  c["ar_lengths"] = torch.from_numpy(ar).to(torch.int32)
+  state["next_pos"] = torch.from_numpy(prefill + ar).to(torch.int32).reshape(slots, 1)
+  state["tokens"] = torch.randint(0, V, (slots, 1), generator=g).to(torch.int32)
+  for _ in range(warmup):
+    state, _ = oracle.generate(state)
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    state, _ = oracle.generate(state)
+  dt = time.perf_counter() - t0
+  return {
+      "value": slots * steps / dt,
+      "unit": "audio tokens/s",
+      "cores": threads,
+      "kind": "port",
+      "ms_per_step": 1e3 * dt / steps,
+      "sample": f"{slots} of {args.batch} slots of the same workload, {steps} decode steps after {warmup} warm-up; "
+                "oracle/decode_ref.py (torch CPU, dtype-faithful restatement of MaxEngine.generate; the reference's JAX path is not installable here)",
+  }
+
+
+def run_reference_arm(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  cfg = make_config(args)
+  res = cpu_reference_run(args, cfg, args.cpu_slots, max(1, min(args.steps, args.cpu_steps)), warmup=1 if args.warmup else 0)
+  line = {
+      "impl": "reference",
+      "metric": "audio tokens/s at batch 64 decode (whole job)",
+      "value": res["value"],
+      "unit": "audio tokens/s",
+      "n_gpus": args.gpus,
+      "steps": args.steps,
+      "warmup": args.warmup,
+      "ms_per_step": res["ms_per_step"],
+      "higher_is_better": True,
+      "scaling": "weak",
+      "vs_baseline": None,
+      "dtype": "bf16",
+      "data": "synthetic",
+      "config": workload_config(args, cfg),
+      "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+      "e2e": {"value": res["value"], "unit": "audio tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "gpu_launches": 0,
+  }
+  print(json.dumps(line))
+
+
+def workload_config(args, cfg):
+  return {
+      "workload": f"IndexTTS2-scale text-to-semantic GPT decode step (BASELINE configs[1]): L={cfg.num_decoder_layers} E={cfg.emb_dim} "
+                  f"Hq={cfg.num_query_heads} Hkv={cfg.num_kv_heads} D={cfg.head_dim} M={cfg.mlp_dim} V={cfg.vocab_size}, greedy",
+      "batch_per_gpu": args.batch,
+      "global_batch": args.batch * args.gpus,
+      "context": f"uniform[{args.context_min},{args.context_max}] valid rows per slot, P={cfg.max_prefill_predict_length} T={cfg.max_target_length}",
+      "parallelism": f"request-batch partitioned x{args.gpus}, no collective",
+      "l2": "working set per step (weights 1.81 GB + KV 1.6 GB) exceeds the 126 MB L2; no flush needed",
+  }
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+
+
+def main():
+  args = parse_args()
+  if args.impl == "reference":
+    run_reference_arm(args)
+    return
+
+  import torch.distributed as dist
+
+  from maxtext_indextts2_b200 import _lib, maxengine
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if world != args.gpus and world > 1:
+    raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+  torch.cuda.set_device(local_rank)
+  if world > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+  if _lib.needs_build():
+    _lib.build()
+  lib = _lib.load()
+
+  cfg = make_config(args)
+  B = args.batch
+  engine = maxengine.MaxEngine(cfg, use_cuda_graph=not args.no_graph)
+  dparams = engine.load_params(on_device_init=True)
+  prefill, ar = context_lengths(args, cfg, rank)
+  state = engine.fill_synthetic_context(prefill, ar)
+  ctx_sum = int((prefill + ar).sum()) + B  # the appended row is read too
+  step_fn = lib.mtx_decode_step if args.no_graph else lib.mtx_decode_step_graph
+  stream = torch.cuda.current_stream()
+  sptr = ctypes.c_void_p(stream.cuda_stream)
+
+  def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # ---- kernel launches per step (counted on one eager step) and per-class times ----
+  n0 = lib.mtx_launch_count()
+  _lib.check(lib.mtx_decode_step(engine._handle, B, sptr))
+  torch.cuda.synchronize()
+  launches_per_step = int(lib.mtx_launch_count() - n0)
+
+  for _ in range(max(3, args.warmup)):
+    _lib.check(step_fn(engine._handle, B, sptr))
+  barrier()
+
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  ev0.record(stream)
+  for _ in range(args.steps):
+    _lib.check(step_fn(engine._handle, B, sptr))
+  ev1.record(stream)
+  barrier()
+  elapsed_ms = ev0.elapsed_time(ev1)
+
+  # ---- end to end through the public API: host tokens in (pinned), result tokens out ----
+  host_in = torch.zeros(B, 1, dtype=torch.int32).pin_memory()
+  host_out = torch.zeros(B, 3, dtype=torch.int32).pin_memory()
+  host_in.copy_(state["tokens"].cpu())
+  for _ in range(2):
+    state["tokens"].copy_(host_in, non_blocking=True)
+    state, result = engine.generate(dparams, state)
+    host_out.copy_(result.data, non_blocking=True)
+    torch.cuda.synchronize()
+  barrier()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  t_wall0 = time.perf_counter()
+  e0.record(stream)
+  for _ in range(args.steps):
+    state["tokens"].copy_(host_in, non_blocking=True)  # H2D: this step's input tokens
+    state, result = engine.generate(dparams, state)
+    host_out.copy_(result.data, non_blocking=True)  # D2H: sampled tokens
+    stream.synchronize()  # the caller needs the tokens before the next step (detokenise / stop check)
+    host_in[:, 0] = host_out[:, 0]
+  e1.record(stream)
+  barrier()
+  e2e_ms = e0.elapsed_time(e1)
+  clocks = sampler.stop()
+
+  # ---- per-kernel-class device times of one eager step (CUDA events on the launching stream) ----
+  class_ms = (ctypes.c_float * 9)()
+  class_n = (ctypes.c_int32 * 9)()
+  acc = np.zeros(9)
+  prof_steps = 3
+  for _ in range(prof_steps):
+    _lib.check(lib.mtx_profile_decode_step(engine._handle, B, sptr, class_ms, class_n))
+    acc += np.array(list(class_ms))
+  acc /= prof_steps
+  counts = list(class_n)
+
+  times = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device="cuda")
+  if world > 1:
+    dist.all_reduce(times, op=dist.ReduceOp.MAX)
+  elapsed_ms, e2e_ms = times.tolist()
+
+  if rank == 0:
+    peaks = {}
+    try:
+      peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+      pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+    ab = algorithmic_bytes(cfg, B, ctx_sum + B * args.steps / 2)
+    step_bytes = ab["weights"] + ab["kv_read"] + ab["kv_write"] + ab["misc"]
+    ms_per_step = elapsed_ms / args.steps
+    tokens_per_s = world * B * args.steps / (elapsed_ms / 1e3)
+    step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # dominant kernel class by device time
+    dom = int(np.argmax(acc))
+    L = cfg.num_decoder_layers
+    E, Hq, Hkv, D, M, V = cfg.emb_dim, cfg.num_query_heads, cfg.num_kv_heads, cfg.head_dim, cfg.mlp_dim, cfg.vocab_size
+    per_launch_bytes = {
+        "attention": ab["attention_per_layer"] + B * Hq * D * 2 * 2,
+        "logits_sample": 2 * E * V + B * E * 2,
+        "mlp_up": 2 * 2 * M * E + B * E * 2 + B * M * 2,
+        "mlp_down": 2 * M * E + B * M * 2 + 2 * B * E * 2,
+        "qkv_rope_append": 2 * (Hq + 2 * Hkv) * D * E + B * E * 2 + B * (Hq + 2 * Hkv) * D * 2,
+        "out_proj": 2 * Hq * D * E + 3 * B * E * 2,
+    }
+    name = KERNEL_CLASSES[dom]
+    n_launch = max(1, counts[dom])
+    dur_ms = acc[dom] / n_launch
+    achieved = per_launch_bytes.get(name, 0) / (dur_ms * 1e-3) / 1e9 if dur_ms > 0 else 0.0
+    roofline = {
+        "bound": "hbm",
+        "kernel": name,
+        "achieved": achieved,
+        "peak": hbm_peak,
+        "unit": "GB/s",
+        "frac": achieved / hbm_peak,
+        "traffic": None,
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": per_launch_bytes.get(name, 0),
+        "launch_ms": dur_ms,
+        "whole_step": {"algorithmic_bytes": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / hbm_peak},
+        "class_ms_per_step": {KERNEL_CLASSES[i]: round(float(acc[i]), 4) for i in range(9)},
+        "class_launches_per_step": {KERNEL_CLASSES[i]: counts[i] for i in range(9)},
+        "class_gbs": {k: round(per_launch_bytes[k] * counts[KERNEL_CLASSES.index(k)] / (acc[KERNEL_CLASSES.index(k)] * 1e-3) / 1e9, 1)
+                      for k in per_launch_bytes if acc[KERNEL_CLASSES.index(k)] > 0},
+    }
+    cpu = None
+    if not args.skip_cpu_baseline:
+      cpu = cpu_reference_run(args, cfg, args.cpu_slots, args.cpu_steps)
+      cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {
+        "metric": "audio tokens/s at batch 64 decode (whole job); decode-step HBM GB/s in roofline.whole_step",
+        "value": tokens_per_s,
+        "unit": "audio tokens/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "bf16",
+        "data": "synthetic",
+        "config": workload_config(args, cfg),
+        "e2e": {
+            "value": world * B * args.steps / (e2e_ms / 1e3),
+            "unit": "audio tokens/s",
+            "ms_per_step": e2e_ms / args.steps,
+            "h2d_bytes_per_step": B * 4,
+            "d2h_bytes_per_step": B * 3 * 4,
+            "api": "MaxEngine.generate with pinned host token buffers, one stream sync per step",
+        },
+        "gpu_launches": launches_per_step * args.steps,
+        "launches_per_step": launches_per_step,
+        "cuda_graph": not args.no_graph,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

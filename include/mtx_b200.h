@@ -137,6 +137,12 @@ int mtx_decode_step(mtx_engine* e, int rows, mtx_stream stream);
 /* Same step, replayed from a CUDA graph captured on first use (one graph per `rows`). */
 int mtx_decode_step_graph(mtx_engine* e, int rows, mtx_stream stream);
 
+/* Measurement aid: one eager decode step with a CUDA-event pair around every kernel launch
+ * (on `stream`), summed per kernel class into class_ms[9] / class_launches[9] (host arrays):
+ * 0 prepare, 1 rmsnorm, 2 qkv+rope+append, 3 attention, 4 out-proj, 5 mlp up, 6 mlp down,
+ * 7 logits+sampling, 8 finalize.  Synchronises the stream; the step really advances the state. */
+int mtx_profile_decode_step(mtx_engine* e, int rows, mtx_stream stream, float* class_ms, int32_t* class_launches);
+
 /* `count` consecutive prompt positions [start_pos, start_pos+count) of one sequence into the
  * prefill segment of plane `slot`: MaxEngine._prefill_jit (maxengine.py:400-530) with
  * KVCache.kv_cache_prefill (kvcache.py:584-624), processed as rows of one step with causal
@@ -152,10 +158,9 @@ int mtx_rmsnorm(const void* x, const void* scale, void* out, int rows, int emb_d
 
 /* DenseGeneral (linears.py:188-232): out[rows,N] = bf16(x[rows,K] . w[N,K]^T), fp32 accumulate on
  * tcgen05 tensor cores.  x must be allocated with rows rounded up to 16/32/64/128/256 (zero
- * padded).  splits > 1 cuts K over that many CTAs per 128-row weight tile; it needs `scratch`
- * of mtx_linear_scratch_bytes(), zeroed once by the caller (it is left zeroed). */
-size_t mtx_linear_scratch_bytes(int rows, int n, int splits);
-int mtx_linear(const void* x, const void* w, void* out, int rows, int n, int k, int splits, void* scratch, mtx_stream stream);
+ * padded).  splits (1, 2, 4, 8 or 16) cuts K over the CTAs of one thread-block cluster per 128-row
+ * weight tile; the partial tiles are reduced over distributed shared memory. */
+int mtx_linear(const void* x, const void* w, void* out, int rows, int n, int k, int splits, mtx_stream stream);
 
 /* GQA decode attention over the valid rows of both cache segments: AttentionOp.__call__ in
  * autoregressive mode (attentions.py:1399-1466: two apply_attention_dot calls merged by
@@ -175,6 +180,9 @@ int mtx_decode_attention(const void* q, const void* k_cache, const void* v_cache
 const char* mtx_last_error(void);
 /* "sm_100a" build tag, so a caller can check what it loaded. */
 const char* mtx_build_info(void);
+/* Debug aid: when non-NULL (device memory, 256 x int64), the GEMM and attention kernels record
+ * a clock64 timeline of their first CTA into it.  NULL (the default) switches it off. */
+void mtx_debug_set_trace(void* device_buffer);
 /* Kernels launched by this library since load (all engines); used by bench.py's gpu_launches. */
 uint64_t mtx_launch_count(void);
 

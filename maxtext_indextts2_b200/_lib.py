@@ -134,14 +134,14 @@ def _declare(lib) -> None:
   lib.mtx_decode_step.argtypes = [vp, i32, vp]
   lib.mtx_decode_step_graph.restype = i32
   lib.mtx_decode_step_graph.argtypes = [vp, i32, vp]
+  lib.mtx_profile_decode_step.restype = i32
+  lib.mtx_profile_decode_step.argtypes = [vp, i32, vp, c.POINTER(c.c_float), c.POINTER(c.c_int32)]
   lib.mtx_prefill_chunk.restype = i32
   lib.mtx_prefill_chunk.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp]
   lib.mtx_rmsnorm.restype = i32
   lib.mtx_rmsnorm.argtypes = [vp, vp, vp, i32, i32, f32, vp]
-  lib.mtx_linear_scratch_bytes.restype = sz
-  lib.mtx_linear_scratch_bytes.argtypes = [i32, i32, i32]
   lib.mtx_linear.restype = i32
-  lib.mtx_linear.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+  lib.mtx_linear.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
   lib.mtx_attention_scratch_bytes.restype = sz
   lib.mtx_attention_scratch_bytes.argtypes = [i32] * 6
   lib.mtx_decode_attention.restype = i32

@@ -40,8 +40,10 @@ struct AttnParams {
   float* part_ml;         // [rows, Hkv, max_chunks, G, 2]
   int* tickets;           // [rows, Hkv], zero between launches
   int rows, hq, hkv, P, T, max_chunks;
+  int tiles_per_item;     // 64-row tiles one CTA iteration covers (multiple of 4); >= all tiles: no cross-CTA merge
   int plane_base;         // layer * num_slots (row coordinate base in the cache tensor map)
   float softcap;
+  long long* trace;  // debug: clock64 timeline of warp 0 of CTA 0 (8 slots per item), or null
 };
 
 struct TileLoc { int p0, cnt; };
@@ -52,9 +54,23 @@ __host__ __device__ inline int attn_num_tiles(int len0, int ring_first, int ring
   return (len0 + 63) / 64 + (a + 63) / 64 + (b + 63) / 64;
 }
 
-__host__ __device__ inline int attn_max_chunks(int P, int T) {
-  const int R = T - P;
-  return ((P + 63) / 64 + (R + 63) / 64 + 1 + kAttnWarps - 1) / kAttnWarps;
+__host__ __device__ inline int attn_max_tiles(int P, int T) { return (P + 63) / 64 + (T - P + 63) / 64 + 1; }
+
+// Chunks of a row's valid sequence when one work item covers `tpi` tiles.
+__host__ __device__ inline int attn_max_chunks(int P, int T, int tpi = kAttnWarps) {
+  return (attn_max_tiles(P, T) + tpi - 1) / tpi;
+}
+
+// Tiles per work item: the whole sequence of a (row, kv head) when there are at least as many such
+// pairs as CTA slots worth filling (no cross-CTA merge at all); otherwise cut so that roughly
+// `target_items` items exist for the longest possible context.
+__host__ inline int attn_tiles_per_item(int rows, int hkv, int P, int T, int target_items) {
+  const int pairs = rows * hkv;
+  const int mt = attn_max_tiles(P, T);
+  if (pairs >= target_items) return (mt + kAttnWarps - 1) / kAttnWarps * kAttnWarps;
+  int tpi = (mt * pairs + target_items - 1) / target_items;
+  tpi = (tpi + kAttnWarps - 1) / kAttnWarps * kAttnWarps;
+  return tpi < kAttnWarps ? kAttnWarps : tpi;
 }
 
 // Physical start row and valid count of 64-row tile t of a row's valid sequence.
@@ -82,14 +98,14 @@ __device__ __forceinline__ TileLoc attn_tile(int t, int len0, int ring_first, in
 
 // One block: per-row chunk counts -> prefix sum -> (row, chunk) list.
 __global__ void attn_build_worklist_kernel(const int* len0, const int* ring_first, const int* ring_len, int rows, int P, int T,
-                                           int* work_items, int* work_count) {
+                                           int tpi, int* work_items, int* work_count) {
   __shared__ int s_off[257];
   griddep_launch_dependents();
   griddep_wait();
   const int R = T - P;
   const int tid = threadIdx.x;
   int chunks = 0;
-  if (tid < rows) chunks = (attn_num_tiles(len0[tid], ring_first[tid], ring_len[tid], R) + kAttnWarps - 1) / kAttnWarps;
+  if (tid < rows) chunks = (attn_num_tiles(len0[tid], ring_first[tid], ring_len[tid], R) + tpi - 1) / tpi;
   s_off[tid + 1] = chunks;
   if (tid == 0) s_off[0] = 0;
   __syncthreads();
@@ -111,20 +127,26 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   constexpr float kLog2e = 1.4426950408889634f;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // [warp][K tile | V tile], then barriers and merge statistics
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAttnWarps * 2 * kTileBytes);
+  const int G = p.hq / p.hkv;
+  const int o_rows = G <= 8 ? 8 : 16;
+  // [warp][K tile | V tile] | merge buffer [warp][o_rows][D] fp32 | barriers | merge statistics
+  float* sm_o_all = reinterpret_cast<float*>(smem + kAttnWarps * 2 * kTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_o_all + kAttnWarps * o_rows * D);
   float* sm_m = reinterpret_cast<float*>(bars + 2 * kAttnWarps);  // [4][16]
   float* sm_l = sm_m + kAttnWarps * 16;                            // [4][16]
   __shared__ int s_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tid4 = lane & 3;
-  const int G = p.hq / p.hkv;
+  const int mtx_i = lane >> 3, lrow = lane & 7;
   const int R = p.T - p.P;
+  const int TPI = p.tiles_per_item;
   uint8_t* k_tile = smem + warp * 2 * kTileBytes;
   uint8_t* v_tile = k_tile + kTileBytes;
+  float* sm_o = sm_o_all + warp * o_rows * D;
   uint64_t* bar_k = bars + 2 * warp;
   uint64_t* bar_v = bar_k + 1;
+  const uint32_t kb = smem_u32(k_tile), vb = smem_u32(v_tile);
 
   griddep_launch_dependents();
   if (lane == 0) {
@@ -140,25 +162,32 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   griddep_wait();
 
   const int n_items = *p.work_count * p.hkv;
+  long long* trace = (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) ? p.trace : nullptr;
+  const long long t_start = clock64();
+  int iter = 0;
   uint32_t phase = 0;
+
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int packed = p.work_items[item / p.hkv];
     const int h = item % p.hkv;
     const int r = packed >> 16, chunk = packed & 0xffff;
     const int len0 = p.len0[r], rf = p.ring_first[r], rl = p.ring_len[r];
-    const int n_chunks = (attn_num_tiles(len0, rf, rl, R) + kAttnWarps - 1) / kAttnWarps;
-    const TileLoc loc = attn_tile(chunk * kAttnWarps + warp, len0, rf, rl, p.P, R);
-    const bool active = loc.cnt > 0;
+    const int nt = attn_num_tiles(len0, rf, rl, R);
+    const int n_chunks = (nt + TPI - 1) / TPI;
+    const int t_begin = chunk * TPI, t_end = min(nt, t_begin + TPI);
+    const int plane_row = ((p.plane_base + p.plane[r]) * p.hkv + h) * p.T;
+    if (trace && iter < 15) trace[iter * 8 + 0] = clock64() - t_start;
 
-    if (active && lane == 0) {
-      fence_proxy_async();  // order the previous iteration's generic reads before the async writes
-      const int row0 = ((p.plane_base + p.plane[r]) * p.hkv + h) * p.T + loc.p0;
+    // first tile of this warp: start both loads before touching Q
+    int t = t_begin + warp;
+    TileLoc loc = attn_tile(t < t_end ? t : nt, len0, rf, rl, p.P, R);  // t >= nt gives an empty tile
+    if (t < t_end && lane == 0) {
       mbar_expect_tx(bar_k, kTileBytes);
 #pragma unroll
-      for (int s = 0; s < kSub; ++s) tma_load_2d(k_tile + s * 8192, &tm_k, s * 64, row0, bar_k, kEvictFirst);
+      for (int s = 0; s < kSub; ++s) tma_load_2d(k_tile + s * 8192, &tm_k, s * 64, plane_row + loc.p0, bar_k, kEvictFirst);
       mbar_expect_tx(bar_v, kTileBytes);
 #pragma unroll
-      for (int s = 0; s < kSub; ++s) tma_load_2d(v_tile + s * 8192, &tm_v, s * 64, row0, bar_v, kEvictFirst);
+      for (int s = 0; s < kSub; ++s) tma_load_2d(v_tile + s * 8192, &tm_v, s * 64, plane_row + loc.p0, bar_v, kEvictFirst);
     }
 
     // Q fragments (A operand, rows = query heads of the group, zero-padded to 16)
@@ -166,42 +195,54 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
     {
       const bf16* qrow = p.q + (long long)r * p.hq * D + (long long)h * G * D;
 #pragma unroll
-      for (int t = 0; t < D / 16; ++t) {
-        const int d = t * 16 + tid4 * 2;
-        qf[t][0] = gid < G ? *reinterpret_cast<const uint32_t*>(qrow + gid * D + d) : 0u;
-        qf[t][1] = gid + 8 < G ? *reinterpret_cast<const uint32_t*>(qrow + (gid + 8) * D + d) : 0u;
-        qf[t][2] = gid < G ? *reinterpret_cast<const uint32_t*>(qrow + gid * D + d + 8) : 0u;
-        qf[t][3] = gid + 8 < G ? *reinterpret_cast<const uint32_t*>(qrow + (gid + 8) * D + d + 8) : 0u;
+      for (int tt = 0; tt < D / 16; ++tt) {
+        const int d = tt * 16 + tid4 * 2;
+        qf[tt][0] = gid < G ? *reinterpret_cast<const uint32_t*>(qrow + gid * D + d) : 0u;
+        qf[tt][1] = gid + 8 < G ? *reinterpret_cast<const uint32_t*>(qrow + (gid + 8) * D + d) : 0u;
+        qf[tt][2] = gid < G ? *reinterpret_cast<const uint32_t*>(qrow + gid * D + d + 8) : 0u;
+        qf[tt][3] = gid + 8 < G ? *reinterpret_cast<const uint32_t*>(qrow + (gid + 8) * D + d + 8) : 0u;
       }
     }
 
+    // running softmax state of this warp over its tiles (rows gid and gid+8 of the fragment)
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
     float o[D / 8][4];
 #pragma unroll
     for (int j = 0; j < D / 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.0f;
 
-    if (active) {
+    for (; t < t_end; t += kAttnWarps) {
+      const int cnt = loc.cnt;
+      const int tn = t + kAttnWarps;
+      const TileLoc nloc = attn_tile(tn < t_end ? tn : nt, len0, rf, rl, p.P, R);
       // ---- S = Q K^T over the 64 rows of the tile ----
       float s[8][4];
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
       mbar_wait(bar_k, phase);
-      const uint32_t kb = smem_u32(k_tile);
-      const int mtx_i = lane >> 3, lrow = lane & 7;
+      if (trace && iter < 15 && t == t_begin) trace[iter * 8 + 1] = clock64() - t_start;
 #pragma unroll
-      for (int t = 0; t < D / 16; ++t) {
+      for (int tt = 0; tt < D / 16; ++tt) {
 #pragma unroll
         for (int jp = 0; jp < 4; ++jp) {
           const int row = 8 * (2 * jp + (mtx_i >> 1)) + lrow;
-          const int c = 2 * t + (mtx_i & 1);
+          const int c = 2 * tt + (mtx_i & 1);
           const uint32_t addr = kb + (c >> 3) * 8192 + row * 128 + (((c & 7) ^ (row & 7)) << 4);
           uint32_t b00, b01, b10, b11;
           ldmatrix_x4(addr, b00, b01, b10, b11);
-          mma_m16n8k16_bf16(s[2 * jp], qf[t], b00, b01);
-          mma_m16n8k16_bf16(s[2 * jp + 1], qf[t], b10, b11);
+          mma_m16n8k16_bf16(s[2 * jp], qf[tt], b00, b01);
+          mma_m16n8k16_bf16(s[2 * jp + 1], qf[tt], b10, b11);
         }
       }
-      // ---- mask + softmax statistics (rows gid and gid+8 of the 16-row fragment) ----
+      // K tile consumed: refill it with the next tile's keys while the softmax and P V run
+      fence_proxy_async();
+      __syncwarp();
+      if (tn < t_end && lane == 0) {
+        mbar_expect_tx(bar_k, kTileBytes);
+#pragma unroll
+        for (int ss = 0; ss < kSub; ++ss) tma_load_2d(k_tile + ss * 8192, &tm_k, ss * 64, plane_row + nloc.p0, bar_k, kEvictFirst);
+      }
+      // ---- mask + online softmax (quad shuffles) ----
+      float tm0 = -INFINITY, tm1 = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -209,15 +250,21 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
           const int col = 8 * j + tid4 * 2 + (e & 1);
           float x = s[j][e];
           if (p.softcap != 0.0f) x = tanhf(x / p.softcap) * p.softcap;
-          s[j][e] = col < loc.cnt ? x : -INFINITY;
+          s[j][e] = col < cnt ? x : -INFINITY;
         }
-        m0 = fmaxf(m0, fmaxf(s[j][0], s[j][1]));
-        m1 = fmaxf(m1, fmaxf(s[j][2], s[j][3]));
+        tm0 = fmaxf(tm0, fmaxf(s[j][0], s[j][1]));
+        tm1 = fmaxf(tm1, fmaxf(s[j][2], s[j][3]));
       }
-      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+      tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1));
+      tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 2));
+      tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1));
+      tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
+      const float nm0 = fmaxf(m0, tm0), nm1 = fmaxf(m1, tm1);
+      const float a0 = exp2f((m0 - nm0) * kLog2e), a1 = exp2f((m1 - nm1) * kLog2e);  // exp2(-inf) = 0 on the first tile
+      m0 = nm0;
+      m1 = nm1;
+      l0 *= a0;
+      l1 *= a1;
       uint32_t pa[4][4];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -230,22 +277,23 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
         pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
         pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
       }
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-
-      // ---- O = P V ----
+#pragma unroll
+      for (int j = 0; j < D / 8; ++j) {
+        o[j][0] *= a0;
+        o[j][1] *= a0;
+        o[j][2] *= a1;
+        o[j][3] *= a1;
+      }
+      // ---- O += P V ----
       mbar_wait(bar_v, phase);
-      if (loc.cnt < 64) {  // rows past the valid count may hold anything: zero them (0 * NaN != 0)
-        const int nvec = (64 - loc.cnt) * 8;
+      if (cnt < 64) {  // rows past the valid count may hold anything: zero them (0 * NaN != 0)
+        const int nvec = (64 - cnt) * 8;
         for (int i = lane; i < nvec * kSub; i += 32) {
           const int sub = i / nvec, w = i % nvec;
-          *reinterpret_cast<uint4*>(v_tile + sub * 8192 + (loc.cnt + w / 8) * 128 + (w & 7) * 16) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(v_tile + sub * 8192 + (cnt + w / 8) * 128 + (w & 7) * 16) = make_uint4(0, 0, 0, 0);
         }
         __syncwarp();
       }
-      const uint32_t vb = smem_u32(v_tile);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
 #pragma unroll
@@ -259,13 +307,25 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
           mma_m16n8k16_bf16(o[2 * jp + 1], pa[u], b10, b11);
         }
       }
+      // V tile consumed: refill
+      fence_proxy_async();
+      __syncwarp();
+      if (tn < t_end && lane == 0) {
+        mbar_expect_tx(bar_v, kTileBytes);
+#pragma unroll
+        for (int ss = 0; ss < kSub; ++ss) tma_load_2d(v_tile + ss * 8192, &tm_v, ss * 64, plane_row + nloc.p0, bar_v, kEvictFirst);
+      }
       phase ^= 1;
+      loc = nloc;
     }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    if (trace && iter < 15) trace[iter * 8 + 4] = clock64() - t_start;
 
     // ---- merge the four warps of the item in shared memory ----
-    __syncwarp();
-    float* sm_o = reinterpret_cast<float*>(k_tile);  // [16][D] fp32, reuses this warp's K tile
-    if (active) {
+    if (m0 > -INFINITY) {
 #pragma unroll
       for (int j = 0; j < D / 8; ++j) {
         const int d = 8 * j + tid4 * 2;
@@ -280,6 +340,7 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
       sm_l[warp * 16 + gid + 8] = l1;
     }
     __syncthreads();
+    if (trace && iter < 15) trace[iter * 8 + 5] = clock64() - t_start;
 
     const long long out_base = (long long)r * p.hq * D + (long long)h * G * D;
     const long long part_base = ((long long)(r * p.hkv + h) * p.max_chunks + chunk) * G;
@@ -295,7 +356,7 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
         if (mw > -INFINITY) {
           const float sc = exp2f((mw - M) * kLog2e);
           L += sm_l[w * 16 + g] * sc;
-          O += reinterpret_cast<const float*>(smem + w * 2 * kTileBytes)[g * D + d] * sc;
+          O += sm_o_all[(w * o_rows + g) * D + d] * sc;
         }
       }
       if (n_chunks == 1) {
@@ -335,11 +396,16 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
         }
       }
     }
-    fence_proxy_async();  // this thread's generic smem accesses precede the next item's TMA writes
-    __syncthreads();
+    if (trace && iter < 15) trace[iter * 8 + 6] = clock64() - t_start;
+    __syncthreads();  // the merge buffer is rewritten by the next item
+    if (trace && iter < 15) trace[iter * 8 + 7] = clock64() - t_start;
+    ++iter;
   }
 }
 
-__host__ inline size_t attn_smem_bytes(int D) { return 1024 + size_t(kAttnWarps) * 2 * (64 * D * 2) + 2 * kAttnWarps * 8 + 2 * kAttnWarps * 16 * 4 + 16; }
+__host__ inline size_t attn_smem_bytes(int D, int G) {
+  const size_t o_rows = G <= 8 ? 8 : 16;
+  return 1024 + size_t(kAttnWarps) * 2 * (64 * D * 2) + kAttnWarps * o_rows * D * 4 + 2 * kAttnWarps * 8 + 2 * kAttnWarps * 16 * 4 + 16;
+}
 
 }  // namespace mtx

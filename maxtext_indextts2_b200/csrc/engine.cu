@@ -89,10 +89,23 @@ int make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, u
 
 // ---- launch helper -------------------------------------------------------------------------
 
+// Optional per-kernel timing: when a sink is installed every launch is bracketed by CUDA
+// events on the launching stream and attributed to the current kernel class.
+enum KernelClass { KC_PREPARE = 0, KC_RMSNORM, KC_QKV, KC_ATTENTION, KC_OUTPROJ, KC_MLP_UP, KC_MLP_DOWN, KC_LOGITS, KC_FINALIZE, KC_COUNT };
+struct ProfileSink {
+  struct Rec { int cls; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+};
+thread_local ProfileSink* g_profile = nullptr;
+thread_local int g_class = KC_PREPARE;
+long long* g_trace = nullptr;  // debug timeline buffer (device), see mtx_debug_set_trace
+
 bool use_pdl() {
   static int v = env_int("MTX_PDL", 1);
   return v != 0;
 }
+
+thread_local int g_cluster_y = 1;  // cluster size along grid.y for the next launch (split-K GEMM)
 
 template <typename... KArgs, typename... Args>
 int launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
@@ -102,12 +115,34 @@ int launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStr
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (use_pdl()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (g_cluster_y > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = unsigned(g_cluster_y);
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl() ? 1 : 0;
+  cfg.numAttrs = na;
+  ProfileSink::Rec rec;
+  if (g_profile != nullptr) {
+    rec.cls = g_class;
+    MTX_CUDA(cudaEventCreate(&rec.a));
+    MTX_CUDA(cudaEventCreate(&rec.b));
+    MTX_CUDA(cudaEventRecord(rec.a, stream));
+  }
   MTX_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  if (g_profile != nullptr) {
+    MTX_CUDA(cudaEventRecord(rec.b, stream));
+    g_profile->recs.push_back(rec);
+  }
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return MTX_OK;
 }
@@ -125,17 +160,20 @@ struct GemmPlan {
   size_t smem;
 };
 
-GemmPlan plan_gemm(int n, int k, int r_tile, int num_sms, int forced_splits = 0) {
+// K splits = cluster size: a power of two <= 16 (8 is the portable maximum, 16 needs the
+// non-portable opt-in), chosen so that n_tiles * splits is close to one CTA per SM.
+GemmPlan plan_gemm(int n, int k, int r_tile, int num_sms, int epi, int forced_splits = 0) {
   GemmPlan g;
   g.n_tiles = (n + kTileN - 1) / kTileN;
   const int kb = k / kBlockK;
   int splits = forced_splits;
   if (splits <= 0) {
     const int target = env_int("MTX_GEMM_TARGET_CTAS", num_sms);
-    splits = target / g.n_tiles;
+    const int max_split = env_int("MTX_GEMM_MAX_SPLIT", 16);
+    const double want = double(target) / g.n_tiles;
+    splits = 1;
+    while (splits * 2 <= max_split && splits * 2 <= kb && splits * 2 <= r_tile && double(splits) * 1.42 < want) splits *= 2;
   }
-  if (splits < 1) splits = 1;
-  if (splits > kb) splits = kb;
   g.splits = splits;
   const int stage_bytes = kWTileBytes + r_tile * kBlockK * 2;
   const int budget = (r_tile <= 128 ? 100 : 200) * 1024;
@@ -145,7 +183,7 @@ GemmPlan plan_gemm(int n, int k, int r_tile, int num_sms, int forced_splits = 0)
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 1) stages = 1;
   g.stages = stages;
-  g.smem = gemm_smem_bytes(stages, r_tile);
+  g.smem = gemm_smem_bytes(stages, r_tile, splits, epi);
   return g;
 }
 
@@ -154,11 +192,16 @@ int launch_gemm(const CUtensorMap& tw, const CUtensorMap& tx, GemmParams p, cons
   static bool attr_set = false;  // per template instance
   if (!attr_set) {
     MTX_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    MTX_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<EPI>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr_set = true;
   }
   p.splits = g.splits;
   p.stages = g.stages;
-  return launch(gemm_umma_kernel<EPI>, dim3(g.n_tiles, g.splits), dim3(kGemmThreads), g.smem, st, tw, tx, p, e);
+  p.trace = g_trace;
+  g_cluster_y = g.splits;
+  const int rc = launch(gemm_umma_kernel<EPI>, dim3(g.n_tiles, g.splits), dim3(kGemmThreads), g.smem, st, tw, tx, p, e);
+  g_cluster_y = 1;
+  return rc;
 }
 
 struct XMaps {
@@ -188,8 +231,6 @@ struct mtx_engine {
   // workspace carve-up
   size_t ws_bytes = 0;
   bf16 *x = nullptr, *h = nullptr, *n = nullptr, *q = nullptr, *attn = nullptr, *act = nullptr;
-  float* gemm_ws = nullptr;
-  int* gemm_tickets = nullptr;
   float *attn_part_o = nullptr, *attn_part_ml = nullptr;
   int* attn_tickets = nullptr;
   RowDesc rd{};
@@ -212,7 +253,7 @@ struct mtx_engine {
 namespace {
 
 struct WsLayout {
-  size_t x, h, n, q, attn, act, gemm_ws, gemm_tickets, attn_part_o, attn_part_ml, attn_tickets;
+  size_t x, h, n, q, attn, act, attn_part_o, attn_part_ml, attn_tickets;
   size_t token, pos, plane, write_row, len0, ring_first, ring_len, rope_cs, work_items, work_count, rope_timescale;
   size_t part_score, part_idx, part_raw, part_max, part_sum;
   size_t total;
@@ -235,10 +276,6 @@ WsLayout layout_workspace(const mtx_engine* e) {
   L.q = take(rt * c.num_q_heads * c.head_dim * 2);
   L.attn = take(rt * c.num_q_heads * c.head_dim * 2);
   L.act = take(rt * c.mlp_dim * 2);
-  // split-K partials: splits * n_tiles <= max(num_sms, n_tiles) tiles of [r_tile][128] fp32 for split GEMMs
-  const size_t max_split_tiles = size_t(e->num_sms) * 2 + 64;
-  L.gemm_ws = take(max_split_tiles * rt * kTileN * 4);
-  L.gemm_tickets = take(4096 * 4);
   L.attn_part_o = take(size_t(c.max_rows) * c.num_kv_heads * e->attn_max_chunks * G * c.head_dim * 4);
   L.attn_part_ml = take(size_t(c.max_rows) * c.num_kv_heads * e->attn_max_chunks * G * 2 * 4);
   L.attn_tickets = take(size_t(c.max_rows) * c.num_kv_heads * 4);
@@ -295,12 +332,14 @@ int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st) {
   p.hkv = c.num_kv_heads;
   p.P = c.max_prefill_len;
   p.T = c.max_target_len;
+  p.tiles_per_item = attn_tiles_per_item(rows, c.num_kv_heads, c.max_prefill_len, c.max_target_len, e->num_sms);
   p.max_chunks = e->attn_max_chunks;
   p.plane_base = layer * c.num_slots;
   p.softcap = c.attn_softcap;
-  const size_t smem = attn_smem_bytes(c.head_dim);
+  p.trace = g_trace;
+  const size_t smem = attn_smem_bytes(c.head_dim, c.num_q_heads / c.num_kv_heads);
   const int ctas_per_sm = c.head_dim == 64 ? 3 : 1;
-  int grid = rows * c.num_kv_heads * e->attn_max_chunks;
+  int grid = rows * c.num_kv_heads * attn_max_chunks(c.max_prefill_len, c.max_target_len, p.tiles_per_item);
   const int cap = e->num_sms * ctas_per_sm;
   if (grid > cap) grid = cap;
   if (c.head_dim == 64) return launch(decode_attn_kernel<64>, dim3(grid), dim3(kAttnThreads), smem, st, e->tm_k, e->tm_v, p);
@@ -332,8 +371,11 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   pa.P = c.max_prefill_len;
   pa.T = c.max_target_len;
   pa.D = c.head_dim;
+  pa.tiles_per_item = attn_tiles_per_item(rows, c.num_kv_heads, c.max_prefill_len, c.max_target_len, e->num_sms);
   pa.rope_timescale = e->rope_timescale;
+  g_class = KC_PREPARE;
   MTX_TRY(launch(prepare_rows_kernel, dim3(1), dim3(256), 0, st, pa, e->rd));
+  g_class = KC_RMSNORM;
 
   const bf16* attn_norm = static_cast<const bf16*>(e->w.attn_norm);
   const bf16* mlp_norm = static_cast<const bf16*>(e->w.mlp_norm);
@@ -344,13 +386,11 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   memset(&gp, 0, sizeof(gp));
   gp.rows = rows;
   gp.r_tile = r_tile;
-  gp.ws = e->gemm_ws;
-  gp.tickets = e->gemm_tickets;
-  const GemmPlan plan_qkv = plan_gemm(e->qkv_n, E, r_tile, e->num_sms);
-  const GemmPlan plan_o = plan_gemm(E, HD, r_tile, e->num_sms);
-  const GemmPlan plan_up = plan_gemm(2 * M, E, r_tile, e->num_sms);
-  const GemmPlan plan_down = plan_gemm(E, M, r_tile, e->num_sms);
-  const GemmPlan plan_logits = plan_gemm(c.vocab_size, E, r_tile, e->num_sms, 1);
+  const GemmPlan plan_qkv = plan_gemm(e->qkv_n, E, r_tile, e->num_sms, EPI_QKV_ROPE);
+  const GemmPlan plan_o = plan_gemm(E, HD, r_tile, e->num_sms, EPI_RESIDUAL);
+  const GemmPlan plan_up = plan_gemm(2 * M, E, r_tile, e->num_sms, EPI_SWIGLU);
+  const GemmPlan plan_down = plan_gemm(E, M, r_tile, e->num_sms, EPI_RESIDUAL);
+  const GemmPlan plan_logits = plan_gemm(c.vocab_size, E, r_tile, e->num_sms, EPI_LOGITS, 1);
 
   for (int l = 0; l < L; ++l) {
     EpiArgs ea;
@@ -367,8 +407,10 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     ea.t_alloc = c.max_target_len;
     gp.n = e->qkv_n;
     gp.k = E;
+    g_class = KC_QKV;
     MTX_TRY(launch_gemm<EPI_QKV_ROPE>(e->tm_wqkv[l], xm->n, gp, ea, plan_qkv, st));
 
+    g_class = KC_ATTENTION;
     MTX_TRY(launch_attention(e, l, rows, st));
 
     memset(&ea, 0, sizeof(ea));
@@ -377,8 +419,10 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     ea.ld_out = E;
     gp.n = E;
     gp.k = HD;
+    g_class = KC_OUTPROJ;
     MTX_TRY(launch_gemm<EPI_RESIDUAL>(e->tm_wo[l], xm->attn, gp, ea, plan_o, st));
 
+    g_class = KC_RMSNORM;
     MTX_TRY(launch(rmsnorm_kernel<false>, dim3(rows), dim3(128), 0, st, (const bf16*)e->h, (const int*)nullptr,
                    (const bf16*)nullptr, mlp_norm + size_t(l) * E, (bf16*)nullptr, e->n, E, c.rms_eps));
 
@@ -387,6 +431,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     ea.ld_out = M;
     gp.n = 2 * M;
     gp.k = E;
+    g_class = KC_MLP_UP;
     MTX_TRY(launch_gemm<EPI_SWIGLU>(e->tm_w01[l], xm->n, gp, ea, plan_up, st));
 
     memset(&ea, 0, sizeof(ea));
@@ -395,8 +440,10 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     ea.ld_out = E;
     gp.n = E;
     gp.k = M;
+    g_class = KC_MLP_DOWN;
     MTX_TRY(launch_gemm<EPI_RESIDUAL>(e->tm_wout[l], xm->act, gp, ea, plan_down, st));
 
+    g_class = KC_RMSNORM;
     const bf16* next_scale = l + 1 < L ? attn_norm + size_t(l + 1) * E : static_cast<const bf16*>(e->w.final_norm);
     if (l + 1 < L || want_logits)
       MTX_TRY(launch(rmsnorm_kernel<false>, dim3(rows), dim3(128), 0, st, (const bf16*)e->x, (const int*)nullptr,
@@ -423,11 +470,14 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     ea.inv_temp = 1.0f / e->temperature;
     ea.round_bf16 = c.logits_round_bf16;
     ea.gumbel = e->strategy == MTX_SAMPLE_WEIGHTED ? 1 : 0;
+    ea.want_lse = e->s.log_prob != nullptr ? 1 : 0;
     ea.rng_state = e->s.rng_state;
     ea.row_offset = 0;
     gp.n = c.vocab_size;
     gp.k = E;
+    g_class = KC_LOGITS;
     MTX_TRY(launch_gemm<EPI_LOGITS>(e->tm_logits, xm->n, gp, ea, plan_logits, st));
+    g_class = KC_FINALIZE;
 
     FinalizeArgs fa;
     memset(&fa, 0, sizeof(fa));
@@ -464,6 +514,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
 extern "C" {
 
 const char* mtx_last_error(void) { return g_error.c_str(); }
+void mtx_debug_set_trace(void* device_buffer) { g_trace = static_cast<long long*>(device_buffer); }
 const char* mtx_build_info(void) { return "mtx_b200 sm_100a (tcgen05 + TMA + mbarrier), CUDA " MTX_STR(CUDART_VERSION); }
 uint64_t mtx_launch_count(void) { return g_launches.load(); }
 
@@ -528,8 +579,6 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   e->q = reinterpret_cast<bf16*>(b + L.q);
   e->attn = reinterpret_cast<bf16*>(b + L.attn);
   e->act = reinterpret_cast<bf16*>(b + L.act);
-  e->gemm_ws = reinterpret_cast<float*>(b + L.gemm_ws);
-  e->gemm_tickets = reinterpret_cast<int*>(b + L.gemm_tickets);
   e->attn_part_o = reinterpret_cast<float*>(b + L.attn_part_o);
   e->attn_part_ml = reinterpret_cast<float*>(b + L.attn_part_ml);
   e->attn_tickets = reinterpret_cast<int*>(b + L.attn_tickets);
@@ -568,9 +617,9 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   MTX_TRY(make_map(&e->tm_k, s->k_cache, c.head_dim, kv_rows, kAttnTileRows));
   MTX_TRY(make_map(&e->tm_v, s->v_cache, c.head_dim, kv_rows, kAttnTileRows));
   if (c.head_dim == 64)
-    MTX_CUDA(cudaFuncSetAttribute(decode_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_smem_bytes(64))));
+    MTX_CUDA(cudaFuncSetAttribute(decode_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_smem_bytes(64, 16))));
   else
-    MTX_CUDA(cudaFuncSetAttribute(decode_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_smem_bytes(128))));
+    MTX_CUDA(cudaFuncSetAttribute(decode_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_smem_bytes(128, 16))));
   e->bound = true;
   return MTX_OK;
 }
@@ -621,6 +670,29 @@ int mtx_decode_step_graph(mtx_engine* e, int rows, mtx_stream stream) {
   return MTX_OK;
 }
 
+int mtx_profile_decode_step(mtx_engine* e, int rows, mtx_stream stream, float* class_ms, int32_t* class_launches) {
+  if (!e || !e->bound || !class_ms || !class_launches) return fail(MTX_ERR_ARG, "bad profile arguments");
+  if (rows < 1 || rows > e->cfg.max_rows) return fail(MTX_ERR_ARG, "rows %d outside [1, %d]", rows, e->cfg.max_rows);
+  ProfileSink sink;
+  g_profile = &sink;
+  const int rc = enqueue_step(e, 0, rows, nullptr, 0, 0, 1, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+  g_profile = nullptr;
+  cudaError_t sync = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  for (int i = 0; i < KC_COUNT; ++i) { class_ms[i] = 0.f; class_launches[i] = 0; }
+  for (auto& r : sink.recs) {
+    float ms = 0.f;
+    if (sync == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      class_ms[r.cls] += ms;
+      class_launches[r.cls] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  if (rc != MTX_OK) return rc;
+  if (sync != cudaSuccess) return fail(MTX_ERR_CUDA, "cudaStreamSynchronize: %s", cudaGetErrorString(sync));
+  return MTX_OK;
+}
+
 int mtx_prefill_chunk(mtx_engine* e, const int32_t* tokens, int count, int start_pos, int slot, int sample_last,
                       int32_t* first_token, float* logits_out, mtx_stream stream) {
   if (!e || !e->bound) return fail(MTX_ERR_ARG, "engine is not bound");
@@ -640,27 +712,22 @@ int mtx_rmsnorm(const void* x, const void* scale, void* out, int rows, int emb_d
                 emb_dim, eps);
 }
 
-size_t mtx_linear_scratch_bytes(int rows, int n, int splits) {
-  const size_t n_tiles = (n + kTileN - 1) / kTileN;
-  return align_up(n_tiles * 4, 1024) + n_tiles * size_t(splits < 1 ? 1 : splits) * round_rows(rows) * kTileN * 4;
-}
-
-int mtx_linear(const void* x, const void* w, void* out, int rows, int n, int k, int splits, void* scratch, mtx_stream stream) {
+int mtx_linear(const void* x, const void* w, void* out, int rows, int n, int k, int splits, mtx_stream stream) {
   if (!x || !w || !out || rows < 1 || rows > 256 || n < 1 || k < 64 || k % 64 != 0) return fail(MTX_ERR_ARG, "bad linear arguments");
-  if (splits > 1 && scratch == nullptr) return fail(MTX_ERR_ARG, "split-K needs scratch");
   const int r_tile = round_rows(rows);
+  if (splits < 1) splits = 1;
+  if ((splits & (splits - 1)) != 0 || splits > 16 || splits > k / kBlockK || splits > r_tile)
+    return fail(MTX_ERR_ARG, "splits must be a power of two <= min(16, k/64, padded rows)");
   CUtensorMap tw, tx;
   MTX_TRY(make_map(&tw, w, k, n, kTileN));
   MTX_TRY(make_map(&tx, x, k, r_tile, r_tile));
-  const GemmPlan g = plan_gemm(n, k, r_tile, 148, splits < 1 ? 1 : splits);
+  const GemmPlan g = plan_gemm(n, k, r_tile, 148, EPI_STORE_BF16, splits);
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.n = n;
   p.k = k;
   p.rows = rows;
   p.r_tile = r_tile;
-  p.tickets = static_cast<int*>(scratch);
-  p.ws = scratch ? reinterpret_cast<float*>(static_cast<uint8_t*>(scratch) + align_up(size_t(g.n_tiles) * 4, 1024)) : nullptr;
   EpiArgs e;
   memset(&e, 0, sizeof(e));
   e.out = static_cast<bf16*>(out);
@@ -706,7 +773,7 @@ int mtx_decode_attention(const void* q, const void* k_cache, const void* v_cache
   p.part_o = reinterpret_cast<float*>(b);
   MTX_CUDA(cudaMemsetAsync(p.tickets, 0, ticket_bytes, st));
   MTX_TRY(launch(attn_build_worklist_kernel, dim3(1), dim3(256), 0, st, (const int*)len0, (const int*)ring_first, (const int*)ring_len,
-                 rows, max_prefill_len, max_target_len, work_items, work_count));
+                 rows, max_prefill_len, max_target_len, attn_tiles_per_item(rows, num_kv_heads, max_prefill_len, max_target_len, 148), work_items, work_count));
   CUtensorMap tk, tv;
   const uint64_t kv_rows = uint64_t(num_slots) * num_kv_heads * max_target_len;
   MTX_TRY(make_map(&tk, k_cache, head_dim, kv_rows, kAttnTileRows));
@@ -724,11 +791,13 @@ int mtx_decode_attention(const void* q, const void* k_cache, const void* v_cache
   p.hkv = num_kv_heads;
   p.P = max_prefill_len;
   p.T = max_target_len;
+  p.tiles_per_item = attn_tiles_per_item(rows, num_kv_heads, max_prefill_len, max_target_len, 148);
   p.max_chunks = int(mc);
   p.plane_base = 0;
   p.softcap = softcap;
-  const size_t smem = attn_smem_bytes(head_dim);
-  int grid = rows * num_kv_heads * int(mc);
+  p.trace = g_trace;
+  const size_t smem = attn_smem_bytes(head_dim, int(G));
+  int grid = rows * num_kv_heads * attn_max_chunks(max_prefill_len, max_target_len, p.tiles_per_item);
   const int cap = 148 * (head_dim == 64 ? 3 : 1);
   if (grid > cap) grid = cap;
   if (head_dim == 64) {

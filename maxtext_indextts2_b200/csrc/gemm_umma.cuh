@@ -10,9 +10,11 @@
 // mbarrier ring; one elected thread issues tcgen05.mma; the fp32 accumulator lives in
 // TMEM and is read back by four epilogue warps with tcgen05.ld.
 //
-// Small matrices are split along K over several CTAs; partial tiles go to an L2-resident
-// workspace and the last CTA to arrive (atomic ticket) sums them in split order -- the
-// result is deterministic -- and runs the epilogue.
+// Small matrices are split along K over the CTAs of one thread-block cluster.  Each CTA
+// parks its partial accumulator tile in its own shared memory; after a cluster barrier CTA c
+// sums rows [c*R/S, (c+1)*R/S) of all S partials over distributed shared memory (fixed
+// order, so the result is deterministic) and runs the epilogue for that slice -- a
+// reduce-scatter with no global-memory round trip and no straggler.
 //
 // Programmatic dependent launch: the producer prefetches weight tiles (which no other
 // kernel writes) before griddepcontrol.wait, so the HBM stream of kernel n+1 starts while
@@ -30,6 +32,8 @@ constexpr int kWTileBytes = kTileN * kBlockK * 2;
 constexpr int kMaxStages = 8;
 constexpr int kGemmThreads = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 constexpr int kEpiThreads = 128;
+constexpr int kPartialPitch = 132;  // fp32 words per row of a parked partial tile (conflict-free, 16-byte aligned)
+constexpr int kLogitPitch = 129;    // fp32 words per row of the transposed logits tile
 
 enum Epilogue : int {
   EPI_STORE_BF16 = 0,  // out[r, n] = bf16(acc)                               (mtx_linear, tests)
@@ -44,10 +48,9 @@ struct GemmParams {
   int k;        // reduction length (multiple of 64)
   int rows;     // valid activation rows
   int r_tile;   // UMMA N: rows rounded up to 16/32/64/128/256
-  int splits;   // K splits (grid.y)
+  int splits;   // K splits = cluster size along y (1, 2, 4, 8 or 16)
   int stages;   // smem ring depth
-  float* ws;    // [n_tiles * splits][r_tile][128] fp32 partials (splits > 1)
-  int* tickets; // [n_tiles] arrival counters, zero between launches
+  long long* trace;  // debug: clock64 timeline of CTA (0,0), 128 slots, or null
 };
 
 struct EpiArgs {
@@ -70,36 +73,52 @@ struct EpiArgs {
   float* part_score;   // [rows, n_tiles] best (possibly Gumbel-perturbed) score in the tile
   int* part_idx;       // [rows, n_tiles] its global vocab id
   float* part_raw;     // [rows, n_tiles] its unperturbed logit
-  float* part_max;     // [rows, n_tiles] max logit in the tile
-  float* part_sum;     // [rows, n_tiles] sum exp(logit - max)
+  float* part_max;     // [rows, n_tiles] max logit in the tile           (want_lse)
+  float* part_sum;     // [rows, n_tiles] sum exp(logit - max)            (want_lse)
   int n_tiles;
   int vocab_offset;
   float scale, softcap, inv_temp;
   int round_bf16;
   int gumbel;          // 1 = add Gumbel noise (weighted sampling)
+  int want_lse;        // 1 = also produce the log-sum-exp partials (return_log_prob)
   const uint32_t* rng_state;  // [4]: step, seed_lo, seed_hi, unused (device memory: graph replays see updates)
   int row_offset;
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-// ---- epilogues: thread owns weight row n (n_local in the tile) and 16 consecutive rows r ----
+// ---- thread-block cluster helpers ----
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 
-__device__ __forceinline__ void epi_store_bf16(const EpiArgs& e, const GemmParams& p, const float (&v)[16], int r0, int n) {
+// ---- epilogues: thread owns weight row n (n_local in the tile) and rows r0 .. r0+15, valid while r < r_lim ----
+
+__device__ __forceinline__ void epi_store_bf16(const EpiArgs& e, const GemmParams& p, const float (&v)[16], int r0, int r_lim, int n) {
   if (n >= p.n) return;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const int r = r0 + j;
-    if (r < p.rows) e.out[(long long)r * e.ld_out + n] = __float2bfloat16_rn(v[j]);
+    if (r < r_lim) e.out[(long long)r * e.ld_out + n] = __float2bfloat16_rn(v[j]);
   }
 }
 
-__device__ __forceinline__ void epi_residual(const EpiArgs& e, const GemmParams& p, const float (&v)[16], int r0, int n) {
+__device__ __forceinline__ void epi_residual(const EpiArgs& e, const GemmParams& p, const float (&v)[16], int r0, int r_lim, int n) {
   if (n >= p.n) return;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const int r = r0 + j;
-    if (r < p.rows) {
+    if (r < r_lim) {
       const long long o = (long long)r * e.ld_out + n;
       e.out[o] = __float2bfloat16_rn(__bfloat162float(e.resid[o]) + bf16r(v[j]));
     }
@@ -107,7 +126,7 @@ __device__ __forceinline__ void epi_residual(const EpiArgs& e, const GemmParams&
 }
 
 // linears.py:425-476 with mlp_activations [silu, linear]; every intermediate is a bf16 array there.
-__device__ __forceinline__ void epi_swiglu(const EpiArgs& e, const GemmParams& p, const float (&v)[16], int r0, int n, int lane) {
+__device__ __forceinline__ void epi_swiglu(const EpiArgs& e, const GemmParams& p, const float (&v)[16], int r0, int r_lim, int n, int lane) {
   const int m = (n >> 5) * 16 + (lane & 15);
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -117,14 +136,14 @@ __device__ __forceinline__ void epi_swiglu(const EpiArgs& e, const GemmParams& p
     const float sg = bf16r(1.0f / (1.0f + expf(-a)));
     const float act = bf16r(a * sg);
     const int r = r0 + j;
-    if (lane < 16 && r < p.rows && n < p.n) e.out[(long long)r * e.ld_out + m] = __float2bfloat16_rn(act * b);
+    if (lane < 16 && r < r_lim && n < p.n) e.out[(long long)r * e.ld_out + m] = __float2bfloat16_rn(act * b);
   }
 }
 
 // embeddings.py:304-315 (half-split rotation, bf16 arithmetic) + kvcache.py:626-718 (append).
 // `exch` is a [128][17] fp32 exchange buffer: the rotation partner of feature d is d +- D/2,
 // which lives in another epilogue warp.
-__device__ __forceinline__ void epi_qkv_rope(const EpiArgs& e, const GemmParams& p, const float (&v)[16], int r0, int n,
+__device__ __forceinline__ void epi_qkv_rope(const EpiArgs& e, const GemmParams& p, const float (&v)[16], int r0, int r_lim, int n,
                                               int n_local, float* exch) {
   const int D = e.d, half = D >> 1;
   const int head = n / D, d = n - head * D;
@@ -143,7 +162,7 @@ __device__ __forceinline__ void epi_qkv_rope(const EpiArgs& e, const GemmParams&
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const int r = r0 + j;
-    if (r >= p.rows || n >= p.n) continue;
+    if (r >= r_lim || n >= p.n) continue;
     float val = own[j];
     if (rot) {
       const float other = exch[partner * 17 + j];
@@ -167,64 +186,96 @@ __device__ __forceinline__ void epi_qkv_rope(const EpiArgs& e, const GemmParams&
   epi_bar_sync();
 }
 
-// decoders.py:537-589 (logits) + inference_utils.py:66-84 (greedy / weighted as Gumbel arg-max)
-// + inference_utils.py:55-63 (log-sum-exp partials).  `red` is [4][16][5] fp32 scratch.
-__device__ __forceinline__ void epi_logits(const EpiArgs& e, const GemmParams& p, const float (&v)[16], int r0, int n, int lane,
-                                            int quarter, int epi_tid, int tile, float* red) {
+// decoders.py:537-589: logits = bf16(dot) (* 1/sqrt(E) when tied), optional tanh soft cap, fp32.
+__device__ __forceinline__ float logit_transform(const EpiArgs& e, float acc) {
+  float lg = e.round_bf16 ? bf16r(acc) : acc;
+  lg *= e.scale;
+  if (e.softcap != 0.0f) lg = tanhf(lg / e.softcap) * e.softcap;
+  return lg;
+}
+
+// Logits epilogue for one group of up to 64 rows: the 128 x RG tile is transposed through shared
+// memory so that each thread then scans a contiguous run of vocabulary entries of ONE row --
+// arg-max with the lowest index winning ties (jnp.argmax, inference_utils.py:76), optionally on
+// Gumbel-perturbed scores (jax.random.categorical, :78), and optionally the (max, sum exp)
+// pair for log-softmax (:55-63).  `lt` / `st` are [RG][129] fp32 tiles, `comb` is [8][64][5].
+__device__ __forceinline__ void epi_logits_group(const EpiArgs& e, const GemmParams& p, uint32_t taddr, int g0, int RG, int n,
+                                                 int n_local, int epi_tid, int tile, float* lt, float* st, float* comb) {
   const bool valid = n < p.n;
   const int gid = e.vocab_offset + n;
-  const uint32_t step = e.gumbel ? e.rng_state[0] : 0u;
-  const uint64_t seed = e.gumbel ? (uint64_t(e.rng_state[2]) << 32) | e.rng_state[1] : 0ull;
+  uint32_t step = 0;
+  uint64_t seed = 0;
+  if (e.gumbel) {
+    step = e.rng_state[0];
+    seed = (uint64_t(e.rng_state[2]) << 32) | e.rng_state[1];
+  }
+  for (int c = 0; c < RG / 16; ++c) {
+    float v[16];
+    tmem_ld_x16(taddr + uint32_t(g0 + c * 16), v);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int r = r0 + j;
-    if (r >= p.rows) continue;  // warp-uniform: every lane of the warp shares r
-    float lg = v[j];
-    if (e.round_bf16) lg = bf16r(lg);
-    lg *= e.scale;
-    if (e.softcap != 0.0f) lg = tanhf(lg / e.softcap) * e.softcap;
-    if (e.logits_out != nullptr && valid) {
-      if (e.logits_only_row < 0) e.logits_out[(long long)r * e.ld_logits + n] = lg;
-      else if (r == e.logits_only_row) e.logits_out[n] = lg;
-    }
-    float raw = valid ? lg : -INFINITY;
-    float score = raw;
-    if (e.gumbel && valid) score = lg * e.inv_temp + gumbel_noise(seed, step, uint32_t(e.row_offset + r), uint32_t(gid));
-    int idx = gid;
-    float mx = raw;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float s2 = __shfl_xor_sync(0xffffffffu, score, o);
-      const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
-      const float r2 = __shfl_xor_sync(0xffffffffu, raw, o);
-      if (s2 > score || (s2 == score && i2 < idx)) { score = s2; idx = i2; raw = r2; }
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    }
-    float ex = valid ? expf(lg - mx) : 0.0f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ex += __shfl_xor_sync(0xffffffffu, ex, o);
-    if (lane == 0) {
-      float* t = red + (quarter * 16 + j) * 5;
-      t[0] = score; t[1] = __int_as_float(idx); t[2] = raw; t[3] = mx; t[4] = ex;
+    for (int j = 0; j < 16; ++j) {
+      const int rl = c * 16 + j;  // row within the group
+      const int r = g0 + rl;
+      float lg = -INFINITY, sc = -INFINITY;
+      if (valid && r < p.rows) {
+        lg = logit_transform(e, v[j]);
+        if (e.logits_out != nullptr) {
+          if (e.logits_only_row < 0) e.logits_out[(long long)r * e.ld_logits + n] = lg;
+          else if (r == e.logits_only_row) e.logits_out[n] = lg;
+        }
+        sc = e.gumbel ? lg * e.inv_temp + gumbel_noise(seed, step, uint32_t(e.row_offset + r), uint32_t(gid)) : lg;
+      }
+      lt[rl * kLogitPitch + n_local] = lg;
+      if (e.gumbel) st[rl * kLogitPitch + n_local] = sc;
     }
   }
   epi_bar_sync();
-  if (epi_tid < 16 && r0 + epi_tid < p.rows) {
-    float score = -INFINITY, raw = -INFINITY, mx = -INFINITY, sum = 0.0f;
+  // thread -> (row, part): a warp covers 32 consecutive rows of one part, so the scans are conflict-free
+  const int nparts = kEpiThreads / RG, span = kTileN / nparts;
+  const int rl = epi_tid % RG, part = epi_tid / RG;
+  const float* lrow = lt + rl * kLogitPitch + part * span;
+  const float* srow = (e.gumbel ? st : lt) + rl * kLogitPitch + part * span;
+  float best = -INFINITY, raw = -INFINITY, mx = -INFINITY, sum = 0.0f;
+  int bi = 0;
+  for (int i = 0; i < span; ++i) {
+    const float s = srow[i];
+    if (s > best) { best = s; bi = i; }  // strict: the first (lowest-index) maximum is kept
+  }
+  raw = lrow[bi];
+  if (e.want_lse) {
+    for (int i = 0; i < span; ++i) mx = fmaxf(mx, lrow[i]);
+    if (mx > -INFINITY)
+      for (int i = 0; i < span; ++i) sum += expf(lrow[i] - mx);
+  }
+  float* cb = comb + (part * 64 + rl) * 5;
+  cb[0] = best; cb[1] = __int_as_float(e.vocab_offset + tile * kTileN + part * span + bi); cb[2] = raw; cb[3] = mx; cb[4] = sum;
+  epi_bar_sync();
+  if (epi_tid < RG && g0 + epi_tid < p.rows) {
+    best = -INFINITY; raw = -INFINITY; mx = -INFINITY; sum = 0.0f;
     int idx = 0x7fffffff;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float* t = red + (q * 16 + epi_tid) * 5;
-      const int i2 = __float_as_int(t[1]);
-      if (t[0] > score || (t[0] == score && i2 < idx)) { score = t[0]; idx = i2; raw = t[2]; }
-      const float m2 = fmaxf(mx, t[3]);
-      if (m2 > -INFINITY) sum = sum * expf(mx - m2) + t[4] * expf(t[3] - m2);
-      mx = m2;
+    for (int q = 0; q < nparts; ++q) {  // parts are in increasing vocabulary order: strict > keeps the lowest index
+      const float* t = comb + (q * 64 + epi_tid) * 5;
+      if (t[0] > best) { best = t[0]; idx = __float_as_int(t[1]); raw = t[2]; }
+      if (e.want_lse) {
+        const float m2 = fmaxf(mx, t[3]);
+        if (m2 > -INFINITY) sum = sum * expf(mx - m2) + t[4] * expf(t[3] - m2);
+        mx = m2;
+      }
     }
-    const long long o = (long long)(r0 + epi_tid) * e.n_tiles + tile;
-    e.part_score[o] = score; e.part_idx[o] = idx; e.part_raw[o] = raw; e.part_max[o] = mx; e.part_sum[o] = sum;
+    const long long o = (long long)(g0 + epi_tid) * e.n_tiles + tile;
+    e.part_score[o] = best; e.part_idx[o] = idx; e.part_raw[o] = raw;
+    if (e.want_lse) { e.part_max[o] = mx; e.part_sum[o] = sum; }
   }
   epi_bar_sync();
+}
+
+template <int EPI>
+__device__ __forceinline__ void run_epilogue(const EpiArgs& e, const GemmParams& p, const float (&v)[16], int r0, int r_lim, int n,
+                                             int n_local, int lane, float* exch) {
+  if (EPI == EPI_STORE_BF16) epi_store_bf16(e, p, v, r0, r_lim, n);
+  if (EPI == EPI_RESIDUAL) epi_residual(e, p, v, r0, r_lim, n);
+  if (EPI == EPI_SWIGLU) epi_swiglu(e, p, v, r0, r_lim, n, lane);
+  if (EPI == EPI_QKV_ROPE) epi_qkv_rope(e, p, v, r0, r_lim, n, n_local, exch);
 }
 
 // ---- the kernel -------------------------------------------------------------------------
@@ -234,11 +285,21 @@ struct GemmSmemTail {
   uint64_t empty[kMaxStages];
   uint64_t tmem_full;
   uint32_t tmem_base;
-  uint32_t is_last;
+  uint32_t pad;
 };
 
-__host__ __device__ inline size_t gemm_smem_bytes(int stages, int r_tile) {
-  return 1024 + size_t(stages) * (kWTileBytes + r_tile * kBlockK * 2) + sizeof(GemmSmemTail) + 16;
+// Shared memory after the 1024-byte alignment slack: max(pipeline stages, epilogue scratch) + tail.
+__host__ __device__ inline size_t gemm_main_region_bytes(int stages, int r_tile, int splits, int epi) {
+  size_t pipe = size_t(stages) * (kWTileBytes + r_tile * kBlockK * 2);
+  size_t scratch = 0;
+  if (splits > 1) scratch += size_t(r_tile) * kPartialPitch * 4;  // parked partial tile
+  if (epi == EPI_QKV_ROPE) scratch += 128 * 17 * 4;               // rotation exchange
+  if (epi == EPI_LOGITS) scratch += 2 * 64 * kLogitPitch * 4 + 8 * 64 * 5 * 4;
+  size_t m = pipe > scratch ? pipe : scratch;
+  return (m + 1023) / 1024 * 1024;
+}
+__host__ __device__ inline size_t gemm_smem_bytes(int stages, int r_tile, int splits, int epi) {
+  return 1024 + gemm_main_region_bytes(stages, r_tile, splits, epi) + sizeof(GemmSmemTail) + 16;
 }
 
 template <int EPI>
@@ -248,10 +309,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int x_tile_bytes = p.r_tile * kBlockK * 2;
   const int stage_bytes = kWTileBytes + x_tile_bytes;
-  GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(smem + size_t(p.stages) * stage_bytes);
+  GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(smem + gemm_main_region_bytes(p.stages, p.r_tile, p.splits, EPI));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x, split = blockIdx.y;
+  const int tile = blockIdx.x, split = blockIdx.y;  // split == rank in the (1, splits, 1) cluster
   const int n0 = tile * kTileN;
   const int kb_total = p.k / kBlockK;
   const int kb0 = int((long long)split * kb_total / p.splits);
@@ -260,6 +321,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   const uint32_t tmem_cols = p.r_tile < 32 ? 32u : uint32_t(p.r_tile);
 
   griddep_launch_dependents();
+  long long* trace = (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) ? p.trace : nullptr;
+  const long long t_start = clock64();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_w);
@@ -284,21 +347,25 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     // ===== TMA producer =====
     if (lane == 0) {
       const int pre = nkb < p.stages ? nkb : p.stages;
+      if (trace) trace[0] = clock64() - t_start;
       for (int i = 0; i < pre; ++i) {  // weights do not depend on the previous kernel
         mbar_expect_tx(&tail->full[i], uint32_t(stage_bytes));
         tma_load_2d(smem + size_t(i) * stage_bytes, &tm_w, (kb0 + i) * kBlockK, n0, &tail->full[i], kEvictFirst);
       }
       griddep_wait();
+      if (trace) trace[1] = clock64() - t_start;
       for (int i = 0; i < pre; ++i)
         tma_load_2d(smem + size_t(i) * stage_bytes + kWTileBytes, &tm_x, (kb0 + i) * kBlockK, 0, &tail->full[i], kEvictLast);
       for (int i = pre; i < nkb; ++i) {
         const int s = i % p.stages;
         mbar_wait(&tail->empty[s], ((i / p.stages) & 1) ^ 1);
+        if (trace && i < 30) trace[2 + i] = clock64() - t_start;
         mbar_expect_tx(&tail->full[s], uint32_t(stage_bytes));
         tma_load_2d(smem + size_t(s) * stage_bytes, &tm_w, (kb0 + i) * kBlockK, n0, &tail->full[s], kEvictFirst);
         tma_load_2d(smem + size_t(s) * stage_bytes + kWTileBytes, &tm_x, (kb0 + i) * kBlockK, 0, &tail->full[s], kEvictLast);
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
@@ -307,6 +374,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         const int s = i % p.stages;
         mbar_wait(&tail->full[s], (i / p.stages) & 1);
         tcgen05_fence_after();
+        if (trace && i < 30) trace[40 + i] = clock64() - t_start;
         const uint64_t da = umma_desc_sw128(smem + size_t(s) * stage_bytes);
         const uint64_t db = umma_desc_sw128(smem + size_t(s) * stage_bytes + kWTileBytes);
 #pragma unroll
@@ -315,67 +383,92 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         umma_commit(&tail->empty[s]);
       }
       umma_commit(&tail->tmem_full);
+      if (trace) trace[39] = clock64() - t_start;
     }
     __syncwarp();
-  } else {
-    // ===== epilogue: warps 2..5 own TMEM lane quarters 2,3,0,1 =====
-    const int quarter = warp & 3;
-    const int n_local = quarter * 32 + lane;
-    const int epi_tid = threadIdx.x - 64;
-    const int n = n0 + n_local;
-    float* scratch = reinterpret_cast<float*>(smem);  // stage memory is free once tmem_full fires
+  }
+
+  // ===== epilogue: warps 2..5 own TMEM lane quarters 2,3,0,1 =====
+  const int quarter = warp & 3;
+  const int n_local = quarter * 32 + lane;
+  const int epi_tid = threadIdx.x - 64;
+  const int n = n0 + n_local;
+  const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16);
+  float* scratch = reinterpret_cast<float*>(smem);  // pipeline stages are free once tmem_full fires
+  if (warp >= 2) {
     mbar_wait(&tail->tmem_full, 0);
     tcgen05_fence_after();
     griddep_wait();
-    const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16);
-    const int chunks = p.r_tile / 16;
-    bool run_epilogue = true;
-    if (p.splits > 1) {
-      float* mine = p.ws + ((size_t)(tile * p.splits + split) * p.r_tile) * kTileN;
-      for (int c = 0; c < chunks; ++c) {
+    if (trace && epi_tid == 0) trace[80] = clock64() - t_start;
+  }
+
+  if (EPI == EPI_LOGITS) {
+    if (warp >= 2) {
+      float* lt = scratch;
+      float* st = lt + 64 * kLogitPitch;
+      float* comb = st + 64 * kLogitPitch;
+      const int RG = p.r_tile < 64 ? p.r_tile : 64;
+      for (int g0 = 0; g0 < p.r_tile && g0 < p.rows; g0 += RG)
+        epi_logits_group(e, p, taddr, g0, RG, n, n_local, epi_tid, tile, lt, st, comb);
+    }
+  } else if (p.splits == 1) {
+    if (warp >= 2) {
+      for (int c = 0; c < p.r_tile / 16 && c * 16 < p.rows; ++c) {
+        float v[16];
+        tmem_ld_x16(taddr + uint32_t(c * 16), v);
+        run_epilogue<EPI>(e, p, v, c * 16, p.rows, n, n_local, lane, scratch);
+      }
+    }
+  } else {
+    // ---- split-K: park the partial tile, cluster barrier, reduce-scatter over DSMEM ----
+    float* partial = scratch;                                // [r_tile][kPartialPitch]
+    float* exch = scratch + p.r_tile * kPartialPitch;        // not aliased: peers read `partial` during the epilogue
+    if (warp >= 2) {
+      for (int c = 0; c < p.r_tile / 16; ++c) {
         float v[16];
         tmem_ld_x16(taddr + uint32_t(c * 16), v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) __stcg(mine + (size_t)(c * 16 + j) * kTileN + n_local, v[j]);
+        for (int j = 0; j < 16; ++j) partial[(c * 16 + j) * kPartialPitch + n_local] = v[j];
       }
-      __threadfence();
-      epi_bar_sync();
-      if (epi_tid == 0) {
-        const int old = atomicAdd(p.tickets + tile, 1);
-        const bool last = old == p.splits - 1;
-        if (last) p.tickets[tile] = 0;
-        tail->is_last = last ? 1u : 0u;
-      }
-      epi_bar_sync();
-      run_epilogue = tail->is_last != 0;
-      if (run_epilogue) __threadfence();
     }
-    if (run_epilogue) {
-      for (int c = 0; c < chunks; ++c) {
+    cluster_sync_all();
+    if (warp >= 2) {
+      const int rpc = p.r_tile / p.splits;  // rows reduced and finished by this CTA
+      const int r_begin = split * rpc;
+      const int r_lim = min(p.rows, r_begin + rpc);
+      const uint32_t my = smem_u32(partial);
+      for (int r0 = r_begin; r0 < r_begin + rpc && r0 < p.rows; r0 += 16) {
         float v[16];
-        if (p.splits > 1) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.0f;
-          for (int s = 0; s < p.splits; ++s) {
-            const float* part = p.ws + ((size_t)(tile * p.splits + s) * p.r_tile + c * 16) * kTileN + n_local;
+        for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+        // remote loads are issued in batches of up to 64 before any of them is consumed (latency ~200
+        // cycles each); the sum itself runs in split order, so the result does not depend on timing
+        for (int s0 = 0; s0 < p.splits; s0 += 4) {
+          float t[4][16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += ldcg_f32(part + (size_t)j * kTileN);
+          for (int ss = 0; ss < 4; ++ss) {
+            const uint32_t peer = dsmem_addr(my, uint32_t(min(s0 + ss, p.splits - 1)));
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              t[ss][j] = 0.0f;
+              if (s0 + ss < p.splits && r0 + j < r_begin + rpc)
+                t[ss][j] = ld_dsmem_f32(peer + uint32_t(((r0 + j) * kPartialPitch + n_local) * 4));
+            }
           }
-        } else {
-          tmem_ld_x16(taddr + uint32_t(c * 16), v);
+#pragma unroll
+          for (int ss = 0; ss < 4; ++ss)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += t[ss][j];
         }
-        const int r0 = c * 16;
-        if (EPI == EPI_STORE_BF16) epi_store_bf16(e, p, v, r0, n);
-        if (EPI == EPI_RESIDUAL) epi_residual(e, p, v, r0, n);
-        if (EPI == EPI_SWIGLU) epi_swiglu(e, p, v, r0, n, lane);
-        if (EPI == EPI_QKV_ROPE) epi_qkv_rope(e, p, v, r0, n, n_local, scratch);
-        if (EPI == EPI_LOGITS) epi_logits(e, p, v, r0, n, lane, quarter, epi_tid, tile, scratch);
+        run_epilogue<EPI>(e, p, v, r0, r_lim, n, n_local, lane, exch);
       }
     }
+    cluster_sync_all();  // keep every CTA's partial alive until all peers have read it
   }
 
   tcgen05_fence_before();
   __syncthreads();
+  if (trace && threadIdx.x == 64) trace[81] = clock64() - t_start;
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 

@@ -32,6 +32,7 @@ struct PrepareArgs {
   const int* chunk_tokens;  // [count]
   int start_pos, slot;
   int mode, rows, P, T, D;
+  int tiles_per_item;  // attention work-item size (attn_tiles_per_item)
   const float* rope_timescale;  // [D/2] min * (max/min)^(2i/D), embeddings.py:270-275
 };
 
@@ -39,6 +40,7 @@ struct PrepareArgs {
 // (embeddings.py:304-307: sin/cos of position / timescale, cast to bf16) and the attention work list.
 __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
   __shared__ int s_off[257];
+  __shared__ int s_pos[256];
   griddep_launch_dependents();
   griddep_wait();
   const int tid = threadIdx.x;
@@ -72,16 +74,20 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
     rd.len0[tid] = l0;
     rd.ring_first[tid] = rf;
     rd.ring_len[tid] = rl;
-    chunks = (attn_num_tiles(l0, rf, rl, R) + kAttnWarps - 1) / kAttnWarps;
-    const int half = a.D / 2;
-    for (int i = 0; i < half; ++i) {
-      const float ang = float(pos) / a.rope_timescale[i];
-      rd.rope_cs[tid * half + i] = make_float2(bf16r(cosf(ang)), bf16r(sinf(ang)));
-    }
+    chunks = (attn_num_tiles(l0, rf, rl, R) + a.tiles_per_item - 1) / a.tiles_per_item;
+    s_pos[tid] = pos;
   }
   s_off[tid + 1] = chunks;
   if (tid == 0) s_off[0] = 0;
   __syncthreads();
+  {  // RoPE table, all threads: (row, frequency) pairs
+    const int half = a.D / 2;
+    for (int idx = tid; idx < a.rows * half; idx += 256) {
+      const int r = idx / half, i = idx - r * half;
+      const float ang = float(s_pos[r]) / a.rope_timescale[i];
+      rd.rope_cs[idx] = make_float2(bf16r(cosf(ang)), bf16r(sinf(ang)));
+    }
+  }
   if (tid == 0)
     for (int i = 1; i <= 256; ++i) s_off[i] += s_off[i - 1];
   __syncthreads();
