@@ -183,6 +183,9 @@ const char* mtx_build_info(void);
 /* Debug aid: when non-NULL (device memory, 256 x int64), the GEMM and attention kernels record
  * a clock64 timeline of their first CTA into it.  NULL (the default) switches it off. */
 void mtx_debug_set_trace(void* device_buffer);
+/* Debug aid: when non-NULL (device memory, 3004+ x uint64, zeroed), every kernel's first CTA appends
+ * (kind, start ns, end ns) by %globaltimer; [0] counts the entries. */
+int mtx_debug_set_timeline(void* device_buffer);
 /* Kernels launched by this library since load (all engines); used by bench.py's gpu_launches. */
 uint64_t mtx_launch_count(void);
 

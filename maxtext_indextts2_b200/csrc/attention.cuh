@@ -148,6 +148,7 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   uint64_t* bar_v = bar_k + 1;
   const uint32_t kb = smem_u32(k_tile), vb = smem_u32(v_tile);
 
+  const int tl = timeline_begin(3);
   griddep_launch_dependents();
   if (lane == 0) {
     mbar_init(bar_k, 1);
@@ -401,6 +402,7 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
     if (trace && iter < 15) trace[iter * 8 + 7] = clock64() - t_start;
     ++iter;
   }
+  timeline_end(tl);
 }
 
 __host__ inline size_t attn_smem_bytes(int D, int G) {

@@ -34,6 +34,32 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float ldcg_f32(const float* p) { return __ldcg(p); }
 
 // ---------------------------------------------------------------------------------
+// debug timeline: (kind, start ns, end ns) of the first CTA of every kernel of a step
+// ---------------------------------------------------------------------------------
+
+__device__ unsigned long long* d_timeline = nullptr;  // [0] = entry counter, entries from [4]
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int timeline_begin(int kind) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && d_timeline != nullptr) {
+    const int idx = int(atomicAdd(d_timeline, 1ull));
+    if (idx < 1000) {
+      d_timeline[4 + 3 * idx] = kind;
+      d_timeline[4 + 3 * idx + 1] = globaltimer_ns();
+      return idx;
+    }
+  }
+  return -1;
+}
+__device__ __forceinline__ void timeline_end(int idx) {
+  if (idx >= 0) d_timeline[4 + 3 * idx + 2] = globaltimer_ns();
+}
+
+// ---------------------------------------------------------------------------------
 // programmatic dependent launch
 // ---------------------------------------------------------------------------------
 

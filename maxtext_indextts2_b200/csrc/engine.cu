@@ -14,6 +14,7 @@
 #include "../../include/mtx_b200.h"
 #include "attention.cuh"
 #include "gemm_umma.cuh"
+#include "sampling.cuh"
 #include "step_kernels.cuh"
 
 using namespace mtx;
@@ -451,8 +452,9 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   }
 
   if (want_logits) {
-    if (e->strategy == MTX_SAMPLE_NUCLEUS || e->strategy == MTX_SAMPLE_TOPK)
-      return fail(MTX_ERR_UNSUPPORTED, "nucleus / topk sampling are not fused yet: use the host sampler on materialised logits");
+    const bool two_pass = e->strategy == MTX_SAMPLE_NUCLEUS || e->strategy == MTX_SAMPLE_TOPK;
+    if (two_pass && (mode == 0 ? e->s.logits == nullptr : prefill_logits == nullptr))
+      return fail(MTX_ERR_ARG, "nucleus / topk sampling read the materialised logits: decode_state.logits (or logits_out) must be set");
     EpiArgs ea;
     memset(&ea, 0, sizeof(ea));
     ea.logits_out = mode == 0 ? e->s.logits : prefill_logits;
@@ -470,7 +472,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     ea.inv_temp = 1.0f / e->temperature;
     ea.round_bf16 = c.logits_round_bf16;
     ea.gumbel = e->strategy == MTX_SAMPLE_WEIGHTED ? 1 : 0;
-    ea.want_lse = e->s.log_prob != nullptr ? 1 : 0;
+    ea.want_lse = (e->s.log_prob != nullptr && !two_pass) ? 1 : 0;
     ea.rng_state = e->s.rng_state;
     ea.row_offset = 0;
     gp.n = c.vocab_size;
@@ -488,7 +490,33 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     fa.part_sum = e->part_sum;
     fa.n_tiles = plan_logits.n_tiles;
     fa.rows = rows;
+    int finalize_rows = rows;
+    if (two_pass) {
+      // inference_utils.py:87-111 on the logits the GEMM just wrote; one candidate per row
+      SampleArgs sa;
+      memset(&sa, 0, sizeof(sa));
+      sa.logits = mode == 0 ? e->s.logits : prefill_logits;
+      sa.ld = c.vocab_size;
+      sa.vocab = c.vocab_size;
+      sa.vocab_offset = c.vocab_offset;
+      sa.mode = e->strategy;
+      sa.top_k = e->top_k;
+      sa.nucleus_p = e->nucleus_p;
+      sa.inv_temp = 1.0f / e->temperature;
+      sa.rng_state = e->s.rng_state;
+      sa.row_offset = mode == 0 ? 0 : rows - 1;
+      sa.out_score = e->part_score;
+      sa.out_idx = e->part_idx;
+      sa.out_raw = e->part_raw;
+      sa.out_max = e->part_max;
+      sa.out_sum = e->part_sum;
+      finalize_rows = mode == 0 ? rows : 1;
+      MTX_TRY(launch(sample_rows_kernel, dim3(finalize_rows), dim3(kSampleThreads), 0, st, sa));
+      fa.n_tiles = 1;
+      fa.rows = finalize_rows;
+    }
     fa.mode = mode;
+    fa.have_lse = (two_pass || e->s.log_prob != nullptr) ? 1 : 0;
     fa.tokens = e->s.tokens;
     fa.next_pos = e->s.next_pos;
     fa.generated = e->s.generated;
@@ -500,7 +528,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     fa.num_slots = c.num_slots;
     fa.R = c.max_target_len - c.max_prefill_len;
     fa.first_token = first_token;
-    MTX_TRY(launch(finalize_kernel, dim3(rows), dim3(128), 0, st, fa));
+    MTX_TRY(launch(finalize_kernel, dim3(finalize_rows), dim3(128), 0, st, fa));
   }
   return MTX_OK;
 }
@@ -515,6 +543,11 @@ extern "C" {
 
 const char* mtx_last_error(void) { return g_error.c_str(); }
 void mtx_debug_set_trace(void* device_buffer) { g_trace = static_cast<long long*>(device_buffer); }
+int mtx_debug_set_timeline(void* device_buffer) {
+  unsigned long long* p = static_cast<unsigned long long*>(device_buffer);
+  MTX_CUDA(cudaMemcpyToSymbol(d_timeline, &p, sizeof(p)));
+  return MTX_OK;
+}
 const char* mtx_build_info(void) { return "mtx_b200 sm_100a (tcgen05 + TMA + mbarrier), CUDA " MTX_STR(CUDART_VERSION); }
 uint64_t mtx_launch_count(void) { return g_launches.load(); }
 

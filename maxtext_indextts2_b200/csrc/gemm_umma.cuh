@@ -96,6 +96,11 @@ __device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_addr, uint32_t cta
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
   return r;
 }
+__device__ __forceinline__ float4 ld_dsmem_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ float ld_dsmem_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
@@ -292,8 +297,8 @@ struct GemmSmemTail {
 __host__ __device__ inline size_t gemm_main_region_bytes(int stages, int r_tile, int splits, int epi) {
   size_t pipe = size_t(stages) * (kWTileBytes + r_tile * kBlockK * 2);
   size_t scratch = 0;
-  if (splits > 1) scratch += size_t(r_tile) * kPartialPitch * 4;  // parked partial tile
-  if (epi == EPI_QKV_ROPE) scratch += 128 * 17 * 4;               // rotation exchange
+  if (splits > 1) scratch += size_t(r_tile) * kPartialPitch * 4 + 128 * 17 * 4 + size_t(r_tile / splits) * kPartialPitch * 4;  // parked partial, exchange, reduced slice
+  else if (epi == EPI_QKV_ROPE) scratch += 128 * 17 * 4;          // rotation exchange
   if (epi == EPI_LOGITS) scratch += 2 * 64 * kLogitPitch * 4 + 8 * 64 * 5 * 4;
   size_t m = pipe > scratch ? pipe : scratch;
   return (m + 1023) / 1024 * 1024;
@@ -320,6 +325,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   const int nkb = kb1 - kb0;
   const uint32_t tmem_cols = p.r_tile < 32 ? 32u : uint32_t(p.r_tile);
 
+  const int tl = timeline_begin(10 + EPI);
   griddep_launch_dependents();
   long long* trace = (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) ? p.trace : nullptr;
   const long long t_start = clock64();
@@ -431,44 +437,53 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         for (int j = 0; j < 16; ++j) partial[(c * 16 + j) * kPartialPitch + n_local] = v[j];
       }
     }
+    if (trace && epi_tid == 0) trace[82] = clock64() - t_start;
     cluster_sync_all();
+    if (trace && epi_tid == 0) trace[83] = clock64() - t_start;
     if (warp >= 2) {
       const int rpc = p.r_tile / p.splits;  // rows reduced and finished by this CTA
       const int r_begin = split * rpc;
       const int r_lim = min(p.rows, r_begin + rpc);
       const uint32_t my = smem_u32(partial);
+      // Pull phase: 16-byte remote loads, one float4 column group of one row per thread and
+      // peer, all peers in flight at once; the sum runs in split order (deterministic).
+      float* reduced = exch + 128 * 17;  // [rpc][kPartialPitch] local staging of the reduced slice
+      for (int u = epi_tid; u < rpc * 32; u += kEpiThreads) {
+        const int rr = u >> 5, c4 = u & 31;
+        const uint32_t off = uint32_t(((r_begin + rr) * kPartialPitch + c4 * 4) * 4);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s0 = 0; s0 < p.splits; s0 += 8) {
+          float4 t[8];
+#pragma unroll
+          for (int ss = 0; ss < 8; ++ss) {
+            t[ss] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s0 + ss < p.splits) t[ss] = ld_dsmem_f32x4(dsmem_addr(my, uint32_t(s0 + ss)) + off);
+          }
+#pragma unroll
+          for (int ss = 0; ss < 8; ++ss) {
+            acc.x += t[ss].x; acc.y += t[ss].y; acc.z += t[ss].z; acc.w += t[ss].w;
+          }
+        }
+        *reinterpret_cast<float4*>(reduced + rr * kPartialPitch + c4 * 4) = acc;
+      }
+      epi_bar_sync();
+      if (trace && epi_tid == 0) trace[84] = clock64() - t_start;
       for (int r0 = r_begin; r0 < r_begin + rpc && r0 < p.rows; r0 += 16) {
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.0f;
-        // remote loads are issued in batches of up to 64 before any of them is consumed (latency ~200
-        // cycles each); the sum itself runs in split order, so the result does not depend on timing
-        for (int s0 = 0; s0 < p.splits; s0 += 4) {
-          float t[4][16];
-#pragma unroll
-          for (int ss = 0; ss < 4; ++ss) {
-            const uint32_t peer = dsmem_addr(my, uint32_t(min(s0 + ss, p.splits - 1)));
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              t[ss][j] = 0.0f;
-              if (s0 + ss < p.splits && r0 + j < r_begin + rpc)
-                t[ss][j] = ld_dsmem_f32(peer + uint32_t(((r0 + j) * kPartialPitch + n_local) * 4));
-            }
-          }
-#pragma unroll
-          for (int ss = 0; ss < 4; ++ss)
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += t[ss][j];
-        }
+        for (int j = 0; j < 16; ++j) v[j] = (r0 + j < r_begin + rpc) ? reduced[(r0 - r_begin + j) * kPartialPitch + n_local] : 0.0f;
         run_epilogue<EPI>(e, p, v, r0, r_lim, n, n_local, lane, exch);
       }
     }
+    if (trace && epi_tid == 0) trace[85] = clock64() - t_start;
     cluster_sync_all();  // keep every CTA's partial alive until all peers have read it
+    if (trace && epi_tid == 0) trace[86] = clock64() - t_start;
   }
 
   tcgen05_fence_before();
   __syncthreads();
   if (trace && threadIdx.x == 64) trace[81] = clock64() - t_start;
+  timeline_end(tl);
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 

@@ -41,6 +41,7 @@ struct PrepareArgs {
 __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
   __shared__ int s_off[257];
   __shared__ int s_pos[256];
+  const int tl = timeline_begin(0);
   griddep_launch_dependents();
   griddep_wait();
   const int tid = threadIdx.x;
@@ -96,6 +97,7 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
     for (int c = 0; c < chunks; ++c) rd.work_items[base + c] = (tid << 16) | c;
   }
   if (tid == 0) *rd.work_count = s_off[a.rows];
+  timeline_end(tl);
 }
 
 // RMSNorm (normalizations.py:57-69), optionally fused with the embedding gather
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(128)
 rmsnorm_kernel(const bf16* __restrict__ x_in, const int* __restrict__ tokens, const bf16* __restrict__ embedding,
                const bf16* __restrict__ scale, bf16* __restrict__ x_out, bf16* __restrict__ n_out, int E, float eps) {
   __shared__ float s_part[4];
+  const int tl = timeline_begin(1);
   griddep_launch_dependents();
   griddep_wait();
   const int r = blockIdx.x;
@@ -141,6 +144,7 @@ rmsnorm_kernel(const bf16* __restrict__ x_in, const int* __restrict__ tokens, co
     }
     *reinterpret_cast<uint4*>(n_out + (long long)r * E + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
+  timeline_end(tl);
 }
 
 struct FinalizeArgs {
@@ -151,6 +155,7 @@ struct FinalizeArgs {
   const float* part_sum;
   int n_tiles, rows;
   int mode;  // 0 = decode step: advance the state; 1 = prefill: only emit the last row's token
+  int have_lse;  // part_max / part_sum are valid
   // decode state (maxengine.py:913-936)
   int* tokens;
   int* next_pos;
@@ -171,6 +176,7 @@ struct FinalizeArgs {
 __global__ void __launch_bounds__(128) finalize_kernel(const FinalizeArgs a) {
   __shared__ float s_score[4], s_raw[4], s_max[4], s_sum[4];
   __shared__ int s_idx[4];
+  const int tl = timeline_begin(8);
   griddep_launch_dependents();
   griddep_wait();
   const int r = blockIdx.x;
@@ -182,10 +188,12 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalizeArgs a) {
     const float s2 = a.part_score[o];
     const int i2 = a.part_idx[o];
     if (s2 > score || (s2 == score && i2 < idx)) { score = s2; idx = i2; raw = a.part_raw[o]; }
-    const float m2 = a.part_max[o];
-    const float mn = fmaxf(mx, m2);
-    if (mn > -INFINITY) sum = sum * expf(mx - mn) + a.part_sum[o] * expf(m2 - mn);
-    mx = mn;
+    if (a.have_lse) {
+      const float m2 = a.part_max[o];
+      const float mn = fmaxf(mx, m2);
+      if (mn > -INFINITY) sum = sum * expf(mx - mn) + a.part_sum[o] * expf(m2 - mn);
+      mx = mn;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -231,6 +239,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalizeArgs a) {
       a.rng_state[0] += 1;
     }
   }
+  timeline_end(tl);
 }
 
 }  // namespace mtx

@@ -273,7 +273,9 @@ class MaxEngine:
     self._prefill_len, self._ar_lengths, self._ar_index = z(S), z(S), z(1)
     self._result = z(B, 3)
     self._log_prob = z(B, 1, dtype=torch.float32) if cfg.return_log_prob else None
-    self._logits = z(B, 1, cfg.vocab_size, dtype=torch.float32) if cfg.materialize_logits else None
+    # top-k / nucleus read the logits back (two-pass sampler), so they are always materialised for them
+    two_pass = cfg.decode_sampling_strategy in ("topk", "nucleus")
+    self._logits = z(B, 1, cfg.vocab_size, dtype=torch.float32) if (cfg.materialize_logits or two_pass) else None
     self._rng_state = z(4)
     self._first_token = z(1)
     self._prefill_logits = z(cfg.vocab_size, dtype=torch.float32)

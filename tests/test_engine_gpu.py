@@ -47,7 +47,7 @@ def _assert_near_tie(row_logits, got, want):
   assert abs(top - other) <= NEAR_TIE * max(1.0, abs(top)), f"token {got} (logit {other}) vs oracle {want} (logit {top}) is not a near-tie"
 
 
-def _lockstep(engine, dparams, oracle, ostate, state, steps, f32_oracle=None, f32_state=None):
+def _lockstep(engine, dparams, oracle, ostate, state, steps, atol=1e-1, rtol=1e-1):
   near_ties = 0
   for step in range(steps):
     ostate, odata = oracle.generate(ostate)
@@ -57,9 +57,7 @@ def _lockstep(engine, dparams, oracle, ostate, state, steps, f32_oracle=None, f3
     assert torch.equal(data[:, 1:], odata[:, 1:])  # valid flag and generated length
     if state["logits"] is not None:
       got = state["logits"].cpu()
-      torch.testing.assert_close(got, ostate["logits"], rtol=1e-1, atol=1e-1)
-      if f32_oracle is not None:
-        f32_state["tokens"] = ostate["tokens"].clone() if step else f32_state["tokens"]
+      torch.testing.assert_close(got, ostate["logits"], rtol=rtol, atol=atol)
     for b in range(data.shape[0]):
       if data[b, 0] != odata[b, 0]:
         _assert_near_tie(ostate["logits"][b, 0], int(data[b, 0]), int(odata[b, 0]))
@@ -201,3 +199,64 @@ def test_engine_api_shapes_and_errors():
     pyconfig.initialize(None, decode_sampling_strategy="beam")
   with pytest.raises(ValueError):
     pyconfig.initialize(None, not_a_key=1)
+
+
+@pytest.mark.parametrize(
+    "strategy,kw",
+    [("topk", dict(decode_sampling_top_k=5)), ("topk", dict(decode_sampling_top_k=1)), ("nucleus", dict(decode_sampling_nucleus_p=0.8))],
+)
+def test_topk_and_nucleus_follow_the_oracle_stream(strategy, kw):
+  """inference_utils.py:87-111 as CUDA radix-select kernels; same Philox stream as the oracle."""
+  temp = 0.9
+  cfg = small_config(per_device_batch_size=4, decode_sampling_strategy=strategy, decode_sampling_temperature=temp,
+                     return_log_prob=True, **kw)
+  params = make_params(cfg)
+  engine = maxengine.MaxEngine(cfg, use_cuda_graph=True)
+  dparams = engine.load_params(params)
+  state = engine.init_decode_state(rng=np.array([77, 0], dtype=np.uint32))
+  assert state["logits"] is not None  # the two-pass sampler materialises them
+  prompts = random_tokens((4, 16), cfg.vocab_size, seed=3)
+  for slot in range(4):
+    prefix, _ = engine.prefill(params=dparams, padded_tokens=prompts[slot], true_length=6 + 2 * slot)
+    state = engine.insert(prefix, state, slot)
+  k = int(cfg.decode_sampling_top_k)
+  p = float(cfg.decode_sampling_nucleus_p)
+  for step in range(6):
+    state, result = engine.generate(dparams, state)
+    logits = state["logits"].cpu()
+    toks, scores = ref.sampling(logits, strategy, topk=k, nucleus_topp=p, temperature=temp, seed=77, step=step, return_scores=True)
+    got = result.data.cpu()[:, 0]
+    for b in range(4):
+      g, w = int(got[b]), int(toks[b, 0])
+      if strategy == "topk":
+        assert g in torch.topk(logits[b, 0], k).indices.tolist()
+        if k == 1:
+          assert g == int(torch.argmax(logits[b, 0]))
+      else:
+        cut = ref.nucleus_cutoff(logits[b], p)[0, 0]
+        assert logits[b, 0, g] >= cut - 1e-6  # inside the nucleus
+      if g != w:
+        assert abs(scores[b][g] - scores[b][w]) < 1e-3, (step, b, g, w)
+    lp = ref.log_prob_of_chosen_token(logits, got.reshape(4, 1).long())
+    torch.testing.assert_close(result.log_prob.cpu(), lp, rtol=1e-3, atol=1e-3)
+
+
+def test_indextts2_scale_logits_and_greedy_tokens():
+  """BASELINE config C2 shape (24 layers, emb 1280, 20/4 heads x 64, mlp 5120, V = 264,192) with short
+  P/T so the CPU oracle finishes in about a minute: prefill + 6 decode steps, 4 slots."""
+  cfg = pyconfig.initialize(None, model_name="indextts2-t2s", per_device_batch_size=4, max_prefill_predict_length=64,
+                            max_target_length=128, materialize_logits=True)
+  params = make_params(cfg, perturb=True)
+  oracle = ref.DecodeOracle(cfg, params, faithful=True)
+  engine = maxengine.MaxEngine(cfg)
+  dparams = engine.load_params(params)
+  rng = np.random.Generator(np.random.PCG64(7))
+  prompts = torch.from_numpy(rng.integers(0, cfg.vocab_size, size=(4, 64), dtype=np.int64))
+  ostate, state = _prefill_both(engine, dparams, oracle, oracle.init_decode_state(), engine.init_decode_state(), prompts, [40, 17, 64, 5])
+  # 24 layers deep, the bf16 rounding noise of the two implementations (bf16 softmax in the oracle, fp32
+  # here) reaches ~6 bf16 ulps on isolated logits: stated tolerance atol = 0.2 (logits span about +-4),
+  # and all but 1e-5 of the entries inside the reference's 1e-1
+  near = _lockstep(engine, dparams, oracle, ostate, state, steps=6, atol=0.2)
+  d = (state["logits"].cpu() - ostate["logits"]).abs()
+  assert (d > 0.1 + 0.1 * ostate["logits"].abs()).float().mean() < 1e-5
+  assert near <= 2

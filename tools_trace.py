@@ -22,7 +22,7 @@ def gemm(rows, n, k, splits):
     print(f"GEMM rows={rows} n={n} k={k} splits={splits}: {e0.elapsed_time(e1)*1e3:.1f} us; W bytes {n*k*2/1e6:.1f} MB")
     print("  producer: start-of-issue", t[0], "after griddep", t[1], "refill issue times", t[2:2+24][t[2:26]>0])
     print("  mma: full-arrived times", t[40:40+24][t[40:64]>0], "all committed", t[39])
-    print("  epilogue: tmem_full", t[80], "cta end", t[81])
+    print("  epilogue: tmem_full", t[80], "parked", t[82], "after cluster sync1", t[83], "reduced", t[84], "epilogue done", t[85], "after sync2", t[86], "cta end", t[81])
     lib.mtx_debug_set_trace(None)
 
 def attn(B, Hq, Hkv, D, P_, T, ctx):
