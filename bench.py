@@ -268,6 +268,8 @@ def main():
     raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
   torch.cuda.set_device(local_rank)
   if world > 1:
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+      os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
   if _lib.needs_build():

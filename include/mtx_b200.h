@@ -137,6 +137,16 @@ int mtx_decode_step(mtx_engine* e, int rows, mtx_stream stream);
 /* Same step, replayed from a CUDA graph captured on first use (one graph per `rows`). */
 int mtx_decode_step_graph(mtx_engine* e, int rows, mtx_stream stream);
 
+/* Vocab-parallel logits: this process holds `vocab_size` rows of the logits matrix starting
+ * at `vocab_offset`.  mtx_decode_step_candidates runs the whole step but, instead of committing a token,
+ * writes this shard's winner per row to candidates[5][rows] (fp32: score, vocab id as int bits, its
+ * logit, shard max, shard sum exp) -- the payload of ONE all-gather.  mtx_commit_candidates takes the
+ * gathered [n_shards][5][rows] buffer, picks the global winner (lowest id on ties) and advances the state
+ * exactly as mtx_decode_step does.  Replaces the all-gather of full fp32 logits that the reference's
+ * sharding rules lower to (maxengine.py:894, configs/base.yml:351). */
+int mtx_decode_step_candidates(mtx_engine* e, int rows, float* candidates, mtx_stream stream);
+int mtx_commit_candidates(mtx_engine* e, int rows, const float* gathered, int n_shards, mtx_stream stream);
+
 /* Measurement aid: one eager decode step with a CUDA-event pair around every kernel launch
  * (on `stream`), summed per kernel class into class_ms[9] / class_launches[9] (host arrays):
  * 0 prepare, 1 rmsnorm, 2 qkv+rope+append, 3 attention, 4 out-proj, 5 mlp up, 6 mlp down,

@@ -134,6 +134,14 @@ def _declare(lib) -> None:
   lib.mtx_decode_step.argtypes = [vp, i32, vp]
   lib.mtx_decode_step_graph.restype = i32
   lib.mtx_decode_step_graph.argtypes = [vp, i32, vp]
+  lib.mtx_decode_step_candidates.restype = i32
+  lib.mtx_decode_step_candidates.argtypes = [vp, i32, vp, vp]
+  lib.mtx_commit_candidates.restype = i32
+  lib.mtx_commit_candidates.argtypes = [vp, i32, vp, i32, vp]
+  lib.mtx_debug_set_trace.restype = None
+  lib.mtx_debug_set_trace.argtypes = [vp]
+  lib.mtx_debug_set_timeline.restype = i32
+  lib.mtx_debug_set_timeline.argtypes = [vp]
   lib.mtx_profile_decode_step.restype = i32
   lib.mtx_profile_decode_step.argtypes = [vp, i32, vp, c.POINTER(c.c_float), c.POINTER(c.c_int32)]
   lib.mtx_prefill_chunk.restype = i32

@@ -349,7 +349,7 @@ int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st) {
 
 // The kernels of one step, in stream order.  mode 0 = decode, 1 = prefill chunk.
 int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens, int start_pos, int slot, int want_logits,
-                 int32_t* first_token, float* prefill_logits, cudaStream_t st) {
+                 int32_t* first_token, float* prefill_logits, cudaStream_t st, float* cand_out = nullptr) {
   const mtx_model_config& c = e->cfg;
   const int r_tile = round_rows(rows);
   XMaps* xm;
@@ -472,7 +472,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     ea.inv_temp = 1.0f / e->temperature;
     ea.round_bf16 = c.logits_round_bf16;
     ea.gumbel = e->strategy == MTX_SAMPLE_WEIGHTED ? 1 : 0;
-    ea.want_lse = (e->s.log_prob != nullptr && !two_pass) ? 1 : 0;
+    ea.want_lse = ((e->s.log_prob != nullptr || cand_out != nullptr) && !two_pass) ? 1 : 0;
     ea.rng_state = e->s.rng_state;
     ea.row_offset = 0;
     gp.n = c.vocab_size;
@@ -490,6 +490,9 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     fa.part_sum = e->part_sum;
     fa.n_tiles = plan_logits.n_tiles;
     fa.rows = rows;
+    fa.stride_r = plan_logits.n_tiles;
+    fa.stride_t = 1;
+    fa.cand_out = cand_out;
     int finalize_rows = rows;
     if (two_pass) {
       // inference_utils.py:87-111 on the logits the GEMM just wrote; one candidate per row
@@ -513,10 +516,11 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
       finalize_rows = mode == 0 ? rows : 1;
       MTX_TRY(launch(sample_rows_kernel, dim3(finalize_rows), dim3(kSampleThreads), 0, st, sa));
       fa.n_tiles = 1;
+      fa.stride_r = 1;
       fa.rows = finalize_rows;
     }
-    fa.mode = mode;
-    fa.have_lse = (two_pass || e->s.log_prob != nullptr) ? 1 : 0;
+    fa.mode = cand_out != nullptr ? 2 : mode;
+    fa.have_lse = (two_pass || e->s.log_prob != nullptr || cand_out != nullptr) ? 1 : 0;
     fa.tokens = e->s.tokens;
     fa.next_pos = e->s.next_pos;
     fa.generated = e->s.generated;
@@ -701,6 +705,45 @@ int mtx_decode_step_graph(mtx_engine* e, int rows, mtx_stream stream) {
   }
   MTX_CUDA(cudaGraphLaunch(it->second, static_cast<cudaStream_t>(stream)));
   return MTX_OK;
+}
+
+int mtx_decode_step_candidates(mtx_engine* e, int rows, float* candidates, mtx_stream stream) {
+  if (!e || !e->bound || !candidates) return fail(MTX_ERR_ARG, "engine is not bound / null candidates");
+  if (rows < 1 || rows > e->cfg.max_rows) return fail(MTX_ERR_ARG, "rows %d outside [1, %d]", rows, e->cfg.max_rows);
+  if (e->strategy == MTX_SAMPLE_NUCLEUS || e->strategy == MTX_SAMPLE_TOPK)
+    return fail(MTX_ERR_UNSUPPORTED, "vocab-parallel logits support greedy and weighted sampling");
+  return enqueue_step(e, 0, rows, nullptr, 0, 0, 1, nullptr, nullptr, static_cast<cudaStream_t>(stream), candidates);
+}
+
+int mtx_commit_candidates(mtx_engine* e, int rows, const float* gathered, int n_shards, mtx_stream stream) {
+  if (!e || !e->bound || !gathered || n_shards < 1) return fail(MTX_ERR_ARG, "bad commit arguments");
+  if (rows < 1 || rows > e->cfg.max_rows) return fail(MTX_ERR_ARG, "rows %d outside [1, %d]", rows, e->cfg.max_rows);
+  const mtx_model_config& c = e->cfg;
+  FinalizeArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.part_score = gathered + 0 * rows;
+  fa.part_idx = reinterpret_cast<const int*>(gathered + 1 * rows);
+  fa.part_raw = gathered + 2 * rows;
+  fa.part_max = gathered + 3 * rows;
+  fa.part_sum = gathered + 4 * rows;
+  fa.n_tiles = n_shards;
+  fa.rows = rows;
+  fa.stride_r = 1;
+  fa.stride_t = 5LL * rows;
+  fa.mode = 0;
+  fa.have_lse = 1;
+  fa.tokens = e->s.tokens;
+  fa.next_pos = e->s.next_pos;
+  fa.generated = e->s.generated;
+  fa.ar_lengths = e->s.ar_lengths;
+  fa.ar_index = e->s.ar_index;
+  fa.result = e->s.result;
+  fa.log_prob = e->s.log_prob;
+  fa.rng_state = e->s.rng_state;
+  fa.num_slots = c.num_slots;
+  fa.R = c.max_target_len - c.max_prefill_len;
+  g_class = KC_FINALIZE;
+  return launch(finalize_kernel, dim3(rows), dim3(128), 0, static_cast<cudaStream_t>(stream), fa);
 }
 
 int mtx_profile_decode_step(mtx_engine* e, int rows, mtx_stream stream, float* class_ms, int32_t* class_launches) {

@@ -154,7 +154,10 @@ struct FinalizeArgs {
   const float* part_max;
   const float* part_sum;
   int n_tiles, rows;
-  int mode;  // 0 = decode step: advance the state; 1 = prefill: only emit the last row's token
+  long long stride_r, stride_t;  // element (row r, tile t) of every part_* array is at [r * stride_r + t * stride_t]
+  float* cand_out;               // mode 2: [5][rows] = best score, vocab id (int bits), its logit, max, sum exp
+  int mode;  // 0 = decode step: advance the state; 1 = prefill: only emit the last row's token;
+             // 2 = vocab-parallel shard: emit this shard's candidate per row, do not advance
   int have_lse;  // part_max / part_sum are valid
   // decode state (maxengine.py:913-936)
   int* tokens;
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalizeArgs a) {
   float score = -INFINITY, raw = -INFINITY, mx = -INFINITY, sum = 0.0f;
   int idx = 0x7fffffff;
   for (int t = threadIdx.x; t < a.n_tiles; t += 128) {
-    const long long o = (long long)r * a.n_tiles + t;
+    const long long o = (long long)r * a.stride_r + (long long)t * a.stride_t;
     const float s2 = a.part_score[o];
     const int i2 = a.part_idx[o];
     if (s2 > score || (s2 == score && i2 < idx)) { score = s2; idx = i2; raw = a.part_raw[o]; }
@@ -217,7 +220,13 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalizeArgs a) {
       mx = mn;
     }
     const float logp = raw - (mx + logf(sum));
-    if (a.mode == 0) {
+    if (a.mode == 2) {
+      a.cand_out[0 * a.rows + r] = score;
+      a.cand_out[1 * a.rows + r] = __int_as_float(idx);
+      a.cand_out[2 * a.rows + r] = raw;
+      a.cand_out[3 * a.rows + r] = mx;
+      a.cand_out[4 * a.rows + r] = sum;
+    } else if (a.mode == 0) {
       const int gen = a.generated[r] + 1;
       a.tokens[r] = idx;
       a.next_pos[r] += 1;

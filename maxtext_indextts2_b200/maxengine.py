@@ -33,6 +33,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import parallel
 from . import params as params_lib
 from .common_types import DECODING_ACTIVE_SEQUENCE_INDICATOR
 
@@ -182,7 +183,10 @@ def random_device_params(config, device, seed: int = 0) -> DeviceParams:
 class MaxEngine:
   """The reference's ``MaxEngine`` for one B200 (one process per GPU)."""
 
-  def __init__(self, config, devices: Any = None, use_cuda_graph: bool = True):
+  def __init__(self, config, devices: Any = None, use_cuda_graph: bool = True, vocab_shard: Optional[tuple] = None,
+               gather: Any = None):
+    """`vocab_shard` = (rank, world) and `gather` (candidates [5,B] -> [world,5,B]) default to the
+    torch.distributed process group when config.vocab_parallelism > 1; tests inject their own."""
     self.config = config
     self.device = _lib.require_cuda()
     self.lib = _lib.load()
@@ -198,6 +202,19 @@ class MaxEngine:
     self._chunk = max(1, min(256, int(config.prefill_chunk_size), config.max_prefill_predict_length))
     self._staging = B  # extra KV plane prefill writes into
     self._num_slots = B + 1
+    self._vp_world, self._vp_rank, self._gather = 1, 0, gather
+    if vocab_shard is not None:
+      self._vp_rank, self._vp_world = int(vocab_shard[0]), int(vocab_shard[1])
+    elif int(config.vocab_parallelism) > 1:
+      import torch.distributed as dist
+
+      if not dist.is_initialized() or dist.get_world_size() != int(config.vocab_parallelism):
+        raise ValueError("vocab_parallelism needs an initialised process group of that size")
+      self._vp_rank, self._vp_world = dist.get_rank(), dist.get_world_size()
+      self._gather = parallel.all_gather_candidates
+    self._v_lo, self._v_hi = parallel.vocab_shard(config.vocab_size, self._vp_world, self._vp_rank)
+    if self._vp_world > 1 and config.decode_sampling_strategy in ("topk", "nucleus"):
+      raise ValueError("vocab-parallel logits support greedy and weighted sampling")
     scale = 1.0
     if config.logits_via_embedding and config.normalize_embedding_logits:
       scale = 1.0 / math.sqrt(config.emb_dim)  # decoders.py:560-562
@@ -208,8 +225,8 @@ class MaxEngine:
         num_kv_heads=config.num_kv_heads,
         head_dim=config.head_dim,
         mlp_dim=config.mlp_dim,
-        vocab_size=config.vocab_size,
-        vocab_offset=0,
+        vocab_size=self._v_hi - self._v_lo,
+        vocab_offset=self._v_lo,
         max_prefill_len=config.max_prefill_predict_length,
         max_target_len=config.max_target_length,
         num_slots=self._num_slots,
@@ -275,10 +292,12 @@ class MaxEngine:
     self._log_prob = z(B, 1, dtype=torch.float32) if cfg.return_log_prob else None
     # top-k / nucleus read the logits back (two-pass sampler), so they are always materialised for them
     two_pass = cfg.decode_sampling_strategy in ("topk", "nucleus")
-    self._logits = z(B, 1, cfg.vocab_size, dtype=torch.float32) if (cfg.materialize_logits or two_pass) else None
+    V = self._v_hi - self._v_lo  # logits columns held by this process (all of them unless vocab-parallel)
+    self._logits = z(B, 1, V, dtype=torch.float32) if (cfg.materialize_logits or two_pass) else None
+    self._cand = z(5, max(B, self._chunk), dtype=torch.float32)
     self._rng_state = z(4)
     self._first_token = z(1)
-    self._prefill_logits = z(cfg.vocab_size, dtype=torch.float32)
+    self._prefill_logits = z(V, dtype=torch.float32)
     self._prefill_tokens = z(cfg.max_prefill_predict_length)
     self._state_struct = _lib.DecodeState(
         k_cache=self._k.data_ptr(),
@@ -335,15 +354,21 @@ class MaxEngine:
     if params is None:
       if on_device_init:
         dp = random_device_params(self.config, self.device, self.config.init_weights_seed)
+        if self._vp_world > 1:
+          dp.tensors["logits"] = dp.tensors["logits"][self._v_lo : self._v_hi].contiguous()
+          dp = DeviceParams(dp.tensors)
       else:
-        dp = pack_params(params_lib.init_params(self.config), self.config, self.device)
+        dp = pack_params(params_lib.init_params(self.config), self.config, self.device, self._shard_or_none())
     elif isinstance(params, DeviceParams):
       dp = params
     else:
-      dp = pack_params(params, self.config, self.device)
+      dp = pack_params(params, self.config, self.device, self._shard_or_none())
     self._params = dp
     self._bind(dp)
     return dp
+
+  def _shard_or_none(self):
+    return (self._v_lo, self._v_hi) if self._vp_world > 1 else None
 
   def init_decode_state(self, rng: Any = None) -> dict:
     """maxengine.py:1370-1453: every field zero."""
@@ -397,7 +422,9 @@ class MaxEngine:
       raise ValueError(f"true_length={true_length}, {toks.numel()} padded tokens, max_prefill_predict_length={cfg.max_prefill_predict_length}")
     n = toks.numel()
     self._prefill_tokens[:n].copy_(toks.to(torch.int32), non_blocking=True)
-    want_logits = self._logits is not None
+    want_logits = self._logits is not None or self._vp_world > 1
+    if self._vp_world > 1 and cfg.decode_sampling_strategy != "greedy":
+      raise NotImplementedError("vocab-parallel prefill picks the first token greedily only")
     for start in range(0, true_length, self._chunk):
       count = min(self._chunk, true_length - start)
       last = start + count == true_length
@@ -414,6 +441,11 @@ class MaxEngine:
               self._stream(),
           )
       )
+    if self._vp_world > 1:
+      # first token: merge the per-shard winners of the last prompt position (not on the decode hot path)
+      cand = parallel.candidates_from_logits(self._prefill_logits.reshape(1, -1), self._v_lo)
+      token, _ = parallel.merge_candidates_reference(self._gather(cand))
+      self._first_token.copy_(token.to(torch.int32))
     first = self._first_token.clone().reshape(1, 1)
     prefix = {
         "logits": self._prefill_logits.clone().reshape(1, 1, -1) if want_logits else None,
@@ -462,8 +494,15 @@ class MaxEngine:
     self._bind(params)
     self._seed(rng)
     B = self.max_concurrent_decodes
-    fn = self.lib.mtx_decode_step_graph if self.use_cuda_graph else self.lib.mtx_decode_step
-    _lib.check(fn(self._handle, B, self._stream()))
+    if self._vp_world > 1:
+      # each rank scores its vocabulary shard; one all-gather of 5*B floats; identical commit everywhere
+      cand = self._cand[:, :B].contiguous()
+      _lib.check(self.lib.mtx_decode_step_candidates(self._handle, B, ctypes.c_void_p(cand.data_ptr()), self._stream()))
+      gathered = self._gather(cand).contiguous()
+      _lib.check(self.lib.mtx_commit_candidates(self._handle, B, ctypes.c_void_p(gathered.data_ptr()), self._vp_world, self._stream()))
+    else:
+      fn = self.lib.mtx_decode_step_graph if self.use_cuda_graph else self.lib.mtx_decode_step
+      _lib.check(fn(self._handle, B, self._stream()))
     result = ResultTokens(
         data=self._result.clone(),
         log_prob=self._log_prob.clone() if self._log_prob is not None else None,
