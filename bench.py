@@ -99,7 +99,7 @@ class ClockSampler:
   def start(self):
     try:
       self.proc = subprocess.Popen(
-          ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+          ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20"],
           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
