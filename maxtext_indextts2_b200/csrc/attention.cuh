@@ -119,24 +119,26 @@ __global__ void attn_build_worklist_kernel(const int* len0, const int* ring_firs
   if (tid == 0) *work_count = s_off[rows];
 }
 
+// The attention work loop of 128 threads (4 warps).  `tiles` = [warp][K tile | V tile] (1024-byte
+// aligned), `sm_o_all` = merge buffer [warp][o_rows][D] fp32, `bars` = 2 initialised mbarriers per warp
+// (their current parity in `phase`, updated on return), `sm_stat` = 128 floats + 1 int.  Items are
+// taken from the work list starting at `first_item` with stride `item_stride`.  `tid` is 0..127; the
+// 128 threads synchronise with the named barrier of epi_bar_sync().
 template <int D>
-__global__ void __launch_bounds__(kAttnThreads)
-decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
+__device__ __forceinline__ void attn_process_items(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnParams& p, uint8_t* tiles,
+                                                   float* sm_o_all, uint64_t* bars, float* sm_stat, uint32_t& phase, int tid,
+                                                   int first_item, int item_stride) {
   constexpr int kSub = D / 64;                 // 64-wide (128-byte) sub-tiles per row
   constexpr int kTileBytes = 64 * D * 2;       // one warp's K (or V) tile
   constexpr float kLog2e = 1.4426950408889634f;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = tiles;
   const int G = p.hq / p.hkv;
   const int o_rows = G <= 8 ? 8 : 16;
-  // [warp][K tile | V tile] | merge buffer [warp][o_rows][D] fp32 | barriers | merge statistics
-  float* sm_o_all = reinterpret_cast<float*>(smem + kAttnWarps * 2 * kTileBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_o_all + kAttnWarps * o_rows * D);
-  float* sm_m = reinterpret_cast<float*>(bars + 2 * kAttnWarps);  // [4][16]
-  float* sm_l = sm_m + kAttnWarps * 16;                            // [4][16]
-  __shared__ int s_last;
+  float* sm_m = sm_stat;                 // [4][16]
+  float* sm_l = sm_m + kAttnWarps * 16;  // [4][16]
+  volatile int* s_last_p = reinterpret_cast<volatile int*>(sm_l + kAttnWarps * 16);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tid >> 5, lane = tid & 31;
   const int gid = lane >> 2, tid4 = lane & 3;
   const int mtx_i = lane >> 3, lrow = lane & 7;
   const int R = p.T - p.P;
@@ -148,27 +150,12 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   uint64_t* bar_v = bar_k + 1;
   const uint32_t kb = smem_u32(k_tile), vb = smem_u32(v_tile);
 
-  const int tl = timeline_begin(3);
-  griddep_launch_dependents();
-  if (lane == 0) {
-    mbar_init(bar_k, 1);
-    mbar_init(bar_v, 1);
-    fence_barrier_init();
-  }
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tm_k);
-    tma_prefetch_desc(&tm_v);
-  }
-  __syncthreads();
-  griddep_wait();
-
   const int n_items = *p.work_count * p.hkv;
-  long long* trace = (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) ? p.trace : nullptr;
+  long long* trace = (p.trace != nullptr && blockIdx.x == 0 && tid == 0) ? p.trace : nullptr;
   const long long t_start = clock64();
   int iter = 0;
-  uint32_t phase = 0;
 
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  for (int item = first_item; item < n_items; item += item_stride) {
     const int packed = p.work_items[item / p.hkv];
     const int h = item % p.hkv;
     const int r = packed >> 16, chunk = packed & 0xffff;
@@ -340,12 +327,12 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
       sm_l[warp * 16 + gid] = l0;
       sm_l[warp * 16 + gid + 8] = l1;
     }
-    __syncthreads();
+    epi_bar_sync();
     if (trace && iter < 15) trace[iter * 8 + 5] = clock64() - t_start;
 
     const long long out_base = (long long)r * p.hq * D + (long long)h * G * D;
     const long long part_base = ((long long)(r * p.hkv + h) * p.max_chunks + chunk) * G;
-    for (int e = threadIdx.x; e < G * D; e += kAttnThreads) {
+    for (int e = tid; e < G * D; e += kAttnThreads) {
       const int g = e / D, d = e - g * D;
       float M = -INFINITY;
 #pragma unroll
@@ -372,18 +359,18 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
     }
     if (n_chunks > 1) {
       __threadfence();
-      __syncthreads();
-      if (threadIdx.x == 0) {
+      epi_bar_sync();
+      if (tid == 0) {
         const int old = atomicAdd(p.tickets + r * p.hkv + h, 1);
         const int last = old == n_chunks - 1;
         if (last) p.tickets[r * p.hkv + h] = 0;
-        s_last = last;
+        *s_last_p = last;
       }
-      __syncthreads();
-      if (s_last) {
+      epi_bar_sync();
+      if (*s_last_p) {
         __threadfence();
         const long long pb = (long long)(r * p.hkv + h) * p.max_chunks * G;
-        for (int e = threadIdx.x; e < G * D; e += kAttnThreads) {
+        for (int e = tid; e < G * D; e += kAttnThreads) {
           const int g = e / D, d = e - g * D;
           float M = -INFINITY;
           for (int c = 0; c < n_chunks; ++c) M = fmaxf(M, __ldcg(p.part_ml + (pb + c * G + g) * 2));
@@ -398,16 +385,46 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
       }
     }
     if (trace && iter < 15) trace[iter * 8 + 6] = clock64() - t_start;
-    __syncthreads();  // the merge buffer is rewritten by the next item
+    epi_bar_sync();  // the merge buffer is rewritten by the next item
     if (trace && iter < 15) trace[iter * 8 + 7] = clock64() - t_start;
     ++iter;
   }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kAttnThreads)
+decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
+  constexpr int kTileBytes = 64 * D * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int G = p.hq / p.hkv;
+  const int o_rows = G <= 8 ? 8 : 16;
+  // [warp][K tile | V tile] | merge buffer [warp][o_rows][D] fp32 | barriers | merge statistics
+  float* sm_o_all = reinterpret_cast<float*>(smem + kAttnWarps * 2 * kTileBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_o_all + kAttnWarps * o_rows * D);
+  float* sm_stat = reinterpret_cast<float*>(bars + 2 * kAttnWarps);
+  const int tl = timeline_begin(3);
+  griddep_launch_dependents();
+  if ((threadIdx.x & 31) == 0) {
+    mbar_init(bars + 2 * (threadIdx.x >> 5), 1);
+    mbar_init(bars + 2 * (threadIdx.x >> 5) + 1, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  __syncthreads();
+  griddep_wait();
+  uint32_t phase = 0;
+  attn_process_items<D>(tm_k, tm_v, p, smem, sm_o_all, bars, sm_stat, phase, threadIdx.x, blockIdx.x, gridDim.x);
   timeline_end(tl);
 }
 
+
 __host__ inline size_t attn_smem_bytes(int D, int G) {
   const size_t o_rows = G <= 8 ? 8 : 16;
-  return 1024 + size_t(kAttnWarps) * 2 * (64 * D * 2) + kAttnWarps * o_rows * D * 4 + 2 * kAttnWarps * 8 + 2 * kAttnWarps * 16 * 4 + 16;
+  return 1024 + size_t(kAttnWarps) * 2 * (64 * D * 2) + kAttnWarps * o_rows * D * 4 + 2 * kAttnWarps * 8 + 2 * kAttnWarps * 16 * 4 + 32;
 }
 
 }  // namespace mtx

@@ -68,6 +68,9 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 // Lets the next kernel in the stream start its prologue (weight prefetch) early.
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Named barrier 1 over the 128 "worker" threads of a CTA (GEMM epilogue warps / attention warps).
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------

@@ -14,6 +14,7 @@
 #include "../../include/mtx_b200.h"
 #include "attention.cuh"
 #include "gemm_umma.cuh"
+#include "megakernel.cuh"
 #include "sampling.cuh"
 #include "step_kernels.cuh"
 
@@ -242,6 +243,9 @@ struct mtx_engine {
   // descriptors
   std::vector<CUtensorMap> tm_wqkv, tm_wo, tm_w01, tm_wout;
   CUtensorMap tm_logits, tm_k, tm_v;
+  CUtensorMap tm_all_wqkv, tm_all_wo, tm_all_w01, tm_all_wout;  // all layers stacked: row = layer * N + n
+  int mega_clusters = 0;          // co-resident clusters of 8 for the persistent step kernel (0 = unavailable)
+  unsigned int* grid_bar = nullptr;
   XMaps xmaps[5];
   // sampling
   int strategy = MTX_SAMPLE_GREEDY, top_k = 0;
@@ -256,7 +260,7 @@ namespace {
 struct WsLayout {
   size_t x, h, n, q, attn, act, attn_part_o, attn_part_ml, attn_tickets;
   size_t token, pos, plane, write_row, len0, ring_first, ring_len, rope_cs, work_items, work_count, rope_timescale;
-  size_t part_score, part_idx, part_raw, part_max, part_sum;
+  size_t part_score, part_idx, part_raw, part_max, part_sum, grid_bar;
   size_t total;
 };
 
@@ -297,6 +301,7 @@ WsLayout layout_workspace(const mtx_engine* e) {
   L.part_raw = take(size_t(c.max_rows) * vt * 4);
   L.part_max = take(size_t(c.max_rows) * vt * 4);
   L.part_sum = take(size_t(c.max_rows) * vt * 4);
+  L.grid_bar = take(64);
   L.total = off;
   return L;
 }
@@ -347,6 +352,116 @@ int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st) {
   return launch(decode_attn_kernel<128>, dim3(grid), dim3(kAttnThreads), smem, st, e->tm_k, e->tm_v, p);
 }
 
+// K splits of a per-layer GEMM inside the persistent kernel: a power of two <= 8 (one cluster), at most
+// the number of k-blocks and of padded rows, aiming at one split unit per resident CTA.
+int mega_splits(int n, int k, int r_tile, int ctas, bool qkv) {
+  const int tiles = (n + kTileN - 1) / kTileN, kb = k / kBlockK;
+  int s = 1;
+  while (s * 2 <= kMegaCluster && s * 2 <= kb && s * 2 <= r_tile && tiles * s * 2 <= ctas) s *= 2;
+  if (qkv && s > 1 && r_tile / s > kMegaExchPitch - 1) s = 1;  // the small RoPE exchange buffer holds 8 rows
+  return s;
+}
+
+bool mega_usable(const mtx_engine* e, int rows) {
+  return e->mega_clusters > 0 && round_rows(rows) <= kMegaMaxRTile && e->cfg.head_dim == 64;
+}
+
+int launch_megakernel(mtx_engine* e, int rows, const XMaps& xm, const EpiArgs& logits_epi, cudaStream_t st) {
+  const mtx_model_config& c = e->cfg;
+  const int r_tile = round_rows(rows);
+  const int ctas = e->mega_clusters * kMegaCluster;
+  MegaParams p;
+  memset(&p, 0, sizeof(p));
+  p.L = c.num_layers;
+  p.E = c.emb_dim;
+  p.HD = c.num_q_heads * c.head_dim;
+  p.M = c.mlp_dim;
+  p.qkv_n = e->qkv_n;
+  p.V = c.vocab_size;
+  p.hq = c.num_q_heads;
+  p.hkv = c.num_kv_heads;
+  p.d = c.head_dim;
+  p.t_alloc = c.max_target_len;
+  p.num_slots = c.num_slots;
+  p.rows = rows;
+  p.r_tile = r_tile;
+  p.eps = c.rms_eps;
+  p.s_qkv = mega_splits(e->qkv_n, p.E, r_tile, ctas, true);
+  p.s_oproj = mega_splits(p.E, p.HD, r_tile, ctas, false);
+  p.s_up = mega_splits(2 * p.M, p.E, r_tile, ctas, false);
+  p.s_down = mega_splits(p.E, p.M, r_tile, ctas, false);
+  p.x = e->x;
+  p.h = e->h;
+  p.n = e->n;
+  p.q = e->q;
+  p.attn = e->attn;
+  p.act = e->act;
+  p.embedding = static_cast<const bf16*>(e->w.embedding);
+  p.attn_norm = static_cast<const bf16*>(e->w.attn_norm);
+  p.mlp_norm = static_cast<const bf16*>(e->w.mlp_norm);
+  p.final_norm = static_cast<const bf16*>(e->w.final_norm);
+  p.k_cache = static_cast<bf16*>(e->s.k_cache);
+  p.v_cache = static_cast<bf16*>(e->s.v_cache);
+  p.kv_layer_elems = (long long)c.num_slots * c.num_kv_heads * c.max_target_len * c.head_dim;
+  p.token = e->rd.token;
+  p.plane = e->rd.plane;
+  p.write_row = e->rd.write_row;
+  p.rope_cs = e->rd.rope_cs;
+  AttnParams& a = p.attn_args;
+  a.q = e->q;
+  a.out = e->attn;
+  a.plane = e->rd.plane;
+  a.len0 = e->rd.len0;
+  a.ring_first = e->rd.ring_first;
+  a.ring_len = e->rd.ring_len;
+  a.work_items = e->rd.work_items;
+  a.work_count = e->rd.work_count;
+  a.part_o = e->attn_part_o;
+  a.part_ml = e->attn_part_ml;
+  a.tickets = e->attn_tickets;
+  a.rows = rows;
+  a.hq = c.num_q_heads;
+  a.hkv = c.num_kv_heads;
+  a.P = c.max_prefill_len;
+  a.T = c.max_target_len;
+  a.tiles_per_item = attn_tiles_per_item(rows, c.num_kv_heads, c.max_prefill_len, c.max_target_len, e->num_sms);
+  a.max_chunks = e->attn_max_chunks;
+  a.softcap = c.attn_softcap;
+  a.trace = nullptr;
+  p.logits = logits_epi;
+  p.grid_bar = e->grid_bar;
+  p.trace = g_trace;
+
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(kMegaThreads);
+  cfg.dynamicSmemBytes = mega_smem_bytes();
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kMegaCluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  ProfileSink::Rec rec;
+  if (g_profile != nullptr) {
+    rec.cls = KC_QKV;
+    MTX_CUDA(cudaEventCreate(&rec.a));
+    MTX_CUDA(cudaEventCreate(&rec.b));
+    MTX_CUDA(cudaEventRecord(rec.a, st));
+  }
+  MTX_CUDA(cudaLaunchKernelEx(&cfg, step_megakernel, e->tm_all_wqkv, e->tm_all_wo, e->tm_all_w01, e->tm_all_wout, e->tm_logits, xm.n,
+                              xm.attn, xm.act, e->tm_k, e->tm_v, p));
+  if (g_profile != nullptr) {
+    MTX_CUDA(cudaEventRecord(rec.b, st));
+    g_profile->recs.push_back(rec);
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return MTX_OK;
+}
+
 // The kernels of one step, in stream order.  mode 0 = decode, 1 = prefill chunk.
 int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens, int start_pos, int slot, int want_logits,
                  int32_t* first_token, float* prefill_logits, cudaStream_t st, float* cand_out = nullptr) {
@@ -374,24 +489,27 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   pa.D = c.head_dim;
   pa.tiles_per_item = attn_tiles_per_item(rows, c.num_kv_heads, c.max_prefill_len, c.max_target_len, e->num_sms);
   pa.rope_timescale = e->rope_timescale;
+  pa.grid_bar = e->grid_bar;
   g_class = KC_PREPARE;
   MTX_TRY(launch(prepare_rows_kernel, dim3(1), dim3(256), 0, st, pa, e->rd));
   g_class = KC_RMSNORM;
-
-  const bf16* attn_norm = static_cast<const bf16*>(e->w.attn_norm);
-  const bf16* mlp_norm = static_cast<const bf16*>(e->w.mlp_norm);
-  MTX_TRY(launch(rmsnorm_kernel<true>, dim3(rows), dim3(128), 0, st, (const bf16*)nullptr, (const int*)e->rd.token,
-                 static_cast<const bf16*>(e->w.embedding), attn_norm, e->x, e->n, E, c.rms_eps));
 
   GemmParams gp;
   memset(&gp, 0, sizeof(gp));
   gp.rows = rows;
   gp.r_tile = r_tile;
+  const GemmPlan plan_logits = plan_gemm(c.vocab_size, c.emb_dim, r_tile, e->num_sms, EPI_LOGITS, 1);
+  const bool mega = mode == 0 && want_logits && mega_usable(e, rows);
+  if (!mega) {
+  const bf16* attn_norm = static_cast<const bf16*>(e->w.attn_norm);
+  const bf16* mlp_norm = static_cast<const bf16*>(e->w.mlp_norm);
+  MTX_TRY(launch(rmsnorm_kernel<true>, dim3(rows), dim3(128), 0, st, (const bf16*)nullptr, (const int*)e->rd.token,
+                 static_cast<const bf16*>(e->w.embedding), attn_norm, e->x, e->n, E, c.rms_eps));
+
   const GemmPlan plan_qkv = plan_gemm(e->qkv_n, E, r_tile, e->num_sms, EPI_QKV_ROPE);
   const GemmPlan plan_o = plan_gemm(E, HD, r_tile, e->num_sms, EPI_RESIDUAL);
   const GemmPlan plan_up = plan_gemm(2 * M, E, r_tile, e->num_sms, EPI_SWIGLU);
   const GemmPlan plan_down = plan_gemm(E, M, r_tile, e->num_sms, EPI_RESIDUAL);
-  const GemmPlan plan_logits = plan_gemm(c.vocab_size, E, r_tile, e->num_sms, EPI_LOGITS, 1);
 
   for (int l = 0; l < L; ++l) {
     EpiArgs ea;
@@ -451,6 +569,8 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
                      (const bf16*)nullptr, next_scale, (bf16*)nullptr, e->n, E, c.rms_eps));
   }
 
+  }
+
   if (want_logits) {
     const bool two_pass = e->strategy == MTX_SAMPLE_NUCLEUS || e->strategy == MTX_SAMPLE_TOPK;
     if (two_pass && (mode == 0 ? e->s.logits == nullptr : prefill_logits == nullptr))
@@ -478,7 +598,12 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     gp.n = c.vocab_size;
     gp.k = E;
     g_class = KC_LOGITS;
-    MTX_TRY(launch_gemm<EPI_LOGITS>(e->tm_logits, xm->n, gp, ea, plan_logits, st));
+    if (mega) {
+      g_class = KC_QKV;
+      MTX_TRY(launch_megakernel(e, rows, *xm, ea, st));
+    } else {
+      MTX_TRY(launch_gemm<EPI_LOGITS>(e->tm_logits, xm->n, gp, ea, plan_logits, st));
+    }
     g_class = KC_FINALIZE;
 
     FinalizeArgs fa;
@@ -635,6 +760,7 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   e->part_raw = reinterpret_cast<float*>(b + L.part_raw);
   e->part_max = reinterpret_cast<float*>(b + L.part_max);
   e->part_sum = reinterpret_cast<float*>(b + L.part_sum);
+  e->grid_bar = reinterpret_cast<unsigned int*>(b + L.grid_bar);
   MTX_CUDA(cudaMemcpy(e->rope_timescale, e->rope_timescale_host.data(), e->rope_timescale_host.size() * 4, cudaMemcpyHostToDevice));
 
   const int E = c.emb_dim, HD = c.num_q_heads * c.head_dim, M = c.mlp_dim, L_ = c.num_layers;
@@ -649,6 +775,32 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
     MTX_TRY(make_map(&e->tm_wout[l], static_cast<const bf16*>(w->wout) + size_t(l) * E * M, M, E, kTileN));
   }
   MTX_TRY(make_map(&e->tm_logits, w->logits, E, c.vocab_size, kTileN));
+  MTX_TRY(make_map(&e->tm_all_wqkv, w->wqkv, E, uint64_t(L_) * e->qkv_n, kTileN));
+  MTX_TRY(make_map(&e->tm_all_wo, w->wo, HD, uint64_t(L_) * E, kTileN));
+  MTX_TRY(make_map(&e->tm_all_w01, w->w01, E, uint64_t(L_) * 2 * M, kTileN));
+  MTX_TRY(make_map(&e->tm_all_wout, w->wout, M, uint64_t(L_) * E, kTileN));
+  e->mega_clusters = 0;
+  if (c.head_dim == 64 && env_int("MTX_MEGAKERNEL", 0) != 0) {
+    cudaError_t a1 = cudaFuncSetAttribute(step_megakernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(mega_smem_bytes()));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(kMegaCluster * 64);
+    cfg.blockDim = dim3(kMegaThreads);
+    cfg.dynamicSmemBytes = mega_smem_bytes();
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kMegaCluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (a1 == cudaSuccess && cudaOccupancyMaxActiveClusters(&n, step_megakernel, &cfg) == cudaSuccess && n > 0) {
+      const int cap = env_int("MTX_MEGA_CLUSTERS", 0);
+      e->mega_clusters = (cap > 0 && cap < n) ? cap : n;
+    }
+    cudaGetLastError();
+  }
   const uint64_t kv_rows = uint64_t(L_) * c.num_slots * c.num_kv_heads * c.max_target_len;
   if (kv_rows >= (1ull << 31)) return fail(MTX_ERR_UNSUPPORTED, "KV cache has too many rows for one tensor map");
   MTX_TRY(make_map(&e->tm_k, s->k_cache, c.head_dim, kv_rows, kAttnTileRows));

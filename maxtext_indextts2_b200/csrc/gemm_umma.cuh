@@ -85,7 +85,6 @@ struct EpiArgs {
   int row_offset;
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // ---- thread-block cluster helpers ----
 __device__ __forceinline__ void cluster_sync_all() {
@@ -149,7 +148,7 @@ __device__ __forceinline__ void epi_swiglu(const EpiArgs& e, const GemmParams& p
 // `exch` is a [128][17] fp32 exchange buffer: the rotation partner of feature d is d +- D/2,
 // which lives in another epilogue warp.
 __device__ __forceinline__ void epi_qkv_rope(const EpiArgs& e, const GemmParams& p, const float (&v)[16], int r0, int r_lim, int n,
-                                              int n_local, float* exch) {
+                                              int n_local, float* exch, int pitch = 17) {
   const int D = e.d, half = D >> 1;
   const int head = n / D, d = n - head * D;
   const bool is_q = head < e.hq, is_k = !is_q && head < e.hq + e.hkv;
@@ -158,7 +157,7 @@ __device__ __forceinline__ void epi_qkv_rope(const EpiArgs& e, const GemmParams&
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     own[j] = bf16r(v[j]);
-    exch[n_local * 17 + j] = own[j];
+    if (j < pitch - 1) exch[n_local * pitch + j] = own[j];
   }
   epi_bar_sync();
   const bool first_half = d < half;
@@ -170,7 +169,7 @@ __device__ __forceinline__ void epi_qkv_rope(const EpiArgs& e, const GemmParams&
     if (r >= r_lim || n >= p.n) continue;
     float val = own[j];
     if (rot) {
-      const float other = exch[partner * 17 + j];
+      const float other = exch[partner * pitch + j];
       const float2 cs = e.rope_cs[r * half + fi];
       // first:  a*cos - b*sin   second: b*cos + a*sin   (own = a resp. b)
       const float t1 = bf16r(own[j] * cs.x), t2 = bf16r(other * cs.y);
@@ -276,11 +275,11 @@ __device__ __forceinline__ void epi_logits_group(const EpiArgs& e, const GemmPar
 
 template <int EPI>
 __device__ __forceinline__ void run_epilogue(const EpiArgs& e, const GemmParams& p, const float (&v)[16], int r0, int r_lim, int n,
-                                             int n_local, int lane, float* exch) {
+                                             int n_local, int lane, float* exch, int pitch = 17) {
   if (EPI == EPI_STORE_BF16) epi_store_bf16(e, p, v, r0, r_lim, n);
   if (EPI == EPI_RESIDUAL) epi_residual(e, p, v, r0, r_lim, n);
   if (EPI == EPI_SWIGLU) epi_swiglu(e, p, v, r0, r_lim, n, lane);
-  if (EPI == EPI_QKV_ROPE) epi_qkv_rope(e, p, v, r0, r_lim, n, n_local, exch);
+  if (EPI == EPI_QKV_ROPE) epi_qkv_rope(e, p, v, r0, r_lim, n, n_local, exch, pitch);
 }
 
 // ---- the kernel -------------------------------------------------------------------------

@@ -34,6 +34,7 @@ struct PrepareArgs {
   int mode, rows, P, T, D;
   int tiles_per_item;  // attention work-item size (attn_tiles_per_item)
   const float* rope_timescale;  // [D/2] min * (max/min)^(2i/D), embeddings.py:270-275
+  unsigned int* grid_bar;       // arrival counter of the persistent step kernel, reset here
 };
 
 // One block of 256 threads.  Fills the row descriptors, the RoPE table
@@ -96,7 +97,10 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
     const int base = s_off[tid];
     for (int c = 0; c < chunks; ++c) rd.work_items[base + c] = (tid << 16) | c;
   }
-  if (tid == 0) *rd.work_count = s_off[a.rows];
+  if (tid == 0) {
+    *rd.work_count = s_off[a.rows];
+    if (a.grid_bar != nullptr) *a.grid_bar = 0u;
+  }
   timeline_end(tl);
 }
 
