@@ -14,9 +14,9 @@
 #include "../../include/mtx_b200.h"
 #include "attention.cuh"
 #include "gemm_umma.cuh"
-#include "megakernel.cuh"
 #include "sampling.cuh"
 #include "step_kernels.cuh"
+#include "step_persistent.cuh"
 
 using namespace mtx;
 
@@ -208,7 +208,7 @@ int launch_gemm(const CUtensorMap& tw, const CUtensorMap& tx, GemmParams p, cons
 
 struct XMaps {
   bool built = false;
-  CUtensorMap n, attn, act;
+  CUtensorMap n, attn, act, x, h;
 };
 
 int log2_tile(int r_tile) {
@@ -244,8 +244,13 @@ struct mtx_engine {
   std::vector<CUtensorMap> tm_wqkv, tm_wo, tm_w01, tm_wout;
   CUtensorMap tm_logits, tm_k, tm_v;
   CUtensorMap tm_all_wqkv, tm_all_wo, tm_all_w01, tm_all_wout;  // all layers stacked: row = layer * N + n
-  int mega_clusters = 0;          // co-resident clusters of 8 for the persistent step kernel (0 = unavailable)
+  // persistent step kernel (step_persistent.cuh)
+  int pk_ctas = 0;  // CTAs of the persistent grid (0 = unavailable)
   unsigned int* grid_bar = nullptr;
+  PkTable* pk_tables = nullptr;
+  float *pk_part_ws = nullptr, *pk_ss_x = nullptr, *pk_ss_h = nullptr, *pk_attn_part_o = nullptr, *pk_attn_part_ml = nullptr;
+  int *pk_tile_cnt = nullptr, *pk_tile_prefix = nullptr, *pk_attn_info = nullptr, *pk_attn_tickets = nullptr;
+  int pk_tile_cnt_stride = 0;
   XMaps xmaps[5];
   // sampling
   int strategy = MTX_SAMPLE_GREEDY, top_k = 0;
@@ -261,8 +266,16 @@ struct WsLayout {
   size_t x, h, n, q, attn, act, attn_part_o, attn_part_ml, attn_tickets;
   size_t token, pos, plane, write_row, len0, ring_first, ring_len, rope_cs, work_items, work_count, rope_timescale;
   size_t part_score, part_idx, part_raw, part_max, part_sum, grid_bar;
+  size_t pk_tables, pk_part_ws, pk_tile_cnt, pk_ss_x, pk_ss_h, pk_attn_part_o, pk_attn_part_ml, pk_attn_tickets, pk_tile_prefix, pk_attn_info;
   size_t total;
 };
+
+int pk_tile_cnt_stride(const mtx_model_config& c) {
+  int n = (c.num_q_heads + 2 * c.num_kv_heads) * c.head_dim;
+  if (2 * c.mlp_dim > n) n = 2 * c.mlp_dim;
+  if (c.emb_dim > n) n = c.emb_dim;
+  return (n + kTileN - 1) / kTileN;
+}
 
 WsLayout layout_workspace(const mtx_engine* e) {
   const mtx_model_config& c = e->cfg;
@@ -302,6 +315,21 @@ WsLayout layout_workspace(const mtx_engine* e) {
   L.part_max = take(size_t(c.max_rows) * vt * 4);
   L.part_sum = take(size_t(c.max_rows) * vt * 4);
   L.grid_bar = take(64);
+  {
+    const size_t pk_rows = c.max_rows < kPkMaxRTile ? c.max_rows : kPkMaxRTile;
+    const size_t pairs = pk_rows * c.num_kv_heads;
+    const size_t ss_tiles = (c.emb_dim + 127) / 128;
+    L.pk_tables = take(size_t(e->num_sms) * sizeof(PkTable));
+    L.pk_part_ws = take(size_t(e->num_sms) * 4 * kPkSlotFloats * 4);
+    L.pk_tile_cnt = take(size_t(4) * pk_tile_cnt_stride(c) * 4);
+    L.pk_ss_x = take(size_t(kPkMaxRTile) * ss_tiles * 4);
+    L.pk_ss_h = take(size_t(kPkMaxRTile) * ss_tiles * 4);
+    L.pk_attn_part_o = take(pairs * kPkMaxParts * ((G * c.head_dim + 2 * G + 3) / 4 * 4) * 4);
+    L.pk_attn_part_ml = take(pairs * kPkMaxParts * G * 2 * 4);
+    L.pk_attn_tickets = take(pairs * 4);
+    L.pk_tile_prefix = take((pk_rows + 1) * 4);
+    L.pk_attn_info = take(64);
+  }
   L.total = off;
   return L;
 }
@@ -313,6 +341,8 @@ int get_xmaps(mtx_engine* e, int r_tile, XMaps** out) {
     MTX_TRY(make_map(&m.n, e->n, c.emb_dim, e->max_r_tile, r_tile));
     MTX_TRY(make_map(&m.attn, e->attn, uint64_t(c.num_q_heads) * c.head_dim, e->max_r_tile, r_tile));
     MTX_TRY(make_map(&m.act, e->act, c.mlp_dim, e->max_r_tile, r_tile));
+    MTX_TRY(make_map(&m.x, e->x, c.emb_dim, e->max_r_tile, r_tile));
+    MTX_TRY(make_map(&m.h, e->h, c.emb_dim, e->max_r_tile, r_tile));
     m.built = true;
   }
   *out = &m;
@@ -352,25 +382,91 @@ int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st) {
   return launch(decode_attn_kernel<128>, dim3(grid), dim3(kAttnThreads), smem, st, e->tm_k, e->tm_v, p);
 }
 
-// K splits of a per-layer GEMM inside the persistent kernel: a power of two <= 8 (one cluster), at most
-// the number of k-blocks and of padded rows, aiming at one split unit per resident CTA.
-int mega_splits(int n, int k, int r_tile, int ctas, bool qkv) {
-  const int tiles = (n + kTileN - 1) / kTileN, kb = k / kBlockK;
-  int s = 1;
-  while (s * 2 <= kMegaCluster && s * 2 <= kb && s * 2 <= r_tile && tiles * s * 2 <= ctas) s *= 2;
-  if (qkv && s > 1 && r_tile / s > kMegaExchPitch - 1) s = 1;  // the small RoPE exchange buffer holds 8 rows
-  return s;
+// ---- persistent step kernel: work tables and launch -------------------------------------------
+
+__global__ void fill_u32_kernel(uint32_t* dst, size_t n, uint32_t value) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) dst[i] = value;
 }
 
-bool mega_usable(const mtx_engine* e, int rows) {
-  return e->mega_clusters > 0 && round_rows(rows) <= kMegaMaxRTile && e->cfg.head_dim == 64;
+
+// Deals the (weight tile, k-block) units of one GEMM phase to the CTAs in contiguous equal ranges (stream-K).
+// A CTA gets at least `q_min` k-blocks so that no tile is shared by more than kPkMaxSplit CTAs.
+bool pk_fill_phase(std::vector<PkTable>& tabs, int ph, int n, int k) {
+  const int n_ctas = int(tabs.size());
+  const int n_tiles = (n + kTileN - 1) / kTileN, kbt = k / kBlockK;
+  const long long total = (long long)n_tiles * kbt;
+  int q_min = (kbt + kPkMaxSplit - 2) / (kPkMaxSplit - 1);
+  if (q_min < 2) q_min = 2;
+  // short reductions: at most 8 contributors, so a row slice is summed with one round of loads
+  if (kbt <= 32 && q_min < (kbt + 6) / 7) q_min = (kbt + 6) / 7;
+  if (q_min > kbt) q_min = kbt;
+  long long active = total / q_min;
+  if (active > n_ctas) active = n_ctas;
+  if (active < 1) active = 1;
+  std::vector<int> first(n_tiles, -1), count(n_tiles, 0);
+  // Small matrices (at least two CTAs per tile): every tile is split evenly over S consecutive CTAs, one unit per
+  // CTA, so nobody straddles two tiles and has to sit through two exchanges.
+  int uniform_s = 0;
+  if (n_tiles * 2 <= n_ctas) {
+    uniform_s = n_ctas / n_tiles;
+    if (uniform_s > kPkMaxSplit) uniform_s = kPkMaxSplit;
+    if (kbt <= 32 && uniform_s > 8) uniform_s = 8;
+    if (uniform_s > kbt / 2) uniform_s = kbt / 2 > 0 ? kbt / 2 : 1;
+  }
+  for (int c = 0; c < n_ctas; ++c) {
+    PkTable& t = tabs[c];
+    t.n_units[ph] = 0;
+    t.kbs[ph] = 0;
+    if (uniform_s > 0) {
+      const int tile = c / uniform_s, si = c % uniform_s;
+      if (tile >= n_tiles) continue;
+      PkUnit& u = t.u[ph][t.n_units[ph]++];
+      u.tile = tile;
+      u.kb0 = si * kbt / uniform_s;
+      u.kb1 = (si + 1) * kbt / uniform_s;
+      t.kbs[ph] = u.kb1 - u.kb0;
+      if (first[tile] < 0) first[tile] = c;
+      ++count[tile];
+      continue;
+    }
+    if (c >= active) continue;
+    long long lo = c * total / active, hi = (c + 1) * total / active;
+    while (lo < hi) {
+      const int tile = int(lo / kbt);
+      long long end = (long long)(tile + 1) * kbt;
+      if (end > hi) end = hi;
+      if (t.n_units[ph] >= kPkMaxUnits) return false;
+      PkUnit& u = t.u[ph][t.n_units[ph]++];
+      u.tile = tile;
+      u.kb0 = int(lo - (long long)tile * kbt);
+      u.kb1 = int(end - (long long)tile * kbt);
+      t.kbs[ph] += u.kb1 - u.kb0;
+      if (first[tile] < 0) first[tile] = c;
+      ++count[tile];
+      lo = end;
+    }
+  }
+  for (int c = 0; c < n_ctas; ++c)
+    for (int i = 0; i < tabs[c].n_units[ph]; ++i) {
+      PkUnit& u = tabs[c].u[ph][i];
+      u.c_first = first[u.tile];
+      u.S = count[u.tile];
+      if (u.S > kPkMaxSplit) return false;
+    }
+  return true;
 }
 
-int launch_megakernel(mtx_engine* e, int rows, const XMaps& xm, const EpiArgs& logits_epi, cudaStream_t st) {
+bool pk_usable(const mtx_engine* e, int rows) {
+  if (e->pk_ctas <= 0 || round_rows(rows) > kPkMaxRTile) return false;
+  // an attention warp's tile list holds kPkAttnListMax entries: bound the worst case (every context full)
   const mtx_model_config& c = e->cfg;
-  const int r_tile = round_rows(rows);
-  const int ctas = e->mega_clusters * kMegaCluster;
-  MegaParams p;
+  const long long worst = (long long)rows * c.num_kv_heads * attn_max_tiles(c.max_prefill_len, c.max_target_len);
+  return worst <= (long long)e->pk_ctas * kPkAttnWarps * kPkAttnListMax;
+}
+
+int launch_persistent(mtx_engine* e, int rows, const XMaps& xm, const EpiArgs& logits_epi, cudaStream_t st) {
+  const mtx_model_config& c = e->cfg;
+  PkParams p;
   memset(&p, 0, sizeof(p));
   p.L = c.num_layers;
   p.E = c.emb_dim;
@@ -384,12 +480,11 @@ int launch_megakernel(mtx_engine* e, int rows, const XMaps& xm, const EpiArgs& l
   p.t_alloc = c.max_target_len;
   p.num_slots = c.num_slots;
   p.rows = rows;
-  p.r_tile = r_tile;
+  p.r_tile = round_rows(rows);
+  p.P = c.max_prefill_len;
+  p.T = c.max_target_len;
   p.eps = c.rms_eps;
-  p.s_qkv = mega_splits(e->qkv_n, p.E, r_tile, ctas, true);
-  p.s_oproj = mega_splits(p.E, p.HD, r_tile, ctas, false);
-  p.s_up = mega_splits(2 * p.M, p.E, r_tile, ctas, false);
-  p.s_down = mega_splits(p.E, p.M, r_tile, ctas, false);
+  p.softcap = c.attn_softcap;
   p.x = e->x;
   p.h = e->h;
   p.n = e->n;
@@ -406,60 +501,26 @@ int launch_megakernel(mtx_engine* e, int rows, const XMaps& xm, const EpiArgs& l
   p.token = e->rd.token;
   p.plane = e->rd.plane;
   p.write_row = e->rd.write_row;
+  p.len0 = e->rd.len0;
+  p.ring_first = e->rd.ring_first;
+  p.ring_len = e->rd.ring_len;
   p.rope_cs = e->rd.rope_cs;
-  AttnParams& a = p.attn_args;
-  a.q = e->q;
-  a.out = e->attn;
-  a.plane = e->rd.plane;
-  a.len0 = e->rd.len0;
-  a.ring_first = e->rd.ring_first;
-  a.ring_len = e->rd.ring_len;
-  a.work_items = e->rd.work_items;
-  a.work_count = e->rd.work_count;
-  a.part_o = e->attn_part_o;
-  a.part_ml = e->attn_part_ml;
-  a.tickets = e->attn_tickets;
-  a.rows = rows;
-  a.hq = c.num_q_heads;
-  a.hkv = c.num_kv_heads;
-  a.P = c.max_prefill_len;
-  a.T = c.max_target_len;
-  a.tiles_per_item = attn_tiles_per_item(rows, c.num_kv_heads, c.max_prefill_len, c.max_target_len, e->num_sms);
-  a.max_chunks = e->attn_max_chunks;
-  a.softcap = c.attn_softcap;
-  a.trace = nullptr;
+  p.tile_prefix = e->pk_tile_prefix;
+  p.attn_info = e->pk_attn_info;
+  p.attn_part_o = e->pk_attn_part_o;
+  p.attn_part_ml = e->pk_attn_part_ml;
+  p.attn_tickets = e->pk_attn_tickets;
+  p.part_ws = e->pk_part_ws;
+  p.tile_cnt = e->pk_tile_cnt;
+  p.tile_cnt_stride = e->pk_tile_cnt_stride;
+  p.ss_x = e->pk_ss_x;
+  p.ss_h = e->pk_ss_h;
+  p.tables = e->pk_tables;
   p.logits = logits_epi;
   p.grid_bar = e->grid_bar;
   p.trace = g_trace;
-
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(ctas);
-  cfg.blockDim = dim3(kMegaThreads);
-  cfg.dynamicSmemBytes = mega_smem_bytes();
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = kMegaCluster;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  ProfileSink::Rec rec;
-  if (g_profile != nullptr) {
-    rec.cls = KC_QKV;
-    MTX_CUDA(cudaEventCreate(&rec.a));
-    MTX_CUDA(cudaEventCreate(&rec.b));
-    MTX_CUDA(cudaEventRecord(rec.a, st));
-  }
-  MTX_CUDA(cudaLaunchKernelEx(&cfg, step_megakernel, e->tm_all_wqkv, e->tm_all_wo, e->tm_all_w01, e->tm_all_wout, e->tm_logits, xm.n,
-                              xm.attn, xm.act, e->tm_k, e->tm_v, p));
-  if (g_profile != nullptr) {
-    MTX_CUDA(cudaEventRecord(rec.b, st));
-    g_profile->recs.push_back(rec);
-  }
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return MTX_OK;
+  return launch(step_persistent_kernel, dim3(e->pk_ctas), dim3(kPkThreads), pk_smem_bytes(), st, e->tm_all_wqkv, e->tm_all_wo, e->tm_all_w01,
+                e->tm_all_wout, e->tm_logits, xm.x, xm.attn, xm.h, xm.act, xm.n, e->tm_k, e->tm_v, p);
 }
 
 // The kernels of one step, in stream order.  mode 0 = decode, 1 = prefill chunk.
@@ -489,7 +550,17 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   pa.D = c.head_dim;
   pa.tiles_per_item = attn_tiles_per_item(rows, c.num_kv_heads, c.max_prefill_len, c.max_target_len, e->num_sms);
   pa.rope_timescale = e->rope_timescale;
-  pa.grid_bar = e->grid_bar;
+  const bool mega = mode == 0 && want_logits && pk_usable(e, rows);
+  if (mega) {
+    pa.grid_bar = e->grid_bar;
+    pa.tile_cnt = e->pk_tile_cnt;
+    pa.tile_cnt_n = 4 * e->pk_tile_cnt_stride;
+    pa.tile_prefix = e->pk_tile_prefix;
+    pa.attn_info = e->pk_attn_info;
+    pa.hkv = c.num_kv_heads;
+    pa.pk_ctas = e->pk_ctas;
+    pa.pk_max_parts = kPkMaxParts;
+  }
   g_class = KC_PREPARE;
   MTX_TRY(launch(prepare_rows_kernel, dim3(1), dim3(256), 0, st, pa, e->rd));
   g_class = KC_RMSNORM;
@@ -499,7 +570,6 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   gp.rows = rows;
   gp.r_tile = r_tile;
   const GemmPlan plan_logits = plan_gemm(c.vocab_size, c.emb_dim, r_tile, e->num_sms, EPI_LOGITS, 1);
-  const bool mega = mode == 0 && want_logits && mega_usable(e, rows);
   if (!mega) {
   const bf16* attn_norm = static_cast<const bf16*>(e->w.attn_norm);
   const bf16* mlp_norm = static_cast<const bf16*>(e->w.mlp_norm);
@@ -600,7 +670,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     g_class = KC_LOGITS;
     if (mega) {
       g_class = KC_QKV;
-      MTX_TRY(launch_megakernel(e, rows, *xm, ea, st));
+      MTX_TRY(launch_persistent(e, rows, *xm, ea, st));
     } else {
       MTX_TRY(launch_gemm<EPI_LOGITS>(e->tm_logits, xm->n, gp, ea, plan_logits, st));
     }
@@ -761,6 +831,17 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   e->part_max = reinterpret_cast<float*>(b + L.part_max);
   e->part_sum = reinterpret_cast<float*>(b + L.part_sum);
   e->grid_bar = reinterpret_cast<unsigned int*>(b + L.grid_bar);
+  e->pk_tables = reinterpret_cast<PkTable*>(b + L.pk_tables);
+  e->pk_part_ws = reinterpret_cast<float*>(b + L.pk_part_ws);
+  e->pk_tile_cnt = reinterpret_cast<int*>(b + L.pk_tile_cnt);
+  e->pk_tile_cnt_stride = pk_tile_cnt_stride(c);
+  e->pk_ss_x = reinterpret_cast<float*>(b + L.pk_ss_x);
+  e->pk_ss_h = reinterpret_cast<float*>(b + L.pk_ss_h);
+  e->pk_attn_part_o = reinterpret_cast<float*>(b + L.pk_attn_part_o);
+  e->pk_attn_part_ml = reinterpret_cast<float*>(b + L.pk_attn_part_ml);
+  e->pk_attn_tickets = reinterpret_cast<int*>(b + L.pk_attn_tickets);
+  e->pk_tile_prefix = reinterpret_cast<int*>(b + L.pk_tile_prefix);
+  e->pk_attn_info = reinterpret_cast<int*>(b + L.pk_attn_info);
   MTX_CUDA(cudaMemcpy(e->rope_timescale, e->rope_timescale_host.data(), e->rope_timescale_host.size() * 4, cudaMemcpyHostToDevice));
 
   const int E = c.emb_dim, HD = c.num_q_heads * c.head_dim, M = c.mlp_dim, L_ = c.num_layers;
@@ -779,25 +860,27 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   MTX_TRY(make_map(&e->tm_all_wo, w->wo, HD, uint64_t(L_) * E, kTileN));
   MTX_TRY(make_map(&e->tm_all_w01, w->w01, E, uint64_t(L_) * 2 * M, kTileN));
   MTX_TRY(make_map(&e->tm_all_wout, w->wout, M, uint64_t(L_) * E, kTileN));
-  e->mega_clusters = 0;
-  if (c.head_dim == 64 && env_int("MTX_MEGAKERNEL", 0) != 0) {
-    cudaError_t a1 = cudaFuncSetAttribute(step_megakernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(mega_smem_bytes()));
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(kMegaCluster * 64);
-    cfg.blockDim = dim3(kMegaThreads);
-    cfg.dynamicSmemBytes = mega_smem_bytes();
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = kMegaCluster;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    int n = 0;
-    if (a1 == cudaSuccess && cudaOccupancyMaxActiveClusters(&n, step_megakernel, &cfg) == cudaSuccess && n > 0) {
-      const int cap = env_int("MTX_MEGA_CLUSTERS", 0);
-      e->mega_clusters = (cap > 0 && cap < n) ? cap : n;
+  e->pk_ctas = 0;
+  if (c.head_dim == 64 && env_int("MTX_PERSISTENT", 1) != 0) {
+    // one CTA per SM, all co-resident (the grid barrier spins): needs the full shared-memory carve-out
+    int blocks = 0;
+    if (cudaFuncSetAttribute(step_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pk_smem_bytes())) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, step_persistent_kernel, kPkThreads, pk_smem_bytes()) == cudaSuccess && blocks >= 1) {
+      int ctas = e->num_sms;
+      const int cap = env_int("MTX_PERSISTENT_CTAS", 0);
+      if (cap > 0 && cap < ctas) ctas = cap;
+      std::vector<PkTable> tabs(ctas);
+      memset(tabs.data(), 0, tabs.size() * sizeof(PkTable));
+      const bool ok = pk_fill_phase(tabs, PK_QKV, e->qkv_n, E) && pk_fill_phase(tabs, PK_OPROJ, E, HD) &&
+                      pk_fill_phase(tabs, PK_UP, 2 * M, E) && pk_fill_phase(tabs, PK_DOWN, E, M);
+      if (ok) {
+        MTX_CUDA(cudaMemcpy(e->pk_tables, tabs.data(), tabs.size() * sizeof(PkTable), cudaMemcpyHostToDevice));
+        // the split-K exchange workspace starts out (and is left by every reader) as "nothing written"
+        fill_u32_kernel<<<256, 256>>>(reinterpret_cast<uint32_t*>(e->pk_part_ws), size_t(e->num_sms) * 4 * kPkSlotFloats, kPkSentinel);
+        MTX_CUDA(cudaGetLastError());
+        MTX_CUDA(cudaDeviceSynchronize());
+        e->pk_ctas = ctas;
+      }
     }
     cudaGetLastError();
   }

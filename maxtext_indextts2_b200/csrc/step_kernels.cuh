@@ -34,7 +34,15 @@ struct PrepareArgs {
   int mode, rows, P, T, D;
   int tiles_per_item;  // attention work-item size (attn_tiles_per_item)
   const float* rope_timescale;  // [D/2] min * (max/min)^(2i/D), embeddings.py:270-275
-  unsigned int* grid_bar;       // arrival counter of the persistent step kernel, reset here
+  // persistent step kernel (step_persistent.cuh): counters reset here, attention tile partition
+  unsigned int* grid_bar;  // grid-barrier arrival counter
+  int* tile_cnt;           // split-K exchange counters
+  int tile_cnt_n;
+  int* tile_prefix;        // [rows + 1] exclusive prefix of the per-row 64-row tile counts
+  int* attn_info;          // [0] CTAs that get attention work, [1] total tiles over all kv heads
+  int hkv;
+  int pk_ctas;             // CTAs of the persistent grid
+  int pk_max_parts;        // most CTAs that may share one (row, kv head)
 };
 
 // One block of 256 threads.  Fills the row descriptors, the RoPE table
@@ -42,6 +50,7 @@ struct PrepareArgs {
 __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
   __shared__ int s_off[257];
   __shared__ int s_pos[256];
+  __shared__ int s_nt[256];
   const int tl = timeline_begin(0);
   griddep_launch_dependents();
   griddep_wait();
@@ -76,7 +85,8 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
     rd.len0[tid] = l0;
     rd.ring_first[tid] = rf;
     rd.ring_len[tid] = rl;
-    chunks = (attn_num_tiles(l0, rf, rl, R) + a.tiles_per_item - 1) / a.tiles_per_item;
+    s_nt[tid] = attn_num_tiles(l0, rf, rl, R);
+    chunks = (s_nt[tid] + a.tiles_per_item - 1) / a.tiles_per_item;
     s_pos[tid] = pos;
   }
   s_off[tid + 1] = chunks;
@@ -97,9 +107,28 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
     const int base = s_off[tid];
     for (int c = 0; c < chunks; ++c) rd.work_items[base + c] = (tid << 16) | c;
   }
-  if (tid == 0) {
-    *rd.work_count = s_off[a.rows];
-    if (a.grid_bar != nullptr) *a.grid_bar = 0u;
+  if (tid == 0) *rd.work_count = s_off[a.rows];
+  if (a.grid_bar != nullptr) {
+    for (int i = tid; i < a.tile_cnt_n; i += 256) a.tile_cnt[i] = 0;
+    if (tid == 0) {
+      *a.grid_bar = 0u;
+      int acc = 0, nt_max = 1;
+      for (int r = 0; r < a.rows; ++r) {
+        a.tile_prefix[r] = acc;
+        acc += s_nt[r];
+        nt_max = s_nt[r] > nt_max ? s_nt[r] : nt_max;
+      }
+      a.tile_prefix[a.rows] = acc;
+      // every active CTA gets total / nc tiles (rounded either way); a pair of nt tiles then spans at most
+      // (nt - 1) / floor(total / nc) + 2 CTAs, which must not exceed pk_max_parts
+      const int total = acc * a.hkv;
+      const int qmin = (nt_max + a.pk_max_parts - 3) / (a.pk_max_parts - 2);
+      int nc = total / (qmin < 1 ? 1 : qmin);
+      if (nc > a.pk_ctas) nc = a.pk_ctas;
+      if (nc < 1) nc = 1;
+      a.attn_info[0] = nc;
+      a.attn_info[1] = total;
+    }
   }
   timeline_end(tl);
 }

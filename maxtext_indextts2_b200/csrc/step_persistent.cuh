@@ -1,0 +1,1440 @@
+// The whole decode step as ONE persistent kernel: one CTA per SM, no clusters.
+//
+// Why: as separate kernels every phase of a layer (QKV, attention, out-proj, MLP up, MLP down, two
+// norms) costs 8-16 us of launch / drain / dependency latency against 0.5-10 us of HBM time
+// (profiles/, round 1).  Here a phase boundary is one grid barrier (~1 us) and the HBM stream never
+// stops at it: the weight producer of every CTA runs AHEAD of the barrier, pulling the next phases'
+// weight tiles into its shared-memory ring while the current phase drains (weights never depend on
+// activations); only the small activation tiles wait for the barrier.
+//
+// Per layer five phases, five grid barriers:
+//   QKV GEMM (+RMSNorm of x in shared memory, RoPE, KV append) | attention | out-proj (+residual,
+//   row sum-of-squares) | MLP up (+RMSNorm of h, SwiGLU) | MLP down (+residual, row sum-of-squares)
+// then one small final-norm phase and the logits GEMM with the sampling partials.
+//
+// RMSNorm is never a phase of its own: the epilogue that produces x (or h) also emits per-row partial
+// sums of squares; the consuming GEMM normalises its activation k-blocks in shared memory (the exact
+// bf16 rounding sequence of normalizations.py:57-69) before the MMA reads them.
+//
+// GEMM work is cut stream-K style: the (weight tile, k-block) units of a phase are dealt to the CTAs
+// in contiguous equal ranges, so every SM streams the same number of weight bytes whatever the matrix
+// shape.  CTAs that share a weight tile exchange fp32 partial tiles through an L2-resident workspace
+// (write partial, bump the tile's counter, wait for the peers, sum a row slice in fixed order) and
+// each finishes the epilogue of its own row slice: deterministic, no atomics on data.
+//
+// Epilogues work on ROW-MAJOR float4 fragments (a warp = 128 consecutive output features of one row),
+// so RoPE / SwiGLU partners are a warp shuffle away and every global store is an 8-byte piece of a
+// 256-byte coalesced row segment.
+//
+// Roles (384 threads): warp 0 weight producer (TMA) | warp 1 tcgen05.mma issuer | warps 2-5 epilogue |
+// warps 6-11 attention; during the GEMM phases warps 6-9 normalise activation tiles and warp 10 is the
+// activation producer (TMA).  Every role walks the same static fill sequence with its own lean loop.
+// Attention is stream-K over 64-row KV tiles at WARP granularity: every attention warp of the grid
+// gets the same number of tiles (the partition is computed once per step: lengths do not change between
+// layers); pairs (row, kv head) that span warps merge through an L2 workspace, the last warp to arrive
+// writing the result.
+#pragma once
+
+#include <type_traits>
+
+#include "attention.cuh"
+#include "gemm_umma.cuh"
+#include "step_kernels.cuh"
+
+namespace mtx {
+
+constexpr int kPkThreads = 384;
+constexpr int kPkStages = 4;
+constexpr int kPkMaxRTile = 64;
+constexpr int kPkStageBytes = kWTileBytes + kPkMaxRTile * kBlockK * 2;  // 24 KB
+constexpr int kPkRingBytes = kPkStages * kPkStageBytes;                 // 96 KB
+constexpr int kPkAttnWarps = 6;
+constexpr int kPkAttnBytes = kPkAttnWarps * 2 * (64 * 64 * 2);          // 96 KB: per warp one K and one V tile (D = 64)
+constexpr int kPkParkFloats = kPkMaxRTile * 128;                        // 32 KB, aliases the attention tiles
+constexpr int kPkAccBufs = 4;                                           // TMEM accumulators
+constexpr int kPkMaxUnits = 4;                                          // work units of one CTA in one phase
+constexpr int kPkMaxSplit = 16;                                         // CTAs sharing one weight tile
+constexpr int kPkMaxParts = 16;                                         // attention warps sharing one (row, kv head)
+constexpr int kPkSlotFloats = 64 * 128;                                 // one partial tile in the exchange workspace
+constexpr uint32_t kPkSentinel = 0xFFFFDEADu;                           // "not written yet" word of the exchange workspace (a NaN no MMA produces)
+constexpr int kPkParkPitch = 136;                                       // floats per row of the parked logits tile (conflict-free scans)
+constexpr int kPkAttnListMax = 32;                                      // KV tiles one attention warp may own per layer
+constexpr int kPkAttnSlotFloats = 16 * 64 + 2 * 16;                     // one attention partial (O, m, l), G <= 16, D = 64
+
+enum PkPhase : int { PK_QKV = 0, PK_OPROJ = 1, PK_UP = 2, PK_DOWN = 3, PK_LOGITS = 4, PK_END = 5 };
+
+struct PkUnit {
+  int tile;     // 128-row weight tile
+  int kb0, kb1; // k-block range
+  int c_first;  // first CTA contributing to this tile
+  int S;        // number of contributing CTAs (consecutive)
+};
+
+struct PkTable {
+  int n_units[4];
+  int kbs[4];  // k-blocks of this CTA per phase
+  PkUnit u[4][kPkMaxUnits];
+};
+
+struct PkTail {
+  uint64_t full_w[kPkStages];
+  uint64_t full_x[kPkStages];
+  uint64_t xready[kPkStages];
+  uint64_t empty[kPkStages];
+  uint64_t tmem_full[kPkAccBufs];
+  uint64_t tmem_empty[kPkAccBufs];
+  uint64_t attn_bars[2 * kPkAttnWarps];
+  uint32_t tmem_base;
+  volatile uint32_t bar_done;  // grid barriers this CTA has seen complete
+  float rstd[kPkMaxRTile];
+  float red[8];
+  // row descriptors of the step (constant across layers), staged once for the attention warps
+  int r_len0[kPkMaxRTile], r_rf[kPkMaxRTile], r_rl[kPkMaxRTile], r_plane[kPkMaxRTile], r_prefix[kPkMaxRTile + 1];
+  // attention: this CTA's warps own contiguous runs of KV tiles, the same for every layer of the step
+  int a_count[kPkAttnWarps];
+  int2 a_list[kPkAttnWarps][kPkAttnListMax];  // .x = cache row of the tile (layer 0), .y = PkAttnMeta bits
+  int4 a_seg[kPkAttnWarps][2];                // partial segments of the current layer: .x = pair (-1: none), .y = flags
+  float a_slot[kPkAttnWarps][kPkAttnSlotFloats];  // partial of a warp's first segment (its K/V buffers stay busy)
+  PkTable tab;
+};
+
+__host__ __device__ inline size_t pk_smem_bytes() { return 1024 + kPkRingBytes + kPkAttnBytes + sizeof(PkTail) + 64; }
+
+struct PkParams {
+  int L, E, HD, M, qkv_n, V;
+  int hq, hkv, d, t_alloc, num_slots;
+  int rows, r_tile;
+  int P, T;
+  float eps, softcap;
+  // activations [r_tile, *] bf16
+  bf16 *x, *h, *n, *q, *attn, *act;
+  const bf16 *embedding, *attn_norm, *mlp_norm, *final_norm;
+  bf16 *k_cache, *v_cache;
+  long long kv_layer_elems;
+  // row descriptors (prepare_rows_kernel)
+  const int *token, *plane, *write_row, *len0, *ring_first, *ring_len;
+  const float2* rope_cs;
+  const int* tile_prefix;  // [rows + 1] exclusive prefix of the per-row tile counts
+  const int* attn_info;    // [0] active attention warps, [1] total tiles (all kv heads)
+  // attention merge workspace
+  float* attn_part_o;   // [pairs, kPkMaxParts, G, D]
+  float* attn_part_ml;  // [pairs, kPkMaxParts, G, 2]
+  int* attn_tickets;    // [pairs]
+  // split-K exchange
+  float* part_ws;  // [n_ctas * 4] slots of kPkSlotFloats
+  int* tile_cnt;   // [4, tile_cnt_stride] zeroed by prepare_rows_kernel
+  int tile_cnt_stride;
+  float* ss_x;     // [E/128 rounded up, kPkMaxRTile] partial sums of squares of the rows of x, one per 128-feature tile
+  float* ss_h;
+  const PkTable* tables;  // [n_ctas]
+  EpiArgs logits;
+  unsigned int* grid_bar;  // zeroed by prepare_rows_kernel
+  long long* trace;        // debug: globaltimer at [barrier k][arrive|release][cta], or null
+};
+
+// ---- small helpers -----------------------------------------------------------------------
+
+// Debug event log: (id, globaltimer) pairs, 32 per role and CTA, after the barrier stamps.
+struct PkEv {
+  long long* base;
+  int n;
+  bool on;
+};
+__device__ __forceinline__ PkEv pk_ev_make(const PkParams& p, int role) {
+  PkEv e;
+  e.base = p.trace ? p.trace + 2 * 200 * (long long)gridDim.x + ((long long)blockIdx.x * 3 + role) * 64 : nullptr;
+  e.n = 0;
+  e.on = false;
+  return e;
+}
+__device__ __forceinline__ void pk_ev(PkEv& e, int id) {
+  if (e.base != nullptr && e.on && e.n < 32) {
+    e.base[2 * e.n] = id;
+    e.base[2 * e.n + 1] = (long long)globaltimer_ns();
+    ++e.n;
+  }
+}
+
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void pk_wait_flag(volatile uint32_t* flag, uint32_t want) {
+  if (*flag >= want) return;
+  const long long t0 = clock64();
+  while (*flag < want) {  // plain spin: __nanosleep wakes microseconds late, and every waiter is on a critical path
+    if (clock64() - t0 > 4000000000LL) {
+      printf("mtx: phase flag wait timed out (block %d thread %d want %u have %u)\n", blockIdx.x, threadIdx.x, want, *flag);
+      __trap();
+    }
+  }
+}
+
+// Grid barrier k, executed by ONE thread of the CTA after the CTA's writers have met at a CTA barrier (the
+// fence below is cumulative over their writes, as in cooperative-groups grid.sync()).
+__device__ __forceinline__ void pk_grid_barrier(const PkParams& p, PkTail* tail, uint32_t k) {
+  // The arrival counter is cumulative: a CTA with nothing to do in a phase must not run ahead and have its
+  // arrival counted towards a barrier that is still collecting.
+  pk_wait_flag(&tail->bar_done, k - 1);
+  __threadfence();
+  if (p.trace) p.trace[(2 * k) * gridDim.x + blockIdx.x] = (long long)globaltimer_ns();
+  atomicAdd(p.grid_bar, 1u);
+  const uint32_t target = k * gridDim.x;
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(p.grid_bar) < target) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("mtx: grid barrier %u timed out (block %d)\n", k, blockIdx.x);
+      __trap();
+    }
+  }
+  if (p.trace) p.trace[(2 * k + 1) * gridDim.x + blockIdx.x] = (long long)globaltimer_ns();
+  tail->bar_done = k;
+  __threadfence_block();
+}
+
+// Barrier ordinals: 1 after the embedding gather; layer l: 2+5l after QKV, 3+5l after attention, 4+5l after
+// out-proj, 5+5l after MLP up, 6+5l after MLP down; then 2+5L after the final norm.  A phase may read its
+// activations once `need` barriers have completed.
+__device__ __forceinline__ uint32_t pk_need(int layer, int ph, int L) {
+  if (ph == PK_QKV) return uint32_t(1 + 5 * layer);
+  if (ph == PK_LOGITS) return uint32_t(2 + 5 * L);
+  return uint32_t(2 + 5 * layer + ph);  // out-proj 3+5l, up 4+5l, down 5+5l
+}
+
+// Ring cursor: stage index and use parity of consecutive fills.
+struct PkCursor {
+  int s;
+  uint32_t par;   // parity of the current use of stage s
+  uint32_t uses;  // 0 while the ring is being filled for the first time
+};
+__device__ __forceinline__ void pk_cursor_init(PkCursor& c) {
+  c.s = 0;
+  c.par = 0;
+  c.uses = 0;
+}
+__device__ __forceinline__ void pk_cursor_next(PkCursor& c) {
+  if (++c.s == kPkStages) {
+    c.s = 0;
+    c.par ^= 1;
+    c.uses = 1;
+  }
+}
+__device__ __forceinline__ void pk_cursor_skip(PkCursor& c, int n) {
+  const int t = c.s + n;
+  const int wraps = t / kPkStages;
+  c.s = t - wraps * kPkStages;
+  if (wraps) c.uses = 1;
+  c.par ^= uint32_t(wraps & 1);
+}
+
+__device__ __forceinline__ float4 ldcg_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Rounds two fp32 values to bf16 (round-to-nearest-even) with ONE packed conversion and returns them as fp32.
+__device__ __forceinline__ void bf16r2(float a, float b, float& ra, float& rb) {
+  const uint32_t pk = pack_bf16x2(a, b);
+  ra = bf16_lo(pk);
+  rb = bf16_hi(pk);
+}
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) { return make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d)); }
+
+// ---- row-major epilogues: a warp holds features n0 = tile*128 + 4*lane .. +3 of row r ----------------
+
+// out[r, n] = bf16(resid[r, n] + bf16(acc)); also the row's partial sum of squares over this tile.
+__device__ __forceinline__ void pk_epi_residual(const float4 a, const uint2 rv, int r, int tile, int lane, int N, bf16* out, float* ss,
+                                                int ss_tiles) {
+  const int n0 = tile * 128 + lane * 4;
+  float sq = 0.0f;
+  if (n0 < N) {
+    float a0, a1, a2, a3;
+    bf16r2(a.x, a.y, a0, a1);
+    bf16r2(a.z, a.w, a2, a3);
+    const uint2 pk = pack_bf16x4(bf16_lo(rv.x) + a0, bf16_hi(rv.x) + a1, bf16_lo(rv.y) + a2, bf16_hi(rv.y) + a3);
+    *reinterpret_cast<uint2*>(out + (long long)r * N + n0) = pk;
+    const float o0 = bf16_lo(pk.x), o1 = bf16_hi(pk.x), o2 = bf16_lo(pk.y), o3 = bf16_hi(pk.y);
+    sq = o0 * o0 + o1 * o1 + o2 * o2 + o3 * o3;
+  }
+  sq = warp_sum(sq);
+  if (lane == 0) ss[tile * kPkMaxRTile + r] = sq;
+}
+
+// linears.py:425-476 with mlp_activations [silu, linear]: rows of w01 are interleaved 16 at a time (gate, value),
+// so the value of a gate feature sits 16 features (4 lanes) further.
+__device__ __forceinline__ void pk_epi_swiglu(const float4 a, int r, int tile, int lane, int N2, int M, bf16* act) {
+  const float bx = __shfl_xor_sync(0xffffffffu, a.x, 4), by = __shfl_xor_sync(0xffffffffu, a.y, 4);
+  const float bz = __shfl_xor_sync(0xffffffffu, a.z, 4), bw = __shfl_xor_sync(0xffffffffu, a.w, 4);
+  const int n0 = tile * 128 + lane * 4;
+  if ((lane & 4) == 0 && n0 < N2) {
+    float g[4], v[4], sg[4], t[4];
+    bf16r2(a.x, a.y, g[0], g[1]);
+    bf16r2(a.z, a.w, g[2], g[3]);
+    bf16r2(bx, by, v[0], v[1]);
+    bf16r2(bz, bw, v[2], v[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sg[i] = __fdividef(1.0f, 1.0f + __expf(-g[i]));
+    bf16r2(sg[0], sg[1], sg[0], sg[1]);
+    bf16r2(sg[2], sg[3], sg[2], sg[3]);
+    bf16r2(g[0] * sg[0], g[1] * sg[1], t[0], t[1]);
+    bf16r2(g[2] * sg[2], g[3] * sg[3], t[2], t[3]);
+    const int m0 = tile * 64 + (lane >> 3) * 16 + (lane & 3) * 4;
+    *reinterpret_cast<uint2*>(act + (long long)r * M + m0) = pack_bf16x4(t[0] * v[0], t[1] * v[1], t[2] * v[2], t[3] * v[3]);
+  }
+}
+
+// Side inputs of the QKV epilogue for one row fragment: they do not depend on the accumulator, so they are
+// requested together with the partial tiles.
+struct PkQkvSide {
+  float4 c01, c23;  // (cos, sin) pairs of the four features
+  int plane, wr;
+};
+__device__ __forceinline__ PkQkvSide pk_qkv_side(const PkParams& p, int r, int tile, int lane) {
+  PkQkvSide s;
+  const int n0 = tile * 128 + lane * 4;
+  const float4* cs = reinterpret_cast<const float4*>(p.rope_cs + r * 32 + (n0 & 31));
+  s.c01 = cs[0];
+  s.c23 = cs[1];
+  s.plane = p.plane[r];
+  s.wr = p.write_row[r];
+  return s;
+}
+
+// embeddings.py:304-315 (half-split rotation in bf16) + kvcache.py:626-718 (append).  D = 64: the rotation partner
+// of feature d is d +- 32, eight lanes away.
+__device__ __forceinline__ void pk_epi_qkv(const float4 a, const PkQkvSide& sd, int r, int tile, int lane, const PkParams& p, bf16* k_layer,
+                                           bf16* v_layer) {
+  float own[4], oth[4];
+  bf16r2(a.x, a.y, own[0], own[1]);
+  bf16r2(a.z, a.w, own[2], own[3]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) oth[i] = __shfl_xor_sync(0xffffffffu, own[i], 8);
+  const int n0 = tile * 128 + lane * 4;
+  if (n0 >= p.qkv_n) return;
+  const int head = n0 >> 6, d0 = n0 & 63;
+  const bool is_q = head < p.hq, is_k = !is_q && head < p.hq + p.hkv;
+  float val[4] = {own[0], own[1], own[2], own[3]};
+  if (is_q || is_k) {
+    const float c[4] = {sd.c01.x, sd.c01.z, sd.c23.x, sd.c23.z}, s[4] = {sd.c01.y, sd.c01.w, sd.c23.y, sd.c23.w};
+    float t1[4], t2[4];
+    bf16r2(own[0] * c[0], own[1] * c[1], t1[0], t1[1]);
+    bf16r2(own[2] * c[2], own[3] * c[3], t1[2], t1[3]);
+    bf16r2(oth[0] * s[0], oth[1] * s[1], t2[0], t2[1]);
+    bf16r2(oth[2] * s[2], oth[3] * s[3], t2[2], t2[3]);
+    const bool first = d0 < 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) val[i] = first ? (t1[i] - t2[i]) : (t1[i] + t2[i]);
+  }
+  const uint2 packed = pack_bf16x4(val[0], val[1], val[2], val[3]);
+  if (is_q) {
+    *reinterpret_cast<uint2*>(p.q + (long long)r * p.HD + n0) = packed;
+  } else if (sd.wr >= 0) {
+    const int kvh = is_k ? head - p.hq : head - p.hq - p.hkv;
+    const long long off = (((long long)sd.plane * p.hkv + kvh) * p.t_alloc + sd.wr) * 64 + d0;
+    *reinterpret_cast<uint2*>((is_k ? k_layer : v_layer) + off) = packed;
+  }
+}
+
+// decoders.py:537-589: logits = bf16(dot) (* 1/sqrt(E) when tied), optional tanh soft cap, fp32.
+__device__ __forceinline__ float4 pk_logit_transform(const EpiArgs& e, float4 a) {
+  if (e.round_bf16) {
+    bf16r2(a.x, a.y, a.x, a.y);
+    bf16r2(a.z, a.w, a.z, a.w);
+  }
+  a.x *= e.scale; a.y *= e.scale; a.z *= e.scale; a.w *= e.scale;
+  if (e.softcap != 0.0f) {
+    a.x = tanhf(a.x / e.softcap) * e.softcap; a.y = tanhf(a.y / e.softcap) * e.softcap;
+    a.z = tanhf(a.z / e.softcap) * e.softcap; a.w = tanhf(a.w / e.softcap) * e.softcap;
+  }
+  return a;
+}
+
+// Sampling partials of one parked logits tile ([rows][kPkParkPitch] fp32 accumulators in shared memory).  Two
+// threads scan one row (alternating 4-wide chunks, so the 8 lanes of a shared-memory phase hit distinct banks):
+// the row's best candidate of this tile (lowest index wins ties, jnp.argmax), optionally Gumbel-perturbed
+// (jax.random.categorical), and the (max, sum exp) pair for log-softmax.  No cross-lane traffic but one shuffle.
+__device__ __forceinline__ void pk_logits_scan(const float* park, int wtid, int rows, int tile, const EpiArgs& e, int V, uint32_t step, uint64_t seed) {
+  const int r = wtid >> 1, half = wtid & 1;
+  const bool active = r < rows;
+  float best = -INFINITY, raw = -INFINITY, mx = -INFINITY, sum = 0.0f;
+  int bi = 0x7fffffff;
+  if (active) {
+    const float* row = park + r * kPkParkPitch;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int c = (2 * i + half) * 4;
+      const int n0 = tile * 128 + c;
+      const float4 lg4 = pk_logit_transform(e, *reinterpret_cast<const float4*>(row + c));
+      const float lg[4] = {lg4.x, lg4.y, lg4.z, lg4.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (n0 + q < V) {
+          const float sc = e.gumbel ? lg[q] * e.inv_temp + gumbel_noise(seed, step, uint32_t(e.row_offset + r), uint32_t(e.vocab_offset + n0 + q)) : lg[q];
+          if (sc > best) { best = sc; raw = lg[q]; bi = n0 + q; }  // ascending scan: strict > keeps the lowest index
+          if (e.want_lse) {
+            const float mn = fmaxf(mx, lg[q]);
+            sum = sum * __expf(mx - mn) + __expf(lg[q] - mn);
+            mx = mn;
+          }
+        }
+      }
+    }
+  }
+  {  // combine the two halves of the row
+    const float b2 = __shfl_xor_sync(0xffffffffu, best, 1);
+    const float r2 = __shfl_xor_sync(0xffffffffu, raw, 1);
+    const int i2 = __shfl_xor_sync(0xffffffffu, bi, 1);
+    if (b2 > best || (b2 == best && i2 < bi)) { best = b2; raw = r2; bi = i2; }
+    if (e.want_lse) {
+      const float m2 = __shfl_xor_sync(0xffffffffu, mx, 1), s2 = __shfl_xor_sync(0xffffffffu, sum, 1);
+      const float mn = fmaxf(mx, m2);
+      if (mn > -INFINITY) sum = sum * __expf(mx - mn) + s2 * __expf(m2 - mn);
+      mx = mn;
+    }
+  }
+  if (active && half == 0) {
+    const long long o = (long long)r * e.n_tiles + tile;
+    e.part_score[o] = best;
+    e.part_idx[o] = e.vocab_offset + bi;
+    e.part_raw[o] = raw;
+    if (e.want_lse) { e.part_max[o] = mx; e.part_sum[o] = sum; }
+  }
+}
+
+// Optional materialisation of the logits of one parked tile: a warp per row, 512-byte coalesced stores.
+__device__ __forceinline__ void pk_logits_store(const float* park, int ew, int lane, int rows, int tile, const EpiArgs& e, int V) {
+  const int n0 = tile * 128 + lane * 4;
+  for (int r = ew; r < rows; r += 4) {
+    float* dst = e.logits_only_row < 0 ? e.logits_out + (long long)r * e.ld_logits + n0 : (r == e.logits_only_row ? e.logits_out + n0 : nullptr);
+    if (dst == nullptr) continue;
+    const float4 lg = pk_logit_transform(e, *reinterpret_cast<const float4*>(park + r * kPkParkPitch + lane * 4));
+    if (n0 + 3 < V && (e.ld_logits & 3) == 0) {
+      *reinterpret_cast<float4*>(dst) = lg;
+    } else {
+      const float v[4] = {lg.x, lg.y, lg.z, lg.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (n0 + q < V) dst[q] = v[q];
+    }
+  }
+}
+
+// ---- attention: stream-K over 64-row KV tiles -----------------------------------------------------
+//
+// The valid KV tiles of all (row, kv head) pairs form one list (row-major over row, head, tile).  The active
+// CTAs take equal contiguous runs of it and the six attention warps of a CTA equal contiguous sub-runs, so
+// every warp streams the same number of bytes whatever the context lengths are.  A warp's run is a sequence
+// of segments (maximal pieces inside one pair).  A pair that lies inside one warp is finished there; a pair
+// cut between warps of one CTA is merged in SHARED memory after the CTA's warps have met; only the pairs cut
+// between CTAs go through an L2 workspace (CTA-level partial + ticket, the last CTA to arrive merges).
+// The partition depends on the context lengths only, so it is built once per step and reused by every layer.
+
+enum PkAttnMeta : int {
+  PKA_SEG_START = 1 << 20,   // first tile of a segment of this warp
+  PKA_SEG_END = 1 << 21,     // last tile of a segment of this warp
+  PKA_PAIR_FIRST = 1 << 22,  // tile 0 of its pair
+  PKA_PAIR_LAST = 1 << 23,   // last tile of its pair: holds the row appended this step
+};
+// meta bits [0,6) = valid rows - 1, [6,14) = row, [14,20) = kv head
+__device__ __forceinline__ int pka_cnt(int m) { return (m & 63) + 1; }
+__device__ __forceinline__ int pka_row(int m) { return (m >> 6) & 255; }
+__device__ __forceinline__ int pka_head(int m) { return (m >> 14) & 63; }
+
+struct PkAttnPos {
+  int r, h, t, nt;
+  int len0, rf, rl;
+  int plane_row;  // cache row of (layer 0, plane, kv head) in the K/V tensor maps
+};
+
+__device__ __forceinline__ void pk_attn_load_row(PkAttnPos& a, const PkParams& p, const PkTail* tail, int R) {
+  a.len0 = tail->r_len0[a.r];
+  a.rf = tail->r_rf[a.r];
+  a.rl = tail->r_rl[a.r];
+  a.nt = attn_num_tiles(a.len0, a.rf, a.rl, R);
+  a.plane_row = (tail->r_plane[a.r] * p.hkv + a.h) * p.T;
+}
+
+// Position of flattened tile index g.
+__device__ __forceinline__ void pk_attn_seek(PkAttnPos& a, long long g, const PkParams& p, const PkTail* tail, int R, int lane) {
+  int cnt = 0;
+  for (int r0 = 0; r0 < p.rows; r0 += 32) {
+    const int r = r0 + lane;
+    const bool le = r < p.rows && (long long)tail->r_prefix[r] * p.hkv <= g;
+    cnt += __popc(__ballot_sync(0xffffffffu, le));
+  }
+  a.r = cnt - 1;
+  a.h = 0;
+  pk_attn_load_row(a, p, tail, R);
+  const int rem = int(g - (long long)tail->r_prefix[a.r] * p.hkv);
+  a.h = rem / a.nt;
+  a.t = rem - a.h * a.nt;
+  a.plane_row += a.h * p.T;
+}
+
+__device__ __forceinline__ void pk_attn_next(PkAttnPos& a, const PkParams& p, const PkTail* tail, int R) {
+  if (++a.t < a.nt) return;
+  a.t = 0;
+  if (++a.h < p.hkv) {
+    a.plane_row += p.T;
+    return;
+  }
+  a.h = 0;
+  if (++a.r < p.rows) pk_attn_load_row(a, p, tail, R);
+}
+
+// CTA that owns flattened tile g when `nc` CTAs share `total` tiles.
+__device__ __forceinline__ int pk_cta_of(long long g, long long nc, long long total) { return int(((g + 1) * nc - 1) / total); }
+
+// Once per step: the tile list of attention warp `aw` of this CTA.
+__device__ __forceinline__ void pk_attn_build_list(const PkParams& p, PkTail* tail, int cta, int aw, int lane) {
+  const long long nc = p.attn_info[0], total = p.attn_info[1];
+  int n = 0;
+  if (cta < nc && total > 0) {
+    const long long clo = cta * total / nc, chi = (cta + 1) * total / nc;
+    const long long wlo = clo + aw * (chi - clo) / kPkAttnWarps, whi = clo + (aw + 1) * (chi - clo) / kPkAttnWarps;
+    n = int(whi - wlo);
+    if (n > kPkAttnListMax) n = kPkAttnListMax;  // excluded by the host-side check (pk_usable)
+    if (n > 0) {
+      const int R = p.T - p.P;
+      PkAttnPos pos;
+      pk_attn_seek(pos, wlo, p, tail, R, lane);
+      for (int i = 0; i < n; ++i) {
+        const TileLoc loc = attn_tile(pos.t, pos.len0, pos.rf, pos.rl, p.P, R);
+        int meta = (loc.cnt - 1) | (pos.r << 6) | (pos.h << 14);
+        if (i == 0 || pos.t == 0) meta |= PKA_SEG_START;
+        if (pos.t == 0) meta |= PKA_PAIR_FIRST;
+        if (i == n - 1 || pos.t == pos.nt - 1) meta |= PKA_SEG_END;
+        if (pos.t == pos.nt - 1) meta |= PKA_PAIR_LAST;
+        if (lane == 0) tail->a_list[aw][i] = make_int2(pos.plane_row + loc.p0, meta);
+        pk_attn_next(pos, p, tail, R);
+      }
+    }
+  }
+  if (lane == 0) tail->a_count[aw] = n;
+}
+
+// The whole CTA's attention for one layer, executed by the six attention warps.
+//   phase 1: every warp walks its tile list (TMA K/V tiles -> S = Q K^T -> online softmax -> O += P V)
+//   phase 2: partial segments are merged in shared memory; pairs shared with other CTAs go through L2
+// `primed`: the first K/V tiles were already requested (before the grid barrier).
+__device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const PkParams& p, PkTail* tail, int layer,
+                                                 uint8_t* attn_tiles, uint32_t& phase, int cta, int aw, int lane, bool primed, PkEv& ev) {
+  constexpr int D = 64;
+  constexpr int kTileBytes = 64 * D * 2;
+  constexpr float kLog2e = 1.4426950408889634f;
+  const int G = p.hq / p.hkv;
+  const int layer_row = layer * p.num_slots * p.hkv * p.T;
+  const int gid = lane >> 2, tid4 = lane & 3;
+  const int mtx_i = lane >> 3, lrow = lane & 7;
+  uint8_t* k_tile = attn_tiles + aw * 2 * 8192;
+  uint8_t* v_tile = k_tile + 8192;
+  uint64_t* bar_k = &tail->attn_bars[2 * aw];
+  uint64_t* bar_v = bar_k + 1;
+  const uint32_t kb = smem_u32(k_tile), vb = smem_u32(v_tile);
+  const int n = tail->a_count[aw];
+  const int2* list = tail->a_list[aw];
+  const int slot_floats = G * D + 2 * G;
+
+  if (lane == 0) {
+    tail->a_seg[aw][0].x = -1;
+    tail->a_seg[aw][1].x = -1;
+  }
+  if (n > 0 && !primed && lane == 0) {
+    fence_proxy_async_all();  // K/V rows appended by the QKV epilogue (generic stores) are read through TMA
+    const int row0 = layer_row + list[0].x;
+    mbar_expect_tx(bar_k, kTileBytes);
+    tma_load_2d(k_tile, &tm_k, 0, row0, bar_k, kEvictFirst);
+    mbar_expect_tx(bar_v, kTileBytes);
+    tma_load_2d(v_tile, &tm_v, 0, row0, bar_v, kEvictFirst);
+  }
+
+  uint32_t qf[D / 16][4];
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+  float o[D / 8][4];
+  bool seg_first = false;   // the running segment starts at tile 0 of its pair
+  int n_partial = 0;        // partial segments this warp has parked so far
+
+  for (int i = 0; i < n; ++i) {
+    const int2 e = list[i];
+    const int meta = e.y;
+    const int r = pka_row(meta), h = pka_head(meta), cnt = pka_cnt(meta);
+    if (meta & PKA_SEG_START) {
+      const bf16* qrow = p.q + (long long)r * p.hq * D + (long long)h * G * D;
+#pragma unroll
+      for (int tt = 0; tt < D / 16; ++tt) {
+        const int d = tt * 16 + tid4 * 2;
+        qf[tt][0] = gid < G ? __ldcg(reinterpret_cast<const uint32_t*>(qrow + gid * D + d)) : 0u;
+        qf[tt][1] = gid + 8 < G ? __ldcg(reinterpret_cast<const uint32_t*>(qrow + (gid + 8) * D + d)) : 0u;
+        qf[tt][2] = gid < G ? __ldcg(reinterpret_cast<const uint32_t*>(qrow + gid * D + d + 8)) : 0u;
+        qf[tt][3] = gid + 8 < G ? __ldcg(reinterpret_cast<const uint32_t*>(qrow + (gid + 8) * D + d + 8)) : 0u;
+      }
+      m0 = m1 = -INFINITY;
+      l0 = l1 = 0.0f;
+#pragma unroll
+      for (int j = 0; j < D / 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.0f;
+      seg_first = (meta & PKA_PAIR_FIRST) != 0;
+    }
+    const bool more = i + 1 < n;
+    const int next_row = more ? layer_row + list[i + 1].x : 0;
+
+    // ---- S = Q K^T over the 64 rows of the tile ----
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
+    if (lane == 0) pk_ev(ev, 600);
+    mbar_wait(bar_k, phase);
+    if (lane == 0) pk_ev(ev, 601);
+#pragma unroll
+    for (int tt = 0; tt < D / 16; ++tt) {
+#pragma unroll
+      for (int jp = 0; jp < 4; ++jp) {
+        const int row = 8 * (2 * jp + (mtx_i >> 1)) + lrow;
+        const int c = 2 * tt + (mtx_i & 1);
+        const uint32_t addr = kb + row * 128 + (((c & 7) ^ (row & 7)) << 4);
+        uint32_t b00, b01, b10, b11;
+        ldmatrix_x4(addr, b00, b01, b10, b11);
+        mma_m16n8k16_bf16(s[2 * jp], qf[tt], b00, b01);
+        mma_m16n8k16_bf16(s[2 * jp + 1], qf[tt], b10, b11);
+      }
+    }
+    // K tile consumed: refill it with the next tile's keys while the softmax and P V run
+    if (lane == 0) pk_ev(ev, 602);
+    fence_proxy_async();
+    __syncwarp();
+    if (more && lane == 0) {
+      mbar_expect_tx(bar_k, kTileBytes);
+      tma_load_2d(k_tile, &tm_k, 0, next_row, bar_k, kEvictFirst);
+    }
+    // ---- mask + online softmax (quad shuffles) ----
+    if (p.softcap != 0.0f) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s[j][q] = tanhf(s[j][q] / p.softcap) * p.softcap;
+    }
+    if (cnt < 64) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (8 * j + tid4 * 2 + (q & 1) >= cnt) s[j][q] = -INFINITY;
+    }
+    float tm0 = -INFINITY, tm1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      tm0 = fmaxf(tm0, fmaxf(s[j][0], s[j][1]));
+      tm1 = fmaxf(tm1, fmaxf(s[j][2], s[j][3]));
+    }
+    tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1));
+    tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 2));
+    tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1));
+    tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
+    const float nm0 = fmaxf(m0, tm0), nm1 = fmaxf(m1, tm1);
+    const float a0 = ex2_approx((m0 - nm0) * kLog2e), a1 = ex2_approx((m1 - nm1) * kLog2e);  // ex2(-inf) = 0 on the first tile
+    m0 = nm0;
+    m1 = nm1;
+    l0 *= a0;
+    l1 *= a1;
+    const float ms0 = m0 * kLog2e, ms1 = m1 * kLog2e;
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = ex2_approx(fmaf(s[j][0], kLog2e, -ms0)), p1 = ex2_approx(fmaf(s[j][1], kLog2e, -ms0));
+      const float p2 = ex2_approx(fmaf(s[j][2], kLog2e, -ms1)), p3 = ex2_approx(fmaf(s[j][3], kLog2e, -ms1));
+      l0 += p0 + p1;
+      l1 += p2 + p3;
+      // probabilities are cast to the value dtype before the PV product (kernels/ragged_attention.py:156)
+      pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+      pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    }
+#pragma unroll
+    for (int j = 0; j < D / 8; ++j) {
+      o[j][0] *= a0;
+      o[j][1] *= a0;
+      o[j][2] *= a1;
+      o[j][3] *= a1;
+    }
+    // ---- O += P V ----
+    if (lane == 0) pk_ev(ev, 603);
+    mbar_wait(bar_v, phase);
+    if (lane == 0) pk_ev(ev, 604);
+    if (cnt < 64) {  // rows past the valid count may hold anything: zero them (0 * NaN != 0)
+      const int nvec = (64 - cnt) * 8;
+      for (int q = lane; q < nvec; q += 32) *reinterpret_cast<uint4*>(v_tile + (cnt + q / 8) * 128 + (q & 7) * 16) = make_uint4(0, 0, 0, 0);
+      __syncwarp();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int jp = 0; jp < D / 16; ++jp) {
+        const int row = 16 * u + 8 * (mtx_i & 1) + lrow;
+        const int c = 2 * jp + (mtx_i >> 1);
+        const uint32_t addr = vb + row * 128 + (((c & 7) ^ (row & 7)) << 4);
+        uint32_t b00, b01, b10, b11;
+        ldmatrix_x4_trans(addr, b00, b01, b10, b11);
+        mma_m16n8k16_bf16(o[2 * jp], pa[u], b00, b01);
+        mma_m16n8k16_bf16(o[2 * jp + 1], pa[u], b10, b11);
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (more && lane == 0) {
+      mbar_expect_tx(bar_v, kTileBytes);
+      tma_load_2d(v_tile, &tm_v, 0, next_row, bar_v, kEvictFirst);
+    }
+    phase ^= 1;
+    if (lane == 0) pk_ev(ev, 605);
+
+    if (meta & PKA_SEG_END) {
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      if (seg_first && (meta & PKA_PAIR_LAST)) {
+        // the whole pair lived in this warp: normalise and store
+        const long long out_base = (long long)r * p.hq * D + (long long)h * G * D;
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+        for (int j = 0; j < D / 8; ++j) {
+          const int d = 8 * j + tid4 * 2;
+          if (gid < G) *reinterpret_cast<uint32_t*>(p.attn + out_base + gid * D + d) = pack_bf16x2(o[j][0] * i0, o[j][1] * i0);
+          if (gid + 8 < G) *reinterpret_cast<uint32_t*>(p.attn + out_base + (gid + 8) * D + d) = pack_bf16x2(o[j][2] * i1, o[j][3] * i1);
+        }
+      } else {
+        // park the partial: the warp's last segment goes to its (now idle) K buffer, an earlier one to its slot
+        const bool final_seg = !more;
+        float* dst = final_seg ? reinterpret_cast<float*>(k_tile) : tail->a_slot[aw];
+#pragma unroll
+        for (int j = 0; j < D / 8; ++j) {
+          const int d = 8 * j + tid4 * 2;
+          if (gid < G) *reinterpret_cast<float2*>(dst + gid * D + d) = make_float2(o[j][0], o[j][1]);
+          if (gid + 8 < G) *reinterpret_cast<float2*>(dst + (gid + 8) * D + d) = make_float2(o[j][2], o[j][3]);
+        }
+        if (tid4 == 0) {
+          if (gid < G) *reinterpret_cast<float2*>(dst + G * D + gid * 2) = make_float2(m0, l0);
+          if (gid + 8 < G) *reinterpret_cast<float2*>(dst + G * D + (gid + 8) * 2) = make_float2(m1, l1);
+        }
+        if (lane == 0) {
+          const int flags = (seg_first ? 1 : 0) | ((meta & PKA_PAIR_LAST) ? 2 : 0);
+          tail->a_seg[aw][final_seg ? 1 : 0] = make_int4(r * p.hkv + h, flags, r, h);
+        }
+        ++n_partial;
+      }
+    }
+  }
+  (void)n_partial;
+  (void)slot_floats;
+
+  // ---- phase 2: merge the partial segments of this CTA ----
+  named_bar_sync(3, kPkAttnWarps * 32);
+  const long long nc = p.attn_info[0], total = p.attn_info[1];
+  for (int k = 0; k < 2; ++k) {
+    const int4 me = tail->a_seg[aw][k];
+    if (me.x < 0) continue;
+    // predecessor in tile order: this warp's slot entry, else the last segment of the nearest earlier warp with tiles
+    bool leader = true;
+    if (k == 0) {
+      for (int w = aw - 1; w >= 0; --w)
+        if (tail->a_count[w] > 0) {
+          leader = tail->a_seg[w][1].x != me.x;
+          break;
+        }
+    } else if (tail->a_seg[aw][0].x == me.x) {
+      leader = false;  // cannot happen (a warp's two partial segments belong to different pairs); kept for safety
+    } else if (tail->a_seg[aw][0].x < 0) {
+      // a warp whose whole run is one partial segment: the pair may continue from the previous warp
+      for (int w = aw - 1; w >= 0; --w)
+        if (tail->a_count[w] > 0) {
+          leader = tail->a_seg[w][1].x != me.x;
+          break;
+        }
+    }
+    if (!leader) continue;
+    // members: (aw, k) then, for a last-segment entry, the following warps while they continue the same pair
+    const float* src[kPkAttnWarps + 1];
+    int n_src = 0, flags = me.y;
+    src[n_src++] = k == 0 ? tail->a_slot[aw] : reinterpret_cast<const float*>(attn_tiles + aw * 2 * 8192);
+    if (k == 1) {
+      for (int w = aw + 1; w < kPkAttnWarps; ++w) {
+        if (tail->a_count[w] == 0) continue;
+        const int4 s0 = tail->a_seg[w][0], s1 = tail->a_seg[w][1];
+        if (s0.x == me.x) {  // the pair ends inside warp w
+          src[n_src++] = tail->a_slot[w];
+          flags |= s0.y;
+          break;
+        }
+        if (s0.x < 0 && s1.x == me.x) {  // warp w lies entirely inside the pair
+          src[n_src++] = reinterpret_cast<const float*>(attn_tiles + w * 2 * 8192);
+          flags |= s1.y;
+          continue;
+        }
+        break;
+      }
+    }
+    const int r = me.z, h = me.w, pair = me.x;
+    const long long out_base = (long long)r * p.hq * D + (long long)h * G * D;
+    const bool complete = (flags & 3) == 3;
+    // CTA-level partial slot when the pair is shared with other CTAs
+    const long long g_first = (long long)tail->r_prefix[r] * p.hkv + (long long)h * attn_num_tiles(tail->r_len0[r], tail->r_rf[r], tail->r_rl[r], p.T - p.P);
+    int c_first = 0, n_parts = 1;
+    float* gpart = nullptr;
+    if (!complete) {
+      const int nt = attn_num_tiles(tail->r_len0[r], tail->r_rf[r], tail->r_rl[r], p.T - p.P);
+      c_first = pk_cta_of(g_first, nc, total);
+      n_parts = pk_cta_of(g_first + nt - 1, nc, total) - c_first + 1;
+      gpart = p.attn_part_o + ((long long)pair * kPkMaxParts + (cta - c_first)) * ((G * D + 2 * G + 3) & ~3);
+    }
+    for (int unit = lane; unit < G * (D / 4); unit += 32) {
+      const int gq = unit / (D / 4), d4 = unit - gq * (D / 4);
+      float M = -INFINITY;
+      for (int c = 0; c < n_src; ++c) M = fmaxf(M, src[c][G * D + gq * 2]);
+      float Ls = 0.0f;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < n_src; ++c) {
+        const float2 ml = *reinterpret_cast<const float2*>(src[c] + G * D + gq * 2);
+        const float4 o4 = *reinterpret_cast<const float4*>(src[c] + gq * D + d4 * 4);
+        const float sc = ex2_approx((ml.x - M) * kLog2e);
+        Ls += ml.y * sc;
+        acc.x += o4.x * sc; acc.y += o4.y * sc; acc.z += o4.z * sc; acc.w += o4.w * sc;
+      }
+      if (complete) {
+        const float inv = 1.0f / Ls;
+        *reinterpret_cast<uint2*>(p.attn + out_base + gq * D + d4 * 4) = pack_bf16x4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+      } else {
+        __stcg(reinterpret_cast<float4*>(gpart + gq * D + d4 * 4), acc);
+        if (d4 == 0) __stcg(reinterpret_cast<float2*>(gpart + G * D + gq * 2), make_float2(M, Ls));
+      }
+    }
+    if (!complete) {
+      __syncwarp();
+      int last = 0;
+      if (lane == 0) {
+        __threadfence();  // cumulative over the warp's stores (ordered before it by the warp barrier)
+        const int old = atomicAdd(p.attn_tickets + pair, 1);
+        last = old == n_parts - 1;
+        if (last) {
+          p.attn_tickets[pair] = 0;
+          __threadfence();
+        }
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        const int stride = (G * D + 2 * G + 3) & ~3;  // 16-byte aligned parts
+        const float* base = p.attn_part_o + (long long)pair * kPkMaxParts * stride;
+        for (int unit = lane; unit < G * (D / 4); unit += 32) {
+          const int gq = unit / (D / 4), d4 = unit - gq * (D / 4);
+          float M = -INFINITY, Ls = 0.0f;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int c0 = 0; c0 < n_parts; c0 += 4) {  // both loads of up to four parts travel together
+            float2 ml[4];
+            float4 o4[4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+              if (c0 + cc < n_parts) {
+                ml[cc] = __ldcg(reinterpret_cast<const float2*>(base + (long long)(c0 + cc) * stride + G * D + gq * 2));
+                o4[cc] = ldcg_f4(base + (long long)(c0 + cc) * stride + gq * D + d4 * 4);
+              }
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+              if (c0 + cc < n_parts) {
+                const float Mn = fmaxf(M, ml[cc].x);
+                const float so = ex2_approx((M - Mn) * kLog2e), sn = ex2_approx((ml[cc].x - Mn) * kLog2e);
+                Ls = Ls * so + ml[cc].y * sn;
+                acc.x = acc.x * so + o4[cc].x * sn; acc.y = acc.y * so + o4[cc].y * sn;
+                acc.z = acc.z * so + o4[cc].z * sn; acc.w = acc.w * so + o4[cc].w * sn;
+                M = Mn;
+              }
+          }
+          const float inv = 1.0f / Ls;
+          *reinterpret_cast<uint2*>(p.attn + out_base + gq * D + d4 * 4) = pack_bf16x4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+        }
+      }
+    }
+  }
+}
+
+// ---- the kernel --------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(kPkThreads, 1)
+step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid_constant__ CUtensorMap tm_wo,
+                       const __grid_constant__ CUtensorMap tm_w01, const __grid_constant__ CUtensorMap tm_wout,
+                       const __grid_constant__ CUtensorMap tm_wlogits, const __grid_constant__ CUtensorMap tm_x,
+                       const __grid_constant__ CUtensorMap tm_attn, const __grid_constant__ CUtensorMap tm_h,
+                       const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_n,
+                       const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const PkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* attn_tiles = smem + kPkRingBytes;
+  float* park = reinterpret_cast<float*>(attn_tiles);
+  PkTail* tail = reinterpret_cast<PkTail*>(smem + kPkRingBytes + kPkAttnBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_ctas = int(gridDim.x), cta = int(blockIdx.x);
+  const int x_bytes = p.r_tile * kBlockK * 2;
+  const uint32_t tmem_cols = uint32_t(kPkAccBufs * p.r_tile < 32 ? 32 : kPkAccBufs * p.r_tile);
+  const int kb_e = p.E / kBlockK;
+  const int logits_tiles_all = (p.V + kTileN - 1) / kTileN;
+  const int logits_tiles = cta < logits_tiles_all ? (logits_tiles_all - cta + n_ctas - 1) / n_ctas : 0;
+  const int ss_tiles = (p.E + 127) / 128;
+  const int tl = timeline_begin(20);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPkStages; ++s) {
+      mbar_init(&tail->full_w[s], 1);
+      mbar_init(&tail->full_x[s], 1);
+      mbar_init(&tail->xready[s], 1);
+      mbar_init(&tail->empty[s], 1);
+    }
+    for (int b = 0; b < kPkAccBufs; ++b) {
+      mbar_init(&tail->tmem_full[b], 1);
+      mbar_init(&tail->tmem_empty[b], 1);
+    }
+    for (int i = 0; i < 2 * kPkAttnWarps; ++i) mbar_init(&tail->attn_bars[i], 1);
+    tail->bar_done = 0;
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_wqkv);
+    tma_prefetch_desc(&tm_wo);
+    tma_prefetch_desc(&tm_w01);
+    tma_prefetch_desc(&tm_wout);
+    tma_prefetch_desc(&tm_wlogits);
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_attn);
+    tma_prefetch_desc(&tm_h);
+    tma_prefetch_desc(&tm_act);
+    tma_prefetch_desc(&tm_n);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  {  // this CTA's work table
+    const int* src = reinterpret_cast<const int*>(p.tables + cta);
+    int* dst = reinterpret_cast<int*>(&tail->tab);
+    for (int i = threadIdx.x; i < int(sizeof(PkTable) / 4); i += kPkThreads) dst[i] = src[i];
+  }
+  if (warp == 1) {
+    tmem_alloc(&tail->tmem_base, tmem_cols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tail->tmem_base;
+  const PkTable& tab = tail->tab;
+
+  // Calls f(layer, phase, weight tile, first k-block, last k-block + 1) for every work unit of this CTA in issue
+  // order.  All GEMM roles walk the same sequence; logits tiles come as units of phase PK_LOGITS.
+  auto for_each_unit = [&](auto&& f) {
+    for (int l = 0; l < p.L; ++l)
+      for (int ph = 0; ph < 4; ++ph) {
+        const int nu = tab.n_units[ph];
+        for (int u = 0; u < nu; ++u) {
+          const PkUnit un = tab.u[ph][u];
+          f(l, ph, un.tile, un.kb0, un.kb1);
+        }
+      }
+    for (int j = 0; j < logits_tiles; ++j) f(p.L, int(PK_LOGITS), cta + j * n_ctas, 0, kb_e);
+  };
+
+  if (warp == 0) {
+    // =================================== weight producer =================================
+    // Runs ahead of the grid barriers, bounded only by the ring: a stage is refilled as soon as the MMAs that
+    // read it have completed.
+    if (lane == 0) {
+      PkCursor c;
+      pk_cursor_init(c);
+      for_each_unit([&](int l, int ph, int tile, int kb0, int kb1) {
+        const CUtensorMap* tmw = ph == PK_QKV ? &tm_wqkv : ph == PK_OPROJ ? &tm_wo : ph == PK_UP ? &tm_w01 : ph == PK_DOWN ? &tm_wout : &tm_wlogits;
+        const int n_ph = ph == PK_QKV ? p.qkv_n : ph == PK_UP ? 2 * p.M : ph == PK_LOGITS ? 0 : p.E;
+        const int row = l * n_ph + tile * kTileN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if (c.uses) mbar_wait(&tail->empty[c.s], c.par ^ 1);
+          mbar_expect_tx(&tail->full_w[c.s], uint32_t(kWTileBytes));
+          tma_load_2d(ring + size_t(c.s) * kPkStageBytes, tmw, kb * kBlockK, row, &tail->full_w[c.s], kEvictFirst);
+          pk_cursor_next(c);
+        }
+      });
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =================================== MMA issuer =====================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kTileN, p.r_tile);
+      PkCursor c;
+      pk_cursor_init(c);
+      uint32_t uc = 0;
+      for_each_unit([&](int, int, int, int kb0, int kb1) {
+        const uint32_t buf = uc % kPkAccBufs;
+        const uint32_t acc = tmem_base + buf * uint32_t(p.r_tile);
+        if (uc >= uint32_t(kPkAccBufs)) mbar_wait(&tail->tmem_empty[buf], ((uc / kPkAccBufs) & 1) ^ 1);
+        tcgen05_fence_after();
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&tail->full_w[c.s], c.par);
+          mbar_wait(&tail->xready[c.s], c.par);
+          tcgen05_fence_after();
+          const uint64_t da = umma_desc_sw128(ring + size_t(c.s) * kPkStageBytes);
+          const uint64_t db = umma_desc_sw128(ring + size_t(c.s) * kPkStageBytes + kWTileBytes);
+#pragma unroll
+          for (int kk = 0; kk < kBlockK / kUmmaK; ++kk)
+            umma_bf16(acc, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc, uint32_t((kb > kb0) || kk > 0));
+          umma_commit(&tail->empty[c.s]);
+          pk_cursor_next(c);
+        }
+        umma_commit(&tail->tmem_full[buf]);
+        ++uc;
+      });
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    // =================================== epilogue warps ==================================
+    const int wtid = threadIdx.x - 64;
+    const int ew = warp - 2;  // 0..3: row-major work is dealt by this index
+    const int quarter = warp & 3;
+    const int n_local = quarter * 32 + lane;
+    const uint32_t tlane = uint32_t(quarter * 32) << 16;
+    uint32_t uc = 0, nbar = 0;
+    PkEv ev = pk_ev_make(p, 0);
+
+    griddep_wait();
+    if (p.trace && wtid == 0) p.trace[gridDim.x + blockIdx.x] = (long long)globaltimer_ns();  // "barrier 0 release" = start
+
+    // Closes a phase: generic writes that other CTAs read through TMA get their proxy fence, the CTA's epilogue
+    // threads meet, one thread runs the grid barrier (its gpu-scope fence is cumulative over the CTA's writes).
+    auto phase_end = [&](bool wait_all) {
+      if (wtid == 0) pk_ev(ev, 90);
+      fence_proxy_async_all();
+      named_bar_sync(1, 128);
+      if (wtid == 0) pk_ev(ev, 91);
+      ++nbar;
+      if (wtid == 0) pk_grid_barrier(p, tail, nbar);
+      if (wait_all) named_bar_sync(1, 128);
+    };
+
+    // ---- embedding gather (embeddings.py:154) + row sums of squares of x ----
+    {
+      const int nvec = p.E / 8;
+      for (int r = cta; r < p.rows; r += n_ctas) {
+        const bf16* src = p.embedding + (long long)p.token[r] * p.E;
+        float ss = 0.0f;
+        for (int i = wtid; i < nvec; i += 128) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(src + i * 8);
+          *reinterpret_cast<uint4*>(p.x + (long long)r * p.E + i * 8) = raw;
+          const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = bf16_lo(w[j]), b = bf16_hi(w[j]);
+            ss += a * a + b * b;
+          }
+        }
+        ss = warp_sum(ss);
+        named_bar_sync(1, 128);
+        if (lane == 0) tail->red[ew] = ss;
+        named_bar_sync(1, 128);
+        if (wtid < ss_tiles) p.ss_x[wtid * kPkMaxRTile + r] = wtid == 0 ? tail->red[0] + tail->red[1] + tail->red[2] + tail->red[3] : 0.0f;
+      }
+      phase_end(false);
+    }
+
+    // One GEMM phase of this CTA: dump every accumulator (partial tile to the exchange workspace, or straight to
+    // the epilogue when the CTA owns the whole reduction), then finish the row slices it owns.
+    auto gemm_phase = [&](auto ph_tag, int layer) {
+      constexpr int ph = decltype(ph_tag)::value;
+      const int nu = tab.n_units[ph];
+      const int N = ph == PK_QKV ? p.qkv_n : ph == PK_UP ? 2 * p.M : p.E;
+      bf16* k_layer = p.k_cache + p.kv_layer_elems * layer;
+      bf16* v_layer = p.v_cache + p.kv_layer_elems * layer;
+      const bf16* resid = ph == PK_OPROJ ? p.x : p.h;
+      bf16* res_out = ph == PK_OPROJ ? p.h : p.x;
+      float* ss_out = ph == PK_OPROJ ? p.ss_h : p.ss_x;
+      // side inputs of a row fragment are requested before the accumulator is final (see the reduce loop)
+      auto epilogue = [&](const float4 a, const PkQkvSide& sd, const uint2 rv, int r, int tile) {
+        if (ph == PK_QKV) pk_epi_qkv(a, sd, r, tile, lane, p, k_layer, v_layer);
+        if (ph == PK_OPROJ || ph == PK_DOWN) pk_epi_residual(a, rv, r, tile, lane, N, res_out, ss_out, ss_tiles);
+        if (ph == PK_UP) pk_epi_swiglu(a, r, tile, lane, N, p.M, p.act);
+      };
+      auto side_qkv = [&](int r, int tile) {
+        PkQkvSide sd;
+        sd.c01 = sd.c23 = make_float4(0.f, 0.f, 0.f, 0.f);
+        sd.plane = sd.wr = 0;
+        if (ph == PK_QKV) sd = pk_qkv_side(p, r, tile, lane);
+        return sd;
+      };
+      auto side_res = [&](int r, int tile) {
+        uint2 rv = make_uint2(0u, 0u);
+        const int n0 = tile * 128 + lane * 4;
+        if ((ph == PK_OPROJ || ph == PK_DOWN) && n0 < N) rv = __ldcg(reinterpret_cast<const uint2*>(resid + (long long)r * N + n0));
+        return rv;
+      };
+      for (int u = 0; u < nu; ++u) {
+        const PkUnit un = tab.u[ph][u];
+        const uint32_t buf = uc % kPkAccBufs;
+        if (wtid == 0) pk_ev(ev, 100 * ph + 10);
+        mbar_wait(&tail->tmem_full[buf], (uc / kPkAccBufs) & 1);
+        tcgen05_fence_after();
+        if (wtid == 0) pk_ev(ev, 100 * ph + 11);
+        const uint32_t taddr = tmem_base + tlane + buf * uint32_t(p.r_tile);
+        if (un.S == 1) {
+          for (int c = 0; c * 16 < p.rows; ++c) {
+            float v[16];
+            tmem_ld_x16(taddr + uint32_t(c * 16), v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) park[(c * 16 + j) * 128 + n_local] = v[j];
+          }
+        } else {
+          float* dst = p.part_ws + (long long)(cta * 4 + (un.tile & 3)) * kPkSlotFloats;
+          for (int c = 0; c * 16 < p.rows; ++c) {
+            float v[16];
+            tmem_ld_x16(taddr + uint32_t(c * 16), v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c * 16 + j < p.rows) dst[(c * 16 + j) * 128 + n_local] = v[j];
+          }
+        }
+        tcgen05_fence_before();
+        if (wtid == 0) pk_ev(ev, 100 * ph + 12);
+        named_bar_sync(1, 128);
+        if (wtid == 0) mbar_arrive(&tail->tmem_empty[buf]);
+        if (un.S == 1) {
+          for (int r = ew; r < p.rows; r += 4)
+            epilogue(*reinterpret_cast<const float4*>(park + r * 128 + lane * 4), side_qkv(r, un.tile), side_res(r, un.tile), r, un.tile);
+          named_bar_sync(1, 128);  // the park buffer is rewritten by the next unit
+        }
+        ++uc;
+      }
+      // Finish the row slices this CTA owns.  The exchange has no flags: a word of the workspace is either the
+      // sentinel or data, so the reader simply re-requests a fragment until all of its words have arrived, then
+      // puts the sentinel back for the next layer (the same thread reads the same words every layer).
+      for (int u = 0; u < nu; ++u) {
+        const PkUnit un = tab.u[ph][u];
+        if (un.S == 1) continue;
+        const int si = cta - un.c_first;
+        const int r_begin = si * p.rows / un.S, r_end = (si + 1) * p.rows / un.S;
+        if (wtid == 0) pk_ev(ev, 100 * ph + 14);
+        float* src0 = p.part_ws + (long long)(un.c_first * 4 + (un.tile & 3)) * kPkSlotFloats + lane * 4;
+        const float4 sent4 = make_float4(__uint_as_float(kPkSentinel), __uint_as_float(kPkSentinel), __uint_as_float(kPkSentinel), __uint_as_float(kPkSentinel));
+        for (int r = r_begin + ew; r < r_end; r += 8) {
+          const int r2 = r + 4;
+          const bool two = r2 < r_end;
+          // side inputs of both rows travel with the partial tiles
+          const PkQkvSide sd_a = side_qkv(r, un.tile), sd_b = side_qkv(two ? r2 : r, un.tile);
+          const uint2 rv_a = side_res(r, un.tile), rv_b = side_res(two ? r2 : r, un.tile);
+          float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_b = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int s0 = 0; s0 < un.S; s0 += 8) {
+            float4 ta[8], tb[8];
+            const long long t_spin = clock64();
+            for (;;) {
+              bool ok = true;
+#pragma unroll
+              for (int ss = 0; ss < 8; ++ss) {
+                ta[ss] = tb[ss] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (s0 + ss < un.S) {
+                  float* ps = src0 + (long long)(s0 + ss) * 4 * kPkSlotFloats;
+                  ta[ss] = ldcg_f4(ps + r * 128);
+                  if (two) tb[ss] = ldcg_f4(ps + r2 * 128);
+                }
+              }
+#pragma unroll
+              for (int ss = 0; ss < 8; ++ss) {
+                const uint32_t bad = uint32_t(__float_as_uint(ta[ss].x) == kPkSentinel) | uint32_t(__float_as_uint(ta[ss].y) == kPkSentinel) |
+                                     uint32_t(__float_as_uint(ta[ss].z) == kPkSentinel) | uint32_t(__float_as_uint(ta[ss].w) == kPkSentinel) |
+                                     uint32_t(__float_as_uint(tb[ss].x) == kPkSentinel) | uint32_t(__float_as_uint(tb[ss].y) == kPkSentinel) |
+                                     uint32_t(__float_as_uint(tb[ss].z) == kPkSentinel) | uint32_t(__float_as_uint(tb[ss].w) == kPkSentinel);
+                ok = ok && bad == 0;
+              }
+              if (__all_sync(0xffffffffu, ok)) break;
+              if (clock64() - t_spin > 4000000000LL) {
+                printf("mtx: split-K exchange timed out (block %d phase %d tile %d row %d)\n", cta, ph, un.tile, r);
+                __trap();
+              }
+            }
+#pragma unroll
+            for (int ss = 0; ss < 8; ++ss) {
+              if (s0 + ss < un.S) {
+                float* ps = src0 + (long long)(s0 + ss) * 4 * kPkSlotFloats;
+                *reinterpret_cast<float4*>(ps + r * 128) = sent4;
+                if (two) *reinterpret_cast<float4*>(ps + r2 * 128) = sent4;
+              }
+              acc_a.x += ta[ss].x; acc_a.y += ta[ss].y; acc_a.z += ta[ss].z; acc_a.w += ta[ss].w;
+              acc_b.x += tb[ss].x; acc_b.y += tb[ss].y; acc_b.z += tb[ss].z; acc_b.w += tb[ss].w;
+            }
+          }
+          epilogue(acc_a, sd_a, rv_a, r, un.tile);
+          if (two) epilogue(acc_b, sd_b, rv_b, r2, un.tile);
+        }
+      }
+    };
+
+    for (int l = 0; l < p.L; ++l) {
+      ev.on = l == 1;
+      gemm_phase(std::integral_constant<int, PK_QKV>{}, l);
+      phase_end(false);
+      ++nbar;  // the attention phase's barrier is run by the attention warps
+      gemm_phase(std::integral_constant<int, PK_OPROJ>{}, l);
+      phase_end(false);
+      gemm_phase(std::integral_constant<int, PK_UP>{}, l);
+      phase_end(false);
+      gemm_phase(std::integral_constant<int, PK_DOWN>{}, l);
+      phase_end(l == p.L - 1);
+    }
+
+    // ---- final RMSNorm (decoders.py:537-589) into the activation buffer the logits GEMM streams ----
+    {
+      const int nvec = p.E / 8;
+      for (int r = cta; r < p.rows; r += n_ctas) {
+        float tot = 0.0f;
+        for (int t = 0; t < ss_tiles; ++t) tot += __ldcg(p.ss_x + t * kPkMaxRTile + r);
+        const float rstd = 1.0f / sqrtf(tot / float(p.E) + p.eps);
+        for (int i = wtid; i < nvec; i += 128) {
+          const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(p.x + (long long)r * p.E + i * 8));
+          const uint4 sc = *reinterpret_cast<const uint4*>(p.final_norm + i * 8);
+          const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+          const uint32_t s[4] = {sc.x, sc.y, sc.z, sc.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float y0, y1;
+            bf16r2(bf16_lo(w[j]) * rstd, bf16_hi(w[j]) * rstd, y0, y1);
+            o[j] = pack_bf16x2(y0 * bf16_lo(s[j]), y1 * bf16_hi(s[j]));
+          }
+          *reinterpret_cast<uint4*>(p.n + (long long)r * p.E + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      phase_end(false);
+    }
+
+    // ---- logits + per-tile sampling partials ----
+    {
+      uint32_t step = 0;
+      uint64_t seed = 0;
+      if (p.logits.gumbel) {
+        step = p.logits.rng_state[0];
+        seed = (uint64_t(p.logits.rng_state[2]) << 32) | p.logits.rng_state[1];
+      }
+      ev.n = 0;
+      for (int j = 0; j < logits_tiles; ++j) {
+        const int tile = cta + j * n_ctas;
+        const uint32_t buf = uc % kPkAccBufs;
+        ev.on = j >= 4 && j < 10;
+        if (wtid == 0) pk_ev(ev, 410);
+        mbar_wait(&tail->tmem_full[buf], (uc / kPkAccBufs) & 1);
+        tcgen05_fence_after();
+        if (wtid == 0) pk_ev(ev, 411);
+        const uint32_t taddr = tmem_base + tlane + buf * uint32_t(p.r_tile);
+        for (int c = 0; c * 16 < p.rows; ++c) {
+          float v[16];
+          tmem_ld_x16(taddr + uint32_t(c * 16), v);
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) park[(c * 16 + jj) * kPkParkPitch + n_local] = v[jj];
+        }
+        tcgen05_fence_before();
+        named_bar_sync(1, 128);
+        if (wtid == 0) mbar_arrive(&tail->tmem_empty[buf]);
+        if (wtid == 0) pk_ev(ev, 412);
+        if (p.logits.logits_out != nullptr) pk_logits_store(park, ew, lane, p.rows, tile, p.logits, p.V);
+        pk_logits_scan(park, wtid, p.rows, tile, p.logits, p.V, step, seed);
+        named_bar_sync(1, 128);
+        if (wtid == 0) pk_ev(ev, 413);
+        ++uc;
+      }
+    }
+    if (p.trace && wtid == 0) p.trace[blockIdx.x] = (long long)globaltimer_ns();  // slot of "barrier 0 arrive" = end of work
+  } else {
+    // ============== attention warps; between attention phases: activation producer and normaliser ==============
+    const int aw = warp - 6;             // 0..5
+    const int atid = threadIdx.x - 192;  // 0..191
+    const bool xformer = aw < 4;         // warps 6-9 normalise activation tiles during the QKV and MLP-up phases
+    const bool xproducer = aw == 4;      // warp 10 requests the activation tiles of every GEMM phase
+    uint32_t kv_phase = 0;
+    PkEv ev = pk_ev_make(p, 1);
+    if (aw != 0) ev.base = nullptr;
+    PkEv evx = pk_ev_make(p, 2);
+    if (!(xproducer && lane == 0)) evx.base = nullptr;
+
+    // ---- once per step: stage the row descriptors, cut this warp's share of the attention tiles ----
+    griddep_wait();
+    for (int r = atid; r < p.rows; r += kPkAttnWarps * 32) {
+      tail->r_len0[r] = p.len0[r];
+      tail->r_rf[r] = p.ring_first[r];
+      tail->r_rl[r] = p.ring_len[r];
+      tail->r_plane[r] = p.plane[r];
+      tail->r_prefix[r] = p.tile_prefix[r];
+    }
+    if (atid == 0) tail->r_prefix[p.rows] = p.tile_prefix[p.rows];
+    named_bar_sync(3, kPkAttnWarps * 32);
+    pk_attn_build_list(p, tail, cta, aw, lane);
+    __syncwarp();
+    // The first K/V tiles of a layer may be requested before the QKV phase has finished unless the tile holds
+    // the row that phase appends, or the tile buffers double as the epilogue's park buffer (single-CTA tiles).
+    bool may_prime = tail->a_count[aw] > 0 && (tail->a_list[aw][0].y & PKA_PAIR_LAST) == 0;
+    for (int ph = 0; ph < 4; ++ph)
+      for (int u = 0; u < tab.n_units[ph]; ++u)
+        if (tab.u[ph][u].S == 1) may_prime = false;
+
+    PkCursor cur;  // shared fill sequence (activation producer and normaliser walk it in step with the weights)
+    pk_cursor_init(cur);
+
+    // Activation tiles of one GEMM phase: requested as soon as the phase's grid barrier has completed and the
+    // ring stage is free.  Normalised phases deliver to full_x (the normaliser signals xready), the others
+    // deliver to xready directly.
+    auto x_phase = [&](int ph, int layer) {
+      const int nu = ph == PK_LOGITS ? logits_tiles : tab.n_units[ph];
+      if (nu == 0) return;
+      const bool xform = ph == PK_QKV || ph == PK_UP;
+      const CUtensorMap* tmx = ph == PK_QKV ? &tm_x : ph == PK_OPROJ ? &tm_attn : ph == PK_UP ? &tm_h : ph == PK_DOWN ? &tm_act : &tm_n;
+      pk_wait_flag(&tail->bar_done, pk_need(layer, ph, p.L));
+      fence_proxy_async_all();  // activations written with generic stores by other CTAs, read through TMA
+      evx.on = layer == 1;
+      for (int u = 0; u < nu; ++u) {
+        const int kb0 = ph == PK_LOGITS ? 0 : tab.u[ph][u].kb0, kb1 = ph == PK_LOGITS ? kb_e : tab.u[ph][u].kb1;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if (cur.uses) mbar_wait(&tail->empty[cur.s], cur.par ^ 1);
+          pk_ev(evx, 100 * ph + 1);
+          uint64_t* bar = xform ? &tail->full_x[cur.s] : &tail->xready[cur.s];
+          if (!xform) mbar_arrive(&tail->full_x[cur.s]);  // keep every barrier of the stage in step
+          mbar_expect_tx(bar, uint32_t(x_bytes));
+          tma_load_2d(ring + size_t(cur.s) * kPkStageBytes + kWTileBytes, tmx, kb * kBlockK, 0, bar, kEvictLast);
+          pk_cursor_next(cur);
+        }
+      }
+    };
+
+    // normalizations.py:57-69 applied in place to the activation k-blocks TMA just delivered:
+    //   n = bf16(bf16(x * rstd) * scale)
+    auto transform_phase = [&](int ph, int layer) {
+      const int nu = tab.n_units[ph];
+      if (nu == 0) return;
+      if (atid == 0) pk_ev(ev, 100 * ph + 20);
+      pk_wait_flag(&tail->bar_done, pk_need(layer, ph, p.L));
+      if (atid == 0) pk_ev(ev, 100 * ph + 21);
+      const float* ss = ph == PK_QKV ? p.ss_x : p.ss_h;
+      {  // rstd of every row: two threads per row, eight independent loads each
+        const int row = atid >> 1, half = atid & 1;
+        float tot = 0.0f;
+        if (row < p.rows) {
+          for (int t0 = half * 8; t0 < ss_tiles; t0 += 16) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = t0 + i < ss_tiles ? __ldcg(ss + (t0 + i) * kPkMaxRTile + row) : 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tot += v[i];
+          }
+        }
+        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+        if (atid == 0) pk_ev(ev, 100 * ph + 25);
+        if (half == 0 && row < p.r_tile) tail->rstd[row] = row < p.rows ? 1.0f / sqrtf(tot / float(p.E) + p.eps) : 0.0f;
+      }
+      if (atid == 0) pk_ev(ev, 100 * ph + 26);
+      named_bar_sync(2, 128);
+      if (atid == 0) pk_ev(ev, 100 * ph + 27);
+      // Each warp normalises whole k-blocks on its own (fill i of the phase belongs to warp i % 4), so the k-blocks
+      // of a phase are processed in parallel and no CTA-level barrier sits between a tile's arrival and its MMA.
+      // lane -> 16-byte chunks (row, physical chunk pc): pc = lane & 7, rows (lane >> 3) + 4 j; the logical chunk
+      // pc ^ (row & 7) takes two values (j even / odd).
+      const int pc = lane & 7, rq = lane >> 3;
+      const int lc_a = pc ^ (rq & 7), lc_b = pc ^ ((rq + 4) & 7);
+      float rs[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) rs[j] = (rq + 4 * j) < p.r_tile ? tail->rstd[rq + 4 * j] : 0.0f;
+      const bf16* scale = (ph == PK_QKV ? p.attn_norm : p.mlp_norm) + (long long)layer * p.E;
+      int fi = 0;
+      for (int u = 0; u < nu; ++u) {
+        const PkUnit un = tab.u[ph][u];
+        for (int kb = un.kb0; kb < un.kb1; ++kb, ++fi) {
+          if ((fi & 3) == aw) {
+            const uint4 sc_a = *reinterpret_cast<const uint4*>(scale + kb * kBlockK + lc_a * 8);
+            const uint4 sc_b = *reinterpret_cast<const uint4*>(scale + kb * kBlockK + lc_b * 8);
+            if (atid == 0) pk_ev(ev, 100 * ph + 22);
+            mbar_wait(&tail->full_x[cur.s], cur.par);
+            if (atid == 0) pk_ev(ev, 100 * ph + 23);
+            uint8_t* xt = ring + size_t(cur.s) * kPkStageBytes + kWTileBytes;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int row = rq + 4 * j;
+              if (row < p.r_tile) {
+                uint4* ptr = reinterpret_cast<uint4*>(xt + row * 128 + pc * 16);
+                const uint4 raw = *ptr;
+                const uint4 sc = (j & 1) ? sc_b : sc_a;
+                const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+                const uint32_t sw[4] = {sc.x, sc.y, sc.z, sc.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  // y = bf16(x * rstd) in fp32, then bf16(y * scale) as one packed bf16 multiply (the product of two
+                  // bf16 values is exact in fp32, so the packed instruction rounds exactly once, like the reference)
+                  const uint32_t y = pack_bf16x2(bf16_lo(w[q]) * rs[j], bf16_hi(w[q]) * rs[j]);
+                  const __nv_bfloat162 prod = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&y), *reinterpret_cast<const __nv_bfloat162*>(&sw[q]));
+                  o[q] = *reinterpret_cast<const uint32_t*>(&prod);
+                }
+                *ptr = make_uint4(o[0], o[1], o[2], o[3]);
+              }
+            }
+            fence_proxy_async();  // the MMA reads the tile through the async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tail->xready[cur.s]);
+            if (atid == 0) pk_ev(ev, 100 * ph + 24);
+          }
+          pk_cursor_next(cur);
+        }
+      }
+    };
+
+    // Between attention phases: warps 6-9 normalise (QKV, MLP up), lane 0 of warp 10 requests activation tiles,
+    // everybody else just keeps the ring cursor in step.
+    auto gemm_duty = [&](int ph, int layer) {
+      const bool xform = ph == PK_QKV || ph == PK_UP;
+      if (xformer && xform) {
+        transform_phase(ph, layer);
+      } else if (xproducer && lane == 0) {
+        x_phase(ph, layer);
+      } else {
+        pk_cursor_skip(cur, tab.kbs[ph]);
+      }
+    };
+
+    for (int l = 0; l < p.L; ++l) {
+      ev.on = l == 1;
+      gemm_duty(PK_QKV, l);
+      __syncwarp();
+      // ---- attention over the valid rows of both cache segments ----
+      if (may_prime && lane == 0) {
+        const int row0 = l * p.num_slots * p.hkv * p.T + tail->a_list[aw][0].x;
+        uint8_t* kt = attn_tiles + aw * 2 * 8192;
+        mbar_expect_tx(&tail->attn_bars[2 * aw], 8192);
+        tma_load_2d(kt, &tm_k, 0, row0, &tail->attn_bars[2 * aw], kEvictFirst);
+        mbar_expect_tx(&tail->attn_bars[2 * aw + 1], 8192);
+        tma_load_2d(kt + 8192, &tm_v, 0, row0, &tail->attn_bars[2 * aw + 1], kEvictFirst);
+      }
+      pk_wait_flag(&tail->bar_done, uint32_t(2 + 5 * l));
+      if (atid == 0) pk_ev(ev, 500);
+      pk_attention_cta(tm_k, tm_v, p, tail, l, attn_tiles, kv_phase, cta, aw, lane, may_prime, ev);
+      if (atid == 0) pk_ev(ev, 501);
+      fence_proxy_async_all();
+      named_bar_sync(3, kPkAttnWarps * 32);
+      if (atid == 0) pk_grid_barrier(p, tail, uint32_t(3 + 5 * l));
+      gemm_duty(PK_OPROJ, l);
+      gemm_duty(PK_UP, l);
+      gemm_duty(PK_DOWN, l);
+      __syncwarp();
+    }
+    if (xproducer && lane == 0) x_phase(PK_LOGITS, p.L);
+    __syncwarp();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  timeline_end(tl);
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+}  // namespace mtx

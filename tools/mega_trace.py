@@ -1,4 +1,4 @@
-"""Debug: barrier arrive / release times of every CTA of the persistent step kernel (batch-64 bench config)."""
+"""Debug: grid-barrier arrive / release times of every CTA of the persistent step kernel (batch-64 bench config)."""
 import ctypes, sys, torch, numpy as np
 sys.path.insert(0, '.')
 import bench
@@ -15,61 +15,83 @@ for _ in range(5):
     _lib.check(lib.mtx_decode_step(eng._handle, args.batch, st))
 torch.cuda.synchronize()
 NB, NC = 200, 320
-tr = torch.zeros(2 * NB * NC, dtype=torch.int64, device='cuda')
+tr = torch.zeros(2 * NB * NC + NC * 64, dtype=torch.int64, device='cuda')
 lib.mtx_debug_set_trace(ctypes.c_void_p(tr.data_ptr()))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
 _lib.check(lib.mtx_decode_step(eng._handle, args.batch, st))
+e1.record()
 torch.cuda.synchronize()
 lib.mtx_debug_set_trace(None)
+print("step (prepare + persistent + finalize), events: %.1f us" % (e0.elapsed_time(e1) * 1e3))
 t = tr.cpu().numpy()
 # rows of gridDim.x entries: row 0 = end stamps (largest values), row 1 = start stamps (smallest)
 g = int(np.argmax(t < t[0] - 100000))
 print("grid", g)
-nb = 0
 a = t[: (len(t) // g) * g].reshape(-1, g)
-start = a[1]; end = a[0]
+start, end = a[1], a[0]
 t0 = start.min()
 print(f"start spread {(start.max()-t0)/1e3:.2f} us; end {(end.max()-t0)/1e3:.2f} us")
-names = ["norm1", "qkv", "attn", "oproj", "norm2", "up", "down"]
+names = ["qkv", "attn", "oproj", "up", "down"]
 prev_rel = start
 rows = []
 k = 1
 while 2 * k + 1 < a.shape[0] and a[2 * k].min() > 0:
     arr, rel = a[2 * k], a[2 * k + 1]
-    rows.append(((arr.min() - prev_rel.max()) / 1e3, (arr.max() - prev_rel.max()) / 1e3, (rel.min() - arr.max()) / 1e3, (rel.max() - arr.max()) / 1e3))
+    rows.append(((arr.min() - prev_rel.max()) / 1e3, np.median(arr - prev_rel.max()) / 1e3, (arr.max() - prev_rel.max()) / 1e3,
+                 (rel.min() - arr.max()) / 1e3, (rel.max() - arr.max()) / 1e3))
     prev_rel = rel
     k += 1
 rows = np.array(rows)
-print("barriers", len(rows))
-L = (len(rows) - 1) // 7
-for i in range(min(len(rows), 15)):
-    nm = names[i % 7] if i < 7 * L else "final_norm"
-    print(f"{i:3d} {nm:8s} first-arrive {rows[i,0]:7.2f} last-arrive {rows[i,1]:7.2f}  release first {rows[i,2]:6.2f} last {rows[i,3]:6.2f}")
+nb = len(rows)
+L = (nb - 2) // 5
+print("barriers", nb, "layers", L)
+def show(i, nm):
+    print(f"{i:3d} {nm:8s} arrive first {rows[i,0]:7.2f} median {rows[i,1]:7.2f} last {rows[i,2]:7.2f} | release first {rows[i,3]:6.2f} last {rows[i,4]:6.2f}")
+show(0, "embed")
+for i in range(1, min(nb, 11)):
+    show(i, names[(i - 1) % 5])
+print("per phase means over layers (us): first / median / last arrival after previous release, barrier latency (last release - last arrival)")
+tot = 0.0
 for j, nm in enumerate(names):
-    sel = rows[j:7 * L:7]
-    print(f"{nm:8s} mean phase(last-arrive after prev release) {sel[:,1].mean():7.2f}  first-arrive {sel[:,0].mean():7.2f}  barrier latency first {sel[:,2].mean():6.2f} last {sel[:,3].mean():6.2f}")
-print("final_norm", rows[7 * L])
+    sel = rows[1 + j:1 + 5 * L:5]
+    print(f"  {nm:6s} {sel[:,0].mean():7.2f} {sel[:,1].mean():7.2f} {sel[:,2].mean():7.2f}   barrier {sel[:,4].mean():6.2f}")
+    tot += sel[:, 2].mean() + sel[:, 4].mean()
+print(f"  layer total {tot:.2f} us -> {tot * L:.1f} us for {L} layers")
+show(nb - 1, "fin.norm")
 print(f"logits phase: {(end.max() - prev_rel.max())/1e3:.2f} us")
-# ---- distribution of arrival times for the phases of layer 1, and worker event logs ----
-k0 = 1 + 7
-for j, nm in enumerate(names):
-    k = k0 + j
-    prev = a[2 * (k - 1) + 1].max()
-    arr = np.sort((a[2 * k] - prev) / 1e3)
-    print(nm, "arrive pct 0/10/50/90/100:", np.percentile(arr, [0, 10, 50, 90, 100]).round(2), "argmax cta", int(np.argmax(a[2 * k])))
-ev = t[2 * 200 * g:2 * 200 * g + g * 64].reshape(g, 32, 2)
-rel = {1: a[2 * (k0 + 0) + 1].max(), 2: a[2 * (k0 + 2) + 1].max(), 3: a[2 * (k0 + 4) + 1].max()}  # qkv after norm1 barrier, oproj after attn, up after norm2
-rel_down = a[2 * (k0 + 5) + 1].max()
-for c in list(range(0, 16)) + [g - 1]:
-    out = []
-    seen2 = 0
-    for i in range(32):
-        eid, tm = int(ev[c, i, 0]), ev[c, i, 1]
-        if tm == 0: break
-        epi = eid // 10
-        base = rel.get(epi, 0)
-        if epi == 2:
-            # two residual phases per layer: oproj first then down
-            seen2 += (eid % 10 == 0)
-            base = rel[2] if seen2 <= 1 else rel_down
-        out.append(f"{eid}:{(tm - base) / 1e3:.2f}")
-    print("cta", c, " ".join(out))
+
+# ---- event logs of layer 1 (times relative to the release of the barrier before that layer's QKV phase) ----
+evs = t[2 * 200 * g:2 * 200 * g + g * 3 * 64].reshape(g, 3, 32, 2)
+base = a[2 * 6 + 1].max()   # barrier 6 = after the MLP-down phase of layer 0
+rel_names = {7: "qkv", 8: "attn", 9: "oproj", 10: "up", 11: "down"}
+print("releases (us after base):", {nm: round((a[2 * k + 1].max() - base) / 1e3, 2) for k, nm in rel_names.items()})
+print("logits phase events are relative to the final-norm barrier release:", round((prev_rel.max() - base) / 1e3, 2))
+for c in [0, 1, 50, 100, 139, 147]:
+    for role, rn in enumerate(["epi", "xform/attn", "producer"]):
+        out = []
+        for i in range(32):
+            eid, tm = int(evs[c, role, i, 0]), evs[c, role, i, 1]
+            if tm == 0: break
+            out.append(f"{eid}:{(tm - base) / 1e3:.2f}")
+        print("cta", c, rn, " ".join(out))
+
+# ---- per-CTA lateness at the attention barrier, averaged over layers ----
+late = np.zeros(g)
+for l in range(L):
+    k = 3 + 5 * l
+    arr = a[2 * k]
+    late += (arr - arr.min()) / 1e3
+late /= L
+order = np.argsort(late)
+print("attention arrival lateness per CTA (us, mean over layers): min %.2f median %.2f max %.2f" % (late.min(), np.median(late), late.max()))
+print("  earliest CTAs:", [(int(c), round(float(late[c]), 1)) for c in order[:8]])
+print("  latest CTAs:  ", [(int(c), round(float(late[c]), 1)) for c in order[-12:]])
+for nm, kk in (("qkv", 2), ("oproj", 4), ("up", 5), ("down", 6)):
+    lt = np.zeros(g)
+    for l in range(L):
+        arr = a[2 * (kk + 5 * l)]
+        lt += (arr - arr.min()) / 1e3
+    lt /= L
+    o2 = np.argsort(lt)
+    print(f"{nm} lateness: median {np.median(lt):.2f} max {lt.max():.2f} latest CTAs", [(int(c), round(float(lt[c]), 1)) for c in o2[-6:]])
