@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(kAttnThreads)
 decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnParams p) {
   constexpr int kTileBytes = 64 * D * 2;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space
   const int G = p.hq / p.hkv;
   const int o_rows = G <= 8 ? 8 : 16;
   // [warp][K tile | V tile] | merge buffer [warp][o_rows][D] fp32 | barriers | merge statistics

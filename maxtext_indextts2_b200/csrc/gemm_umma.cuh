@@ -310,7 +310,7 @@ template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x, const GemmParams p, const EpiArgs e) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space
   const int x_tile_bytes = p.r_tile * kBlockK * 2;
   const int stage_bytes = kWTileBytes + x_tile_bytes;
   GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(smem + gemm_main_region_bytes(p.stages, p.r_tile, p.splits, EPI));

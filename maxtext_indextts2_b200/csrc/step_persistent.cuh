@@ -875,7 +875,7 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
                        const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_n,
                        const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const PkParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space
   uint8_t* ring = smem;
   uint8_t* attn_tiles = smem + kPkRingBytes;
   float* park = reinterpret_cast<float*>(attn_tiles);
@@ -1343,9 +1343,6 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
       // pc ^ (row & 7) takes two values (j even / odd).
       const int pc = lane & 7, rq = lane >> 3;
       const int lc_a = pc ^ (rq & 7), lc_b = pc ^ ((rq + 4) & 7);
-      float rs[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) rs[j] = (rq + 4 * j) < p.r_tile ? tail->rstd[rq + 4 * j] : 0.0f;
       const bf16* scale = (ph == PK_QKV ? p.attn_norm : p.mlp_norm) + (long long)layer * p.E;
       int fi = 0;
       for (int u = 0; u < nu; ++u) {
@@ -1358,28 +1355,37 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
             mbar_wait(&tail->full_x[cur.s], cur.par);
             if (atid == 0) pk_ev(ev, 100 * ph + 23);
             uint8_t* xt = ring + size_t(cur.s) * kPkStageBytes + kWTileBytes;
+            // four chunks at a time (loads, math, stores): the in-place update would otherwise serialise one
+            // dependent chain per chunk.  Rows past r_tile lie in the stage's unused activation space: harmless.
+            uint8_t* lane_base = xt + rq * 128 + pc * 16;
+#pragma unroll 1  // keep the body small: it is entered once per k-block and must stay resident in the instruction cache
+            for (int j0 = 0; j0 < 16; j0 += 4) {
+              uint4 raw[4];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int row = rq + 4 * j;
-              if (row < p.r_tile) {
-                uint4* ptr = reinterpret_cast<uint4*>(xt + row * 128 + pc * 16);
-                const uint4 raw = *ptr;
-                const uint4 sc = (j & 1) ? sc_b : sc_a;
-                const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-                const uint32_t sw[4] = {sc.x, sc.y, sc.z, sc.w};
-                uint32_t o[4];
+              for (int jj = 0; jj < 4; ++jj) raw[jj] = *reinterpret_cast<const uint4*>(lane_base + (j0 + jj) * 512);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  // y = bf16(x * rstd) in fp32, then bf16(y * scale) as one packed bf16 multiply (the product of two
-                  // bf16 values is exact in fp32, so the packed instruction rounds exactly once, like the reference)
-                  const uint32_t y = pack_bf16x2(bf16_lo(w[q]) * rs[j], bf16_hi(w[q]) * rs[j]);
-                  const __nv_bfloat162 prod = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&y), *reinterpret_cast<const __nv_bfloat162*>(&sw[q]));
-                  o[q] = *reinterpret_cast<const uint32_t*>(&prod);
-                }
-                *ptr = make_uint4(o[0], o[1], o[2], o[3]);
+              for (int jj = 0; jj < 4; ++jj) {
+                const uint4 sc = (jj & 1) ? sc_b : sc_a;
+                const float r = tail->rstd[rq + 4 * (j0 + jj)];
+                // y = bf16(x * rstd) in fp32, then bf16(y * scale) as one packed bf16 multiply (the product of two
+                // bf16 values is exact in fp32, so the packed instruction rounds exactly once, like the reference)
+                const uint32_t y0 = pack_bf16x2(bf16_lo(raw[jj].x) * r, bf16_hi(raw[jj].x) * r);
+                const uint32_t y1 = pack_bf16x2(bf16_lo(raw[jj].y) * r, bf16_hi(raw[jj].y) * r);
+                const uint32_t y2 = pack_bf16x2(bf16_lo(raw[jj].z) * r, bf16_hi(raw[jj].z) * r);
+                const uint32_t y3 = pack_bf16x2(bf16_lo(raw[jj].w) * r, bf16_hi(raw[jj].w) * r);
+                const __nv_bfloat162 p0 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&y0), *reinterpret_cast<const __nv_bfloat162*>(&sc.x));
+                const __nv_bfloat162 p1 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&y1), *reinterpret_cast<const __nv_bfloat162*>(&sc.y));
+                const __nv_bfloat162 p2 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&y2), *reinterpret_cast<const __nv_bfloat162*>(&sc.z));
+                const __nv_bfloat162 p3 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&y3), *reinterpret_cast<const __nv_bfloat162*>(&sc.w));
+                raw[jj] = make_uint4(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1),
+                                     *reinterpret_cast<const uint32_t*>(&p2), *reinterpret_cast<const uint32_t*>(&p3));
               }
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) *reinterpret_cast<uint4*>(lane_base + (j0 + jj) * 512) = raw[jj];
             }
+            if (atid == 0) pk_ev(ev, 100 * ph + 28);
             fence_proxy_async();  // the MMA reads the tile through the async proxy
+            if (atid == 0) pk_ev(ev, 100 * ph + 29);
             __syncwarp();
             if (lane == 0) mbar_arrive(&tail->xready[cur.s]);
             if (atid == 0) pk_ev(ev, 100 * ph + 24);
