@@ -458,6 +458,7 @@ bool pk_fill_phase(std::vector<PkTable>& tabs, int ph, int n, int k) {
 
 bool pk_usable(const mtx_engine* e, int rows) {
   if (e->pk_ctas <= 0 || round_rows(rows) > kPkMaxRTile) return false;
+  if (e->cfg.num_q_heads / e->cfg.num_kv_heads > 8) return false;  // the attention MMA carries the group's heads in its 8 columns
   // an attention warp's tile list holds kPkAttnListMax entries: bound the worst case (every context full)
   const mtx_model_config& c = e->cfg;
   const long long worst = (long long)rows * c.num_kv_heads * attn_max_tiles(c.max_prefill_len, c.max_target_len);
@@ -877,6 +878,13 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
         MTX_CUDA(cudaMemcpy(e->pk_tables, tabs.data(), tabs.size() * sizeof(PkTable), cudaMemcpyHostToDevice));
         // the split-K exchange workspace starts out (and is left by every reader) as "nothing written"
         fill_u32_kernel<<<256, 256>>>(reinterpret_cast<uint32_t*>(e->pk_part_ws), size_t(e->num_sms) * 4 * kPkSlotFloats, kPkSentinel);
+        {
+          const mtx_model_config& cc = e->cfg;
+          const size_t pk_rows = cc.max_rows < kPkMaxRTile ? cc.max_rows : kPkMaxRTile;
+          const size_t Gq = cc.num_q_heads / cc.num_kv_heads;
+          const size_t words = pk_rows * cc.num_kv_heads * kPkMaxParts * ((Gq * cc.head_dim + 2 * Gq + 3) / 4 * 4);
+          fill_u32_kernel<<<256, 256>>>(reinterpret_cast<uint32_t*>(e->pk_attn_part_o), words, kPkSentinel);
+        }
         MTX_CUDA(cudaGetLastError());
         MTX_CUDA(cudaDeviceSynchronize());
         e->pk_ctas = ctas;

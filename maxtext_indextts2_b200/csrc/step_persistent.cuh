@@ -162,6 +162,12 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
   return v;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// Transposes an 8x8 matrix of 16-bit elements held one row pair per thread (thread (gid, tid4) holds M[gid][2 tid4 .. +1]).
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -537,7 +543,6 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
   const int G = p.hq / p.hkv;
   const int layer_row = layer * p.num_slots * p.hkv * p.T;
   const int gid = lane >> 2, tid4 = lane & 3;
-  const int mtx_i = lane >> 3, lrow = lane & 7;
   uint8_t* k_tile = attn_tiles + aw * 2 * 8192;
   uint8_t* v_tile = k_tile + 8192;
   uint64_t* bar_k = &tail->attn_bars[2 * aw];
@@ -545,7 +550,6 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
   const uint32_t kb = smem_u32(k_tile), vb = smem_u32(v_tile);
   const int n = tail->a_count[aw];
   const int2* list = tail->a_list[aw];
-  const int slot_floats = G * D + 2 * G;
 
   if (lane == 0) {
     tail->a_seg[aw][0].x = -1;
@@ -560,53 +564,55 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
     tma_load_2d(v_tile, &tm_v, 0, row0, bar_v, kEvictFirst);
   }
 
-  uint32_t qf[D / 16][4];
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
-  float o[D / 8][4];
+  // Transposed formulation: S^T = K Q^T and O^T = V^T P^T, so the 16-row MMA dimension carries KV rows / head
+  // dimensions and the 8-column dimension carries the (up to 8) query heads of the group: no padding of the
+  // heads to 16, half the MMAs, exponentials and accumulator registers of the head-major form.
+  //   thread (gid, tid4) owns heads h0 = 2 tid4, h1 = h0 + 1
+  //   s[mb][0..3]  = S^T[kv = 16 mb + gid (+8 for 2,3)][h0, h1]
+  //   o[db][0..3]  = O^T[d  = 16 db + gid (+8 for 2,3)][h0, h1]
+  uint32_t qb[D / 16][2];
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;  // per head h0 / h1 (l: this thread's rows only)
+  float o[D / 16][4];
   bool seg_first = false;   // the running segment starts at tile 0 of its pair
-  int n_partial = 0;        // partial segments this warp has parked so far
+  const int a_row = (lane & 7) + 8 * ((lane >> 3) & 1), a_chunk = lane >> 4;  // ldmatrix addressing, K tile as A
+  const int v_row = (lane & 7) + 8 * (lane >> 4), v_chunk = (lane >> 3) & 1;   // ldmatrix.trans addressing, V^T as A
 
   for (int i = 0; i < n; ++i) {
     const int2 e = list[i];
     const int meta = e.y;
     const int r = pka_row(meta), h = pka_head(meta), cnt = pka_cnt(meta);
     if (meta & PKA_SEG_START) {
-      const bf16* qrow = p.q + (long long)r * p.hq * D + (long long)h * G * D;
+      const bf16* qrow = p.q + (long long)r * p.hq * D + (long long)h * G * D + gid * D + tid4 * 2;
 #pragma unroll
-      for (int tt = 0; tt < D / 16; ++tt) {
-        const int d = tt * 16 + tid4 * 2;
-        qf[tt][0] = gid < G ? __ldcg(reinterpret_cast<const uint32_t*>(qrow + gid * D + d)) : 0u;
-        qf[tt][1] = gid + 8 < G ? __ldcg(reinterpret_cast<const uint32_t*>(qrow + (gid + 8) * D + d)) : 0u;
-        qf[tt][2] = gid < G ? __ldcg(reinterpret_cast<const uint32_t*>(qrow + gid * D + d + 8)) : 0u;
-        qf[tt][3] = gid + 8 < G ? __ldcg(reinterpret_cast<const uint32_t*>(qrow + (gid + 8) * D + d + 8)) : 0u;
+      for (int kk = 0; kk < D / 16; ++kk) {
+        qb[kk][0] = gid < G ? __ldcg(reinterpret_cast<const uint32_t*>(qrow + kk * 16)) : 0u;
+        qb[kk][1] = gid < G ? __ldcg(reinterpret_cast<const uint32_t*>(qrow + kk * 16 + 8)) : 0u;
       }
       m0 = m1 = -INFINITY;
       l0 = l1 = 0.0f;
 #pragma unroll
-      for (int j = 0; j < D / 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.0f;
+      for (int db = 0; db < D / 16; ++db) o[db][0] = o[db][1] = o[db][2] = o[db][3] = 0.0f;
       seg_first = (meta & PKA_PAIR_FIRST) != 0;
     }
     const bool more = i + 1 < n;
     const int next_row = more ? layer_row + list[i + 1].x : 0;
 
-    // ---- S = Q K^T over the 64 rows of the tile ----
-    float s[8][4];
+    // ---- S^T = K Q^T over the 64 rows of the tile ----
+    float s[4][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
+    for (int mb = 0; mb < 4; ++mb) s[mb][0] = s[mb][1] = s[mb][2] = s[mb][3] = 0.0f;
     if (lane == 0) pk_ev(ev, 600);
     mbar_wait(bar_k, phase);
     if (lane == 0) pk_ev(ev, 601);
 #pragma unroll
-    for (int tt = 0; tt < D / 16; ++tt) {
+    for (int mb = 0; mb < 4; ++mb) {
 #pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {
-        const int row = 8 * (2 * jp + (mtx_i >> 1)) + lrow;
-        const int c = 2 * tt + (mtx_i & 1);
-        const uint32_t addr = kb + row * 128 + (((c & 7) ^ (row & 7)) << 4);
-        uint32_t b00, b01, b10, b11;
-        ldmatrix_x4(addr, b00, b01, b10, b11);
-        mma_m16n8k16_bf16(s[2 * jp], qf[tt], b00, b01);
-        mma_m16n8k16_bf16(s[2 * jp + 1], qf[tt], b10, b11);
+      for (int kk = 0; kk < D / 16; ++kk) {
+        const int row = 16 * mb + a_row;
+        const uint32_t addr = kb + row * 128 + ((((2 * kk + a_chunk) & 7) ^ (row & 7)) << 4);
+        uint32_t a[4];
+        ldmatrix_x4(addr, a[0], a[1], a[2], a[3]);
+        mma_m16n8k16_bf16(s[mb], a, qb[kk][0], qb[kk][1]);
       }
     }
     // K tile consumed: refill it with the next tile's keys while the softmax and P V run
@@ -617,30 +623,31 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
       mbar_expect_tx(bar_k, kTileBytes);
       tma_load_2d(k_tile, &tm_k, 0, next_row, bar_k, kEvictFirst);
     }
-    // ---- mask + online softmax (quad shuffles) ----
+    // ---- mask + online softmax: a head's scores live in the 8 threads of equal tid4 ----
     if (p.softcap != 0.0f) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) s[j][q] = tanhf(s[j][q] / p.softcap) * p.softcap;
+        for (int q = 0; q < 4; ++q) s[mb][q] = tanhf(s[mb][q] / p.softcap) * p.softcap;
     }
     if (cnt < 64) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (8 * j + tid4 * 2 + (q & 1) >= cnt) s[j][q] = -INFINITY;
+          if (16 * mb + gid + (q >> 1) * 8 >= cnt) s[mb][q] = -INFINITY;
     }
     float tm0 = -INFINITY, tm1 = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      tm0 = fmaxf(tm0, fmaxf(s[j][0], s[j][1]));
-      tm1 = fmaxf(tm1, fmaxf(s[j][2], s[j][3]));
+    for (int mb = 0; mb < 4; ++mb) {
+      tm0 = fmaxf(tm0, fmaxf(s[mb][0], s[mb][2]));
+      tm1 = fmaxf(tm1, fmaxf(s[mb][1], s[mb][3]));
     }
-    tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1));
-    tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 2));
-    tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1));
-    tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
+#pragma unroll
+    for (int sh = 4; sh < 32; sh <<= 1) {
+      tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, sh));
+      tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, sh));
+    }
     const float nm0 = fmaxf(m0, tm0), nm1 = fmaxf(m1, tm1);
     const float a0 = ex2_approx((m0 - nm0) * kLog2e), a1 = ex2_approx((m1 - nm1) * kLog2e);  // ex2(-inf) = 0 on the first tile
     m0 = nm0;
@@ -648,25 +655,26 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
     l0 *= a0;
     l1 *= a1;
     const float ms0 = m0 * kLog2e, ms1 = m1 * kLog2e;
-    uint32_t pa[4][4];
+    uint32_t pb[4][2];  // P^T as the B operand of O^T += V^T P^T, one k-step per 16 KV rows
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float p0 = ex2_approx(fmaf(s[j][0], kLog2e, -ms0)), p1 = ex2_approx(fmaf(s[j][1], kLog2e, -ms0));
-      const float p2 = ex2_approx(fmaf(s[j][2], kLog2e, -ms1)), p3 = ex2_approx(fmaf(s[j][3], kLog2e, -ms1));
-      l0 += p0 + p1;
-      l1 += p2 + p3;
-      // probabilities are cast to the value dtype before the PV product (kernels/ragged_attention.py:156)
-      pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-      pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+    for (int mb = 0; mb < 4; ++mb) {
+      const float p0 = ex2_approx(fmaf(s[mb][0], kLog2e, -ms0)), p1 = ex2_approx(fmaf(s[mb][1], kLog2e, -ms1));
+      const float p2 = ex2_approx(fmaf(s[mb][2], kLog2e, -ms0)), p3 = ex2_approx(fmaf(s[mb][3], kLog2e, -ms1));
+      l0 += p0 + p2;
+      l1 += p1 + p3;
+      // probabilities are cast to the value dtype before the PV product (kernels/ragged_attention.py:156);
+      // the transpose turns (kv row, head pair) fragments into (head, kv row pair) fragments
+      pb[mb][0] = movmatrix_trans(pack_bf16x2(p0, p1));
+      pb[mb][1] = movmatrix_trans(pack_bf16x2(p2, p3));
     }
 #pragma unroll
-    for (int j = 0; j < D / 8; ++j) {
-      o[j][0] *= a0;
-      o[j][1] *= a0;
-      o[j][2] *= a1;
-      o[j][3] *= a1;
+    for (int db = 0; db < D / 16; ++db) {
+      o[db][0] *= a0;
+      o[db][1] *= a1;
+      o[db][2] *= a0;
+      o[db][3] *= a1;
     }
-    // ---- O += P V ----
+    // ---- O^T += V^T P^T ----
     if (lane == 0) pk_ev(ev, 603);
     mbar_wait(bar_v, phase);
     if (lane == 0) pk_ev(ev, 604);
@@ -676,16 +684,14 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
       __syncwarp();
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int mb = 0; mb < 4; ++mb) {
 #pragma unroll
-      for (int jp = 0; jp < D / 16; ++jp) {
-        const int row = 16 * u + 8 * (mtx_i & 1) + lrow;
-        const int c = 2 * jp + (mtx_i >> 1);
-        const uint32_t addr = vb + row * 128 + (((c & 7) ^ (row & 7)) << 4);
-        uint32_t b00, b01, b10, b11;
-        ldmatrix_x4_trans(addr, b00, b01, b10, b11);
-        mma_m16n8k16_bf16(o[2 * jp], pa[u], b00, b01);
-        mma_m16n8k16_bf16(o[2 * jp + 1], pa[u], b10, b11);
+      for (int db = 0; db < D / 16; ++db) {
+        const int row = 16 * mb + v_row;
+        const uint32_t addr = vb + row * 128 + ((((2 * db + v_chunk) & 7) ^ (row & 7)) << 4);
+        uint32_t a[4];
+        ldmatrix_x4_trans(addr, a[0], a[1], a[2], a[3]);
+        mma_m16n8k16_bf16(o[db], a, pb[mb][0], pb[mb][1]);
       }
     }
     fence_proxy_async();
@@ -698,44 +704,53 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
     if (lane == 0) pk_ev(ev, 605);
 
     if (meta & PKA_SEG_END) {
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+#pragma unroll
+      for (int sh = 4; sh < 32; sh <<= 1) {
+        l0 += __shfl_xor_sync(0xffffffffu, l0, sh);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, sh);
+      }
+      const int h0 = tid4 * 2;
       if (seg_first && (meta & PKA_PAIR_LAST)) {
-        // the whole pair lived in this warp: normalise and store
+        // the whole pair lived in this warp: normalise, transpose back to (head, d pair) fragments and store
         const long long out_base = (long long)r * p.hq * D + (long long)h * G * D;
         const float i0 = 1.0f / l0, i1 = 1.0f / l1;
 #pragma unroll
-        for (int j = 0; j < D / 8; ++j) {
-          const int d = 8 * j + tid4 * 2;
-          if (gid < G) *reinterpret_cast<uint32_t*>(p.attn + out_base + gid * D + d) = pack_bf16x2(o[j][0] * i0, o[j][1] * i0);
-          if (gid + 8 < G) *reinterpret_cast<uint32_t*>(p.attn + out_base + (gid + 8) * D + d) = pack_bf16x2(o[j][2] * i1, o[j][3] * i1);
+        for (int db = 0; db < D / 16; ++db) {
+          const uint32_t lo = movmatrix_trans(pack_bf16x2(o[db][0] * i0, o[db][1] * i1));  // (head gid, d = 16 db + 2 tid4 ..)
+          const uint32_t hi = movmatrix_trans(pack_bf16x2(o[db][2] * i0, o[db][3] * i1));  // (head gid, d = 16 db + 8 + 2 tid4 ..)
+          if (gid < G) {
+            *reinterpret_cast<uint32_t*>(p.attn + out_base + gid * D + 16 * db + tid4 * 2) = lo;
+            *reinterpret_cast<uint32_t*>(p.attn + out_base + gid * D + 16 * db + 8 + tid4 * 2) = hi;
+          }
         }
       } else {
-        // park the partial: the warp's last segment goes to its (now idle) K buffer, an earlier one to its slot
+        // park the partial ([head][d] fp32, then (m, l) per head): the warp's last segment goes to its (now idle)
+        // K buffer, an earlier one to its slot
         const bool final_seg = !more;
         float* dst = final_seg ? reinterpret_cast<float*>(k_tile) : tail->a_slot[aw];
 #pragma unroll
-        for (int j = 0; j < D / 8; ++j) {
-          const int d = 8 * j + tid4 * 2;
-          if (gid < G) *reinterpret_cast<float2*>(dst + gid * D + d) = make_float2(o[j][0], o[j][1]);
-          if (gid + 8 < G) *reinterpret_cast<float2*>(dst + (gid + 8) * D + d) = make_float2(o[j][2], o[j][3]);
+        for (int db = 0; db < D / 16; ++db) {
+          const int d = 16 * db + gid;
+          if (h0 < G) {
+            dst[h0 * D + d] = o[db][0];
+            dst[h0 * D + d + 8] = o[db][2];
+          }
+          if (h0 + 1 < G) {
+            dst[(h0 + 1) * D + d] = o[db][1];
+            dst[(h0 + 1) * D + d + 8] = o[db][3];
+          }
         }
-        if (tid4 == 0) {
-          if (gid < G) *reinterpret_cast<float2*>(dst + G * D + gid * 2) = make_float2(m0, l0);
-          if (gid + 8 < G) *reinterpret_cast<float2*>(dst + G * D + (gid + 8) * 2) = make_float2(m1, l1);
+        if (gid == 0) {
+          if (h0 < G) *reinterpret_cast<float2*>(dst + G * D + h0 * 2) = make_float2(m0, l0);
+          if (h0 + 1 < G) *reinterpret_cast<float2*>(dst + G * D + (h0 + 1) * 2) = make_float2(m1, l1);
         }
         if (lane == 0) {
           const int flags = (seg_first ? 1 : 0) | ((meta & PKA_PAIR_LAST) ? 2 : 0);
           tail->a_seg[aw][final_seg ? 1 : 0] = make_int4(r * p.hkv + h, flags, r, h);
         }
-        ++n_partial;
       }
     }
   }
-  (void)n_partial;
-  (void)slot_floats;
 
   // ---- phase 2: merge the partial segments of this CTA ----
   named_bar_sync(3, kPkAttnWarps * 32);
@@ -786,15 +801,20 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
     const int r = me.z, h = me.w, pair = me.x;
     const long long out_base = (long long)r * p.hq * D + (long long)h * G * D;
     const bool complete = (flags & 3) == 3;
-    // CTA-level partial slot when the pair is shared with other CTAs
-    const long long g_first = (long long)tail->r_prefix[r] * p.hkv + (long long)h * attn_num_tiles(tail->r_len0[r], tail->r_rf[r], tail->r_rl[r], p.T - p.P);
-    int c_first = 0, n_parts = 1;
-    float* gpart = nullptr;
+    // A pair cut between CTAs: the CTA that holds the pair's FIRST tile merges.  That tile sits at the END of its
+    // tile range, so it finishes last; the other CTAs hold the pair at the START of their ranges and have long
+    // stored their parts by then.  Parts travel through an L2 workspace with the flag-in-data protocol of the
+    // split-K exchange (a word is the sentinel or data): no fence, no ticket, one load round for the merger.
+    const bool merger = !complete && (flags & 1) != 0;
+    const int stride = (G * D + 2 * G + 3) & ~3;  // 16-byte aligned parts
+    float* gbase = p.attn_part_o + (long long)pair * kPkMaxParts * stride;
+    int n_other = 0, my_part = 0;
     if (!complete) {
       const int nt = attn_num_tiles(tail->r_len0[r], tail->r_rf[r], tail->r_rl[r], p.T - p.P);
-      c_first = pk_cta_of(g_first, nc, total);
-      n_parts = pk_cta_of(g_first + nt - 1, nc, total) - c_first + 1;
-      gpart = p.attn_part_o + ((long long)pair * kPkMaxParts + (cta - c_first)) * ((G * D + 2 * G + 3) & ~3);
+      const long long g_first = (long long)tail->r_prefix[r] * p.hkv + (long long)h * nt;
+      const int c_first = pk_cta_of(g_first, nc, total);
+      n_other = pk_cta_of(g_first + nt - 1, nc, total) - c_first;  // parts held by other CTAs
+      my_part = cta - c_first - 1;                                  // -1 for the merger
     }
     for (int unit = lane; unit < G * (D / 4); unit += 32) {
       const int gq = unit / (D / 4), d4 = unit - gq * (D / 4);
@@ -809,57 +829,57 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
         Ls += ml.y * sc;
         acc.x += o4.x * sc; acc.y += o4.y * sc; acc.z += o4.z * sc; acc.w += o4.w * sc;
       }
-      if (complete) {
+      if (merger) {
+        for (int c0 = 0; c0 < n_other; c0 += 4) {  // both loads of up to four parts travel together
+          float2 ml[4];
+          float4 o4[4];
+          const long long t_spin = clock64();
+          for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+              if (c0 + cc < n_other) {
+                const float* part = gbase + (long long)(c0 + cc) * stride;
+                ml[cc] = __ldcg(reinterpret_cast<const float2*>(part + G * D + gq * 2));
+                o4[cc] = ldcg_f4(part + gq * D + d4 * 4);
+                ok = ok && __float_as_uint(ml[cc].x) != kPkSentinel && __float_as_uint(ml[cc].y) != kPkSentinel &&
+                     __float_as_uint(o4[cc].x) != kPkSentinel && __float_as_uint(o4[cc].y) != kPkSentinel &&
+                     __float_as_uint(o4[cc].z) != kPkSentinel && __float_as_uint(o4[cc].w) != kPkSentinel;
+              }
+            if (ok) break;
+            if (clock64() - t_spin > 4000000000LL) {
+              printf("mtx: attention merge timed out (block %d pair %d)\n", cta, pair);
+              __trap();
+            }
+          }
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+            if (c0 + cc < n_other) {
+              const float Mn = fmaxf(M, ml[cc].x);
+              const float so = ex2_approx((M - Mn) * kLog2e), sn = ex2_approx((ml[cc].x - Mn) * kLog2e);
+              Ls = Ls * so + ml[cc].y * sn;
+              acc.x = acc.x * so + o4[cc].x * sn; acc.y = acc.y * so + o4[cc].y * sn;
+              acc.z = acc.z * so + o4[cc].z * sn; acc.w = acc.w * so + o4[cc].w * sn;
+              M = Mn;
+            }
+        }
+      }
+      if (complete || merger) {
         const float inv = 1.0f / Ls;
         *reinterpret_cast<uint2*>(p.attn + out_base + gq * D + d4 * 4) = pack_bf16x4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
       } else {
-        __stcg(reinterpret_cast<float4*>(gpart + gq * D + d4 * 4), acc);
-        if (d4 == 0) __stcg(reinterpret_cast<float2*>(gpart + G * D + gq * 2), make_float2(M, Ls));
+        float* gpart = gbase + (long long)my_part * stride;
+        *reinterpret_cast<float4*>(gpart + gq * D + d4 * 4) = acc;
+        if (d4 == 0) *reinterpret_cast<float2*>(gpart + G * D + gq * 2) = make_float2(M, Ls);
       }
     }
-    if (!complete) {
+    if (merger) {
+      // every lane has read its fragments: put the sentinel back for the next layer
       __syncwarp();
-      int last = 0;
-      if (lane == 0) {
-        __threadfence();  // cumulative over the warp's stores (ordered before it by the warp barrier)
-        const int old = atomicAdd(p.attn_tickets + pair, 1);
-        last = old == n_parts - 1;
-        if (last) {
-          p.attn_tickets[pair] = 0;
-          __threadfence();
-        }
-      }
-      last = __shfl_sync(0xffffffffu, last, 0);
-      if (last) {
-        const int stride = (G * D + 2 * G + 3) & ~3;  // 16-byte aligned parts
-        const float* base = p.attn_part_o + (long long)pair * kPkMaxParts * stride;
-        for (int unit = lane; unit < G * (D / 4); unit += 32) {
-          const int gq = unit / (D / 4), d4 = unit - gq * (D / 4);
-          float M = -INFINITY, Ls = 0.0f;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int c0 = 0; c0 < n_parts; c0 += 4) {  // both loads of up to four parts travel together
-            float2 ml[4];
-            float4 o4[4];
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc)
-              if (c0 + cc < n_parts) {
-                ml[cc] = __ldcg(reinterpret_cast<const float2*>(base + (long long)(c0 + cc) * stride + G * D + gq * 2));
-                o4[cc] = ldcg_f4(base + (long long)(c0 + cc) * stride + gq * D + d4 * 4);
-              }
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc)
-              if (c0 + cc < n_parts) {
-                const float Mn = fmaxf(M, ml[cc].x);
-                const float so = ex2_approx((M - Mn) * kLog2e), sn = ex2_approx((ml[cc].x - Mn) * kLog2e);
-                Ls = Ls * so + ml[cc].y * sn;
-                acc.x = acc.x * so + o4[cc].x * sn; acc.y = acc.y * so + o4[cc].y * sn;
-                acc.z = acc.z * so + o4[cc].z * sn; acc.w = acc.w * so + o4[cc].w * sn;
-                M = Mn;
-              }
-          }
-          const float inv = 1.0f / Ls;
-          *reinterpret_cast<uint2*>(p.attn + out_base + gq * D + d4 * 4) = pack_bf16x4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-        }
+      const float sent = __uint_as_float(kPkSentinel);
+      for (int c = 0; c < n_other; ++c) {
+        float* part = gbase + (long long)c * stride;
+        for (int q = lane; q < (G * D + 2 * G + 3) / 4; q += 32) *reinterpret_cast<float4*>(part + q * 4) = make_float4(sent, sent, sent, sent);
       }
     }
   }
