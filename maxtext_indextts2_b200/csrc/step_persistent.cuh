@@ -130,6 +130,7 @@ struct PkParams {
   EpiArgs logits;
   unsigned int* grid_bar;  // zeroed by prepare_rows_kernel
   long long* trace;        // debug: globaltimer at [barrier k][arrive|release][cta], or null
+  int variant;             // debug knob (MTX_PK_VARIANT)
 };
 
 // ---- small helpers -----------------------------------------------------------------------
@@ -243,6 +244,24 @@ __device__ __forceinline__ void pk_cursor_skip(PkCursor& c, int n) {
 }
 
 __device__ __forceinline__ float4 ldcg_f4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+// Polling loads of the flag-in-data exchanges: volatile, so the compiler can neither hoist them out of the spin
+// loop nor merge re-reads; .cg keeps them out of L1.
+// Pause between polling attempts without touching the memory pipeline (__nanosleep wakes microseconds late).
+__device__ __forceinline__ void pk_backoff() {
+  const long long t = clock64();
+  while (clock64() - t < 256) {
+  }
+}
+__device__ __forceinline__ float4 ld_poll_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 ld_poll_f2(const float* p) {
+  float2 v;
+  asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -840,13 +859,14 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
             for (int cc = 0; cc < 4; ++cc)
               if (c0 + cc < n_other) {
                 const float* part = gbase + (long long)(c0 + cc) * stride;
-                ml[cc] = __ldcg(reinterpret_cast<const float2*>(part + G * D + gq * 2));
-                o4[cc] = ldcg_f4(part + gq * D + d4 * 4);
+                ml[cc] = ld_poll_f2(part + G * D + gq * 2);
+                o4[cc] = ld_poll_f4(part + gq * D + d4 * 4);
                 ok = ok && __float_as_uint(ml[cc].x) != kPkSentinel && __float_as_uint(ml[cc].y) != kPkSentinel &&
                      __float_as_uint(o4[cc].x) != kPkSentinel && __float_as_uint(o4[cc].y) != kPkSentinel &&
                      __float_as_uint(o4[cc].z) != kPkSentinel && __float_as_uint(o4[cc].w) != kPkSentinel;
               }
             if (ok) break;
+            pk_backoff();
             if (clock64() - t_spin > 4000000000LL) {
               printf("mtx: attention merge timed out (block %d pair %d)\n", cta, pair);
               __trap();
@@ -873,6 +893,7 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
         if (d4 == 0) *reinterpret_cast<float2*>(gpart + G * D + gq * 2) = make_float2(M, Ls);
       }
     }
+    if (!complete && !merger) __threadfence();  // the part must leave the SM even if other warps here are polling
     if (merger) {
       // every lane has read its fragments: put the sentinel back for the next layer
       __syncwarp();
@@ -1123,6 +1144,9 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
         }
         tcgen05_fence_before();
         if (wtid == 0) pk_ev(ev, 100 * ph + 12);
+        // Polling loads issued back to back can starve the SM's own pending stores (then every CTA waits for
+        // everybody): the poll loops below pause between attempts so that the store queue always drains.
+        if (un.S > 1 && p.variant == 1) __threadfence();
         named_bar_sync(1, 128);
         if (wtid == 0) mbar_arrive(&tail->tmem_empty[buf]);
         if (un.S == 1) {
@@ -1143,54 +1167,58 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
         if (wtid == 0) pk_ev(ev, 100 * ph + 14);
         float* src0 = p.part_ws + (long long)(un.c_first * 4 + (un.tile & 3)) * kPkSlotFloats + lane * 4;
         const float4 sent4 = make_float4(__uint_as_float(kPkSentinel), __uint_as_float(kPkSentinel), __uint_as_float(kPkSentinel), __uint_as_float(kPkSentinel));
-        for (int r = r_begin + ew; r < r_end; r += 8) {
-          const int r2 = r + 4;
-          const bool two = r2 < r_end;
-          // side inputs of both rows travel with the partial tiles
-          const PkQkvSide sd_a = side_qkv(r, un.tile), sd_b = side_qkv(two ? r2 : r, un.tile);
-          const uint2 rv_a = side_res(r, un.tile), rv_b = side_res(two ? r2 : r, un.tile);
-          float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_b = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int s0 = 0; s0 < un.S; s0 += 8) {
-            float4 ta[8], tb[8];
+        // NR rows x NS parts = 16 fragments in flight per warp: the loop is bound by L2 round trips, not by bytes.
+        // MLP-up tiles are shared by two or three CTAs that each own many rows; the others by up to 16 CTAs.
+        constexpr int NR = ph == PK_UP ? 4 : 2, NS = ph == PK_UP ? 4 : 8;
+        for (int r = r_begin + ew; r < r_end; r += 4 * NR) {
+          // side inputs of the rows travel with the partial tiles
+          PkQkvSide sd[NR];
+          uint2 rv[NR];
+#pragma unroll
+          for (int k = 0; k < NR; ++k) {
+            const int rr = r + 4 * k < r_end ? r + 4 * k : r;
+            sd[k] = side_qkv(rr, un.tile);
+            rv[k] = side_res(rr, un.tile);
+          }
+          float4 acc[NR];
+#pragma unroll
+          for (int k = 0; k < NR; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int s0 = 0; s0 < un.S; s0 += NS) {
+            float4 t[NR][NS];
             const long long t_spin = clock64();
             for (;;) {
               bool ok = true;
 #pragma unroll
-              for (int ss = 0; ss < 8; ++ss) {
-                ta[ss] = tb[ss] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (s0 + ss < un.S) {
-                  float* ps = src0 + (long long)(s0 + ss) * 4 * kPkSlotFloats;
-                  ta[ss] = ldcg_f4(ps + r * 128);
-                  if (two) tb[ss] = ldcg_f4(ps + r2 * 128);
-                }
-              }
+              for (int k = 0; k < NR; ++k)
 #pragma unroll
-              for (int ss = 0; ss < 8; ++ss) {
-                const uint32_t bad = uint32_t(__float_as_uint(ta[ss].x) == kPkSentinel) | uint32_t(__float_as_uint(ta[ss].y) == kPkSentinel) |
-                                     uint32_t(__float_as_uint(ta[ss].z) == kPkSentinel) | uint32_t(__float_as_uint(ta[ss].w) == kPkSentinel) |
-                                     uint32_t(__float_as_uint(tb[ss].x) == kPkSentinel) | uint32_t(__float_as_uint(tb[ss].y) == kPkSentinel) |
-                                     uint32_t(__float_as_uint(tb[ss].z) == kPkSentinel) | uint32_t(__float_as_uint(tb[ss].w) == kPkSentinel);
-                ok = ok && bad == 0;
-              }
+                for (int ss = 0; ss < NS; ++ss) {
+                  t[k][ss] = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (r + 4 * k < r_end && s0 + ss < un.S) t[k][ss] = ld_poll_f4(src0 + (long long)(s0 + ss) * 4 * kPkSlotFloats + (r + 4 * k) * 128);
+                }
+#pragma unroll
+              for (int k = 0; k < NR; ++k)
+#pragma unroll
+                for (int ss = 0; ss < NS; ++ss)
+                  ok = ok && __float_as_uint(t[k][ss].x) != kPkSentinel && __float_as_uint(t[k][ss].y) != kPkSentinel &&
+                       __float_as_uint(t[k][ss].z) != kPkSentinel && __float_as_uint(t[k][ss].w) != kPkSentinel;
               if (__all_sync(0xffffffffu, ok)) break;
+              pk_backoff();  // the missing fragments are still in flight somewhere: let stores (ours too) drain
               if (clock64() - t_spin > 4000000000LL) {
                 printf("mtx: split-K exchange timed out (block %d phase %d tile %d row %d)\n", cta, ph, un.tile, r);
                 __trap();
               }
             }
 #pragma unroll
-            for (int ss = 0; ss < 8; ++ss) {
-              if (s0 + ss < un.S) {
-                float* ps = src0 + (long long)(s0 + ss) * 4 * kPkSlotFloats;
-                *reinterpret_cast<float4*>(ps + r * 128) = sent4;
-                if (two) *reinterpret_cast<float4*>(ps + r2 * 128) = sent4;
+            for (int k = 0; k < NR; ++k)
+#pragma unroll
+              for (int ss = 0; ss < NS; ++ss) {
+                if (r + 4 * k < r_end && s0 + ss < un.S) *reinterpret_cast<float4*>(src0 + (long long)(s0 + ss) * 4 * kPkSlotFloats + (r + 4 * k) * 128) = sent4;
+                acc[k].x += t[k][ss].x; acc[k].y += t[k][ss].y; acc[k].z += t[k][ss].z; acc[k].w += t[k][ss].w;
               }
-              acc_a.x += ta[ss].x; acc_a.y += ta[ss].y; acc_a.z += ta[ss].z; acc_a.w += ta[ss].w;
-              acc_b.x += tb[ss].x; acc_b.y += tb[ss].y; acc_b.z += tb[ss].z; acc_b.w += tb[ss].w;
-            }
           }
-          epilogue(acc_a, sd_a, rv_a, r, un.tile);
-          if (two) epilogue(acc_b, sd_b, rv_b, r2, un.tile);
+#pragma unroll
+          for (int k = 0; k < NR; ++k)
+            if (r + 4 * k < r_end) epilogue(acc[k], sd[k], rv[k], r + 4 * k, un.tile);
         }
       }
     };
@@ -1241,11 +1269,10 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
         step = p.logits.rng_state[0];
         seed = (uint64_t(p.logits.rng_state[2]) << 32) | p.logits.rng_state[1];
       }
-      ev.n = 0;
       for (int j = 0; j < logits_tiles; ++j) {
         const int tile = cta + j * n_ctas;
         const uint32_t buf = uc % kPkAccBufs;
-        ev.on = j >= 4 && j < 10;
+        ev.on = false;
         if (wtid == 0) pk_ev(ev, 410);
         mbar_wait(&tail->tmem_full[buf], (uc / kPkAccBufs) & 1);
         tcgen05_fence_after();
