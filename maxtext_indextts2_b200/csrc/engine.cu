@@ -413,6 +413,11 @@ bool pk_fill_phase(std::vector<PkTable>& tabs, int ph, int n, int k) {
     if (kbt <= 32 && uniform_s > 8) uniform_s = 8;
     if (uniform_s > kbt / 2) uniform_s = kbt / 2 > 0 ? kbt / 2 : 1;
   }
+  // Mid-sized matrices (at least half as many tiles as CTAs): one whole tile per CTA.  The CTA streams more bytes
+  // than with stream-K, but nothing is exchanged: the accumulator goes straight from TMEM through shared memory to
+  // the epilogue, and the exchange of a shared tile costs more (about 12 k-blocks' worth of streaming time) than
+  // the extra streaming.  CTAs without a tile run ahead into the next phase's weights.
+  if (uniform_s == 0 && n_tiles <= n_ctas && kbt <= total / n_ctas + env_int("MTX_PK_WHOLE_TILE_SLACK", 12)) uniform_s = 1;
   for (int c = 0; c < n_ctas; ++c) {
     PkTable& t = tabs[c];
     t.n_units[ph] = 0;
