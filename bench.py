@@ -31,7 +31,8 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
-KERNEL_CLASSES = ["prepare", "rmsnorm", "qkv_rope_append", "attention", "out_proj", "mlp_up", "mlp_down", "logits_sample", "finalize"]
+KERNEL_CLASSES = ["prepare", "rmsnorm", "qkv_rope_append", "attention", "out_proj", "mlp_up", "mlp_down", "logits_sample", "finalize", "persistent_step"]
+NCLS = len(KERNEL_CLASSES)
 
 
 def parse_args():
@@ -251,6 +252,55 @@ def workload_config(args, cfg):
 # ---------------------------------------------------------------------------------------------
 
 
+def ncu_traffic(kernel):
+  """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, or None."""
+  try:
+    table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    return table.get(kernel)
+  except (OSError, ValueError):
+    return None
+
+
+def persistent_phase_times(lib, engine, B, sptr, L):
+  """One traced step of the persistent kernel: microseconds per phase (mean over layers), measured from the
+  release of the previous grid barrier to the release of the phase's own barrier (all CTAs, %globaltimer)."""
+  from maxtext_indextts2_b200 import _lib
+
+  words = int(lib.mtx_step_trace_words())
+  tr = torch.zeros(words, dtype=torch.int64, device="cuda")
+  lib.mtx_debug_set_trace(ctypes.c_void_p(tr.data_ptr()))
+  try:
+    _lib.check(lib.mtx_decode_step(engine._handle, B, sptr))
+    torch.cuda.synchronize()
+  finally:
+    lib.mtx_debug_set_trace(None)
+  t = tr.cpu().numpy()
+  if t[0] == 0:
+    return None
+  g = int(np.argmax(t < t[0] - 100000))  # row 0 = end stamps (largest), row 1 = start stamps (smallest)
+  if g <= 0:
+    return None
+  a = t[: 400 * g].reshape(-1, g)
+  start, end = a[1], a[0]
+  rel = [start.max()]
+  nb = 2 + 5 * L
+  for k in range(1, nb + 1):
+    if a[2 * k + 1].min() <= 0:
+      return None
+    rel.append(a[2 * k + 1].max())
+  rel = np.array(rel, dtype=np.float64) / 1e3
+  names = ["qkv_rope_append", "attention", "out_proj", "mlp_up", "mlp_down"]
+  out = {"ctas": g, "embed_gather": round(float(rel[1] - rel[0]), 2)}
+  for j, nm in enumerate(names):
+    d = [rel[2 + 5 * l + j] - rel[1 + 5 * l + j] for l in range(L)]
+    out[nm + "_per_layer"] = round(float(np.mean(d)), 2)
+  out["final_norm"] = round(float(rel[nb] - rel[nb - 1]), 2)
+  out["logits_sample"] = round(float(end.max() / 1e3 - rel[nb]), 2)
+  out["kernel_total"] = round(float(end.max() / 1e3 - start.min() / 1e3), 2)
+  out["unit"] = "us"
+  return out
+
+
 def main():
   args = parse_args()
   if args.impl == "reference":
@@ -339,15 +389,16 @@ def main():
   clocks = sampler.stop()
 
   # ---- per-kernel-class device times of one eager step (CUDA events on the launching stream) ----
-  class_ms = (ctypes.c_float * 9)()
-  class_n = (ctypes.c_int32 * 9)()
-  acc = np.zeros(9)
+  class_ms = (ctypes.c_float * NCLS)()
+  class_n = (ctypes.c_int32 * NCLS)()
+  acc = np.zeros(NCLS)
   prof_steps = 3
   for _ in range(prof_steps):
     _lib.check(lib.mtx_profile_decode_step(engine._handle, B, sptr, class_ms, class_n))
     acc += np.array(list(class_ms))
   acc /= prof_steps
   counts = list(class_n)
+  phases = persistent_phase_times(lib, engine, B, sptr, cfg.num_decoder_layers) if counts[NCLS - 1] > 0 else None
 
   times = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device="cuda")
   if world > 1:
@@ -373,6 +424,7 @@ def main():
     L = cfg.num_decoder_layers
     E, Hq, Hkv, D, M, V = cfg.emb_dim, cfg.num_query_heads, cfg.num_kv_heads, cfg.head_dim, cfg.mlp_dim, cfg.vocab_size
     per_launch_bytes = {
+        "persistent_step": step_bytes,
         "attention": ab["attention_per_layer"] + B * Hq * D * 2 * 2,
         "logits_sample": 2 * E * V + B * E * 2,
         "mlp_up": 2 * 2 * M * E + B * E * 2 + B * M * 2,
@@ -391,13 +443,14 @@ def main():
         "peak": hbm_peak,
         "unit": "GB/s",
         "frac": achieved / hbm_peak,
-        "traffic": None,
+        "traffic": ncu_traffic(name),
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": per_launch_bytes.get(name, 0),
         "launch_ms": dur_ms,
         "whole_step": {"algorithmic_bytes": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / hbm_peak},
-        "class_ms_per_step": {KERNEL_CLASSES[i]: round(float(acc[i]), 4) for i in range(9)},
-        "class_launches_per_step": {KERNEL_CLASSES[i]: counts[i] for i in range(9)},
+        "class_ms_per_step": {KERNEL_CLASSES[i]: round(float(acc[i]), 4) for i in range(NCLS)},
+        "class_launches_per_step": {KERNEL_CLASSES[i]: counts[i] for i in range(NCLS)},
+        "persistent_step_phases": phases,
         "class_gbs": {k: round(per_launch_bytes[k] * counts[KERNEL_CLASSES.index(k)] / (acc[KERNEL_CLASSES.index(k)] * 1e-3) / 1e9, 1)
                       for k in per_launch_bytes if acc[KERNEL_CLASSES.index(k)] > 0},
     }

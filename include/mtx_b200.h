@@ -148,9 +148,11 @@ int mtx_decode_step_candidates(mtx_engine* e, int rows, float* candidates, mtx_s
 int mtx_commit_candidates(mtx_engine* e, int rows, const float* gathered, int n_shards, mtx_stream stream);
 
 /* Measurement aid: one eager decode step with a CUDA-event pair around every kernel launch
- * (on `stream`), summed per kernel class into class_ms[9] / class_launches[9] (host arrays):
+ * (on `stream`), summed per kernel class into class_ms[10] / class_launches[10] (host arrays):
  * 0 prepare, 1 rmsnorm, 2 qkv+rope+append, 3 attention, 4 out-proj, 5 mlp up, 6 mlp down,
- * 7 logits+sampling, 8 finalize.  Synchronises the stream; the step really advances the state. */
+ * 7 logits+sampling, 8 finalize, 9 the persistent step kernel (all layers + logits in one launch; used
+ * for up to 64 rows, then classes 1-7 stay empty).  Synchronises the stream; the step really advances
+ * the state. */
 int mtx_profile_decode_step(mtx_engine* e, int rows, mtx_stream stream, float* class_ms, int32_t* class_launches);
 
 /* `count` consecutive prompt positions [start_pos, start_pos+count) of one sequence into the
@@ -186,6 +188,11 @@ int mtx_decode_attention(const void* q, const void* k_cache, const void* v_cache
                          float softcap, void* scratch, mtx_stream stream);
 
 /* ---- misc ---------------------------------------------------------------------------------- */
+
+/* Measurement aid: grid-barrier timeline of the persistent step kernel.  While a device buffer of
+ * mtx_step_trace_words() 64-bit words is installed with mtx_debug_set_trace, every CTA records
+ * %globaltimer at the arrival at and the release from each grid barrier (see tools/mega_trace.py). */
+size_t mtx_step_trace_words(void);
 
 const char* mtx_last_error(void);
 /* "sm_100a" build tag, so a caller can check what it loaded. */

@@ -140,6 +140,8 @@ def _declare(lib) -> None:
   lib.mtx_commit_candidates.argtypes = [vp, i32, vp, i32, vp]
   lib.mtx_debug_set_trace.restype = None
   lib.mtx_debug_set_trace.argtypes = [vp]
+  lib.mtx_step_trace_words.restype = sz
+  lib.mtx_step_trace_words.argtypes = []
   lib.mtx_debug_set_timeline.restype = i32
   lib.mtx_debug_set_timeline.argtypes = [vp]
   lib.mtx_profile_decode_step.restype = i32

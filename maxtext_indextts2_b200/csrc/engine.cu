@@ -93,7 +93,7 @@ int make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, u
 
 // Optional per-kernel timing: when a sink is installed every launch is bracketed by CUDA
 // events on the launching stream and attributed to the current kernel class.
-enum KernelClass { KC_PREPARE = 0, KC_RMSNORM, KC_QKV, KC_ATTENTION, KC_OUTPROJ, KC_MLP_UP, KC_MLP_DOWN, KC_LOGITS, KC_FINALIZE, KC_COUNT };
+enum KernelClass { KC_PREPARE = 0, KC_RMSNORM, KC_QKV, KC_ATTENTION, KC_OUTPROJ, KC_MLP_UP, KC_MLP_DOWN, KC_LOGITS, KC_FINALIZE, KC_PERSISTENT, KC_COUNT };
 struct ProfileSink {
   struct Rec { int cls; cudaEvent_t a, b; };
   std::vector<Rec> recs;
@@ -676,7 +676,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     gp.k = E;
     g_class = KC_LOGITS;
     if (mega) {
-      g_class = KC_QKV;
+      g_class = KC_PERSISTENT;
       MTX_TRY(launch_persistent(e, rows, *xm, ea, st));
     } else {
       MTX_TRY(launch_gemm<EPI_LOGITS>(e->tm_logits, xm->n, gp, ea, plan_logits, st));
@@ -748,6 +748,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
 extern "C" {
 
 const char* mtx_last_error(void) { return g_error.c_str(); }
+size_t mtx_step_trace_words(void) { return size_t(2) * 200 * 148 + size_t(148) * 3 * 64; }
 void mtx_debug_set_trace(void* device_buffer) { g_trace = static_cast<long long*>(device_buffer); }
 int mtx_debug_set_timeline(void* device_buffer) {
   unsigned long long* p = static_cast<unsigned long long*>(device_buffer);
