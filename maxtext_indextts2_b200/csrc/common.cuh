@@ -103,16 +103,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
-// Waits for the phase with the given parity.  A wait that lasts ~2 s is a protocol bug
-// (wrong tx byte count, missing arrive): trap instead of hanging the GPU.
+// A wait that lasts ~2 s is a protocol bug (wrong tx byte count, missing arrive): report and trap instead of
+// hanging the GPU.  Out of line: the persistent kernel has dozens of wait sites and lives off its instruction cache.
+__device__ __noinline__ void mtx_wait_timeout(int what, int a, int b) {
+  printf("mtx: wait %d timed out (block %d,%d,%d thread %d: %d %d)\n", what, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, a, b);
+  __trap();
+}
+
+// Waits for the phase with the given parity.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("mtx: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) mtx_wait_timeout(0, int(parity), 0);
   }
 }
 
@@ -248,7 +251,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 
 // Gumbel(0,1) noise for (row, vocab id) at a given step: word (v & 3) of
 // philox(counter = (v >> 2, row, step, 0), key = seed).
-__device__ __forceinline__ float gumbel_noise(uint64_t seed, uint32_t step, uint32_t row, uint32_t v) {
+__device__ __noinline__ float gumbel_noise(uint64_t seed, uint32_t step, uint32_t row, uint32_t v) {
   const uint4 w = philox4x32_10(make_uint4(v >> 2, row, step, 0u), make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
   const uint32_t sel = v & 3u;
   const uint32_t x = sel == 0 ? w.x : sel == 1 ? w.y : sel == 2 ? w.z : w.w;

@@ -149,11 +149,16 @@ __device__ __forceinline__ PkEv pk_ev_make(const PkParams& p, int role) {
   return e;
 }
 __device__ __forceinline__ void pk_ev(PkEv& e, int id) {
+#ifdef MTX_PK_EVENTS  // per-role event log (tools/mega_trace.py); compiled out by default to keep the kernel small
   if (e.base != nullptr && e.on && e.n < 32) {
     e.base[2 * e.n] = id;
     e.base[2 * e.n + 1] = (long long)globaltimer_ns();
     ++e.n;
   }
+#else
+  (void)e;
+  (void)id;
+#endif
 }
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
@@ -179,10 +184,7 @@ __device__ __forceinline__ void pk_wait_flag(volatile uint32_t* flag, uint32_t w
   if (*flag >= want) return;
   const long long t0 = clock64();
   while (*flag < want) {  // plain spin: __nanosleep wakes microseconds late, and every waiter is on a critical path
-    if (clock64() - t0 > 4000000000LL) {
-      printf("mtx: phase flag wait timed out (block %d thread %d want %u have %u)\n", blockIdx.x, threadIdx.x, want, *flag);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) mtx_wait_timeout(1, int(want), int(*flag));
   }
 }
 
@@ -198,10 +200,7 @@ __device__ __forceinline__ void pk_grid_barrier(const PkParams& p, PkTail* tail,
   const uint32_t target = k * gridDim.x;
   const long long t0 = clock64();
   while (ld_acquire_gpu(p.grid_bar) < target) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("mtx: grid barrier %u timed out (block %d)\n", k, blockIdx.x);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) mtx_wait_timeout(2, int(k), 0);
   }
   if (p.trace) p.trace[(2 * k + 1) * gridDim.x + blockIdx.x] = (long long)globaltimer_ns();
   tail->bar_done = k;
@@ -620,9 +619,7 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
     float s[4][4];
 #pragma unroll
     for (int mb = 0; mb < 4; ++mb) s[mb][0] = s[mb][1] = s[mb][2] = s[mb][3] = 0.0f;
-    if (lane == 0) pk_ev(ev, 600);
     mbar_wait(bar_k, phase);
-    if (lane == 0) pk_ev(ev, 601);
 #pragma unroll
     for (int mb = 0; mb < 4; ++mb) {
 #pragma unroll
@@ -635,7 +632,6 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
       }
     }
     // K tile consumed: refill it with the next tile's keys while the softmax and P V run
-    if (lane == 0) pk_ev(ev, 602);
     fence_proxy_async();
     __syncwarp();
     if (more && lane == 0) {
@@ -694,9 +690,7 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
       o[db][3] *= a1;
     }
     // ---- O^T += V^T P^T ----
-    if (lane == 0) pk_ev(ev, 603);
     mbar_wait(bar_v, phase);
-    if (lane == 0) pk_ev(ev, 604);
     if (cnt < 64) {  // rows past the valid count may hold anything: zero them (0 * NaN != 0)
       const int nvec = (64 - cnt) * 8;
       for (int q = lane; q < nvec; q += 32) *reinterpret_cast<uint4*>(v_tile + (cnt + q / 8) * 128 + (q & 7) * 16) = make_uint4(0, 0, 0, 0);
@@ -720,7 +714,6 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
       tma_load_2d(v_tile, &tm_v, 0, next_row, bar_v, kEvictFirst);
     }
     phase ^= 1;
-    if (lane == 0) pk_ev(ev, 605);
 
     if (meta & PKA_SEG_END) {
 #pragma unroll
@@ -772,7 +765,9 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
   }
 
   // ---- phase 2: merge the partial segments of this CTA ----
+  if (lane == 0) pk_ev(ev, 610);
   named_bar_sync(3, kPkAttnWarps * 32);
+  if (lane == 0) pk_ev(ev, 611);
   const long long nc = p.attn_info[0], total = p.attn_info[1];
   for (int k = 0; k < 2; ++k) {
     const int4 me = tail->a_seg[aw][k];
@@ -835,6 +830,7 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
       n_other = pk_cta_of(g_first + nt - 1, nc, total) - c_first;  // parts held by other CTAs
       my_part = cta - c_first - 1;                                  // -1 for the merger
     }
+    if (lane == 0) pk_ev(ev, 620 + k * 100 + (complete ? 1 : 0) + (merger ? 2 : 0) + 10 * n_src + 1000 * n_other);
     for (int unit = lane; unit < G * (D / 4); unit += 32) {
       const int gq = unit / (D / 4), d4 = unit - gq * (D / 4);
       float M = -INFINITY;
@@ -867,10 +863,7 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
               }
             if (ok) break;
             pk_backoff();
-            if (clock64() - t_spin > 4000000000LL) {
-              printf("mtx: attention merge timed out (block %d pair %d)\n", cta, pair);
-              __trap();
-            }
+            if (clock64() - t_spin > 4000000000LL) mtx_wait_timeout(4, pair, 0);
           }
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc)
@@ -893,7 +886,7 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
         if (d4 == 0) *reinterpret_cast<float2*>(gpart + G * D + gq * 2) = make_float2(M, Ls);
       }
     }
-    if (!complete && !merger) __threadfence();  // the part must leave the SM even if other warps here are polling
+    if (lane == 0) pk_ev(ev, 690 + k);
     if (merger) {
       // every lane has read its fragments: put the sentinel back for the next layer
       __syncwarp();
@@ -1090,7 +1083,7 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
     // One GEMM phase of this CTA: dump every accumulator (partial tile to the exchange workspace, or straight to
     // the epilogue when the CTA owns the whole reduction), then finish the row slices it owns.
     auto gemm_phase = [&](auto ph_tag, int layer) {
-      constexpr int ph = decltype(ph_tag)::value;
+      constexpr int ph = decltype(ph_tag)::value;  // specialised per phase: measurably faster than one generic body
       const int nu = tab.n_units[ph];
       const int N = ph == PK_QKV ? p.qkv_n : ph == PK_UP ? 2 * p.M : p.E;
       bf16* k_layer = p.k_cache + p.kv_layer_elems * layer;
@@ -1098,33 +1091,34 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
       const bf16* resid = ph == PK_OPROJ ? p.x : p.h;
       bf16* res_out = ph == PK_OPROJ ? p.h : p.x;
       float* ss_out = ph == PK_OPROJ ? p.ss_h : p.ss_x;
-      // side inputs of a row fragment are requested before the accumulator is final (see the reduce loop)
-      auto epilogue = [&](const float4 a, const PkQkvSide& sd, const uint2 rv, int r, int tile) {
-        if (ph == PK_QKV) pk_epi_qkv(a, sd, r, tile, lane, p, k_layer, v_layer);
-        if (ph == PK_OPROJ || ph == PK_DOWN) pk_epi_residual(a, rv, r, tile, lane, N, res_out, ss_out, ss_tiles);
-        if (ph == PK_UP) pk_epi_swiglu(a, r, tile, lane, N, p.M, p.act);
+      // Side inputs of a row fragment do not depend on the accumulator: they are requested before the fragment's
+      // partial tiles are polled, so the epilogue itself never waits on memory.
+      struct Side {
+        PkQkvSide q;
+        uint2 rv;
       };
-      auto side_qkv = [&](int r, int tile) {
-        PkQkvSide sd;
-        sd.c01 = sd.c23 = make_float4(0.f, 0.f, 0.f, 0.f);
-        sd.plane = sd.wr = 0;
-        if (ph == PK_QKV) sd = pk_qkv_side(p, r, tile, lane);
+      auto side = [&](int r, int tile) {
+        Side sd;
+        sd.q.c01 = sd.q.c23 = make_float4(0.f, 0.f, 0.f, 0.f);
+        sd.q.plane = sd.q.wr = 0;
+        sd.rv = make_uint2(0u, 0u);
+        const int n0 = tile * 128 + lane * 4;
+        if (ph == PK_QKV) sd.q = pk_qkv_side(p, r, tile, lane);
+        else if (ph != PK_UP && n0 < N) sd.rv = __ldcg(reinterpret_cast<const uint2*>(resid + (long long)r * N + n0));
         return sd;
       };
-      auto side_res = [&](int r, int tile) {
-        uint2 rv = make_uint2(0u, 0u);
-        const int n0 = tile * 128 + lane * 4;
-        if ((ph == PK_OPROJ || ph == PK_DOWN) && n0 < N) rv = __ldcg(reinterpret_cast<const uint2*>(resid + (long long)r * N + n0));
-        return rv;
+      auto epilogue = [&](const float4 a, const Side& sd, int r, int tile) {
+        if (ph == PK_QKV) pk_epi_qkv(a, sd.q, r, tile, lane, p, k_layer, v_layer);
+        else if (ph == PK_UP) pk_epi_swiglu(a, r, tile, lane, N, p.M, p.act);
+        else pk_epi_residual(a, sd.rv, r, tile, lane, N, res_out, ss_out, ss_tiles);
       };
       for (int u = 0; u < nu; ++u) {
         const PkUnit un = tab.u[ph][u];
         const uint32_t buf = uc % kPkAccBufs;
-        if (wtid == 0) pk_ev(ev, 100 * ph + 10);
         mbar_wait(&tail->tmem_full[buf], (uc / kPkAccBufs) & 1);
         tcgen05_fence_after();
-        if (wtid == 0) pk_ev(ev, 100 * ph + 11);
         const uint32_t taddr = tmem_base + tlane + buf * uint32_t(p.r_tile);
+        // exchange slot in global memory, or the park buffer in shared memory for a tile this CTA owns alone
         if (un.S == 1) {
           for (int c = 0; c * 16 < p.rows; ++c) {
             float v[16];
@@ -1143,15 +1137,12 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
           }
         }
         tcgen05_fence_before();
-        if (wtid == 0) pk_ev(ev, 100 * ph + 12);
         // Polling loads issued back to back can starve the SM's own pending stores (then every CTA waits for
-        // everybody): the poll loops below pause between attempts so that the store queue always drains.
-        if (un.S > 1 && p.variant == 1) __threadfence();
+        // everybody): the poll loop below pauses between attempts so that the store queue always drains.
         named_bar_sync(1, 128);
         if (wtid == 0) mbar_arrive(&tail->tmem_empty[buf]);
         if (un.S == 1) {
-          for (int r = ew; r < p.rows; r += 4)
-            epilogue(*reinterpret_cast<const float4*>(park + r * 128 + lane * 4), side_qkv(r, un.tile), side_res(r, un.tile), r, un.tile);
+          for (int r = ew; r < p.rows; r += 4) epilogue(*reinterpret_cast<const float4*>(park + r * 128 + lane * 4), side(r, un.tile), r, un.tile);
           named_bar_sync(1, 128);  // the park buffer is rewritten by the next unit
         }
         ++uc;
@@ -1164,76 +1155,66 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
         if (un.S == 1) continue;
         const int si = cta - un.c_first;
         const int r_begin = si * p.rows / un.S, r_end = (si + 1) * p.rows / un.S;
-        if (wtid == 0) pk_ev(ev, 100 * ph + 14);
         float* src0 = p.part_ws + (long long)(un.c_first * 4 + (un.tile & 3)) * kPkSlotFloats + lane * 4;
-        const float4 sent4 = make_float4(__uint_as_float(kPkSentinel), __uint_as_float(kPkSentinel), __uint_as_float(kPkSentinel), __uint_as_float(kPkSentinel));
-        // NR rows x NS parts = 16 fragments in flight per warp: the loop is bound by L2 round trips, not by bytes.
-        // MLP-up tiles are shared by two or three CTAs that each own many rows; the others by up to 16 CTAs.
-        constexpr int NR = ph == PK_UP ? 4 : 2, NS = ph == PK_UP ? 4 : 8;
-        for (int r = r_begin + ew; r < r_end; r += 4 * NR) {
-          // side inputs of the rows travel with the partial tiles
-          PkQkvSide sd[NR];
-          uint2 rv[NR];
-#pragma unroll
-          for (int k = 0; k < NR; ++k) {
-            const int rr = r + 4 * k < r_end ? r + 4 * k : r;
-            sd[k] = side_qkv(rr, un.tile);
-            rv[k] = side_res(rr, un.tile);
-          }
-          float4 acc[NR];
-#pragma unroll
-          for (int k = 0; k < NR; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int s0 = 0; s0 < un.S; s0 += NS) {
-            float4 t[NR][NS];
+        const float sent = __uint_as_float(kPkSentinel);
+        // two rows x eight parts = 16 fragments in flight per warp: the loop is bound by L2 round trips
+        for (int r = r_begin + ew; r < r_end; r += 8) {
+          const int r2 = r + 4;
+          const bool two = r2 < r_end;
+          const Side sd_a = side(r, un.tile), sd_b = side(two ? r2 : r, un.tile);
+          float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_b = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int s0 = 0; s0 < un.S; s0 += 8) {
+            float4 ta[8], tb[8];
             const long long t_spin = clock64();
             for (;;) {
               bool ok = true;
 #pragma unroll
-              for (int k = 0; k < NR; ++k)
-#pragma unroll
-                for (int ss = 0; ss < NS; ++ss) {
-                  t[k][ss] = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (r + 4 * k < r_end && s0 + ss < un.S) t[k][ss] = ld_poll_f4(src0 + (long long)(s0 + ss) * 4 * kPkSlotFloats + (r + 4 * k) * 128);
+              for (int ss = 0; ss < 8; ++ss) {
+                ta[ss] = tb[ss] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (s0 + ss < un.S) {
+                  const float* ps = src0 + (long long)(s0 + ss) * 4 * kPkSlotFloats;
+                  ta[ss] = ld_poll_f4(ps + r * 128);
+                  if (two) tb[ss] = ld_poll_f4(ps + r2 * 128);
                 }
+              }
 #pragma unroll
-              for (int k = 0; k < NR; ++k)
-#pragma unroll
-                for (int ss = 0; ss < NS; ++ss)
-                  ok = ok && __float_as_uint(t[k][ss].x) != kPkSentinel && __float_as_uint(t[k][ss].y) != kPkSentinel &&
-                       __float_as_uint(t[k][ss].z) != kPkSentinel && __float_as_uint(t[k][ss].w) != kPkSentinel;
+              for (int ss = 0; ss < 8; ++ss)
+                ok = ok && __float_as_uint(ta[ss].x) != kPkSentinel && __float_as_uint(ta[ss].y) != kPkSentinel &&
+                     __float_as_uint(ta[ss].z) != kPkSentinel && __float_as_uint(ta[ss].w) != kPkSentinel &&
+                     __float_as_uint(tb[ss].x) != kPkSentinel && __float_as_uint(tb[ss].y) != kPkSentinel &&
+                     __float_as_uint(tb[ss].z) != kPkSentinel && __float_as_uint(tb[ss].w) != kPkSentinel;
               if (__all_sync(0xffffffffu, ok)) break;
               pk_backoff();  // the missing fragments are still in flight somewhere: let stores (ours too) drain
-              if (clock64() - t_spin > 4000000000LL) {
-                printf("mtx: split-K exchange timed out (block %d phase %d tile %d row %d)\n", cta, ph, un.tile, r);
-                __trap();
-              }
+              if (clock64() - t_spin > 4000000000LL) mtx_wait_timeout(3, ph, un.tile);
             }
 #pragma unroll
-            for (int k = 0; k < NR; ++k)
-#pragma unroll
-              for (int ss = 0; ss < NS; ++ss) {
-                if (r + 4 * k < r_end && s0 + ss < un.S) *reinterpret_cast<float4*>(src0 + (long long)(s0 + ss) * 4 * kPkSlotFloats + (r + 4 * k) * 128) = sent4;
-                acc[k].x += t[k][ss].x; acc[k].y += t[k][ss].y; acc[k].z += t[k][ss].z; acc[k].w += t[k][ss].w;
+            for (int ss = 0; ss < 8; ++ss) {
+              if (s0 + ss < un.S) {
+                float* ps = src0 + (long long)(s0 + ss) * 4 * kPkSlotFloats;
+                *reinterpret_cast<float4*>(ps + r * 128) = make_float4(sent, sent, sent, sent);
+                if (two) *reinterpret_cast<float4*>(ps + r2 * 128) = make_float4(sent, sent, sent, sent);
               }
+              acc_a.x += ta[ss].x; acc_a.y += ta[ss].y; acc_a.z += ta[ss].z; acc_a.w += ta[ss].w;
+              acc_b.x += tb[ss].x; acc_b.y += tb[ss].y; acc_b.z += tb[ss].z; acc_b.w += tb[ss].w;
+            }
           }
-#pragma unroll
-          for (int k = 0; k < NR; ++k)
-            if (r + 4 * k < r_end) epilogue(acc[k], sd[k], rv[k], r + 4 * k, un.tile);
+          epilogue(acc_a, sd_a, r, un.tile);
+          if (two) epilogue(acc_b, sd_b, r2, un.tile);
         }
       }
     };
 
     for (int l = 0; l < p.L; ++l) {
       ev.on = l == 1;
-      gemm_phase(std::integral_constant<int, PK_QKV>{}, l);
-      phase_end(false);
-      ++nbar;  // the attention phase's barrier is run by the attention warps
-      gemm_phase(std::integral_constant<int, PK_OPROJ>{}, l);
-      phase_end(false);
-      gemm_phase(std::integral_constant<int, PK_UP>{}, l);
-      phase_end(false);
-      gemm_phase(std::integral_constant<int, PK_DOWN>{}, l);
-      phase_end(l == p.L - 1);
+#pragma unroll 1  // one copy of the phase body
+      for (int ph = 0; ph < 4; ++ph) {
+        if (ph == PK_QKV) gemm_phase(std::integral_constant<int, PK_QKV>{}, l);
+        else if (ph == PK_OPROJ) gemm_phase(std::integral_constant<int, PK_OPROJ>{}, l);
+        else if (ph == PK_UP) gemm_phase(std::integral_constant<int, PK_UP>{}, l);
+        else gemm_phase(std::integral_constant<int, PK_DOWN>{}, l);
+        phase_end(l == p.L - 1 && ph == PK_DOWN);
+        if (ph == PK_QKV) ++nbar;  // the attention phase's barrier is run by the attention warps
+      }
     }
 
     // ---- final RMSNorm (decoders.py:537-589) into the activation buffer the logits GEMM streams ----
@@ -1303,10 +1284,10 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
     const bool xformer = aw < 4;         // warps 6-9 normalise activation tiles during the QKV and MLP-up phases
     const bool xproducer = aw == 4;      // warp 10 requests the activation tiles of every GEMM phase
     uint32_t kv_phase = 0;
-    PkEv ev = pk_ev_make(p, 1);
-    if (aw != 0) ev.base = nullptr;
+    PkEv ev = pk_ev_make(p, aw == 5 ? 2 : 1);  // debug: first and last attention warp
+    if (aw != 0 && aw != 5) ev.base = nullptr;
     PkEv evx = pk_ev_make(p, 2);
-    if (!(xproducer && lane == 0)) evx.base = nullptr;
+    evx.base = nullptr;
 
     // ---- once per step: stage the row descriptors, cut this warp's share of the attention tiles ----
     griddep_wait();
@@ -1322,11 +1303,11 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
     pk_attn_build_list(p, tail, cta, aw, lane);
     __syncwarp();
     // The first K/V tiles of a layer may be requested before the QKV phase has finished unless the tile holds
-    // the row that phase appends, or the tile buffers double as the epilogue's park buffer (single-CTA tiles).
+    // the row that phase appends, or the QKV epilogue of this CTA parks a whole tile in the same shared memory
+    // (single-CTA tiles; the other phases' parked tiles are long consumed when the next layer's QKV phase starts).
     bool may_prime = tail->a_count[aw] > 0 && (tail->a_list[aw][0].y & PKA_PAIR_LAST) == 0;
-    for (int ph = 0; ph < 4; ++ph)
-      for (int u = 0; u < tab.n_units[ph]; ++u)
-        if (tab.u[ph][u].S == 1) may_prime = false;
+    for (int u = 0; u < tab.n_units[PK_QKV]; ++u)
+      if (tab.u[PK_QKV][u].S == 1) may_prime = false;
 
     PkCursor cur;  // shared fill sequence (activation producer and normaliser walk it in step with the weights)
     pk_cursor_init(cur);
@@ -1457,27 +1438,28 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
 
     for (int l = 0; l < p.L; ++l) {
       ev.on = l == 1;
-      gemm_duty(PK_QKV, l);
-      __syncwarp();
-      // ---- attention over the valid rows of both cache segments ----
-      if (may_prime && lane == 0) {
-        const int row0 = l * p.num_slots * p.hkv * p.T + tail->a_list[aw][0].x;
-        uint8_t* kt = attn_tiles + aw * 2 * 8192;
-        mbar_expect_tx(&tail->attn_bars[2 * aw], 8192);
-        tma_load_2d(kt, &tm_k, 0, row0, &tail->attn_bars[2 * aw], kEvictFirst);
-        mbar_expect_tx(&tail->attn_bars[2 * aw + 1], 8192);
-        tma_load_2d(kt + 8192, &tm_v, 0, row0, &tail->attn_bars[2 * aw + 1], kEvictFirst);
+#pragma unroll 1  // one copy of the duty code
+      for (int ph = 0; ph < 4; ++ph) {
+        gemm_duty(ph, l);
+        if (ph != PK_QKV) continue;
+        __syncwarp();
+        // ---- attention over the valid rows of both cache segments ----
+        if (may_prime && lane == 0) {
+          const int row0 = l * p.num_slots * p.hkv * p.T + tail->a_list[aw][0].x;
+          uint8_t* kt = attn_tiles + aw * 2 * 8192;
+          mbar_expect_tx(&tail->attn_bars[2 * aw], 8192);
+          tma_load_2d(kt, &tm_k, 0, row0, &tail->attn_bars[2 * aw], kEvictFirst);
+          mbar_expect_tx(&tail->attn_bars[2 * aw + 1], 8192);
+          tma_load_2d(kt + 8192, &tm_v, 0, row0, &tail->attn_bars[2 * aw + 1], kEvictFirst);
+        }
+        pk_wait_flag(&tail->bar_done, uint32_t(2 + 5 * l));
+        if (lane == 0) pk_ev(ev, 500);
+        pk_attention_cta(tm_k, tm_v, p, tail, l, attn_tiles, kv_phase, cta, aw, lane, may_prime, ev);
+        if (lane == 0) pk_ev(ev, 501);
+        fence_proxy_async_all();
+        named_bar_sync(3, kPkAttnWarps * 32);
+        if (atid == 0) pk_grid_barrier(p, tail, uint32_t(3 + 5 * l));
       }
-      pk_wait_flag(&tail->bar_done, uint32_t(2 + 5 * l));
-      if (atid == 0) pk_ev(ev, 500);
-      pk_attention_cta(tm_k, tm_v, p, tail, l, attn_tiles, kv_phase, cta, aw, lane, may_prime, ev);
-      if (atid == 0) pk_ev(ev, 501);
-      fence_proxy_async_all();
-      named_bar_sync(3, kPkAttnWarps * 32);
-      if (atid == 0) pk_grid_barrier(p, tail, uint32_t(3 + 5 * l));
-      gemm_duty(PK_OPROJ, l);
-      gemm_duty(PK_UP, l);
-      gemm_duty(PK_DOWN, l);
       __syncwarp();
     }
     if (xproducer && lane == 0) x_phase(PK_LOGITS, p.L);
