@@ -45,6 +45,8 @@ def parse_args():
   ap.add_argument("--model", default="indextts2-t2s")
   ap.add_argument("--context-min", type=int, default=512)
   ap.add_argument("--context-max", type=int, default=1536)
+  ap.add_argument("--prefill-len", type=int, default=0, help="override max_prefill_predict_length (BASELINE configs[3]: 4096)")
+  ap.add_argument("--target-len", type=int, default=0, help="override max_target_length (BASELINE configs[3]: 5632)")
   ap.add_argument("--no-graph", action="store_true")
   ap.add_argument("--skip-cpu-baseline", action="store_true")
   ap.add_argument("--cpu-slots", type=int, default=8, help="slots in the CPU baseline sample")
@@ -55,7 +57,12 @@ def parse_args():
 def make_config(args):
   from maxtext_indextts2_b200 import pyconfig
 
-  return pyconfig.initialize(None, model_name=args.model, per_device_batch_size=args.batch)
+  kw = {}
+  if args.prefill_len:
+    kw["max_prefill_predict_length"] = args.prefill_len
+  if args.target_len:
+    kw["max_target_length"] = args.target_len
+  return pyconfig.initialize(None, model_name=args.model, per_device_batch_size=args.batch, **kw)
 
 
 def context_lengths(args, cfg, rank=0):

@@ -319,7 +319,7 @@ WsLayout layout_workspace(const mtx_engine* e) {
     const size_t pk_rows = c.max_rows < kPkMaxRTile ? c.max_rows : kPkMaxRTile;
     const size_t pairs = pk_rows * c.num_kv_heads;
     const size_t ss_tiles = (c.emb_dim + 127) / 128;
-    L.pk_tables = take(size_t(e->num_sms) * sizeof(PkTable));
+    L.pk_tables = take(size_t(2) * e->num_sms * sizeof(PkTable));  // [0] many rows, [1] few rows
     L.pk_part_ws = take(size_t(e->num_sms) * 4 * kPkSlotFloats * 4);
     L.pk_tile_cnt = take(size_t(4) * pk_tile_cnt_stride(c) * 4);
     L.pk_ss_x = take(size_t(kPkMaxRTile) * ss_tiles * 4);
@@ -391,7 +391,7 @@ __global__ void fill_u32_kernel(uint32_t* dst, size_t n, uint32_t value) {
 
 // Deals the (weight tile, k-block) units of one GEMM phase to the CTAs in contiguous equal ranges (stream-K).
 // A CTA gets at least `q_min` k-blocks so that no tile is shared by more than kPkMaxSplit CTAs.
-bool pk_fill_phase(std::vector<PkTable>& tabs, int ph, int n, int k) {
+bool pk_fill_phase(std::vector<PkTable>& tabs, int ph, int n, int k, bool allow_whole_tile) {
   const int n_ctas = int(tabs.size());
   const int n_tiles = (n + kTileN - 1) / kTileN, kbt = k / kBlockK;
   const long long total = (long long)n_tiles * kbt;
@@ -416,8 +416,9 @@ bool pk_fill_phase(std::vector<PkTable>& tabs, int ph, int n, int k) {
   // Mid-sized matrices (at least half as many tiles as CTAs): one whole tile per CTA.  The CTA streams more bytes
   // than with stream-K, but nothing is exchanged: the accumulator goes straight from TMEM through shared memory to
   // the epilogue, and the exchange of a shared tile costs more (about 12 k-blocks' worth of streaming time) than
-  // the extra streaming.  CTAs without a tile run ahead into the next phase's weights.
-  if (uniform_s == 0 && n_tiles <= n_ctas && kbt <= total / n_ctas + env_int("MTX_PK_WHOLE_TILE_SLACK", 12)) uniform_s = 1;
+  // the extra streaming.  CTAs without a tile run ahead into the next phase's weights.  (The exchange cost grows with
+  // the number of rows, so steps of few rows use the second table set, built without this rule.)
+  if (allow_whole_tile && uniform_s == 0 && n_tiles <= n_ctas && kbt <= total / n_ctas + env_int("MTX_PK_WHOLE_TILE_SLACK", 12)) uniform_s = 1;
   for (int c = 0; c < n_ctas; ++c) {
     PkTable& t = tabs[c];
     t.n_units[ph] = 0;
@@ -521,7 +522,7 @@ int launch_persistent(mtx_engine* e, int rows, const XMaps& xm, const EpiArgs& l
   p.tile_cnt_stride = e->pk_tile_cnt_stride;
   p.ss_x = e->pk_ss_x;
   p.ss_h = e->pk_ss_h;
-  p.tables = e->pk_tables;
+  p.tables = e->pk_tables + (rows <= env_int("MTX_PK_FEW_ROWS", 16) ? e->pk_ctas : 0);
   p.logits = logits_epi;
   p.grid_bar = e->grid_bar;
   p.trace = g_trace;
@@ -567,6 +568,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     pa.hkv = c.num_kv_heads;
     pa.pk_ctas = e->pk_ctas;
     pa.pk_max_parts = kPkMaxParts;
+    pa.pk_pair_mode_tiles = env_int("MTX_PK_PAIR_MODE_TILES", 36);
   }
   g_class = KC_PREPARE;
   MTX_TRY(launch(prepare_rows_kernel, dim3(1), dim3(256), 0, st, pa, e->rd));
@@ -877,12 +879,18 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
       int ctas = e->num_sms;
       const int cap = env_int("MTX_PERSISTENT_CTAS", 0);
       if (cap > 0 && cap < ctas) ctas = cap;
-      std::vector<PkTable> tabs(ctas);
+      std::vector<PkTable> tabs(ctas), tabs_few(ctas);
       memset(tabs.data(), 0, tabs.size() * sizeof(PkTable));
-      const bool ok = pk_fill_phase(tabs, PK_QKV, e->qkv_n, E) && pk_fill_phase(tabs, PK_OPROJ, E, HD) &&
-                      pk_fill_phase(tabs, PK_UP, 2 * M, E) && pk_fill_phase(tabs, PK_DOWN, E, M);
+      memset(tabs_few.data(), 0, tabs_few.size() * sizeof(PkTable));
+      bool ok = true;
+      for (int set = 0; set < 2 && ok; ++set) {
+        std::vector<PkTable>& t = set == 0 ? tabs : tabs_few;
+        ok = pk_fill_phase(t, PK_QKV, e->qkv_n, E, set == 0) && pk_fill_phase(t, PK_OPROJ, E, HD, set == 0) &&
+             pk_fill_phase(t, PK_UP, 2 * M, E, set == 0) && pk_fill_phase(t, PK_DOWN, E, M, set == 0);
+      }
       if (ok) {
         MTX_CUDA(cudaMemcpy(e->pk_tables, tabs.data(), tabs.size() * sizeof(PkTable), cudaMemcpyHostToDevice));
+        MTX_CUDA(cudaMemcpy(e->pk_tables + ctas, tabs_few.data(), tabs_few.size() * sizeof(PkTable), cudaMemcpyHostToDevice));
         // the split-K exchange workspace starts out (and is left by every reader) as "nothing written"
         fill_u32_kernel<<<256, 256>>>(reinterpret_cast<uint32_t*>(e->pk_part_ws), size_t(e->num_sms) * 4 * kPkSlotFloats, kPkSentinel);
         {

@@ -39,10 +39,11 @@ struct PrepareArgs {
   int* tile_cnt;           // split-K exchange counters
   int tile_cnt_n;
   int* tile_prefix;        // [rows + 1] exclusive prefix of the per-row 64-row tile counts
-  int* attn_info;          // [0] CTAs that get attention work, [1] total tiles over all kv heads
+  int* attn_info;          // [0] CTAs that get attention work, [1] total tiles over all kv heads, [2] 1 = one pair per CTA
   int hkv;
   int pk_ctas;             // CTAs of the persistent grid
   int pk_max_parts;        // most CTAs that may share one (row, kv head)
+  int pk_pair_mode_tiles;  // longest pair (in 64-row tiles) for which a CTA takes a whole pair
 };
 
 // One block of 256 threads.  Fills the row descriptors, the RoPE table
@@ -126,8 +127,17 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
       int nc = total / (qmin < 1 ? 1 : qmin);
       if (nc > a.pk_ctas) nc = a.pk_ctas;
       if (nc < 1) nc = 1;
+      // Few, short pairs: one whole (row, kv head) pair per CTA.  The CTAs are unevenly loaded, but no pair is cut
+      // between CTAs, so no partial result crosses the L2 and the phase ends with the on-chip merge.
+      const int pairs = a.rows * a.hkv;
+      int mode = 0;
+      if (pairs <= a.pk_ctas && nt_max <= a.pk_pair_mode_tiles) {
+        mode = 1;
+        nc = pairs;
+      }
       a.attn_info[0] = nc;
       a.attn_info[1] = total;
+      a.attn_info[2] = mode;
     }
   }
   timeline_end(tl);

@@ -115,7 +115,7 @@ struct PkParams {
   const int *token, *plane, *write_row, *len0, *ring_first, *ring_len;
   const float2* rope_cs;
   const int* tile_prefix;  // [rows + 1] exclusive prefix of the per-row tile counts
-  const int* attn_info;    // [0] active attention warps, [1] total tiles (all kv heads)
+  const int* attn_info;    // [0] CTAs with attention work, [1] total tiles (all kv heads), [2] 1 = one pair per CTA
   // attention merge workspace
   float* attn_part_o;   // [pairs, kPkMaxParts, G, D]
   float* attn_part_ml;  // [pairs, kPkMaxParts, G, 2]
@@ -524,9 +524,16 @@ __device__ __forceinline__ int pk_cta_of(long long g, long long nc, long long to
 // Once per step: the tile list of attention warp `aw` of this CTA.
 __device__ __forceinline__ void pk_attn_build_list(const PkParams& p, PkTail* tail, int cta, int aw, int lane) {
   const long long nc = p.attn_info[0], total = p.attn_info[1];
+  const bool pair_mode = p.attn_info[2] != 0;  // CTA c owns the whole pair c (few short pairs: nothing crosses CTAs)
   int n = 0;
   if (cta < nc && total > 0) {
-    const long long clo = cta * total / nc, chi = (cta + 1) * total / nc;
+    long long clo = cta * total / nc, chi = (cta + 1) * total / nc;
+    if (pair_mode) {
+      const int r = cta / p.hkv, h = cta - r * p.hkv;
+      const int nt = attn_num_tiles(tail->r_len0[r], tail->r_rf[r], tail->r_rl[r], p.T - p.P);
+      clo = (long long)tail->r_prefix[r] * p.hkv + (long long)h * nt;
+      chi = clo + nt;
+    }
     const long long wlo = clo + aw * (chi - clo) / kPkAttnWarps, whi = clo + (aw + 1) * (chi - clo) / kPkAttnWarps;
     n = int(whi - wlo);
     if (n > kPkAttnListMax) n = kPkAttnListMax;  // excluded by the host-side check (pk_usable)
