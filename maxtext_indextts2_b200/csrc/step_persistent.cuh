@@ -26,8 +26,8 @@
 // so RoPE / SwiGLU partners are a warp shuffle away and every global store is an 8-byte piece of a
 // 256-byte coalesced row segment.
 //
-// Roles (384 threads): warp 0 weight producer (TMA) | warp 1 tcgen05.mma issuer | warps 2-5 epilogue |
-// warps 6-11 attention; during the GEMM phases warps 6-9 normalise activation tiles and warp 10 is the
+// Roles (352 threads): warp 0 weight producer (TMA) | warp 1 tcgen05.mma issuer | warps 2-5 epilogue |
+// warps 6-10 attention; during the GEMM phases warps 6-9 normalise activation tiles and warp 10 is the
 // activation producer (TMA).  Every role walks the same static fill sequence with its own lean loop.
 // Attention is stream-K over 64-row KV tiles at WARP granularity: every attention warp of the grid
 // gets the same number of tiles (the partition is computed once per step: lengths do not change between
@@ -43,13 +43,13 @@
 
 namespace mtx {
 
-constexpr int kPkThreads = 384;
-constexpr int kPkStages = 4;
+constexpr int kPkThreads = 352;
+constexpr int kPkStages = 5;
 constexpr int kPkMaxRTile = 64;
 constexpr int kPkStageBytes = kWTileBytes + kPkMaxRTile * kBlockK * 2;  // 24 KB
-constexpr int kPkRingBytes = kPkStages * kPkStageBytes;                 // 96 KB
-constexpr int kPkAttnWarps = 6;
-constexpr int kPkAttnBytes = kPkAttnWarps * 2 * (64 * 64 * 2);          // 96 KB: per warp one K and one V tile (D = 64)
+constexpr int kPkRingBytes = kPkStages * kPkStageBytes;                 // 120 KB
+constexpr int kPkAttnWarps = 5;
+constexpr int kPkAttnBytes = kPkAttnWarps * 2 * (64 * 64 * 2);          // 80 KB: per warp one K and one V tile (D = 64)
 constexpr int kPkParkFloats = kPkMaxRTile * 128;                        // 32 KB, aliases the attention tiles
 constexpr int kPkAccBufs = 4;                                           // TMEM accumulators
 constexpr int kPkMaxUnits = 4;                                          // work units of one CTA in one phase
@@ -59,7 +59,7 @@ constexpr int kPkSlotFloats = 64 * 128;                                 // one p
 constexpr uint32_t kPkSentinel = 0xFFFFDEADu;                           // "not written yet" word of the exchange workspace (a NaN no MMA produces)
 constexpr int kPkParkPitch = 136;                                       // floats per row of the parked logits tile (conflict-free scans)
 constexpr int kPkAttnListMax = 32;                                      // KV tiles one attention warp may own per layer
-constexpr int kPkAttnSlotFloats = 16 * 64 + 2 * 16;                     // one attention partial (O, m, l), G <= 16, D = 64
+constexpr int kPkAttnSlotFloats = 8 * 64 + 2 * 8;                       // one attention partial (O, m, l), G <= 8, D = 64
 
 enum PkPhase : int { PK_QKV = 0, PK_OPROJ = 1, PK_UP = 2, PK_DOWN = 3, PK_LOGITS = 4, PK_END = 5 };
 
@@ -458,7 +458,7 @@ __device__ __forceinline__ void pk_logits_store(const float* park, int ew, int l
 // ---- attention: stream-K over 64-row KV tiles -----------------------------------------------------
 //
 // The valid KV tiles of all (row, kv head) pairs form one list (row-major over row, head, tile).  The active
-// CTAs take equal contiguous runs of it and the six attention warps of a CTA equal contiguous sub-runs, so
+// CTAs take equal contiguous runs of it and the five attention warps of a CTA equal contiguous sub-runs, so
 // every warp streams the same number of bytes whatever the context lengths are.  A warp's run is a sequence
 // of segments (maximal pieces inside one pair).  A pair that lies inside one warp is finished there; a pair
 // cut between warps of one CTA is merged in SHARED memory after the CTA's warps have met; only the pairs cut
@@ -556,7 +556,7 @@ __device__ __forceinline__ void pk_attn_build_list(const PkParams& p, PkTail* ta
   if (lane == 0) tail->a_count[aw] = n;
 }
 
-// The whole CTA's attention for one layer, executed by the six attention warps.
+// The whole CTA's attention for one layer, executed by the attention warps.
 //   phase 1: every warp walks its tile list (TMA K/V tiles -> S = Q K^T -> online softmax -> O += P V)
 //   phase 2: partial segments are merged in shared memory; pairs shared with other CTAs go through L2
 // `primed`: the first K/V tiles were already requested (before the grid barrier).
@@ -1287,12 +1287,12 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
   } else {
     // ============== attention warps; between attention phases: activation producer and normaliser ==============
     const int aw = warp - 6;             // 0..5
-    const int atid = threadIdx.x - 192;  // 0..191
+    const int atid = threadIdx.x - 192;  // 0..159
     const bool xformer = aw < 4;         // warps 6-9 normalise activation tiles during the QKV and MLP-up phases
     const bool xproducer = aw == 4;      // warp 10 requests the activation tiles of every GEMM phase
     uint32_t kv_phase = 0;
-    PkEv ev = pk_ev_make(p, aw == 5 ? 2 : 1);  // debug: first and last attention warp
-    if (aw != 0 && aw != 5) ev.base = nullptr;
+    PkEv ev = pk_ev_make(p, aw == kPkAttnWarps - 1 ? 2 : 1);  // debug: first and last attention warp
+    if (aw != 0 && aw != kPkAttnWarps - 1) ev.base = nullptr;
     PkEv evx = pk_ev_make(p, 2);
     evx.base = nullptr;
 
