@@ -324,6 +324,11 @@ def main():
   if world != args.gpus and world > 1:
     raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
   torch.cuda.set_device(local_rank)
+  # Libraries (NCCL's version banner) write to file descriptor 1; rank 0 must print exactly ONE JSON line there.
+  # Everything until that line goes to stderr.
+  sys.stdout.flush()
+  saved_stdout = os.dup(1)
+  os.dup2(2, 1)
   if world > 1:
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
       os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
@@ -494,7 +499,10 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()
