@@ -99,7 +99,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
   if not force and not needs_build():
     return LIB_PATH
   nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-  cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "engine.cu")]
+  defines = ["-D" + d for d in os.environ.get("MTX_NVCC_DEFINES", "").split() if d]  # e.g. MTX_PK_EVENTS for tools/mega_trace.py
+  cmd = [nvcc] + NVCC_FLAGS + defines + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "engine.cu")]
   proc = subprocess.run(cmd, capture_output=True, text=True)
   if proc.returncode != 0:
     raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)

@@ -92,6 +92,7 @@ struct PkTail {
   int r_len0[kPkMaxRTile], r_rf[kPkMaxRTile], r_rl[kPkMaxRTile], r_plane[kPkMaxRTile], r_prefix[kPkMaxRTile + 1];
   // attention: this CTA's warps own contiguous runs of KV tiles, the same for every layer of the step
   int a_count[kPkAttnWarps];
+  int a_info[2];                          // attn_info[0..1], kept on chip: phase 2 of every layer needs them
   int2 a_list[kPkAttnWarps][kPkAttnListMax];  // .x = cache row of the tile (layer 0), .y = PkAttnMeta bits
   int4 a_seg[kPkAttnWarps][2];                // partial segments of the current layer: .x = pair (-1: none), .y = flags
   float a_slot[kPkAttnWarps][kPkAttnSlotFloats];  // partial of a warp's first segment (its K/V buffers stay busy)
@@ -455,6 +456,57 @@ __device__ __forceinline__ void pk_logits_store(const float* park, int ew, int l
   }
 }
 
+// Finishes the rows r_begin + w, r_begin + w + nw, ... of a shared MLP-up tile: sums the S partial tiles (flag-in-data
+// exchange, see the GEMM phase) and runs the SwiGLU epilogue.  Out of line and shared by the epilogue warps and the
+// attention warps: MLP-up tiles are shared by two or three CTAs that each own 20-30 rows, so the finish is bound by
+// L2 round trips per row and every idle warp of the CTA takes rows.  Four rows x four parts are in flight per warp.
+__device__ __noinline__ void pk_finish_swiglu(const PkParams* pp, int cta, int tile, int c_first, int S, int w, int nw, int lane) {
+  const PkParams& p = *pp;
+  const int si = cta - c_first;
+  const int r_begin = si * p.rows / S, r_end = (si + 1) * p.rows / S;
+  float* src0 = p.part_ws + (long long)(c_first * 4 + (tile & 3)) * kPkSlotFloats + lane * 4;
+  const float sent = __uint_as_float(kPkSentinel);
+  for (int r = r_begin + w; r < r_end; r += 4 * nw) {
+    float4 acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s0 = 0; s0 < S; s0 += 4) {
+      float4 t[4][4];
+      const long long t_spin = clock64();
+      for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int ss = 0; ss < 4; ++ss) {
+            t[k][ss] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r + k * nw < r_end && s0 + ss < S) t[k][ss] = ld_poll_f4(src0 + (long long)(s0 + ss) * 4 * kPkSlotFloats + (r + k * nw) * 128);
+          }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int ss = 0; ss < 4; ++ss)
+            ok = ok && __float_as_uint(t[k][ss].x) != kPkSentinel && __float_as_uint(t[k][ss].y) != kPkSentinel &&
+                 __float_as_uint(t[k][ss].z) != kPkSentinel && __float_as_uint(t[k][ss].w) != kPkSentinel;
+        if (__all_sync(0xffffffffu, ok)) break;
+        pk_backoff();
+        if (clock64() - t_spin > 4000000000LL) mtx_wait_timeout(5, tile, r);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int ss = 0; ss < 4; ++ss) {
+          if (r + k * nw < r_end && s0 + ss < S)
+            *reinterpret_cast<float4*>(src0 + (long long)(s0 + ss) * 4 * kPkSlotFloats + (r + k * nw) * 128) = make_float4(sent, sent, sent, sent);
+          acc[k].x += t[k][ss].x; acc[k].y += t[k][ss].y; acc[k].z += t[k][ss].z; acc[k].w += t[k][ss].w;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (r + k * nw < r_end) pk_epi_swiglu(acc[k], r + k * nw, tile, lane, 2 * p.M, p.M, p.act);
+  }
+}
+
 // ---- attention: stream-K over 64-row KV tiles -----------------------------------------------------
 //
 // The valid KV tiles of all (row, kv head) pairs form one list (row-major over row, head, tile).  The active
@@ -554,6 +606,7 @@ __device__ __forceinline__ void pk_attn_build_list(const PkParams& p, PkTail* ta
     }
   }
   if (lane == 0) tail->a_count[aw] = n;
+  if (aw == 0 && lane < 2) tail->a_info[lane] = lane == 0 ? int(nc) : int(total);
 }
 
 // The whole CTA's attention for one layer, executed by the attention warps.
@@ -775,7 +828,7 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
   if (lane == 0) pk_ev(ev, 610);
   named_bar_sync(3, kPkAttnWarps * 32);
   if (lane == 0) pk_ev(ev, 611);
-  const long long nc = p.attn_info[0], total = p.attn_info[1];
+  const long long nc = tail->a_info[0], total = tail->a_info[1];  // (a global load here is an L2 round trip per layer)
   for (int k = 0; k < 2; ++k) {
     const int4 me = tail->a_seg[aw][k];
     if (me.x < 0) continue;
@@ -914,7 +967,7 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
                        const __grid_constant__ CUtensorMap tm_wlogits, const __grid_constant__ CUtensorMap tm_x,
                        const __grid_constant__ CUtensorMap tm_attn, const __grid_constant__ CUtensorMap tm_h,
                        const __grid_constant__ CUtensorMap tm_act, const __grid_constant__ CUtensorMap tm_n,
-                       const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const PkParams p) {
+                       const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ PkParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space
   uint8_t* ring = smem;
@@ -1046,6 +1099,8 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
     const uint32_t tlane = uint32_t(quarter * 32) << 16;
     uint32_t uc = 0, nbar = 0;
     PkEv ev = pk_ev_make(p, 0);
+    bool up_shared = false;  // this CTA shares MLP-up tiles with other CTAs: all its warps help to finish them
+    for (int u = 0; u < tab.n_units[PK_UP]; ++u) up_shared = up_shared || tab.u[PK_UP][u].S > 1;
 
     griddep_wait();
     if (p.trace && wtid == 0) p.trace[gridDim.x + blockIdx.x] = (long long)globaltimer_ns();  // "barrier 0 release" = start
@@ -1124,6 +1179,7 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
         const uint32_t buf = uc % kPkAccBufs;
         mbar_wait(&tail->tmem_full[buf], (uc / kPkAccBufs) & 1);
         tcgen05_fence_after();
+        if (wtid == 0) pk_ev(ev, 100 * ph + 12);
         const uint32_t taddr = tmem_base + tlane + buf * uint32_t(p.r_tile);
         // exchange slot in global memory, or the park buffer in shared memory for a tile this CTA owns alone
         if (un.S == 1) {
@@ -1144,6 +1200,7 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
           }
         }
         tcgen05_fence_before();
+        if (wtid == 0) pk_ev(ev, 100 * ph + 13);
         // Polling loads issued back to back can starve the SM's own pending stores (then every CTA waits for
         // everybody): the poll loop below pauses between attempts so that the store queue always drains.
         named_bar_sync(1, 128);
@@ -1160,6 +1217,12 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
       for (int u = 0; u < nu; ++u) {
         const PkUnit un = tab.u[ph][u];
         if (un.S == 1) continue;
+        if (ph == PK_UP) {  // every warp of the CTA takes rows (the attention warps call the same routine)
+          if (wtid == 0) pk_ev(ev, 100 * ph + 14);
+          pk_finish_swiglu(&p, cta, un.tile, un.c_first, un.S, ew, 4 + kPkAttnWarps, lane);
+          if (wtid == 0) pk_ev(ev, 100 * ph + 15);
+          continue;
+        }
         const int si = cta - un.c_first;
         const int r_begin = si * p.rows / un.S, r_end = (si + 1) * p.rows / un.S;
         float* src0 = p.part_ws + (long long)(un.c_first * 4 + (un.tile & 3)) * kPkSlotFloats + lane * 4;
@@ -1219,6 +1282,9 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
         else if (ph == PK_OPROJ) gemm_phase(std::integral_constant<int, PK_OPROJ>{}, l);
         else if (ph == PK_UP) gemm_phase(std::integral_constant<int, PK_UP>{}, l);
         else gemm_phase(std::integral_constant<int, PK_DOWN>{}, l);
+        if (ph == PK_UP && up_shared) {  // the attention warps' share of the MLP-up rows is stored too
+          asm volatile("bar.sync 4, %0;" ::"r"(128 + kPkAttnWarps * 32) : "memory");
+        }
         phase_end(l == p.L - 1 && ph == PK_DOWN);
         if (ph == PK_QKV) ++nbar;  // the attention phase's barrier is run by the attention warps
       }
@@ -1316,6 +1382,8 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
     for (int u = 0; u < tab.n_units[PK_QKV]; ++u)
       if (tab.u[PK_QKV][u].S == 1) may_prime = false;
 
+    bool up_shared = false;  // see the epilogue warps
+    for (int u = 0; u < tab.n_units[PK_UP]; ++u) up_shared = up_shared || tab.u[PK_UP][u].S > 1;
     PkCursor cur;  // shared fill sequence (activation producer and normaliser walk it in step with the weights)
     pk_cursor_init(cur);
 
@@ -1350,6 +1418,29 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
       const int nu = tab.n_units[ph];
       if (nu == 0) return;
       if (atid == 0) pk_ev(ev, 100 * ph + 20);
+      // lane -> 16-byte chunks (row, physical chunk pc): pc = lane & 7, rows (lane >> 3) + 4 j; the logical chunk
+      // pc ^ (row & 7) takes two values (j even / odd).
+      const int pc = lane & 7, rq = lane >> 3;
+      const int lc_a = pc ^ (rq & 7), lc_b = pc ^ ((rq + 4) & 7);
+      const bf16* scale = (ph == PK_QKV ? p.attn_norm : p.mlp_norm) + (long long)layer * p.E;
+      // k-block of this warp's fill number f of the phase (-1 past the end); the norm scales of the next owned
+      // k-block are requested one fill ahead, the first ones before the phase's barrier completes
+      auto kb_of_fill = [&](int f) {
+        for (int u = 0; u < nu; ++u) {
+          const int n = tab.u[ph][u].kb1 - tab.u[ph][u].kb0;
+          if (f < n) return tab.u[ph][u].kb0 + f;
+          f -= n;
+        }
+        return -1;
+      };
+      uint4 sc_a = make_uint4(0, 0, 0, 0), sc_b = sc_a;
+      {
+        const int kbn = kb_of_fill(aw);
+        if (kbn >= 0) {
+          sc_a = *reinterpret_cast<const uint4*>(scale + kbn * kBlockK + lc_a * 8);
+          sc_b = *reinterpret_cast<const uint4*>(scale + kbn * kBlockK + lc_b * 8);
+        }
+      }
       pk_wait_flag(&tail->bar_done, pk_need(layer, ph, p.L));
       if (atid == 0) pk_ev(ev, 100 * ph + 21);
       const float* ss = ph == PK_QKV ? p.ss_x : p.ss_h;
@@ -1374,18 +1465,11 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
       if (atid == 0) pk_ev(ev, 100 * ph + 27);
       // Each warp normalises whole k-blocks on its own (fill i of the phase belongs to warp i % 4), so the k-blocks
       // of a phase are processed in parallel and no CTA-level barrier sits between a tile's arrival and its MMA.
-      // lane -> 16-byte chunks (row, physical chunk pc): pc = lane & 7, rows (lane >> 3) + 4 j; the logical chunk
-      // pc ^ (row & 7) takes two values (j even / odd).
-      const int pc = lane & 7, rq = lane >> 3;
-      const int lc_a = pc ^ (rq & 7), lc_b = pc ^ ((rq + 4) & 7);
-      const bf16* scale = (ph == PK_QKV ? p.attn_norm : p.mlp_norm) + (long long)layer * p.E;
       int fi = 0;
       for (int u = 0; u < nu; ++u) {
         const PkUnit un = tab.u[ph][u];
         for (int kb = un.kb0; kb < un.kb1; ++kb, ++fi) {
           if ((fi & 3) == aw) {
-            const uint4 sc_a = *reinterpret_cast<const uint4*>(scale + kb * kBlockK + lc_a * 8);
-            const uint4 sc_b = *reinterpret_cast<const uint4*>(scale + kb * kBlockK + lc_b * 8);
             if (atid == 0) pk_ev(ev, 100 * ph + 22);
             mbar_wait(&tail->full_x[cur.s], cur.par);
             if (atid == 0) pk_ev(ev, 100 * ph + 23);
@@ -1418,6 +1502,13 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) *reinterpret_cast<uint4*>(lane_base + (j0 + jj) * 512) = raw[jj];
             }
+            {
+              const int kbn = kb_of_fill(fi + 4);
+              if (kbn >= 0) {
+                sc_a = *reinterpret_cast<const uint4*>(scale + kbn * kBlockK + lc_a * 8);
+                sc_b = *reinterpret_cast<const uint4*>(scale + kbn * kBlockK + lc_b * 8);
+              }
+            }
             if (atid == 0) pk_ev(ev, 100 * ph + 28);
             fence_proxy_async();  // the MMA reads the tile through the async proxy
             if (atid == 0) pk_ev(ev, 100 * ph + 29);
@@ -1448,6 +1539,15 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
 #pragma unroll 1  // one copy of the duty code
       for (int ph = 0; ph < 4; ++ph) {
         gemm_duty(ph, l);
+        if (ph == PK_UP && up_shared) {
+          __syncwarp();
+          for (int u = 0; u < tab.n_units[PK_UP]; ++u) {
+            const PkUnit un = tab.u[PK_UP][u];
+            if (un.S > 1) pk_finish_swiglu(&p, cta, un.tile, un.c_first, un.S, 4 + aw, 4 + kPkAttnWarps, lane);
+          }
+          fence_proxy_async_all();
+          asm volatile("bar.arrive 4, %0;" ::"r"(128 + kPkAttnWarps * 32) : "memory");
+        }
         if (ph != PK_QKV) continue;
         __syncwarp();
         // ---- attention over the valid rows of both cache segments ----
