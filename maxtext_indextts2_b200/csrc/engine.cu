@@ -568,6 +568,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     pa.hkv = c.num_kv_heads;
     pa.pk_ctas = e->pk_ctas;
     pa.pk_max_parts = kPkMaxParts;
+    pa.pk_warps = kPkAttnWarps;
     pa.pk_pair_mode_tiles = env_int("MTX_PK_PAIR_MODE_TILES", 36);
   }
   g_class = KC_PREPARE;

@@ -42,7 +42,8 @@ struct PrepareArgs {
   int* attn_info;          // [0] CTAs that get attention work, [1] total tiles over all kv heads, [2] 1 = one pair per CTA
   int hkv;
   int pk_ctas;             // CTAs of the persistent grid
-  int pk_max_parts;        // most CTAs that may share one (row, kv head)
+  int pk_max_parts;        // most attention warps of other CTAs that may hold tiles of one (row, kv head)
+  int pk_warps;            // attention warps per CTA
   int pk_pair_mode_tiles;  // longest pair (in 64-row tiles) for which a CTA takes a whole pair
 };
 
@@ -120,12 +121,16 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
         nt_max = s_nt[r] > nt_max ? s_nt[r] : nt_max;
       }
       a.tile_prefix[a.rows] = acc;
-      // every active CTA gets total / nc tiles (rounded either way); a pair of nt tiles then spans at most
-      // (nt - 1) / floor(total / nc) + 2 CTAs, which must not exceed pk_max_parts
+      // Every active CTA gets q = total / nc tiles (rounded either way) and each of its pk_warps attention warps a
+      // fifth of them.  The warps that hold the tiles of a pair outside the pair's first CTA each own one slot of
+      // the pair's exchange workspace: at most nt - 1 of them, and at most (nt - 1) / floor(q / warps) + 2.
       const int total = acc * a.hkv;
-      const int qmin = (nt_max + a.pk_max_parts - 3) / (a.pk_max_parts - 2);
-      int nc = total / (qmin < 1 ? 1 : qmin);
-      if (nc > a.pk_ctas) nc = a.pk_ctas;
+      int nc = total < a.pk_ctas ? total : a.pk_ctas;
+      if (nt_max - 1 > a.pk_max_parts) {
+        const int f = (nt_max - 1 + a.pk_max_parts - 3) / (a.pk_max_parts - 2);  // tiles per warp needed
+        const int by_parts = total / (f * a.pk_warps);
+        nc = by_parts < nc ? by_parts : nc;
+      }
       if (nc < 1) nc = 1;
       // Few, short pairs: one whole (row, kv head) pair per CTA.  The CTAs are unevenly loaded, but no pair is cut
       // between CTAs, so no partial result crosses the L2 and the phase ends with the on-chip merge.

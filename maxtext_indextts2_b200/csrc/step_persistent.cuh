@@ -54,7 +54,7 @@ constexpr int kPkParkFloats = kPkMaxRTile * 128;                        // 32 KB
 constexpr int kPkAccBufs = 4;                                           // TMEM accumulators
 constexpr int kPkMaxUnits = 4;                                          // work units of one CTA in one phase
 constexpr int kPkMaxSplit = 16;                                         // CTAs sharing one weight tile
-constexpr int kPkMaxParts = 16;                                         // attention warps sharing one (row, kv head)
+constexpr int kPkMaxParts = 48;                                         // attention warps sharing one (row, kv head)
 constexpr int kPkSlotFloats = 64 * 128;                                 // one partial tile in the exchange workspace
 constexpr uint32_t kPkSentinel = 0xFFFFDEADu;                           // "not written yet" word of the exchange workspace (a NaN no MMA produces)
 constexpr int kPkParkPitch = 136;                                       // floats per row of the parked logits tile (conflict-free scans)
@@ -92,7 +92,8 @@ struct PkTail {
   int r_len0[kPkMaxRTile], r_rf[kPkMaxRTile], r_rl[kPkMaxRTile], r_plane[kPkMaxRTile], r_prefix[kPkMaxRTile + 1];
   // attention: this CTA's warps own contiguous runs of KV tiles, the same for every layer of the step
   int a_count[kPkAttnWarps];
-  int a_info[2];                          // attn_info[0..1], kept on chip: phase 2 of every layer needs them
+  int a_tail[kPkAttnWarps];               // part slot (pair * kPkMaxParts + ordinal) of the warp's tail segment, -1: none
+  int a_head[4];                          // the pair this CTA merges for other CTAs: pair (-1: none), row * 64 + kv head, first warp, parts
   int2 a_list[kPkAttnWarps][kPkAttnListMax];  // .x = cache row of the tile (layer 0), .y = PkAttnMeta bits
   int4 a_seg[kPkAttnWarps][2];                // partial segments of the current layer: .x = pair (-1: none), .y = flags
   float a_slot[kPkAttnWarps][kPkAttnSlotFloats];  // partial of a warp's first segment (its K/V buffers stay busy)
@@ -522,6 +523,7 @@ enum PkAttnMeta : int {
   PKA_SEG_END = 1 << 21,     // last tile of a segment of this warp
   PKA_PAIR_FIRST = 1 << 22,  // tile 0 of its pair
   PKA_PAIR_LAST = 1 << 23,   // last tile of its pair: holds the row appended this step
+  PKA_TAIL = 1 << 24,        // end of a segment whose pair began in another CTA: the partial goes to that CTA through L2
 };
 // meta bits [0,6) = valid rows - 1, [6,14) = row, [14,20) = kv head
 __device__ __forceinline__ int pka_cnt(int m) { return (m & 63) + 1; }
@@ -573,40 +575,100 @@ __device__ __forceinline__ void pk_attn_next(PkAttnPos& a, const PkParams& p, co
 // CTA that owns flattened tile g when `nc` CTAs share `total` tiles.
 __device__ __forceinline__ int pk_cta_of(long long g, long long nc, long long total) { return int(((g + 1) * nc - 1) / total); }
 
-// Once per step: the tile list of attention warp `aw` of this CTA.
+// Tiles [wlo, whi) of attention warp a of CTA c (equal contiguous runs per CTA, equal sub-runs per warp).
+__device__ __forceinline__ void pk_warp_range(int c, int a, int nc, int total, int& wlo, int& whi) {
+  const int clo = int((long long)c * total / nc), chi = int((long long)(c + 1) * total / nc);
+  wlo = clo + a * (chi - clo) / kPkAttnWarps;
+  whi = clo + (a + 1) * (chi - clo) / kPkAttnWarps;
+}
+// Number of warps that hold tiles, from warp 0 of CTA c0 up to (not including) the first warp starting at or after g_stop.
+__device__ __noinline__ int pk_count_warps(int c0, int g_stop, int nc, int total) {
+  int count = 0;
+  for (int c = c0; c < nc; ++c)
+    for (int a = 0; a < kPkAttnWarps; ++a) {
+      int wlo, whi;
+      pk_warp_range(c, a, nc, total, wlo, whi);
+      if (wlo >= g_stop) return count;
+      if (whi > wlo) ++count;
+    }
+  return count;
+}
+
+// Once per step: the tile list of attention warp `aw` of this CTA, and the CTA's place in the exchange of the
+// pairs cut between CTAs.  A pair is merged by the CTA that holds its first tile (the "head"); every warp of a
+// later CTA that holds tiles of the pair (the "tail") writes its partial straight from registers into its own
+// slot of the pair's L2 workspace when its segment ends, i.e. DURING the tile loop: by the time the head CTA
+// has merged its own warps the tail parts are already there.  Slots are numbered by the warp's ordinal among the
+// tail warps; both sides derive it from the partition alone.
 __device__ __forceinline__ void pk_attn_build_list(const PkParams& p, PkTail* tail, int cta, int aw, int lane) {
-  const long long nc = p.attn_info[0], total = p.attn_info[1];
+  const int nc = p.attn_info[0], total = p.attn_info[1];
   const bool pair_mode = p.attn_info[2] != 0;  // CTA c owns the whole pair c (few short pairs: nothing crosses CTAs)
-  int n = 0;
+  const int R = p.T - p.P;
+  int n = 0, tail_slot = -1;
+  int head[4] = {-1, 0, 0, 0};
   if (cta < nc && total > 0) {
-    long long clo = cta * total / nc, chi = (cta + 1) * total / nc;
+    int clo = int((long long)cta * total / nc), chi = int((long long)(cta + 1) * total / nc);
     if (pair_mode) {
       const int r = cta / p.hkv, h = cta - r * p.hkv;
-      const int nt = attn_num_tiles(tail->r_len0[r], tail->r_rf[r], tail->r_rl[r], p.T - p.P);
-      clo = (long long)tail->r_prefix[r] * p.hkv + (long long)h * nt;
+      const int nt = attn_num_tiles(tail->r_len0[r], tail->r_rf[r], tail->r_rl[r], R);
+      clo = tail->r_prefix[r] * p.hkv + h * nt;
       chi = clo + nt;
     }
-    const long long wlo = clo + aw * (chi - clo) / kPkAttnWarps, whi = clo + (aw + 1) * (chi - clo) / kPkAttnWarps;
-    n = int(whi - wlo);
+    const int wlo = clo + aw * (chi - clo) / kPkAttnWarps, whi = clo + (aw + 1) * (chi - clo) / kPkAttnWarps;
+    n = whi - wlo;
     if (n > kPkAttnListMax) n = kPkAttnListMax;  // excluded by the host-side check (pk_usable)
     if (n > 0) {
-      const int R = p.T - p.P;
       PkAttnPos pos;
       pk_attn_seek(pos, wlo, p, tail, R, lane);
+      // the warp's first segment is a tail if its pair began in an earlier CTA
+      const int g_first = tail->r_prefix[pos.r] * p.hkv + pos.h * pos.nt;
+      bool is_tail = !pair_mode && g_first < clo;
+      if (is_tail) {
+        const int c_first = pk_cta_of(g_first, nc, total);
+        const int ordinal = pk_count_warps(c_first + 1, wlo, nc, total);
+        if (ordinal >= kPkMaxParts) __trap();  // excluded by prepare_rows_kernel's choice of nc
+        tail_slot = (pos.r * p.hkv + pos.h) * kPkMaxParts + ordinal;
+      }
       for (int i = 0; i < n; ++i) {
         const TileLoc loc = attn_tile(pos.t, pos.len0, pos.rf, pos.rl, p.P, R);
         int meta = (loc.cnt - 1) | (pos.r << 6) | (pos.h << 14);
         if (i == 0 || pos.t == 0) meta |= PKA_SEG_START;
         if (pos.t == 0) meta |= PKA_PAIR_FIRST;
-        if (i == n - 1 || pos.t == pos.nt - 1) meta |= PKA_SEG_END;
+        if (i == n - 1 || pos.t == pos.nt - 1) {
+          meta |= PKA_SEG_END;
+          if (is_tail) meta |= PKA_TAIL;
+          is_tail = false;
+        }
         if (pos.t == pos.nt - 1) meta |= PKA_PAIR_LAST;
         if (lane == 0) tail->a_list[aw][i] = make_int2(pos.plane_row + loc.p0, meta);
         pk_attn_next(pos, p, tail, R);
       }
     }
+    if (aw == 0 && !pair_mode && chi > clo) {
+      // the pair of the CTA's last tile: if it continues in later CTAs and began here, this CTA merges it
+      PkAttnPos pos;
+      pk_attn_seek(pos, chi - 1, p, tail, R, lane);
+      const int g_first = chi - 1 - pos.t;
+      if (pos.t != pos.nt - 1 && g_first >= clo) {
+        int w_a = 0;
+        while (w_a < kPkAttnWarps - 1 && clo + (w_a + 1) * (chi - clo) / kPkAttnWarps <= g_first) ++w_a;
+        head[0] = pos.r * p.hkv + pos.h;
+        head[1] = pos.r * 64 + pos.h;
+        head[2] = w_a;
+        head[3] = pk_count_warps(cta + 1, g_first + pos.nt, nc, total);
+      }
+    }
   }
-  if (lane == 0) tail->a_count[aw] = n;
-  if (aw == 0 && lane < 2) tail->a_info[lane] = lane == 0 ? int(nc) : int(total);
+  if (lane == 0) {
+    tail->a_count[aw] = n;
+    tail->a_tail[aw] = tail_slot;
+  }
+  if (aw == 0 && lane == 0) {
+    tail->a_head[0] = head[0];
+    tail->a_head[1] = head[1];
+    tail->a_head[2] = head[2];
+    tail->a_head[3] = head[3];
+  }
 }
 
 // The whole CTA's attention for one layer, executed by the attention warps.
@@ -797,9 +859,10 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
         }
       } else {
         // park the partial ([head][d] fp32, then (m, l) per head): the warp's last segment goes to its (now idle)
-        // K buffer, an earlier one to its slot
-        const bool final_seg = !more;
-        float* dst = final_seg ? reinterpret_cast<float*>(k_tile) : tail->a_slot[aw];
+        // K buffer, an earlier one to its slot; a tail segment goes to its slot of the pair's L2 workspace
+        const bool final_seg = !more, to_l2 = (meta & PKA_TAIL) != 0;
+        const int stride = (G * D + 2 * G + 3) & ~3;  // 16-byte aligned parts
+        float* dst = to_l2 ? p.attn_part_o + (long long)tail->a_tail[aw] * stride : final_seg ? reinterpret_cast<float*>(k_tile) : tail->a_slot[aw];
 #pragma unroll
         for (int db = 0; db < D / 16; ++db) {
           const int d = 16 * db + gid;
@@ -816,7 +879,7 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
           if (h0 < G) *reinterpret_cast<float2*>(dst + G * D + h0 * 2) = make_float2(m0, l0);
           if (h0 + 1 < G) *reinterpret_cast<float2*>(dst + G * D + (h0 + 1) * 2) = make_float2(m1, l1);
         }
-        if (lane == 0) {
+        if (lane == 0 && !to_l2) {
           const int flags = (seg_first ? 1 : 0) | ((meta & PKA_PAIR_LAST) ? 2 : 0);
           tail->a_seg[aw][final_seg ? 1 : 0] = make_int4(r * p.hkv + h, flags, r, h);
         }
@@ -828,22 +891,81 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
   if (lane == 0) pk_ev(ev, 610);
   named_bar_sync(3, kPkAttnWarps * 32);
   if (lane == 0) pk_ev(ev, 611);
-  const long long nc = tail->a_info[0], total = tail->a_info[1];  // (a global load here is an L2 round trip per layer)
+  const int stride = (G * D + 2 * G + 3) & ~3;
+
+  // (a) The pair this CTA merges for later CTAs: one thread per (head, 4 dims) unit.  Sources: the K buffers of
+  // the warps from the pair's first warp on (each parked its last segment there), then the tail warps' parts in
+  // L2 (flag-in-data: a word is the sentinel or data; written during the other CTAs' tile loops, so normally all
+  // present already), four parts per round trip.  Fixed order: deterministic.
+  if (tail->a_head[0] >= 0 && aw * 32 < G * (D / 4)) {  // (whole warps: they meet again before the flags are reset)
+    const int unit = aw * 32 + lane;
+    const bool act = unit < G * (D / 4);
+    const int pair = tail->a_head[0], r = tail->a_head[1] >> 6, h = tail->a_head[1] & 63, n_parts = act ? tail->a_head[3] : 0;
+    const int gq = act ? unit / (D / 4) : 0, d4 = unit - gq * (D / 4);
+    float M = -INFINITY, Ls = 0.0f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto fold = [&](const float2 ml, const float4 o4) {
+      const float Mn = fmaxf(M, ml.x);
+      const float so = ex2_approx((M - Mn) * kLog2e), sn = ex2_approx((ml.x - Mn) * kLog2e);
+      Ls = Ls * so + ml.y * sn;
+      acc.x = acc.x * so + o4.x * sn; acc.y = acc.y * so + o4.y * sn;
+      acc.z = acc.z * so + o4.z * sn; acc.w = acc.w * so + o4.w * sn;
+      M = Mn;
+    };
+    for (int w = tail->a_head[2]; w < kPkAttnWarps; ++w) {
+      if (tail->a_count[w] == 0 || !act) continue;
+      const float* src = reinterpret_cast<const float*>(attn_tiles + w * 2 * 8192);
+      fold(*reinterpret_cast<const float2*>(src + G * D + gq * 2), *reinterpret_cast<const float4*>(src + gq * D + d4 * 4));
+    }
+    float* gbase = p.attn_part_o + (long long)pair * kPkMaxParts * stride;
+    const float sent = __uint_as_float(kPkSentinel);
+    for (int c0 = 0; c0 < n_parts; c0 += 4) {
+      float2 ml[4];
+      float4 o4[4];
+      const long long t_spin = clock64();
+      for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+          if (c0 + cc < n_parts) {
+            const float* part = gbase + (long long)(c0 + cc) * stride;
+            ml[cc] = ld_poll_f2(part + G * D + gq * 2);
+            o4[cc] = ld_poll_f4(part + gq * D + d4 * 4);
+            ok = ok && __float_as_uint(ml[cc].x) != kPkSentinel && __float_as_uint(ml[cc].y) != kPkSentinel &&
+                 __float_as_uint(o4[cc].x) != kPkSentinel && __float_as_uint(o4[cc].y) != kPkSentinel &&
+                 __float_as_uint(o4[cc].z) != kPkSentinel && __float_as_uint(o4[cc].w) != kPkSentinel;
+          }
+        if (ok) break;
+        pk_backoff();
+        if (clock64() - t_spin > 4000000000LL) mtx_wait_timeout(4, pair, c0);
+      }
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc)
+        if (c0 + cc < n_parts) {
+          // the words this thread has read are put back to the sentinel for the next layer (the (m, l) words are
+          // shared by the 16 threads of a head: see below)
+          float* part = gbase + (long long)(c0 + cc) * stride;
+          *reinterpret_cast<float4*>(part + gq * D + d4 * 4) = make_float4(sent, sent, sent, sent);
+          fold(ml[cc], o4[cc]);
+        }
+    }
+    if (act) {
+      const float inv = 1.0f / Ls;
+      *reinterpret_cast<uint2*>(p.attn + (long long)r * p.hq * D + (long long)h * G * D + gq * D + d4 * 4) =
+          pack_bf16x4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    }
+    __syncwarp();  // the 16 threads of a head sit in one warp: all of them have read the head's (m, l) words
+    if (act && d4 == 0)
+      for (int c = 0; c < n_parts; ++c) *reinterpret_cast<float2*>(gbase + (long long)c * stride + G * D + gq * 2) = make_float2(sent, sent);
+  }
+
+  // (b) Pairs cut between warps of this CTA only: the warp that holds the pair's first segment merges.
   for (int k = 0; k < 2; ++k) {
     const int4 me = tail->a_seg[aw][k];
     if (me.x < 0) continue;
     // predecessor in tile order: this warp's slot entry, else the last segment of the nearest earlier warp with tiles
     bool leader = true;
-    if (k == 0) {
-      for (int w = aw - 1; w >= 0; --w)
-        if (tail->a_count[w] > 0) {
-          leader = tail->a_seg[w][1].x != me.x;
-          break;
-        }
-    } else if (tail->a_seg[aw][0].x == me.x) {
-      leader = false;  // cannot happen (a warp's two partial segments belong to different pairs); kept for safety
-    } else if (tail->a_seg[aw][0].x < 0) {
-      // a warp whose whole run is one partial segment: the pair may continue from the previous warp
+    if (k == 0 || tail->a_seg[aw][0].x < 0) {
       for (int w = aw - 1; w >= 0; --w)
         if (tail->a_count[w] > 0) {
           leader = tail->a_seg[w][1].x != me.x;
@@ -872,27 +994,11 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
         break;
       }
     }
-    const int r = me.z, h = me.w, pair = me.x;
-    const long long out_base = (long long)r * p.hq * D + (long long)h * G * D;
-    const bool complete = (flags & 3) == 3;
-    // A pair cut between CTAs: the CTA that holds the pair's FIRST tile merges.  That tile sits at the END of its
-    // tile range, so it finishes last; the other CTAs hold the pair at the START of their ranges and have long
-    // stored their parts by then.  Parts travel through an L2 workspace with the flag-in-data protocol of the
-    // split-K exchange (a word is the sentinel or data): no fence, no ticket, one load round for the merger.
-    const bool merger = !complete && (flags & 1) != 0;
-    const int stride = (G * D + 2 * G + 3) & ~3;  // 16-byte aligned parts
-    float* gbase = p.attn_part_o + (long long)pair * kPkMaxParts * stride;
-    int n_other = 0, my_part = 0;
-    if (!complete) {
-      const int nt = attn_num_tiles(tail->r_len0[r], tail->r_rf[r], tail->r_rl[r], p.T - p.P);
-      const long long g_first = (long long)tail->r_prefix[r] * p.hkv + (long long)h * nt;
-      const int c_first = pk_cta_of(g_first, nc, total);
-      n_other = pk_cta_of(g_first + nt - 1, nc, total) - c_first;  // parts held by other CTAs
-      my_part = cta - c_first - 1;                                  // -1 for the merger
-    }
-    if (lane == 0) pk_ev(ev, 620 + k * 100 + (complete ? 1 : 0) + (merger ? 2 : 0) + 10 * n_src + 1000 * n_other);
-    for (int unit = lane; unit < G * (D / 4); unit += 32) {
-      const int gq = unit / (D / 4), d4 = unit - gq * (D / 4);
+    if ((flags & 3) != 3) continue;  // continues in other CTAs: merged under (a)
+    const long long out_base = (long long)me.z * p.hq * D + (long long)me.w * G * D;
+    if (lane == 0) pk_ev(ev, 620 + k * 100 + 10 * n_src);
+    for (int u = lane; u < G * (D / 4); u += 32) {
+      const int gq = u / (D / 4), d4 = u - gq * (D / 4);
       float M = -INFINITY;
       for (int c = 0; c < n_src; ++c) M = fmaxf(M, src[c][G * D + gq * 2]);
       float Ls = 0.0f;
@@ -904,58 +1010,10 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
         Ls += ml.y * sc;
         acc.x += o4.x * sc; acc.y += o4.y * sc; acc.z += o4.z * sc; acc.w += o4.w * sc;
       }
-      if (merger) {
-        for (int c0 = 0; c0 < n_other; c0 += 4) {  // both loads of up to four parts travel together
-          float2 ml[4];
-          float4 o4[4];
-          const long long t_spin = clock64();
-          for (;;) {
-            bool ok = true;
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc)
-              if (c0 + cc < n_other) {
-                const float* part = gbase + (long long)(c0 + cc) * stride;
-                ml[cc] = ld_poll_f2(part + G * D + gq * 2);
-                o4[cc] = ld_poll_f4(part + gq * D + d4 * 4);
-                ok = ok && __float_as_uint(ml[cc].x) != kPkSentinel && __float_as_uint(ml[cc].y) != kPkSentinel &&
-                     __float_as_uint(o4[cc].x) != kPkSentinel && __float_as_uint(o4[cc].y) != kPkSentinel &&
-                     __float_as_uint(o4[cc].z) != kPkSentinel && __float_as_uint(o4[cc].w) != kPkSentinel;
-              }
-            if (ok) break;
-            pk_backoff();
-            if (clock64() - t_spin > 4000000000LL) mtx_wait_timeout(4, pair, 0);
-          }
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc)
-            if (c0 + cc < n_other) {
-              const float Mn = fmaxf(M, ml[cc].x);
-              const float so = ex2_approx((M - Mn) * kLog2e), sn = ex2_approx((ml[cc].x - Mn) * kLog2e);
-              Ls = Ls * so + ml[cc].y * sn;
-              acc.x = acc.x * so + o4[cc].x * sn; acc.y = acc.y * so + o4[cc].y * sn;
-              acc.z = acc.z * so + o4[cc].z * sn; acc.w = acc.w * so + o4[cc].w * sn;
-              M = Mn;
-            }
-        }
-      }
-      if (complete || merger) {
-        const float inv = 1.0f / Ls;
-        *reinterpret_cast<uint2*>(p.attn + out_base + gq * D + d4 * 4) = pack_bf16x4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-      } else {
-        float* gpart = gbase + (long long)my_part * stride;
-        *reinterpret_cast<float4*>(gpart + gq * D + d4 * 4) = acc;
-        if (d4 == 0) *reinterpret_cast<float2*>(gpart + G * D + gq * 2) = make_float2(M, Ls);
-      }
+      const float inv = 1.0f / Ls;
+      *reinterpret_cast<uint2*>(p.attn + out_base + gq * D + d4 * 4) = pack_bf16x4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
     }
     if (lane == 0) pk_ev(ev, 690 + k);
-    if (merger) {
-      // every lane has read its fragments: put the sentinel back for the next layer
-      __syncwarp();
-      const float sent = __uint_as_float(kPkSentinel);
-      for (int c = 0; c < n_other; ++c) {
-        float* part = gbase + (long long)c * stride;
-        for (int q = lane; q < (G * D + 2 * G + 3) / 4; q += 32) *reinterpret_cast<float4*>(part + q * 4) = make_float4(sent, sent, sent, sent);
-      }
-    }
   }
 }
 
@@ -1144,15 +1202,18 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
 
     // One GEMM phase of this CTA: dump every accumulator (partial tile to the exchange workspace, or straight to
     // the epilogue when the CTA owns the whole reduction), then finish the row slices it owns.
-    auto gemm_phase = [&](auto ph_tag, int layer) {
-      constexpr int ph = decltype(ph_tag)::value;  // specialised per phase: measurably faster than one generic body
-      const int nu = tab.n_units[ph];
+    // `ph_tag` selects the epilogue kind at compile time (QKV / SwiGLU / residual); out-proj and MLP down share the
+    // residual body and differ only in `tph` (work table, buffers): per layer the instruction footprint of the CTA
+    // has to stay inside the instruction cache, every copy of this body costs ~20 KB of it.
+    auto gemm_phase = [&](auto ph_tag, int tph, int layer) {
+      constexpr int ph = decltype(ph_tag)::value;
+      const int nu = tab.n_units[tph];
       const int N = ph == PK_QKV ? p.qkv_n : ph == PK_UP ? 2 * p.M : p.E;
       bf16* k_layer = p.k_cache + p.kv_layer_elems * layer;
       bf16* v_layer = p.v_cache + p.kv_layer_elems * layer;
-      const bf16* resid = ph == PK_OPROJ ? p.x : p.h;
-      bf16* res_out = ph == PK_OPROJ ? p.h : p.x;
-      float* ss_out = ph == PK_OPROJ ? p.ss_h : p.ss_x;
+      const bf16* resid = tph == PK_OPROJ ? p.x : p.h;
+      bf16* res_out = tph == PK_OPROJ ? p.h : p.x;
+      float* ss_out = tph == PK_OPROJ ? p.ss_h : p.ss_x;
       // Side inputs of a row fragment do not depend on the accumulator: they are requested before the fragment's
       // partial tiles are polled, so the epilogue itself never waits on memory.
       struct Side {
@@ -1175,11 +1236,11 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
         else pk_epi_residual(a, sd.rv, r, tile, lane, N, res_out, ss_out, ss_tiles);
       };
       for (int u = 0; u < nu; ++u) {
-        const PkUnit un = tab.u[ph][u];
+        const PkUnit un = tab.u[tph][u];
         const uint32_t buf = uc % kPkAccBufs;
         mbar_wait(&tail->tmem_full[buf], (uc / kPkAccBufs) & 1);
         tcgen05_fence_after();
-        if (wtid == 0) pk_ev(ev, 100 * ph + 12);
+        if (wtid == 0) pk_ev(ev, 100 * tph + 12);
         const uint32_t taddr = tmem_base + tlane + buf * uint32_t(p.r_tile);
         // exchange slot in global memory, or the park buffer in shared memory for a tile this CTA owns alone
         if (un.S == 1) {
@@ -1200,13 +1261,26 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
           }
         }
         tcgen05_fence_before();
-        if (wtid == 0) pk_ev(ev, 100 * ph + 13);
+        if (wtid == 0) pk_ev(ev, 100 * tph + 13);
         // Polling loads issued back to back can starve the SM's own pending stores (then every CTA waits for
         // everybody): the poll loop below pauses between attempts so that the store queue always drains.
         named_bar_sync(1, 128);
         if (wtid == 0) mbar_arrive(&tail->tmem_empty[buf]);
         if (un.S == 1) {
-          for (int r = ew; r < p.rows; r += 4) epilogue(*reinterpret_cast<const float4*>(park + r * 128 + lane * 4), side(r, un.tile), r, un.tile);
+          // four rows at a time: one row's epilogue is a single dependent chain (shuffles, exponentials, roundings)
+          for (int r0 = ew; r0 < p.rows; r0 += 16) {
+            float4 a4[4];
+            Side sd4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int r = r0 + 4 * j < p.rows ? r0 + 4 * j : r0;
+              a4[j] = *reinterpret_cast<const float4*>(park + r * 128 + lane * 4);
+              sd4[j] = side(r, un.tile);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (r0 + 4 * j < p.rows) epilogue(a4[j], sd4[j], r0 + 4 * j, un.tile);
+          }
           named_bar_sync(1, 128);  // the park buffer is rewritten by the next unit
         }
         ++uc;
@@ -1215,12 +1289,12 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
       // sentinel or data, so the reader simply re-requests a fragment until all of its words have arrived, then
       // puts the sentinel back for the next layer (the same thread reads the same words every layer).
       for (int u = 0; u < nu; ++u) {
-        const PkUnit un = tab.u[ph][u];
+        const PkUnit un = tab.u[tph][u];
         if (un.S == 1) continue;
         if (ph == PK_UP) {  // every warp of the CTA takes rows (the attention warps call the same routine)
-          if (wtid == 0) pk_ev(ev, 100 * ph + 14);
+          if (wtid == 0) pk_ev(ev, 100 * tph + 14);
           pk_finish_swiglu(&p, cta, un.tile, un.c_first, un.S, ew, 4 + kPkAttnWarps, lane);
-          if (wtid == 0) pk_ev(ev, 100 * ph + 15);
+          if (wtid == 0) pk_ev(ev, 100 * tph + 15);
           continue;
         }
         const int si = cta - un.c_first;
@@ -1255,7 +1329,7 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
                      __float_as_uint(tb[ss].z) != kPkSentinel && __float_as_uint(tb[ss].w) != kPkSentinel;
               if (__all_sync(0xffffffffu, ok)) break;
               pk_backoff();  // the missing fragments are still in flight somewhere: let stores (ours too) drain
-              if (clock64() - t_spin > 4000000000LL) mtx_wait_timeout(3, ph, un.tile);
+              if (clock64() - t_spin > 4000000000LL) mtx_wait_timeout(3, tph, un.tile);
             }
 #pragma unroll
             for (int ss = 0; ss < 8; ++ss) {
@@ -1278,10 +1352,9 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
       ev.on = l == 1;
 #pragma unroll 1  // one copy of the phase body
       for (int ph = 0; ph < 4; ++ph) {
-        if (ph == PK_QKV) gemm_phase(std::integral_constant<int, PK_QKV>{}, l);
-        else if (ph == PK_OPROJ) gemm_phase(std::integral_constant<int, PK_OPROJ>{}, l);
-        else if (ph == PK_UP) gemm_phase(std::integral_constant<int, PK_UP>{}, l);
-        else gemm_phase(std::integral_constant<int, PK_DOWN>{}, l);
+        if (ph == PK_QKV) gemm_phase(std::integral_constant<int, PK_QKV>{}, ph, l);
+        else if (ph == PK_UP) gemm_phase(std::integral_constant<int, PK_UP>{}, ph, l);
+        else gemm_phase(std::integral_constant<int, PK_DOWN>{}, ph, l);
         if (ph == PK_UP && up_shared) {  // the attention warps' share of the MLP-up rows is stored too
           asm volatile("bar.sync 4, %0;" ::"r"(128 + kPkAttnWarps * 32) : "memory");
         }
