@@ -461,7 +461,7 @@ __device__ __forceinline__ void pk_logits_store(const float* park, int ew, int l
 // exchange, see the GEMM phase) and runs the SwiGLU epilogue.  Out of line and shared by the epilogue warps and the
 // attention warps: MLP-up tiles are shared by two or three CTAs that each own 20-30 rows, so the finish is bound by
 // L2 round trips per row and every idle warp of the CTA takes rows.  Four rows x four parts are in flight per warp.
-__device__ __noinline__ void pk_finish_swiglu(const PkParams* pp, int cta, int tile, int c_first, int S, int w, int nw, int lane) {
+__device__ __noinline__ void pk_finish_swiglu(const PkParams* pp, const float* rstd, int cta, int tile, int c_first, int S, int w, int nw, int lane) {
   const PkParams& p = *pp;
   const int si = cta - c_first;
   const int r_begin = si * p.rows / S, r_end = (si + 1) * p.rows / S;
@@ -504,7 +504,10 @@ __device__ __noinline__ void pk_finish_swiglu(const PkParams* pp, int cta, int t
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (r + k * nw < r_end) pk_epi_swiglu(acc[k], r + k * nw, tile, lane, 2 * p.M, p.M, p.act);
+      if (r + k * nw < r_end) {
+        const float rs = rstd[r + k * nw];
+        pk_epi_swiglu(make_float4(acc[k].x * rs, acc[k].y * rs, acc[k].z * rs, acc[k].w * rs), r + k * nw, tile, lane, 2 * p.M, p.M, p.act);
+      }
   }
 }
 
@@ -1211,6 +1214,27 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
       const int N = ph == PK_QKV ? p.qkv_n : ph == PK_UP ? 2 * p.M : p.E;
       bf16* k_layer = p.k_cache + p.kv_layer_elems * layer;
       bf16* v_layer = p.v_cache + p.kv_layer_elems * layer;
+      if ((ph == PK_QKV || ph == PK_UP) && nu > 0) {
+        // rstd of every row from the per-tile sums of squares the previous epilogue left: two threads per row,
+        // eight independent loads each; off the critical path (the MMAs of the phase run meanwhile)
+        pk_wait_flag(&tail->bar_done, pk_need(layer, ph, p.L));
+        const float* ss = ph == PK_QKV ? p.ss_x : p.ss_h;
+        const int row = wtid >> 1, half = wtid & 1;
+        float tot = 0.0f;
+        if (row < p.rows) {
+          for (int t0 = half * 8; t0 < ss_tiles; t0 += 16) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = t0 + i < ss_tiles ? __ldcg(ss + (t0 + i) * kPkMaxRTile + row) : 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tot += v[i];
+          }
+        }
+        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+        if (half == 0 && row < p.r_tile) tail->rstd[row] = row < p.rows ? 1.0f / sqrtf(tot / float(p.E) + p.eps) : 0.0f;
+        named_bar_sync(1, 128);
+        if (ph == PK_UP && up_shared) asm volatile("bar.arrive 2, %0;" ::"r"(128 + kPkAttnWarps * 32) : "memory");  // attention warps read rstd too
+      }
       const bf16* resid = tph == PK_OPROJ ? p.x : p.h;
       bf16* res_out = tph == PK_OPROJ ? p.h : p.x;
       float* ss_out = tph == PK_OPROJ ? p.ss_h : p.ss_x;
@@ -1230,7 +1254,11 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
         else if (ph != PK_UP && n0 < N) sd.rv = __ldcg(reinterpret_cast<const uint2*>(resid + (long long)r * N + n0));
         return sd;
       };
-      auto epilogue = [&](const float4 a, const Side& sd, int r, int tile) {
+      auto epilogue = [&](float4 a, const Side& sd, int r, int tile) {
+        if (ph == PK_QKV || ph == PK_UP) {
+          const float rs = tail->rstd[r];
+          a.x *= rs; a.y *= rs; a.z *= rs; a.w *= rs;
+        }
         if (ph == PK_QKV) pk_epi_qkv(a, sd.q, r, tile, lane, p, k_layer, v_layer);
         else if (ph == PK_UP) pk_epi_swiglu(a, r, tile, lane, N, p.M, p.act);
         else pk_epi_residual(a, sd.rv, r, tile, lane, N, res_out, ss_out, ss_tiles);
@@ -1293,7 +1321,7 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
         if (un.S == 1) continue;
         if (ph == PK_UP) {  // every warp of the CTA takes rows (the attention warps call the same routine)
           if (wtid == 0) pk_ev(ev, 100 * tph + 14);
-          pk_finish_swiglu(&p, cta, un.tile, un.c_first, un.S, ew, 4 + kPkAttnWarps, lane);
+          pk_finish_swiglu(&p, tail->rstd, cta, un.tile, un.c_first, un.S, ew, 4 + kPkAttnWarps, lane);
           if (wtid == 0) pk_ev(ev, 100 * tph + 15);
           continue;
         }
@@ -1485,8 +1513,12 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
       }
     };
 
-    // normalizations.py:57-69 applied in place to the activation k-blocks TMA just delivered:
-    //   n = bf16(bf16(x * rstd) * scale)
+    // normalizations.py:57-69, reassociated: the per-feature scale is applied in place to the activation k-blocks TMA
+    // just delivered (n' = bf16(x * scale)); the per-row factor rstd multiplies the fp32 accumulator in the epilogue
+    // (dot(W, x * scale) * rstd).  The reference rounds x * rstd to bf16 before the scale; here that rounding is
+    // skipped (one rounding less, |rel. difference| <= 2^-9 per term before the dot product averages it out): the
+    // per-row factor then no longer sits between a tile's arrival and its MMA, nor does the phase start wait for
+    // the row statistics.
     auto transform_phase = [&](int ph, int layer) {
       const int nu = tab.n_units[ph];
       if (nu == 0) return;
@@ -1516,26 +1548,6 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
       }
       pk_wait_flag(&tail->bar_done, pk_need(layer, ph, p.L));
       if (atid == 0) pk_ev(ev, 100 * ph + 21);
-      const float* ss = ph == PK_QKV ? p.ss_x : p.ss_h;
-      {  // rstd of every row: two threads per row, eight independent loads each
-        const int row = atid >> 1, half = atid & 1;
-        float tot = 0.0f;
-        if (row < p.rows) {
-          for (int t0 = half * 8; t0 < ss_tiles; t0 += 16) {
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = t0 + i < ss_tiles ? __ldcg(ss + (t0 + i) * kPkMaxRTile + row) : 0.0f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) tot += v[i];
-          }
-        }
-        tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-        if (atid == 0) pk_ev(ev, 100 * ph + 25);
-        if (half == 0 && row < p.r_tile) tail->rstd[row] = row < p.rows ? 1.0f / sqrtf(tot / float(p.E) + p.eps) : 0.0f;
-      }
-      if (atid == 0) pk_ev(ev, 100 * ph + 26);
-      named_bar_sync(2, 128);
-      if (atid == 0) pk_ev(ev, 100 * ph + 27);
       // Each warp normalises whole k-blocks on its own (fill i of the phase belongs to warp i % 4), so the k-blocks
       // of a phase are processed in parallel and no CTA-level barrier sits between a tile's arrival and its MMA.
       int fi = 0;
@@ -1558,17 +1570,11 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {
                 const uint4 sc = (jj & 1) ? sc_b : sc_a;
-                const float r = tail->rstd[rq + 4 * (j0 + jj)];
-                // y = bf16(x * rstd) in fp32, then bf16(y * scale) as one packed bf16 multiply (the product of two
-                // bf16 values is exact in fp32, so the packed instruction rounds exactly once, like the reference)
-                const uint32_t y0 = pack_bf16x2(bf16_lo(raw[jj].x) * r, bf16_hi(raw[jj].x) * r);
-                const uint32_t y1 = pack_bf16x2(bf16_lo(raw[jj].y) * r, bf16_hi(raw[jj].y) * r);
-                const uint32_t y2 = pack_bf16x2(bf16_lo(raw[jj].z) * r, bf16_hi(raw[jj].z) * r);
-                const uint32_t y3 = pack_bf16x2(bf16_lo(raw[jj].w) * r, bf16_hi(raw[jj].w) * r);
-                const __nv_bfloat162 p0 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&y0), *reinterpret_cast<const __nv_bfloat162*>(&sc.x));
-                const __nv_bfloat162 p1 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&y1), *reinterpret_cast<const __nv_bfloat162*>(&sc.y));
-                const __nv_bfloat162 p2 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&y2), *reinterpret_cast<const __nv_bfloat162*>(&sc.z));
-                const __nv_bfloat162 p3 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&y3), *reinterpret_cast<const __nv_bfloat162*>(&sc.w));
+                // one packed bf16 multiply per feature pair: bf16(x * scale), rounded once
+                const __nv_bfloat162 p0 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&raw[jj].x), *reinterpret_cast<const __nv_bfloat162*>(&sc.x));
+                const __nv_bfloat162 p1 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&raw[jj].y), *reinterpret_cast<const __nv_bfloat162*>(&sc.y));
+                const __nv_bfloat162 p2 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&raw[jj].z), *reinterpret_cast<const __nv_bfloat162*>(&sc.z));
+                const __nv_bfloat162 p3 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&raw[jj].w), *reinterpret_cast<const __nv_bfloat162*>(&sc.w));
                 raw[jj] = make_uint4(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1),
                                      *reinterpret_cast<const uint32_t*>(&p2), *reinterpret_cast<const uint32_t*>(&p3));
               }
@@ -1614,9 +1620,10 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
         gemm_duty(ph, l);
         if (ph == PK_UP && up_shared) {
           __syncwarp();
+          asm volatile("bar.sync 2, %0;" ::"r"(128 + kPkAttnWarps * 32) : "memory");  // the epilogue warps have stored rstd
           for (int u = 0; u < tab.n_units[PK_UP]; ++u) {
             const PkUnit un = tab.u[PK_UP][u];
-            if (un.S > 1) pk_finish_swiglu(&p, cta, un.tile, un.c_first, un.S, 4 + aw, 4 + kPkAttnWarps, lane);
+            if (un.S > 1) pk_finish_swiglu(&p, tail->rstd, cta, un.tile, un.c_first, un.S, 4 + aw, 4 + kPkAttnWarps, lane);
           }
           fence_proxy_async_all();
           asm volatile("bar.arrive 4, %0;" ::"r"(128 + kPkAttnWarps * 32) : "memory");

@@ -95,3 +95,25 @@ for nm, kk in (("qkv", 2), ("oproj", 4), ("up", 5), ("down", 6)):
     lt /= L
     o2 = np.argsort(lt)
     print(f"{nm} lateness: median {np.median(lt):.2f} max {lt.max():.2f} latest CTAs", [(int(c), round(float(lt[c]), 1)) for c in o2[-6:]])
+
+# ---- attention phase of layer 1, all CTAs: when the tile loop ends, when the CTA's warps have met, when the
+# merges are done (events 500 / 610 / 611 / 501 of the first and the last attention warp; MTX_PK_EVENTS build) ----
+def _first(c, role, eid):
+    for i in range(32):
+        if int(evs[c, role, i, 0]) == eid and evs[c, role, i, 1] != 0:
+            return (evs[c, role, i, 1] - base) / 1e3
+    return np.nan
+if np.any(evs[:, 1, :, 0] == 610):
+    rel_qkv = (a[2 * 7 + 1].max() - base) / 1e3
+    for role, rn in ((1, "first attention warp"), (2, "last attention warp")):
+        st = {e: np.array([_first(c, role, e) for c in range(g)]) - rel_qkv for e in (500, 610, 611, 501)}
+        def q(x):
+            x = x[~np.isnan(x)]
+            return "min %.2f med %.2f p90 %.2f max %.2f" % (x.min(), np.median(x), np.percentile(x, 90), x.max()) if len(x) else "-"
+        print(f"attention, {rn} (us after the QKV barrier release):")
+        print("  loop start   ", q(st[500]))
+        print("  loop end     ", q(st[610]))
+        print("  warps met    ", q(st[611]))
+        print("  merges done  ", q(st[501]))
+    arr = (a[2 * 8] - base) / 1e3 - rel_qkv
+    print("  barrier arrival min %.2f med %.2f max %.2f; release %.2f" % (arr.min(), np.median(arr), arr.max(), (a[2 * 8 + 1].max() - base) / 1e3 - rel_qkv))
