@@ -419,6 +419,54 @@ bool pk_fill_phase(std::vector<PkTable>& tabs, int ph, int n, int k, bool allow_
   // the extra streaming.  CTAs without a tile run ahead into the next phase's weights.  (The exchange cost grows with
   // the number of rows, so steps of few rows use the second table set, built without this rule.)
   if (allow_whole_tile && uniform_s == 0 && n_tiles <= n_ctas && kbt <= total / n_ctas + env_int("MTX_PK_WHOLE_TILE_SLACK", 12)) uniform_s = 1;
+  // MLP up with between one and two CTAs per tile: CTA t < n_tiles OWNS tile t and reduces its first k_own k-blocks;
+  // the other CTAs (helpers) share the remaining k-blocks of all tiles in contiguous ranges and hand their partials
+  // over through the exchange.  Helpers get less work than owners, so their partials are in L2 by the time an owner
+  // has finished its own stream: the owner's accumulator never leaves the chip, it waits for nobody, and it streams
+  // k_own instead of all k-blocks (a single SM pulls ~40 GB/s, which bounds the whole-tile variant).
+  const int k_own_env = env_int("MTX_PK_UP_OWNER_KB", -1);
+  if (ph == PK_UP && allow_whole_tile && k_own_env != 0 && n_tiles < n_ctas && 2 * n_tiles > n_ctas && kbt >= 8) {
+    int k_own = k_own_env > 0 ? k_own_env : int((total + n_ctas - 1) / n_ctas) + 2;
+    if (k_own > kbt - 1) k_own = kbt - 1;
+    const int helpers = n_ctas - n_tiles, kh = kbt - k_own;
+    const long long total_h = (long long)n_tiles * kh;
+    for (int c = 0; c < n_ctas; ++c) {
+      tabs[c].n_units[ph] = 0;
+      tabs[c].kbs[ph] = 0;
+    }
+    for (int i = 0; i < helpers; ++i) {
+      PkTable& t = tabs[n_tiles + i];
+      long long lo = i * total_h / helpers, hi = (i + 1) * total_h / helpers;
+      while (lo < hi) {
+        const int tile = int(lo / kh);
+        long long end = (long long)(tile + 1) * kh;
+        if (end > hi) end = hi;
+        if (t.n_units[ph] >= kPkMaxUnits) return false;
+        PkUnit& u = t.u[ph][t.n_units[ph]++];
+        u.tile = tile;
+        u.kb0 = k_own + int(lo - (long long)tile * kh);
+        u.kb1 = k_own + int(end - (long long)tile * kh);
+        u.c_first = tile;
+        u.S = 0;
+        t.kbs[ph] += u.kb1 - u.kb0;
+        if (first[tile] < 0) first[tile] = n_tiles + i;
+        ++count[tile];
+        lo = end;
+      }
+    }
+    for (int tile = 0; tile < n_tiles; ++tile) {
+      PkTable& t = tabs[tile];
+      PkUnit& u = t.u[ph][t.n_units[ph]++];
+      u.tile = tile;
+      u.kb0 = 0;
+      u.kb1 = k_own;
+      u.c_first = first[tile];
+      u.S = -count[tile];
+      t.kbs[ph] = k_own;
+      if (count[tile] < 1 || count[tile] > kPkMaxSplit) return false;
+    }
+    return true;
+  }
   for (int c = 0; c < n_ctas; ++c) {
     PkTable& t = tabs[c];
     t.n_units[ph] = 0;

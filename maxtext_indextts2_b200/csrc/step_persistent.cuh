@@ -299,26 +299,20 @@ __device__ __forceinline__ void pk_epi_residual(const float4 a, const uint2 rv, 
 }
 
 // linears.py:425-476 with mlp_activations [silu, linear]: rows of w01 are interleaved 16 at a time (gate, value),
-// so the value of a gate feature sits 16 features (4 lanes) further.
+// so the value of a gate feature sits 16 features (4 lanes) further.  The two lanes of a (gate, value) pair split
+// the four outputs between them (two shuffles, two outputs per lane): these epilogues run as one dependent chain
+// per warp, their length in instructions is their cost.
 __device__ __forceinline__ void pk_epi_swiglu(const float4 a, int r, int tile, int lane, int N2, int M, bf16* act) {
-  const float bx = __shfl_xor_sync(0xffffffffu, a.x, 4), by = __shfl_xor_sync(0xffffffffu, a.y, 4);
-  const float bz = __shfl_xor_sync(0xffffffffu, a.z, 4), bw = __shfl_xor_sync(0xffffffffu, a.w, 4);
-  const int n0 = tile * 128 + lane * 4;
-  if ((lane & 4) == 0 && n0 < N2) {
-    float g[4], v[4], sg[4], t[4];
-    bf16r2(a.x, a.y, g[0], g[1]);
-    bf16r2(a.z, a.w, g[2], g[3]);
-    bf16r2(bx, by, v[0], v[1]);
-    bf16r2(bz, bw, v[2], v[3]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) sg[i] = __fdividef(1.0f, 1.0f + __expf(-g[i]));
-    bf16r2(sg[0], sg[1], sg[0], sg[1]);
-    bf16r2(sg[2], sg[3], sg[2], sg[3]);
-    bf16r2(g[0] * sg[0], g[1] * sg[1], t[0], t[1]);
-    bf16r2(g[2] * sg[2], g[3] * sg[3], t[2], t[3]);
-    const int m0 = tile * 64 + (lane >> 3) * 16 + (lane & 3) * 4;
-    *reinterpret_cast<uint2*>(act + (long long)r * M + m0) = pack_bf16x4(t[0] * v[0], t[1] * v[1], t[2] * v[2], t[3] * v[3]);
-  }
+  const bool gate_lane = (lane & 4) == 0;
+  const float r0 = __shfl_xor_sync(0xffffffffu, gate_lane ? a.z : a.x, 4), r1 = __shfl_xor_sync(0xffffffffu, gate_lane ? a.w : a.y, 4);
+  if (tile * 128 + (lane & ~4) * 4 >= N2) return;
+  float g0, g1, v0, v1, s0, s1, t0, t1;
+  bf16r2(gate_lane ? a.x : r0, gate_lane ? a.y : r1, g0, g1);
+  bf16r2(gate_lane ? r0 : a.z, gate_lane ? r1 : a.w, v0, v1);
+  bf16r2(__fdividef(1.0f, 1.0f + __expf(-g0)), __fdividef(1.0f, 1.0f + __expf(-g1)), s0, s1);
+  bf16r2(g0 * s0, g1 * s1, t0, t1);
+  const int m0 = tile * 64 + (lane >> 3) * 16 + (lane & 3) * 4 + (gate_lane ? 0 : 2);
+  *reinterpret_cast<uint32_t*>(act + (long long)r * M + m0) = pack_bf16x2(t0 * v0, t1 * v1);
 }
 
 // Side inputs of the QKV epilogue for one row fragment: they do not depend on the accumulator, so they are
@@ -457,21 +451,41 @@ __device__ __forceinline__ void pk_logits_store(const float* park, int ew, int l
   }
 }
 
-// Finishes the rows r_begin + w, r_begin + w + nw, ... of a shared MLP-up tile: sums the S partial tiles (flag-in-data
-// exchange, see the GEMM phase) and runs the SwiGLU epilogue.  Out of line and shared by the epilogue warps and the
-// attention warps: MLP-up tiles are shared by two or three CTAs that each own 20-30 rows, so the finish is bound by
-// L2 round trips per row and every idle warp of the CTA takes rows.  Four rows x four parts are in flight per warp.
-__device__ __noinline__ void pk_finish_swiglu(const PkParams* pp, const float* rstd, int cta, int tile, int c_first, int S, int w, int nw, int lane) {
+// Finishes rows r_begin + w, r_begin + w + nw, ... < r_end of a shared MLP-up tile: sums the partial tiles of `parts`
+// CTAs starting at c_first (flag-in-data exchange, see the GEMM phase), adds the CTA's own accumulator parked in
+// shared memory (`own`, row-major, or null when the CTA's part went through the exchange like everybody's),
+// applies the row's rstd and runs the SwiGLU epilogue.  Out of line and shared by the epilogue warps and the
+// attention warps: the finish is bound by L2 round trips per row, so every idle warp of the CTA takes rows.
+// Four rows x four parts are in flight per warp.
+__device__ __noinline__ void pk_finish_swiglu(const PkParams* pp, const float* rstd, const float* own, int tile, int c_first, int parts, int r_begin,
+                                              int r_end, int w, int nw, int lane) {
   const PkParams& p = *pp;
-  const int si = cta - c_first;
-  const int r_begin = si * p.rows / S, r_end = (si + 1) * p.rows / S;
+  if (parts == 0) {  // the CTA holds the whole reduction: nothing to fetch, two rows at a time
+    const float* src = own + lane * 4;
+    int r = r_begin + w;
+    for (; r + nw < r_end; r += 2 * nw) {
+      const float4 a = *reinterpret_cast<const float4*>(src + r * 128), b = *reinterpret_cast<const float4*>(src + (r + nw) * 128);
+      const float ra = rstd[r], rb = rstd[r + nw];
+      pk_epi_swiglu(make_float4(a.x * ra, a.y * ra, a.z * ra, a.w * ra), r, tile, lane, 2 * p.M, p.M, p.act);
+      pk_epi_swiglu(make_float4(b.x * rb, b.y * rb, b.z * rb, b.w * rb), r + nw, tile, lane, 2 * p.M, p.M, p.act);
+    }
+    if (r < r_end) {
+      const float4 a = *reinterpret_cast<const float4*>(src + r * 128);
+      const float ra = rstd[r];
+      pk_epi_swiglu(make_float4(a.x * ra, a.y * ra, a.z * ra, a.w * ra), r, tile, lane, 2 * p.M, p.M, p.act);
+    }
+    return;
+  }
   float* src0 = p.part_ws + (long long)(c_first * 4 + (tile & 3)) * kPkSlotFloats + lane * 4;
   const float sent = __uint_as_float(kPkSentinel);
   for (int r = r_begin + w; r < r_end; r += 4 * nw) {
     float4 acc[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s0 = 0; s0 < S; s0 += 4) {
+    for (int k = 0; k < 4; ++k) {
+      acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (own != nullptr && r + k * nw < r_end) acc[k] = *reinterpret_cast<const float4*>(own + (r + k * nw) * 128 + lane * 4);
+    }
+    for (int s0 = 0; s0 < parts; s0 += 4) {
       float4 t[4][4];
       const long long t_spin = clock64();
       for (;;) {
@@ -481,7 +495,7 @@ __device__ __noinline__ void pk_finish_swiglu(const PkParams* pp, const float* r
 #pragma unroll
           for (int ss = 0; ss < 4; ++ss) {
             t[k][ss] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r + k * nw < r_end && s0 + ss < S) t[k][ss] = ld_poll_f4(src0 + (long long)(s0 + ss) * 4 * kPkSlotFloats + (r + k * nw) * 128);
+            if (r + k * nw < r_end && s0 + ss < parts) t[k][ss] = ld_poll_f4(src0 + (long long)(s0 + ss) * 4 * kPkSlotFloats + (r + k * nw) * 128);
           }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -497,7 +511,7 @@ __device__ __noinline__ void pk_finish_swiglu(const PkParams* pp, const float* r
       for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int ss = 0; ss < 4; ++ss) {
-          if (r + k * nw < r_end && s0 + ss < S)
+          if (r + k * nw < r_end && s0 + ss < parts)
             *reinterpret_cast<float4*>(src0 + (long long)(s0 + ss) * 4 * kPkSlotFloats + (r + k * nw) * 128) = make_float4(sent, sent, sent, sent);
           acc[k].x += t[k][ss].x; acc[k].y += t[k][ss].y; acc[k].z += t[k][ss].z; acc[k].w += t[k][ss].w;
         }
@@ -509,6 +523,26 @@ __device__ __noinline__ void pk_finish_swiglu(const PkParams* pp, const float* r
         pk_epi_swiglu(make_float4(acc[k].x * rs, acc[k].y * rs, acc[k].z * rs, acc[k].w * rs), r + k * nw, tile, lane, 2 * p.M, p.M, p.act);
       }
   }
+}
+// One unit of the MLP-up phase as seen by the finishing warps: S > 1, the tile is shared evenly (every sharer dumps
+// its partial and finishes a row slice); S < 0, this CTA owns the tile (its own accumulator is parked on chip,
+// -S helper CTAs starting at c_first contribute partials, the owner finishes every row); S == 0, helper (dumps
+// only); S == 1, the CTA holds the whole reduction.
+__device__ __forceinline__ void pk_finish_up_unit(const PkParams* pp, const float* rstd, const float* park, const PkUnit& un, bool solo, int cta, int w,
+                                                  int nw, int lane) {
+  if (un.S > 1) {
+    const int si = cta - un.c_first;
+    pk_finish_swiglu(pp, rstd, nullptr, un.tile, un.c_first, un.S, si * pp->rows / un.S, (si + 1) * pp->rows / un.S, w, nw, lane);
+  } else if (un.S < 0 || (un.S == 1 && solo)) {  // (solo: a whole tile that is the CTA's only unit of the phase, see pk_up_all_warps)
+    pk_finish_swiglu(pp, rstd, park, un.tile, un.c_first, un.S < 0 ? -un.S : 0, 0, pp->rows, w, nw, lane);
+  }
+}
+// MLP up: do all warps of the CTA finish its units?  Yes when a tile is shared, and also for a single whole tile:
+// one row's SwiGLU epilogue is a dependent chain of ~60 instructions, 64 rows on four warps take ~3 us.
+__device__ __forceinline__ bool pk_up_all_warps(const PkTable& tab) {
+  bool any = tab.n_units[PK_UP] == 1 && tab.u[PK_UP][0].S == 1;
+  for (int u = 0; u < tab.n_units[PK_UP]; ++u) any = any || tab.u[PK_UP][u].S > 1 || tab.u[PK_UP][u].S < 0;
+  return any;
 }
 
 // ---- attention: stream-K over 64-row KV tiles -----------------------------------------------------
@@ -1161,7 +1195,8 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
     uint32_t uc = 0, nbar = 0;
     PkEv ev = pk_ev_make(p, 0);
     bool up_shared = false;  // this CTA shares MLP-up tiles with other CTAs: all its warps help to finish them
-    for (int u = 0; u < tab.n_units[PK_UP]; ++u) up_shared = up_shared || tab.u[PK_UP][u].S > 1;
+    up_shared = pk_up_all_warps(tab);
+    const bool up_solo = tab.n_units[PK_UP] == 1 && tab.u[PK_UP][0].S == 1;
 
     griddep_wait();
     if (p.trace && wtid == 0) p.trace[gridDim.x + blockIdx.x] = (long long)globaltimer_ns();  // "barrier 0 release" = start
@@ -1233,7 +1268,6 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
         tot += __shfl_xor_sync(0xffffffffu, tot, 1);
         if (half == 0 && row < p.r_tile) tail->rstd[row] = row < p.rows ? 1.0f / sqrtf(tot / float(p.E) + p.eps) : 0.0f;
         named_bar_sync(1, 128);
-        if (ph == PK_UP && up_shared) asm volatile("bar.arrive 2, %0;" ::"r"(128 + kPkAttnWarps * 32) : "memory");  // attention warps read rstd too
       }
       const bf16* resid = tph == PK_OPROJ ? p.x : p.h;
       bf16* res_out = tph == PK_OPROJ ? p.h : p.x;
@@ -1271,7 +1305,7 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
         if (wtid == 0) pk_ev(ev, 100 * tph + 12);
         const uint32_t taddr = tmem_base + tlane + buf * uint32_t(p.r_tile);
         // exchange slot in global memory, or the park buffer in shared memory for a tile this CTA owns alone
-        if (un.S == 1) {
+        if (un.S == 1 || un.S < 0) {
           for (int c = 0; c * 16 < p.rows; ++c) {
             float v[16];
             tmem_ld_x16(taddr + uint32_t(c * 16), v);
@@ -1294,7 +1328,7 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
         // everybody): the poll loop below pauses between attempts so that the store queue always drains.
         named_bar_sync(1, 128);
         if (wtid == 0) mbar_arrive(&tail->tmem_empty[buf]);
-        if (un.S == 1) {
+        if (un.S == 1 && !(ph == PK_UP && up_solo)) {
           // four rows at a time: one row's epilogue is a single dependent chain (shuffles, exponentials, roundings)
           for (int r0 = ew; r0 < p.rows; r0 += 16) {
             float4 a4[4];
@@ -1316,12 +1350,14 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
       // Finish the row slices this CTA owns.  The exchange has no flags: a word of the workspace is either the
       // sentinel or data, so the reader simply re-requests a fragment until all of its words have arrived, then
       // puts the sentinel back for the next layer (the same thread reads the same words every layer).
+      // MLP up: the attention warps help to finish; they need rstd and this CTA's parked accumulator
+      if (ph == PK_UP && up_shared) asm volatile("bar.arrive 2, %0;" ::"r"(128 + kPkAttnWarps * 32) : "memory");
       for (int u = 0; u < nu; ++u) {
         const PkUnit un = tab.u[tph][u];
-        if (un.S == 1) continue;
+        if ((un.S == 1 && !(ph == PK_UP && up_solo)) || un.S == 0) continue;
         if (ph == PK_UP) {  // every warp of the CTA takes rows (the attention warps call the same routine)
           if (wtid == 0) pk_ev(ev, 100 * tph + 14);
-          pk_finish_swiglu(&p, tail->rstd, cta, un.tile, un.c_first, un.S, ew, 4 + kPkAttnWarps, lane);
+          pk_finish_up_unit(&p, tail->rstd, park, un, up_solo, cta, ew, 4 + kPkAttnWarps, lane);
           if (wtid == 0) pk_ev(ev, 100 * tph + 15);
           continue;
         }
@@ -1484,7 +1520,7 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
       if (tab.u[PK_QKV][u].S == 1) may_prime = false;
 
     bool up_shared = false;  // see the epilogue warps
-    for (int u = 0; u < tab.n_units[PK_UP]; ++u) up_shared = up_shared || tab.u[PK_UP][u].S > 1;
+    up_shared = pk_up_all_warps(tab);
     PkCursor cur;  // shared fill sequence (activation producer and normaliser walk it in step with the weights)
     pk_cursor_init(cur);
 
@@ -1620,11 +1656,9 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
         gemm_duty(ph, l);
         if (ph == PK_UP && up_shared) {
           __syncwarp();
-          asm volatile("bar.sync 2, %0;" ::"r"(128 + kPkAttnWarps * 32) : "memory");  // the epilogue warps have stored rstd
-          for (int u = 0; u < tab.n_units[PK_UP]; ++u) {
-            const PkUnit un = tab.u[PK_UP][u];
-            if (un.S > 1) pk_finish_swiglu(&p, tail->rstd, cta, un.tile, un.c_first, un.S, 4 + aw, 4 + kPkAttnWarps, lane);
-          }
+          asm volatile("bar.sync 2, %0;" ::"r"(128 + kPkAttnWarps * 32) : "memory");  // rstd and the parked accumulator are in place
+          for (int u = 0; u < tab.n_units[PK_UP]; ++u)
+            pk_finish_up_unit(&p, tail->rstd, park, tab.u[PK_UP][u], tab.n_units[PK_UP] == 1, cta, 4 + aw, 4 + kPkAttnWarps, lane);
           fence_proxy_async_all();
           asm volatile("bar.arrive 4, %0;" ::"r"(128 + kPkAttnWarps * 32) : "memory");
         }

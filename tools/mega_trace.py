@@ -117,3 +117,19 @@ if np.any(evs[:, 1, :, 0] == 610):
         print("  merges done  ", q(st[501]))
     arr = (a[2 * 8] - base) / 1e3 - rel_qkv
     print("  barrier arrival min %.2f med %.2f max %.2f; release %.2f" % (arr.min(), np.median(arr), arr.max(), (a[2 * 8 + 1].max() - base) / 1e3 - rel_qkv))
+
+# ---- epilogue-warp events of layer 1 over all CTAs: id -> distribution of the n-th occurrence (us after base) ----
+if np.any(evs[:, 0, :, 0] != 0):
+    from collections import defaultdict
+    occ = defaultdict(list)
+    for c in range(g):
+        seen = defaultdict(int)
+        for i in range(32):
+            eid, tm = int(evs[c, 0, i, 0]), evs[c, 0, i, 1]
+            if tm == 0: break
+            occ[(eid, seen[eid])].append((tm - base) / 1e3)
+            seen[eid] += 1
+    print("epilogue-warp events (id, occurrence): CTAs, min / median / max us after base")
+    for key in sorted(occ, key=lambda k: np.median(occ[k])):
+        v = np.array(occ[key])
+        print(f"  {key[0]:4d}#{key[1]}: n={len(v):3d}  {v.min():7.2f} {np.median(v):7.2f} {v.max():7.2f}")
