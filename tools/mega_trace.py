@@ -133,3 +133,15 @@ if np.any(evs[:, 0, :, 0] != 0):
     for key in sorted(occ, key=lambda k: np.median(occ[k])):
         v = np.array(occ[key])
         print(f"  {key[0]:4d}#{key[1]}: n={len(v):3d}  {v.min():7.2f} {np.median(v):7.2f} {v.max():7.2f}")
+
+# per-CTA arrays for offline analysis
+try:
+    np.save("gpurun_out/attn_lateness.npy", late)
+    if np.any(evs[:, 1, :, 0] == 610):
+        arrs = {}
+        for role in (1, 2):
+            for e in (500, 610, 611, 501):
+                arrs[f"r{role}_{e}"] = np.array([_first(c, role, e) for c in range(g)]) - rel_qkv
+        np.savez("gpurun_out/attn_events.npz", **arrs)
+except Exception as ex:  # noqa
+    print("could not save arrays:", ex)
