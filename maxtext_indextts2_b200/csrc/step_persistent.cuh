@@ -93,10 +93,17 @@ struct PkTail {
   // attention: this CTA's warps own contiguous runs of KV tiles, the same for every layer of the step
   int a_count[kPkAttnWarps];
   int a_tail[kPkAttnWarps];               // part slot (pair * kPkMaxParts + ordinal) of the warp's tail segment, -1: none
-  int a_head[4];                          // the pair this CTA merges for other CTAs: pair (-1: none), row * 64 + kv head, first warp, parts
+  // merge plan of the CTA (built once per step: the partition does not change between layers): one job per pair
+  // that starts in this CTA and is cut between its warps or continues in later CTAs
+  int a_njobs;
+  struct Job {
+    int pair, row, head;       // (row, kv head) and pair = row * hkv + head
+    int n_src;                 // partials parked on chip: src[i] = w (warp w's K buffer) or 8 + w (warp w's slot)
+    int src[kPkAttnWarps];
+    int n_parts;               // partials of later CTAs' warps in the pair's L2 workspace
+  } a_jobs[kPkAttnWarps + 1];
   int2 a_list[kPkAttnWarps][kPkAttnListMax];  // .x = cache row of the tile (layer 0), .y = PkAttnMeta bits
-  int4 a_seg[kPkAttnWarps][2];                // partial segments of the current layer: .x = pair (-1: none), .y = flags
-  float a_slot[kPkAttnWarps][kPkAttnSlotFloats];  // partial of a warp's first segment (its K/V buffers stay busy)
+  alignas(16) float a_slot[kPkAttnWarps][kPkAttnSlotFloats];  // partial of a warp's first segment (its K/V buffers stay busy)
   PkTable tab;
 };
 
@@ -142,17 +149,19 @@ struct PkEv {
   long long* base;
   int n;
   bool on;
+  bool brief;  // log only the end of the attention tile loop (610) and of the merges (501): fits every other layer
 };
 __device__ __forceinline__ PkEv pk_ev_make(const PkParams& p, int role) {
   PkEv e;
   e.base = p.trace ? p.trace + 2 * 200 * (long long)gridDim.x + ((long long)blockIdx.x * 3 + role) * 64 : nullptr;
   e.n = 0;
   e.on = false;
+  e.brief = false;
   return e;
 }
 __device__ __forceinline__ void pk_ev(PkEv& e, int id) {
 #ifdef MTX_PK_EVENTS  // per-role event log (tools/mega_trace.py); compiled out by default to keep the kernel small
-  if (e.base != nullptr && e.on && e.n < 32) {
+  if (e.base != nullptr && e.on && e.n < 32 && (!e.brief || id == 610 || id == 501)) {
     e.base[2 * e.n] = id;
     e.base[2 * e.n + 1] = (long long)globaltimer_ns();
     ++e.n;
@@ -642,7 +651,6 @@ __device__ __forceinline__ void pk_attn_build_list(const PkParams& p, PkTail* ta
   const bool pair_mode = p.attn_info[2] != 0;  // CTA c owns the whole pair c (few short pairs: nothing crosses CTAs)
   const int R = p.T - p.P;
   int n = 0, tail_slot = -1;
-  int head[4] = {-1, 0, 0, 0};
   if (cta < nc && total > 0) {
     int clo = int((long long)cta * total / nc), chi = int((long long)(cta + 1) * total / nc);
     if (pair_mode) {
@@ -681,30 +689,44 @@ __device__ __forceinline__ void pk_attn_build_list(const PkParams& p, PkTail* ta
         pk_attn_next(pos, p, tail, R);
       }
     }
-    if (aw == 0 && !pair_mode && chi > clo) {
-      // the pair of the CTA's last tile: if it continues in later CTAs and began here, this CTA merges it
-      PkAttnPos pos;
-      pk_attn_seek(pos, chi - 1, p, tail, R, lane);
-      const int g_first = chi - 1 - pos.t;
-      if (pos.t != pos.nt - 1 && g_first >= clo) {
-        int w_a = 0;
-        while (w_a < kPkAttnWarps - 1 && clo + (w_a + 1) * (chi - clo) / kPkAttnWarps <= g_first) ++w_a;
-        head[0] = pos.r * p.hkv + pos.h;
-        head[1] = pos.r * 64 + pos.h;
-        head[2] = w_a;
-        head[3] = pk_count_warps(cta + 1, g_first + pos.nt, nc, total);
+    if (aw == 0) {
+      // Merge plan.  Walk the pairs that start inside [clo, chi); a pair that leaves the warp it starts in needs a
+      // merge.  Its partial in warp w is w's last segment (parked in w's K buffer) when it runs to the end of w's
+      // range, else w's first segment (parked in w's slot).
+      int nj = 0, g = clo;
+      while (g < chi) {
+        PkAttnPos pos;
+        pk_attn_seek(pos, g, p, tail, R, lane);
+        const int g_first = g - pos.t, g_end = g_first + pos.nt;
+        if (g_first >= clo) {
+          int w_a = 0;
+          while (w_a < kPkAttnWarps - 1 && clo + (w_a + 1) * (chi - clo) / kPkAttnWarps <= g_first) ++w_a;
+          if (g_end > clo + (w_a + 1) * (chi - clo) / kPkAttnWarps && nj < kPkAttnWarps + 1) {
+            PkTail::Job jb;
+            jb.pair = pos.r * p.hkv + pos.h;
+            jb.row = pos.r;
+            jb.head = pos.h;
+            jb.n_src = 0;
+            for (int w = w_a; w < kPkAttnWarps; ++w) {
+              const int wl = clo + w * (chi - clo) / kPkAttnWarps, wh = clo + (w + 1) * (chi - clo) / kPkAttnWarps;
+              if (wl >= g_end) break;
+              if (wh > wl) jb.src[jb.n_src++] = wh <= g_end ? w : 8 + w;
+            }
+            jb.n_parts = g_end > chi ? pk_count_warps(cta + 1, g_end, nc, total) : 0;
+            if (lane == 0) tail->a_jobs[nj] = jb;
+            ++nj;
+          }
+        }
+        g = g_end;
       }
+      if (lane == 0) tail->a_njobs = nj;
     }
+  } else if (aw == 0 && lane == 0) {
+    tail->a_njobs = 0;
   }
   if (lane == 0) {
     tail->a_count[aw] = n;
     tail->a_tail[aw] = tail_slot;
-  }
-  if (aw == 0 && lane == 0) {
-    tail->a_head[0] = head[0];
-    tail->a_head[1] = head[1];
-    tail->a_head[2] = head[2];
-    tail->a_head[3] = head[3];
   }
 }
 
@@ -728,10 +750,6 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
   const int n = tail->a_count[aw];
   const int2* list = tail->a_list[aw];
 
-  if (lane == 0) {
-    tail->a_seg[aw][0].x = -1;
-    tail->a_seg[aw][1].x = -1;
-  }
   if (n > 0 && !primed && lane == 0) {
     fence_proxy_async_all();  // K/V rows appended by the QKV epilogue (generic stores) are read through TMA
     const int row0 = layer_row + list[0].x;
@@ -916,142 +934,92 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
           if (h0 < G) *reinterpret_cast<float2*>(dst + G * D + h0 * 2) = make_float2(m0, l0);
           if (h0 + 1 < G) *reinterpret_cast<float2*>(dst + G * D + (h0 + 1) * 2) = make_float2(m1, l1);
         }
-        if (lane == 0 && !to_l2) {
-          const int flags = (seg_first ? 1 : 0) | ((meta & PKA_PAIR_LAST) ? 2 : 0);
-          tail->a_seg[aw][final_seg ? 1 : 0] = make_int4(r * p.hkv + h, flags, r, h);
-        }
       }
     }
   }
 
-  // ---- phase 2: merge the partial segments of this CTA ----
+  // ---- phase 2: the CTA's merge jobs (static plan, see pk_attn_build_list) ----
   if (lane == 0) pk_ev(ev, 610);
   named_bar_sync(3, kPkAttnWarps * 32);
   if (lane == 0) pk_ev(ev, 611);
+  // One thread per (head, 4 dims) unit of a job, so 160 / (16 G) jobs run side by side; a thread folds the job's
+  // on-chip partials, then the parts of later CTAs' warps from L2 (flag-in-data: a word is the sentinel or data;
+  // they were written during those warps' tile loops, so normally all are present), four parts per round trip.
+  // Fixed order: deterministic.  A thread puts the words it has read back to the sentinel.
+  const int n_units = G * (D / 4);
+  const int t = aw * 32 + lane;
+  const int lanes = (kPkAttnWarps * 32) / n_units;  // jobs in flight
+  const int jl = t / n_units, unit = t - jl * n_units;
+  const int gq = unit / (D / 4), d4 = unit - gq * (D / 4);
   const int stride = (G * D + 2 * G + 3) & ~3;
-
-  // (a) The pair this CTA merges for later CTAs: one thread per (head, 4 dims) unit.  Sources: the K buffers of
-  // the warps from the pair's first warp on (each parked its last segment there), then the tail warps' parts in
-  // L2 (flag-in-data: a word is the sentinel or data; written during the other CTAs' tile loops, so normally all
-  // present already), four parts per round trip.  Fixed order: deterministic.
-  if (tail->a_head[0] >= 0 && aw * 32 < G * (D / 4)) {  // (whole warps: they meet again before the flags are reset)
-    const int unit = aw * 32 + lane;
-    const bool act = unit < G * (D / 4);
-    const int pair = tail->a_head[0], r = tail->a_head[1] >> 6, h = tail->a_head[1] & 63, n_parts = act ? tail->a_head[3] : 0;
-    const int gq = act ? unit / (D / 4) : 0, d4 = unit - gq * (D / 4);
-    float M = -INFINITY, Ls = 0.0f;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto fold = [&](const float2 ml, const float4 o4) {
-      const float Mn = fmaxf(M, ml.x);
-      const float so = ex2_approx((M - Mn) * kLog2e), sn = ex2_approx((ml.x - Mn) * kLog2e);
-      Ls = Ls * so + ml.y * sn;
-      acc.x = acc.x * so + o4.x * sn; acc.y = acc.y * so + o4.y * sn;
-      acc.z = acc.z * so + o4.z * sn; acc.w = acc.w * so + o4.w * sn;
-      M = Mn;
-    };
-    for (int w = tail->a_head[2]; w < kPkAttnWarps; ++w) {
-      if (tail->a_count[w] == 0 || !act) continue;
-      const float* src = reinterpret_cast<const float*>(attn_tiles + w * 2 * 8192);
-      fold(*reinterpret_cast<const float2*>(src + G * D + gq * 2), *reinterpret_cast<const float4*>(src + gq * D + d4 * 4));
-    }
-    float* gbase = p.attn_part_o + (long long)pair * kPkMaxParts * stride;
-    const float sent = __uint_as_float(kPkSentinel);
-    for (int c0 = 0; c0 < n_parts; c0 += 4) {
+  const float sent = __uint_as_float(kPkSentinel);
+  const uint32_t head_mask = 0xFFFFu << (lane & 16);  // the 16 threads of a head sit in one half warp
+  if (jl < lanes) {
+    for (int j = jl; j < tail->a_njobs; j += lanes) {
+      const int n_src = tail->a_jobs[j].n_src, n_parts = tail->a_jobs[j].n_parts, pair = tail->a_jobs[j].pair;
+      float M = -INFINITY, Ls = 0.0f;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto fold = [&](const float2 ml, const float4 o4) {
+        const float Mn = fmaxf(M, ml.x);
+        const float so = ex2_approx((M - Mn) * kLog2e), sn = ex2_approx((ml.x - Mn) * kLog2e);
+        Ls = Ls * so + ml.y * sn;
+        acc.x = acc.x * so + o4.x * sn; acc.y = acc.y * so + o4.y * sn;
+        acc.z = acc.z * so + o4.z * sn; acc.w = acc.w * so + o4.w * sn;
+        M = Mn;
+      };
+      float* gbase = p.attn_part_o + (long long)pair * kPkMaxParts * stride;
+      // the first round of remote parts is requested before the on-chip partials are folded
       float2 ml[4];
       float4 o4[4];
-      const long long t_spin = clock64();
-      for (;;) {
-        bool ok = true;
+      auto request = [&](int c0) {
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc)
           if (c0 + cc < n_parts) {
             const float* part = gbase + (long long)(c0 + cc) * stride;
             ml[cc] = ld_poll_f2(part + G * D + gq * 2);
             o4[cc] = ld_poll_f4(part + gq * D + d4 * 4);
-            ok = ok && __float_as_uint(ml[cc].x) != kPkSentinel && __float_as_uint(ml[cc].y) != kPkSentinel &&
-                 __float_as_uint(o4[cc].x) != kPkSentinel && __float_as_uint(o4[cc].y) != kPkSentinel &&
-                 __float_as_uint(o4[cc].z) != kPkSentinel && __float_as_uint(o4[cc].w) != kPkSentinel;
           }
-        if (ok) break;
-        pk_backoff();
-        if (clock64() - t_spin > 4000000000LL) mtx_wait_timeout(4, pair, c0);
+      };
+      request(0);
+      for (int c = 0; c < n_src; ++c) {  // on-chip partials, folded like the remote ones (online rescaling)
+        const int code = tail->a_jobs[j].src[c];
+        const float* src = code < 8 ? reinterpret_cast<const float*>(attn_tiles + code * 2 * 8192) : tail->a_slot[code - 8];
+        fold(*reinterpret_cast<const float2*>(src + G * D + gq * 2), *reinterpret_cast<const float4*>(src + gq * D + d4 * 4));
       }
+      for (int c0 = 0; c0 < n_parts; c0 += 4) {
+        const long long t_spin = clock64();
+        for (;;) {
+          bool ok = true;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc)
-        if (c0 + cc < n_parts) {
-          // the words this thread has read are put back to the sentinel for the next layer (the (m, l) words are
-          // shared by the 16 threads of a head: see below)
-          float* part = gbase + (long long)(c0 + cc) * stride;
-          *reinterpret_cast<float4*>(part + gq * D + d4 * 4) = make_float4(sent, sent, sent, sent);
-          fold(ml[cc], o4[cc]);
+          for (int cc = 0; cc < 4; ++cc)
+            if (c0 + cc < n_parts)
+              ok = ok && __float_as_uint(ml[cc].x) != kPkSentinel && __float_as_uint(ml[cc].y) != kPkSentinel &&
+                   __float_as_uint(o4[cc].x) != kPkSentinel && __float_as_uint(o4[cc].y) != kPkSentinel &&
+                   __float_as_uint(o4[cc].z) != kPkSentinel && __float_as_uint(o4[cc].w) != kPkSentinel;
+          if (ok) break;
+          pk_backoff();
+          if (clock64() - t_spin > 4000000000LL) mtx_wait_timeout(4, pair, c0);
+          request(c0);
         }
-    }
-    if (act) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+          if (c0 + cc < n_parts) {
+            *reinterpret_cast<float4*>(gbase + (long long)(c0 + cc) * stride + gq * D + d4 * 4) = make_float4(sent, sent, sent, sent);
+            fold(ml[cc], o4[cc]);
+          }
+        if (c0 + 4 < n_parts) request(c0 + 4);
+      }
       const float inv = 1.0f / Ls;
-      *reinterpret_cast<uint2*>(p.attn + (long long)r * p.hq * D + (long long)h * G * D + gq * D + d4 * 4) =
+      *reinterpret_cast<uint2*>(p.attn + (long long)tail->a_jobs[j].row * p.hq * D + (long long)tail->a_jobs[j].head * G * D + gq * D + d4 * 4) =
           pack_bf16x4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-    }
-    __syncwarp();  // the 16 threads of a head sit in one warp: all of them have read the head's (m, l) words
-    if (act && d4 == 0)
-      for (int c = 0; c < n_parts; ++c) *reinterpret_cast<float2*>(gbase + (long long)c * stride + G * D + gq * 2) = make_float2(sent, sent);
-  }
-
-  // (b) Pairs cut between warps of this CTA only: the warp that holds the pair's first segment merges.
-  for (int k = 0; k < 2; ++k) {
-    const int4 me = tail->a_seg[aw][k];
-    if (me.x < 0) continue;
-    // predecessor in tile order: this warp's slot entry, else the last segment of the nearest earlier warp with tiles
-    bool leader = true;
-    if (k == 0 || tail->a_seg[aw][0].x < 0) {
-      for (int w = aw - 1; w >= 0; --w)
-        if (tail->a_count[w] > 0) {
-          leader = tail->a_seg[w][1].x != me.x;
-          break;
-        }
-    }
-    if (!leader) continue;
-    // members: (aw, k) then, for a last-segment entry, the following warps while they continue the same pair
-    const float* src[kPkAttnWarps + 1];
-    int n_src = 0, flags = me.y;
-    src[n_src++] = k == 0 ? tail->a_slot[aw] : reinterpret_cast<const float*>(attn_tiles + aw * 2 * 8192);
-    if (k == 1) {
-      for (int w = aw + 1; w < kPkAttnWarps; ++w) {
-        if (tail->a_count[w] == 0) continue;
-        const int4 s0 = tail->a_seg[w][0], s1 = tail->a_seg[w][1];
-        if (s0.x == me.x) {  // the pair ends inside warp w
-          src[n_src++] = tail->a_slot[w];
-          flags |= s0.y;
-          break;
-        }
-        if (s0.x < 0 && s1.x == me.x) {  // warp w lies entirely inside the pair
-          src[n_src++] = reinterpret_cast<const float*>(attn_tiles + w * 2 * 8192);
-          flags |= s1.y;
-          continue;
-        }
-        break;
+      if (n_parts > 0) {
+        __syncwarp(head_mask);  // all 16 threads of the head have read its (m, l) words
+        if (d4 == 0)
+          for (int c = 0; c < n_parts; ++c) *reinterpret_cast<float2*>(gbase + (long long)c * stride + G * D + gq * 2) = make_float2(sent, sent);
       }
     }
-    if ((flags & 3) != 3) continue;  // continues in other CTAs: merged under (a)
-    const long long out_base = (long long)me.z * p.hq * D + (long long)me.w * G * D;
-    if (lane == 0) pk_ev(ev, 620 + k * 100 + 10 * n_src);
-    for (int u = lane; u < G * (D / 4); u += 32) {
-      const int gq = u / (D / 4), d4 = u - gq * (D / 4);
-      float M = -INFINITY;
-      for (int c = 0; c < n_src; ++c) M = fmaxf(M, src[c][G * D + gq * 2]);
-      float Ls = 0.0f;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int c = 0; c < n_src; ++c) {
-        const float2 ml = *reinterpret_cast<const float2*>(src[c] + G * D + gq * 2);
-        const float4 o4 = *reinterpret_cast<const float4*>(src[c] + gq * D + d4 * 4);
-        const float sc = ex2_approx((ml.x - M) * kLog2e);
-        Ls += ml.y * sc;
-        acc.x += o4.x * sc; acc.y += o4.y * sc; acc.z += o4.z * sc; acc.w += o4.w * sc;
-      }
-      const float inv = 1.0f / Ls;
-      *reinterpret_cast<uint2*>(p.attn + out_base + gq * D + d4 * 4) = pack_bf16x4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-    }
-    if (lane == 0) pk_ev(ev, 690 + k);
   }
+  if (lane == 0) pk_ev(ev, 691);
 }
 
 // ---- the kernel --------------------------------------------------------------------------
@@ -1649,8 +1617,9 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
       }
     };
 
+    ev.brief = aw == kPkAttnWarps - 1;
     for (int l = 0; l < p.L; ++l) {
-      ev.on = l == 1;
+      ev.on = ev.brief ? (l & 1) == 0 && l < 32 : l == 1;
 #pragma unroll 1  // one copy of the duty code
       for (int ph = 0; ph < 4; ++ph) {
         gemm_duty(ph, l);

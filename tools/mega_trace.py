@@ -145,3 +145,38 @@ try:
         np.savez("gpurun_out/attn_events.npz", **arrs)
 except Exception as ex:  # noqa
     print("could not save arrays:", ex)
+
+# ---- last attention warp, every other layer: loop end (610) and merges done (501) relative to that layer's QKV
+# barrier release, per CTA mean over the logged layers ----
+if np.any(evs[:, 2, :, 0] == 610):
+    le = np.full((g, 16), np.nan); md = np.full((g, 16), np.nan)
+    for c in range(g):
+        k610 = k501 = 0
+        for i in range(32):
+            eid, tm = int(evs[c, 2, i, 0]), evs[c, 2, i, 1]
+            if tm == 0: break
+            if eid == 610 and k610 < 16:
+                lay = 2 * k610
+                le[c, k610] = (tm - a[2 * (2 + 5 * lay) + 1].max()) / 1e3; k610 += 1
+            if eid == 501 and k501 < 16:
+                lay = 2 * k501
+                md[c, k501] = (tm - a[2 * (2 + 5 * lay) + 1].max()) / 1e3; k501 += 1
+    lem, mdm = np.nanmean(le, axis=1), np.nanmean(md, axis=1)
+    print("last attention warp over %d layers: loop end mean-per-CTA min %.2f med %.2f max %.2f | merges done min %.2f med %.2f max %.2f" % (
+        int(np.sum(~np.isnan(le[0]))), np.nanmin(lem), np.nanmedian(lem), np.nanmax(lem), np.nanmin(mdm), np.nanmedian(mdm), np.nanmax(mdm)))
+    print("  per-layer spread of loop end (max - median over CTAs):", np.round(np.nanmax(le, axis=0) - np.nanmedian(le, axis=0), 2))
+    print("  slowest CTAs by mean loop end:", [(int(c), round(float(lem[c]), 2)) for c in np.argsort(lem)[-10:]])
+    print("  fastest CTAs by mean loop end:", [(int(c), round(float(lem[c]), 2)) for c in np.argsort(lem)[:10]])
+    np.savez("gpurun_out/attn_all_layers.npz", loop_end=le, merges_done=md)
+
+# ---- the CTAs whose first attention warp finishes its merges last (layer 1): full event logs ----
+if np.any(evs[:, 1, :, 0] == 501):
+    t501 = np.array([_first(c, 1, 501) for c in range(g)])
+    for c in np.argsort(np.nan_to_num(t501))[-6:]:
+        for role, rn in ((1, "first attn warp"), (2, "last attn warp")):
+            out = []
+            for i in range(32):
+                eid, tm = int(evs[c, role, i, 0]), evs[c, role, i, 1]
+                if tm == 0: break
+                if (tm - base) / 1e3 > rel_qkv - 1 and eid >= 500: out.append(f"{eid}:{(tm - base) / 1e3 - rel_qkv:.2f}")
+            print("late cta", int(c), rn, " ".join(out[:14]))
