@@ -89,6 +89,8 @@ int main() {
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q));
   EncodeFn enc = (EncodeFn)fp;
   int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  if (getenv("MTX_SMS")) sms = atoi(getenv("MTX_SMS"));  // stream from a subset of the SMs (per-SM rate when the others are idle)
+  printf("CTAs: %d\n", sms);
   CK(cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   auto run = [&](const char* name, int mode, int chunk, int stages, int issuers, int K, int hint = 0, int xload = 0) {
@@ -122,7 +124,7 @@ int main() {
     const double moved = double(a.n_chunks) * chunk;
     printf("%-34s chunk %6d stages %2d issuers %d in-flight/SM %4d KB : %7.1f GB/s\n", name, chunk, stages, issuers, stages * chunk / 1024, moved / best / 1e6);
   };
-  for (int st : {4, 5, 8}) run("2-D weight + X tile, no hint", 1, 16384, st, 1, 1280, 0, 1);
+  for (int st : {4, 5, 8, 12}) run("2-D weight + X tile, no hint", 1, 16384, st, 1, 1280, 0, 1);
   for (int st : {4, 5, 8}) run("2-D weight + X tile, evict_first", 1, 16384, st, 1, 1280, 1, 1);
   return 0;
 }
