@@ -785,7 +785,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     fa.num_slots = c.num_slots;
     fa.R = c.max_target_len - c.max_prefill_len;
     fa.first_token = first_token;
-    MTX_TRY(launch(finalize_kernel, dim3(finalize_rows), dim3(128), 0, st, fa));
+    MTX_TRY(launch(finalize_kernel, dim3(finalize_rows), dim3(kFinalizeThreads), 0, st, fa));
   }
   return MTX_OK;
 }
@@ -1050,7 +1050,7 @@ int mtx_commit_candidates(mtx_engine* e, int rows, const float* gathered, int n_
   fa.num_slots = c.num_slots;
   fa.R = c.max_target_len - c.max_prefill_len;
   g_class = KC_FINALIZE;
-  return launch(finalize_kernel, dim3(rows), dim3(128), 0, static_cast<cudaStream_t>(stream), fa);
+  return launch(finalize_kernel, dim3(rows), dim3(kFinalizeThreads), 0, static_cast<cudaStream_t>(stream), fa);
 }
 
 int mtx_profile_decode_step(mtx_engine* e, int rows, mtx_stream stream, float* class_ms, int32_t* class_launches) {

@@ -102,14 +102,16 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
       rd.rope_cs[idx] = make_float2(bf16r(cosf(ang)), bf16r(sinf(ang)));
     }
   }
-  if (tid == 0)
-    for (int i = 1; i <= 256; ++i) s_off[i] += s_off[i - 1];
-  __syncthreads();
-  if (tid < a.rows) {
-    const int base = s_off[tid];
-    for (int c = 0; c < chunks; ++c) rd.work_items[base + c] = (tid << 16) | c;
+  if (a.grid_bar == nullptr) {  // the per-kernel path's attention work list (the persistent kernel cuts its own)
+    if (tid == 0)
+      for (int i = 1; i <= 256; ++i) s_off[i] += s_off[i - 1];
+    __syncthreads();
+    if (tid < a.rows) {
+      const int base = s_off[tid];
+      for (int c = 0; c < chunks; ++c) rd.work_items[base + c] = (tid << 16) | c;
+    }
+    if (tid == 0) *rd.work_count = s_off[a.rows];
   }
-  if (tid == 0) *rd.work_count = s_off[a.rows];
   if (a.grid_bar != nullptr) {
     for (int i = tid; i < a.tile_cnt_n; i += 256) a.tile_cnt[i] = 0;
     if (tid == 0) {
@@ -221,12 +223,16 @@ struct FinalizeArgs {
   int* first_token;
 };
 
-// One CTA (128 threads) per row: reduce the per-tile candidates (first maximum wins, as
+// One CTA (kFinalizeThreads threads) per row: reduce the per-tile candidates (first maximum wins, as
 // jnp.argmax), compute log-softmax of the choice (inference_utils.py:55-63), then the
-// bookkeeping of maxengine.py:913-914 and kvcache.py:778-779.
-__global__ void __launch_bounds__(128) finalize_kernel(const FinalizeArgs a) {
-  __shared__ float s_score[4], s_raw[4], s_max[4], s_sum[4];
-  __shared__ int s_idx[4];
+// bookkeeping of maxengine.py:913-914 and kvcache.py:778-779.  The candidates of a row are strided in memory
+// (one L2 sector each): many threads and four independent candidates per thread keep the kernel at a few L2
+// round trips.
+constexpr int kFinalizeThreads = 512;
+__global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const FinalizeArgs a) {
+  constexpr int kWarps = kFinalizeThreads / 32;
+  __shared__ float s_score[kWarps], s_raw[kWarps], s_max[kWarps], s_sum[kWarps];
+  __shared__ int s_idx[kWarps];
   const int tl = timeline_begin(8);
   griddep_launch_dependents();
   griddep_wait();
@@ -234,16 +240,28 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalizeArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float score = -INFINITY, raw = -INFINITY, mx = -INFINITY, sum = 0.0f;
   int idx = 0x7fffffff;
-  for (int t = threadIdx.x; t < a.n_tiles; t += 128) {
-    const long long o = (long long)r * a.stride_r + (long long)t * a.stride_t;
-    const float s2 = a.part_score[o];
-    const int i2 = a.part_idx[o];
-    if (s2 > score || (s2 == score && i2 < idx)) { score = s2; idx = i2; raw = a.part_raw[o]; }
-    if (a.have_lse) {
-      const float m2 = a.part_max[o];
-      const float mn = fmaxf(mx, m2);
-      if (mn > -INFINITY) sum = sum * expf(mx - mn) + a.part_sum[o] * expf(m2 - mn);
-      mx = mn;
+  for (int t0 = threadIdx.x; t0 < a.n_tiles; t0 += 4 * kFinalizeThreads) {
+    float s4[4], r4[4], m4[4], u4[4];
+    int i4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = t0 + q * kFinalizeThreads;
+      const long long o = (long long)r * a.stride_r + (long long)(t < a.n_tiles ? t : t0) * a.stride_t;
+      s4[q] = a.part_score[o];
+      i4[q] = a.part_idx[o];
+      r4[q] = a.part_raw[o];
+      m4[q] = a.have_lse ? a.part_max[o] : -INFINITY;
+      u4[q] = a.have_lse ? a.part_sum[o] : 0.0f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (t0 + q * kFinalizeThreads >= a.n_tiles) continue;
+      if (s4[q] > score || (s4[q] == score && i4[q] < idx)) { score = s4[q]; idx = i4[q]; raw = r4[q]; }
+      if (a.have_lse) {
+        const float mn = fmaxf(mx, m4[q]);
+        if (mn > -INFINITY) sum = sum * expf(mx - mn) + u4[q] * expf(m4[q] - mn);
+        mx = mn;
+      }
     }
   }
 #pragma unroll
@@ -261,7 +279,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalizeArgs a) {
   if (lane == 0) { s_score[warp] = score; s_idx[warp] = idx; s_raw[warp] = raw; s_max[warp] = mx; s_sum[warp] = sum; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < 4; ++w) {
+    for (int w = 1; w < kWarps; ++w) {
       if (s_score[w] > score || (s_score[w] == score && s_idx[w] < idx)) { score = s_score[w]; idx = s_idx[w]; raw = s_raw[w]; }
       const float mn = fmaxf(mx, s_max[w]);
       if (mn > -INFINITY) sum = sum * expf(mx - mn) + s_sum[w] * expf(s_max[w] - mn);
@@ -290,7 +308,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const FinalizeArgs a) {
   }
   if (a.mode == 0 && blockIdx.x == 0) {
     // every slot's counter advances, occupied or not (kvcache.py:779 `.at[:].add(1)`)
-    for (int s = threadIdx.x; s < a.num_slots; s += 128) a.ar_lengths[s] += 1;
+    for (int s = threadIdx.x; s < a.num_slots; s += kFinalizeThreads) a.ar_lengths[s] += 1;
     if (threadIdx.x == 0) {
       a.ar_index[0] = (a.ar_index[0] + 1) % a.R;
       a.rng_state[0] += 1;

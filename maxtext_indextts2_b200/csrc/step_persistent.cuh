@@ -506,12 +506,20 @@ __device__ __noinline__ void pk_finish_swiglu(const PkParams* pp, const float* r
             t[k][ss] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r + k * nw < r_end && s0 + ss < parts) t[k][ss] = ld_poll_f4(src0 + (long long)(s0 + ss) * 4 * kPkSlotFloats + (r + k * nw) * 128);
           }
+        // (the sentinel is a quiet NaN: test the sum first, compare word by word only when it is NaN)
+        float chk = 0.0f;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
-          for (int ss = 0; ss < 4; ++ss)
-            ok = ok && __float_as_uint(t[k][ss].x) != kPkSentinel && __float_as_uint(t[k][ss].y) != kPkSentinel &&
-                 __float_as_uint(t[k][ss].z) != kPkSentinel && __float_as_uint(t[k][ss].w) != kPkSentinel;
+          for (int ss = 0; ss < 4; ++ss) chk += (t[k][ss].x + t[k][ss].y) + (t[k][ss].z + t[k][ss].w);
+        if (chk != chk) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int ss = 0; ss < 4; ++ss)
+              ok = ok && __float_as_uint(t[k][ss].x) != kPkSentinel && __float_as_uint(t[k][ss].y) != kPkSentinel &&
+                   __float_as_uint(t[k][ss].z) != kPkSentinel && __float_as_uint(t[k][ss].w) != kPkSentinel;
+        }
         if (__all_sync(0xffffffffu, ok)) break;
         pk_backoff();
         if (clock64() - t_spin > 4000000000LL) mtx_wait_timeout(5, tile, r);
