@@ -466,26 +466,29 @@ __device__ __forceinline__ void pk_logits_store(const float* park, int ew, int l
 // applies the row's rstd and runs the SwiGLU epilogue.  Out of line and shared by the epilogue warps and the
 // attention warps: the finish is bound by L2 round trips per row, so every idle warp of the CTA takes rows.
 // Four rows x four parts are in flight per warp.
-__device__ __noinline__ void pk_finish_swiglu(const PkParams* pp, const float* rstd, const float* own, int tile, int c_first, int parts, int r_begin,
-                                              int r_end, int w, int nw, int lane) {
-  const PkParams& p = *pp;
-  if (parts == 0) {  // the CTA holds the whole reduction: nothing to fetch, two rows at a time
+// (Scalars by value: a pointer to the kernel parameters would make every use a generic load from the constant bank,
+// reloaded after each store.)
+__device__ __noinline__ void pk_finish_swiglu(float* part_ws, bf16* act, int M, const float* rstd, const float* own, int tile, int c_first, int parts,
+                                              int r_begin, int r_end, int w, int nw, int lane) {
+  if (parts == 0) {  // the CTA holds the whole reduction: nothing to fetch; four rows at a time (independent chains)
     const float* src = own + lane * 4;
-    int r = r_begin + w;
-    for (; r + nw < r_end; r += 2 * nw) {
-      const float4 a = *reinterpret_cast<const float4*>(src + r * 128), b = *reinterpret_cast<const float4*>(src + (r + nw) * 128);
-      const float ra = rstd[r], rb = rstd[r + nw];
-      pk_epi_swiglu(make_float4(a.x * ra, a.y * ra, a.z * ra, a.w * ra), r, tile, lane, 2 * p.M, p.M, p.act);
-      pk_epi_swiglu(make_float4(b.x * rb, b.y * rb, b.z * rb, b.w * rb), r + nw, tile, lane, 2 * p.M, p.M, p.act);
-    }
-    if (r < r_end) {
-      const float4 a = *reinterpret_cast<const float4*>(src + r * 128);
-      const float ra = rstd[r];
-      pk_epi_swiglu(make_float4(a.x * ra, a.y * ra, a.z * ra, a.w * ra), r, tile, lane, 2 * p.M, p.M, p.act);
+    for (int r = r_begin + w; r < r_end; r += 4 * nw) {
+      float4 a[4];
+      float rs[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int rk = r + k * nw < r_end ? r + k * nw : r;
+        a[k] = *reinterpret_cast<const float4*>(src + rk * 128);
+        rs[k] = rstd[rk];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (r + k * nw < r_end)  // (warp-uniform)
+          pk_epi_swiglu(make_float4(a[k].x * rs[k], a[k].y * rs[k], a[k].z * rs[k], a[k].w * rs[k]), r + k * nw, tile, lane, 2 * M, M, act);
     }
     return;
   }
-  float* src0 = p.part_ws + (long long)(c_first * 4 + (tile & 3)) * kPkSlotFloats + lane * 4;
+  float* src0 = part_ws + (long long)(c_first * 4 + (tile & 3)) * kPkSlotFloats + lane * 4;
   const float sent = __uint_as_float(kPkSentinel);
   for (int r = r_begin + w; r < r_end; r += 4 * nw) {
     float4 acc[4];
@@ -537,7 +540,7 @@ __device__ __noinline__ void pk_finish_swiglu(const PkParams* pp, const float* r
     for (int k = 0; k < 4; ++k)
       if (r + k * nw < r_end) {
         const float rs = rstd[r + k * nw];
-        pk_epi_swiglu(make_float4(acc[k].x * rs, acc[k].y * rs, acc[k].z * rs, acc[k].w * rs), r + k * nw, tile, lane, 2 * p.M, p.M, p.act);
+        pk_epi_swiglu(make_float4(acc[k].x * rs, acc[k].y * rs, acc[k].z * rs, acc[k].w * rs), r + k * nw, tile, lane, 2 * M, M, act);
       }
   }
 }
@@ -549,9 +552,9 @@ __device__ __forceinline__ void pk_finish_up_unit(const PkParams* pp, const floa
                                                   int nw, int lane) {
   if (un.S > 1) {
     const int si = cta - un.c_first;
-    pk_finish_swiglu(pp, rstd, nullptr, un.tile, un.c_first, un.S, si * pp->rows / un.S, (si + 1) * pp->rows / un.S, w, nw, lane);
+    pk_finish_swiglu(pp->part_ws, pp->act, pp->M, rstd, nullptr, un.tile, un.c_first, un.S, si * pp->rows / un.S, (si + 1) * pp->rows / un.S, w, nw, lane);
   } else if (un.S < 0 || (un.S == 1 && solo)) {  // (solo: a whole tile that is the CTA's only unit of the phase, see pk_up_all_warps)
-    pk_finish_swiglu(pp, rstd, park, un.tile, un.c_first, un.S < 0 ? -un.S : 0, 0, pp->rows, w, nw, lane);
+    pk_finish_swiglu(pp->part_ws, pp->act, pp->M, rstd, park, un.tile, un.c_first, un.S < 0 ? -un.S : 0, 0, pp->rows, w, nw, lane);
   }
 }
 // MLP up: do all warps of the CTA finish its units?  Yes when a tile is shared, and also for a single whole tile:
@@ -1335,6 +1338,10 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
           if (wtid == 0) pk_ev(ev, 100 * tph + 14);
           pk_finish_up_unit(&p, tail->rstd, park, un, up_solo, cta, ew, 4 + kPkAttnWarps, lane);
           if (wtid == 0) pk_ev(ev, 100 * tph + 15);
+#ifdef MTX_PK_ICACHE_PROBE  // the same (idempotent) work again: how much of the first pass was instruction fetch?
+          if (up_solo) pk_finish_up_unit(&p, tail->rstd, park, un, up_solo, cta, ew, 4 + kPkAttnWarps, lane);
+          if (wtid == 0) pk_ev(ev, 100 * tph + 16);
+#endif
           continue;
         }
         const int si = cta - un.c_first;
