@@ -617,7 +617,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     pa.pk_ctas = e->pk_ctas;
     pa.pk_max_parts = kPkMaxParts;
     pa.pk_warps = kPkAttnWarps;
-    pa.pk_pair_mode_tiles = env_int("MTX_PK_PAIR_MODE_TILES", 36);
+    pa.pk_pair_mode_tiles = env_int("MTX_PK_PAIR_MODE_TILES", 8);
   }
   g_class = KC_PREPARE;
   MTX_TRY(launch(prepare_rows_kernel, dim3(1), dim3(256), 0, st, pa, e->rd));
