@@ -424,7 +424,7 @@ bool pk_fill_phase(std::vector<PkTable>& tabs, int ph, int n, int k, bool allow_
   // over through the exchange.  Helpers get less work than owners, so their partials are in L2 by the time an owner
   // has finished its own stream: the owner's accumulator never leaves the chip, it waits for nobody, and it streams
   // k_own instead of all k-blocks (a single SM pulls ~40 GB/s, which bounds the whole-tile variant).
-  const int k_own_env = env_int("MTX_PK_UP_OWNER_KB", 0);  // 0 = off (measured: 13.3-14.8 us per layer against 12.4 for whole tiles), -1 = automatic
+  const int k_own_env = env_int("MTX_PK_UP_OWNER_KB", -1);  // -1 = automatic (an equal share of the k-blocks), 0 = off (one whole tile per CTA)
   if (ph == PK_UP && allow_whole_tile && k_own_env != 0 && n_tiles < n_ctas && 2 * n_tiles > n_ctas && kbt >= 8) {
     int k_own = k_own_env > 0 ? k_own_env : int((total + n_ctas - 1) / n_ctas);
     if (k_own > kbt - 1) k_own = kbt - 1;
