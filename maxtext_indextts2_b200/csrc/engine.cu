@@ -570,7 +570,7 @@ int launch_persistent(mtx_engine* e, int rows, const XMaps& xm, const EpiArgs& l
   p.tile_cnt_stride = e->pk_tile_cnt_stride;
   p.ss_x = e->pk_ss_x;
   p.ss_h = e->pk_ss_h;
-  p.tables = e->pk_tables + (rows <= env_int("MTX_PK_FEW_ROWS", 16) ? e->pk_ctas : 0);
+  p.tables = e->pk_tables + (rows <= env_int("MTX_PK_FEW_ROWS", 0) ? e->pk_ctas : 0);
   p.logits = logits_epi;
   p.grid_bar = e->grid_bar;
   p.trace = g_trace;

@@ -41,13 +41,14 @@ def _prefill_both(engine, dparams, oracle, ostate, state, prompts, lengths):
   return ostate, state
 
 
-def _assert_near_tie(row_logits, got, want):
+def _assert_near_tie(row_logits, got, want, margin=None):
   top = row_logits[want].item()
   other = row_logits[got].item()
-  assert abs(top - other) <= NEAR_TIE * max(1.0, abs(top)), f"token {got} (logit {other}) vs oracle {want} (logit {top}) is not a near-tie"
+  bound = NEAR_TIE * max(1.0, abs(top)) if margin is None else margin
+  assert abs(top - other) <= bound, f"token {got} (logit {other}) vs oracle {want} (logit {top}) is not a near-tie"
 
 
-def _lockstep(engine, dparams, oracle, ostate, state, steps, atol=1e-1, rtol=1e-1):
+def _lockstep(engine, dparams, oracle, ostate, state, steps, atol=1e-1, rtol=1e-1, tie_margin=None):
   near_ties = 0
   for step in range(steps):
     ostate, odata = oracle.generate(ostate)
@@ -60,7 +61,7 @@ def _lockstep(engine, dparams, oracle, ostate, state, steps, atol=1e-1, rtol=1e-
       torch.testing.assert_close(got, ostate["logits"], rtol=rtol, atol=atol)
     for b in range(data.shape[0]):
       if data[b, 0] != odata[b, 0]:
-        _assert_near_tie(ostate["logits"][b, 0], int(data[b, 0]), int(odata[b, 0]))
+        _assert_near_tie(ostate["logits"][b, 0], int(data[b, 0]), int(odata[b, 0]), tie_margin)
         near_ties += 1
         state["tokens"][b] = int(odata[b, 0])  # re-synchronise on the oracle's token
     assert torch.equal(state["next_pos"].cpu(), ostate["next_pos"])
@@ -258,7 +259,10 @@ def test_indextts2_scale_logits_and_greedy_tokens():
   # 24 layers deep, the bf16 rounding noise of the two implementations (bf16 softmax in the oracle, fp32
   # here) reaches ~6 bf16 ulps on isolated logits: stated tolerance atol = 0.2 (logits span about +-4),
   # and all but 1e-5 of the entries inside the reference's 1e-1
-  near = _lockstep(engine, dparams, oracle, ostate, state, steps=6, atol=0.2)
+  # (a greedy mismatch is a near-tie here when the oracle's margin is inside that same logit tolerance: two correct
+  # implementations of this depth differ by 0.02 on average and up to 0.15 on single logits, measured between the
+  # persistent kernel, its whole-tile variant and the per-kernel path)
+  near = _lockstep(engine, dparams, oracle, ostate, state, steps=6, atol=0.2, tie_margin=0.2)
   d = (state["logits"].cpu() - ostate["logits"]).abs()
   assert (d > 0.1 + 0.1 * ostate["logits"].abs()).float().mean() < 1e-5
   assert near <= 2
