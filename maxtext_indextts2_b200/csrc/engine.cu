@@ -248,9 +248,8 @@ struct mtx_engine {
   int pk_ctas = 0;  // CTAs of the persistent grid (0 = unavailable)
   unsigned int* grid_bar = nullptr;
   PkTable* pk_tables = nullptr;
-  float *pk_part_ws = nullptr, *pk_ss_x = nullptr, *pk_ss_h = nullptr, *pk_attn_part_o = nullptr, *pk_attn_part_ml = nullptr;
-  int *pk_tile_cnt = nullptr, *pk_tile_prefix = nullptr, *pk_attn_info = nullptr, *pk_attn_tickets = nullptr;
-  int pk_tile_cnt_stride = 0;
+  float *pk_part_ws = nullptr, *pk_ss_x = nullptr, *pk_ss_h = nullptr, *pk_attn_part_o = nullptr;
+  int *pk_tile_prefix = nullptr, *pk_attn_info = nullptr;
   XMaps xmaps[5];
   // sampling
   int strategy = MTX_SAMPLE_GREEDY, top_k = 0;
@@ -266,16 +265,9 @@ struct WsLayout {
   size_t x, h, n, q, attn, act, attn_part_o, attn_part_ml, attn_tickets;
   size_t token, pos, plane, write_row, len0, ring_first, ring_len, rope_cs, work_items, work_count, rope_timescale;
   size_t part_score, part_idx, part_raw, part_max, part_sum, grid_bar;
-  size_t pk_tables, pk_part_ws, pk_tile_cnt, pk_ss_x, pk_ss_h, pk_attn_part_o, pk_attn_part_ml, pk_attn_tickets, pk_tile_prefix, pk_attn_info;
+  size_t pk_tables, pk_part_ws, pk_ss_x, pk_ss_h, pk_attn_part_o, pk_tile_prefix, pk_attn_info;
   size_t total;
 };
-
-int pk_tile_cnt_stride(const mtx_model_config& c) {
-  int n = (c.num_q_heads + 2 * c.num_kv_heads) * c.head_dim;
-  if (2 * c.mlp_dim > n) n = 2 * c.mlp_dim;
-  if (c.emb_dim > n) n = c.emb_dim;
-  return (n + kTileN - 1) / kTileN;
-}
 
 WsLayout layout_workspace(const mtx_engine* e) {
   const mtx_model_config& c = e->cfg;
@@ -321,12 +313,9 @@ WsLayout layout_workspace(const mtx_engine* e) {
     const size_t ss_tiles = (c.emb_dim + 127) / 128;
     L.pk_tables = take(size_t(2) * e->num_sms * sizeof(PkTable));  // [0] many rows, [1] few rows
     L.pk_part_ws = take(size_t(e->num_sms) * 4 * kPkSlotFloats * 4);
-    L.pk_tile_cnt = take(size_t(4) * pk_tile_cnt_stride(c) * 4);
     L.pk_ss_x = take(size_t(kPkMaxRTile) * ss_tiles * 4);
     L.pk_ss_h = take(size_t(kPkMaxRTile) * ss_tiles * 4);
     L.pk_attn_part_o = take(pairs * kPkMaxParts * ((G * c.head_dim + 2 * G + 3) / 4 * 4) * 4);
-    L.pk_attn_part_ml = take(pairs * kPkMaxParts * G * 2 * 4);
-    L.pk_attn_tickets = take(pairs * 4);
     L.pk_tile_prefix = take((pk_rows + 1) * 4);
     L.pk_attn_info = take(64);
   }
@@ -563,11 +552,7 @@ int launch_persistent(mtx_engine* e, int rows, const XMaps& xm, const EpiArgs& l
   p.tile_prefix = e->pk_tile_prefix;
   p.attn_info = e->pk_attn_info;
   p.attn_part_o = e->pk_attn_part_o;
-  p.attn_part_ml = e->pk_attn_part_ml;
-  p.attn_tickets = e->pk_attn_tickets;
   p.part_ws = e->pk_part_ws;
-  p.tile_cnt = e->pk_tile_cnt;
-  p.tile_cnt_stride = e->pk_tile_cnt_stride;
   p.ss_x = e->pk_ss_x;
   p.ss_h = e->pk_ss_h;
   p.tables = e->pk_tables + (rows <= env_int("MTX_PK_FEW_ROWS", 0) ? e->pk_ctas : 0);
@@ -609,8 +594,6 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   const bool mega = mode == 0 && want_logits && pk_usable(e, rows);
   if (mega) {
     pa.grid_bar = e->grid_bar;
-    pa.tile_cnt = e->pk_tile_cnt;
-    pa.tile_cnt_n = 4 * e->pk_tile_cnt_stride;
     pa.tile_prefix = e->pk_tile_prefix;
     pa.attn_info = e->pk_attn_info;
     pa.hkv = c.num_kv_heads;
@@ -892,13 +875,9 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   e->grid_bar = reinterpret_cast<unsigned int*>(b + L.grid_bar);
   e->pk_tables = reinterpret_cast<PkTable*>(b + L.pk_tables);
   e->pk_part_ws = reinterpret_cast<float*>(b + L.pk_part_ws);
-  e->pk_tile_cnt = reinterpret_cast<int*>(b + L.pk_tile_cnt);
-  e->pk_tile_cnt_stride = pk_tile_cnt_stride(c);
   e->pk_ss_x = reinterpret_cast<float*>(b + L.pk_ss_x);
   e->pk_ss_h = reinterpret_cast<float*>(b + L.pk_ss_h);
   e->pk_attn_part_o = reinterpret_cast<float*>(b + L.pk_attn_part_o);
-  e->pk_attn_part_ml = reinterpret_cast<float*>(b + L.pk_attn_part_ml);
-  e->pk_attn_tickets = reinterpret_cast<int*>(b + L.pk_attn_tickets);
   e->pk_tile_prefix = reinterpret_cast<int*>(b + L.pk_tile_prefix);
   e->pk_attn_info = reinterpret_cast<int*>(b + L.pk_attn_info);
   MTX_CUDA(cudaMemcpy(e->rope_timescale, e->rope_timescale_host.data(), e->rope_timescale_host.size() * 4, cudaMemcpyHostToDevice));

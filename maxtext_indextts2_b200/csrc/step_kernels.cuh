@@ -36,8 +36,6 @@ struct PrepareArgs {
   const float* rope_timescale;  // [D/2] min * (max/min)^(2i/D), embeddings.py:270-275
   // persistent step kernel (step_persistent.cuh): counters reset here, attention tile partition
   unsigned int* grid_bar;  // grid-barrier arrival counter
-  int* tile_cnt;           // split-K exchange counters
-  int tile_cnt_n;
   int* tile_prefix;        // [rows + 1] exclusive prefix of the per-row 64-row tile counts
   int* attn_info;          // [0] CTAs that get attention work, [1] total tiles over all kv heads, [2] 1 = one pair per CTA
   int hkv;
@@ -113,7 +111,6 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
     if (tid == 0) *rd.work_count = s_off[a.rows];
   }
   if (a.grid_bar != nullptr) {
-    for (int i = tid; i < a.tile_cnt_n; i += 256) a.tile_cnt[i] = 0;
     if (tid == 0) {
       *a.grid_bar = 0u;
       int acc = 0, nt_max = 1;

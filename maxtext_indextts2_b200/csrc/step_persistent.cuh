@@ -2,37 +2,39 @@
 //
 // Why: as separate kernels every phase of a layer (QKV, attention, out-proj, MLP up, MLP down, two
 // norms) costs 8-16 us of launch / drain / dependency latency against 0.5-10 us of HBM time
-// (profiles/, round 1).  Here a phase boundary is one grid barrier (~1 us) and the HBM stream never
+// (profiles/, round 1).  Here a phase boundary is one grid barrier (~1.3 us) and the HBM stream never
 // stops at it: the weight producer of every CTA runs AHEAD of the barrier, pulling the next phases'
 // weight tiles into its shared-memory ring while the current phase drains (weights never depend on
 // activations); only the small activation tiles wait for the barrier.
 //
 // Per layer five phases, five grid barriers:
-//   QKV GEMM (+RMSNorm of x in shared memory, RoPE, KV append) | attention | out-proj (+residual,
-//   row sum-of-squares) | MLP up (+RMSNorm of h, SwiGLU) | MLP down (+residual, row sum-of-squares)
+//   QKV GEMM (+RMSNorm of x, RoPE, KV append) | attention | out-proj (+residual, row sum-of-squares) |
+//   MLP up (+RMSNorm of h, SwiGLU) | MLP down (+residual, row sum-of-squares)
 // then one small final-norm phase and the logits GEMM with the sampling partials.
 //
 // RMSNorm is never a phase of its own: the epilogue that produces x (or h) also emits per-row partial
-// sums of squares; the consuming GEMM normalises its activation k-blocks in shared memory (the exact
-// bf16 rounding sequence of normalizations.py:57-69) before the MMA reads them.
+// sums of squares; the consuming GEMM is computed as rstd[row] * dot(W, bf16(x * scale)): the per-feature
+// scale is applied to the activation k-blocks in shared memory, the per-row factor to the fp32
+// accumulator in the epilogue (normalizations.py:57-69 rounds x * rstd to bf16 first).
 //
-// GEMM work is cut stream-K style: the (weight tile, k-block) units of a phase are dealt to the CTAs
-// in contiguous equal ranges, so every SM streams the same number of weight bytes whatever the matrix
-// shape.  CTAs that share a weight tile exchange fp32 partial tiles through an L2-resident workspace
-// (write partial, bump the tile's counter, wait for the peers, sum a row slice in fixed order) and
-// each finishes the epilogue of its own row slice: deterministic, no atomics on data.
+// GEMM work tables are built on the host (engine.cu, pk_fill_phase).  CTAs that share a weight tile
+// exchange fp32 partial tiles through an L2-resident workspace WITHOUT flags: a word of a slot is either
+// a sentinel NaN or data, the CTA that owns a row slice polls the fragments themselves, sums them in
+// fixed order (deterministic, no atomics on data), runs the epilogue and puts the sentinel back.
 //
 // Epilogues work on ROW-MAJOR float4 fragments (a warp = 128 consecutive output features of one row),
-// so RoPE / SwiGLU partners are a warp shuffle away and every global store is an 8-byte piece of a
-// 256-byte coalesced row segment.
+// so RoPE / SwiGLU partners are a warp shuffle away and every global store is a piece of a 256-byte
+// coalesced row segment.  A warp's epilogue is one dependent instruction chain (~2.6 ns per
+// instruction): these paths are written for instruction count and independent rows in flight.
 //
 // Roles (352 threads): warp 0 weight producer (TMA) | warp 1 tcgen05.mma issuer | warps 2-5 epilogue |
-// warps 6-10 attention; during the GEMM phases warps 6-9 normalise activation tiles and warp 10 is the
-// activation producer (TMA).  Every role walks the same static fill sequence with its own lean loop.
+// warps 6-10 attention; during the GEMM phases warps 6-9 scale activation tiles, warp 10 is the
+// activation producer (TMA) and all five help to finish MLP-up rows.  Every role walks the same static
+// fill sequence with its own lean loop.
 // Attention is stream-K over 64-row KV tiles at WARP granularity: every attention warp of the grid
-// gets the same number of tiles (the partition is computed once per step: lengths do not change between
-// layers); pairs (row, kv head) that span warps merge through an L2 workspace, the last warp to arrive
-// writing the result.
+// gets the same number of tiles (the partition and the merge plan are computed once per step: lengths do
+// not change between layers); a (row, kv head) pair that spans warps is merged by the CTA that holds its
+// first tile, from shared memory and -- for warps of other CTAs -- from flag-in-data parts in L2.
 #pragma once
 
 #include <type_traits>
@@ -127,12 +129,8 @@ struct PkParams {
   const int* attn_info;    // [0] CTAs with attention work, [1] total tiles (all kv heads), [2] 1 = one pair per CTA
   // attention merge workspace
   float* attn_part_o;   // [pairs, kPkMaxParts, G, D]
-  float* attn_part_ml;  // [pairs, kPkMaxParts, G, 2]
-  int* attn_tickets;    // [pairs]
   // split-K exchange
   float* part_ws;  // [n_ctas * 4] slots of kPkSlotFloats
-  int* tile_cnt;   // [4, tile_cnt_stride] zeroed by prepare_rows_kernel
-  int tile_cnt_stride;
   float* ss_x;     // [E/128 rounded up, kPkMaxRTile] partial sums of squares of the rows of x, one per 128-feature tile
   float* ss_h;
   const PkTable* tables;  // [n_ctas]
@@ -623,7 +621,8 @@ __device__ __forceinline__ bool pk_up_all_warps(const PkTable& tab) {
 // every warp streams the same number of bytes whatever the context lengths are.  A warp's run is a sequence
 // of segments (maximal pieces inside one pair).  A pair that lies inside one warp is finished there; a pair
 // cut between warps of one CTA is merged in SHARED memory after the CTA's warps have met; only the pairs cut
-// between CTAs go through an L2 workspace (CTA-level partial + ticket, the last CTA to arrive merges).
+// between CTAs go through an L2 workspace (one part per warp, written when the warp's segment ends; the CTA
+// that holds the pair's first tile merges).
 // The partition depends on the context lengths only, so it is built once per step and reused by every layer.
 
 enum PkAttnMeta : int {
