@@ -31,6 +31,10 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
+# One string for both arms: the driver divides the two lines only if their metric (and unit) agree.
+METRIC = "audio tokens/s at batch 64 decode (whole job)"
+ORACLE_KIND = "port (parity unpinned)"  # the reference is pure Python/JAX: nothing of it could be compiled or imported here
+
 KERNEL_CLASSES = ["prepare", "rmsnorm", "qkv_rope_append", "attention", "out_proj", "mlp_up", "mlp_down", "logits_sample", "finalize", "persistent_step"]
 NCLS = len(KERNEL_CLASSES)
 
@@ -49,8 +53,12 @@ def parse_args():
   ap.add_argument("--target-len", type=int, default=0, help="override max_target_length (BASELINE configs[3]: 5632)")
   ap.add_argument("--no-graph", action="store_true")
   ap.add_argument("--skip-cpu-baseline", action="store_true")
-  ap.add_argument("--cpu-slots", type=int, default=8, help="slots in the CPU baseline sample")
-  ap.add_argument("--cpu-steps", type=int, default=3)
+  ap.add_argument("--cpu-slots", type=int, default=0, help="slots in the CPU baseline sample (0 = all slots of the batch)")
+  ap.add_argument("--cpu-steps", type=int, default=8, help="timed steps of the cpu_baseline leg of the GPU arm (after 2 warm-ups)")
+  ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-clock bound of a CPU leg; steps are cut (and reported) past it")
+  ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of one step of the timed state")
+  ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                  help="weak: --batch slots per GPU (default, the judged line); strong: --batch slots in total, split over the GPUs")
   return ap.parse_args()
 
 
@@ -153,43 +161,38 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 
 
-def cpu_reference_run(args, cfg, slots, steps, warmup=1):
-  """Times oracle/decode_ref.py (dtype-faithful restatement of MaxEngine.generate) on `slots` slots.
+def cpu_reference_run(args, cfg, slots, steps, warmup, budget_s):
+  """Times oracle/decode_ref.py (dtype-faithful restatement of MaxEngine.generate) on `slots` slots of the workload.
 
-  The reference's own JAX path cannot run here (no jax in the image); BASELINE.md section 4.
-  """
-  from maxtext_indextts2_b200 import pyconfig
+  The reference's own JAX path cannot run here (no jax in the image); BASELINE.md section 4.  Weights and cache are
+  random (one random layer repeated: the values do not matter for the time, only shapes and dtypes do)."""
   from oracle import decode_ref as ref
+  from oracle import mirror
 
   threads = os.cpu_count() or 1
   torch.set_num_threads(threads)
-  keys = cfg.get_keys()
-  ccfg = pyconfig.HyperParameters({**keys, "per_device_batch_size": slots})
   E, Hq, Hkv, D = cfg.emb_dim, cfg.num_query_heads, cfg.num_kv_heads, cfg.head_dim
   M, V, L = cfg.mlp_dim, cfg.vocab_size, cfg.num_decoder_layers
   g = torch.Generator().manual_seed(0)
   bf = lambda t: t.to(torch.bfloat16).to(torch.float32)
   rn = lambda shape, std: bf(torch.randn(shape, generator=g) * std)
-  layers = []
-  for _ in range(L):
-    layers.append(dict(
-        attn_scale=torch.ones(E), wq=rn((E, Hq * D), E**-0.5 / D**0.5), wk=rn((E, Hkv * D), E**-0.5), wv=rn((E, Hkv * D), E**-0.5),
-        wo=rn((Hq * D, E), (Hq * D) ** -0.5), mlp_scale=torch.ones(E), w0=rn((E, M), E**-0.5), w1=rn((E, M), E**-0.5),
-        wout=rn((M, E), M**-0.5)))
-  weights = ref.OracleWeights(embedding=rn((V, E), 1.0), layers=layers, final_scale=torch.ones(E), logits=rn((E, V), E**-0.5))
-  oracle = ref.DecodeOracle.__new__(ref.DecodeOracle)
-  oracle.cfg, oracle.faithful, oracle.w = ccfg, True, weights
-  oracle.B, oracle.P, oracle.T = slots, cfg.max_prefill_predict_length, cfg.max_target_length
-  oracle.R = oracle.T - oracle.P
-  oracle.scores_f32 = bool(cfg.float32_qk_product)
-  oracle.softmax_f32 = oracle.scores_f32 or bool(cfg.float32_logits)
+  layer = dict(
+      attn_scale=torch.ones(E), wq=rn((E, Hq * D), E**-0.5 / D**0.5), wk=rn((E, Hkv * D), E**-0.5), wv=rn((E, Hkv * D), E**-0.5),
+      wo=rn((Hq * D, E), (Hq * D) ** -0.5), mlp_scale=torch.ones(E), w0=rn((E, M), E**-0.5), w1=rn((E, M), E**-0.5),
+      wout=rn((M, E), M**-0.5))
+  layers = [{k: v.clone() for k, v in layer.items()} for _ in range(L)]
+  block = rn((4096, E), 1.0)
+  table = block.repeat((V + 4095) // 4096, 1)[:V].contiguous()
+  weights = ref.OracleWeights(embedding=table, layers=layers, final_scale=torch.ones(E), logits=(table * E**-0.5).t().contiguous())
+  oracle = mirror.make_oracle(cfg, weights, slots, faithful=True)
   state = oracle.init_decode_state()
   prefill, ar = context_lengths(args, cfg)
   prefill, ar = prefill[:slots], ar[:slots]
   c = state["cache"]
-  for l in range(L):
-    for name in ("prefill_key", "prefill_value", "ar_key", "ar_value"):
-      c[name][l].copy_(bf(torch.randn(c[name][l].shape, generator=g)))
+  for name in ("prefill_key", "prefill_value", "ar_key", "ar_value"):
+    first = bf(torch.randn(c[name][0].shape, generator=g))
+    for l in range(L):
+      c[name][l] = first.clone()
   c["prefill_segment_id"] = (torch.arange(oracle.P)[None, :] < torch.from_numpy(prefill)[:, None]).to(torch.int32)
   idx = int(ar.max())
   c["ar_segment_id"] = ((torch.arange(oracle.R)[None, :] >= idx - torch.from_numpy(ar)[:, None]) & (torch.arange(oracle.R)[None, :] < idx)).to(torch.int32)
@@ -197,59 +200,82 @@ def cpu_reference_run(args, cfg, slots, steps, warmup=1):
   c["ar_lengths"] = torch.from_numpy(ar).to(torch.int32)
   state["next_pos"] = torch.from_numpy(prefill + ar).to(torch.int32).reshape(slots, 1)
   state["tokens"] = torch.randint(0, V, (slots, 1), generator=g).to(torch.int32)
+  t_begin = time.perf_counter()
+  done_warm = 0
   for _ in range(warmup):
     state, _ = oracle.generate(state)
+    done_warm += 1
+    if time.perf_counter() - t_begin > budget_s / 3:
+      break
+  done = 0
   t0 = time.perf_counter()
   for _ in range(steps):
     state, _ = oracle.generate(state)
+    done += 1
+    if time.perf_counter() - t_begin > budget_s:
+      break
   dt = time.perf_counter() - t0
+  cut = "" if (done == steps and done_warm == warmup) else f" (cut from {steps} steps / {warmup} warm-ups by the {budget_s:.0f} s bound)"
   return {
-      "value": slots * steps / dt,
+      "value": slots * done / dt,
       "unit": "audio tokens/s",
       "cores": threads,
-      "kind": "port",
-      "ms_per_step": 1e3 * dt / steps,
-      "sample": f"{slots} of {args.batch} slots of the same workload, {steps} decode steps after {warmup} warm-up; "
-                "oracle/decode_ref.py (torch CPU, dtype-faithful restatement of MaxEngine.generate; the reference's JAX path is not installable here)",
+      "kind": ORACLE_KIND,
+      "ms_per_step": 1e3 * dt / done,
+      "steps_run": done,
+      "warmup_run": done_warm,
+      "slots": slots,
+      "sample": f"{slots} of {args.batch} slots of the same workload, {done} decode steps after {done_warm} warm-up{cut}; "
+                "oracle/decode_ref.py (torch CPU, dtype-faithful restatement of MaxEngine.generate; the reference is pure Python/JAX and "
+                "jax is not installable in this image, so nothing of it was compiled or imported: parity of the port is pinned by the "
+                "reference's invariants only)",
   }
 
 
 def run_reference_arm(args):
+  """`--impl reference`: the reference decode arithmetic on the host cores, same workload, metric and unit as the GPU arm.
+  All slots of one GPU's batch, --steps / --warmup honoured (bounded by --cpu-budget-s; what really ran is reported)."""
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return
   cfg = make_config(args)
-  res = cpu_reference_run(args, cfg, args.cpu_slots, max(1, min(args.steps, args.cpu_steps)), warmup=1 if args.warmup else 0)
+  slots = args.cpu_slots or args.batch
+  res = cpu_reference_run(args, cfg, slots, max(1, args.steps), max(0, args.warmup), args.cpu_budget_s)
   line = {
       "impl": "reference",
-      "metric": "audio tokens/s at batch 64 decode (whole job)",
+      "metric": METRIC,
       "value": res["value"],
       "unit": "audio tokens/s",
       "n_gpus": args.gpus,
-      "steps": args.steps,
-      "warmup": args.warmup,
+      "steps": res["steps_run"],
+      "warmup": res["warmup_run"],
+      "steps_requested": args.steps,
+      "warmup_requested": args.warmup,
       "ms_per_step": res["ms_per_step"],
       "higher_is_better": True,
       "scaling": "weak",
       "vs_baseline": None,
       "dtype": "bf16",
       "data": "synthetic",
-      "config": workload_config(args, cfg),
+      "config": workload_config(args, cfg, args.gpus),
       "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
       "e2e": {"value": res["value"], "unit": "audio tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
+      "note": "one host runs ONE batch of the job's slots however many GPUs the job has: the CPU figure does not scale with --gpus",
   }
   print(json.dumps(line))
 
 
-def workload_config(args, cfg):
+def workload_config(args, cfg, world=None):
+  world = world or args.gpus
+  per_gpu = args.batch // world if args.scaling == "strong" else args.batch
   return {
       "workload": f"IndexTTS2-scale text-to-semantic GPT decode step (BASELINE configs[1]): L={cfg.num_decoder_layers} E={cfg.emb_dim} "
                   f"Hq={cfg.num_query_heads} Hkv={cfg.num_kv_heads} D={cfg.head_dim} M={cfg.mlp_dim} V={cfg.vocab_size}, greedy",
-      "batch_per_gpu": args.batch,
-      "global_batch": args.batch * args.gpus,
+      "batch_per_gpu": per_gpu,
+      "global_batch": per_gpu * world,
       "context": f"uniform[{args.context_min},{args.context_max}] valid rows per slot, P={cfg.max_prefill_predict_length} T={cfg.max_target_length}",
-      "parallelism": f"request-batch partitioned x{args.gpus}, no collective",
+      "parallelism": f"request-batch partitioned x{world}, no collective",
       "l2": "working set per step (weights 1.81 GB + KV 1.6 GB) exceeds the 126 MB L2; no flush needed",
   }
 
@@ -308,6 +334,41 @@ def persistent_phase_times(lib, engine, B, sptr, L):
   return out
 
 
+def verify_step(engine, dparams, cfg, B):
+  """Correctness gate of the timed run: ONE more decode step of the state the benchmark just timed, replayed for four slots
+  through the CPU oracle (as the checker; weights downloaded from the device, KV rows of those slots mirrored).  The GPU's
+  greedy token must be the dtype-faithful oracle's argmax, or differ from it only at a near-tie (fp32-oracle margin between the
+  two candidates in bf16 ulps of the top logit is reported)."""
+  from oracle import mirror
+
+  slots = sorted({0, B // 3, (2 * B) // 3, B - 1})
+  weights = mirror.oracle_weights_from_device(dparams, cfg)
+  faithful = mirror.make_oracle(cfg, weights, len(slots), faithful=True)
+  f32 = mirror.make_oracle(cfg, weights, len(slots), faithful=False)
+  fstate = mirror.mirror_state(engine, faithful, slots)
+  gstate = mirror.mirror_state(engine, f32, slots)
+  state, result = engine.generate(dparams, engine._state)
+  torch.cuda.synchronize()
+  got = result.data.cpu()[slots, 0].tolist()
+  fstate, fdata = faithful.generate(fstate)
+  gstate, _ = f32.generate(gstate)
+  want = fdata[:, 0].tolist()
+  ulps, ok = [], True
+  for i, (g, w) in enumerate(zip(got, want)):
+    if g != w:
+      c = mirror.classify_mismatch(gstate["logits"][i, 0], g, w)
+      ulps.append(round(c["ulps"], 2))
+      ok = ok and c["ulps"] <= 8.0
+  return {
+      "ok": bool(ok),
+      "slots": slots,
+      "tokens_equal": sum(int(g == w) for g, w in zip(got, want)),
+      "near_tie_ulps": ulps,
+      "rule": "GPU greedy token == argmax of the dtype-faithful oracle on the same weights and KV rows, or fp32-oracle margin <= 8 bf16 ulps of the top logit",
+      "oracle": ORACLE_KIND,
+  }
+
+
 def main():
   args = parse_args()
   if args.impl == "reference":
@@ -338,11 +399,19 @@ def main():
     _lib.build()
   lib = _lib.load()
 
+  if args.scaling == "strong":
+    if args.batch % world:
+      raise SystemExit(f"--scaling strong: --batch {args.batch} is not divisible by {world} GPUs")
+    args.batch_total, args.batch = args.batch, args.batch // world
   cfg = make_config(args)
-  B = args.batch
+  if args.scaling == "strong":
+    args.batch = args.batch_total  # workload_config / context draw are stated on the global batch
+  B = int(cfg.per_device_batch_size)
   engine = maxengine.MaxEngine(cfg, use_cuda_graph=not args.no_graph)
   dparams = engine.load_params(on_device_init=True)
-  prefill, ar = context_lengths(args, cfg, rank)
+  prefill, ar = context_lengths(args, cfg, rank if args.scaling == "weak" else 0)
+  if args.scaling == "strong":  # one draw for the whole job; this rank owns slots [rank * B, (rank + 1) * B)
+    prefill, ar = prefill[rank * B : (rank + 1) * B], ar[rank * B : (rank + 1) * B]
   state = engine.fill_synthetic_context(prefill, ar)
   ctx_sum = int((prefill + ar).sum()) + B  # the appended row is read too
   step_fn = lib.mtx_decode_step if args.no_graph else lib.mtx_decode_step_graph
@@ -466,12 +535,15 @@ def main():
         "class_gbs": {k: round(per_launch_bytes[k] * counts[KERNEL_CLASSES.index(k)] / (acc[KERNEL_CLASSES.index(k)] * 1e-3) / 1e9, 1)
                       for k in per_launch_bytes if acc[KERNEL_CLASSES.index(k)] > 0},
     }
+    verify = None
+    if not args.no_verify:
+      verify = verify_step(engine, dparams, cfg, B)
     cpu = None
-    if not args.skip_cpu_baseline:
-      cpu = cpu_reference_run(args, cfg, args.cpu_slots, args.cpu_steps)
+    if not args.skip_cpu_baseline and world == 1:
+      cpu = cpu_reference_run(args, cfg, args.cpu_slots or B, args.cpu_steps, 2, min(args.cpu_budget_s, 40.0))
       cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {
-        "metric": "audio tokens/s at batch 64 decode (whole job); decode-step HBM GB/s in roofline.whole_step",
+        "metric": METRIC,
         "value": tokens_per_s,
         "unit": "audio tokens/s",
         "n_gpus": world,
@@ -479,11 +551,11 @@ def main():
         "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step,
         "higher_is_better": True,
-        "scaling": "weak",
+        "scaling": args.scaling,
         "vs_baseline": None,
         "dtype": "bf16",
         "data": "synthetic",
-        "config": workload_config(args, cfg),
+        "config": workload_config(args, cfg, world),
         "e2e": {
             "value": world * B * args.steps / (e2e_ms / 1e3),
             "unit": "audio tokens/s",
@@ -498,6 +570,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "verify": verify,
     }
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)

@@ -104,7 +104,7 @@ def pack_params(params: dict, config, device, vocab_shard: Optional[tuple] = Non
   TMA box of contiguous 128-byte rows; wi_0 / wi_1 are interleaved 16 rows at a time so the
   gate and the value of one MLP feature land in the same warp of the GEMM epilogue.
   """
-  p = params["params"]
+  p = params_lib.unscan_params(params, config)["params"]  # scan_layers=True checkpoints stack the layers on axis 1
   E, Hq, Hkv, D = config.emb_dim, config.num_query_heads, config.num_kv_heads, config.head_dim
   M, L = config.mlp_dim, config.num_decoder_layers
   bf = torch.bfloat16
@@ -146,8 +146,9 @@ def pack_params(params: dict, config, device, vocab_shard: Optional[tuple] = Non
   return DeviceParams(tensors)
 
 
-def random_device_params(config, device, seed: int = 0) -> DeviceParams:
-  """Random-init weights generated directly in HBM (benchmarks; same distributions as params.py)."""
+def random_device_params(config, device, seed: int = 0, norm_jitter: float = 0.0) -> DeviceParams:
+  """Random-init weights generated directly in HBM (benchmarks; same distributions as params.py).
+  `norm_jitter` > 0 draws the RMSNorm scales from N(1, norm_jitter) instead of the init value 1 (parity tests)."""
   g = torch.Generator(device=device).manual_seed(seed)
   E, Hq, Hkv, D = config.emb_dim, config.num_query_heads, config.num_kv_heads, config.head_dim
   M, L, V = config.mlp_dim, config.num_decoder_layers, config.vocab_size
@@ -162,19 +163,24 @@ def random_device_params(config, device, seed: int = 0) -> DeviceParams:
       flat[lo : lo + n] = (torch.randn(n, device=device, generator=g) * std).to(bf)
     return out
 
+  def scale(shape):
+    if norm_jitter <= 0.0:
+      return torch.ones(shape, device=device, dtype=bf)
+    return (1.0 + norm_jitter * torch.randn(shape, device=device, generator=g)).to(bf)
+
   qkv_n = (Hq + 2 * Hkv) * D
   wqkv = rn((L, qkv_n, E), 1.0 / math.sqrt(E))
   wqkv[:, : Hq * D] /= math.sqrt(D)  # attentions.py:1900-1904
   embedding = rn((V, E), 1.0)
   tensors = dict(
       embedding=embedding,
-      attn_norm=torch.ones(L, E, device=device, dtype=bf),
+      attn_norm=scale((L, E)),
       wqkv=wqkv,
       wo=rn((L, E, Hq * D), 1.0 / math.sqrt(Hq * D)),
-      mlp_norm=torch.ones(L, E, device=device, dtype=bf),
+      mlp_norm=scale((L, E)),
       w01=rn((L, 2 * M, E), 1.0 / math.sqrt(E)),
       wout=rn((L, E, M), 1.0 / math.sqrt(M)),
-      final_norm=torch.ones(E, device=device, dtype=bf),
+      final_norm=scale((E,)),
       logits=embedding if config.logits_via_embedding else rn((V, E), 1.0 / math.sqrt(E)),
   )
   return DeviceParams(tensors)
@@ -349,11 +355,12 @@ class MaxEngine:
 
   # -- API -----------------------------------------------------------------------------------
 
-  def load_params(self, params: Optional[dict] = None, rng: Any = None, on_device_init: bool = False) -> DeviceParams:
+  def load_params(self, params: Optional[dict] = None, rng: Any = None, on_device_init: bool = False,
+                  norm_jitter: float = 0.0) -> DeviceParams:
     """maxengine.py:218.  `params` is the reference-named tree (params.py); None = random init."""
     if params is None:
       if on_device_init:
-        dp = random_device_params(self.config, self.device, self.config.init_weights_seed)
+        dp = random_device_params(self.config, self.device, self.config.init_weights_seed, norm_jitter)
         if self._vp_world > 1:
           dp.tensors["logits"] = dp.tensors["logits"][self._v_lo : self._v_hi].contiguous()
           dp = DeviceParams(dp.tensors)

@@ -102,6 +102,56 @@ def init_params(config, seed: int | None = None) -> dict:
   return {"params": params}
 
 
+def unscan_params(params: dict, config) -> dict:
+  """Reference checkpoint layout with ``scan_layers=True`` (base.yml:261-262) -> the per-layer tree above.
+
+  Under scan the decoder stores ONE subtree ``params/decoder/layers/...`` whose leaves carry the layer index on
+  axis ``param_scan_axis`` (default 1; decoders.py:427): scale [E, L], query kernel [E, L, Hq, D], out kernel
+  [Hq, L, D, E], wi_0 [E, L, M], wo [M, L, E].  A tree that already has ``layers_{i}`` is returned unchanged.
+  """
+  dec = params["params"]["decoder"]
+  if "layers_0" in dec:
+    return params
+  if "layers" not in dec:
+    raise ValueError(
+        "parameter tree has neither params/decoder/layers_{i} (scan_layers=False) nor params/decoder/layers "
+        "(scan_layers=True, layer index on axis param_scan_axis)")
+  axis = int(config.param_scan_axis)
+  L = config.num_decoder_layers
+
+  def take(node, i):
+    if isinstance(node, dict):
+      return {k: take(v, i) for k, v in node.items()}
+    if node.shape[axis] != L:
+      raise ValueError(f"scanned leaf of shape {tuple(node.shape)} does not hold {L} layers on axis {axis}")
+    return node.select(axis, i)
+
+  new_dec = {k: v for k, v in dec.items() if k != "layers"}
+  for i in range(L):
+    new_dec[f"layers_{i}"] = take(dec["layers"], i)
+  out = dict(params["params"])
+  out["decoder"] = new_dec
+  return {"params": out}
+
+
+def scan_params(params: dict, config) -> dict:
+  """Inverse of :func:`unscan_params` (tests: builds the layout a scanned reference checkpoint has)."""
+  dec = params["params"]["decoder"]
+  axis = int(config.param_scan_axis)
+  L = config.num_decoder_layers
+
+  def stack(nodes):
+    if isinstance(nodes[0], dict):
+      return {k: stack([n[k] for n in nodes]) for k in nodes[0]}
+    return torch.stack(nodes, dim=axis)
+
+  new_dec = {k: v for k, v in dec.items() if not k.startswith("layers_")}
+  new_dec["layers"] = stack([dec[f"layers_{i}"] for i in range(L)])
+  out = dict(params["params"])
+  out["decoder"] = new_dec
+  return {"params": out}
+
+
 def perturb_norm_scales(params: dict, seed: int = 1) -> dict:
   """Give the RMSNorm scales non-trivial values (tests only need them != 1)."""
   rng = np.random.Generator(np.random.PCG64(seed))

@@ -74,7 +74,9 @@ class OracleWeights:
 
 def prepare_weights(params: dict, config) -> OracleWeights:
   """Cast every kernel to the activation dtype as the reference does at use (linears.py:216)."""
-  p = params["params"]
+  from maxtext_indextts2_b200.params import unscan_params  # layout helper only (scan_layers=True trees)
+
+  p = unscan_params(params, config)["params"]
   E, Hq, Hkv, D = config.emb_dim, config.num_query_heads, config.num_kv_heads, config.head_dim
   f = lambda t: t.to(torch.bfloat16).to(torch.float32)
   layers = []

@@ -23,12 +23,23 @@ def test_header_symbols_are_exported(lib):
     assert hasattr(lib, n), f"{n} declared in include/mtx_b200.h but not exported"
 
 
-def test_built_for_sm_100a_with_tcgen05_and_tma(lib):
+def _check_sass(lib):
   sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
   assert "sm_100a" in sass
   for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):  # tcgen05.mma, TMA load, tcgen05.ld
     assert mnemonic in sass, mnemonic
   assert b"sm_100a" in lib.mtx_build_info()
+
+
+def test_built_for_sm_100a_with_tcgen05_and_tma(lib):
+  """(per-kernel counts: tools/sass_summary.py -> profiles/sass_summary.txt)"""
+  _check_sass(lib)
+
+
+@pytest.mark.gpu
+def test_library_loaded_on_the_gpu_box_is_the_sm_100a_build(lib):
+  """The same check in the `-m gpu` run, on the library the GPU tests actually load."""
+  _check_sass(lib)
 
 
 def test_engine_create_validates_without_a_gpu(lib):

@@ -1,0 +1,213 @@
+"""Oracle parity ON THE BASELINE CONFIGURATIONS THEMSELVES (BASELINE.json configs[1..3]).
+
+The engine runs the full configuration (24 layers, E = 1280, 20/4 heads x 64, M = 5120, V = 264,192; all slots), the
+CPU oracle follows in lock step on the same weights (downloaded from the device) and the same KV cache
+(``oracle/mirror.py``).  Slots never interact inside a step, so where the oracle holds a subset of the slots
+(batch 256) the comparison of those slots is still exact.
+
+Stated tolerances
+* logits vs the dtype-faithful oracle: the reference's own criterion ``rtol = atol = 1e-1``
+  (MaxText/tests/model_test.py:191) on all but 1e-5 of the entries, and 0.25 on every entry: 24 layers deep and
+  17 M logits per step wide, two correct bf16 evaluation orders differ by more than 0.1 on isolated entries -- the
+  test measures the same statistic between the faithful and the fp32 ORACLE and asserts the GPU is no worse;
+* logits vs the fp32 oracle: ``|d| <= 2^-5 max|logit|``;
+* greedy ids: equal to the faithful oracle's, except where the fp32 oracle's margin between the two candidates is
+  within twice the measured logit error of that row (+ one bf16 ulp of the top logit): a near-tie.  Every mismatch
+  is also classified by SURVEY 8c's strict rule (fp32 margin below ONE bf16 ulp of the top logit); the counts and
+  margins are written to ``gpurun_out/parity_stats.jsonl`` and summarised in profiles/ and DESIGN.md.
+"""
+
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from maxtext_indextts2_b200 import maxengine, pyconfig
+from oracle import mirror
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _record(name, stats):
+  out = os.path.join(ROOT, "gpurun_out")
+  try:
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_stats.jsonl"), "a", encoding="utf-8") as f:
+      f.write(json.dumps({"test": name, **stats}) + "\n")
+  except OSError:
+    pass
+  print(name, json.dumps(stats))
+
+
+def _contexts(batch, lo, hi, P, seed=7):
+  rng = np.random.Generator(np.random.PCG64(seed))
+  total = rng.integers(lo, hi + 1, size=batch)
+  prefill = np.minimum(total, P)
+  return prefill.astype(np.int64), (total - prefill).astype(np.int64)
+
+
+def _lockstep(cfg, prefill, ar, slots, steps, name, with_f32=True, expect_launches=None):
+  """Engine on all slots, oracles on `slots`; returns the stats dict (and asserts the tolerances)."""
+  B = int(cfg.per_device_batch_size)
+  engine = maxengine.MaxEngine(cfg, use_cuda_graph=False)
+  dparams = engine.load_params(on_device_init=True, norm_jitter=0.1)
+  state = engine.fill_synthetic_context(prefill, ar, seed=11)
+  weights = mirror.oracle_weights_from_device(dparams, cfg)
+  faithful = mirror.make_oracle(cfg, weights, len(slots), faithful=True)
+  fstate = mirror.mirror_state(engine, faithful, slots)
+  f32 = f32state = None
+  if with_f32:
+    f32 = mirror.make_oracle(cfg, weights, len(slots), faithful=False)
+    f32state = mirror.mirror_state(engine, f32, slots)
+  sl = torch.as_tensor(slots)
+  stats = {"batch": B, "oracle_slots": len(slots), "steps": steps, "tokens": steps * len(slots), "mismatch": 0, "strict_near_tie": 0,
+           "mismatch_ulps": [], "max_abs_vs_faithful": 0.0, "max_abs_vs_f32": 0.0, "max_abs_faithful_vs_f32": 0.0,
+           "frac_outside_1e-1": 0.0, "frac_outside_1e-1_faithful_vs_f32": 0.0, "mean_abs_vs_f32": 0.0, "mean_abs_faithful_vs_f32": 0.0,
+           "oracle_self_mismatch": 0}
+  problems = []
+  for step in range(steps):
+    n0 = engine.lib.mtx_launch_count()
+    state, result = engine.generate(dparams, state)
+    torch.cuda.synchronize()
+    if expect_launches is not None:
+      n = int(engine.lib.mtx_launch_count() - n0)
+      assert expect_launches(n), f"{n} kernel launches per step"
+    tok_in = fstate["tokens"].clone()  # the tokens this step consumes (every side sees the same history)
+    fstate, fdata = faithful.generate(fstate)
+    got = state["logits"].cpu()[sl, 0]  # [n, V]
+    want = fstate["logits"][:, 0]
+    d = (got - want).abs()
+    outside = (d > 0.1 + 0.1 * want.abs()).float().mean().item()
+    stats["max_abs_vs_faithful"] = max(stats["max_abs_vs_faithful"], d.max().item())
+    stats["frac_outside_1e-1"] = max(stats["frac_outside_1e-1"], outside)
+    if d.max().item() > 0.25:
+      problems.append(f"step {step}: |gpu - faithful oracle| max {d.max().item():.3f} > 0.25")
+    if outside > 1e-5:
+      problems.append(f"step {step}: {outside:.2e} of the logits outside rtol = atol = 1e-1")
+    truth = want
+    if f32 is not None:
+      f32state["tokens"] = tok_in
+      f32state, f32data = f32.generate(f32state)
+      truth = f32state["logits"][:, 0]
+      d32 = (got - truth).abs()
+      dff = (want - truth).abs()
+      stats["max_abs_vs_f32"] = max(stats["max_abs_vs_f32"], d32.max().item())
+      stats["max_abs_faithful_vs_f32"] = max(stats["max_abs_faithful_vs_f32"], dff.max().item())
+      stats["mean_abs_vs_f32"] = max(stats["mean_abs_vs_f32"], d32.mean().item())
+      stats["mean_abs_faithful_vs_f32"] = max(stats["mean_abs_faithful_vs_f32"], dff.mean().item())
+      stats["frac_outside_1e-1_faithful_vs_f32"] = max(stats["frac_outside_1e-1_faithful_vs_f32"], (dff > 0.1 + 0.1 * truth.abs()).float().mean().item())
+      stats["max_logit"] = max(stats.get("max_logit", 0.0), truth.abs().max().item())
+      if d32.max().item() > 2**-5 * truth.abs().max().item():
+        problems.append(f"step {step}: |gpu - fp32 oracle| max {d32.max().item():.3f} > 2^-5 * {truth.abs().max().item():.2f}")
+      # the CUDA path is as close to the fp32 truth as the dtype-faithful CPU restatement is
+      if d32.mean().item() > 1.25 * dff.mean().item() + 1e-4:
+        problems.append(f"step {step}: mean |gpu - fp32| {d32.mean().item():.4f} vs mean |faithful - fp32| {dff.mean().item():.4f}")
+      stats["oracle_self_mismatch"] += int((f32data[:, 0] != fdata[:, 0]).sum())
+    data = result.data.cpu()
+    assert torch.equal(data[sl, 1:], fdata[:, 1:])
+    for i, s in enumerate(slots):
+      g, w = int(data[s, 0]), int(fdata[i, 0])
+      if g != w:
+        c = mirror.classify_mismatch(truth[i], g, w)
+        err = (got[i] - truth[i]).abs().max().item()
+        stats["mismatch"] += 1
+        stats["strict_near_tie"] += int(c["strict"])
+        stats["mismatch_ulps"].append(round(c["ulps"], 2))
+        if c["margin"] > 2 * err + mirror.bf16_ulp(c["top"]):
+          problems.append(f"step {step} slot {s}: token {g} vs oracle {w}, fp32 margin {c['margin']:.4f} ({c['ulps']:.1f} ulps), row error {err:.4f}")
+    # teacher-force the faithful oracle's tokens so every side sees the same history
+    state["tokens"][sl.to(state["tokens"].device)] = fdata[:, :1].to(state["tokens"].device)
+  stats["problems"] = problems
+  _record(name, stats)
+  assert not problems, "; ".join(problems[:8])
+  return stats
+
+
+def test_headline_batch64_full_scale_against_the_oracle():
+  """BASELINE configs[1] / SURVEY C2, the configuration bench.py times: batch 64, P = 1024, T = 3072, V = 264,192, contexts
+  uniform in [512, 1536] (seed 7), persistent step kernel (3 launches per step), all 64 slots in both oracles."""
+  cfg = pyconfig.initialize(None, model_name="indextts2-t2s", per_device_batch_size=64, materialize_logits=True)
+  prefill, ar = _contexts(64, 512, 1536, cfg.max_prefill_predict_length)
+  stats = _lockstep(cfg, prefill, ar, list(range(64)), steps=6, name="C2_batch64", expect_launches=lambda n: n == 3)
+  assert stats["mismatch"] <= 0.02 * stats["tokens"]
+
+
+def test_batch256_context2048_against_the_oracle():
+  """BASELINE configs[2] / SURVEY C3: batch 256, every context 2048 (P = 1024 + 1024 ring rows), per-kernel path; the oracle
+  follows 12 of the 256 slots (first, last and a spread)."""
+  cfg = pyconfig.initialize(None, model_name="indextts2-t2s", per_device_batch_size=256, materialize_logits=True)
+  prefill = np.full(256, 1024, dtype=np.int64)
+  ar = np.full(256, 1024, dtype=np.int64)
+  slots = [0, 1, 31, 63, 64, 100, 127, 128, 191, 200, 254, 255]
+  stats = _lockstep(cfg, prefill, ar, slots, steps=2, name="C3_batch256_ctx2048", with_f32=False, expect_launches=lambda n: n > 3)
+  assert stats["mismatch"] <= 1
+
+
+@pytest.mark.parametrize("batch", [1, 8])
+def test_long_prompt_config_against_the_oracle(batch):
+  """BASELINE configs[3] / SURVEY C4: P = 4096, T = 5632, prompt length 4000, part of the 1.5k-token decode already done
+  (ring rows 100..1500): the persistent kernel's long-pair partition (one pair spans many CTAs) against the oracle."""
+  cfg = pyconfig.initialize(None, model_name="indextts2-t2s", per_device_batch_size=batch, max_prefill_predict_length=4096,
+                            max_target_length=5632, materialize_logits=True)
+  rng = np.random.Generator(np.random.PCG64(40 + batch))
+  prefill = np.full(batch, 4000, dtype=np.int64)
+  ar = rng.integers(100, 1500, size=batch).astype(np.int64)
+  ar[0] = 1499
+  stats = _lockstep(cfg, prefill, ar, list(range(batch)), steps=3, name=f"C4_long_prompt_batch{batch}", expect_launches=lambda n: n == 3)
+  assert stats["mismatch"] <= 1
+
+
+def test_near_tie_rate_tiny_config_320_greedy_steps():
+  """BASELINE configs[0] / SURVEY C1 model (4 layers, E = 256, V = 264,192, batch 1, greedy) decoded for 320 steps (ring of 320
+  rows after a 37-token prompt), both oracles in lock step: how often does the CUDA path pick another token than the faithful
+  oracle, and how many of those are near-ties by SURVEY 8c's strict rule?"""
+  from oracle import decode_ref as ref
+  from tests.helpers import make_params
+
+  cfg = pyconfig.initialize(None, model_name="tiny-audio", materialize_logits=True, max_target_length=64 + 320)
+  params = make_params(cfg, perturb=True)
+  faithful = ref.DecodeOracle(cfg, params, faithful=True)
+  f32 = ref.DecodeOracle(cfg, params, faithful=False)
+  engine = maxengine.MaxEngine(cfg)
+  dparams = engine.load_params(params)
+  rng = np.random.Generator(np.random.PCG64(1234))
+  prompt = torch.from_numpy(rng.integers(0, 262144, size=64, dtype=np.int64))
+  fprefix, ffirst = faithful.prefill(prompt, 37)
+  fstate = faithful.insert(fprefix, faithful.init_decode_state(), 0)
+  gprefix, _ = f32.prefill(prompt, 37)
+  gprefix["tokens"] = fprefix["tokens"].clone()
+  gstate = f32.insert(gprefix, f32.init_decode_state(), 0)
+  prefix, _ = engine.prefill(params=dparams, padded_tokens=prompt, true_length=37)
+  prefix["tokens"].fill_(int(ffirst))
+  state = engine.insert(prefix, engine.init_decode_state(), 0)
+  steps = 320
+  stats = {"steps": steps, "mismatch": 0, "strict_near_tie": 0, "mismatch_ulps": [], "oracle_self_mismatch": 0, "max_abs_vs_faithful": 0.0,
+           "max_abs_vs_f32": 0.0, "max_abs_faithful_vs_f32": 0.0}
+  for step in range(steps):
+    fstate, fdata = faithful.generate(fstate)
+    gstate, gdata = f32.generate(gstate)
+    state, result = engine.generate(dparams, state)
+    got = state["logits"].cpu()[0, 0]
+    want, truth = fstate["logits"][0, 0], gstate["logits"][0, 0]
+    torch.testing.assert_close(got, want, rtol=1e-1, atol=1e-1)
+    assert (got - truth).abs().max() <= 2**-5 * truth.abs().max()
+    stats["max_abs_vs_faithful"] = max(stats["max_abs_vs_faithful"], (got - want).abs().max().item())
+    stats["max_abs_vs_f32"] = max(stats["max_abs_vs_f32"], (got - truth).abs().max().item())
+    stats["max_abs_faithful_vs_f32"] = max(stats["max_abs_faithful_vs_f32"], (want - truth).abs().max().item())
+    stats["oracle_self_mismatch"] += int(gdata[0, 0] != fdata[0, 0])
+    g, w = int(result.data[0, 0]), int(fdata[0, 0])
+    if g != w:
+      c = mirror.classify_mismatch(truth, g, w)
+      err = (got - truth).abs().max().item()
+      stats["mismatch"] += 1
+      stats["strict_near_tie"] += int(c["strict"])
+      stats["mismatch_ulps"].append(round(c["ulps"], 2))
+      assert c["margin"] <= 2 * err + mirror.bf16_ulp(c["top"]), f"step {step}: token {g} vs {w}: fp32 margin {c['margin']:.4f} ({c['ulps']:.1f} ulps), row error {err:.4f}"
+    state["tokens"].copy_(fdata[:, :1])
+    gstate["tokens"] = fdata[:, :1].clone()
+  _record("C1_tiny_320_steps", stats)
+  assert stats["mismatch"] <= 0.03 * steps
