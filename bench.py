@@ -52,6 +52,7 @@ def parse_args():
   ap.add_argument("--prefill-len", type=int, default=0, help="override max_prefill_predict_length (BASELINE configs[3]: 4096)")
   ap.add_argument("--target-len", type=int, default=0, help="override max_target_length (BASELINE configs[3]: 5632)")
   ap.add_argument("--no-graph", action="store_true")
+  ap.add_argument("--no-fold", action="store_true", help="keep the RMSNorm scales out of the weights (fold_norm_scales=False)")
   ap.add_argument("--skip-cpu-baseline", action="store_true")
   ap.add_argument("--cpu-slots", type=int, default=0, help="slots in the CPU baseline sample (0 = all slots of the batch)")
   ap.add_argument("--cpu-steps", type=int, default=8, help="timed steps of the cpu_baseline leg of the GPU arm (after 2 warm-ups)")
@@ -70,6 +71,8 @@ def make_config(args):
     kw["max_prefill_predict_length"] = args.prefill_len
   if args.target_len:
     kw["max_target_length"] = args.target_len
+  if args.no_fold:
+    kw["fold_norm_scales"] = False
   return pyconfig.initialize(None, model_name=args.model, per_device_batch_size=args.batch, **kw)
 
 

@@ -66,6 +66,8 @@ typedef struct {
   float final_softcap;       /* final_logits_soft_cap, 0 = off */
   float logits_scale;        /* 1, or 1/sqrt(E) when logits_via_embedding && normalize_embedding_logits */
   int32_t logits_round_bf16; /* 1 unless logits_dot_in_fp32 (decoders.py:557,571) */
+  int32_t norm_scales_folded; /* 1: wqkv / w01 already carry the per-feature RMSNorm scales of their input (W' = W * diag(scale),
+                                 folded at load time) and attn_norm / mlp_norm are all ones: the step skips the scale pass */
 } mtx_model_config;
 
 /* Weights, repacked once at load time for K-major streaming (see DESIGN.md "Data layout").

@@ -53,6 +53,7 @@ class ModelConfig(ctypes.Structure):
       ("final_softcap", ctypes.c_float),
       ("logits_scale", ctypes.c_float),
       ("logits_round_bf16", ctypes.c_int32),
+      ("norm_scales_folded", ctypes.c_int32),
   ]
 
 

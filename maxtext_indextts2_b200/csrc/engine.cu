@@ -560,6 +560,7 @@ int launch_persistent(mtx_engine* e, int rows, const XMaps& xm, const EpiArgs& l
   p.grid_bar = e->grid_bar;
   p.trace = g_trace;
   p.variant = env_int("MTX_PK_VARIANT", 0);
+  p.fold = c.norm_scales_folded ? 1 : 0;
   return launch(step_persistent_kernel, dim3(e->pk_ctas), dim3(kPkThreads), pk_smem_bytes(), st, e->tm_all_wqkv, e->tm_all_wo, e->tm_all_w01,
                 e->tm_all_wout, e->tm_logits, xm.x, xm.attn, xm.h, xm.act, xm.n, e->tm_k, e->tm_v, p);
 }

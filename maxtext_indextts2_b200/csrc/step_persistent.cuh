@@ -137,7 +137,9 @@ struct PkParams {
   EpiArgs logits;
   unsigned int* grid_bar;  // zeroed by prepare_rows_kernel
   long long* trace;        // debug: globaltimer at [barrier k][arrive|release][cta], or null
-  int variant;             // debug knob (MTX_PK_VARIANT)
+  int variant;             // experiment switches (MTX_PK_VARIANT): bit 0 = L2 prefetch of the next layer's K/V tiles at the end of a
+                           // warp's tile loop, bit 1 = L2 prefetch of this layer's K/V tiles at the start of the layer
+  int fold;                // 1: the RMSNorm scales are folded into wqkv / w01 (mtx_model_config.norm_scales_folded): no scale pass
 };
 
 // ---- small helpers -----------------------------------------------------------------------
@@ -170,6 +172,10 @@ __device__ __forceinline__ void pk_ev(PkEv& e, int id) {
 #endif
 }
 
+// Pulls one box of a tensor map into L2 (no shared-memory destination, no completion to wait for).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* tm, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
   uint32_t v;
@@ -999,6 +1005,15 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
     }
   }
 
+  // The HBM is idle for most of the GEMM phases that follow: ask for the next layer's K/V tiles of this warp now, so that its
+  // next tile loop streams from L2 (the list is the same for every layer; a tile is 8 KB, a warp holds ~6).
+  if ((p.variant & 1) && layer + 1 < p.L) {
+    const int next_layer_row = layer_row + p.num_slots * p.hkv * p.T;
+    for (int i = lane; i < n; i += 32) {
+      tma_prefetch_l2_2d(&tm_k, 0, next_layer_row + list[i].x);
+      tma_prefetch_l2_2d(&tm_v, 0, next_layer_row + list[i].x);
+    }
+  }
   // ---- phase 2: the CTA's merge jobs (static plan, see pk_attn_build_list) ----
   if (lane == 0) pk_ev(ev, 610);
   named_bar_sync(3, kPkAttnWarps * 32);
@@ -1576,7 +1591,7 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
     auto x_phase = [&](int ph, int layer) {
       const int nu = ph == PK_LOGITS ? logits_tiles : tab.n_units[ph];
       if (nu == 0) return;
-      const bool xform = ph == PK_QKV || ph == PK_UP;
+      const bool xform = (ph == PK_QKV || ph == PK_UP) && !p.fold;
       const CUtensorMap* tmx = ph == PK_QKV ? &tm_x : ph == PK_OPROJ ? &tm_attn : ph == PK_UP ? &tm_h : ph == PK_DOWN ? &tm_act : &tm_n;
       pk_wait_flag(&tail->bar_done, pk_need(layer, ph, p.L));
       fence_proxy_async_all();  // activations written with generic stores by other CTAs, read through TMA
@@ -1685,7 +1700,7 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
     // Between attention phases: warps 6-9 normalise (QKV, MLP up), lane 0 of warp 10 requests activation tiles,
     // everybody else just keeps the ring cursor in step.
     auto gemm_duty = [&](int ph, int layer) {
-      const bool xform = ph == PK_QKV || ph == PK_UP;
+      const bool xform = (ph == PK_QKV || ph == PK_UP) && !p.fold;
       if (xformer && xform) {
         transform_phase(ph, layer);
       } else if (xproducer && lane == 0) {
@@ -1700,6 +1715,15 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
       ev.on = ev.brief ? (l & 1) == 0 && l < 32 : l == 1;
 #pragma unroll 1  // one copy of the duty code
       for (int ph = 0; ph < 4; ++ph) {
+        if (ph == PK_QKV && ((p.variant & 2) || ((p.variant & 1) && l == 0))) {
+          // this layer's K/V tiles towards L2 while the QKV phase runs (the row appended by that phase is written later: L2 stays coherent)
+          const int lrow = l * p.num_slots * p.hkv * p.T;
+          const int n_own = tail->a_count[aw];
+          for (int i = lane; i < n_own; i += 32) {
+            tma_prefetch_l2_2d(&tm_k, 0, lrow + tail->a_list[aw][i].x);
+            tma_prefetch_l2_2d(&tm_v, 0, lrow + tail->a_list[aw][i].x);
+          }
+        }
         gemm_duty(ph, l);
         if (ph == PK_UP && up_shared) {
           __syncwarp();

@@ -82,10 +82,15 @@ class ResultTokens:
 
 
 class DeviceParams:
-  """Weights in the layout of ``mtx_weights`` (include/mtx_b200.h), resident in HBM."""
+  """Weights in the layout of ``mtx_weights`` (include/mtx_b200.h), resident in HBM.
 
-  def __init__(self, tensors: dict):
+  `folded`: wqkv / w01 carry the RMSNorm scales of their input and attn_norm / mlp_norm are ones
+  (see :func:`fold_norm_scales`); `source` is then the unfolded original (kept for checkers), else None."""
+
+  def __init__(self, tensors: dict, folded: bool = False, source: "Optional[DeviceParams]" = None):
     self.tensors = tensors
+    self.folded = folded
+    self.source = source
     self.struct = _lib.Weights(**{k: v.data_ptr() for k, v in tensors.items()})
 
   def nbytes(self) -> int:
@@ -95,6 +100,32 @@ class DeviceParams:
         seen.add(t.data_ptr())
         total += t.numel() * t.element_size()
     return total
+
+
+def fold_norm_scales(dp: DeviceParams) -> DeviceParams:
+  """W' = bf16(W * diag(scale)) for the two projections that consume a normalised activation, scales -> 1.
+
+  normalizations.py:57-69 computes ``bf16(bf16(x * rstd) * scale)`` and linears.py:216 multiplies that by ``bf16(W)``;
+  ``rstd * dot(x, bf16(scale * W))`` is the same product with the per-feature factor rounded into the weight instead of
+  into the activation (one bf16 rounding per term either way; the difference is measured by the parity tests, which
+  keep the oracle on the UNFOLDED weights).  What it buys: the decode step no longer touches the activation tiles
+  between their arrival and the MMA.  When every scale is exactly 1 (random init) this is the identity
+  and nothing is copied."""
+  if dp.folded:
+    return dp
+  t = dp.tensors
+  an, mn = t["attn_norm"], t["mlp_norm"]
+  if bool((an == 1).all()) and bool((mn == 1).all()):
+    return DeviceParams(t, folded=True, source=None)
+  new = dict(t)
+  new["wqkv"] = (t["wqkv"].float() * an.float()[:, None, :]).to(torch.bfloat16).contiguous()
+  w01 = torch.empty_like(t["w01"])
+  for l in range(w01.shape[0]):  # layer by layer: the fp32 temporary of the whole tensor would be 1.3 GB
+    w01[l] = (t["w01"][l].float() * mn[l].float()[None, :]).to(torch.bfloat16)
+  new["w01"] = w01
+  new["attn_norm"] = torch.ones_like(an)
+  new["mlp_norm"] = torch.ones_like(mn)
+  return DeviceParams(new, folded=True, source=dp)
 
 
 def pack_params(params: dict, config, device, vocab_shard: Optional[tuple] = None) -> DeviceParams:
@@ -244,6 +275,7 @@ class MaxEngine:
         final_softcap=float(config.final_logits_soft_cap or 0.0),
         logits_scale=scale,
         logits_round_bf16=0 if config.logits_dot_in_fp32 else 1,
+        norm_scales_folded=1 if config.fold_norm_scales else 0,
     )
     _lib.check(self.lib.mtx_engine_create(ctypes.byref(self._cfg_struct), ctypes.byref(self._handle)))
     ws = self.lib.mtx_engine_workspace_bytes(self._handle)
@@ -335,6 +367,8 @@ class MaxEngine:
   def _bind(self, params: DeviceParams) -> None:
     if self._bound_params is params:
       return
+    if bool(self.config.fold_norm_scales) != bool(params.folded):
+      raise ValueError("pass the DeviceParams returned by this engine's load_params (fold_norm_scales decides their layout)")
     _lib.check(
         self.lib.mtx_engine_bind(
             self._handle, ctypes.byref(params.struct), ctypes.byref(self._state_struct), ctypes.c_void_p(self._ws_ptr), self._ws_bytes
@@ -370,6 +404,10 @@ class MaxEngine:
       dp = params
     else:
       dp = pack_params(params, self.config, self.device, self._shard_or_none())
+    if self.config.fold_norm_scales:
+      dp = fold_norm_scales(dp)
+    elif dp.folded and dp.source is not None:
+      raise ValueError("these DeviceParams carry folded RMSNorm scales but fold_norm_scales=False")
     self._params = dp
     self._bind(dp)
     return dp

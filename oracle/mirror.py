@@ -22,6 +22,7 @@ from . import decode_ref as ref
 
 def oracle_weights_from_device(dparams, cfg) -> ref.OracleWeights:
   """Packed K-major device tensors (include/mtx_b200.h ``mtx_weights``) -> matmul-ready fp32 oracle weights."""
+  dparams = getattr(dparams, "source", None) or dparams  # the oracle stays on the UNFOLDED weights (maxengine.fold_norm_scales)
   t = dparams.tensors
   E, Hq, Hkv, D, M = cfg.emb_dim, cfg.num_query_heads, cfg.num_kv_heads, cfg.head_dim, cfg.mlp_dim
   f = lambda x: x.detach().to("cpu").to(torch.float32)
