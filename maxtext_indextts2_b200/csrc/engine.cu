@@ -13,6 +13,7 @@
 
 #include "../../include/mtx_b200.h"
 #include "attention.cuh"
+#include "gemm_rows.cuh"
 #include "gemm_umma.cuh"
 #include "sampling.cuh"
 #include "step_kernels.cuh"
@@ -206,6 +207,66 @@ int launch_gemm(const CUtensorMap& tw, const CUtensorMap& tx, GemmParams p, cons
   return rc;
 }
 
+// ---- steps of 65..256 rows: gemm_rows.cuh ------------------------------------------------------
+struct RowsPlan {
+  int n_tiles, splits, stages, grid_x, row_blocks, r_tile_cta;
+  size_t smem;
+};
+
+RowsPlan plan_rows(int n, int k, int r_tile, int num_sms, int epi, int forced_splits = 0) {
+  RowsPlan g;
+  g.n_tiles = (n + kTileN - 1) / kTileN;
+  const int kb = k / kBlockK;
+  int splits = forced_splits;
+  if (splits <= 0) {
+    splits = 1;
+    // few tiles: cut K over a cluster of up to 8 CTAs (the portable maximum; two such clusters fit a GPC) until the
+    // grid covers most of the SMs.  Many tiles: one persistent CTA per SM walks them with double-buffered accumulators.
+    // (a split unit covers one 128-row block, and two units fit one SM: up to 1.25 units per SM)
+    if (epi != EPI_LOGITS && g.n_tiles * 2 <= num_sms) {
+      const int max_split = env_int("MTX_ROWS_MAX_SPLIT", 8);
+      const int zb = r_tile / 128;
+      while (splits * 2 <= max_split && splits * 2 <= kb && g.n_tiles * zb * splits * 2 <= num_sms + num_sms / 4) splits *= 2;
+    }
+  }
+  g.splits = splits;
+  g.row_blocks = splits > 1 ? r_tile / 128 : 1;
+  g.r_tile_cta = splits > 1 ? 128 : r_tile;
+  r_tile = g.r_tile_cta;
+  const int stage_bytes = kWTileBytes + r_tile * kBlockK * 2;
+  int stages = ((splits > 1 ? 96 : 192) * 1024) / stage_bytes;
+  const int max_kb = splits > 1 ? (kb + splits - 1) / splits : kb * 2;
+  if (stages > max_kb) stages = max_kb;
+  if (stages > kRowsMaxStages) stages = kRowsMaxStages;
+  if (stages < 1) stages = 1;
+  g.stages = stages;
+  g.grid_x = splits > 1 ? g.n_tiles : (g.n_tiles < num_sms ? g.n_tiles : num_sms);
+  g.smem = rows_smem_bytes(stages, r_tile, splits);
+  return g;
+}
+
+template <int EPI>
+int launch_rows(const CUtensorMap& tw, const CUtensorMap& tx, GemmParams p, const EpiArgs& e, const RowsPlan& g, cudaStream_t st) {
+  static bool attr_set = false;  // per template instance
+  if (!attr_set) {
+    MTX_CUDA(cudaFuncSetAttribute(gemm_rows_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  p.splits = g.splits;
+  p.stages = g.stages;
+  p.r_tile = g.r_tile_cta;
+  p.trace = g_trace;
+  g_cluster_y = g.splits;
+  const int rc = launch(gemm_rows_kernel<EPI>, dim3(g.grid_x, g.splits, g.row_blocks), dim3(kRowsThreads), g.smem, st, tw, tx, p, e);
+  g_cluster_y = 1;
+  return rc;
+}
+
+bool use_rows_kernel(int r_tile) {
+  static int on = env_int("MTX_ROWS_KERNEL", 1);
+  return on != 0 && r_tile >= 128;
+}
+
 struct XMaps {
   bool built = false;
   CUtensorMap n, attn, act, x, h;
@@ -249,6 +310,7 @@ struct mtx_engine {
   unsigned int* grid_bar = nullptr;
   PkTable* pk_tables = nullptr;
   float *pk_part_ws = nullptr, *pk_ss_x = nullptr, *pk_ss_h = nullptr, *pk_attn_part_o = nullptr;
+  float *rows_ss_x = nullptr, *rows_ss_h = nullptr;  // gemm_rows.cuh fused RMSNorm statistics: [E/128 rounded up][max_r_tile]
   int *pk_tile_prefix = nullptr, *pk_attn_info = nullptr;
   XMaps xmaps[5];
   // sampling
@@ -266,6 +328,7 @@ struct WsLayout {
   size_t token, pos, plane, write_row, len0, ring_first, ring_len, rope_cs, work_items, work_count, rope_timescale;
   size_t part_score, part_idx, part_raw, part_max, part_sum, grid_bar;
   size_t pk_tables, pk_part_ws, pk_ss_x, pk_ss_h, pk_attn_part_o, pk_tile_prefix, pk_attn_info;
+  size_t rows_ss_x, rows_ss_h;
   size_t total;
 };
 
@@ -318,6 +381,8 @@ WsLayout layout_workspace(const mtx_engine* e) {
     L.pk_attn_part_o = take(pairs * kPkMaxParts * ((G * c.head_dim + 2 * G + 3) / 4 * 4) * 4);
     L.pk_tile_prefix = take((pk_rows + 1) * 4);
     L.pk_attn_info = take(64);
+    L.rows_ss_x = take(rt * ss_tiles * 4);
+    L.rows_ss_h = take(rt * ss_tiles * 4);
   }
   L.total = off;
   return L;
@@ -612,9 +677,29 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   gp.rows = rows;
   gp.r_tile = r_tile;
   const GemmPlan plan_logits = plan_gemm(c.vocab_size, c.emb_dim, r_tile, e->num_sms, EPI_LOGITS, 1);
+  const bool rows_k = use_rows_kernel(r_tile);  // 65..256 rows: the row-major tensor-core GEMM (gemm_rows.cuh)
+  XMaps* xm128 = xm;  // split-K units of that kernel load 128-row activation boxes
+  if (rows_k) MTX_TRY(get_xmaps(e, 128, &xm128));
+  auto xmap = [&](const RowsPlan& pl, CUtensorMap XMaps::*m) -> const CUtensorMap& { return pl.splits > 1 ? xm128->*m : xm->*m; };
+  // 65..256 rows with the norm scales folded into the weights: RMSNorm is fused into the GEMMs around it (the residual
+  // epilogues leave the row statistics, the consuming epilogues apply rstd; the per-kernel rmsnorm launches disappear)
+  const bool fused_norm = rows_k && c.norm_scales_folded && env_int("MTX_ROWS_FUSED_NORM", 1) != 0;
+  const int ss_tiles = (E + 127) / 128;
+  auto ss_args = [&](EpiArgs& ea, const float* in, float* out) {
+    ea.ss_in = fused_norm ? in : nullptr;
+    ea.ss_out = fused_norm ? out : nullptr;
+    ea.ss_tiles = ss_tiles;
+    ea.ss_pitch = e->max_r_tile;
+    ea.ss_dim = E;
+    ea.ss_eps = c.rms_eps;
+  };
   if (!mega) {
   const bf16* attn_norm = static_cast<const bf16*>(e->w.attn_norm);
   const bf16* mlp_norm = static_cast<const bf16*>(e->w.mlp_norm);
+  if (fused_norm)
+    MTX_TRY(launch(embed_gather_ss_kernel, dim3(rows), dim3(128), 0, st, (const int*)e->rd.token, static_cast<const bf16*>(e->w.embedding), e->x,
+                   e->rows_ss_x, ss_tiles, e->max_r_tile, E));
+  else
   MTX_TRY(launch(rmsnorm_kernel<true>, dim3(rows), dim3(128), 0, st, (const bf16*)nullptr, (const int*)e->rd.token,
                  static_cast<const bf16*>(e->w.embedding), attn_norm, e->x, e->n, E, c.rms_eps));
 
@@ -639,7 +724,12 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     gp.n = e->qkv_n;
     gp.k = E;
     g_class = KC_QKV;
-    MTX_TRY(launch_gemm<EPI_QKV_ROPE>(e->tm_wqkv[l], xm->n, gp, ea, plan_qkv, st));
+    ss_args(ea, e->rows_ss_x, nullptr);
+    if (rows_k) {
+      const RowsPlan pl = plan_rows(e->qkv_n, E, r_tile, e->num_sms, EPI_QKV_ROPE);
+      MTX_TRY(launch_rows<EPI_QKV_ROPE>(e->tm_wqkv[l], xmap(pl, fused_norm ? &XMaps::x : &XMaps::n), gp, ea, pl, st));
+    }
+    else MTX_TRY(launch_gemm<EPI_QKV_ROPE>(e->tm_wqkv[l], xm->n, gp, ea, plan_qkv, st));
 
     g_class = KC_ATTENTION;
     MTX_TRY(launch_attention(e, l, rows, st));
@@ -651,9 +741,15 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     gp.n = E;
     gp.k = HD;
     g_class = KC_OUTPROJ;
-    MTX_TRY(launch_gemm<EPI_RESIDUAL>(e->tm_wo[l], xm->attn, gp, ea, plan_o, st));
+    ss_args(ea, nullptr, e->rows_ss_h);
+    if (rows_k) {
+      const RowsPlan pl = plan_rows(E, HD, r_tile, e->num_sms, EPI_RESIDUAL);
+      MTX_TRY(launch_rows<EPI_RESIDUAL>(e->tm_wo[l], xmap(pl, &XMaps::attn), gp, ea, pl, st));
+    }
+    else MTX_TRY(launch_gemm<EPI_RESIDUAL>(e->tm_wo[l], xm->attn, gp, ea, plan_o, st));
 
     g_class = KC_RMSNORM;
+    if (!fused_norm)
     MTX_TRY(launch(rmsnorm_kernel<false>, dim3(rows), dim3(128), 0, st, (const bf16*)e->h, (const int*)nullptr,
                    (const bf16*)nullptr, mlp_norm + size_t(l) * E, (bf16*)nullptr, e->n, E, c.rms_eps));
 
@@ -663,7 +759,12 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     gp.n = 2 * M;
     gp.k = E;
     g_class = KC_MLP_UP;
-    MTX_TRY(launch_gemm<EPI_SWIGLU>(e->tm_w01[l], xm->n, gp, ea, plan_up, st));
+    ss_args(ea, e->rows_ss_h, nullptr);
+    if (rows_k) {
+      const RowsPlan pl = plan_rows(2 * M, E, r_tile, e->num_sms, EPI_SWIGLU);
+      MTX_TRY(launch_rows<EPI_SWIGLU>(e->tm_w01[l], xmap(pl, fused_norm ? &XMaps::h : &XMaps::n), gp, ea, pl, st));
+    }
+    else MTX_TRY(launch_gemm<EPI_SWIGLU>(e->tm_w01[l], xm->n, gp, ea, plan_up, st));
 
     memset(&ea, 0, sizeof(ea));
     ea.out = e->x;
@@ -672,11 +773,16 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     gp.n = E;
     gp.k = M;
     g_class = KC_MLP_DOWN;
-    MTX_TRY(launch_gemm<EPI_RESIDUAL>(e->tm_wout[l], xm->act, gp, ea, plan_down, st));
+    ss_args(ea, nullptr, e->rows_ss_x);
+    if (rows_k) {
+      const RowsPlan pl = plan_rows(E, M, r_tile, e->num_sms, EPI_RESIDUAL);
+      MTX_TRY(launch_rows<EPI_RESIDUAL>(e->tm_wout[l], xmap(pl, &XMaps::act), gp, ea, pl, st));
+    }
+    else MTX_TRY(launch_gemm<EPI_RESIDUAL>(e->tm_wout[l], xm->act, gp, ea, plan_down, st));
 
     g_class = KC_RMSNORM;
     const bf16* next_scale = l + 1 < L ? attn_norm + size_t(l + 1) * E : static_cast<const bf16*>(e->w.final_norm);
-    if (l + 1 < L || want_logits)
+    if ((l + 1 < L && !fused_norm) || (l + 1 == L && want_logits))
       MTX_TRY(launch(rmsnorm_kernel<false>, dim3(rows), dim3(128), 0, st, (const bf16*)e->x, (const int*)nullptr,
                      (const bf16*)nullptr, next_scale, (bf16*)nullptr, e->n, E, c.rms_eps));
   }
@@ -713,6 +819,8 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     if (mega) {
       g_class = KC_PERSISTENT;
       MTX_TRY(launch_persistent(e, rows, *xm, ea, st));
+    } else if (rows_k) {
+      MTX_TRY(launch_rows<EPI_LOGITS>(e->tm_logits, xm->n, gp, ea, plan_rows(c.vocab_size, E, r_tile, e->num_sms, EPI_LOGITS), st));
     } else {
       MTX_TRY(launch_gemm<EPI_LOGITS>(e->tm_logits, xm->n, gp, ea, plan_logits, st));
     }
@@ -881,6 +989,8 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   e->pk_attn_part_o = reinterpret_cast<float*>(b + L.pk_attn_part_o);
   e->pk_tile_prefix = reinterpret_cast<int*>(b + L.pk_tile_prefix);
   e->pk_attn_info = reinterpret_cast<int*>(b + L.pk_attn_info);
+  e->rows_ss_x = reinterpret_cast<float*>(b + L.rows_ss_x);
+  e->rows_ss_h = reinterpret_cast<float*>(b + L.rows_ss_h);
   MTX_CUDA(cudaMemcpy(e->rope_timescale, e->rope_timescale_host.data(), e->rope_timescale_host.size() * 4, cudaMemcpyHostToDevice));
 
   const int E = c.emb_dim, HD = c.num_q_heads * c.head_dim, M = c.mlp_dim, L_ = c.num_layers;
@@ -1084,6 +1194,21 @@ int mtx_linear(const void* x, const void* w, void* out, int rows, int n, int k, 
   CUtensorMap tw, tx;
   MTX_TRY(make_map(&tw, w, k, n, kTileN));
   MTX_TRY(make_map(&tx, x, k, r_tile, r_tile));
+  if (use_rows_kernel(r_tile) && splits <= 8) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.n = n;
+    p.k = k;
+    p.rows = rows;
+    p.r_tile = r_tile;
+    EpiArgs e;
+    memset(&e, 0, sizeof(e));
+    e.out = static_cast<bf16*>(out);
+    e.ld_out = n;
+    const RowsPlan pl = plan_rows(n, k, r_tile, 148, EPI_STORE_BF16, splits);
+    if (pl.splits > 1) MTX_TRY(make_map(&tx, x, k, r_tile, 128));
+    return launch_rows<EPI_STORE_BF16>(tw, tx, p, e, pl, static_cast<cudaStream_t>(stream));
+  }
   const GemmPlan g = plan_gemm(n, k, r_tile, 148, EPI_STORE_BF16, splits);
   GemmParams p;
   memset(&p, 0, sizeof(p));

@@ -83,6 +83,13 @@ struct EpiArgs {
   int want_lse;        // 1 = also produce the log-sum-exp partials (return_log_prob)
   const uint32_t* rng_state;  // [4]: step, seed_lo, seed_hi, unused (device memory: graph replays see updates)
   int row_offset;
+  // gemm_rows.cuh only: RMSNorm fused into the GEMMs around it (norm scales folded into the weights).  A residual epilogue
+  // leaves the per-row sums of squares of its output, one partial per 128-feature tile, in ss_out[tile * ss_pitch + row]; a
+  // GEMM whose input is that output multiplies its accumulator by rstd[row] = rsqrt(sum_t ss_in[t * ss_pitch + row] / ss_dim + eps).
+  const float* ss_in;
+  float* ss_out;
+  int ss_tiles, ss_pitch, ss_dim;
+  float ss_eps;
 };
 
 

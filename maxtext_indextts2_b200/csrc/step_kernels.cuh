@@ -194,6 +194,34 @@ rmsnorm_kernel(const bf16* __restrict__ x_in, const int* __restrict__ tokens, co
   timeline_end(tl);
 }
 
+// Embedding gather (embeddings.py:154) that also leaves the row's sum of squares as the first RMSNorm's statistic
+// (ss[0 * pitch + r] = total, the other tile partials of the row zero): the fused-norm path of gemm_rows.cuh.
+__global__ void __launch_bounds__(128)
+embed_gather_ss_kernel(const int* __restrict__ tokens, const bf16* __restrict__ embedding, bf16* __restrict__ x_out, float* __restrict__ ss,
+                       int ss_tiles, int ss_pitch, int E) {
+  __shared__ float s_part[4];
+  griddep_launch_dependents();
+  griddep_wait();
+  const int r = blockIdx.x;
+  const bf16* src = embedding + (long long)tokens[r] * E;
+  float acc = 0.0f;
+  for (int i = threadIdx.x; i < E / 8; i += 128) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(src + i * 8);
+    *reinterpret_cast<uint4*>(x_out + (long long)r * E + i * 8) = raw;
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = bf16_lo(w[j]), b = bf16_hi(w[j]);
+      acc += a * a + b * b;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < ss_tiles) ss[threadIdx.x * ss_pitch + r] = threadIdx.x == 0 ? s_part[0] + s_part[1] + s_part[2] + s_part[3] : 0.0f;
+}
+
 struct FinalizeArgs {
   const float* part_score;  // [rows, n_tiles]
   const int* part_idx;

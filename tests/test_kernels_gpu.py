@@ -59,7 +59,11 @@ def test_rmsnorm(rows, E):
 @pytest.mark.parametrize(
     "rows,n,k,splits",
     [(1, 256, 128, 1), (16, 512, 256, 1), (64, 1792, 1280, 1), (64, 1792, 1280, 8), (64, 1280, 5120, 16),
-     (37, 384, 1280, 4), (200, 1280, 1280, 1), (256, 640, 320, 4), (64, 1000, 192, 2), (3, 256, 1280, 16)],
+     (37, 384, 1280, 4), (200, 1280, 1280, 1), (256, 640, 320, 4), (64, 1000, 192, 2), (3, 256, 1280, 16),
+     # 65..256 rows: gemm_rows.cuh -- persistent with several tiles per CTA (double-buffered accumulators, both row-block
+     # counts), split-K over clusters of 2 / 4 / 8, ragged N
+     (256, 24000, 256, 1), (130, 40000, 128, 1), (100, 1792, 1280, 8), (256, 1280, 5120, 8), (256, 1000, 192, 2), (65, 10240, 1280, 1),
+     (256, 1280, 1280, 4)],
 )
 def test_linear_tcgen05(rows, n, k, splits):
   lib = _lib.load()
