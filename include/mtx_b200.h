@@ -189,12 +189,43 @@ int mtx_decode_attention(const void* q, const void* k_cache, const void* v_cache
                          int num_q_heads, int num_kv_heads, int head_dim, int max_prefill_len, int max_target_len,
                          float softcap, void* scratch, mtx_stream stream);
 
+/* One cache segment with prefix lengths, returning the UNNORMALISED output and the softmax statistics: the contract of
+ * the reference's own pluggable decode-attention kernels, AttentionOp.gpu_ragged_attention / tpu_ragged_attention
+ * (attentions.py:761-845: `(out [B,1,Hq,D], max [B,1,Hq,1], sum [B,1,Hq,1])`, sm_scale = 1), so it can sit behind
+ * AttentionOp.apply_attention unchanged; the caller merges the segments with normalize_attention (attentions.py:1376-1397).
+ *   q [rows, Hq*D] bf16; lengths [rows] valid rows of the segment (>= 1);
+ *   k, v: seq_major = 1: [rows, seq_len, Hkv, D] (the reference's logical cache layout, CACHE_BATCH/SEQUENCE/HEADS/KV),
+ *         seq_major = 0: [rows, Hkv, seq_len, D] (this library's layout, ar_cache_axis_order 0,2,1,3);
+ *   out [rows, Hq*D] bf16 = sum_t exp(s_t - max) v_t;  out_max, out_sum [rows, Hq] fp32. */
+size_t mtx_ragged_attention_scratch_bytes(int rows, int num_kv_heads, int num_q_heads, int head_dim, int seq_len);
+int mtx_ragged_attention(const void* q, const void* k, const void* v, const int32_t* lengths, void* out, float* out_max, float* out_sum,
+                         int rows, int seq_len, int num_q_heads, int num_kv_heads, int head_dim, int seq_major, float softcap,
+                         void* scratch, mtx_stream stream);
+
+/* Attention.query/key/value projections + RotaryEmbedding + KVCache append of one decode step (attentions.py:1894-2030,
+ * 2236-2265; embeddings.py:277-315; kvcache.py:626-718) as ONE GEMM with a fused epilogue:
+ *   n [rows padded to 16/32/64/128/256, E] bf16 normalised activations; wqkv [(Hq+2Hkv)*D, E] (mtx_weights.wqkv of one layer);
+ *   pos [rows] RoPE positions; row i's key / value go to row write_row[i] (< 0: skip) of plane plane[i] of the layer's cache
+ *   [planes, Hkv, rows_per_plane, D]; q_out [rows, Hq*D] rotated queries.  scratch: mtx_qkv_rope_append_scratch_bytes(). */
+size_t mtx_qkv_rope_append_scratch_bytes(int rows, int head_dim);
+int mtx_qkv_rope_append(const void* n, const void* wqkv, const int32_t* pos, const int32_t* plane, const int32_t* write_row, void* q_out,
+                        void* k_cache, void* v_cache, int rows, int emb_dim, int num_q_heads, int num_kv_heads, int head_dim,
+                        int rows_per_plane, float rope_min_timescale, float rope_max_timescale, void* scratch, mtx_stream stream);
+
+/* Re-attach the decode-state buffers without repacking anything else (an XLA FFI handler receives its operand buffers anew
+ * at every call; see csrc/mtx_jax_ffi.cc).  A no-op when nothing moved. */
+int mtx_engine_rebind_state(mtx_engine* e, const mtx_decode_state* s);
+
 /* ---- misc ---------------------------------------------------------------------------------- */
 
 /* Measurement aid: grid-barrier timeline of the persistent step kernel.  While a device buffer of
  * mtx_step_trace_words() 64-bit words is installed with mtx_debug_set_trace, every CTA records
  * %globaltimer at the arrival at and the release from each grid barrier (see tools/mega_trace.py). */
 size_t mtx_step_trace_words(void);
+
+/* 1 when the library was built with jaxlib's headers and exports the XLA FFI handler symbols of csrc/mtx_jax_ffi.cc
+ * (MtxRaggedAttention, MtxDecodeAttention, MtxQkvRopeAppend, MtxDecodeStep), else 0. */
+int mtx_jax_ffi_available(void);
 
 const char* mtx_last_error(void);
 /* "sm_100a" build tag, so a caller can check what it loaded. */

@@ -85,7 +85,21 @@ class DecodeState(ctypes.Structure):
 
 
 def sources() -> list[str]:
-  return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))) + [HEADER]
+  return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cc"))) + [HEADER]
+
+
+def _jaxlib_include() -> list[str]:
+  """-I for jaxlib's headers when jaxlib is importable: csrc/mtx_jax_ffi.cc then builds the XLA FFI handlers."""
+  try:
+    import importlib.util
+
+    spec = importlib.util.find_spec("jaxlib")
+    if spec is None or not spec.submodule_search_locations:
+      return []
+    inc = os.path.join(list(spec.submodule_search_locations)[0], "include")
+    return ["-I", inc] if os.path.isfile(os.path.join(inc, "xla", "ffi", "api", "ffi.h")) else []
+  except Exception:
+    return []
 
 
 def needs_build() -> bool:
@@ -101,7 +115,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
   nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
   defines = ["-D" + d for d in os.environ.get("MTX_NVCC_DEFINES", "").split() if d]  # e.g. MTX_PK_EVENTS for tools/mega_trace.py
-  cmd = [nvcc] + NVCC_FLAGS + defines + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "engine.cu")]
+  cmd = ([nvcc] + NVCC_FLAGS + defines + _jaxlib_include() + (["-Xptxas", "-v"] if verbose else []) +
+         ["-o", LIB_PATH, os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "mtx_jax_ffi.cc")])
   proc = subprocess.run(cmd, capture_output=True, text=True)
   if proc.returncode != 0:
     raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
@@ -158,6 +173,18 @@ def _declare(lib) -> None:
   lib.mtx_attention_scratch_bytes.argtypes = [i32] * 6
   lib.mtx_decode_attention.restype = i32
   lib.mtx_decode_attention.argtypes = [vp] * 8 + [i32] * 7 + [f32, vp, vp]
+  lib.mtx_ragged_attention_scratch_bytes.restype = sz
+  lib.mtx_ragged_attention_scratch_bytes.argtypes = [i32] * 5
+  lib.mtx_ragged_attention.restype = i32
+  lib.mtx_ragged_attention.argtypes = [vp] * 7 + [i32] * 6 + [f32, vp, vp]
+  lib.mtx_qkv_rope_append_scratch_bytes.restype = sz
+  lib.mtx_qkv_rope_append_scratch_bytes.argtypes = [i32, i32]
+  lib.mtx_qkv_rope_append.restype = i32
+  lib.mtx_qkv_rope_append.argtypes = [vp] * 8 + [i32] * 6 + [f32, f32, vp, vp]
+  lib.mtx_jax_ffi_available.restype = i32
+  lib.mtx_jax_ffi_available.argtypes = []
+  lib.mtx_engine_rebind_state.restype = i32
+  lib.mtx_engine_rebind_state.argtypes = [vp, c.POINTER(DecodeState)]
 
 
 def load():

@@ -44,6 +44,10 @@ struct AttnParams {
   int plane_base;         // layer * num_slots (row coordinate base in the cache tensor map)
   float softcap;
   long long* trace;  // debug: clock64 timeline of warp 0 of CTA 0 (8 slots per item), or null
+  // mtx_ragged_attention (the gpu_ragged_attention contract, attentions.py:761-815):
+  int seq_major;     // 1: K/V are [plane, T, Hkv, D] (the reference's logical cache layout): tile = rows of one head at stride Hkv*D
+  float* out_max;    // [rows, Hq] or null.  Non-null: `out` is left UNNORMALISED (sum_t exp(s_t - max) v_t) and the row's
+  float* out_sum;    // [rows, Hq]   (max, sum) are returned for the caller's cross-segment merge (attentions.py:1376-1397)
 };
 
 struct TileLoc { int p0, cnt; };
@@ -163,7 +167,8 @@ __device__ __forceinline__ void attn_process_items(const CUtensorMap& tm_k, cons
     const int nt = attn_num_tiles(len0, rf, rl, R);
     const int n_chunks = (nt + TPI - 1) / TPI;
     const int t_begin = chunk * TPI, t_end = min(nt, t_begin + TPI);
-    const int plane_row = ((p.plane_base + p.plane[r]) * p.hkv + h) * p.T;
+    const int plane_row = p.seq_major ? (p.plane_base + p.plane[r]) * p.T : ((p.plane_base + p.plane[r]) * p.hkv + h) * p.T;
+    const int col0 = p.seq_major ? h * D : 0;  // element column of the head inside a cache row
     if (trace && iter < 15) trace[iter * 8 + 0] = clock64() - t_start;
 
     // first tile of this warp: start both loads before touching Q
@@ -172,10 +177,10 @@ __device__ __forceinline__ void attn_process_items(const CUtensorMap& tm_k, cons
     if (t < t_end && lane == 0) {
       mbar_expect_tx(bar_k, kTileBytes);
 #pragma unroll
-      for (int s = 0; s < kSub; ++s) tma_load_2d(k_tile + s * 8192, &tm_k, s * 64, plane_row + loc.p0, bar_k, kEvictFirst);
+      for (int s = 0; s < kSub; ++s) tma_load_2d(k_tile + s * 8192, &tm_k, col0 + s * 64, plane_row + loc.p0, bar_k, kEvictFirst);
       mbar_expect_tx(bar_v, kTileBytes);
 #pragma unroll
-      for (int s = 0; s < kSub; ++s) tma_load_2d(v_tile + s * 8192, &tm_v, s * 64, plane_row + loc.p0, bar_v, kEvictFirst);
+      for (int s = 0; s < kSub; ++s) tma_load_2d(v_tile + s * 8192, &tm_v, col0 + s * 64, plane_row + loc.p0, bar_v, kEvictFirst);
     }
 
     // Q fragments (A operand, rows = query heads of the group, zero-padded to 16)
@@ -227,7 +232,7 @@ __device__ __forceinline__ void attn_process_items(const CUtensorMap& tm_k, cons
       if (tn < t_end && lane == 0) {
         mbar_expect_tx(bar_k, kTileBytes);
 #pragma unroll
-        for (int ss = 0; ss < kSub; ++ss) tma_load_2d(k_tile + ss * 8192, &tm_k, ss * 64, plane_row + nloc.p0, bar_k, kEvictFirst);
+        for (int ss = 0; ss < kSub; ++ss) tma_load_2d(k_tile + ss * 8192, &tm_k, col0 + ss * 64, plane_row + nloc.p0, bar_k, kEvictFirst);
       }
       // ---- mask + online softmax (quad shuffles) ----
       float tm0 = -INFINITY, tm1 = -INFINITY;
@@ -301,7 +306,7 @@ __device__ __forceinline__ void attn_process_items(const CUtensorMap& tm_k, cons
       if (tn < t_end && lane == 0) {
         mbar_expect_tx(bar_v, kTileBytes);
 #pragma unroll
-        for (int ss = 0; ss < kSub; ++ss) tma_load_2d(v_tile + ss * 8192, &tm_v, ss * 64, plane_row + nloc.p0, bar_v, kEvictFirst);
+        for (int ss = 0; ss < kSub; ++ss) tma_load_2d(v_tile + ss * 8192, &tm_v, col0 + ss * 64, plane_row + nloc.p0, bar_v, kEvictFirst);
       }
       phase ^= 1;
       loc = nloc;
@@ -348,7 +353,11 @@ __device__ __forceinline__ void attn_process_items(const CUtensorMap& tm_k, cons
         }
       }
       if (n_chunks == 1) {
-        p.out[out_base + e] = __float2bfloat16_rn(O / L);
+        p.out[out_base + e] = __float2bfloat16_rn(p.out_max != nullptr ? O : O / L);
+        if (p.out_max != nullptr && d == 0) {
+          p.out_max[(long long)r * p.hq + h * G + g] = M;
+          p.out_sum[(long long)r * p.hq + h * G + g] = L;
+        }
       } else {
         __stcg(p.part_o + (part_base + g) * D + d, O);
         if (d == 0) {
@@ -380,7 +389,11 @@ __device__ __forceinline__ void attn_process_items(const CUtensorMap& tm_k, cons
             L += __ldcg(p.part_ml + (pb + c * G + g) * 2 + 1) * sc;
             O += __ldcg(p.part_o + (pb + c * G + g) * D + d) * sc;
           }
-          p.out[out_base + e] = __float2bfloat16_rn(O / L);
+          p.out[out_base + e] = __float2bfloat16_rn(p.out_max != nullptr ? O : O / L);
+          if (p.out_max != nullptr && d == 0) {
+            p.out_max[(long long)r * p.hq + h * G + g] = M;
+            p.out_sum[(long long)r * p.hq + h * G + g] = L;
+          }
         }
       }
     }

@@ -150,6 +150,11 @@ int launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStr
   return MTX_OK;
 }
 
+// Attention work items the per-kernel path aims for: a multiple of the SM count, so that the (at most 3 per SM) persistent CTAs
+// of decode_attn_kernel each walk several items and finish together (with one item per (row, kv head) pair, batch 256 leaves
+// 1024 whole-sequence items for 444 CTAs: two or three each, a 30 % imbalance).
+int attn_target_items(int num_sms) { return num_sms * env_int("MTX_ATTN_ITEMS_PER_SM", 1); }
+
 int round_rows(int rows) {
   int t = 16;
   while (t < rows) t *= 2;
@@ -406,6 +411,7 @@ int get_xmaps(mtx_engine* e, int r_tile, XMaps** out) {
 int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st) {
   const mtx_model_config& c = e->cfg;
   AttnParams p;
+  memset(&p, 0, sizeof(p));
   p.q = e->q;
   p.out = e->attn;
   p.plane = e->rd.plane;
@@ -422,7 +428,7 @@ int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st) {
   p.hkv = c.num_kv_heads;
   p.P = c.max_prefill_len;
   p.T = c.max_target_len;
-  p.tiles_per_item = attn_tiles_per_item(rows, c.num_kv_heads, c.max_prefill_len, c.max_target_len, e->num_sms);
+  p.tiles_per_item = attn_tiles_per_item(rows, c.num_kv_heads, c.max_prefill_len, c.max_target_len, attn_target_items(e->num_sms));
   p.max_chunks = e->attn_max_chunks;
   p.plane_base = layer * c.num_slots;
   p.softcap = c.attn_softcap;
@@ -655,7 +661,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   pa.P = c.max_prefill_len;
   pa.T = c.max_target_len;
   pa.D = c.head_dim;
-  pa.tiles_per_item = attn_tiles_per_item(rows, c.num_kv_heads, c.max_prefill_len, c.max_target_len, e->num_sms);
+  pa.tiles_per_item = attn_tiles_per_item(rows, c.num_kv_heads, c.max_prefill_len, c.max_target_len, attn_target_items(e->num_sms));
   pa.rope_timescale = e->rope_timescale;
   const bool mega = mode == 0 && want_logits && pk_usable(e, rows);
   if (mega) {
@@ -1294,6 +1300,170 @@ int mtx_decode_attention(const void* q, const void* k_cache, const void* v_cache
   }
   MTX_CUDA(cudaFuncSetAttribute(decode_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   return launch(decode_attn_kernel<128>, dim3(grid), dim3(kAttnThreads), smem, st, tk, tv, p);
+}
+
+// ---- gpu_ragged_attention contract ----------------------------------------------------------------
+
+namespace {
+__global__ void ragged_rows_kernel(int* plane, int* zeros_a, int* zeros_b, int rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) {
+    plane[i] = i;
+    zeros_a[i] = 0;
+    zeros_b[i] = 0;
+  }
+}
+// RoPE table of mtx_qkv_rope_append: (cos, sin) of pos / timescale, rounded to bf16 (embeddings.py:270-307)
+__global__ void rope_table_kernel(const int* pos, float2* cs, int rows, int half, float min_ts, float max_ts) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * half) return;
+  const int r = idx / half, i = idx - r * half;
+  const double fraction = 2.0 * double(i) / double(2 * half);
+  const float ts = float(double(min_ts) * pow(double(max_ts) / double(min_ts), fraction));
+  const float ang = float(pos[r]) / ts;
+  cs[idx] = make_float2(bf16r(cosf(ang)), bf16r(sinf(ang)));
+}
+}  // namespace
+
+size_t mtx_ragged_attention_scratch_bytes(int rows, int num_kv_heads, int num_q_heads, int head_dim, int seq_len) {
+  return mtx_attention_scratch_bytes(rows, num_kv_heads, num_q_heads, head_dim, seq_len, seq_len + 64) + align_up(size_t(rows) * 12, 1024);
+}
+
+int mtx_ragged_attention(const void* q, const void* k, const void* v, const int32_t* lengths, void* out, float* out_max, float* out_sum,
+                         int rows, int seq_len, int num_q_heads, int num_kv_heads, int head_dim, int seq_major, float softcap,
+                         void* scratch, mtx_stream stream) {
+  if (!q || !k || !v || !lengths || !out || !out_max || !out_sum || !scratch) return fail(MTX_ERR_ARG, "null argument");
+  if (head_dim != 64 && head_dim != 128) return fail(MTX_ERR_UNSUPPORTED, "head_dim %d: only 64 and 128", head_dim);
+  if (rows < 1 || rows > 256 || seq_len < 1) return fail(MTX_ERR_ARG, "rows must be in [1, 256], seq_len >= 1");
+  if (num_q_heads % num_kv_heads != 0 || num_q_heads / num_kv_heads > 16) return fail(MTX_ERR_UNSUPPORTED, "bad head grouping");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the segment is addressed as a "prefill segment" of seq_len rows with an empty ring behind it
+  const int P = seq_len, T = seq_len + 64;
+  const size_t mc = attn_max_chunks(P, T);
+  const size_t G = num_q_heads / num_kv_heads;
+  uint8_t* b = static_cast<uint8_t*>(scratch);
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  int* work_items = reinterpret_cast<int*>(b);
+  b += align_up(size_t(rows) * mc * 4, 1024);
+  int* work_count = reinterpret_cast<int*>(b);
+  b += 1024;
+  p.tickets = reinterpret_cast<int*>(b);
+  const size_t ticket_bytes = align_up(size_t(rows) * num_kv_heads * 4, 1024);
+  b += ticket_bytes;
+  p.part_ml = reinterpret_cast<float*>(b);
+  b += align_up(size_t(rows) * num_kv_heads * mc * G * 2 * 4, 1024);
+  p.part_o = reinterpret_cast<float*>(b);
+  b += align_up(size_t(rows) * num_kv_heads * mc * G * head_dim * 4, 1024);
+  int* plane = reinterpret_cast<int*>(b);
+  int* zeros_a = plane + rows;
+  int* zeros_b = zeros_a + rows;
+  MTX_CUDA(cudaMemsetAsync(p.tickets, 0, ticket_bytes, st));
+  ragged_rows_kernel<<<(rows + 127) / 128, 128, 0, st>>>(plane, zeros_a, zeros_b, rows);
+  const int tpi = attn_tiles_per_item(rows, num_kv_heads, P, T, 148);
+  MTX_TRY(launch(attn_build_worklist_kernel, dim3(1), dim3(256), 0, st, (const int*)lengths, (const int*)zeros_a, (const int*)zeros_b, rows, P, T, tpi,
+                 work_items, work_count));
+  CUtensorMap tk, tv;
+  if (seq_major) {  // [rows, S, Hkv, D]: a tile is 64 rows of one head's D columns out of Hkv * D
+    MTX_TRY(make_map(&tk, k, uint64_t(num_kv_heads) * head_dim, uint64_t(rows) * seq_len, kAttnTileRows));
+    MTX_TRY(make_map(&tv, v, uint64_t(num_kv_heads) * head_dim, uint64_t(rows) * seq_len, kAttnTileRows));
+  } else {          // [rows, Hkv, S, D]
+    MTX_TRY(make_map(&tk, k, head_dim, uint64_t(rows) * num_kv_heads * seq_len, kAttnTileRows));
+    MTX_TRY(make_map(&tv, v, head_dim, uint64_t(rows) * num_kv_heads * seq_len, kAttnTileRows));
+  }
+  p.q = static_cast<const bf16*>(q);
+  p.out = static_cast<bf16*>(out);
+  p.out_max = out_max;
+  p.out_sum = out_sum;
+  p.seq_major = seq_major ? 1 : 0;
+  p.plane = plane;
+  p.len0 = lengths;
+  p.ring_first = zeros_a;
+  p.ring_len = zeros_b;
+  p.work_items = work_items;
+  p.work_count = work_count;
+  p.rows = rows;
+  p.hq = num_q_heads;
+  p.hkv = num_kv_heads;
+  p.P = P;
+  p.T = seq_len;  // rows allocated per (plane, head): the stride of a plane in the tensor map
+  p.tiles_per_item = tpi;
+  p.max_chunks = int(mc);
+  p.softcap = softcap;
+  // (attn_tile only ever sees prefill tiles here: ring_len = 0, so R = T - P is never used as a divisor)
+  const size_t smem = attn_smem_bytes(head_dim, int(G));
+  int grid = rows * num_kv_heads * attn_max_chunks(P, T, tpi);
+  const int cap = 148 * (head_dim == 64 ? 3 : 1);
+  if (grid > cap) grid = cap;
+  if (head_dim == 64) {
+    MTX_CUDA(cudaFuncSetAttribute(decode_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    return launch(decode_attn_kernel<64>, dim3(grid), dim3(kAttnThreads), smem, st, tk, tv, p);
+  }
+  MTX_CUDA(cudaFuncSetAttribute(decode_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  return launch(decode_attn_kernel<128>, dim3(grid), dim3(kAttnThreads), smem, st, tk, tv, p);
+}
+
+// ---- fused QKV projection + RoPE + KV append ------------------------------------------------------
+
+size_t mtx_qkv_rope_append_scratch_bytes(int rows, int head_dim) { return align_up(size_t(round_rows(rows)) * (head_dim / 2) * 8, 1024); }
+
+int mtx_qkv_rope_append(const void* n, const void* wqkv, const int32_t* pos, const int32_t* plane, const int32_t* write_row, void* q_out,
+                        void* k_cache, void* v_cache, int rows, int emb_dim, int num_q_heads, int num_kv_heads, int head_dim,
+                        int rows_per_plane, float rope_min_timescale, float rope_max_timescale, void* scratch, mtx_stream stream) {
+  if (!n || !wqkv || !pos || !plane || !write_row || !q_out || !k_cache || !v_cache || !scratch) return fail(MTX_ERR_ARG, "null argument");
+  if (head_dim != 64 && head_dim != 128) return fail(MTX_ERR_UNSUPPORTED, "head_dim %d: only 64 and 128", head_dim);
+  if (rows < 1 || rows > 256 || emb_dim % 64 != 0) return fail(MTX_ERR_ARG, "rows must be in [1, 256], emb_dim a multiple of 64");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int r_tile = round_rows(rows);
+  const int qkv_n = (num_q_heads + 2 * num_kv_heads) * head_dim;
+  float2* cs = static_cast<float2*>(scratch);
+  const int half = head_dim / 2;
+  rope_table_kernel<<<(rows * half + 127) / 128, 128, 0, st>>>(pos, cs, rows, half, rope_min_timescale, rope_max_timescale);
+  CUtensorMap tw, tx;
+  MTX_TRY(make_map(&tw, wqkv, emb_dim, qkv_n, kTileN));
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = qkv_n;
+  p.k = emb_dim;
+  p.rows = rows;
+  p.r_tile = r_tile;
+  EpiArgs ea;
+  memset(&ea, 0, sizeof(ea));
+  ea.q_out = static_cast<bf16*>(q_out);
+  ea.k_cache = static_cast<bf16*>(k_cache);
+  ea.v_cache = static_cast<bf16*>(v_cache);
+  ea.plane = plane;
+  ea.write_row = write_row;
+  ea.rope_cs = cs;
+  ea.hq = num_q_heads;
+  ea.hkv = num_kv_heads;
+  ea.d = head_dim;
+  ea.t_alloc = rows_per_plane;
+  if (use_rows_kernel(r_tile)) {
+    const RowsPlan pl = plan_rows(qkv_n, emb_dim, r_tile, 148, EPI_QKV_ROPE);
+    MTX_TRY(make_map(&tx, n, emb_dim, r_tile, pl.splits > 1 ? 128 : r_tile));
+    return launch_rows<EPI_QKV_ROPE>(tw, tx, p, ea, pl, st);
+  }
+  MTX_TRY(make_map(&tx, n, emb_dim, r_tile, r_tile));
+  return launch_gemm<EPI_QKV_ROPE>(tw, tx, p, ea, plan_gemm(qkv_n, emb_dim, r_tile, 148, EPI_QKV_ROPE), st);
+}
+
+// Re-attach the decode-state buffers (an XLA FFI caller receives them anew at every call): only what depends on the
+// state pointers is rebuilt (the K/V tensor maps; captured graphs are dropped).
+int mtx_engine_rebind_state(mtx_engine* e, const mtx_decode_state* s) {
+  if (!e || !e->bound || !s) return fail(MTX_ERR_ARG, "engine is not bound / null state");
+  if (memcmp(&e->s, s, sizeof(*s)) == 0) return MTX_OK;
+  const mtx_model_config& c = e->cfg;
+  const bool kv_moved = e->s.k_cache != s->k_cache || e->s.v_cache != s->v_cache;
+  e->s = *s;
+  for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  e->graphs.clear();
+  if (kv_moved) {
+    const uint64_t kv_rows = uint64_t(c.num_layers) * c.num_slots * c.num_kv_heads * c.max_target_len;
+    MTX_TRY(make_map(&e->tm_k, s->k_cache, c.head_dim, kv_rows, kAttnTileRows));
+    MTX_TRY(make_map(&e->tm_v, s->v_cache, c.head_dim, kv_rows, kAttnTileRows));
+  }
+  return MTX_OK;
 }
 
 }  // extern "C"

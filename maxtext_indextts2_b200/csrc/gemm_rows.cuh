@@ -400,6 +400,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         if (active) {
           mbar_wait(&tail->tmem_full[buf], (j >> 1) & 1);
           tcgen05_fence_after();
+          if (trace && threadIdx.x == 64 && j == 0) trace[4] = clock64() - t_start;
           if (j == 0) {
             griddep_wait();  // side inputs (residual, row descriptors, row statistics) come from earlier kernels
             if (row_valid) rs = rows_rstd(e, r);
@@ -428,6 +429,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tail->tmem_empty[buf]);
+          if (trace && threadIdx.x == 64 && j == 0) trace[8] = clock64() - t_start;
         }
       }
     } else {
@@ -537,6 +539,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
 
   tcgen05_fence_before();
   __syncthreads();
+  if (trace && threadIdx.x == 0) trace[10] = clock64() - t_start;
   timeline_end(tl);
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }

@@ -160,3 +160,107 @@ def test_unsupported_shapes_fail_loudly():
   assert rc == _lib.MTX_ERR_UNSUPPORTED and "head_dim" in _lib.last_error()
   rc = lib.mtx_linear(_ptr(t), _ptr(t), _ptr(t), 4, 128, 100, 1, _stream())
   assert rc == _lib.MTX_ERR_ARG
+
+
+@pytest.mark.parametrize("seq_major", [1, 0])
+@pytest.mark.parametrize("B,Hq,Hkv,D,S", [(4, 20, 4, 64, 300), (3, 8, 8, 128, 130), (2, 5, 1, 64, 2048)])
+def test_ragged_attention_returns_unnormalised_out_max_sum(B, Hq, Hkv, D, S, seq_major):
+  """The contract of AttentionOp.gpu_ragged_attention (attentions.py:761-815): (q, k, v, lengths) -> (unnormalised out, max,
+  sum) for ONE segment, in the reference's logical cache layout [B,S,Hkv,D] and in this library's [B,Hkv,S,D]; checked against
+  reference_gqa's arithmetic (kernels/ragged_attention.py:122-161) and by merging two segments the way the caller does
+  (normalize_attention, attentions.py:1376-1397)."""
+  lib = _lib.load()
+  g = torch.Generator().manual_seed(B * 100 + S)
+  q = torch.randn(B, Hq * D, generator=g).to(torch.bfloat16)
+  K = torch.randn(B, S, Hkv, D, generator=g).to(torch.bfloat16)
+  V = torch.randn(B, S, Hkv, D, generator=g).to(torch.bfloat16)
+  lengths = torch.randint(1, S + 1, (B,), generator=g).to(torch.int32)
+  lengths[0] = S
+  valid = torch.arange(S)[None, :] < lengths[:, None]
+  want_o, want_m, want_l = ref.gqa_decode_ref(q.float().reshape(B, Hq, D), K.float(), V.float(), valid, p_bf16=True)
+  kd = (K if seq_major else K.permute(0, 2, 1, 3).contiguous()).cuda()
+  vd = (V if seq_major else V.permute(0, 2, 1, 3).contiguous()).cuda()
+  qd, ld = q.cuda(), lengths.cuda()
+  out = torch.zeros(B, Hq * D, dtype=torch.bfloat16, device="cuda")
+  om = torch.zeros(B, Hq, dtype=torch.float32, device="cuda")
+  ol = torch.zeros(B, Hq, dtype=torch.float32, device="cuda")
+  scratch = torch.empty(lib.mtx_ragged_attention_scratch_bytes(B, Hkv, Hq, D, S), dtype=torch.uint8, device="cuda")
+  _lib.check(lib.mtx_ragged_attention(_ptr(qd), _ptr(kd), _ptr(vd), _ptr(ld), _ptr(out), _ptr(om), _ptr(ol), B, S, Hq, Hkv, D, seq_major, 0.0,
+                                      _ptr(scratch), _stream()))
+  torch.cuda.synchronize()
+  got_o = out.cpu().float().reshape(B, Hq, D)
+  got_m, got_l = om.cpu(), ol.cpu()
+  torch.testing.assert_close(got_m, want_m, rtol=1e-5, atol=1e-5)
+  torch.testing.assert_close(got_l, want_l, rtol=2e-3, atol=1e-3)  # exp2-based exponentials, fp32 sums in tile order
+  norm = got_o / got_l[..., None]
+  assert (norm - want_o).abs().max() <= 2**-6 * want_o.abs().max()  # one more bf16 rounding than the normalised kernel (of the unnormalised sums)
+  # the caller's merge (normalize_attention, attentions.py:1376-1397) of two calls over the two halves of the sequence equals the
+  # single call, for the rows that reach into the second half
+  S1 = S // 2
+  la = torch.clamp(lengths, max=S1)
+  lb = torch.clamp(lengths - S1, min=1)
+  both = lengths > S1
+
+  def call(kk, vv, ll, seq):
+    o_ = torch.zeros(B, Hq * D, dtype=torch.bfloat16, device="cuda")
+    m_ = torch.zeros(B, Hq, dtype=torch.float32, device="cuda")
+    l_ = torch.zeros(B, Hq, dtype=torch.float32, device="cuda")
+    kk, vv, ll = kk.contiguous().cuda(), vv.contiguous().cuda(), ll.cuda()
+    _lib.check(lib.mtx_ragged_attention(_ptr(qd), _ptr(kk), _ptr(vv), _ptr(ll), _ptr(o_), _ptr(m_), _ptr(l_), B, seq, Hq, Hkv, D, 1, 0.0,
+                                        _ptr(scratch), _stream()))
+    torch.cuda.synchronize()
+    return o_.cpu().float().reshape(B, Hq, D), m_.cpu(), l_.cpu()
+
+  oa, ma, sa = call(K[:, :S1], V[:, :S1], la, S1)
+  ob, mb, sb = call(K[:, S1:], V[:, S1:], lb, S - S1)
+  gmax = torch.maximum(ma, mb)
+  wa, wb = torch.exp(ma - gmax), torch.exp(mb - gmax)
+  merged = (wa[..., None] * oa + wb[..., None] * ob) / (wa * sa + wb * sb)[..., None]
+  assert (merged[both] - want_o[both]).abs().max() <= 2**-6 * want_o.abs().max()
+
+
+@pytest.mark.parametrize("rows,E,Hq,Hkv,D", [(5, 256, 4, 2, 64), (64, 1280, 20, 4, 64), (200, 512, 8, 8, 128), (256, 1280, 20, 4, 64)])
+def test_qkv_rope_append_op(rows, E, Hq, Hkv, D):
+  """Attention.query/key/value + RotaryEmbedding + KVCache append as one fused op through the C ABI, against the oracle's
+  dense + rope (embeddings.py:277-315) and the cache rows it must have written (kvcache.py:626-718)."""
+  lib = _lib.load()
+  g = torch.Generator().manual_seed(rows + E)
+  rt = _round_rows(rows)
+  n = torch.zeros(rt, E, dtype=torch.bfloat16)
+  n[:rows] = torch.randn(rows, E, generator=g).to(torch.bfloat16)
+  qkv_n = (Hq + 2 * Hkv) * D
+  w = (torch.randn(qkv_n, E, generator=g) / np.sqrt(E)).to(torch.bfloat16)
+  planes, T = rows + 3, 40
+  pos = torch.randint(0, 3000, (rows,), generator=g).to(torch.int32)
+  plane = torch.randperm(planes, generator=g)[:rows].to(torch.int32)
+  write_row = torch.randint(0, T, (rows,), generator=g).to(torch.int32)
+  write_row[rows // 2] = -1  # skipped
+  kc = torch.zeros(planes, Hkv, T, D, dtype=torch.bfloat16, device="cuda")
+  vc = torch.zeros_like(kc)
+  qo = torch.zeros(rows, Hq * D, dtype=torch.bfloat16, device="cuda")
+  scratch = torch.empty(lib.mtx_qkv_rope_append_scratch_bytes(rows, D), dtype=torch.uint8, device="cuda")
+  nd, wd, pd, pld, wrd = n.cuda(), w.cuda(), pos.cuda(), plane.cuda(), write_row.cuda()
+  _lib.check(lib.mtx_qkv_rope_append(_ptr(nd), _ptr(wd), _ptr(pd), _ptr(pld), _ptr(wrd), _ptr(qo), _ptr(kc), _ptr(vc), rows, E, Hq, Hkv, D, T,
+                                     1.0, 10000.0, _ptr(scratch), _stream()))
+  torch.cuda.synchronize()
+
+  class C:
+    rope_min_timescale, rope_max_timescale = 1, 10000
+
+  o = ref.DecodeOracle.__new__(ref.DecodeOracle)
+  o.cfg, o.faithful = C, True
+  y = o.r(n[:rows].float() @ w.float().t())
+  q = o.rope(y[:, : Hq * D].reshape(rows, 1, Hq, D), pos.reshape(rows, 1))[:, 0]
+  k = o.rope(y[:, Hq * D : (Hq + Hkv) * D].reshape(rows, 1, Hkv, D), pos.reshape(rows, 1))[:, 0]
+  v = y[:, (Hq + Hkv) * D :].reshape(rows, Hkv, D)
+  tol = dict(rtol=2e-2, atol=2e-2)  # bf16 products of the rotation on top of the last-bit difference of the dense output
+  torch.testing.assert_close(qo.cpu().float().reshape(rows, Hq, D), q, **tol)
+  kcc, vcc = kc.cpu().float(), vc.cpu().float()
+  written = torch.zeros(planes, T, dtype=torch.bool)
+  for r in range(rows):
+    if write_row[r] < 0:
+      continue
+    written[plane[r], write_row[r]] = True
+    torch.testing.assert_close(kcc[plane[r], :, write_row[r]], k[r], **tol)
+    torch.testing.assert_close(vcc[plane[r], :, write_row[r]], v[r], **tol)
+  assert kcc.permute(0, 2, 1, 3)[~written].abs().max() == 0 and vcc.permute(0, 2, 1, 3)[~written].abs().max() == 0  # nothing else touched

@@ -33,10 +33,11 @@ for sp in (0, 2, 4, 8):
   e1.record(); torch.cuda.synchronize()
   print(f"rows {rows} splits {sp or 'auto'}: {e0.elapsed_time(e1) * 10:.2f} us per 4-GEMM layer sequence")
 trace = torch.zeros(256, dtype=torch.int64, device='cuda')
-for name, n, k, s in shapes:
-  for it in range(3):
-    trace.zero_(); lib.mtx_debug_set_trace(P(trace))
-    run(name, n, k, 0); torch.cuda.synchronize()
-  t = trace.cpu().numpy()[:10]
-  print(name, "clock64 stamps [setup, past griddep, first stage, mma committed, acc ready, parked, cluster1, reduced, epilogue, cluster2]:", t.tolist(), "(cycles; 1.9 GHz)")
-  lib.mtx_debug_set_trace(None)
+for sp in (1, 4, 8):
+  for name, n, k, s in shapes:
+    for it in range(3):
+      trace.zero_(); lib.mtx_debug_set_trace(P(trace))
+      run(name, n, k, sp); torch.cuda.synchronize()
+    t = trace.cpu().numpy()[:11]
+    print(f"splits {sp}", name, "clock64 stamps [setup, past griddep, first stage, mma committed, acc ready, parked, cluster1, reduced, epilogue, cluster2, end]:", t.tolist(), "(cycles; 1.9 GHz)")
+    lib.mtx_debug_set_trace(None)
