@@ -58,6 +58,10 @@ def parse_args():
   ap.add_argument("--cpu-steps", type=int, default=8, help="timed steps of the cpu_baseline leg of the GPU arm (after 2 warm-ups)")
   ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-clock bound of a CPU leg; steps are cut (and reported) past it")
   ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of one step of the timed state")
+  ap.add_argument("--mode", default="batch", choices=["batch", "vocab-parallel"],
+                  help="batch: request-batch partitioned, no collective (default); vocab-parallel: every GPU decodes the same --batch slots, "
+                       "the logits projection is sharded over the GPUs and one NCCL all-gather carries the per-shard candidates")
+  ap.add_argument("--sampling", default="greedy", choices=["greedy", "weighted", "topk", "nucleus"], help="decode_sampling_strategy")
   ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                   help="weak: --batch slots per GPU (default, the judged line); strong: --batch slots in total, split over the GPUs")
   return ap.parse_args()
@@ -73,6 +77,12 @@ def make_config(args):
     kw["max_target_length"] = args.target_len
   if args.no_fold:
     kw["fold_norm_scales"] = False
+  if args.sampling != "greedy":
+    kw["decode_sampling_strategy"] = args.sampling
+    kw["decode_sampling_top_k"] = 64
+    kw["decode_sampling_nucleus_p"] = 0.9
+  if args.mode == "vocab-parallel":
+    kw["vocab_parallelism"] = int(os.environ.get("WORLD_SIZE", "1"))
   return pyconfig.initialize(None, model_name=args.model, per_device_batch_size=args.batch, **kw)
 
 
@@ -372,6 +382,111 @@ def verify_step(engine, dparams, cfg, B):
   }
 
 
+def run_vocab_parallel(args, world, rank, local_rank):
+  """--mode vocab-parallel: every rank decodes the same `batch` slots (weights of the layers and the KV cache replicated), rank r
+  scores vocabulary rows [r V/N, (r+1) V/N) and ONE NCCL all-gather per step carries the candidates (BASELINE
+  configs[4]).  Strong scaling of the logits projection only: the whole-job throughput is `batch` tokens per step."""
+  import torch.distributed as dist
+
+  from maxtext_indextts2_b200 import maxengine
+
+  cfg = make_config(args)
+  B = int(cfg.per_device_batch_size)
+  engine = maxengine.MaxEngine(cfg, use_cuda_graph=False)
+  dparams = engine.load_params(on_device_init=True)
+  prefill, ar = context_lengths(args, cfg, 0)  # the same slots on every rank
+  state = engine.fill_synthetic_context(prefill, ar)
+  stream = torch.cuda.current_stream()
+
+  def barrier():
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+
+  n0 = engine.lib.mtx_launch_count()
+  state, _ = engine.generate(dparams, state)
+  torch.cuda.synchronize()
+  launches_per_step = int(engine.lib.mtx_launch_count() - n0)
+  for _ in range(max(3, args.warmup)):
+    state, _ = engine.generate(dparams, state)
+  barrier()
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  ev0.record(stream)
+  for _ in range(args.steps):
+    state, result = engine.generate(dparams, state)
+  ev1.record(stream)
+  barrier()
+  step_ms = ev0.elapsed_time(ev1) / args.steps
+  # end to end: host tokens in, sampled tokens out, one sync per step
+  host_in = torch.zeros(B, 1, dtype=torch.int32).pin_memory()
+  host_out = torch.zeros(B, 3, dtype=torch.int32).pin_memory()
+  host_in.copy_(state["tokens"].cpu())
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  e0.record(stream)
+  for _ in range(args.steps):
+    state["tokens"].copy_(host_in, non_blocking=True)
+    state, result = engine.generate(dparams, state)
+    host_out.copy_(result.data, non_blocking=True)
+    stream.synchronize()
+    host_in[:, 0] = host_out[:, 0]
+  e1.record(stream)
+  barrier()
+  e2e_ms = e0.elapsed_time(e1) / args.steps
+  clocks = sampler.stop()
+  # the collective alone
+  cand = engine.candidate_buffer(B)
+  for _ in range(5):
+    engine._gather(cand)
+  barrier()
+  g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  g0.record(stream)
+  for _ in range(50):
+    engine._gather(cand)
+  g1.record(stream)
+  barrier()
+  gather_us = g0.elapsed_time(g1) / 50 * 1e3
+  tok = result.data[:, 0].clone().to(torch.int64)
+  lo, hi = tok.clone(), tok.clone()
+  dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+  dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+  times = torch.tensor([step_ms, e2e_ms, gather_us], dtype=torch.float64, device="cuda")
+  dist.all_reduce(times, op=dist.ReduceOp.MAX)
+  step_ms, e2e_ms, gather_us = times.tolist()
+  if rank != 0:
+    return None
+  V = cfg.vocab_size
+  return {
+      "metric": METRIC,
+      "mode": "vocab-parallel",
+      "value": B * 1e3 / step_ms,
+      "unit": "audio tokens/s",
+      "n_gpus": world,
+      "steps": args.steps,
+      "warmup": max(3, args.warmup),
+      "ms_per_step": step_ms,
+      "higher_is_better": True,
+      "scaling": "strong",
+      "vs_baseline": None,
+      "dtype": "bf16",
+      "data": "synthetic",
+      "config": {**workload_config(args, cfg, 1), "parallelism": f"vocab-parallel logits x{world}: V/N = {V // world} rows per GPU, layers and KV replicated, "
+                 f"one NCCL all-gather of the per-shard candidates per step ({args.sampling} sampling)"},
+      "e2e": {"value": B * 1e3 / e2e_ms, "unit": "audio tokens/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": B * 4, "d2h_bytes_per_step": B * 12,
+              "api": "MaxEngine.generate (vocab_parallelism=N) with pinned host token buffers, one stream sync per step"},
+      "gpu_launches": launches_per_step * args.steps,
+      "launches_per_step": launches_per_step,
+      "cuda_graph": False,
+      "clocks": clocks,
+      "allgather": {"us": gather_us, "payload_bytes_per_rank": int(cand.numel() * 4), "floats_per_row": int(cand.numel() // B),
+                    "what": "dist.all_gather_into_tensor of the candidate payload, 50 back to back, max over ranks"},
+      "tokens_identical_on_all_ranks": bool(torch.equal(lo, hi)),
+  }
+
+
 def main():
   args = parse_args()
   if args.impl == "reference":
@@ -401,6 +516,19 @@ def main():
   if _lib.needs_build():
     _lib.build()
   lib = _lib.load()
+
+  if args.mode == "vocab-parallel":
+    if world < 2:
+      raise SystemExit("--mode vocab-parallel needs torchrun with at least 2 ranks")
+    line = run_vocab_parallel(args, world, rank, local_rank)
+    if rank == 0:
+      sys.stdout.flush()
+      os.dup2(saved_stdout, 1)
+      print(json.dumps(line), flush=True)
+      os.dup2(2, 1)
+    dist.barrier()
+    dist.destroy_process_group()
+    return
 
   if args.scaling == "strong":
     if args.batch % world:

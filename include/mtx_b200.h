@@ -148,6 +148,21 @@ int mtx_decode_step_graph(mtx_engine* e, int rows, mtx_stream stream);
  * sharding rules lower to (maxengine.py:894, configs/base.yml:351). */
 int mtx_decode_step_candidates(mtx_engine* e, int rows, float* candidates, mtx_stream stream);
 int mtx_commit_candidates(mtx_engine* e, int rows, const float* gathered, int n_shards, mtx_stream stream);
+/* With top-k / nucleus sampling the payload is each shard's 64 best logits per row instead of its single winner:
+ * candidates[rows][130] = 64 logits (descending), their 64 vocabulary ids (int bits), shard max, shard sum exp
+ * (decode_state.logits must be set: the shard's logits are materialised).  mtx_candidate_floats() = floats per row of the
+ * payload for the engine's current sampling strategy (5 or 130); `gathered` is [n_shards][5][rows] resp. [n_shards][rows][130].
+ * top-k is exact for k <= 64; nucleus is exact when no shard's 64th logit reaches the cut-off, otherwise the nucleus is
+ * truncated to the candidates and the row is counted: mtx_engine_counter(e, 0, &n) (synchronising read). */
+size_t mtx_candidate_floats(const mtx_engine* e);
+int mtx_engine_counter(mtx_engine* e, int which, long long* value);
+
+/* inference_utils.sampling (+ log_prob_of_chosen_token) over MATERIALISED fp32 logits [rows, ld] (vocab entries per row) with
+ * the engine's strategy, temperature and random stream (row r draws the noise of row row_offset + r of the current step; the
+ * step counter is not advanced): token_out [rows], log_prob_out [rows] or NULL.  The decode step fuses this into the logits
+ * projection; this entry point serves callers that hold logits already (vocab-parallel prefill, tests). */
+int mtx_sample_logits(mtx_engine* e, const float* logits, int rows, long long ld, int vocab, int row_offset, int32_t* token_out,
+                      float* log_prob_out, mtx_stream stream);
 
 /* Measurement aid: one eager decode step with a CUDA-event pair around every kernel launch
  * (on `stream`), summed per kernel class into class_ms[10] / class_launches[10] (host arrays):

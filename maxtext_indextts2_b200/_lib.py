@@ -153,6 +153,12 @@ def _declare(lib) -> None:
   lib.mtx_decode_step_graph.argtypes = [vp, i32, vp]
   lib.mtx_decode_step_candidates.restype = i32
   lib.mtx_decode_step_candidates.argtypes = [vp, i32, vp, vp]
+  lib.mtx_sample_logits.restype = i32
+  lib.mtx_sample_logits.argtypes = [vp, vp, i32, c.c_longlong, i32, i32, vp, vp, vp]
+  lib.mtx_candidate_floats.restype = sz
+  lib.mtx_candidate_floats.argtypes = [vp]
+  lib.mtx_engine_counter.restype = i32
+  lib.mtx_engine_counter.argtypes = [vp, i32, c.POINTER(c.c_longlong)]
   lib.mtx_commit_candidates.restype = i32
   lib.mtx_commit_candidates.argtypes = [vp, i32, vp, i32, vp]
   lib.mtx_debug_set_trace.restype = None

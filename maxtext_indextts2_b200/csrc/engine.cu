@@ -315,6 +315,7 @@ struct mtx_engine {
   unsigned int* grid_bar = nullptr;
   PkTable* pk_tables = nullptr;
   float *pk_part_ws = nullptr, *pk_ss_x = nullptr, *pk_ss_h = nullptr, *pk_attn_part_o = nullptr;
+  int* cand_counters = nullptr;  // [0] nucleus rows truncated to the candidates, [1] commit ticket
   float *rows_ss_x = nullptr, *rows_ss_h = nullptr;  // gemm_rows.cuh fused RMSNorm statistics: [E/128 rounded up][max_r_tile]
   int *pk_tile_prefix = nullptr, *pk_attn_info = nullptr;
   XMaps xmaps[5];
@@ -333,7 +334,7 @@ struct WsLayout {
   size_t token, pos, plane, write_row, len0, ring_first, ring_len, rope_cs, work_items, work_count, rope_timescale;
   size_t part_score, part_idx, part_raw, part_max, part_sum, grid_bar;
   size_t pk_tables, pk_part_ws, pk_ss_x, pk_ss_h, pk_attn_part_o, pk_tile_prefix, pk_attn_info;
-  size_t rows_ss_x, rows_ss_h;
+  size_t rows_ss_x, rows_ss_h, cand_counters;
   size_t total;
 };
 
@@ -388,6 +389,7 @@ WsLayout layout_workspace(const mtx_engine* e) {
     L.pk_attn_info = take(64);
     L.rows_ss_x = take(rt * ss_tiles * 4);
     L.rows_ss_h = take(rt * ss_tiles * 4);
+    L.cand_counters = take(64);
   }
   L.total = off;
   return L;
@@ -845,6 +847,18 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     fa.stride_t = 1;
     fa.cand_out = cand_out;
     int finalize_rows = rows;
+    if (two_pass && cand_out != nullptr) {
+      // vocab-parallel top-k / nucleus: this shard's kCandK best logits per row + its (max, sum exp); the selection
+      // happens after the all-gather (mtx_commit_candidates)
+      ShardTopkArgs ta;
+      memset(&ta, 0, sizeof(ta));
+      ta.logits = e->s.logits;
+      ta.ld = c.vocab_size;
+      ta.vocab = c.vocab_size;
+      ta.vocab_offset = c.vocab_offset;
+      ta.cand = cand_out;
+      return launch(shard_topk_kernel, dim3(rows), dim3(kSampleThreads), 0, st, ta);
+    }
     if (two_pass) {
       // inference_utils.py:87-111 on the logits the GEMM just wrote; one candidate per row
       SampleArgs sa;
@@ -997,6 +1011,7 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   e->pk_attn_info = reinterpret_cast<int*>(b + L.pk_attn_info);
   e->rows_ss_x = reinterpret_cast<float*>(b + L.rows_ss_x);
   e->rows_ss_h = reinterpret_cast<float*>(b + L.rows_ss_h);
+  e->cand_counters = reinterpret_cast<int*>(b + L.cand_counters);
   MTX_CUDA(cudaMemcpy(e->rope_timescale, e->rope_timescale_host.data(), e->rope_timescale_host.size() * 4, cudaMemcpyHostToDevice));
 
   const int E = c.emb_dim, HD = c.num_q_heads * c.head_dim, M = c.mlp_dim, L_ = c.num_layers;
@@ -1113,15 +1128,97 @@ int mtx_decode_step_graph(mtx_engine* e, int rows, mtx_stream stream) {
 int mtx_decode_step_candidates(mtx_engine* e, int rows, float* candidates, mtx_stream stream) {
   if (!e || !e->bound || !candidates) return fail(MTX_ERR_ARG, "engine is not bound / null candidates");
   if (rows < 1 || rows > e->cfg.max_rows) return fail(MTX_ERR_ARG, "rows %d outside [1, %d]", rows, e->cfg.max_rows);
-  if (e->strategy == MTX_SAMPLE_NUCLEUS || e->strategy == MTX_SAMPLE_TOPK)
-    return fail(MTX_ERR_UNSUPPORTED, "vocab-parallel logits support greedy and weighted sampling");
+  if (e->strategy == MTX_SAMPLE_TOPK && e->top_k > kCandK)
+    return fail(MTX_ERR_UNSUPPORTED, "vocab-parallel top-k carries %d candidates per shard: decode_sampling_top_k must be <= %d", kCandK, kCandK);
   return enqueue_step(e, 0, rows, nullptr, 0, 0, 1, nullptr, nullptr, static_cast<cudaStream_t>(stream), candidates);
+}
+
+int mtx_sample_logits(mtx_engine* e, const float* logits, int rows, long long ld, int vocab, int row_offset, int32_t* token_out,
+                      float* log_prob_out, mtx_stream stream) {
+  if (!e || !e->bound || !logits || !token_out) return fail(MTX_ERR_ARG, "engine is not bound / null argument");
+  if (rows < 1 || rows > e->cfg.max_rows || vocab < 1 || ld < vocab) return fail(MTX_ERR_ARG, "bad rows / vocab / ld");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SampleArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.logits = logits;
+  sa.ld = ld;
+  sa.vocab = vocab;
+  sa.vocab_offset = 0;
+  sa.mode = e->strategy;
+  sa.top_k = e->top_k;
+  sa.nucleus_p = e->nucleus_p;
+  sa.inv_temp = 1.0f / e->temperature;
+  sa.rng_state = e->s.rng_state;
+  sa.row_offset = row_offset;
+  sa.out_score = e->part_score;
+  sa.out_idx = e->part_idx;
+  sa.out_raw = e->part_raw;
+  sa.out_max = e->part_max;
+  sa.out_sum = e->part_sum;
+  MTX_TRY(launch(sample_rows_kernel, dim3(rows), dim3(kSampleThreads), 0, st, sa));
+  FinalizeArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.part_score = e->part_score;
+  fa.part_idx = e->part_idx;
+  fa.part_raw = e->part_raw;
+  fa.part_max = e->part_max;
+  fa.part_sum = e->part_sum;
+  fa.n_tiles = 1;
+  fa.rows = rows;
+  fa.stride_r = 1;
+  fa.stride_t = 1;
+  fa.mode = 3;
+  fa.have_lse = 1;
+  fa.first_token = token_out;
+  fa.log_prob = log_prob_out;
+  fa.rng_state = e->s.rng_state;
+  return launch(finalize_kernel, dim3(rows), dim3(kFinalizeThreads), 0, st, fa);
+}
+
+size_t mtx_candidate_floats(const mtx_engine* e) {
+  if (!e) return 0;
+  return (e->strategy == MTX_SAMPLE_NUCLEUS || e->strategy == MTX_SAMPLE_TOPK) ? size_t(kCandFloats) : size_t(5);
+}
+
+int mtx_engine_counter(mtx_engine* e, int which, long long* value) {
+  if (!e || !e->bound || !value || which != 0) return fail(MTX_ERR_ARG, "bad counter request");
+  int v = 0;
+  MTX_CUDA(cudaMemcpy(&v, e->cand_counters + which, sizeof(int), cudaMemcpyDeviceToHost));
+  *value = v;
+  return MTX_OK;
 }
 
 int mtx_commit_candidates(mtx_engine* e, int rows, const float* gathered, int n_shards, mtx_stream stream) {
   if (!e || !e->bound || !gathered || n_shards < 1) return fail(MTX_ERR_ARG, "bad commit arguments");
   if (rows < 1 || rows > e->cfg.max_rows) return fail(MTX_ERR_ARG, "rows %d outside [1, %d]", rows, e->cfg.max_rows);
   const mtx_model_config& c = e->cfg;
+  if (e->strategy == MTX_SAMPLE_NUCLEUS || e->strategy == MTX_SAMPLE_TOPK) {
+    if (n_shards > kCandMaxShards) return fail(MTX_ERR_UNSUPPORTED, "at most %d vocabulary shards", kCandMaxShards);
+    CommitTopkArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.gathered = gathered;
+    ca.n_shards = n_shards;
+    ca.rows = rows;
+    ca.shard_vocab = c.vocab_size;
+    ca.mode = e->strategy;
+    ca.top_k = e->top_k;
+    ca.nucleus_p = e->nucleus_p;
+    ca.inv_temp = 1.0f / e->temperature;
+    ca.tokens = e->s.tokens;
+    ca.next_pos = e->s.next_pos;
+    ca.generated = e->s.generated;
+    ca.ar_lengths = e->s.ar_lengths;
+    ca.ar_index = e->s.ar_index;
+    ca.result = e->s.result;
+    ca.log_prob = e->s.log_prob;
+    ca.rng_state = e->s.rng_state;
+    ca.num_slots = c.num_slots;
+    ca.R = c.max_target_len - c.max_prefill_len;
+    ca.truncated = e->cand_counters;
+    ca.ticket = e->cand_counters + 1;
+    g_class = KC_FINALIZE;
+    return launch(commit_topk_kernel, dim3(rows), dim3(kSampleThreads), 0, static_cast<cudaStream_t>(stream), ca);
+  }
   FinalizeArgs fa;
   memset(&fa, 0, sizeof(fa));
   fa.part_score = gathered + 0 * rows;

@@ -232,7 +232,8 @@ struct FinalizeArgs {
   long long stride_r, stride_t;  // element (row r, tile t) of every part_* array is at [r * stride_r + t * stride_t]
   float* cand_out;               // mode 2: [5][rows] = best score, vocab id (int bits), its logit, max, sum exp
   int mode;  // 0 = decode step: advance the state; 1 = prefill: only emit the last row's token;
-             // 2 = vocab-parallel shard: emit this shard's candidate per row, do not advance
+             // 2 = vocab-parallel shard: emit this shard's candidate per row, do not advance;
+             // 3 = mtx_sample_logits: first_token[r] / log_prob[r] for every row, nothing advances
   int have_lse;  // part_max / part_sum are valid
   // decode state (maxengine.py:913-936)
   int* tokens;
@@ -325,6 +326,9 @@ __global__ void __launch_bounds__(kFinalizeThreads) finalize_kernel(const Finali
       a.result[r * 3 + 0] = idx;
       a.result[r * 3 + 1] = 1;
       a.result[r * 3 + 2] = gen;
+      if (a.log_prob != nullptr) a.log_prob[r] = logp;
+    } else if (a.mode == 3) {
+      a.first_token[r] = idx;
       if (a.log_prob != nullptr) a.log_prob[r] = logp;
     } else if (r == a.rows - 1) {
       a.first_token[0] = idx;

@@ -250,8 +250,10 @@ class MaxEngine:
       self._vp_rank, self._vp_world = dist.get_rank(), dist.get_world_size()
       self._gather = parallel.all_gather_candidates
     self._v_lo, self._v_hi = parallel.vocab_shard(config.vocab_size, self._vp_world, self._vp_rank)
-    if self._vp_world > 1 and config.decode_sampling_strategy in ("topk", "nucleus"):
-      raise ValueError("vocab-parallel logits support greedy and weighted sampling")
+    if self._vp_world > 1 and config.decode_sampling_strategy == "topk" and int(config.decode_sampling_top_k) > 64:
+      raise ValueError("vocab-parallel top-k gathers 64 candidates per shard: decode_sampling_top_k must be <= 64")
+    if self._vp_world > 8:
+      raise ValueError("at most 8 vocabulary shards")
     scale = 1.0
     if config.logits_via_embedding and config.normalize_embedding_logits:
       scale = 1.0 / math.sqrt(config.emb_dim)  # decoders.py:560-562
@@ -332,7 +334,7 @@ class MaxEngine:
     two_pass = cfg.decode_sampling_strategy in ("topk", "nucleus")
     V = self._v_hi - self._v_lo  # logits columns held by this process (all of them unless vocab-parallel)
     self._logits = z(B, 1, V, dtype=torch.float32) if (cfg.materialize_logits or two_pass) else None
-    self._cand = z(5, max(B, self._chunk), dtype=torch.float32)
+    self._cand = z(130 * max(B, self._chunk), dtype=torch.float32)  # candidate payload of the vocab-parallel mode (5 or 130 floats per row)
     self._rng_state = z(4)
     self._first_token = z(1)
     self._prefill_logits = z(V, dtype=torch.float32)
@@ -468,11 +470,11 @@ class MaxEngine:
     n = toks.numel()
     self._prefill_tokens[:n].copy_(toks.to(torch.int32), non_blocking=True)
     want_logits = self._logits is not None or self._vp_world > 1
-    if self._vp_world > 1 and cfg.decode_sampling_strategy != "greedy":
-      raise NotImplementedError("vocab-parallel prefill picks the first token greedily only")
+    last_count = 1
     for start in range(0, true_length, self._chunk):
       count = min(self._chunk, true_length - start)
       last = start + count == true_length
+      last_count = count
       _lib.check(
           self.lib.mtx_prefill_chunk(
               self._handle,
@@ -487,10 +489,12 @@ class MaxEngine:
           )
       )
     if self._vp_world > 1:
-      # first token: merge the per-shard winners of the last prompt position (not on the decode hot path)
-      cand = parallel.candidates_from_logits(self._prefill_logits.reshape(1, -1), self._v_lo)
-      token, _ = parallel.merge_candidates_reference(self._gather(cand))
-      self._first_token.copy_(token.to(torch.int32))
+      # first token (not on the decode hot path): the shards' logits of the last prompt position are gathered into the full
+      # row and sampled with the configured strategy by the same kernel on every rank
+      full = self._gather(self._prefill_logits.reshape(1, -1)).reshape(1, -1).contiguous()  # shards are in vocabulary order
+      # (the noise row of the last prompt position inside its chunk, as the unsharded prefill draws it)
+      _lib.check(self.lib.mtx_sample_logits(self._handle, ctypes.c_void_p(full.data_ptr()), 1, full.shape[1], full.shape[1], last_count - 1,
+                                            ctypes.c_void_p(self._first_token.data_ptr()), None, self._stream()))
     first = self._first_token.clone().reshape(1, 1)
     prefix = {
         "logits": self._prefill_logits.clone().reshape(1, 1, -1) if want_logits else None,
@@ -541,7 +545,7 @@ class MaxEngine:
     B = self.max_concurrent_decodes
     if self._vp_world > 1:
       # each rank scores its vocabulary shard; one all-gather of 5*B floats; identical commit everywhere
-      cand = self._cand[:, :B].contiguous()
+      cand = self.candidate_buffer(B)
       _lib.check(self.lib.mtx_decode_step_candidates(self._handle, B, ctypes.c_void_p(cand.data_ptr()), self._stream()))
       gathered = self._gather(cand).contiguous()
       _lib.check(self.lib.mtx_commit_candidates(self._handle, B, ctypes.c_void_p(gathered.data_ptr()), self._vp_world, self._stream()))
@@ -553,6 +557,19 @@ class MaxEngine:
         log_prob=self._log_prob.clone() if self._log_prob is not None else None,
     )
     return decode_state, result
+
+  def candidate_buffer(self, rows: int) -> torch.Tensor:
+    """This rank's payload of the vocab-parallel all-gather: [5, rows] (greedy / weighted: the shard's winner per row) or
+    [rows, 130] (top-k / nucleus: its 64 best logits, their ids, max, sum exp)."""
+    nf = int(self.lib.mtx_candidate_floats(self._handle))
+    flat = self._cand[: rows * nf]
+    return flat.view(5, rows) if nf == 5 else flat.view(rows, nf)
+
+  def nucleus_truncated_rows(self) -> int:
+    """Rows (since load_params) whose nucleus reached past the gathered candidates (vocab-parallel nucleus only)."""
+    v = ctypes.c_longlong(0)
+    _lib.check(self.lib.mtx_engine_counter(self._handle, 0, ctypes.byref(v)))
+    return int(v.value)
 
   # -- helpers for tests / benchmarks ----------------------------------------------------------
 
