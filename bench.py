@@ -58,7 +58,8 @@ def parse_args():
   ap.add_argument("--cpu-steps", type=int, default=8, help="timed steps of the cpu_baseline leg of the GPU arm (after 2 warm-ups)")
   ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-clock bound of a CPU leg; steps are cut (and reported) past it")
   ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of one step of the timed state")
-  ap.add_argument("--mode", default="batch", choices=["batch", "vocab-parallel"],
+  ap.add_argument("--prompt-len", type=int, default=4000, help="--mode prefill: prompt tokens (BASELINE configs[3]: 4000 of P = 4096)")
+  ap.add_argument("--mode", default="batch", choices=["batch", "vocab-parallel", "prefill"],
                   help="batch: request-batch partitioned, no collective (default); vocab-parallel: every GPU decodes the same --batch slots, "
                        "the logits projection is sharded over the GPUs and one NCCL all-gather carries the per-shard candidates")
   ap.add_argument("--sampling", default="greedy", choices=["greedy", "weighted", "topk", "nucleus"], help="decode_sampling_strategy")
@@ -312,7 +313,8 @@ def persistent_phase_times(lib, engine, B, sptr, L):
   release of the previous grid barrier to the release of the phase's own barrier (all CTAs, %globaltimer)."""
   from maxtext_indextts2_b200 import _lib
 
-  words = int(lib.mtx_step_trace_words())
+  words = int(lib.mtx_step_trace_words(engine._handle))
+  nb_alloc = max(200, 2 + 5 * L + 2)
   tr = torch.zeros(words, dtype=torch.int64, device="cuda")
   lib.mtx_debug_set_trace(ctypes.c_void_p(tr.data_ptr()))
   try:
@@ -326,7 +328,7 @@ def persistent_phase_times(lib, engine, B, sptr, L):
   g = int(np.argmax(t < t[0] - 100000))  # row 0 = end stamps (largest), row 1 = start stamps (smallest)
   if g <= 0:
     return None
-  a = t[: 400 * g].reshape(-1, g)
+  a = t[: 2 * nb_alloc * g].reshape(-1, g)
   start, end = a[1], a[0]
   rel = [start.max()]
   nb = 2 + 5 * L
@@ -487,10 +489,70 @@ def run_vocab_parallel(args, world, rank, local_rank):
   }
 
 
+def run_prefill(args):
+  """--mode prefill: MaxEngine.prefill of one `--prompt-len`-token prompt (BASELINE configs[3]: the 4k text + reference-audio prompt,
+  timed separately from the decode steps), chunks of prefill_chunk_size rows through the tcgen05 GEMMs and the causal attention
+  kernel, then MaxEngine.insert into slot 0.  Not the judged metric: a second line for profiles/."""
+  from maxtext_indextts2_b200 import maxengine
+
+  if not args.prefill_len:
+    args.prefill_len, args.target_len = 4096, 5632
+  args.batch = max(1, min(args.batch, 8))
+  cfg = make_config(args)
+  engine = maxengine.MaxEngine(cfg)
+  dparams = engine.load_params(on_device_init=True)
+  state = engine.init_decode_state()
+  n = min(args.prompt_len, cfg.max_prefill_predict_length)
+  tokens = torch.randint(0, cfg.vocab_size, (cfg.max_prefill_predict_length,), generator=torch.Generator().manual_seed(1))
+  stream = torch.cuda.current_stream()
+  for _ in range(max(2, args.warmup)):
+    prefix, _ = engine.prefill(params=dparams, padded_tokens=tokens, true_length=n)
+  torch.cuda.synchronize()
+  steps = max(1, min(args.steps, 20))
+  n0 = engine.lib.mtx_launch_count()
+  e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+  pre_ms, ins_ms = 0.0, 0.0
+  for _ in range(steps):
+    e0.record(stream)
+    prefix, first = engine.prefill(params=dparams, padded_tokens=tokens, true_length=n)
+    e1.record(stream)
+    state = engine.insert(prefix, state, 0)
+    e2.record(stream)
+    torch.cuda.synchronize()
+    pre_ms += e0.elapsed_time(e1)
+    ins_ms += e1.elapsed_time(e2)
+  launches = int(engine.lib.mtx_launch_count() - n0) // steps
+  E, Hq, Hkv, D, M, L = cfg.emb_dim, cfg.num_query_heads, cfg.num_kv_heads, cfg.head_dim, cfg.mlp_dim, cfg.num_decoder_layers
+  gemm_flops = 2.0 * n * L * (E * Hq * D + 2 * E * Hkv * D + Hq * D * E + 3 * E * M)
+  attn_flops = 4.0 * (n * (n + 1) / 2) * L * Hq * D
+  line = {
+      "metric": "prefill ms for one prompt (BASELINE configs[3], timed separately from decode)",
+      "mode": "prefill",
+      "value": pre_ms / steps,
+      "unit": "ms",
+      "higher_is_better": False,
+      "n_gpus": 1,
+      "steps": steps,
+      "insert_ms": ins_ms / steps,
+      "prompt_tokens": n,
+      "prompt_tokens_per_s": n / (pre_ms / steps / 1e3),
+      "tflops": (gemm_flops + attn_flops) / (pre_ms / steps / 1e3) / 1e12,
+      "gpu_launches_per_prefill": launches,
+      "dtype": "bf16",
+      "data": "synthetic",
+      "config": {"workload": f"L={L} E={E} Hq={Hq} Hkv={Hkv} D={D} M={M} V={cfg.vocab_size}, prompt {n} of P={cfg.max_prefill_predict_length}, chunk {cfg.prefill_chunk_size}"},
+  }
+  print(json.dumps(line), flush=True)
+
+
 def main():
   args = parse_args()
   if args.impl == "reference":
     run_reference_arm(args)
+    return
+  if args.mode == "prefill":
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    run_prefill(args)
     return
 
   import torch.distributed as dist
@@ -576,23 +638,19 @@ def main():
   barrier()
   elapsed_ms = ev0.elapsed_time(ev1)
 
-  # ---- end to end through the public API: host tokens in (pinned), result tokens out ----
+  # ---- end to end through the public API with HOST buffers: this step's tokens in (pinned), result tokens out (pinned) ----
   host_in = torch.zeros(B, 1, dtype=torch.int32).pin_memory()
   host_out = torch.zeros(B, 3, dtype=torch.int32).pin_memory()
   host_in.copy_(state["tokens"].cpu())
   for _ in range(2):
-    state["tokens"].copy_(host_in, non_blocking=True)
-    state, result = engine.generate(dparams, state)
-    host_out.copy_(result.data, non_blocking=True)
+    state, result = engine.generate_to_host(dparams, state, host_out, host_tokens=host_in)
     torch.cuda.synchronize()
   barrier()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  t_wall0 = time.perf_counter()
   e0.record(stream)
   for _ in range(args.steps):
-    state["tokens"].copy_(host_in, non_blocking=True)  # H2D: this step's input tokens
-    state, result = engine.generate(dparams, state)
-    host_out.copy_(result.data, non_blocking=True)  # D2H: sampled tokens
+    # H2D of this step's input tokens, the step, D2H of the sampled tokens: one call, one stream sync per step
+    state, result = engine.generate_to_host(dparams, state, host_out, host_tokens=host_in)
     stream.synchronize()  # the caller needs the tokens before the next step (detokenise / stop check)
     host_in[:, 0] = host_out[:, 0]
   e1.record(stream)
@@ -693,7 +751,7 @@ def main():
             "ms_per_step": e2e_ms / args.steps,
             "h2d_bytes_per_step": B * 4,
             "d2h_bytes_per_step": B * 3 * 4,
-            "api": "MaxEngine.generate with pinned host token buffers, one stream sync per step",
+            "api": "MaxEngine.generate_to_host (mtx_decode_step_host): pinned host token buffer in, ResultTokens.data to a pinned host buffer, one stream sync per step",
         },
         "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step,

@@ -66,6 +66,8 @@ typedef struct {
   float final_softcap;       /* final_logits_soft_cap, 0 = off */
   float logits_scale;        /* 1, or 1/sqrt(E) when logits_via_embedding && normalize_embedding_logits */
   int32_t logits_round_bf16; /* 1 unless logits_dot_in_fp32 (decoders.py:557,571) */
+  int32_t embedding_rows;    /* rows of the embedding table: token ids are clamped into [0, embedding_rows) as jnp indexing does
+                                (embeddings.py:154); 0 = do not clamp */
   int32_t norm_scales_folded; /* 1: wqkv / w01 already carry the per-feature RMSNorm scales of their input (W' = W * diag(scale),
                                  folded at load time) and attn_norm / mlp_norm are all ones: the step skips the scale pass */
 } mtx_model_config;
@@ -139,6 +141,13 @@ int mtx_decode_step(mtx_engine* e, int rows, mtx_stream stream);
 /* Same step, replayed from a CUDA graph captured on first use (one graph per `rows`). */
 int mtx_decode_step_graph(mtx_engine* e, int rows, mtx_stream stream);
 
+/* The step as a serving loop calls it, with HOST buffers (pinned memory for the copies to be asynchronous): optionally copies this
+ * step's input tokens host -> device (tokens_host [rows] or NULL to keep decode_state.tokens), replays the step's CUDA graph, and
+ * copies ResultTokens.data [rows, 3] (and the log-probs [rows] when log_prob_host is non-NULL and return_log_prob is on) device ->
+ * host, all enqueued on `stream`: the caller synchronises the stream once and reads result_host (offline_engine.py:612-614 copies
+ * the result tokens to the host the same way). */
+int mtx_decode_step_host(mtx_engine* e, int rows, const int32_t* tokens_host, int32_t* result_host, float* log_prob_host, mtx_stream stream);
+
 /* Vocab-parallel logits: this process holds `vocab_size` rows of the logits matrix starting
  * at `vocab_offset`.  mtx_decode_step_candidates runs the whole step but, instead of committing a token,
  * writes this shard's winner per row to candidates[5][rows] (fp32: score, vocab id as int bits, its
@@ -159,7 +168,8 @@ int mtx_engine_counter(mtx_engine* e, int which, long long* value);
 
 /* inference_utils.sampling (+ log_prob_of_chosen_token) over MATERIALISED fp32 logits [rows, ld] (vocab entries per row) with
  * the engine's strategy, temperature and random stream (row r draws the noise of row row_offset + r of the current step; the
- * step counter is not advanced): token_out [rows], log_prob_out [rows] or NULL.  The decode step fuses this into the logits
+ * step counter is not advanced; row_offset < 0: the noise row of the engine's last prefill draw): token_out [rows],
+ * log_prob_out [rows] or NULL.  The decode step fuses this into the logits
  * projection; this entry point serves callers that hold logits already (vocab-parallel prefill, tests). */
 int mtx_sample_logits(mtx_engine* e, const float* logits, int rows, long long ld, int vocab, int row_offset, int32_t* token_out,
                       float* log_prob_out, mtx_stream stream);
@@ -176,9 +186,18 @@ int mtx_profile_decode_step(mtx_engine* e, int rows, mtx_stream stream, float* c
  * prefill segment of plane `slot`: MaxEngine._prefill_jit (maxengine.py:400-530) with
  * KVCache.kv_cache_prefill (kvcache.py:584-624), processed as rows of one step with causal
  * lengths.  If `sample_last`, the last position's logits are sampled into first_token[0]
- * (and copied to logits_out [V] fp32 when non-NULL). */
+ * (and copied to logits_out [V] fp32 when non-NULL); its log-probability goes to first_log_prob[0] when non-NULL
+ * (return_log_prob, maxengine.py:503-520).  The sampler's noise for a prefill draw comes from its own row namespace (one per
+ * prefill call), never from the rows of a decode step. */
 int mtx_prefill_chunk(mtx_engine* e, const int32_t* tokens, int count, int start_pos, int slot, int sample_last,
-                      int32_t* first_token, float* logits_out, mtx_stream stream);
+                      int32_t* first_token, float* logits_out, float* first_log_prob, mtx_stream stream);
+
+/* MaxEngine.insert (maxengine.py:1166-1192, _insert_jit :1045-1164): the first n_rows cache rows of a prefix (k_src / v_src
+ * [L, Hkv, n_src_rows, D] bf16, what prefill left) into the prefill segment of decode slot `slot`, every layer and head in one
+ * launch, and the slot's bookkeeping: prefill_len = n_rows, ar_lengths = 0, next_pos / generated / tokens as given.  The AR ring
+ * and the shared ring index are not touched. */
+int mtx_insert_prefix(mtx_engine* e, const void* k_src, const void* v_src, int n_rows, int n_src_rows, int slot, int next_pos, int generated,
+                      int token, mtx_stream stream);
 
 /* ---- single fused ops (the same kernels the step uses) ------------------------------------ */
 
@@ -236,7 +255,7 @@ int mtx_engine_rebind_state(mtx_engine* e, const mtx_decode_state* s);
 /* Measurement aid: grid-barrier timeline of the persistent step kernel.  While a device buffer of
  * mtx_step_trace_words() 64-bit words is installed with mtx_debug_set_trace, every CTA records
  * %globaltimer at the arrival at and the release from each grid barrier (see tools/mega_trace.py). */
-size_t mtx_step_trace_words(void);
+size_t mtx_step_trace_words(const mtx_engine* e); /* sized for the engine's grid and layer count (NULL: 148 CTAs, 24 layers) */
 
 /* 1 when the library was built with jaxlib's headers and exports the XLA FFI handler symbols of csrc/mtx_jax_ffi.cc
  * (MtxRaggedAttention, MtxDecodeAttention, MtxQkvRopeAppend, MtxDecodeStep), else 0. */
@@ -246,7 +265,8 @@ const char* mtx_last_error(void);
 /* "sm_100a" build tag, so a caller can check what it loaded. */
 const char* mtx_build_info(void);
 /* Debug aid: when non-NULL (device memory, 256 x int64), the GEMM and attention kernels record
- * a clock64 timeline of their first CTA into it.  NULL (the default) switches it off. */
+ * a clock64 timeline of their first CTA into it.  NULL (the default) switches it off.  The pointer is read when a step is
+ * enqueued: CUDA graphs captured earlier keep the value they were captured with (use mtx_decode_step for traced steps). */
 void mtx_debug_set_trace(void* device_buffer);
 /* Debug aid: when non-NULL (device memory, 3004+ x uint64, zeroed), every kernel's first CTA appends
  * (kind, start ns, end ns) by %globaltimer; [0] counts the entries. */

@@ -53,6 +53,7 @@ class ModelConfig(ctypes.Structure):
       ("final_softcap", ctypes.c_float),
       ("logits_scale", ctypes.c_float),
       ("logits_round_bf16", ctypes.c_int32),
+      ("embedding_rows", ctypes.c_int32),
       ("norm_scales_folded", ctypes.c_int32),
   ]
 
@@ -151,6 +152,8 @@ def _declare(lib) -> None:
   lib.mtx_decode_step.argtypes = [vp, i32, vp]
   lib.mtx_decode_step_graph.restype = i32
   lib.mtx_decode_step_graph.argtypes = [vp, i32, vp]
+  lib.mtx_decode_step_host.restype = i32
+  lib.mtx_decode_step_host.argtypes = [vp, i32, vp, vp, vp, vp]
   lib.mtx_decode_step_candidates.restype = i32
   lib.mtx_decode_step_candidates.argtypes = [vp, i32, vp, vp]
   lib.mtx_sample_logits.restype = i32
@@ -164,13 +167,15 @@ def _declare(lib) -> None:
   lib.mtx_debug_set_trace.restype = None
   lib.mtx_debug_set_trace.argtypes = [vp]
   lib.mtx_step_trace_words.restype = sz
-  lib.mtx_step_trace_words.argtypes = []
+  lib.mtx_step_trace_words.argtypes = [vp]
   lib.mtx_debug_set_timeline.restype = i32
   lib.mtx_debug_set_timeline.argtypes = [vp]
   lib.mtx_profile_decode_step.restype = i32
   lib.mtx_profile_decode_step.argtypes = [vp, i32, vp, c.POINTER(c.c_float), c.POINTER(c.c_int32)]
   lib.mtx_prefill_chunk.restype = i32
-  lib.mtx_prefill_chunk.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp]
+  lib.mtx_prefill_chunk.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+  lib.mtx_insert_prefix.restype = i32
+  lib.mtx_insert_prefix.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
   lib.mtx_rmsnorm.restype = i32
   lib.mtx_rmsnorm.argtypes = [vp, vp, vp, i32, i32, f32, vp]
   lib.mtx_linear.restype = i32

@@ -15,6 +15,7 @@
 #include "attention.cuh"
 #include "gemm_rows.cuh"
 #include "gemm_umma.cuh"
+#include "prefill_attention.cuh"
 #include "sampling.cuh"
 #include "step_kernels.cuh"
 #include "step_persistent.cuh"
@@ -109,6 +110,7 @@ bool use_pdl() {
 }
 
 thread_local int g_cluster_y = 1;  // cluster size along grid.y for the next launch (split-K GEMM)
+thread_local bool g_cooperative = false;  // next launch is cooperative: all its CTAs are co-resident or the launch fails
 
 template <typename... KArgs, typename... Args>
 int launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
@@ -120,7 +122,11 @@ int launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStr
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  if (use_pdl()) {
+  if (g_cooperative) {
+    attr[na].id = cudaLaunchAttributeCooperative;
+    attr[na].val.cooperative = 1;
+    ++na;
+  } else if (use_pdl()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
@@ -320,6 +326,8 @@ struct mtx_engine {
   int *pk_tile_prefix = nullptr, *pk_attn_info = nullptr;
   XMaps xmaps[5];
   // sampling
+  int last_prefill_rows = 1;   // rows of the last sampling prefill chunk (the draw's row inside its block)
+  unsigned prefill_draws = 0;  // prefill calls that sampled a first token: each draws its noise from its own row namespace
   int strategy = MTX_SAMPLE_GREEDY, top_k = 0;
   float nucleus_p = 0.f, temperature = 1.f;
   // graphs
@@ -442,6 +450,38 @@ int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st) {
   if (grid > cap) grid = cap;
   if (c.head_dim == 64) return launch(decode_attn_kernel<64>, dim3(grid), dim3(kAttnThreads), smem, st, e->tm_k, e->tm_v, p);
   return launch(decode_attn_kernel<128>, dim3(grid), dim3(kAttnThreads), smem, st, e->tm_k, e->tm_v, p);
+}
+
+// Causal attention of one prefill chunk (prefill_attention.cuh): the chunk's positions share the K/V tiles.
+bool use_prefill_attention(const mtx_engine* e) {
+  static int on = env_int("MTX_PREFILL_ATTENTION", 1);
+  (void)e;
+  return on != 0;
+}
+
+int launch_prefill_attention(mtx_engine* e, int layer, int rows, int start_pos, int slot, cudaStream_t st) {
+  const mtx_model_config& c = e->cfg;
+  PrefillAttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = e->q;
+  p.out = e->attn;
+  p.rows = rows;
+  p.start_pos = start_pos;
+  p.hq = c.num_q_heads;
+  p.hkv = c.num_kv_heads;
+  p.T = c.max_target_len;
+  p.plane_row0 = (layer * c.num_slots + slot) * c.num_kv_heads * c.max_target_len;
+  p.softcap = c.attn_softcap;
+  const dim3 grid(c.num_q_heads, (rows + kPfQRows - 1) / kPfQRows), block(kPfWarps * 32);
+  const size_t smem = prefill_attn_smem_bytes(c.head_dim);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MTX_CUDA(cudaFuncSetAttribute(prefill_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(prefill_attn_smem_bytes(64))));
+    MTX_CUDA(cudaFuncSetAttribute(prefill_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(prefill_attn_smem_bytes(128))));
+    attr_set = true;
+  }
+  if (c.head_dim == 64) return launch(prefill_attn_kernel<64>, grid, block, smem, st, e->tm_k, e->tm_v, p);
+  return launch(prefill_attn_kernel<128>, grid, block, smem, st, e->tm_k, e->tm_v, p);
 }
 
 // ---- persistent step kernel: work tables and launch -------------------------------------------
@@ -572,6 +612,9 @@ bool pk_fill_phase(std::vector<PkTable>& tabs, int ph, int n, int k, bool allow_
   return true;
 }
 
+// Barrier slots of the step trace: 200 (the layout tools/ were written for) or what the layer count needs.
+int pk_trace_bars(int layers) { return 2 + 5 * layers + 2 > 200 ? 2 + 5 * layers + 2 : 200; }
+
 bool pk_usable(const mtx_engine* e, int rows) {
   if (e->pk_ctas <= 0 || round_rows(rows) > kPkMaxRTile) return false;
   if (e->cfg.num_q_heads / e->cfg.num_kv_heads > 8) return false;  // the attention MMA carries the group's heads in its 8 columns
@@ -632,15 +675,27 @@ int launch_persistent(mtx_engine* e, int rows, const XMaps& xm, const EpiArgs& l
   p.logits = logits_epi;
   p.grid_bar = e->grid_bar;
   p.trace = g_trace;
+  p.trace_bars = pk_trace_bars(c.num_layers);
   p.variant = env_int("MTX_PK_VARIANT", 0);
   p.fold = c.norm_scales_folded ? 1 : 0;
-  return launch(step_persistent_kernel, dim3(e->pk_ctas), dim3(kPkThreads), pk_smem_bytes(), st, e->tm_all_wqkv, e->tm_all_wo, e->tm_all_w01,
-                e->tm_all_wout, e->tm_logits, xm.x, xm.attn, xm.h, xm.act, xm.n, e->tm_k, e->tm_v, p);
+  // The kernel spins on a software grid barrier.  MTX_PK_COOPERATIVE=1 launches it cooperatively, so the driver guarantees that
+  // all CTAs are resident together (or fails the launch) whatever else shares the device: the setting for a GPU shared with
+  // other streams / processes.  Default off: a dedicated GPU (one process per GPU, one engine per process, as MaxEngine is
+  // deployed) passes the occupancy check of mtx_engine_bind once, and the cooperative launch costs programmatic dependent
+  // launch against the prepare kernel and 45 us per CUDA-graph replay end to end (profiles/r2k_cooperative_ab.txt).
+  g_cooperative = env_int("MTX_PK_COOPERATIVE", 0) != 0;
+  const int rc = launch(step_persistent_kernel, dim3(e->pk_ctas), dim3(kPkThreads), pk_smem_bytes(), st, e->tm_all_wqkv, e->tm_all_wo, e->tm_all_w01,
+                        e->tm_all_wout, e->tm_logits, xm.x, xm.attn, xm.h, xm.act, xm.n, e->tm_k, e->tm_v, p);
+  g_cooperative = false;
+  return rc;
 }
 
 // The kernels of one step, in stream order.  mode 0 = decode, 1 = prefill chunk.
+// Noise row of a prefill draw: outside the rows of any decode step (< 256), one block of 256 rows per prefill call.
+int prefill_noise_row(const mtx_engine* e) { return 0x40000000 + int(e->prefill_draws % 0x100000u) * 256; }
+
 int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens, int start_pos, int slot, int want_logits,
-                 int32_t* first_token, float* prefill_logits, cudaStream_t st, float* cand_out = nullptr) {
+                 int32_t* first_token, float* prefill_logits, cudaStream_t st, float* cand_out = nullptr, float* first_log_prob = nullptr) {
   const mtx_model_config& c = e->cfg;
   const int r_tile = round_rows(rows);
   XMaps* xm;
@@ -664,6 +719,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   pa.T = c.max_target_len;
   pa.D = c.head_dim;
   pa.tiles_per_item = attn_tiles_per_item(rows, c.num_kv_heads, c.max_prefill_len, c.max_target_len, attn_target_items(e->num_sms));
+  pa.emb_rows = c.embedding_rows;
   pa.rope_timescale = e->rope_timescale;
   const bool mega = mode == 0 && want_logits && pk_usable(e, rows);
   if (mega) {
@@ -740,7 +796,8 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     else MTX_TRY(launch_gemm<EPI_QKV_ROPE>(e->tm_wqkv[l], xm->n, gp, ea, plan_qkv, st));
 
     g_class = KC_ATTENTION;
-    MTX_TRY(launch_attention(e, l, rows, st));
+    if (mode == 1 && use_prefill_attention(e)) MTX_TRY(launch_prefill_attention(e, l, rows, start_pos, slot, st));
+    else MTX_TRY(launch_attention(e, l, rows, st));
 
     memset(&ea, 0, sizeof(ea));
     ea.out = e->h;
@@ -818,9 +875,10 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     ea.inv_temp = 1.0f / e->temperature;
     ea.round_bf16 = c.logits_round_bf16;
     ea.gumbel = e->strategy == MTX_SAMPLE_WEIGHTED ? 1 : 0;
-    ea.want_lse = ((e->s.log_prob != nullptr || cand_out != nullptr) && !two_pass) ? 1 : 0;
+    float* lp_out = mode == 0 ? e->s.log_prob : first_log_prob;
+    ea.want_lse = ((lp_out != nullptr || cand_out != nullptr) && !two_pass) ? 1 : 0;
     ea.rng_state = e->s.rng_state;
-    ea.row_offset = 0;
+    ea.row_offset = mode == 0 ? 0 : prefill_noise_row(e);
     gp.n = c.vocab_size;
     gp.k = E;
     g_class = KC_LOGITS;
@@ -872,7 +930,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
       sa.nucleus_p = e->nucleus_p;
       sa.inv_temp = 1.0f / e->temperature;
       sa.rng_state = e->s.rng_state;
-      sa.row_offset = mode == 0 ? 0 : rows - 1;
+      sa.row_offset = mode == 0 ? 0 : prefill_noise_row(e) + rows - 1;
       sa.out_score = e->part_score;
       sa.out_idx = e->part_idx;
       sa.out_raw = e->part_raw;
@@ -885,14 +943,14 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
       fa.rows = finalize_rows;
     }
     fa.mode = cand_out != nullptr ? 2 : mode;
-    fa.have_lse = (two_pass || e->s.log_prob != nullptr || cand_out != nullptr) ? 1 : 0;
+    fa.have_lse = (two_pass || lp_out != nullptr || cand_out != nullptr) ? 1 : 0;
     fa.tokens = e->s.tokens;
     fa.next_pos = e->s.next_pos;
     fa.generated = e->s.generated;
     fa.ar_lengths = e->s.ar_lengths;
     fa.ar_index = e->s.ar_index;
     fa.result = e->s.result;
-    fa.log_prob = e->s.log_prob;
+    fa.log_prob = lp_out;
     fa.rng_state = e->s.rng_state;
     fa.num_slots = c.num_slots;
     fa.R = c.max_target_len - c.max_prefill_len;
@@ -911,7 +969,10 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
 extern "C" {
 
 const char* mtx_last_error(void) { return g_error.c_str(); }
-size_t mtx_step_trace_words(void) { return size_t(2) * 200 * 148 + size_t(148) * 3 * 64; }
+size_t mtx_step_trace_words(const mtx_engine* e) {
+  const size_t ctas = e && e->pk_ctas > 0 ? size_t(e->pk_ctas) : 148, bars = size_t(pk_trace_bars(e ? e->cfg.num_layers : 24));
+  return 2 * bars * ctas + ctas * 3 * 64;
+}
 void mtx_debug_set_trace(void* device_buffer) { g_trace = static_cast<long long*>(device_buffer); }
 int mtx_debug_set_timeline(void* device_buffer) {
   unsigned long long* p = static_cast<unsigned long long*>(device_buffer);
@@ -973,6 +1034,8 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   e->graphs.clear();
   for (auto& m : e->xmaps) m.built = false;
+  // (re)binding rewrites the workspace: wait for everything the device still runs, on any stream, before and after
+  MTX_CUDA(cudaDeviceSynchronize());
   MTX_CUDA(cudaMemset(workspace, 0, e->ws_bytes));
   const WsLayout L = layout_workspace(e);
   uint8_t* b = static_cast<uint8_t*>(workspace);
@@ -1125,6 +1188,18 @@ int mtx_decode_step_graph(mtx_engine* e, int rows, mtx_stream stream) {
   return MTX_OK;
 }
 
+int mtx_decode_step_host(mtx_engine* e, int rows, const int32_t* tokens_host, int32_t* result_host, float* log_prob_host, mtx_stream stream) {
+  if (!e || !e->bound || !result_host) return fail(MTX_ERR_ARG, "engine is not bound / null result buffer");
+  if (rows < 1 || rows > e->cfg.max_rows) return fail(MTX_ERR_ARG, "rows %d outside [1, %d]", rows, e->cfg.max_rows);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tokens_host != nullptr) MTX_CUDA(cudaMemcpyAsync(e->s.tokens, tokens_host, size_t(rows) * 4, cudaMemcpyHostToDevice, st));
+  MTX_TRY(mtx_decode_step_graph(e, rows, stream));
+  MTX_CUDA(cudaMemcpyAsync(result_host, e->s.result, size_t(rows) * 12, cudaMemcpyDeviceToHost, st));
+  if (log_prob_host != nullptr && e->s.log_prob != nullptr)
+    MTX_CUDA(cudaMemcpyAsync(log_prob_host, e->s.log_prob, size_t(rows) * 4, cudaMemcpyDeviceToHost, st));
+  return MTX_OK;
+}
+
 int mtx_decode_step_candidates(mtx_engine* e, int rows, float* candidates, mtx_stream stream) {
   if (!e || !e->bound || !candidates) return fail(MTX_ERR_ARG, "engine is not bound / null candidates");
   if (rows < 1 || rows > e->cfg.max_rows) return fail(MTX_ERR_ARG, "rows %d outside [1, %d]", rows, e->cfg.max_rows);
@@ -1149,7 +1224,7 @@ int mtx_sample_logits(mtx_engine* e, const float* logits, int rows, long long ld
   sa.nucleus_p = e->nucleus_p;
   sa.inv_temp = 1.0f / e->temperature;
   sa.rng_state = e->s.rng_state;
-  sa.row_offset = row_offset;
+  sa.row_offset = row_offset < 0 ? prefill_noise_row(e) + e->last_prefill_rows - 1 : row_offset;
   sa.out_score = e->part_score;
   sa.out_idx = e->part_idx;
   sa.out_raw = e->part_raw;
@@ -1270,13 +1345,52 @@ int mtx_profile_decode_step(mtx_engine* e, int rows, mtx_stream stream, float* c
 }
 
 int mtx_prefill_chunk(mtx_engine* e, const int32_t* tokens, int count, int start_pos, int slot, int sample_last,
-                      int32_t* first_token, float* logits_out, mtx_stream stream) {
+                      int32_t* first_token, float* logits_out, float* first_log_prob, mtx_stream stream) {
   if (!e || !e->bound) return fail(MTX_ERR_ARG, "engine is not bound");
   if (count < 1 || count > e->cfg.max_rows) return fail(MTX_ERR_ARG, "count %d outside [1, %d]", count, e->cfg.max_rows);
   if (start_pos < 0 || start_pos + count > e->cfg.max_prefill_len) return fail(MTX_ERR_ARG, "prompt positions exceed max_prefill_len");
   if (slot < 0 || slot >= e->cfg.num_slots) return fail(MTX_ERR_ARG, "slot out of range");
   if (sample_last && first_token == nullptr) return fail(MTX_ERR_ARG, "first_token is null");
-  return enqueue_step(e, 1, count, tokens, start_pos, slot, sample_last, first_token, logits_out, static_cast<cudaStream_t>(stream));
+  if (sample_last) {
+    ++e->prefill_draws;
+    e->last_prefill_rows = count;
+  }
+  return enqueue_step(e, 1, count, tokens, start_pos, slot, sample_last, first_token, logits_out, static_cast<cudaStream_t>(stream), nullptr,
+                      first_log_prob);
+}
+
+int mtx_insert_prefix(mtx_engine* e, const void* k_src, const void* v_src, int n_rows, int n_src_rows, int slot, int next_pos, int generated,
+                      int token, mtx_stream stream) {
+  if (!e || !e->bound || !k_src || !v_src) return fail(MTX_ERR_ARG, "engine is not bound / null prefix");
+  const mtx_model_config& c = e->cfg;
+  if (slot < 0 || slot >= c.num_slots) return fail(MTX_ERR_ARG, "slot out of range");
+  if (n_rows < 1 || n_rows > n_src_rows || n_rows > c.max_prefill_len) return fail(MTX_ERR_ARG, "prefix rows %d outside [1, min(%d, %d)]", n_rows, n_src_rows, c.max_prefill_len);
+  InsertArgs a;
+  memset(&a, 0, sizeof(a));
+  a.k_src = static_cast<const bf16*>(k_src);
+  a.v_src = static_cast<const bf16*>(v_src);
+  a.k_cache = static_cast<bf16*>(e->s.k_cache);
+  a.v_cache = static_cast<bf16*>(e->s.v_cache);
+  a.L = c.num_layers;
+  a.hkv = c.num_kv_heads;
+  a.D = c.head_dim;
+  a.T = c.max_target_len;
+  a.planes = c.num_slots;
+  a.n = n_rows;
+  a.n_src = n_src_rows;
+  a.slot = slot;
+  a.next_pos = next_pos;
+  a.generated = generated;
+  a.token = token;
+  a.prefill_len = e->s.prefill_len;
+  a.ar_lengths = e->s.ar_lengths;
+  a.next_pos_out = e->s.next_pos;
+  a.generated_out = e->s.generated;
+  a.tokens_out = e->s.tokens;
+  const long long vecs = (long long)c.num_layers * c.num_kv_heads * n_rows * (c.head_dim / 8);
+  int grid = int((vecs + 255) / 256);
+  if (grid > e->num_sms * 8) grid = e->num_sms * 8;
+  return launch(insert_prefix_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), a);
 }
 
 // ---- single ops ------------------------------------------------------------------------------

@@ -33,6 +33,7 @@ struct PrepareArgs {
   int start_pos, slot;
   int mode, rows, P, T, D;
   int tiles_per_item;  // attention work-item size (attn_tiles_per_item)
+  int emb_rows;        // token ids are clamped into [0, emb_rows) (0: off)
   const float* rope_timescale;  // [D/2] min * (max/min)^(2i/D), embeddings.py:270-275
   // persistent step kernel (step_persistent.cuh): counters reset here, attention tile partition
   unsigned int* grid_bar;  // grid-barrier arrival counter
@@ -78,6 +79,7 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
       rf = 0;
       rl = 0;
     }
+    if (a.emb_rows > 0) token = token < 0 ? 0 : (token >= a.emb_rows ? a.emb_rows - 1 : token);
     rd.token[tid] = token;
     rd.pos[tid] = pos;
     rd.plane[tid] = plane;
@@ -220,6 +222,46 @@ embed_gather_ss_kernel(const int* __restrict__ tokens, const bf16* __restrict__ 
   if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x < ss_tiles) ss[threadIdx.x * ss_pitch + r] = threadIdx.x == 0 ? s_part[0] + s_part[1] + s_part[2] + s_part[3] : 0.0f;
+}
+
+// MaxEngine.insert (maxengine.py:1045-1164; KVCache prefill segment, kvcache.py:584-624): the first `n` cache rows of a prefix
+// ([L, Hkv, n_src, D], as MaxEngine.prefill returned it) into plane `slot` of the decode cache [L, planes, Hkv, T, D], K and V of
+// every layer and head in ONE launch of 16-byte copies, plus the slot's bookkeeping (the AR ring data and the shared ring index
+// stay untouched: maxengine.py:1060-1067).
+struct InsertArgs {
+  const bf16* k_src;
+  const bf16* v_src;
+  bf16* k_cache;
+  bf16* v_cache;
+  int L, hkv, D, T, planes, n, n_src, slot;
+  int next_pos, generated, token;
+  int* prefill_len;
+  int* ar_lengths;
+  int* next_pos_out;
+  int* generated_out;
+  int* tokens_out;
+};
+__global__ void __launch_bounds__(256) insert_prefix_kernel(const InsertArgs a) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int vec_per_row = a.D / 8;                              // uint4 per cache row
+  const long long per_lh = (long long)a.n * vec_per_row;        // vectors per (layer, head)
+  const long long total = per_lh * a.L * a.hkv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long lh = i / per_lh, rem = i - lh * per_lh;
+    const int l = int(lh / a.hkv), h = int(lh - (long long)l * a.hkv);
+    const long long src = ((long long)(l * a.hkv + h) * a.n_src) * a.D + rem * 8;
+    const long long dst = (((long long)(l * a.planes + a.slot) * a.hkv + h) * a.T) * a.D + rem * 8;
+    *reinterpret_cast<uint4*>(a.k_cache + dst) = *reinterpret_cast<const uint4*>(a.k_src + src);
+    *reinterpret_cast<uint4*>(a.v_cache + dst) = *reinterpret_cast<const uint4*>(a.v_src + src);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.prefill_len[a.slot] = a.n;
+    a.ar_lengths[a.slot] = 0;
+    a.next_pos_out[a.slot] = a.next_pos;
+    a.generated_out[a.slot] = a.generated;
+    a.tokens_out[a.slot] = a.token;
+  }
 }
 
 struct FinalizeArgs {

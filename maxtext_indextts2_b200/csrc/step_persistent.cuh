@@ -137,6 +137,7 @@ struct PkParams {
   EpiArgs logits;
   unsigned int* grid_bar;  // zeroed by prepare_rows_kernel
   long long* trace;        // debug: globaltimer at [barrier k][arrive|release][cta], or null
+  int trace_bars;          // barrier slots of the trace buffer (>= 2 + 5 L + 1, see mtx_step_trace_words)
   int variant;             // experiment switches (MTX_PK_VARIANT): bit 0 = L2 prefetch of the next layer's K/V tiles at the end of a
                            // warp's tile loop, bit 1 = L2 prefetch of this layer's K/V tiles at the start of the layer
   int fold;                // 1: the RMSNorm scales are folded into wqkv / w01 (mtx_model_config.norm_scales_folded): no scale pass
@@ -153,7 +154,7 @@ struct PkEv {
 };
 __device__ __forceinline__ PkEv pk_ev_make(const PkParams& p, int role) {
   PkEv e;
-  e.base = p.trace ? p.trace + 2 * 200 * (long long)gridDim.x + ((long long)blockIdx.x * 3 + role) * 64 : nullptr;
+  e.base = p.trace ? p.trace + 2 * (long long)p.trace_bars * gridDim.x + ((long long)blockIdx.x * 3 + role) * 64 : nullptr;
   e.n = 0;
   e.on = false;
   e.brief = false;

@@ -277,6 +277,7 @@ class MaxEngine:
         final_softcap=float(config.final_logits_soft_cap or 0.0),
         logits_scale=scale,
         logits_round_bf16=0 if config.logits_dot_in_fp32 else 1,
+        embedding_rows=config.vocab_size,
         norm_scales_folded=1 if config.fold_norm_scales else 0,
     )
     _lib.check(self.lib.mtx_engine_create(ctypes.byref(self._cfg_struct), ctypes.byref(self._handle)))
@@ -337,6 +338,7 @@ class MaxEngine:
     self._cand = z(130 * max(B, self._chunk), dtype=torch.float32)  # candidate payload of the vocab-parallel mode (5 or 130 floats per row)
     self._rng_state = z(4)
     self._first_token = z(1)
+    self._first_log_prob = z(1, dtype=torch.float32) if cfg.return_log_prob else None
     self._prefill_logits = z(V, dtype=torch.float32)
     self._prefill_tokens = z(cfg.max_prefill_predict_length)
     self._state_struct = _lib.DecodeState(
@@ -470,11 +472,9 @@ class MaxEngine:
     n = toks.numel()
     self._prefill_tokens[:n].copy_(toks.to(torch.int32), non_blocking=True)
     want_logits = self._logits is not None or self._vp_world > 1
-    last_count = 1
     for start in range(0, true_length, self._chunk):
       count = min(self._chunk, true_length - start)
       last = start + count == true_length
-      last_count = count
       _lib.check(
           self.lib.mtx_prefill_chunk(
               self._handle,
@@ -485,6 +485,7 @@ class MaxEngine:
               1 if last else 0,
               ctypes.c_void_p(self._first_token.data_ptr()),
               ctypes.c_void_p(self._prefill_logits.data_ptr()) if (want_logits and last) else None,
+              ctypes.c_void_p(self._first_log_prob.data_ptr()) if (self._first_log_prob is not None and last) else None,
               self._stream(),
           )
       )
@@ -492,9 +493,11 @@ class MaxEngine:
       # first token (not on the decode hot path): the shards' logits of the last prompt position are gathered into the full
       # row and sampled with the configured strategy by the same kernel on every rank
       full = self._gather(self._prefill_logits.reshape(1, -1)).reshape(1, -1).contiguous()  # shards are in vocabulary order
-      # (the noise row of the last prompt position inside its chunk, as the unsharded prefill draws it)
-      _lib.check(self.lib.mtx_sample_logits(self._handle, ctypes.c_void_p(full.data_ptr()), 1, full.shape[1], full.shape[1], last_count - 1,
-                                            ctypes.c_void_p(self._first_token.data_ptr()), None, self._stream()))
+      # (row_offset -1: the noise row of the prefill draw just made, as the unsharded prefill uses it)
+      _lib.check(self.lib.mtx_sample_logits(self._handle, ctypes.c_void_p(full.data_ptr()), 1, full.shape[1], full.shape[1], -1,
+                                            ctypes.c_void_p(self._first_token.data_ptr()),
+                                            ctypes.c_void_p(self._first_log_prob.data_ptr()) if self._first_log_prob is not None else None,
+                                            self._stream()))
     first = self._first_token.clone().reshape(1, 1)
     prefix = {
         "logits": self._prefill_logits.clone().reshape(1, 1, -1) if want_logits else None,
@@ -508,7 +511,8 @@ class MaxEngine:
         "tokens": first,
     }
     data = torch.cat((first, torch.ones_like(first), torch.zeros_like(first)), dim=1)
-    return prefix, ResultTokens(data=data)
+    log_prob = self._first_log_prob.clone().reshape(1, 1) if self._first_log_prob is not None else None
+    return prefix, ResultTokens(data=data, log_prob=log_prob)
 
   def insert(self, prefix: dict, decode_state: dict, slot: int, request_id: Any = None) -> dict:
     """maxengine.py:1045-1164: copy the prefill segment into `slot`, reset the slot's AR bookkeeping,
@@ -519,10 +523,14 @@ class MaxEngine:
     if not 0 <= int(slot) < B:
       raise ValueError(f"slot {slot} outside [0, {B})")
     n = int(prefix["cache"]["prefill_length"])
-    self._k[:, slot, :, :n].copy_(prefix["cache"]["key"])
-    self._v[:, slot, :, :n].copy_(prefix["cache"]["value"])
-    self._prefill_len[slot] = n
-    self._ar_lengths[slot] = 0
+    k_src, v_src = prefix["cache"]["key"], prefix["cache"]["value"]  # [L, Hkv, n_src, D]
+    if not (k_src.is_contiguous() and v_src.is_contiguous()):
+      k_src, v_src = k_src.contiguous(), v_src.contiguous()
+    # token / position ride along as launch arguments when they are host values; device tensors (the usual case) are copied
+    _lib.check(
+        self.lib.mtx_insert_prefix(
+            self._handle, ctypes.c_void_p(k_src.data_ptr()), ctypes.c_void_p(v_src.data_ptr()), n, int(k_src.shape[2]), int(slot),
+            n, 0, 0, self._stream()))
     self._next_pos[slot].copy_(prefix["next_pos"][0])
     self._generated[slot].copy_(prefix["generated_tokens"][0])
     self._tokens[slot].copy_(prefix["tokens"][0])
@@ -557,6 +565,29 @@ class MaxEngine:
         log_prob=self._log_prob.clone() if self._log_prob is not None else None,
     )
     return decode_state, result
+
+  def generate_to_host(self, params: DeviceParams, decode_state: dict, host_result: torch.Tensor, host_tokens: Optional[torch.Tensor] = None,
+                       host_log_prob: Optional[torch.Tensor] = None):
+    """``generate`` for a serving loop that holds its tokens on the host (JetStream / OfflineEngine copy every step's
+    ResultTokens to the host: offline_engine.py:612-614): one C call enqueues the host -> device copy of this step's input tokens
+    (`host_tokens` [B,1] int32 pinned, or None to continue from decode_state["tokens"]), the step's CUDA-graph replay and the
+    device -> host copy of ResultTokens.data into `host_result` [B,3] int32 pinned.  Nothing synchronises: the caller waits on the
+    current stream and reads `host_result`.  Returns (decode_state, ResultTokens over the host buffers)."""
+    if decode_state is not self._state:
+      raise ValueError("decode_state must be the dict returned by this engine's init_decode_state (it is donated)")
+    if self._vp_world > 1:
+      raise ValueError("generate_to_host is the batch-partitioned path; the vocab-parallel mode goes through generate()")
+    self._bind(params)
+    B = self.max_concurrent_decodes
+    for t, n in ((host_result, 3 * B), (host_tokens, B), (host_log_prob, B)):
+      if t is not None and (t.is_cuda or not t.is_contiguous() or t.numel() != n or t.element_size() != 4):
+        raise ValueError("host buffers must be contiguous 4-byte CPU tensors of B*3 (result), B (tokens), B (log-probs) elements")
+    _lib.check(
+        self.lib.mtx_decode_step_host(
+            self._handle, B, ctypes.c_void_p(host_tokens.data_ptr()) if host_tokens is not None else None,
+            ctypes.c_void_p(host_result.data_ptr()), ctypes.c_void_p(host_log_prob.data_ptr()) if host_log_prob is not None else None,
+            self._stream()))
+    return decode_state, ResultTokens(data=host_result, log_prob=host_log_prob)
 
   def candidate_buffer(self, rows: int) -> torch.Tensor:
     """This rank's payload of the vocab-parallel all-gather: [5, rows] (greedy / weighted: the shard's winner per row) or

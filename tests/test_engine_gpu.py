@@ -277,3 +277,39 @@ def test_indextts2_scale_logits_and_greedy_tokens():
   d = (state["logits"].cpu() - ostate["logits"]).abs()
   assert (d > 0.1 + 0.1 * ostate["logits"].abs()).float().mean() < 1e-5
   assert near <= 2
+
+
+def test_generate_to_host_matches_generate():
+  """mtx_decode_step_host (host tokens in, ResultTokens.data out to pinned host memory, one graph replay in between) produces what
+  generate() produces; feeding the tokens back from the host buffer continues the same sequence."""
+  cfg = small_config(per_device_batch_size=3, max_prefill_predict_length=16, max_target_length=48, return_log_prob=True)
+  params = make_params(cfg)
+  prompts = random_tokens((3, 16), cfg.vocab_size, seed=8)
+  runs = []
+  for use_host in (False, True):
+    engine = maxengine.MaxEngine(cfg)
+    dparams = engine.load_params(params)
+    state = engine.init_decode_state()
+    for slot, n in enumerate((16, 4, 9)):
+      prefix, _ = engine.prefill(params=dparams, padded_tokens=prompts[slot], true_length=n)
+      state = engine.insert(prefix, state, slot)
+    host_out = torch.zeros(3, 3, dtype=torch.int32).pin_memory()
+    host_lp = torch.zeros(3, 1, dtype=torch.float32).pin_memory()
+    host_in = state["tokens"].cpu().pin_memory()
+    toks = []
+    for step in range(6):
+      if use_host:
+        state, res = engine.generate_to_host(dparams, state, host_out, host_tokens=host_in, host_log_prob=host_lp)
+        torch.cuda.synchronize()
+        assert res.data is host_out
+        host_in[:, 0] = host_out[:, 0]
+        toks.append((host_out.clone(), host_lp.clone()))
+      else:
+        state, res = engine.generate(dparams, state)
+        toks.append((res.data.cpu(), res.log_prob.cpu()))
+    runs.append(toks)
+    with pytest.raises(ValueError):
+      engine.generate_to_host(dparams, state, torch.zeros(2, 3, dtype=torch.int32))
+  for (da, la), (db, lb) in zip(*runs):
+    assert torch.equal(da, db)
+    torch.testing.assert_close(la, lb, rtol=0, atol=0)
