@@ -52,6 +52,7 @@ def parse_args():
   ap.add_argument("--prefill-len", type=int, default=0, help="override max_prefill_predict_length (BASELINE configs[3]: 4096)")
   ap.add_argument("--target-len", type=int, default=0, help="override max_target_length (BASELINE configs[3]: 5632)")
   ap.add_argument("--no-graph", action="store_true")
+  ap.add_argument("--kv-int8", action="store_true", help="quantize_kvcache=True, kv_quant_dtype=int8, kv_quant_axis=dkv (SURVEY 8f-2; not the judged line)")
   ap.add_argument("--no-fold", action="store_true", help="keep the RMSNorm scales out of the weights (fold_norm_scales=False)")
   ap.add_argument("--skip-cpu-baseline", action="store_true")
   ap.add_argument("--cpu-slots", type=int, default=0, help="slots in the CPU baseline sample (0 = all slots of the batch)")
@@ -78,6 +79,8 @@ def make_config(args):
     kw["max_target_length"] = args.target_len
   if args.no_fold:
     kw["fold_norm_scales"] = False
+  if args.kv_int8:
+    kw.update(quantize_kvcache=True, kv_quant_dtype="int8", kv_quant_axis="dkv")
   if args.sampling != "greedy":
     kw["decode_sampling_strategy"] = args.sampling
     kw["decode_sampling_top_k"] = 64
@@ -105,13 +108,15 @@ def algorithmic_bytes(cfg, batch, ctx_sum):
   w_norm = 2 * (2 * L + 1) * E
   w_logits = 2 * E * V
   kv_row = L * 2 * Hkv * D * 2
+  if cfg.quantize_kvcache:
+    kv_row = L * 2 * Hkv * (D + 4)  # one byte per element + one fp32 scale per (token, kv head)
   return {
       "weights": w_layers + w_norm + w_logits,
       "kv_read": int(ctx_sum) * kv_row,
       "kv_write": batch * kv_row,
       "misc": batch * E * 2 + batch * 8,
       "logits_weights": w_logits,
-      "attention_per_layer": int(ctx_sum) * 2 * Hkv * D * 2,
+      "attention_per_layer": int(ctx_sum) * kv_row // L,
   }
 
 
@@ -290,6 +295,7 @@ def workload_config(args, cfg, world=None):
       "global_batch": per_gpu * world,
       "context": f"uniform[{args.context_min},{args.context_max}] valid rows per slot, P={cfg.max_prefill_predict_length} T={cfg.max_target_length}",
       "parallelism": f"request-batch partitioned x{world}, no collective",
+      "kv_cache": "int8 + fp32 scale per (token, kv head)" if cfg.quantize_kvcache else "bf16",
       "l2": "working set per step (weights 1.81 GB + KV 1.6 GB) exceeds the 126 MB L2; no flush needed",
   }
 
@@ -742,7 +748,7 @@ def main():
         "higher_is_better": True,
         "scaling": args.scaling,
         "vs_baseline": None,
-        "dtype": "bf16",
+        "dtype": "bf16" if not cfg.quantize_kvcache else "bf16 (int8 KV cache)",
         "data": "synthetic",
         "config": workload_config(args, cfg, world),
         "e2e": {

@@ -68,6 +68,9 @@ typedef struct {
   int32_t logits_round_bf16; /* 1 unless logits_dot_in_fp32 (decoders.py:557,571) */
   int32_t embedding_rows;    /* rows of the embedding table: token ids are clamped into [0, embedding_rows) as jnp indexing does
                                 (embeddings.py:154); 0 = do not clamp */
+  int32_t kv_quant;          /* 0: bf16 KV cache.  1: int8 with one fp32 scale per (token, kv head) -- quantize_kvcache=True,
+                                kv_quant_dtype=int8, kv_quant_axis=dkv (inference/kvcache.py:36-90): decode_state.kq_cache / vq_cache /
+                                k_scale / v_scale hold the decode cache, k_cache / v_cache are ONE bf16 staging plane for prefill */
   int32_t norm_scales_folded; /* 1: wqkv / w01 already carry the per-feature RMSNorm scales of their input (W' = W * diag(scale),
                                  folded at load time) and attn_norm / mlp_norm are all ones: the step skips the scale pass */
 } mtx_model_config;
@@ -115,6 +118,14 @@ typedef struct {
   float* log_prob;       /* [B] or NULL (return_log_prob)         */
   float* logits;         /* [B,V] fp32 or NULL: decode_state["logits"], only written when non-NULL */
   uint32_t* rng_state;   /* [4] sampler stream: {step, seed_lo, seed_hi, 0}; step advances once per decode step */
+  /* kv_quant = 1 only (else NULL): the decode cache as unsigned bytes u = q + 128, q = clip(rint(x * 127.5 / scale), -128, 127),
+   * [L, num_slots, Hkv, T, D] with scale = max|x| over the D dims of the row in k_scale / v_scale [L, num_slots, Hkv, T] fp32
+   * (KVQuant.quantize, kvcache.py:76-90; dequantised value = q * scale / 127.5).  k_cache / v_cache are then [L, 1, Hkv, T, D]
+   * bf16: the plane prefill writes; mtx_insert_prefix quantises a prefix into a slot. */
+  void* kq_cache;
+  void* vq_cache;
+  float* k_scale;
+  float* v_scale;
 } mtx_decode_state;
 
 /* ---- engine ---------------------------------------------------------------------------- */

@@ -54,6 +54,7 @@ class ModelConfig(ctypes.Structure):
       ("logits_scale", ctypes.c_float),
       ("logits_round_bf16", ctypes.c_int32),
       ("embedding_rows", ctypes.c_int32),
+      ("kv_quant", ctypes.c_int32),
       ("norm_scales_folded", ctypes.c_int32),
   ]
 
@@ -81,6 +82,10 @@ class DecodeState(ctypes.Structure):
           "log_prob",
           "logits",
           "rng_state",
+          "kq_cache",
+          "vq_cache",
+          "k_scale",
+          "v_scale",
       )
   ]
 

@@ -19,6 +19,8 @@
 // arrive for a (row, kv-head) writing the bf16 result.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace mtx {
@@ -438,6 +440,350 @@ decode_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
 __host__ inline size_t attn_smem_bytes(int D, int G) {
   const size_t o_rows = G <= 8 ? 8 : 16;
   return 1024 + size_t(kAttnWarps) * 2 * (64 * D * 2) + kAttnWarps * o_rows * D * 4 + 2 * kAttnWarps * 8 + 2 * kAttnWarps * 16 * 4 + 32;
+}
+
+// ---- int8 KV cache (quantize_kvcache, kv_quant_dtype int8, kv_quant_axis dkv: MaxText/inference/kvcache.py:36-90) ---------
+//
+// A cache row of one kv head is 64 unsigned bytes u = q + 128 with q = clip(rint(x * 127.5 / scale), -128, 127) and one fp32
+// scale = max|x| over the head's 64 dims (KVQuant.quantize with the "dkv" axis); x ~ q * scale / 127.5.  The tile loop below is
+// the bf16 one with three changes:
+//   * K / V tiles are 4 KB (TMA, SWIZZLE_64B); bytes become EXACT fp16 integers in registers with one byte permute per pair
+//     (0x6400 | u = 1024 + u, minus 1152) and the MMAs run in fp16 (the queries, bf16 values, convert exactly);
+//   * the per-row scales are folded in where they are per-MMA-row constants: k_scale[kv] / 127.5 multiplies the scores,
+//     v_scale[kv] / 127.5 multiplies the probabilities before the P V product;
+//   * a dot product does not care about the order of its terms, so the head dims are PERMUTED to make every operand fragment
+//     a vector load: a thread takes 16 consecutive bytes of a K row for all four k-steps of S = Q K^T (the query fragments are
+//     gathered with the same permutation), and 8 consecutive bytes of a V row for all eight output blocks of O = P V (the
+//     output columns come out permuted: element (n-block j, column c) is head dim 8 c + j).
+constexpr int kQ8WarpBytes = 9216;  // per warp: K tile 4 KB | V tile 4 KB | 64 K scales + 64 V scales (+ pad)
+constexpr float kQ8Inv = 1.0f / 127.5f;
+
+__device__ __forceinline__ void mma_m16n8k16_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// Two bytes of `w` (selected by `sel`: 0x4140 = bytes 0,1; 0x4342 = bytes 2,3; 0x5140 = byte 0 of w and byte 0 of the second word ...)
+// as the exact fp16 pair (u_lo - 128, u_hi - 128).
+__device__ __forceinline__ uint32_t q8_pair_f16(uint32_t w, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x64646464u), "r"(sel));
+  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(0x64806480u));
+  return r;
+}
+__device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t v) {
+  const __half2 h = __floats2half2_rn(bf16_lo(v), bf16_hi(v));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// The attention work loop of 128 threads (4 warps) over an int8 cache, head_dim 64.  Same contract as attn_process_items;
+// `tiles` = [warp][kQ8WarpBytes], k_scale / v_scale = fp32 per cache row, indexed like the rows of the K/V tensor maps.
+__device__ __forceinline__ void attn_process_items_q8(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnParams& p, const float* k_scale,
+                                                      const float* v_scale, uint8_t* tiles, float* sm_o_all, uint64_t* bars, float* sm_stat,
+                                                      uint32_t& phase, int tid, int first_item, int item_stride) {
+  constexpr int D = 64;
+  constexpr int kTileBytes = 64 * D;  // one warp's K (or V) tile: 64 rows of 64 bytes
+  constexpr float kLog2e = 1.4426950408889634f;
+  const int G = p.hq / p.hkv;
+  const int o_rows = G <= 8 ? 8 : 16;
+  float* sm_m = sm_stat;                 // [4][16]
+  float* sm_l = sm_m + kAttnWarps * 16;  // [4][16]
+  volatile int* s_last_p = reinterpret_cast<volatile int*>(sm_l + kAttnWarps * 16);
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int gid = lane >> 2, tid4 = lane & 3;
+  const int R = p.T - p.P;
+  const int TPI = p.tiles_per_item;
+  uint8_t* k_tile = tiles + warp * kQ8WarpBytes;
+  uint8_t* v_tile = k_tile + kTileBytes;
+  float* s_ks = reinterpret_cast<float*>(k_tile + 2 * kTileBytes);  // [64] K scales of the tile (already / 127.5)
+  float* s_vs = s_ks + 64;                                          // [64] V scales
+  float* sm_o = sm_o_all + warp * o_rows * D;
+  uint64_t* bar_k = bars + 2 * warp;
+  uint64_t* bar_v = bar_k + 1;
+  const uint32_t kb = smem_u32(k_tile), vb = smem_u32(v_tile);
+
+  const int n_items = *p.work_count * p.hkv;
+  for (int item = first_item; item < n_items; item += item_stride) {
+    const int packed = p.work_items[item / p.hkv];
+    const int h = item % p.hkv;
+    const int r = packed >> 16, chunk = packed & 0xffff;
+    const int len0 = p.len0[r], rf = p.ring_first[r], rl = p.ring_len[r];
+    const int nt = attn_num_tiles(len0, rf, rl, R);
+    const int n_chunks = (nt + TPI - 1) / TPI;
+    const int t_begin = chunk * TPI, t_end = min(nt, t_begin + TPI);
+    const int plane_row = ((p.plane_base + p.plane[r]) * p.hkv + h) * p.T;
+
+    int t = t_begin + warp;
+    TileLoc loc = attn_tile(t < t_end ? t : nt, len0, rf, rl, p.P, R);  // t >= nt gives an empty tile
+    if (t < t_end && lane == 0) {
+      mbar_expect_tx(bar_k, kTileBytes);
+      tma_load_2d(k_tile, &tm_k, 0, plane_row + loc.p0, bar_k, kEvictFirst);
+      mbar_expect_tx(bar_v, kTileBytes);
+      tma_load_2d(v_tile, &tm_v, 0, plane_row + loc.p0, bar_v, kEvictFirst);
+    }
+
+    // Q fragments (A operand: rows = query heads of the group, zero-padded to 16) as fp16, head dims gathered with the K
+    // permutation: k-slot (2 tid4 + e) of k-step tt is head dim 16 tid4 + 4 tt + e, k-slot (2 tid4 + 8 + e) is dim 16 tid4 + 4 tt + 2 + e
+    uint32_t qf[4][4];
+    {
+      const bf16* qrow = p.q + (long long)r * p.hq * D + (long long)h * G * D;
+#pragma unroll
+      for (int tt = 0; tt < 4; ++tt) {
+        const int d = 16 * tid4 + 4 * tt;
+        qf[tt][0] = gid < G ? bf16x2_to_f16x2(*reinterpret_cast<const uint32_t*>(qrow + gid * D + d)) : 0u;
+        qf[tt][1] = gid + 8 < G ? bf16x2_to_f16x2(*reinterpret_cast<const uint32_t*>(qrow + (gid + 8) * D + d)) : 0u;
+        qf[tt][2] = gid < G ? bf16x2_to_f16x2(*reinterpret_cast<const uint32_t*>(qrow + gid * D + d + 2)) : 0u;
+        qf[tt][3] = gid + 8 < G ? bf16x2_to_f16x2(*reinterpret_cast<const uint32_t*>(qrow + (gid + 8) * D + d + 2)) : 0u;
+      }
+    }
+
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+    float o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.0f;
+
+    for (; t < t_end; t += kAttnWarps) {
+      const int cnt = loc.cnt;
+      const int tn = t + kAttnWarps;
+      const TileLoc nloc = attn_tile(tn < t_end ? tn : nt, len0, rf, rl, p.P, R);
+      // the tile's scales: two rows per lane, staged for the per-column reads below
+      {
+        const long long row0 = (long long)plane_row + loc.p0;
+        __syncwarp();
+        s_ks[lane] = lane < cnt ? __ldg(k_scale + row0 + lane) * kQ8Inv : 0.0f;
+        s_ks[lane + 32] = lane + 32 < cnt ? __ldg(k_scale + row0 + lane + 32) * kQ8Inv : 0.0f;
+        s_vs[lane] = lane < cnt ? __ldg(v_scale + row0 + lane) * kQ8Inv : 0.0f;
+        s_vs[lane + 32] = lane + 32 < cnt ? __ldg(v_scale + row0 + lane + 32) * kQ8Inv : 0.0f;
+        __syncwarp();
+      }
+      // ---- S = Q K^T over the 64 rows of the tile: n-block j = kv rows 8 j .. 8 j + 7, one 16-byte load per row ----
+      float s[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
+      mbar_wait(bar_k, phase);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int row = 8 * j + gid;
+        const uint32_t addr = kb + row * 64 + ((tid4 ^ ((row >> 1) & 3)) << 4);
+        uint32_t w[4];
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt) mma_m16n8k16_f16(s[j], qf[tt], q8_pair_f16(w[tt], 0x4140u), q8_pair_f16(w[tt], 0x4342u));
+      }
+      // K tile consumed: refill it with the next tile's keys while the softmax and P V run
+      fence_proxy_async();
+      __syncwarp();
+      if (tn < t_end && lane == 0) {
+        mbar_expect_tx(bar_k, kTileBytes);
+        tma_load_2d(k_tile, &tm_k, 0, plane_row + nloc.p0, bar_k, kEvictFirst);
+      }
+      // ---- dequantise the scores (per kv column), mask, online softmax ----
+      float vs[8][2];
+      float tm0 = -INFINITY, tm1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 ks2 = *reinterpret_cast<const float2*>(s_ks + 8 * j + tid4 * 2);
+        const float2 vs2 = *reinterpret_cast<const float2*>(s_vs + 8 * j + tid4 * 2);
+        vs[j][0] = vs2.x;
+        vs[j][1] = vs2.y;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = 8 * j + tid4 * 2 + (e & 1);
+          float x = s[j][e] * ((e & 1) ? ks2.y : ks2.x);
+          if (p.softcap != 0.0f) x = tanhf(x / p.softcap) * p.softcap;
+          s[j][e] = col < cnt ? x : -INFINITY;
+        }
+        tm0 = fmaxf(tm0, fmaxf(s[j][0], s[j][1]));
+        tm1 = fmaxf(tm1, fmaxf(s[j][2], s[j][3]));
+      }
+      tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 1));
+      tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, 2));
+      tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 1));
+      tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, 2));
+      const float nm0 = fmaxf(m0, tm0), nm1 = fmaxf(m1, tm1);
+      const float a0 = exp2f((m0 - nm0) * kLog2e), a1 = exp2f((m1 - nm1) * kLog2e);  // exp2(-inf) = 0 on the first tile
+      m0 = nm0;
+      m1 = nm1;
+      l0 *= a0;
+      l1 *= a1;
+      uint32_t pa[4][4];  // P (times the V scale of its column) as the fp16 A operand, one k-step per 16 kv rows
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p0 = exp2f((s[j][0] - m0) * kLog2e), p1 = exp2f((s[j][1] - m0) * kLog2e);
+        const float p2 = exp2f((s[j][2] - m1) * kLog2e), p3 = exp2f((s[j][3] - m1) * kLog2e);
+        l0 += p0 + p1;
+        l1 += p2 + p3;
+        pa[j >> 1][(j & 1) * 2 + 0] = pack_f16x2(p0 * vs[j][0], p1 * vs[j][1]);
+        pa[j >> 1][(j & 1) * 2 + 1] = pack_f16x2(p2 * vs[j][0], p3 * vs[j][1]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j][0] *= a0;
+        o[j][1] *= a0;
+        o[j][2] *= a1;
+        o[j][3] *= a1;
+      }
+      // ---- O += P V: k-step u = kv rows 16 u .. 16 u + 15; B column gid of n-block j is head dim 8 gid + j, so a thread reads the
+      // 8 bytes V[row][8 gid .. 8 gid + 7] of its four kv rows and builds the B fragments of all eight n-blocks from them ----
+      mbar_wait(bar_v, phase);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint32_t lo[4], hi[4];  // rows 16 u + 2 tid4, + 1, + 8, + 9: bytes 0..3 and 4..7 of the 8-byte run
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int row = 16 * u + 2 * tid4 + (q & 1) + 8 * (q >> 1);
+          const uint32_t addr = vb + row * 64 + ((((gid >> 1) ^ ((row >> 1) & 3)) << 4) | ((gid & 1) << 3));
+          asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(lo[q]), "=r"(hi[q]) : "r"(addr));
+          if (row >= cnt) lo[q] = hi[q] = 0x80808080u;  // rows past the valid count may hold anything: make them zero (u = 128)
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // byte j of the run: rows (2 tid4, 2 tid4 + 1) -> b0, rows (2 tid4 + 8, 2 tid4 + 9) -> b1
+          const uint32_t w0 = j < 4 ? lo[0] : hi[0], w1 = j < 4 ? lo[1] : hi[1], w2 = j < 4 ? lo[2] : hi[2], w3 = j < 4 ? lo[3] : hi[3];
+          uint32_t g0, g1;
+          const uint32_t selg = 0x0040u + 0x0011u * uint32_t(j & 3);  // (byte j of the first word, byte j of the second word)
+          asm("prmt.b32 %0, %1, %2, %3;" : "=r"(g0) : "r"(w0), "r"(w1), "r"(selg));
+          asm("prmt.b32 %0, %1, %2, %3;" : "=r"(g1) : "r"(w2), "r"(w3), "r"(selg));
+          mma_m16n8k16_f16(o[j], pa[u], q8_pair_f16(g0, 0x4140u), q8_pair_f16(g1, 0x4140u));
+        }
+      }
+      // V tile consumed: refill
+      fence_proxy_async();
+      __syncwarp();
+      if (tn < t_end && lane == 0) {
+        mbar_expect_tx(bar_v, kTileBytes);
+        tma_load_2d(v_tile, &tm_v, 0, plane_row + nloc.p0, bar_v, kEvictFirst);
+      }
+      phase ^= 1;
+      loc = nloc;
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+
+    // ---- merge the four warps of the item in shared memory (accumulator column 2 tid4 + e of n-block j is head dim 16 tid4 + 8 e + j) ----
+    if (m0 > -INFINITY) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int d0 = 16 * tid4 + j, d1 = d0 + 8;
+        if (gid < G) { sm_o[gid * D + d0] = o[j][0]; sm_o[gid * D + d1] = o[j][1]; }
+        if (gid + 8 < G) { sm_o[(gid + 8) * D + d0] = o[j][2]; sm_o[(gid + 8) * D + d1] = o[j][3]; }
+      }
+    }
+    if (tid4 == 0) {
+      sm_m[warp * 16 + gid] = m0;
+      sm_m[warp * 16 + gid + 8] = m1;
+      sm_l[warp * 16 + gid] = l0;
+      sm_l[warp * 16 + gid + 8] = l1;
+    }
+    epi_bar_sync();
+
+    const long long out_base = (long long)r * p.hq * D + (long long)h * G * D;
+    const long long part_base = ((long long)(r * p.hkv + h) * p.max_chunks + chunk) * G;
+    for (int e = tid; e < G * D; e += kAttnThreads) {
+      const int g = e / D, d = e - g * D;
+      float M = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < kAttnWarps; ++w) M = fmaxf(M, sm_m[w * 16 + g]);
+      float L = 0.0f, O = 0.0f;
+#pragma unroll
+      for (int w = 0; w < kAttnWarps; ++w) {
+        const float mw = sm_m[w * 16 + g];
+        if (mw > -INFINITY) {
+          const float sc = exp2f((mw - M) * kLog2e);
+          L += sm_l[w * 16 + g] * sc;
+          O += sm_o_all[(w * o_rows + g) * D + d] * sc;
+        }
+      }
+      if (n_chunks == 1) {
+        p.out[out_base + e] = __float2bfloat16_rn(p.out_max != nullptr ? O : O / L);
+        if (p.out_max != nullptr && d == 0) {
+          p.out_max[(long long)r * p.hq + h * G + g] = M;
+          p.out_sum[(long long)r * p.hq + h * G + g] = L;
+        }
+      } else {
+        __stcg(p.part_o + (part_base + g) * D + d, O);
+        if (d == 0) {
+          __stcg(p.part_ml + (part_base + g) * 2, M);
+          __stcg(p.part_ml + (part_base + g) * 2 + 1, L);
+        }
+      }
+    }
+    if (n_chunks > 1) {
+      __threadfence();
+      epi_bar_sync();
+      if (tid == 0) {
+        const int old = atomicAdd(p.tickets + r * p.hkv + h, 1);
+        const int last = old == n_chunks - 1;
+        if (last) p.tickets[r * p.hkv + h] = 0;
+        *s_last_p = last;
+      }
+      epi_bar_sync();
+      if (*s_last_p) {
+        __threadfence();
+        const long long pb = (long long)(r * p.hkv + h) * p.max_chunks * G;
+        for (int e = tid; e < G * D; e += kAttnThreads) {
+          const int g = e / D, d = e - g * D;
+          float M = -INFINITY;
+          for (int c = 0; c < n_chunks; ++c) M = fmaxf(M, __ldcg(p.part_ml + (pb + c * G + g) * 2));
+          float L = 0.0f, O = 0.0f;
+          for (int c = 0; c < n_chunks; ++c) {
+            const float sc = exp2f((__ldcg(p.part_ml + (pb + c * G + g) * 2) - M) * kLog2e);
+            L += __ldcg(p.part_ml + (pb + c * G + g) * 2 + 1) * sc;
+            O += __ldcg(p.part_o + (pb + c * G + g) * D + d) * sc;
+          }
+          p.out[out_base + e] = __float2bfloat16_rn(p.out_max != nullptr ? O : O / L);
+          if (p.out_max != nullptr && d == 0) {
+            p.out_max[(long long)r * p.hq + h * G + g] = M;
+            p.out_sum[(long long)r * p.hq + h * G + g] = L;
+          }
+        }
+      }
+    }
+    epi_bar_sync();  // the merge buffer is rewritten by the next item
+  }
+}
+
+
+__global__ void __launch_bounds__(kAttnThreads)
+decode_attn_q8_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnParams p, const float* k_scale,
+                      const float* v_scale) {
+  constexpr int D = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int G = p.hq / p.hkv;
+  const int o_rows = G <= 8 ? 8 : 16;
+  float* sm_o_all = reinterpret_cast<float*>(smem + kAttnWarps * kQ8WarpBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_o_all + kAttnWarps * o_rows * D);
+  float* sm_stat = reinterpret_cast<float*>(bars + 2 * kAttnWarps);
+  const int tl = timeline_begin(4);
+  griddep_launch_dependents();
+  if ((threadIdx.x & 31) == 0) {
+    mbar_init(bars + 2 * (threadIdx.x >> 5), 1);
+    mbar_init(bars + 2 * (threadIdx.x >> 5) + 1, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  __syncthreads();
+  griddep_wait();
+  uint32_t phase = 0;
+  attn_process_items_q8(tm_k, tm_v, p, k_scale, v_scale, smem, sm_o_all, bars, sm_stat, phase, threadIdx.x, blockIdx.x, gridDim.x);
+  timeline_end(tl);
+}
+
+__host__ inline size_t attn_q8_smem_bytes(int G) {
+  const size_t o_rows = G <= 8 ? 8 : 16;
+  return 1024 + size_t(kAttnWarps) * kQ8WarpBytes + kAttnWarps * o_rows * 64 * 4 + 2 * kAttnWarps * 8 + 2 * kAttnWarps * 16 * 4 + 32;
 }
 
 }  // namespace mtx

@@ -91,6 +91,21 @@ int make_map(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, u
   return MTX_OK;
 }
 
+// uint8 matrix [outer, 64] (one int8 cache row of a kv head per matrix row), box [64, 64] with the 64-byte swizzle.
+int make_map_u8(CUtensorMap* m, const void* base, uint64_t outer) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return fail(MTX_ERR_CUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(MTX_ERR_ARG, "TMA needs a 16-byte aligned base");
+  const cuuint64_t dims[2] = {64, outer};
+  const cuuint64_t strides[1] = {64};
+  const cuuint32_t box[2] = {64, 64};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) return fail(MTX_ERR_CUDA, "cuTensorMapEncodeTiled (uint8) failed with CUresult %d", int(rc));
+  return MTX_OK;
+}
+
 // ---- launch helper -------------------------------------------------------------------------
 
 // Optional per-kernel timing: when a sink is installed every launch is bracketed by CUDA
@@ -315,6 +330,7 @@ struct mtx_engine {
   // descriptors
   std::vector<CUtensorMap> tm_wqkv, tm_wo, tm_w01, tm_wout;
   CUtensorMap tm_logits, tm_k, tm_v;
+  CUtensorMap tm_kq, tm_vq;  // kv_quant: the int8 decode cache (tm_k / tm_v then address the bf16 prefill staging plane)
   CUtensorMap tm_all_wqkv, tm_all_wo, tm_all_w01, tm_all_wout;  // all layers stacked: row = layer * N + n
   // persistent step kernel (step_persistent.cuh)
   int pk_ctas = 0;  // CTAs of the persistent grid (0 = unavailable)
@@ -448,6 +464,13 @@ int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st) {
   int grid = rows * c.num_kv_heads * attn_max_chunks(c.max_prefill_len, c.max_target_len, p.tiles_per_item);
   const int cap = e->num_sms * ctas_per_sm;
   if (grid > cap) grid = cap;
+  if (c.kv_quant) {
+    const size_t smem_q = attn_q8_smem_bytes(c.num_q_heads / c.num_kv_heads);
+    int grid_q = rows * c.num_kv_heads * attn_max_chunks(c.max_prefill_len, c.max_target_len, p.tiles_per_item);
+    if (grid_q > e->num_sms * 4) grid_q = e->num_sms * 4;
+    return launch(decode_attn_q8_kernel, dim3(grid_q), dim3(kAttnThreads), smem_q, st, e->tm_kq, e->tm_vq, p, (const float*)e->s.k_scale,
+                  (const float*)e->s.v_scale);
+  }
   if (c.head_dim == 64) return launch(decode_attn_kernel<64>, dim3(grid), dim3(kAttnThreads), smem, st, e->tm_k, e->tm_v, p);
   return launch(decode_attn_kernel<128>, dim3(grid), dim3(kAttnThreads), smem, st, e->tm_k, e->tm_v, p);
 }
@@ -461,6 +484,7 @@ bool use_prefill_attention(const mtx_engine* e) {
 
 int launch_prefill_attention(mtx_engine* e, int layer, int rows, int start_pos, int slot, cudaStream_t st) {
   const mtx_model_config& c = e->cfg;
+  const int planes = c.kv_quant ? 1 : c.num_slots;  // an int8 engine prefills into its single bf16 staging plane
   PrefillAttnParams p;
   memset(&p, 0, sizeof(p));
   p.q = e->q;
@@ -470,7 +494,7 @@ int launch_prefill_attention(mtx_engine* e, int layer, int rows, int start_pos, 
   p.hq = c.num_q_heads;
   p.hkv = c.num_kv_heads;
   p.T = c.max_target_len;
-  p.plane_row0 = (layer * c.num_slots + slot) * c.num_kv_heads * c.max_target_len;
+  p.plane_row0 = (layer * planes + slot) * c.num_kv_heads * c.max_target_len;
   p.softcap = c.attn_softcap;
   const dim3 grid(c.num_q_heads, (rows + kPfQRows - 1) / kPfQRows), block(kPfWarps * 32);
   const size_t smem = prefill_attn_smem_bytes(c.head_dim);
@@ -616,7 +640,7 @@ bool pk_fill_phase(std::vector<PkTable>& tabs, int ph, int n, int k, bool allow_
 int pk_trace_bars(int layers) { return 2 + 5 * layers + 2 > 200 ? 2 + 5 * layers + 2 : 200; }
 
 bool pk_usable(const mtx_engine* e, int rows) {
-  if (e->pk_ctas <= 0 || round_rows(rows) > kPkMaxRTile) return false;
+  if (e->pk_ctas <= 0 || round_rows(rows) > kPkMaxRTile || e->cfg.kv_quant) return false;
   if (e->cfg.num_q_heads / e->cfg.num_kv_heads > 8) return false;  // the attention MMA carries the group's heads in its 8 columns
   // an attention warp's tile list holds kPkAttnListMax entries: bound the worst case (every context full)
   const mtx_model_config& c = e->cfg;
@@ -697,11 +721,17 @@ int prefill_noise_row(const mtx_engine* e) { return 0x40000000 + int(e->prefill_
 int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens, int start_pos, int slot, int want_logits,
                  int32_t* first_token, float* prefill_logits, cudaStream_t st, float* cand_out = nullptr, float* first_log_prob = nullptr) {
   const mtx_model_config& c = e->cfg;
-  const int r_tile = round_rows(rows);
+  // (an int8 cache is appended to by the row-major GEMM's epilogue only: steps of any size run it, padded to 128 rows)
+  const int r_tile = c.kv_quant && round_rows(rows) < 128 ? 128 : round_rows(rows);
   XMaps* xm;
   MTX_TRY(get_xmaps(e, r_tile, &xm));
+  // prefill (mode 1) of an int8 engine writes the ONE bf16 staging plane that k_cache / v_cache then are
+  const int planes = (c.kv_quant && mode == 1) ? 1 : c.num_slots;
+  if (c.kv_quant && mode == 1) slot = 0;
   const int E = c.emb_dim, HD = c.num_q_heads * c.head_dim, M = c.mlp_dim, L = c.num_layers;
-  const size_t kv_layer = size_t(c.num_slots) * c.num_kv_heads * c.max_target_len * c.head_dim;
+  const size_t kv_layer = size_t(planes) * c.num_kv_heads * c.max_target_len * c.head_dim;
+  const size_t kvq_layer = size_t(c.num_slots) * c.num_kv_heads * c.max_target_len * c.head_dim;  // bytes of one layer of the int8 cache
+  const size_t kvs_layer = size_t(c.num_slots) * c.num_kv_heads * c.max_target_len;                // its scales
 
   PrepareArgs pa;
   memset(&pa, 0, sizeof(pa));
@@ -741,7 +771,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   gp.rows = rows;
   gp.r_tile = r_tile;
   const GemmPlan plan_logits = plan_gemm(c.vocab_size, c.emb_dim, r_tile, e->num_sms, EPI_LOGITS, 1);
-  const bool rows_k = use_rows_kernel(r_tile);  // 65..256 rows: the row-major tensor-core GEMM (gemm_rows.cuh)
+  const bool rows_k = c.kv_quant ? true : use_rows_kernel(r_tile);  // 65..256 rows: the row-major tensor-core GEMM (gemm_rows.cuh)
   XMaps* xm128 = xm;  // split-K units of that kernel load 128-row activation boxes
   if (rows_k) MTX_TRY(get_xmaps(e, 128, &xm128));
   auto xmap = [&](const RowsPlan& pl, CUtensorMap XMaps::*m) -> const CUtensorMap& { return pl.splits > 1 ? xm128->*m : xm->*m; };
@@ -785,6 +815,12 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     ea.hkv = c.num_kv_heads;
     ea.d = c.head_dim;
     ea.t_alloc = c.max_target_len;
+    if (c.kv_quant && mode == 0) {
+      ea.kq_cache = static_cast<uint8_t*>(e->s.kq_cache) + kvq_layer * l;
+      ea.vq_cache = static_cast<uint8_t*>(e->s.vq_cache) + kvq_layer * l;
+      ea.k_scale = e->s.k_scale + kvs_layer * l;
+      ea.v_scale = e->s.v_scale + kvs_layer * l;
+    }
     gp.n = e->qkv_n;
     gp.k = E;
     g_class = KC_QKV;
@@ -796,7 +832,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     else MTX_TRY(launch_gemm<EPI_QKV_ROPE>(e->tm_wqkv[l], xm->n, gp, ea, plan_qkv, st));
 
     g_class = KC_ATTENTION;
-    if (mode == 1 && use_prefill_attention(e)) MTX_TRY(launch_prefill_attention(e, l, rows, start_pos, slot, st));
+    if (mode == 1 && (use_prefill_attention(e) || c.kv_quant)) MTX_TRY(launch_prefill_attention(e, l, rows, start_pos, slot, st));
     else MTX_TRY(launch_attention(e, l, rows, st));
 
     memset(&ea, 0, sizeof(ea));
@@ -1000,7 +1036,10 @@ int mtx_engine_create(const mtx_model_config* cfg, mtx_engine** out) {
   if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
     e->num_sms = sms;
   cudaGetLastError();
+  if (c.kv_quant != 0 && c.kv_quant != 1) return fail(MTX_ERR_ARG, "kv_quant must be 0 (bf16) or 1 (int8 per token and kv head)");
+  if (c.kv_quant && c.head_dim != 64) return fail(MTX_ERR_UNSUPPORTED, "the int8 KV cache is implemented for head_dim 64");
   e->max_r_tile = round_rows(c.max_rows);
+  if (c.kv_quant && e->max_r_tile < 128) e->max_r_tile = 128;  // every step of an int8 engine runs the 128-row-block GEMM
   e->qkv_n = (c.num_q_heads + 2 * c.num_kv_heads) * c.head_dim;
   e->attn_max_chunks = attn_max_chunks(c.max_prefill_len, c.max_target_len);
   e->rope_timescale_host.resize(c.head_dim / 2);
@@ -1132,8 +1171,18 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   }
   const uint64_t kv_rows = uint64_t(L_) * c.num_slots * c.num_kv_heads * c.max_target_len;
   if (kv_rows >= (1ull << 31)) return fail(MTX_ERR_UNSUPPORTED, "KV cache has too many rows for one tensor map");
+  if (c.kv_quant) {
+    if (!s->kq_cache || !s->vq_cache || !s->k_scale || !s->v_scale) return fail(MTX_ERR_ARG, "kv_quant: kq_cache / vq_cache / k_scale / v_scale must be set");
+    const uint64_t stage_rows = uint64_t(L_) * c.num_kv_heads * c.max_target_len;  // one bf16 plane per layer
+    MTX_TRY(make_map(&e->tm_k, s->k_cache, c.head_dim, stage_rows, kAttnTileRows));
+    MTX_TRY(make_map(&e->tm_v, s->v_cache, c.head_dim, stage_rows, kAttnTileRows));
+    MTX_TRY(make_map_u8(&e->tm_kq, s->kq_cache, kv_rows));
+    MTX_TRY(make_map_u8(&e->tm_vq, s->vq_cache, kv_rows));
+    MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_q8_smem_bytes(16))));
+  } else {
   MTX_TRY(make_map(&e->tm_k, s->k_cache, c.head_dim, kv_rows, kAttnTileRows));
   MTX_TRY(make_map(&e->tm_v, s->v_cache, c.head_dim, kv_rows, kAttnTileRows));
+  }
   if (c.head_dim == 64)
     MTX_CUDA(cudaFuncSetAttribute(decode_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_smem_bytes(64, 16))));
   else
@@ -1387,6 +1436,18 @@ int mtx_insert_prefix(mtx_engine* e, const void* k_src, const void* v_src, int n
   a.next_pos_out = e->s.next_pos;
   a.generated_out = e->s.generated;
   a.tokens_out = e->s.tokens;
+  if (c.kv_quant) {
+    InsertQ8Args q;
+    q.base = a;
+    q.kq_cache = static_cast<uint8_t*>(e->s.kq_cache);
+    q.vq_cache = static_cast<uint8_t*>(e->s.vq_cache);
+    q.k_scale = e->s.k_scale;
+    q.v_scale = e->s.v_scale;
+    const long long warps = (long long)c.num_layers * c.num_kv_heads * n_rows * 2;
+    int grid_q = int((warps + 7) / 8);
+    if (grid_q > e->num_sms * 8) grid_q = e->num_sms * 8;
+    return launch(insert_prefix_q8_kernel, dim3(grid_q), dim3(256), 0, static_cast<cudaStream_t>(stream), q);
+  }
   const long long vecs = (long long)c.num_layers * c.num_kv_heads * n_rows * (c.head_dim / 8);
   int grid = int((vecs + 255) / 256);
   if (grid > e->num_sms * 8) grid = e->num_sms * 8;
@@ -1669,6 +1730,7 @@ int mtx_engine_rebind_state(mtx_engine* e, const mtx_decode_state* s) {
   e->s = *s;
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   e->graphs.clear();
+  if (c.kv_quant) return fail(MTX_ERR_UNSUPPORTED, "mtx_engine_rebind_state with an int8 KV cache: bind again instead");
   if (kv_moved) {
     const uint64_t kv_rows = uint64_t(c.num_layers) * c.num_slots * c.num_kv_heads * c.max_target_len;
     MTX_TRY(make_map(&e->tm_k, s->k_cache, c.head_dim, kv_rows, kAttnTileRows));

@@ -191,6 +191,63 @@ __device__ __forceinline__ void rows_epi_qkv(const EpiArgs& e, int N, int r, int
   }
 }
 
+// One head (64 dims) of one row for the int8 cache: RoPE (key heads), then KVQuant.quantize over the head's dims.
+// x0 = dims 0..15, x1 = 16..31 (first half), y0 = 32..47, y1 = 48..63 (second half), accumulator values.
+__device__ __forceinline__ void rows_epi_qkv_q8(const EpiArgs& e, int N, int r, int head, float (&x0)[16], float (&x1)[16], float (&y0)[16], float (&y1)[16]) {
+  if (head * 64 >= N) return;
+  const bool is_q = head < e.hq, is_k = !is_q && head < e.hq + e.hkv;
+  if (is_q) {  // queries are not cached: the bf16 path
+    rows_epi_qkv(e, N, r, head, 0, x0, y0);
+    rows_epi_qkv(e, N, r, head, 16, x1, y1);
+    return;
+  }
+  float* part[4] = {x0, x1, y0, y1};
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) part[q][j] = bf16r(part[q][j]);
+  if (is_k) {
+    const float2* cs = e.rope_cs + (long long)r * 32;
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float2 c = cs[16 * q + j];
+        const float a = part[q][j], b = part[q + 2][j];
+        part[q][j] = bf16r(bf16r(a * c.x) - bf16r(b * c.y));      // the cached key is a bf16 array (embeddings.py:304-315)
+        part[q + 2][j] = bf16r(bf16r(b * c.x) + bf16r(a * c.y));
+      }
+  }
+  const int wr = e.write_row[r];
+  if (wr < 0) return;
+  float mx = 0.0f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) mx = fmaxf(mx, fabsf(part[q][j]));
+  const float inv = mx > 0.0f ? 127.5f / mx : 0.0f;
+  const int kvh = is_k ? head - e.hq : head - e.hq - e.hkv;
+  const long long row = ((long long)e.plane[r] * e.hkv + kvh) * e.t_alloc + wr;
+  uint8_t* dst = (is_k ? e.kq_cache : e.vq_cache) + row * 64;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint32_t pk = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        float v = rintf(part[q][4 * i + b] * inv);
+        v = fminf(fmaxf(v, -128.0f), 127.0f);
+        pk |= uint32_t(int(v) + 128) << (8 * b);
+      }
+      w[i] = pk;
+    }
+    *reinterpret_cast<uint4*>(dst + 16 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  (is_k ? e.k_scale : e.v_scale)[row] = mx;
+}
+
 // Running sampling partials of one row over the columns of one weight tile (decoders.py:537-589 transform, then
 // inference_utils.py:55-84): best (optionally Gumbel-perturbed) score with the lowest index on ties, its raw logit,
 // and the (max, sum exp) pair.
@@ -379,6 +436,21 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         }
       } else if (EPI == EPI_QKV_ROPE) {
         const int D = e.d, half = D >> 1;
+        if (e.kq_cache != nullptr) {  // int8 cache (head_dim 64): a whole head per step, so that its scale is one thread's business
+          for (int c = c_begin; c < c_end; c += 64) {
+            float x0[16], x1[16], y0[16], y1[16];
+            ld16(c, x0);
+            ld16(c + 16, x1);
+            ld16(c + 32, y0);
+            ld16(c + 48, y1);
+            rows_scale16(x0, rs);
+            rows_scale16(x1, rs);
+            rows_scale16(y0, rs);
+            rows_scale16(y1, rs);
+            if (valid) rows_epi_qkv_q8(e, p.n, row, (nbase + c) / 64, x0, x1, y0, y1);
+          }
+          return;
+        }
         for (int c = c_begin; c < c_end; c += 16) {
           const int d = (nbase + c) % D;
           if (d >= half) continue;  // second halves are produced together with their first halves
@@ -481,6 +553,21 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       griddep_wait();
       // epilogue: thread -> (row of the slice, 16-column chunk); RoPE / SwiGLU partners are read from the same row
       const int tile = first_tile;
+      if (EPI == EPI_QKV_ROPE && e.kq_cache != nullptr) {  // int8 cache: thread -> (row of the slice, one of the tile's two heads)
+        for (int u = epi_tid; u < rpc * 2; u += kRowsEpiWarps * 32) {
+          const int rr = u >> 1, c0 = (u & 1) * 64;
+          const int row = row_base + r_begin + rr;
+          if (row >= p.rows) continue;
+          const float* src = reduced + rr * kRowsPitch + c0;
+          const float rs = rows_rstd(e, row);
+          float x[4][16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[q][j] = src[16 * q + j] * rs;
+          rows_epi_qkv_q8(e, p.n, row, (tile * kTileN + c0) / 64, x[0], x[1], x[2], x[3]);
+        }
+      } else
       for (int u = epi_tid; u < rpc * 8; u += kRowsEpiWarps * 32) {
         const int rr = u >> 3, c0 = (u & 7) * 16;
         const int row = row_base + r_begin + rr;

@@ -264,6 +264,50 @@ __global__ void __launch_bounds__(256) insert_prefix_kernel(const InsertArgs a) 
   }
 }
 
+// The same insert into an int8 decode cache (mtx_model_config.kv_quant): one warp per (layer, kv head, row) quantises the 64 dims
+// of the bf16 prefix row (KVQuant.quantize, kvcache.py:76-90: scale = max|x|, q = rint(x * 127.5 / scale) clipped to int8).
+struct InsertQ8Args {
+  InsertArgs base;
+  uint8_t* kq_cache;
+  uint8_t* vq_cache;
+  float* k_scale;
+  float* v_scale;
+};
+__global__ void __launch_bounds__(256) insert_prefix_q8_kernel(const InsertQ8Args q) {
+  const InsertArgs& a = q.base;
+  griddep_launch_dependents();
+  griddep_wait();
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long total = (long long)a.L * a.hkv * a.n * 2;  // K and V rows
+  for (long long i = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); i < total; i += warps) {
+    const int which = int(i & 1);
+    const long long j = i >> 1;
+    const int row = int(j % a.n);
+    const long long lh = j / a.n;
+    const int l = int(lh / a.hkv), h = int(lh - (long long)l * a.hkv);
+    const bf16* src = (which ? a.v_src : a.k_src) + ((long long)(l * a.hkv + h) * a.n_src + row) * 64;
+    const uint32_t pk = *reinterpret_cast<const uint32_t*>(src + 2 * lane);
+    const float x0 = bf16_lo(pk), x1 = bf16_hi(pk);
+    float mx = fmaxf(fabsf(x0), fabsf(x1));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float inv = mx > 0.0f ? 127.5f / mx : 0.0f;
+    const int q0 = int(fminf(fmaxf(rintf(x0 * inv), -128.0f), 127.0f)) + 128, q1 = int(fminf(fmaxf(rintf(x1 * inv), -128.0f), 127.0f)) + 128;
+    const long long drow = ((long long)(l * a.planes + a.slot) * a.hkv + h) * a.T + row;
+    uint8_t* dst = (which ? q.vq_cache : q.kq_cache) + drow * 64;
+    *reinterpret_cast<uint16_t*>(dst + 2 * lane) = uint16_t(q0 | (q1 << 8));
+    if (lane == 0) (which ? q.v_scale : q.k_scale)[drow] = mx;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.prefill_len[a.slot] = a.n;
+    a.ar_lengths[a.slot] = 0;
+    a.next_pos_out[a.slot] = a.next_pos;
+    a.generated_out[a.slot] = a.generated;
+    a.tokens_out[a.slot] = a.token;
+  }
+}
+
 struct FinalizeArgs {
   const float* part_score;  // [rows, n_tiles]
   const int* part_idx;

@@ -239,6 +239,8 @@ class MaxEngine:
     self._chunk = max(1, min(256, int(config.prefill_chunk_size), config.max_prefill_predict_length))
     self._staging = B  # extra KV plane prefill writes into
     self._num_slots = B + 1
+    if config.quantize_kvcache:  # the int8 cache holds the decode slots only; prefill has its own bf16 plane (index 0)
+      self._staging, self._num_slots = 0, B
     self._vp_world, self._vp_rank, self._gather = 1, 0, gather
     if vocab_shard is not None:
       self._vp_rank, self._vp_world = int(vocab_shard[0]), int(vocab_shard[1])
@@ -278,6 +280,7 @@ class MaxEngine:
         logits_scale=scale,
         logits_round_bf16=0 if config.logits_dot_in_fp32 else 1,
         embedding_rows=config.vocab_size,
+        kv_quant=1 if config.quantize_kvcache else 0,
         norm_scales_folded=1 if config.fold_norm_scales else 0,
     )
     _lib.check(self.lib.mtx_engine_create(ctypes.byref(self._cfg_struct), ctypes.byref(self._handle)))
@@ -325,8 +328,20 @@ class MaxEngine:
     L, Hkv, T, D = cfg.num_decoder_layers, cfg.num_kv_heads, cfg.max_target_length, cfg.head_dim
     i32 = torch.int32
     z = lambda *shape, dtype=i32: torch.zeros(*shape, dtype=dtype, device=dev)
-    self._k = z(L, S, Hkv, T, D, dtype=torch.bfloat16)
-    self._v = z(L, S, Hkv, T, D, dtype=torch.bfloat16)
+    self._kv_quant = bool(cfg.quantize_kvcache)
+    if self._kv_quant:
+      # int8 decode cache (u = q + 128) + one fp32 scale per (layer, slot, kv head, row); prefill writes ONE bf16 staging plane
+      self._kq = torch.full((L, S, Hkv, T, D), 128, dtype=torch.uint8, device=dev)
+      self._vq = torch.full((L, S, Hkv, T, D), 128, dtype=torch.uint8, device=dev)
+      self._k_scale = z(L, S, Hkv, T, dtype=torch.float32)
+      self._v_scale = z(L, S, Hkv, T, dtype=torch.float32)
+      self._k = z(L, 1, Hkv, T, D, dtype=torch.bfloat16)
+      self._v = z(L, 1, Hkv, T, D, dtype=torch.bfloat16)
+      self._staging = 0
+    else:
+      self._kq = self._vq = self._k_scale = self._v_scale = None
+      self._k = z(L, S, Hkv, T, D, dtype=torch.bfloat16)
+      self._v = z(L, S, Hkv, T, D, dtype=torch.bfloat16)
     self._tokens, self._next_pos, self._generated = z(B, 1), z(B, 1), z(B, 1)
     self._prefill_len, self._ar_lengths, self._ar_index = z(S), z(S), z(1)
     self._result = z(B, 3)
@@ -354,6 +369,10 @@ class MaxEngine:
         log_prob=self._log_prob.data_ptr() if self._log_prob is not None else None,
         logits=self._logits.data_ptr() if self._logits is not None else None,
         rng_state=self._rng_state.data_ptr(),
+        kq_cache=self._kq.data_ptr() if self._kq is not None else None,
+        vq_cache=self._vq.data_ptr() if self._vq is not None else None,
+        k_scale=self._k_scale.data_ptr() if self._k_scale is not None else None,
+        v_scale=self._v_scale.data_ptr() if self._v_scale is not None else None,
     )
 
   def _apply_sampling(self) -> None:
@@ -425,14 +444,23 @@ class MaxEngine:
               self._ar_index, self._result):
       t.zero_()
     self._rng_state[0:1].zero_()
+    if self._kv_quant:
+      self._kq.fill_(128)
+      self._vq.fill_(128)
+      self._k_scale.zero_()
+      self._v_scale.zero_()
     if self._logits is not None:
       self._logits.zero_()
     self._seed(rng)
     self._state = {
         "logits": self._logits,
         "cache": {
-            "key": self._k,  # [L, slots, Hkv, T, D]: rows [0,P) = cached_prefill_key, [P,T) = cached_ar_key
-            "value": self._v,
+            # [L, slots, Hkv, T, D]: rows [0,P) = cached_prefill_key, [P,T) = cached_ar_key (uint8 q + 128 with "key_scale" /
+            # "value_scale" [L, slots, Hkv, T] when quantize_kvcache: KVTensor's qvalue / scale, kvcache.py:658-736)
+            "key": self._kq if self._kv_quant else self._k,
+            "value": self._vq if self._kv_quant else self._v,
+            "key_scale": self._k_scale,
+            "value_scale": self._v_scale,
             "prefill_length": self._prefill_len,  # == cache_prefill_segment_id.sum(-1)
             "cached_ar_lengths": self._ar_lengths,
             "cache_ar_index": self._ar_index,
@@ -612,7 +640,18 @@ class MaxEngine:
     P, R = cfg.max_prefill_predict_length, cfg.max_target_length - cfg.max_prefill_predict_length
     state = self.init_decode_state()
     g = torch.Generator(device=self.device).manual_seed(seed)
-    for buf in (self._k, self._v):
+    if self._kv_quant:
+      # random int8 rows that are consistent with KVQuant.quantize: every row holds a +-127 (its max) and has scale ~ |N(0,1)| + 2
+      for buf in (self._kq, self._vq):
+        flat = buf.view(-1)
+        step = 1 << 26
+        for lo in range(0, flat.numel(), step):
+          n = min(step, flat.numel() - lo)
+          flat[lo : lo + n] = torch.randint(1, 256, (n,), device=self.device, generator=g, dtype=torch.int32).to(torch.uint8)
+        buf[..., 0] = 255  # q = 127: the row's largest magnitude
+      for sc in (self._k_scale, self._v_scale):
+        sc.copy_(torch.randn(sc.shape, device=self.device, generator=g).abs() + 2.0)
+    for buf in (() if self._kv_quant else (self._k, self._v)):
       flat = buf.view(-1)
       step = 1 << 26
       for lo in range(0, flat.numel(), step):

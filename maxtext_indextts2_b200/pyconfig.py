@@ -108,7 +108,15 @@ def _validate(keys: dict) -> None:
   if keys["decode_sampling_strategy"] not in _VALID_SAMPLING:
     raise ValueError(f"Sampling algorithm={keys['decode_sampling_strategy']!r} not supported!")
   if keys["quantize_kvcache"]:
-    raise ValueError("quantize_kvcache=True is outside this decode path (bf16 KV only)")
+    # inference/kvcache.py:36-90.  Implemented: int8 with one scale per (token, kv head), i.e. kv_quant_axis "dkv" -- the
+    # reference's default "heads_and_dkv" shares one scale between the kv heads of a token, which the fused QKV epilogue
+    # (one head per thread) does not produce; "dkv" is the variant base.yml:108-110 describes as the more accurate one.
+    if keys["kv_quant_dtype"] != "int8":
+      raise ValueError(f"Invalid kv_quant_dtype: {keys['kv_quant_dtype']} (this decode path implements int8)")
+    if keys["kv_quant_axis"] != "dkv":
+      raise ValueError(f"kv_quant_axis={keys['kv_quant_axis']!r}: this decode path implements kv_quant_axis=dkv (one scale per token and kv head)")
+    if keys["head_dim"] != 64:
+      raise ValueError("quantize_kvcache is implemented for head_dim=64")
   if keys["quantization"] not in ("", None):
     raise ValueError("quantization must be '' on this decode path (bf16 weights only)")
   if keys["decoder_block"] != "llama2":

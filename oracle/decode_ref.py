@@ -120,6 +120,16 @@ class DecodeOracle:
     self.scores_f32 = bool(config.float32_qk_product) or not faithful
     self.softmax_f32 = self.scores_f32 or bool(config.float32_logits)
 
+  def kv_quant(self, x):
+    """KVQuant.quantize + dequantisation (inference/kvcache.py:76-90, int8, kv_quant_axis "dkv": one scale per token and kv
+    head): scale = max|x| over the head's dims, q = int8(rint(x * 127.5 / scale)) (the conversion saturates: the row's maximum
+    maps to rint(127.5) = 128 -> 127), cached value = q * scale / 127.5.  Identity unless quantize_kvcache."""
+    if not getattr(self.cfg, "quantize_kvcache", False):
+      return x
+    scale = x.abs().amax(dim=-1, keepdim=True)
+    q = torch.where(scale > 0, torch.clamp(torch.round(x * (127.5 / scale.clamp(min=1e-30))), -128.0, 127.0), torch.zeros_like(x))
+    return q * (scale / 127.5)
+
   # -- small ops ---------------------------------------------------------------
 
   def r(self, x):
@@ -313,8 +323,9 @@ class DecodeOracle:
     """maxengine.py:1045-1164: AR data and the shared ring index are left untouched."""
     c, pc = state["cache"], prefix["cache"]
     for l in range(self.cfg.num_decoder_layers):
-      c["prefill_key"][l][slot] = pc["prefill_key"][l][0]
-      c["prefill_value"][l][slot] = pc["prefill_value"][l][0]
+      # (kv_cache_prefill stores the quantised prefill keys / values, kvcache.py:610-617; what is inserted is that cache)
+      c["prefill_key"][l][slot] = self.kv_quant(pc["prefill_key"][l][0])
+      c["prefill_value"][l][slot] = self.kv_quant(pc["prefill_value"][l][0])
     c["prefill_segment_id"][slot] = pc["prefill_segment_id"][0]
     c["ar_segment_id"][slot] = 0
     c["ar_lengths"][slot] = 0
@@ -339,8 +350,8 @@ class DecodeOracle:
     for l, lw in enumerate(self.w.layers):
       n = self.rms_norm(x, lw["attn_scale"])
       q, k, v = self._qkv(lw, n, pos)
-      c["ar_key"][l][:, idx] = k[:, 0]  # kvcache.py:696-701
-      c["ar_value"][l][:, idx] = v[:, 0]
+      c["ar_key"][l][:, idx] = self.kv_quant(k[:, 0])  # kvcache.py:696-701 (quantised when quantize_kvcache: :658-718)
+      c["ar_value"][l][:, idx] = self.kv_quant(v[:, 0])
       o_p, m_p, l_p = self._local_attention(q, c["prefill_key"][l], c["prefill_value"][l], pmask)
       o_a, m_a, l_a = self._local_attention(q, c["ar_key"][l], c["ar_value"][l], amask)
       a = self._normalize_attention([o_p, o_a], [m_p, m_a], [l_p, l_a])

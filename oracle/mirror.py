@@ -55,6 +55,7 @@ def make_oracle(cfg, weights: ref.OracleWeights, slots: int, faithful: bool = Tr
   o.cfg, o.faithful, o.w = ocfg, faithful, weights
   o.B, o.P, o.T = slots, cfg.max_prefill_predict_length, cfg.max_target_length
   o.R = o.T - o.P
+  # (cfg carries quantize_kvcache: DecodeOracle.kv_quant follows it)
   o.scores_f32 = bool(cfg.float32_qk_product) or not faithful
   o.softmax_f32 = o.scores_f32 or bool(cfg.float32_logits)
   return o
@@ -73,9 +74,16 @@ def mirror_state(engine, oracle: ref.DecodeOracle, slots) -> dict:
   state = oracle.init_decode_state()
   c = state["cache"]
   sl = torch.as_tensor(slots, device=engine._k.device)
+  quant = bool(getattr(engine, "_kv_quant", False))
   for l in range(L):
-    k = engine._k[l].index_select(0, sl).to("cpu").to(torch.float32)  # [n, Hkv, T, D]
-    v = engine._v[l].index_select(0, sl).to("cpu").to(torch.float32)
+    if quant:  # int8 cache: the oracle holds the dequantised values q * scale / 127.5 (kvcache.py:76-90)
+      ks = engine._k_scale[l].index_select(0, sl).to("cpu")[..., None]
+      vs = engine._v_scale[l].index_select(0, sl).to("cpu")[..., None]
+      k = (engine._kq[l].index_select(0, sl).to("cpu").to(torch.float32) - 128.0) * (ks / 127.5)
+      v = (engine._vq[l].index_select(0, sl).to("cpu").to(torch.float32) - 128.0) * (vs / 127.5)
+    else:
+      k = engine._k[l].index_select(0, sl).to("cpu").to(torch.float32)  # [n, Hkv, T, D]
+      v = engine._v[l].index_select(0, sl).to("cpu").to(torch.float32)
     c["prefill_key"][l] = k[:, :, :P].permute(0, 2, 1, 3).contiguous()
     c["prefill_value"][l] = v[:, :, :P].permute(0, 2, 1, 3).contiguous()
     c["ar_key"][l] = k[:, :, P:].permute(0, 2, 1, 3).contiguous()

@@ -1,0 +1,94 @@
+"""int8 KV cache (MaxText/inference/kvcache.py:36-90, 658-736; configs/base.yml:104-112) on the B200 against the
+oracle with the same quantiser: quantize_kvcache=True, kv_quant_dtype=int8, kv_quant_axis=dkv (one scale per token and kv head).
+
+Tolerances: logits vs the quantised dtype-faithful oracle rtol = atol = 1e-1 (the reference's ceiling, as for bf16); cache bytes
+equal to the oracle's quantiser up to one step of the int8 grid on isolated elements (fp32 product order)."""
+
+import numpy as np
+import pytest
+import torch
+
+from maxtext_indextts2_b200 import maxengine, pyconfig
+from oracle import decode_ref as ref
+from oracle import mirror
+from tests.helpers import make_params, random_tokens, small_config
+
+pytestmark = pytest.mark.gpu
+
+QUANT = dict(quantize_kvcache=True, kv_quant_dtype="int8", kv_quant_axis="dkv")
+
+
+def test_config_accepts_only_the_implemented_quantiser():
+  assert pyconfig.initialize(None, head_dim=64, **QUANT).quantize_kvcache
+  with pytest.raises(ValueError, match="kv_quant_axis"):
+    pyconfig.initialize(None, head_dim=64, quantize_kvcache=True)  # the reference default heads_and_dkv
+  with pytest.raises(ValueError, match="kv_quant_dtype"):
+    pyconfig.initialize(None, head_dim=64, quantize_kvcache=True, kv_quant_axis="dkv", kv_quant_dtype="fp8")
+
+
+def test_prefill_insert_and_decode_with_int8_cache_match_the_quantised_oracle():
+  cfg = small_config(per_device_batch_size=3, max_prefill_predict_length=16, max_target_length=28, materialize_logits=True, **QUANT)
+  params = make_params(cfg)
+  oracle = ref.DecodeOracle(cfg, params, faithful=True)
+  engine = maxengine.MaxEngine(cfg, use_cuda_graph=False)
+  dparams = engine.load_params(params)
+  prompts = random_tokens((3, 16), cfg.vocab_size, seed=12)
+  ostate, state = oracle.init_decode_state(), engine.init_decode_state()
+  assert state["cache"]["key"].dtype == torch.uint8 and state["cache"]["key_scale"].dtype == torch.float32
+  for slot, n in enumerate((16, 5, 9)):
+    oprefix, ofirst = oracle.prefill(prompts[slot], n)
+    ostate = oracle.insert(oprefix, ostate, slot)
+    prefix, _ = engine.prefill(params=dparams, padded_tokens=prompts[slot], true_length=n)
+    torch.testing.assert_close(prefix["logits"].cpu()[0], oprefix["logits"][0], rtol=1e-1, atol=1e-1)
+    prefix["tokens"].fill_(int(ofirst))
+    state = engine.insert(prefix, state, slot)
+    # the inserted rows: bytes and scales against the oracle's quantiser applied to the ENGINE's bf16 prefix
+    for name, src in (("key", prefix["cache"]["key"]), ("value", prefix["cache"]["value"])):
+      x = src.float().cpu()  # [L, Hkv, n, D]
+      scale = x.abs().amax(-1)
+      q = torch.clamp(torch.round(x * (127.5 / scale.clamp(min=1e-30))[..., None]), -128, 127)
+      got_q = state["cache"][name][:, slot, :, :n].cpu().to(torch.int32) - 128
+      got_s = state["cache"][name + "_scale"][:, slot, :, :n].cpu()
+      torch.testing.assert_close(got_s, scale, rtol=0, atol=0)
+      d = (got_q - q.to(torch.int32)).abs()
+      assert d.max() <= 1 and (d > 0).float().mean() < 5e-3  # x * (127.5 / scale) lands within an fp32 ulp of a .5 boundary for ~0.1 % of the elements
+  for step in range(16):  # ring of 12 rows: wraps
+    ostate, odata = oracle.generate(ostate)
+    state, result = engine.generate(dparams, state)
+    torch.testing.assert_close(state["logits"].cpu(), ostate["logits"], rtol=1e-1, atol=1e-1)
+    state["tokens"].copy_(odata[:, :1])
+  assert int(state["cache"]["cache_ar_index"].item()) == 4
+
+
+@pytest.mark.parametrize("batch", [5, 64, 200])
+def test_int8_decode_on_a_synthetic_cache_against_the_oracle(batch):
+  """Ragged contexts on a random int8 cache (every step size runs the 128-row-block GEMM: padded to 128 rows, 128, 256), the oracle
+  following a few slots through oracle/mirror.py on the dequantised cache; also the bf16 engine on the dequantised cache for
+  reference: the two CUDA paths must agree far more tightly than either does with the CPU oracle."""
+  cfg = pyconfig.initialize(
+      None, base_num_decoder_layers=3, base_emb_dim=384, base_num_query_heads=10, base_num_kv_heads=2, head_dim=64, base_mlp_dim=768,
+      vocab_size=5000, per_device_batch_size=batch, max_prefill_predict_length=192, max_target_length=448, weight_dtype="bfloat16",
+      attention="dot_product", scan_layers=False, materialize_logits=True, **QUANT)
+  rng = np.random.Generator(np.random.PCG64(batch))
+  pl = rng.integers(1, 193, size=batch)
+  al = rng.integers(0, 240, size=batch)
+  al[pl < 192] = 0
+  pl[0], al[0] = 192, 239
+  engine = maxengine.MaxEngine(cfg, use_cuda_graph=False)
+  dparams = engine.load_params(make_params(cfg))
+  state = engine.fill_synthetic_context(pl, al, seed=3)
+  slots = sorted({0, batch // 2, batch - 1})
+  weights = mirror.oracle_weights_from_device(dparams, cfg)
+  oracle = mirror.make_oracle(cfg, weights, len(slots), faithful=True)
+  ostate = mirror.mirror_state(engine, oracle, slots)
+  sl = torch.as_tensor(slots)
+  for step in range(3):
+    state, result = engine.generate(dparams, state)
+    ostate, odata = oracle.generate(ostate)
+    torch.testing.assert_close(state["logits"].cpu()[sl], ostate["logits"], rtol=1e-1, atol=1e-1)
+    state["tokens"][sl.to(state["tokens"].device)] = odata[:, :1].to(state["tokens"].device)
+  # the appended rows are quantised rows: every row written this run has its scale > 0 and a byte of magnitude 127 or 128
+  idx = int(state["cache"]["cache_ar_index"].item())
+  P = cfg.max_prefill_predict_length
+  last = state["cache"]["key"][:, slots[0], :, P + idx - 1].cpu().to(torch.int32) - 128
+  assert (last.abs().amax(-1) >= 127).all()
