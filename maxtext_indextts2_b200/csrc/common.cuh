@@ -259,4 +259,13 @@ __device__ __noinline__ float gumbel_noise(uint64_t seed, uint32_t step, uint32_
   return -logf(-logf(u));
 }
 
+// The noise of four consecutive vocabulary ids v .. v+3 with v a multiple of 4: ONE Philox block (the same values as four
+// gumbel_noise calls, a quarter of the work).
+__device__ __forceinline__ float4 gumbel_noise4(uint64_t seed, uint32_t step, uint32_t row, uint32_t v) {
+  const uint4 w = philox4x32_10(make_uint4(v >> 2, row, step, 0u), make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+  const float s = 1.1920928955078125e-07f;  // 2^-23
+  return make_float4(-logf(-logf((float(w.x >> 9) + 0.5f) * s)), -logf(-logf((float(w.y >> 9) + 0.5f) * s)),
+                     -logf(-logf((float(w.z >> 9) + 0.5f) * s)), -logf(-logf((float(w.w >> 9) + 0.5f) * s)));
+}
+
 }  // namespace mtx

@@ -338,6 +338,12 @@ struct mtx_engine {
   PkTable* pk_tables = nullptr;
   float *pk_part_ws = nullptr, *pk_ss_x = nullptr, *pk_ss_h = nullptr, *pk_attn_part_o = nullptr;
   int* cand_counters = nullptr;  // [0] nucleus rows truncated to the candidates, [1] commit ticket
+  // all-SM top-k / nucleus sampler (sampling.cuh, par_*): per-row state and the per-slice histograms
+  float *par_M = nullptr, *par_Z = nullptr;
+  unsigned long long *par_target = nullptr, *par_above = nullptr, *par_hist = nullptr;
+  uint32_t* par_prefix = nullptr;
+  int* par_found = nullptr;
+  int* par_eq = nullptr;
   float *rows_ss_x = nullptr, *rows_ss_h = nullptr;  // gemm_rows.cuh fused RMSNorm statistics: [E/128 rounded up][max_r_tile]
   int *pk_tile_prefix = nullptr, *pk_attn_info = nullptr;
   XMaps xmaps[5];
@@ -359,6 +365,7 @@ struct WsLayout {
   size_t part_score, part_idx, part_raw, part_max, part_sum, grid_bar;
   size_t pk_tables, pk_part_ws, pk_ss_x, pk_ss_h, pk_attn_part_o, pk_tile_prefix, pk_attn_info;
   size_t rows_ss_x, rows_ss_h, cand_counters;
+  size_t par_M, par_Z, par_target, par_above, par_prefix, par_found, par_hist, par_eq;
   size_t total;
 };
 
@@ -393,7 +400,8 @@ WsLayout layout_workspace(const mtx_engine* e) {
   L.work_items = take(size_t(c.max_rows) * e->attn_max_chunks * 4);
   L.work_count = take(4);
   L.rope_timescale = take((c.head_dim / 2) * 4);
-  const size_t vt = (c.vocab_size + kTileN - 1) / kTileN;
+  size_t vt = (c.vocab_size + kTileN - 1) / kTileN;
+  if (vt < size_t(par_slices(c.vocab_size)) * kParWarps) vt = size_t(par_slices(c.vocab_size)) * kParWarps;  // par_scan_kernel's pieces
   L.part_score = take(size_t(c.max_rows) * vt * 4);
   L.part_idx = take(size_t(c.max_rows) * vt * 4);
   L.part_raw = take(size_t(c.max_rows) * vt * 4);
@@ -414,6 +422,14 @@ WsLayout layout_workspace(const mtx_engine* e) {
     L.rows_ss_x = take(rt * ss_tiles * 4);
     L.rows_ss_h = take(rt * ss_tiles * 4);
     L.cand_counters = take(64);
+    L.par_M = take(size_t(c.max_rows) * 4);
+    L.par_Z = take(size_t(c.max_rows) * 4);
+    L.par_target = take(size_t(c.max_rows) * 8);
+    L.par_above = take(size_t(c.max_rows) * 8);
+    L.par_prefix = take(size_t(c.max_rows) * 4);
+    L.par_found = take(size_t(c.max_rows) * 4);
+    L.par_hist = take(size_t(c.max_rows) * kParBins * 8);
+    L.par_eq = take(size_t(kParMaxSlices) * kParWarps * c.max_rows * 4);
   }
   L.total = off;
   return L;
@@ -912,7 +928,9 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     ea.round_bf16 = c.logits_round_bf16;
     ea.gumbel = e->strategy == MTX_SAMPLE_WEIGHTED ? 1 : 0;
     float* lp_out = mode == 0 ? e->s.log_prob : first_log_prob;
-    ea.want_lse = ((lp_out != nullptr || cand_out != nullptr) && !two_pass) ? 1 : 0;
+    // decode steps with top-k / nucleus run the all-SM sampler, which starts from the per-tile (max, sum exp) partials
+    const bool par_sampler = two_pass && mode == 0 && cand_out == nullptr && env_int("MTX_PAR_SAMPLER", 1) != 0;
+    ea.want_lse = (((lp_out != nullptr || cand_out != nullptr) && !two_pass) || par_sampler) ? 1 : 0;
     ea.rng_state = e->s.rng_state;
     ea.row_offset = mode == 0 ? 0 : prefill_noise_row(e);
     gp.n = c.vocab_size;
@@ -953,7 +971,50 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
       ta.cand = cand_out;
       return launch(shard_topk_kernel, dim3(rows), dim3(kSampleThreads), 0, st, ta);
     }
-    if (two_pass) {
+    if (par_sampler) {
+      // inference_utils.py:87-111 on the logits the GEMM just wrote, cut along the vocabulary over all SMs (sampling.cuh, par_*)
+      ParSampleArgs ps;
+      memset(&ps, 0, sizeof(ps));
+      ps.logits = e->s.logits;
+      ps.ld = c.vocab_size;
+      ps.vocab = c.vocab_size;
+      ps.vocab_offset = c.vocab_offset;
+      ps.rows = rows;
+      ps.mode = e->strategy;
+      ps.top_k = e->top_k;
+      ps.nucleus_p = e->nucleus_p;
+      ps.inv_temp = 1.0f / e->temperature;
+      ps.rng_state = e->s.rng_state;
+      ps.row_offset = 0;
+      ps.part_max = e->part_max;
+      ps.part_sum = e->part_sum;
+      ps.n_tiles = plan_logits.n_tiles;
+      ps.row_M = e->par_M;
+      ps.row_Z = e->par_Z;
+      ps.target = e->par_target;
+      ps.above = e->par_above;
+      ps.prefix = e->par_prefix;
+      ps.found = e->par_found;
+      ps.hist = e->par_hist;
+      ps.eq_count = e->par_eq;
+      ps.out_score = e->part_score;
+      ps.out_idx = e->part_idx;
+      ps.out_raw = e->part_raw;
+      ps.out_max = e->part_max;
+      ps.out_sum = e->part_sum;
+      ps.slices = par_slices(c.vocab_size);
+      ps.row_group = par_row_group(c.vocab_size, rows);
+      const dim3 sweep(ps.slices, (rows + ps.row_group - 1) / ps.row_group);
+      MTX_TRY(launch(par_stats_kernel, dim3(rows), dim3(kParThreads), 0, st, ps));
+      for (int level = 0; level < kParLevels; ++level) {
+        MTX_TRY(launch(par_hist_kernel, sweep, dim3(kParThreads), 0, st, ps, level));
+        MTX_TRY(launch(par_select_kernel, dim3(rows), dim3(256), 0, st, ps, level));
+      }
+      if (e->strategy == MTX_SAMPLE_TOPK) MTX_TRY(launch(par_eqcount_kernel, sweep, dim3(kParThreads), 0, st, ps));
+      MTX_TRY(launch(par_scan_kernel, sweep, dim3(kParThreads), 0, st, ps));
+      fa.n_tiles = ps.slices * kParWarps;
+      fa.stride_r = ps.slices * kParWarps;
+    } else if (two_pass) {
       // inference_utils.py:87-111 on the logits the GEMM just wrote; one candidate per row
       SampleArgs sa;
       memset(&sa, 0, sizeof(sa));
@@ -1114,6 +1175,14 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   e->rows_ss_x = reinterpret_cast<float*>(b + L.rows_ss_x);
   e->rows_ss_h = reinterpret_cast<float*>(b + L.rows_ss_h);
   e->cand_counters = reinterpret_cast<int*>(b + L.cand_counters);
+  e->par_M = reinterpret_cast<float*>(b + L.par_M);
+  e->par_Z = reinterpret_cast<float*>(b + L.par_Z);
+  e->par_target = reinterpret_cast<unsigned long long*>(b + L.par_target);
+  e->par_above = reinterpret_cast<unsigned long long*>(b + L.par_above);
+  e->par_prefix = reinterpret_cast<uint32_t*>(b + L.par_prefix);
+  e->par_found = reinterpret_cast<int*>(b + L.par_found);
+  e->par_hist = reinterpret_cast<unsigned long long*>(b + L.par_hist);
+  e->par_eq = reinterpret_cast<int*>(b + L.par_eq);
   MTX_CUDA(cudaMemcpy(e->rope_timescale, e->rope_timescale_host.data(), e->rope_timescale_host.size() * 4, cudaMemcpyHostToDevice));
 
   const int E = c.emb_dim, HD = c.num_q_heads * c.head_dim, M = c.mlp_dim, L_ = c.num_layers;

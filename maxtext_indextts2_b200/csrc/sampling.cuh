@@ -501,3 +501,464 @@ __global__ void __launch_bounds__(kSampleThreads) commit_topk_kernel(const Commi
 }
 
 }  // namespace mtx
+
+namespace mtx {
+
+// =============================================================================================================
+// top-k / nucleus over materialised logits on ALL SMs (round 2).  sample_rows_kernel above walks a row with one CTA
+// (64 CTAs at batch 64, seven passes over 1 MB each: ~1.4 ms per step); here the same radix descent is cut along the
+// vocabulary: slices x ceil(rows / row_group) CTAs histogram their slice in shared memory and add the non-empty bins to
+// the row's global histogram, one small CTA per row picks the bin; three levels of 11 + 11 + 10 key bits, one sweep counts
+// the entries equal to the cut-off (top-k ties) and one more draws the Gumbel-max winner of every (row, slice, warp);
+// finalize_kernel merges those like the tiles of the fused path.  Every sweep reads 16 bytes per lane, keeps four such
+// loads in flight per thread and issues the next batch's loads before it works on the current one: a sweep is a handful of
+// dependent DRAM/L2 round trips per CTA, so what it costs is how many of them are serialised.
+// Why 11-bit digits: the top BYTE of a float key is sign + 7 exponent bits, and the logits of a row share a few exponents,
+// so an 8-bit first level piles every element onto ~6 shared-memory addresses (measured: 0.8 ms of serialised atomics;
+// warp-aggregating them with match.any was slower still); two mantissa bits more spread a row over ~80 bins.
+// Mass histograms are 2^-40 fixed point in integers: exact, and independent of the order in which threads and slices
+// add -- the cut-off is a deterministic function of the logits.
+// =============================================================================================================
+
+constexpr int kParMaxSlices = 128;
+constexpr int kParThreads = 256;
+constexpr int kParWarps = kParThreads / 32;
+constexpr int kParBatch = 4 * kParThreads;  // 16-byte units one CTA has in flight
+constexpr int kParLevels = 3;
+constexpr int kParBins = 2048;
+constexpr float kParFix = 1099511627776.0f;  // 2^40
+__device__ __forceinline__ int par_shift(int level) { return level == 0 ? 21 : level == 1 ? 10 : 0; }  // level 0 = most significant digit
+__device__ __forceinline__ int par_width(int level) { return level == 2 ? 10 : 11; }
+
+// Host: the cut of a row -- one batch per slice when the vocabulary allows it -- and the rows a CTA walks.
+inline int par_slices(int vocab) {
+  const int n4 = (vocab + 3) / 4;
+  const int s = (n4 + kParBatch - 1) / kParBatch;
+  return s < 1 ? 1 : s > kParMaxSlices ? kParMaxSlices : s;
+}
+inline int par_row_group(int vocab, int rows) {
+  const int g = par_slices(vocab) * rows / 1024;  // ~7 CTAs of 256 threads per SM
+  return g < 1 ? 1 : g > 16 ? 16 : g;
+}
+
+struct ParSampleArgs {
+  const float* logits;  // [rows, ld]
+  long long ld;
+  int vocab, vocab_offset, rows;
+  int slices, row_group;
+  int mode;             // MTX_SAMPLE_NUCLEUS (2) or MTX_SAMPLE_TOPK (3)
+  int top_k;
+  float nucleus_p, inv_temp;
+  const uint32_t* rng_state;
+  int row_offset;
+  const float* part_max;  // [rows, n_tiles] per-tile (max, sum exp) the logits epilogue left
+  const float* part_sum;
+  int n_tiles;
+  float* row_M;                    // [rows]
+  float* row_Z;                    // [rows]
+  unsigned long long* target;      // [rows] mass (2^-40 fixed point of exp(x - M)) or count to reach
+  unsigned long long* above;       // [rows] mass / count strictly above the selected prefix
+  uint32_t* prefix;                // [rows] radix prefix of the cut-off key
+  int* found;                      // [rows] 0: the target exceeds the total, nothing is cut; 1: cut; 2: cut, and only some of the
+                                   // entries equal to the cut-off key are kept (top-k ties: rank them by index)
+  unsigned long long* hist;        // [rows, kParBins] zero between levels (par_select_kernel clears what it reads)
+  int* eq_count;                   // [rows, slices * kParWarps] entries equal to the cut-off per warp piece (rows with found == 2)
+  float* out_score;                // [rows, slices * kParWarps] partials for finalize_kernel
+  int* out_idx;
+  float* out_raw;
+  float* out_max;
+  float* out_sum;
+};
+
+// Slice s of a row in units of 4 consecutive entries (16-byte loads): vec4 indices [lo4, hi4).
+__device__ __forceinline__ void par_slice4(int vocab, int slices, int s, int& lo4, int& hi4) {
+  const int n4 = (vocab + 3) >> 2;
+  lo4 = int((long long)s * n4 / slices);
+  hi4 = int((long long)(s + 1) * n4 / slices);
+}
+// Warp w's contiguous piece of a slice.
+__device__ __forceinline__ void par_piece4(int lo4, int hi4, int w, int& wlo, int& whi) {
+  wlo = lo4 + int((long long)w * (hi4 - lo4) / kParWarps);
+  whi = lo4 + int((long long)(w + 1) * (hi4 - lo4) / kParWarps);
+}
+// Entries 4 q .. 4 q + 3 of a row; entries at or past `vocab` read as -inf.  `vec` = rows are 16-byte aligned and whole.
+__device__ __forceinline__ float4 par_load4(const float* row, int q, int vocab, bool vec) {
+  if (vec) return __ldg(reinterpret_cast<const float4*>(row) + q);
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = 4 * q + j < vocab ? __ldg(row + 4 * q + j) : -INFINITY;
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ float4 par_neg_inf4() { return make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); }
+__device__ __forceinline__ int par_count_eq(const float4& x, int q, int vocab, uint32_t key) {
+  return (4 * q < vocab && f32_order_key(x.x) == key) + (4 * q + 1 < vocab && f32_order_key(x.y) == key) +
+         (4 * q + 2 < vocab && f32_order_key(x.z) == key) + (4 * q + 3 < vocab && f32_order_key(x.w) == key);
+}
+
+// One CTA per row: softmax statistics from the per-tile partials, the descent's target, state reset.
+__global__ void __launch_bounds__(kParThreads) par_stats_kernel(const ParSampleArgs a) {
+  __shared__ float s_red[kParWarps];
+  griddep_launch_dependents();
+  griddep_wait();
+  const int r = blockIdx.x, tid = threadIdx.x;
+  float mx = -INFINITY;
+  for (int t = tid; t < a.n_tiles; t += kParThreads) mx = fmaxf(mx, a.part_max[(long long)r * a.n_tiles + t]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+  __syncthreads();
+  mx = s_red[0];
+  for (int w = 1; w < kParWarps; ++w) mx = fmaxf(mx, s_red[w]);
+  __syncthreads();
+  float z = 0.0f;
+  for (int t = tid; t < a.n_tiles; t += kParThreads) {
+    const float m = a.part_max[(long long)r * a.n_tiles + t];
+    if (m > -INFINITY) z += a.part_sum[(long long)r * a.n_tiles + t] * expf(m - mx);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+  if ((tid & 31) == 0) s_red[tid >> 5] = z;
+  __syncthreads();
+  for (int i = tid; i < kParBins; i += kParThreads) a.hist[(long long)r * kParBins + i] = 0ull;
+  if (tid == 0) {
+    float tot = 0.0f;
+    for (int w = 0; w < kParWarps; ++w) tot += s_red[w];  // fixed order
+    a.row_M[r] = mx;
+    a.row_Z[r] = tot;
+    a.target[r] = a.mode == 2 ? (unsigned long long)(double(a.nucleus_p) * double(tot) * double(kParFix))
+                              : (unsigned long long)(a.top_k < a.vocab ? a.top_k : a.vocab);
+    a.above[r] = 0ull;
+    a.prefix[r] = 0u;
+    a.found[r] = 1;
+  }
+}
+
+// Histogram of one radix level over one vocabulary slice for a group of rows, added to the rows' global histograms.
+// Shared-memory counters are 32-bit (native atomics; the 64-bit ones are compare-and-swap loops): a count is one counter,
+// a 2^-40 fixed-point weight is split into 14 + 14 + 13 bits over three (a slice would need 2^18 entries to overflow one).
+__global__ void __launch_bounds__(kParThreads) par_hist_kernel(const ParSampleArgs a, int level) {
+  __shared__ uint32_t s_hist[3][kParBins];
+  griddep_launch_dependents();
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 3 * kParBins; i += kParThreads) (&s_hist[0][0])[i] = 0u;
+  __syncthreads();
+  griddep_wait();
+  int lo4, hi4;
+  par_slice4(a.vocab, a.slices, blockIdx.x, lo4, hi4);
+  const bool vec = (a.ld & 3) == 0 && (a.vocab & 3) == 0;
+  const bool mass = a.mode == 2;
+  const int r0 = blockIdx.y * a.row_group;
+  const int n_rows = min(a.row_group, a.rows - r0);
+  const int nb = (hi4 - lo4 + kParBatch - 1) / kParBatch;  // batches per row
+  const int shift = par_shift(level), above_bits = shift + par_width(level);
+  const uint32_t mask = (1u << par_width(level)) - 1u;
+  auto load = [&](int it, float4 (&x)[4]) {
+    const float* row = a.logits + (long long)(r0 + it / nb) * a.ld;
+    const int q0 = lo4 + (it % nb) * kParBatch;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * kParThreads + tid;
+      x[u] = q < hi4 ? par_load4(row, q, a.vocab, vec) : par_neg_inf4();
+    }
+  };
+  const int total = n_rows * nb;
+  float4 cur[4], nxt[4];
+  if (total > 0) load(0, nxt);
+  for (int it = 0; it < total; ++it) {
+    const int r = r0 + it / nb, b = it % nb;
+    const bool live = a.found[r] != 0;  // (block-uniform)
+    const uint32_t prefix = a.prefix[r];
+    const float M = a.row_M[r];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+    if (it + 1 < total) load(it + 1, nxt);
+    if (live) {
+      const int q0 = lo4 + b * kParBatch;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = q0 + u * kParThreads + tid;
+        const float xs[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (q >= hi4 || 4 * q + j >= a.vocab) continue;
+          const uint32_t key = f32_order_key(xs[j]);
+          if (level == 0 || (key >> above_bits) == (prefix >> above_bits)) {
+            const uint32_t bin = (key >> shift) & mask;
+            if (level > 0) {
+              // the entries under the selected prefix are few (a row spreads over ~80 first-level bins): no staging
+              atomicAdd(a.hist + (long long)r * kParBins + bin, mass ? __float2ull_rz(expf(xs[j] - M) * kParFix) : 1ull);
+            } else if (mass) {
+              const unsigned long long w = __float2ull_rz(expf(xs[j] - M) * kParFix);
+              atomicAdd(&s_hist[0][bin], uint32_t(w & 0x3FFFu));
+              atomicAdd(&s_hist[1][bin], uint32_t((w >> 14) & 0x3FFFu));
+              atomicAdd(&s_hist[2][bin], uint32_t(w >> 28));
+            } else {
+              atomicAdd(&s_hist[0][bin], 1u);
+            }
+          }
+        }
+      }
+    }
+    if (level == 0 && b == nb - 1 && live) {
+      __syncthreads();
+      for (int i = tid; i < kParBins; i += kParThreads) {
+        const unsigned long long v = mass ? (unsigned long long)s_hist[0][i] + ((unsigned long long)s_hist[1][i] << 14) + ((unsigned long long)s_hist[2][i] << 28)
+                                          : (unsigned long long)s_hist[0][i];
+        if (v != 0ull) {
+          atomicAdd(a.hist + (long long)r * kParBins + i, v);
+          s_hist[0][i] = s_hist[1][i] = s_hist[2][i] = 0u;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// One CTA per row: descend one level on the row's histogram (and clear it for the next level).  Thread t owns bins
+// 8 t .. 8 t + 7; a block-wide suffix sum over the 256 chunk totals finds the chunk the target falls in.
+__global__ void __launch_bounds__(256) par_select_kernel(const ParSampleArgs a, int level) {
+  __shared__ unsigned long long s_warp[8];
+  __shared__ int s_sel;
+  griddep_launch_dependents();
+  griddep_wait();
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (!a.found[r]) return;
+  constexpr int kPer = kParBins / 256;
+  unsigned long long* h = a.hist + (long long)r * kParBins;
+  unsigned long long bins[kPer];
+  unsigned long long t = 0ull;
+  {
+    const ulonglong2* h2 = reinterpret_cast<const ulonglong2*>(h + tid * kPer);
+#pragma unroll
+    for (int j = 0; j < kPer / 2; ++j) {
+      const ulonglong2 v = h2[j];
+      bins[2 * j] = v.x;
+      bins[2 * j + 1] = v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      t += bins[j];
+      if (bins[j] != 0ull) h[tid * kPer + j] = 0ull;
+    }
+  }
+  if (tid == 0) s_sel = -1;
+  // inclusive suffix sum over threads (thread 255 = the highest bins)
+  unsigned long long suf = t;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long v = __shfl_down_sync(0xffffffffu, suf, o);
+    if (lane + o < 32) suf += v;
+  }
+  if (lane == 0) s_warp[warp] = suf;
+  __syncthreads();
+  for (int w = warp + 1; w < 8; ++w) suf += s_warp[w];
+  const unsigned long long above0 = a.above[r], target = a.target[r];
+  // the highest chunk whose inclusive suffix reaches the target owns the bin (its own total is then non-zero)
+  const bool hit = above0 + suf >= target && t > 0ull;
+  if (hit) atomicMax(&s_sel, tid);
+  __syncthreads();
+  const int sel_chunk = s_sel;
+  if (sel_chunk < 0) {
+    if (tid == 0) a.found[r] = 0;  // the target exceeds the total (p >= 1 up to rounding): nothing is cut
+    return;
+  }
+  if (tid == sel_chunk) {
+    unsigned long long above = above0 + suf - t;
+    int sel = tid * kPer;
+#pragma unroll
+    for (int j = kPer - 1; j >= 0; --j) {
+      if (above + bins[j] >= target && bins[j] > 0ull) { sel = tid * kPer + j; break; }
+      above += bins[j];
+    }
+    a.above[r] = above;
+    a.prefix[r] |= uint32_t(sel) << par_shift(level);
+    // top-k, last level: bins[sel] entries carry the cut-off key and target - above of them are kept
+    if (a.mode != 2 && level == kParLevels - 1 && bins[sel - tid * kPer] != target - above) a.found[r] = 2;
+  }
+}
+
+// top-k only: entries equal to the cut-off key per (slice, warp piece, row) -- the tie rule of lax.top_k is "lowest index
+// first", and par_scan_kernel's warps need the count in the pieces before theirs.
+__global__ void __launch_bounds__(kParThreads) par_eqcount_kernel(const ParSampleArgs a) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int lo4, hi4, wlo, whi;
+  par_slice4(a.vocab, a.slices, blockIdx.x, lo4, hi4);
+  par_piece4(lo4, hi4, warp, wlo, whi);
+  const bool vec = (a.ld & 3) == 0 && (a.vocab & 3) == 0;
+  const int r0 = blockIdx.y * a.row_group;
+  const int n_rows = min(a.row_group, a.rows - r0);
+  const int nb = (whi - wlo + 127) / 128;  // batches of 4 x 32 lanes per row
+  const int total = n_rows * nb;
+  const int piece = blockIdx.x * kParWarps + warp, pieces = a.slices * kParWarps;
+  auto load = [&](int it, float4 (&x)[4]) {
+    const int r = r0 + it / nb;
+    const float* row = a.logits + (long long)r * a.ld;
+    const int q0 = wlo + (it % nb) * 128;
+    const bool tied = a.found[r] == 2;  // the other rows keep every entry that equals the cut-off: nothing to count
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * 32 + lane;
+      x[u] = tied && q < whi ? par_load4(row, q, a.vocab, vec) : par_neg_inf4();
+    }
+  };
+  float4 cur[4], nxt[4];
+  if (total > 0) load(0, nxt);
+  int mine = 0;
+  for (int it = 0; it < total; ++it) {
+    const int r = r0 + it / nb, b = it % nb;
+    const uint32_t cut_key = a.prefix[r];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+    if (it + 1 < total) load(it + 1, nxt);
+    const int q0 = wlo + b * 128;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * 32 + lane;
+      if (q < whi) mine += par_count_eq(cur[u], q, a.vocab, cut_key);
+    }
+    if (b == nb - 1) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+      if (lane == 0) a.eq_count[(long long)r * pieces + piece] = mine;
+      mine = 0;
+    }
+  }
+  if (total == 0 && lane == 0)
+    for (int rr = 0; rr < n_rows; ++rr) a.eq_count[(long long)(r0 + rr) * pieces + piece] = 0;
+}
+
+// The draw: for every (row, slice, warp piece) the best Gumbel-perturbed kept entry (inference_utils.py:87-111), lowest
+// index on ties.  A warp owns a contiguous piece and a lane four consecutive entries, so "the first `need` entries equal to
+// the cut-off in index order" needs the counts of the pieces before this one (par_eqcount_kernel) and four ballots per 128
+// entries -- no block-wide scan, no barrier; the noise of a lane's four entries is one Philox block.  Nucleus: the
+// reference leaves the entries below the cut-off in the draw with logit -1e7; their score is below every kept entry's by
+// ~1e7 / temperature (Gumbel noise is < 17), they cannot win, and they are skipped here (no noise is generated for them).
+__global__ void __launch_bounds__(kParThreads, 4) par_scan_kernel(const ParSampleArgs a) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int piece = blockIdx.x * kParWarps + warp, pieces = a.slices * kParWarps;
+  int lo4, hi4, wlo, whi;
+  par_slice4(a.vocab, a.slices, blockIdx.x, lo4, hi4);
+  par_piece4(lo4, hi4, warp, wlo, whi);
+  const bool vec = (a.ld & 3) == 0 && (a.vocab & 3) == 0;
+  const bool noise4 = (a.vocab_offset & 3) == 0;
+  const uint32_t step = a.rng_state[0];
+  const uint64_t seed = (uint64_t(a.rng_state[2]) << 32) | a.rng_state[1];
+  const uint32_t lt = (1u << lane) - 1u;
+  const int r0 = blockIdx.y * a.row_group;
+  const int n_rows = min(a.row_group, a.rows - r0);
+  const int nb = (whi - wlo + 127) / 128;
+  const int total = n_rows * nb;
+  auto load = [&](int it, float4 (&x)[4]) {
+    const float* row = a.logits + (long long)(r0 + it / nb) * a.ld;
+    const int q0 = wlo + (it % nb) * 128;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * 32 + lane;
+      x[u] = q < whi ? par_load4(row, q, a.vocab, vec) : par_neg_inf4();
+    }
+  };
+  float4 cur[4], nxt[4];
+  if (total > 0) load(0, nxt);
+  float best = -INFINITY, raw = -INFINITY;
+  int bi = 0x7fffffff, need = 0, before = 0;
+  uint32_t cut_key = 0u;
+  bool found = false, tied = false;
+  for (int it = 0; it < total; ++it) {
+    const int r = r0 + it / nb, b = it % nb;
+    if (b == 0) {
+      const int f = a.found[r];
+      found = f != 0;
+      tied = f == 2;
+      cut_key = found ? a.prefix[r] : 0u;
+      best = raw = -INFINITY;
+      bi = 0x7fffffff;
+      before = 0;
+      if (tied) {
+        need = int(a.target[r] - a.above[r]);
+        for (int p2 = lane; p2 < piece; p2 += 32) before += a.eq_count[(long long)r * pieces + p2];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+    if (it + 1 < total) load(it + 1, nxt);
+    const int q0 = wlo + b * 128;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * 32 + lane;
+      const bool in = q < whi;
+      const float xs[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
+      bool keep[4];
+      if (!tied) {  // (warp-uniform)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) keep[j] = in && 4 * q + j < a.vocab && f32_order_key(xs[j]) >= cut_key;  // (by key: -0.0 < +0.0)
+      } else {
+        bool eq[4];
+        uint32_t bal[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          eq[j] = in && 4 * q + j < a.vocab && f32_order_key(xs[j]) == cut_key;
+          bal[j] = __ballot_sync(0xffffffffu, eq[j]);
+        }
+        // index order inside the 128 entries: lane-major, then the lane's four entries
+        int rank = before + __popc(bal[0] & lt) + __popc(bal[1] & lt) + __popc(bal[2] & lt) + __popc(bal[3] & lt);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          keep[j] = in && 4 * q + j < a.vocab && (f32_order_key(xs[j]) > cut_key || (eq[j] && rank < need));
+          rank += eq[j] ? 1 : 0;
+        }
+        before += __popc(bal[0]) + __popc(bal[1]) + __popc(bal[2]) + __popc(bal[3]);
+      }
+      if (keep[0] || keep[1] || keep[2] || keep[3]) {
+        float g[4];
+        if (noise4) {
+          const float4 g4 = gumbel_noise4(seed, step, uint32_t(a.row_offset + r), uint32_t(a.vocab_offset + 4 * q));
+          g[0] = g4.x; g[1] = g4.y; g[2] = g4.z; g[3] = g4.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) g[j] = keep[j] ? gumbel_noise(seed, step, uint32_t(a.row_offset + r), uint32_t(a.vocab_offset + 4 * q + j)) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!keep[j]) continue;
+          const float sc = xs[j] * a.inv_temp + g[j];
+          if (sc > best) { best = sc; bi = 4 * q + j; raw = xs[j]; }
+        }
+      }
+    }
+    if (b == nb - 1) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float s2 = __shfl_xor_sync(0xffffffffu, best, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+        const float r2 = __shfl_xor_sync(0xffffffffu, raw, o);
+        if (s2 > best || (s2 == best && i2 < bi)) { best = s2; bi = i2; raw = r2; }
+      }
+      if (lane == 0) {
+        const long long o = (long long)r * pieces + piece;
+        a.out_score[o] = best;
+        a.out_idx[o] = bi == 0x7fffffff ? 0x7fffffff : a.vocab_offset + bi;
+        a.out_raw[o] = raw;
+        a.out_max[o] = piece == 0 ? a.row_M[r] : -INFINITY;
+        a.out_sum[o] = piece == 0 ? a.row_Z[r] : 0.0f;
+      }
+    }
+  }
+  if (total == 0 && lane == 0) {
+    for (int rr = 0; rr < n_rows; ++rr) {
+      const long long o = (long long)(r0 + rr) * pieces + piece;
+      a.out_score[o] = -INFINITY;
+      a.out_idx[o] = 0x7fffffff;
+      a.out_raw[o] = -INFINITY;
+      a.out_max[o] = piece == 0 ? a.row_M[r0 + rr] : -INFINITY;
+      a.out_sum[o] = piece == 0 ? a.row_Z[r0 + rr] : 0.0f;
+    }
+  }
+}
+
+}  // namespace mtx

@@ -412,10 +412,21 @@ __device__ __forceinline__ void pk_logits_scan(const float* park, int wtid, int 
       const int n0 = tile * 128 + c;
       const float4 lg4 = pk_logit_transform(e, *reinterpret_cast<const float4*>(row + c));
       const float lg[4] = {lg4.x, lg4.y, lg4.z, lg4.w};
+      // the four ids of the chunk share one Philox block when the shard starts at a multiple of four
+      float gn[4] = {0.f, 0.f, 0.f, 0.f};
+      if (e.gumbel) {
+        if ((e.vocab_offset & 3) == 0) {
+          const float4 g4 = gumbel_noise4(seed, step, uint32_t(e.row_offset + r), uint32_t(e.vocab_offset + n0));
+          gn[0] = g4.x; gn[1] = g4.y; gn[2] = g4.z; gn[3] = g4.w;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gn[q] = gumbel_noise(seed, step, uint32_t(e.row_offset + r), uint32_t(e.vocab_offset + n0 + q));
+        }
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (n0 + q < V) {
-          const float sc = e.gumbel ? lg[q] * e.inv_temp + gumbel_noise(seed, step, uint32_t(e.row_offset + r), uint32_t(e.vocab_offset + n0 + q)) : lg[q];
+          const float sc = e.gumbel ? lg[q] * e.inv_temp + gn[q] : lg[q];
           if (sc > best) { best = sc; raw = lg[q]; bi = n0 + q; }  // ascending scan: strict > keeps the lowest index
           if (e.want_lse) {
             const float mn = fmaxf(mx, lg[q]);

@@ -255,6 +255,44 @@ def test_topk_and_nucleus_follow_the_oracle_stream(strategy, kw):
     torch.testing.assert_close(result.log_prob.cpu(), lp, rtol=1e-3, atol=1e-3)
 
 
+def test_topk_ties_keep_the_lowest_index():
+  """lax.top_k (inference_utils.py:103) keeps the lower index of equal logits.  Every logit appears twice here (the output
+  projection's columns come in identical pairs) and k is odd, so the cut-off value always has one entry kept and one dropped;
+  a high temperature makes the draw visit the whole kept set."""
+  temp, k = 6.0, 5
+  cfg = small_config(per_device_batch_size=4, decode_sampling_strategy="topk", decode_sampling_top_k=k,
+                     decode_sampling_temperature=temp)
+  params = make_params(cfg)
+  if cfg.logits_via_embedding:
+    emb = params["params"]["token_embedder"]["embedding"]
+    emb[1::2] = emb[0::2]
+  else:
+    w = params["params"]["decoder"]["logits_dense"]["kernel"]
+    w[:, 1::2] = w[:, 0::2]
+  engine = maxengine.MaxEngine(cfg, use_cuda_graph=True)
+  dparams = engine.load_params(params)
+  state = engine.init_decode_state(rng=np.array([5, 0], dtype=np.uint32))
+  prompts = random_tokens((4, 16), cfg.vocab_size, seed=11)
+  for slot in range(4):
+    prefix, _ = engine.prefill(params=dparams, padded_tokens=prompts[slot], true_length=9 + slot)
+    state = engine.insert(prefix, state, slot)
+  picked_last = 0
+  for step in range(16):
+    state, result = engine.generate(dparams, state)
+    logits = state["logits"].cpu()
+    assert torch.equal(logits[..., 0::2], logits[..., 1::2])
+    toks, scores = ref.sampling(logits, "topk", topk=k, temperature=temp, seed=5, step=step, return_scores=True)
+    got = result.data.cpu()[:, 0]
+    for b in range(4):
+      g, w = int(got[b]), int(toks[b, 0])
+      assert scores[b][g] > -float("inf"), (step, b, g)  # inside the oracle's kept set
+      if g != w:
+        assert abs(scores[b][g] - scores[b][w]) < 1e-3, (step, b, g, w)
+      kept = torch.nonzero(scores[b] > -float("inf"))[:, 0]
+      picked_last += int(g == int(kept[torch.argmin(logits[b, 0, kept])]))
+  assert picked_last > 0  # the tied entry itself was drawn at least once
+
+
 def test_indextts2_scale_logits_and_greedy_tokens():
   """BASELINE config C2 shape (24 layers, emb 1280, 20/4 heads x 64, mlp 5120, V = 264,192) with short
   P/T so the CPU oracle finishes in about a minute: prefill + 6 decode steps, 4 slots."""
