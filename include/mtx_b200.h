@@ -73,6 +73,16 @@ typedef struct {
                                 k_scale / v_scale hold the decode cache, k_cache / v_cache are ONE bf16 staging plane for prefill */
   int32_t norm_scales_folded; /* 1: wqkv / w01 already carry the per-feature RMSNorm scales of their input (W' = W * diag(scale),
                                  folded at load time) and attn_norm / mlp_norm are all ones: the step skips the scale pass */
+  /* decoder block (MaxText/layers/decoders.py:352-357).  0 = llama2 (layers/llama2.py:54-165); 1 = gemma3 (layers/gemma3.py:62-197):
+   * RMSNorm of q and k over head_dim before RoPE (attentions.py:2246-2248), query * query_scalar after it (:2263-2265), RMSNorm of
+   * the attention and MLP outputs before their residual adds (gemma3.py:142-170), GELU-gated MLP (tanh form, linears.py:460), five
+   * sliding-window layers followed by one global layer (gemma3.py:36-48), the local layers with their own RoPE base
+   * (attentions.py:2085-2088).  Requires norm_scales_folded, a bf16 cache and the weights q_norm / k_norm / post_attn_norm /
+   * post_ffw_norm. */
+  int32_t decoder_block;
+  int32_t sliding_window;          /* sliding_window_size of the local layers (gemma3), 0 = none */
+  float local_rope_max_timescale;  /* RoPE base of the local layers; <= 0: rope_max_timescale */
+  float query_scalar;              /* query_pre_attn_scalar (gemma3.py:51-58); 0 or 1 = none */
 } mtx_model_config;
 
 /* Weights, repacked once at load time for K-major streaming (see DESIGN.md "Data layout").
@@ -83,6 +93,7 @@ typedef struct {
  *                                rows 32g..32g+15 = wi_0[:, 16g..16g+15]^T, rows 32g+16..32g+31 = wi_1[...]^T
  *   wout[l]  [ E, M ]            wo kernel transposed (linears.py:425-476)
  *   logits   [ V, E ]            logits_dense kernel transposed, or the embedding table when tied
+ * gemma3: attn_norm = pre_self_attention_norm/scale (gemma3.py:86-92), mlp_norm = mlp/mlp_layer_norm/scale (use_pre_norm).
  */
 typedef struct {
   const void* embedding;  /* [V_full, E]   token_embedder/embedding as bf16 (embeddings.py:154) */
@@ -94,6 +105,11 @@ typedef struct {
   const void* wout;       /* [L, E, M] */
   const void* final_norm; /* [E]           decoder_norm/scale */
   const void* logits;     /* [V, E] */
+  /* gemma3 block only (null otherwise) */
+  const void* q_norm;         /* [L, D]  self_attention/query_norm/scale */
+  const void* k_norm;         /* [L, D]  self_attention/key_norm/scale */
+  const void* post_attn_norm; /* [L, E]  post_self_attention_norm/scale */
+  const void* post_ffw_norm;  /* [L, E]  post_ffw_norm/scale */
 } mtx_weights;
 
 /* Decode state: the device-resident fields of the reference's decode_state dict

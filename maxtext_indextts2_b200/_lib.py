@@ -56,13 +56,18 @@ class ModelConfig(ctypes.Structure):
       ("embedding_rows", ctypes.c_int32),
       ("kv_quant", ctypes.c_int32),
       ("norm_scales_folded", ctypes.c_int32),
+      ("decoder_block", ctypes.c_int32),
+      ("sliding_window", ctypes.c_int32),
+      ("local_rope_max_timescale", ctypes.c_float),
+      ("query_scalar", ctypes.c_float),
   ]
 
 
 class Weights(ctypes.Structure):
   _fields_ = [
       (name, ctypes.c_void_p)
-      for name in ("embedding", "attn_norm", "wqkv", "wo", "mlp_norm", "w01", "wout", "final_norm", "logits")
+      for name in ("embedding", "attn_norm", "wqkv", "wo", "mlp_norm", "w01", "wout", "final_norm", "logits",
+                   "q_norm", "k_norm", "post_attn_norm", "post_ffw_norm")
   ]
 
 

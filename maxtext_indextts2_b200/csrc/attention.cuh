@@ -50,6 +50,12 @@ struct AttnParams {
   int seq_major;     // 1: K/V are [plane, T, Hkv, D] (the reference's logical cache layout): tile = rows of one head at stride Hkv*D
   float* out_max;    // [rows, Hq] or null.  Non-null: `out` is left UNNORMALISED (sum_t exp(s_t - max) v_t) and the row's
   float* out_sum;    // [rows, Hq]   (max, sum) are returned for the caller's cross-segment merge (attentions.py:1376-1397)
+  // Sliding-window layers in AUTOREGRESSIVE mode (attentions.py:600-602,624-631: the window is taken over the CACHE INDICES of
+  // each segment, next_pos = kv_seq_len - 1): only prefill rows [skip0, P) and ring indices [ring_off, R) can be attended.
+  // len0 / ring_first / ring_len then describe the valid rows INSIDE those two sub-ranges (prepare_rows_kernel, *_w arrays).
+  int skip0;      // first prefill row of the window (0: no window)
+  int ring_off;   // first ring index of the window (0: no window)
+  int ring_size;  // ring indices in the window (0: the whole ring, T - P)
 };
 
 struct TileLoc { int p0, cnt; };
@@ -80,7 +86,7 @@ __host__ inline int attn_tiles_per_item(int rows, int hkv, int P, int T, int tar
 }
 
 // Physical start row and valid count of 64-row tile t of a row's valid sequence.
-__device__ __forceinline__ TileLoc attn_tile(int t, int len0, int ring_first, int ring_len, int P, int R) {
+__device__ __forceinline__ TileLoc attn_tile(int t, int len0, int ring_first, int ring_len, int P, int R, int skip0 = 0, int ring_off = 0) {
   const int a = min(ring_len, R - ring_first);
   const int b = ring_len - a;
   const int n0 = (len0 + 63) >> 6, na = (a + 63) >> 6, nb = (b + 63) >> 6;
@@ -88,15 +94,15 @@ __device__ __forceinline__ TileLoc attn_tile(int t, int len0, int ring_first, in
   loc.cnt = 0;
   loc.p0 = 0;
   if (t < n0) {
-    loc.p0 = t * 64;
+    loc.p0 = skip0 + t * 64;
     loc.cnt = min(64, len0 - t * 64);
   } else if (t < n0 + na) {
     const int u = t - n0;
-    loc.p0 = P + ring_first + u * 64;
+    loc.p0 = P + ring_off + ring_first + u * 64;
     loc.cnt = min(64, a - u * 64);
   } else if (t < n0 + na + nb) {
     const int u = t - n0 - na;
-    loc.p0 = P + u * 64;
+    loc.p0 = P + ring_off + u * 64;
     loc.cnt = min(64, b - u * 64);
   }
   return loc;
@@ -147,7 +153,7 @@ __device__ __forceinline__ void attn_process_items(const CUtensorMap& tm_k, cons
   const int warp = tid >> 5, lane = tid & 31;
   const int gid = lane >> 2, tid4 = lane & 3;
   const int mtx_i = lane >> 3, lrow = lane & 7;
-  const int R = p.T - p.P;
+  const int R = p.ring_size > 0 ? p.ring_size : p.T - p.P;
   const int TPI = p.tiles_per_item;
   uint8_t* k_tile = smem + warp * 2 * kTileBytes;
   uint8_t* v_tile = k_tile + kTileBytes;
@@ -175,7 +181,7 @@ __device__ __forceinline__ void attn_process_items(const CUtensorMap& tm_k, cons
 
     // first tile of this warp: start both loads before touching Q
     int t = t_begin + warp;
-    TileLoc loc = attn_tile(t < t_end ? t : nt, len0, rf, rl, p.P, R);  // t >= nt gives an empty tile
+    TileLoc loc = attn_tile(t < t_end ? t : nt, len0, rf, rl, p.P, R, p.skip0, p.ring_off);  // t >= nt gives an empty tile
     if (t < t_end && lane == 0) {
       mbar_expect_tx(bar_k, kTileBytes);
 #pragma unroll
@@ -208,7 +214,7 @@ __device__ __forceinline__ void attn_process_items(const CUtensorMap& tm_k, cons
     for (; t < t_end; t += kAttnWarps) {
       const int cnt = loc.cnt;
       const int tn = t + kAttnWarps;
-      const TileLoc nloc = attn_tile(tn < t_end ? tn : nt, len0, rf, rl, p.P, R);
+      const TileLoc nloc = attn_tile(tn < t_end ? tn : nt, len0, rf, rl, p.P, R, p.skip0, p.ring_off);
       // ---- S = Q K^T over the 64 rows of the tile ----
       float s[8][4];
 #pragma unroll

@@ -15,6 +15,7 @@
 #include "attention.cuh"
 #include "gemm_rows.cuh"
 #include "gemm_umma.cuh"
+#include "gemma3_kernels.cuh"
 #include "prefill_attention.cuh"
 #include "sampling.cuh"
 #include "step_kernels.cuh"
@@ -324,9 +325,11 @@ struct mtx_engine {
   int* attn_tickets = nullptr;
   RowDesc rd{};
   float* rope_timescale = nullptr;
+  float* rope_timescale_w = nullptr;  // gemma3: the local layers' RoPE base
+  bf16* qkv_tmp = nullptr;            // gemma3: [max_r_tile, qkv_n] the QKV projection before q/k norm, RoPE and the cache append
   float *part_score = nullptr, *part_raw = nullptr, *part_max = nullptr, *part_sum = nullptr;
   int* part_idx = nullptr;
-  std::vector<float> rope_timescale_host;
+  std::vector<float> rope_timescale_host, rope_timescale_w_host;
   // descriptors
   std::vector<CUtensorMap> tm_wqkv, tm_wo, tm_w01, tm_wout;
   CUtensorMap tm_logits, tm_k, tm_v;
@@ -362,6 +365,7 @@ namespace {
 struct WsLayout {
   size_t x, h, n, q, attn, act, attn_part_o, attn_part_ml, attn_tickets;
   size_t token, pos, plane, write_row, len0, ring_first, ring_len, rope_cs, work_items, work_count, rope_timescale;
+  size_t len0_w, ring_first_w, ring_len_w, rope_cs_w, work_items_w, work_count_w, rope_timescale_w, qkv_tmp;
   size_t part_score, part_idx, part_raw, part_max, part_sum, grid_bar;
   size_t pk_tables, pk_part_ws, pk_ss_x, pk_ss_h, pk_attn_part_o, pk_tile_prefix, pk_attn_info;
   size_t rows_ss_x, rows_ss_h, cand_counters;
@@ -400,6 +404,16 @@ WsLayout layout_workspace(const mtx_engine* e) {
   L.work_items = take(size_t(c.max_rows) * e->attn_max_chunks * 4);
   L.work_count = take(4);
   L.rope_timescale = take((c.head_dim / 2) * 4);
+  if (c.decoder_block == 1) {
+    L.len0_w = take(rt * 4);
+    L.ring_first_w = take(rt * 4);
+    L.ring_len_w = take(rt * 4);
+    L.rope_cs_w = take(rt * (c.head_dim / 2) * 8);
+    L.work_items_w = take(size_t(c.max_rows) * e->attn_max_chunks * 4);
+    L.work_count_w = take(4);
+    L.rope_timescale_w = take((c.head_dim / 2) * 4);
+    L.qkv_tmp = take(rt * size_t(e->qkv_n) * 2);
+  }
   size_t vt = (c.vocab_size + kTileN - 1) / kTileN;
   if (vt < size_t(par_slices(c.vocab_size)) * kParWarps) vt = size_t(par_slices(c.vocab_size)) * kParWarps;  // par_scan_kernel's pieces
   L.part_score = take(size_t(c.max_rows) * vt * 4);
@@ -450,6 +464,9 @@ int get_xmaps(mtx_engine* e, int r_tile, XMaps** out) {
   return MTX_OK;
 }
 
+// gemma3.py:36-48: layers 0..4 of every six use sliding-window attention (and the local RoPE base), the sixth is global.
+bool layer_is_local(const mtx_engine* e, int layer) { return e->cfg.decoder_block == 1 && layer % 6 != 5; }
+
 int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st) {
   const mtx_model_config& c = e->cfg;
   AttnParams p;
@@ -462,6 +479,17 @@ int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st) {
   p.ring_len = e->rd.ring_len;
   p.work_items = e->rd.work_items;
   p.work_count = e->rd.work_count;
+  if (layer_is_local(e, layer)) {  // the window's two cache sub-ranges (attention.cuh, AttnParams.skip0)
+    const int R = c.max_target_len - c.max_prefill_len, W = c.sliding_window;
+    p.len0 = e->rd.len0_w;
+    p.ring_first = e->rd.ring_first_w;
+    p.ring_len = e->rd.ring_len_w;
+    p.work_items = e->rd.work_items_w;
+    p.work_count = e->rd.work_count_w;
+    p.skip0 = c.max_prefill_len > W ? c.max_prefill_len - W : 0;
+    p.ring_off = R > W ? R - W : 0;
+    p.ring_size = R - p.ring_off;
+  }
   p.part_o = e->attn_part_o;
   p.part_ml = e->attn_part_ml;
   p.tickets = e->attn_tickets;
@@ -512,6 +540,7 @@ int launch_prefill_attention(mtx_engine* e, int layer, int rows, int start_pos, 
   p.T = c.max_target_len;
   p.plane_row0 = (layer * planes + slot) * c.num_kv_heads * c.max_target_len;
   p.softcap = c.attn_softcap;
+  p.window = layer_is_local(e, layer) ? c.sliding_window : 0;
   const dim3 grid(c.num_q_heads, (rows + kPfQRows - 1) / kPfQRows), block(kPfWarps * 32);
   const size_t smem = prefill_attn_smem_bytes(c.head_dim);
   static bool attr_set = false;
@@ -656,7 +685,7 @@ bool pk_fill_phase(std::vector<PkTable>& tabs, int ph, int n, int k, bool allow_
 int pk_trace_bars(int layers) { return 2 + 5 * layers + 2 > 200 ? 2 + 5 * layers + 2 : 200; }
 
 bool pk_usable(const mtx_engine* e, int rows) {
-  if (e->pk_ctas <= 0 || round_rows(rows) > kPkMaxRTile || e->cfg.kv_quant) return false;
+  if (e->pk_ctas <= 0 || round_rows(rows) > kPkMaxRTile || e->cfg.kv_quant || e->cfg.decoder_block != 0) return false;
   if (e->cfg.num_q_heads / e->cfg.num_kv_heads > 8) return false;  // the attention MMA carries the group's heads in its 8 columns
   // an attention warp's tile list holds kPkAttnListMax entries: bound the worst case (every context full)
   const mtx_model_config& c = e->cfg;
@@ -738,7 +767,8 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
                  int32_t* first_token, float* prefill_logits, cudaStream_t st, float* cand_out = nullptr, float* first_log_prob = nullptr) {
   const mtx_model_config& c = e->cfg;
   // (an int8 cache is appended to by the row-major GEMM's epilogue only: steps of any size run it, padded to 128 rows)
-  const int r_tile = c.kv_quant && round_rows(rows) < 128 ? 128 : round_rows(rows);
+  const bool gemma3 = c.decoder_block == 1;
+  const int r_tile = (c.kv_quant || gemma3) && round_rows(rows) < 128 ? 128 : round_rows(rows);
   XMaps* xm;
   MTX_TRY(get_xmaps(e, r_tile, &xm));
   // prefill (mode 1) of an int8 engine writes the ONE bf16 staging plane that k_cache / v_cache then are
@@ -767,6 +797,8 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   pa.tiles_per_item = attn_tiles_per_item(rows, c.num_kv_heads, c.max_prefill_len, c.max_target_len, attn_target_items(e->num_sms));
   pa.emb_rows = c.embedding_rows;
   pa.rope_timescale = e->rope_timescale;
+  pa.window = gemma3 ? c.sliding_window : 0;
+  pa.rope_timescale_w = e->rope_timescale_w;
   const bool mega = mode == 0 && want_logits && pk_usable(e, rows);
   if (mega) {
     pa.grid_bar = e->grid_bar;
@@ -787,13 +819,13 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   gp.rows = rows;
   gp.r_tile = r_tile;
   const GemmPlan plan_logits = plan_gemm(c.vocab_size, c.emb_dim, r_tile, e->num_sms, EPI_LOGITS, 1);
-  const bool rows_k = c.kv_quant ? true : use_rows_kernel(r_tile);  // 65..256 rows: the row-major tensor-core GEMM (gemm_rows.cuh)
+  const bool rows_k = (c.kv_quant || gemma3) ? true : use_rows_kernel(r_tile);  // 65..256 rows: the row-major tensor-core GEMM (gemm_rows.cuh)
   XMaps* xm128 = xm;  // split-K units of that kernel load 128-row activation boxes
   if (rows_k) MTX_TRY(get_xmaps(e, 128, &xm128));
   auto xmap = [&](const RowsPlan& pl, CUtensorMap XMaps::*m) -> const CUtensorMap& { return pl.splits > 1 ? xm128->*m : xm->*m; };
   // 65..256 rows with the norm scales folded into the weights: RMSNorm is fused into the GEMMs around it (the residual
   // epilogues leave the row statistics, the consuming epilogues apply rstd; the per-kernel rmsnorm launches disappear)
-  const bool fused_norm = rows_k && c.norm_scales_folded && env_int("MTX_ROWS_FUSED_NORM", 1) != 0;
+  const bool fused_norm = rows_k && c.norm_scales_folded && (gemma3 || env_int("MTX_ROWS_FUSED_NORM", 1) != 0);
   const int ss_tiles = (E + 127) / 128;
   auto ss_args = [&](EpiArgs& ea, const float* in, float* out) {
     ea.ss_in = fused_norm ? in : nullptr;
@@ -803,7 +835,92 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     ea.ss_dim = E;
     ea.ss_eps = c.rms_eps;
   };
-  if (!mega) {
+  if (gemma3) {
+    // ---- layers/gemma3.py:62-197 on the row-major GEMMs; the element-wise steps between them in gemma3_kernels.cuh ----
+    MTX_TRY(launch(embed_gather_ss_kernel, dim3(rows), dim3(128), 0, st, (const int*)e->rd.token, static_cast<const bf16*>(e->w.embedding), e->x,
+                   e->rows_ss_x, ss_tiles, e->max_r_tile, E));
+    const RowsPlan pl_qkv = plan_rows(e->qkv_n, E, r_tile, e->num_sms, EPI_STORE_BF16);
+    const RowsPlan pl_o = plan_rows(E, HD, r_tile, e->num_sms, EPI_STORE_BF16);
+    const RowsPlan pl_up = plan_rows(2 * M, E, r_tile, e->num_sms, EPI_SWIGLU);
+    const RowsPlan pl_down = plan_rows(E, M, r_tile, e->num_sms, EPI_STORE_BF16);
+    for (int l = 0; l < L; ++l) {
+      const bool local = layer_is_local(e, l);
+      EpiArgs ea;
+      // q, k, v = dense(rms_norm(x))  (the pre-norm's scale is folded into wqkv, its rstd applied to the accumulator)
+      memset(&ea, 0, sizeof(ea));
+      ea.out = e->qkv_tmp;
+      ea.ld_out = e->qkv_n;
+      ss_args(ea, e->rows_ss_x, nullptr);
+      gp.n = e->qkv_n;
+      gp.k = E;
+      g_class = KC_QKV;
+      MTX_TRY(launch_rows<EPI_STORE_BF16>(e->tm_wqkv[l], xmap(pl_qkv, &XMaps::x), gp, ea, pl_qkv, st));
+      QkNormArgs qa;
+      memset(&qa, 0, sizeof(qa));
+      qa.qkv = e->qkv_tmp;
+      qa.q_scale = static_cast<const bf16*>(e->w.q_norm) + size_t(l) * c.head_dim;
+      qa.k_scale = static_cast<const bf16*>(e->w.k_norm) + size_t(l) * c.head_dim;
+      qa.rope_cs = local ? e->rd.rope_cs_w : e->rd.rope_cs;
+      qa.plane = e->rd.plane;
+      qa.write_row = e->rd.write_row;
+      qa.q_out = e->q;
+      qa.k_cache = static_cast<bf16*>(e->s.k_cache) + kv_layer * l;
+      qa.v_cache = static_cast<bf16*>(e->s.v_cache) + kv_layer * l;
+      qa.hq = c.num_q_heads;
+      qa.hkv = c.num_kv_heads;
+      qa.d = c.head_dim;
+      qa.t_alloc = c.max_target_len;
+      qa.eps = c.rms_eps;
+      qa.q_scalar = c.query_scalar;
+      MTX_TRY(launch(qk_norm_rope_append_kernel, dim3(rows, c.num_q_heads + 2 * c.num_kv_heads), dim3(c.head_dim / 2), 0, st, qa));
+
+      g_class = KC_ATTENTION;
+      // A row whose window holds no valid key (a prompt shorter than max_prefill_len - window while the ring's window is still
+      // empty) gets no work item: its attention output is defined as zero.  (The reference softmaxes the all-masked scores, i.e.
+      // averages every allocated cache row, valid or not: nothing a caller can rely on.)
+      if (mode == 0 && local) MTX_CUDA(cudaMemsetAsync(e->attn, 0, size_t(rows) * HD * 2, st));
+      if (mode == 1) MTX_TRY(launch_prefill_attention(e, l, rows, start_pos, slot, st));
+      else MTX_TRY(launch_attention(e, l, rows, st));
+
+      // h = x + rms_norm(dense(attn))
+      memset(&ea, 0, sizeof(ea));
+      ea.out = e->n;
+      ea.ld_out = E;
+      ss_args(ea, nullptr, nullptr);
+      gp.n = E;
+      gp.k = HD;
+      g_class = KC_OUTPROJ;
+      MTX_TRY(launch_rows<EPI_STORE_BF16>(e->tm_wo[l], xmap(pl_o, &XMaps::attn), gp, ea, pl_o, st));
+      g_class = KC_RMSNORM;
+      MTX_TRY(launch(post_norm_residual_kernel, dim3(rows), dim3(128), 0, st, (const bf16*)e->n, (const bf16*)e->x,
+                     static_cast<const bf16*>(e->w.post_attn_norm) + size_t(l) * E, e->h, e->rows_ss_h, e->max_r_tile, E, c.rms_eps));
+
+      // x = h + rms_norm(dense(gelu(dense(n2, wi_0)) * dense(n2, wi_1))),  n2 = rms_norm(h) (scale folded into w01)
+      memset(&ea, 0, sizeof(ea));
+      ea.out = e->act;
+      ea.ld_out = M;
+      ea.act_gelu = 1;
+      ss_args(ea, e->rows_ss_h, nullptr);
+      gp.n = 2 * M;
+      gp.k = E;
+      g_class = KC_MLP_UP;
+      MTX_TRY(launch_rows<EPI_SWIGLU>(e->tm_w01[l], xmap(pl_up, &XMaps::h), gp, ea, pl_up, st));
+      memset(&ea, 0, sizeof(ea));
+      ea.out = e->n;
+      ea.ld_out = E;
+      ss_args(ea, nullptr, nullptr);
+      gp.n = E;
+      gp.k = M;
+      g_class = KC_MLP_DOWN;
+      MTX_TRY(launch_rows<EPI_STORE_BF16>(e->tm_wout[l], xmap(pl_down, &XMaps::act), gp, ea, pl_down, st));
+      g_class = KC_RMSNORM;
+      MTX_TRY(launch(post_norm_residual_kernel, dim3(rows), dim3(128), 0, st, (const bf16*)e->n, (const bf16*)e->h,
+                     static_cast<const bf16*>(e->w.post_ffw_norm) + size_t(l) * E, e->x, e->rows_ss_x, e->max_r_tile, E, c.rms_eps));
+    }
+    if (want_logits)
+      MTX_TRY(launch(rmsnorm_kernel<false>, dim3(rows), dim3(128), 0, st, (const bf16*)e->x, (const int*)nullptr, (const bf16*)nullptr,
+                     static_cast<const bf16*>(e->w.final_norm), (bf16*)nullptr, e->n, E, c.rms_eps));
+  } else if (!mega) {
   const bf16* attn_norm = static_cast<const bf16*>(e->w.attn_norm);
   const bf16* mlp_norm = static_cast<const bf16*>(e->w.mlp_norm);
   if (fused_norm)
@@ -1099,8 +1216,12 @@ int mtx_engine_create(const mtx_model_config* cfg, mtx_engine** out) {
   cudaGetLastError();
   if (c.kv_quant != 0 && c.kv_quant != 1) return fail(MTX_ERR_ARG, "kv_quant must be 0 (bf16) or 1 (int8 per token and kv head)");
   if (c.kv_quant && c.head_dim != 64) return fail(MTX_ERR_UNSUPPORTED, "the int8 KV cache is implemented for head_dim 64");
+  if (c.decoder_block != 0 && c.decoder_block != 1) return fail(MTX_ERR_ARG, "decoder_block must be 0 (llama2) or 1 (gemma3)");
+  if (c.decoder_block == 1 && (c.kv_quant || !c.norm_scales_folded || c.sliding_window <= 0))
+    return fail(MTX_ERR_UNSUPPORTED, "the gemma3 block needs a bf16 KV cache, norm_scales_folded and a sliding_window");
   e->max_r_tile = round_rows(c.max_rows);
   if (c.kv_quant && e->max_r_tile < 128) e->max_r_tile = 128;  // every step of an int8 engine runs the 128-row-block GEMM
+  if (c.decoder_block == 1 && e->max_r_tile < 128) e->max_r_tile = 128;  // and so does every step of the gemma3 block
   e->qkv_n = (c.num_q_heads + 2 * c.num_kv_heads) * c.head_dim;
   e->attn_max_chunks = attn_max_chunks(c.max_prefill_len, c.max_target_len);
   e->rope_timescale_host.resize(c.head_dim / 2);
@@ -1108,6 +1229,12 @@ int mtx_engine_create(const mtx_model_config* cfg, mtx_engine** out) {
     // embeddings.py:270-275, evaluated in fp64 and rounded once
     const double fraction = 2.0 * double(i) / double(c.head_dim);
     e->rope_timescale_host[i] = float(double(c.rope_min_timescale) * pow(double(c.rope_max_timescale) / double(c.rope_min_timescale), fraction));
+  }
+  e->rope_timescale_w_host.resize(c.head_dim / 2);
+  for (int i = 0; i < c.head_dim / 2; ++i) {
+    const double fraction = 2.0 * double(i) / double(c.head_dim);
+    const double hi = c.local_rope_max_timescale > 0.0f ? double(c.local_rope_max_timescale) : double(c.rope_max_timescale);  // attentions.py:2085-2088
+    e->rope_timescale_w_host[i] = float(double(c.rope_min_timescale) * pow(hi / double(c.rope_min_timescale), fraction));
   }
   e->ws_bytes = layout_workspace(e).total;
   *out = e;
@@ -1129,6 +1256,8 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   if (workspace_bytes < e->ws_bytes) return fail(MTX_ERR_ARG, "workspace too small: %zu < %zu", workspace_bytes, e->ws_bytes);
   if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return fail(MTX_ERR_ARG, "workspace must be 1024-byte aligned");
   const mtx_model_config& c = e->cfg;
+  if (c.decoder_block == 1 && (!w->q_norm || !w->k_norm || !w->post_attn_norm || !w->post_ffw_norm))
+    return fail(MTX_ERR_ARG, "the gemma3 block needs q_norm, k_norm, post_attn_norm and post_ffw_norm");
   e->w = *w;
   e->s = *s;
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
@@ -1159,6 +1288,16 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   e->rd.work_items = reinterpret_cast<int*>(b + L.work_items);
   e->rd.work_count = reinterpret_cast<int*>(b + L.work_count);
   e->rope_timescale = reinterpret_cast<float*>(b + L.rope_timescale);
+  if (c.decoder_block == 1) {
+    e->rd.len0_w = reinterpret_cast<int*>(b + L.len0_w);
+    e->rd.ring_first_w = reinterpret_cast<int*>(b + L.ring_first_w);
+    e->rd.ring_len_w = reinterpret_cast<int*>(b + L.ring_len_w);
+    e->rd.rope_cs_w = reinterpret_cast<float2*>(b + L.rope_cs_w);
+    e->rd.work_items_w = reinterpret_cast<int*>(b + L.work_items_w);
+    e->rd.work_count_w = reinterpret_cast<int*>(b + L.work_count_w);
+    e->rope_timescale_w = reinterpret_cast<float*>(b + L.rope_timescale_w);
+    e->qkv_tmp = reinterpret_cast<bf16*>(b + L.qkv_tmp);
+  }
   e->part_score = reinterpret_cast<float*>(b + L.part_score);
   e->part_idx = reinterpret_cast<int*>(b + L.part_idx);
   e->part_raw = reinterpret_cast<float*>(b + L.part_raw);
@@ -1184,6 +1323,8 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   e->par_hist = reinterpret_cast<unsigned long long*>(b + L.par_hist);
   e->par_eq = reinterpret_cast<int*>(b + L.par_eq);
   MTX_CUDA(cudaMemcpy(e->rope_timescale, e->rope_timescale_host.data(), e->rope_timescale_host.size() * 4, cudaMemcpyHostToDevice));
+  if (c.decoder_block == 1)
+    MTX_CUDA(cudaMemcpy(e->rope_timescale_w, e->rope_timescale_w_host.data(), e->rope_timescale_w_host.size() * 4, cudaMemcpyHostToDevice));
 
   const int E = c.emb_dim, HD = c.num_q_heads * c.head_dim, M = c.mlp_dim, L_ = c.num_layers;
   e->tm_wqkv.resize(L_);

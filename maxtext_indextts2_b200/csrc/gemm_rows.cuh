@@ -145,7 +145,10 @@ __device__ __forceinline__ void rows_epi_swiglu(const EpiArgs& e, int N2, int r,
   for (int j = 0; j < 16; j += 2) {
     const uint32_t ga = pack_bf16x2(g[j], g[j + 1]), ub = pack_bf16x2(u[j], u[j + 1]);
     const float a0 = bf16_lo(ga), a1 = bf16_hi(ga);
-    const uint32_t sg = pack_bf16x2(__fdividef(1.0f, 1.0f + __expf(-a0)), __fdividef(1.0f, 1.0f + __expf(-a1)));
+    // gate: silu(a) = a * sigmoid(a), or (gemma3, linears.py:460 with "gelu" = flax nn.gelu) a * 0.5 (1 + tanh(sqrt(2/pi) (a + 0.044715 a^3)))
+    const uint32_t sg = e.act_gelu ? pack_bf16x2(0.5f * (1.0f + tanhf(0.7978845608028654f * (a0 + 0.044715f * a0 * a0 * a0))),
+                                                 0.5f * (1.0f + tanhf(0.7978845608028654f * (a1 + 0.044715f * a1 * a1 * a1))))
+                                   : pack_bf16x2(__fdividef(1.0f, 1.0f + __expf(-a0)), __fdividef(1.0f, 1.0f + __expf(-a1)));
     const uint32_t act = pack_bf16x2(a0 * bf16_lo(sg), a1 * bf16_hi(sg));
     o[j] = bf16_lo(act) * bf16_lo(ub);
     o[j + 1] = bf16_hi(act) * bf16_hi(ub);
@@ -421,8 +424,12 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           float v[16];
           ld16(c, v);
           if (!valid || nbase + c >= p.n) continue;
-          if (EPI == EPI_STORE_BF16) rows_epi_store(e, p.n, row, nbase + c, v);
-          else sq += rows_epi_residual(e, p.n, row, nbase + c, v);
+          if (EPI == EPI_STORE_BF16) {
+            rows_scale16(v, rs);  // (1 unless the input's RMSNorm is fused: ss_in)
+            rows_epi_store(e, p.n, row, nbase + c, v);
+          } else {
+            sq += rows_epi_residual(e, p.n, row, nbase + c, v);
+          }
         }
         if (EPI == EPI_RESIDUAL && e.ss_out != nullptr && valid) e.ss_out[tile * e.ss_pitch + row] = sq;
       } else if (EPI == EPI_SWIGLU) {
@@ -580,7 +587,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           }
         };
         const bool valid = row < p.rows;
-        const float rs = (valid && (EPI == EPI_SWIGLU || EPI == EPI_QKV_ROPE)) ? rows_rstd(e, row) : 1.0f;
+        const float rs = (valid && (EPI == EPI_SWIGLU || EPI == EPI_QKV_ROPE || EPI == EPI_STORE_BF16)) ? rows_rstd(e, row) : 1.0f;
         if (EPI == EPI_SWIGLU) {
           if ((c0 & 16) == 0) {
             float g[16], uu[16];
@@ -606,8 +613,12 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           ld16(c0, v);
           float sq = 0.0f;
           if (valid && tile * kTileN + c0 < p.n) {
-            if (EPI == EPI_STORE_BF16) rows_epi_store(e, p.n, row, tile * kTileN + c0, v);
-            else sq = rows_epi_residual(e, p.n, row, tile * kTileN + c0, v);
+            if (EPI == EPI_STORE_BF16) {
+              rows_scale16(v, rs);
+              rows_epi_store(e, p.n, row, tile * kTileN + c0, v);
+            } else {
+              sq = rows_epi_residual(e, p.n, row, tile * kTileN + c0, v);
+            }
           }
           if (EPI == EPI_RESIDUAL && e.ss_out != nullptr) {
             // the eight chunks of a row sit in eight consecutive lanes (the trip count is warp-uniform: rpc * 8 is a multiple of 32)

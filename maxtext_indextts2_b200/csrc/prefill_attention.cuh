@@ -34,6 +34,7 @@ struct PrefillAttnParams {
   int hq, hkv, T;
   int plane_row0;  // cache row of (layer, plane, kv head 0, position 0) in the K/V tensor maps; kv head h adds h * T
   float softcap;
+  int window;      // sliding_window_size of a local layer (attentions.py:624-631: key in (position - window, position]); 0 = none
 };
 
 __host__ inline size_t prefill_attn_smem_bytes(int D) {
@@ -62,6 +63,9 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
   const int last_row = (q0 + kPfQRows < p.rows ? q0 + kPfQRows : p.rows) - 1;
   const int n_keys = p.start_pos + last_row + 1;
   const int n_tiles = (n_keys + 63) / 64;
+  // sliding window: the lowest key the CTA's first position still sees
+  const int first_key = p.window > 0 ? max(0, p.start_pos + q0 - p.window + 1) : 0;
+  const int t_first = first_key / 64;
   const int plane_row = p.plane_row0 + h * p.T;
   uint8_t* k_tile = smem + size_t(warp) * 2 * kTileBytes;
   uint8_t* v_tile = k_tile + kTileBytes;
@@ -89,7 +93,7 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
   const bool v_lo = r_lo < p.rows, v_hi = r_hi < p.rows;
   const int pos_lo = p.start_pos + r_lo, pos_hi = p.start_pos + r_hi;  // a key at index j is visible to a row iff j <= its position
 
-  int t = warp;
+  int t = t_first + warp;
   if (t < n_tiles && lane == 0) {
     mbar_expect_tx(bar_k, kTileBytes);
 #pragma unroll
@@ -148,7 +152,7 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
       for (int ss = 0; ss < kSub; ++ss) tma_load_2d(k_tile + ss * 8192, &tm_k, ss * 64, plane_row + tn * 64, bar_k, kEvictLast);
     }
     // ---- causal mask + online softmax ----
-    const bool need_mask = key0 + 63 > p.start_pos + q0;  // some key of the tile lies beyond the CTA's first position
+    const bool need_mask = key0 + 63 > p.start_pos + q0 || p.window > 0;  // some key of the tile lies beyond the CTA's first position
     float tm0 = -INFINITY, tm1 = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -158,7 +162,8 @@ prefill_attn_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_const
         if (p.softcap != 0.0f) x = tanhf(x / p.softcap) * p.softcap;
         if (need_mask) {
           const int key = key0 + 8 * j + tid4 * 2 + (e & 1);
-          if (key > ((e & 2) ? pos_hi : pos_lo)) x = -INFINITY;
+          const int pos = (e & 2) ? pos_hi : pos_lo;
+          if (key > pos || (p.window > 0 && key <= pos - p.window)) x = -INFINITY;
         }
         sc[j][e] = x;
       }

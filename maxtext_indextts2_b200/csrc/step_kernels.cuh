@@ -19,6 +19,14 @@ struct RowDesc {
   float2* rope_cs;  // [max_rows, D/2] (cos, sin), bf16-rounded
   int* work_items;  // attention work list
   int* work_count;
+  // sliding-window layers (gemma3 local attention; PrepareArgs.window > 0): the valid rows INSIDE the window's two cache
+  // sub-ranges (AttnParams.skip0 / ring_off / ring_size), their work list, and the RoPE table of the local base
+  int* len0_w;
+  int* ring_first_w;
+  int* ring_len_w;
+  float2* rope_cs_w;
+  int* work_items_w;
+  int* work_count_w;
 };
 
 struct PrepareArgs {
@@ -35,6 +43,8 @@ struct PrepareArgs {
   int tiles_per_item;  // attention work-item size (attn_tiles_per_item)
   int emb_rows;        // token ids are clamped into [0, emb_rows) (0: off)
   const float* rope_timescale;  // [D/2] min * (max/min)^(2i/D), embeddings.py:270-275
+  int window;                     // sliding_window_size of the local layers (0: the model has none)
+  const float* rope_timescale_w;  // [D/2] the same table for local_rope_max_timescale (attentions.py:2085-2088)
   // persistent step kernel (step_persistent.cuh): counters reset here, attention tile partition
   unsigned int* grid_bar;  // grid-barrier arrival counter
   int* tile_prefix;        // [rows + 1] exclusive prefix of the per-row 64-row tile counts
@@ -57,7 +67,7 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
   griddep_wait();
   const int tid = threadIdx.x;
   const int R = a.T - a.P;
-  int chunks = 0;
+  int chunks = 0, chunks_w = 0;
   if (tid < a.rows) {
     int token, pos, plane, wr, l0, rf, rl;
     if (a.mode == 0) {
@@ -90,6 +100,22 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
     s_nt[tid] = attn_num_tiles(l0, rf, rl, R);
     chunks = (s_nt[tid] + a.tiles_per_item - 1) / a.tiles_per_item;
     s_pos[tid] = pos;
+    if (a.window > 0) {
+      // attentions.py:600-602,624-631 in AUTOREGRESSIVE mode: the window covers the last `window` CACHE INDICES of each segment
+      // (next_pos = kv_seq_len - 1): prefill rows [s0, P) and ring indices [o, R).  The valid ring rows inside [o, R) are again a
+      // circular range of the sub-ring of size R - o: [max(rf, o), min(rf + rl, R)) followed, when the valid range wraps past
+      // index o, by [o, rf + rl - R).  (Prefill chunks, mode 1, go through prefill_attn_kernel, which masks by position.)
+      const int s0 = a.P > a.window ? a.P - a.window : 0, o = R > a.window ? R - a.window : 0;
+      const int l0w = l0 > s0 ? l0 - s0 : 0;
+      const int a_lo = rf > o ? rf : o, a_hi = rf + rl < R ? rf + rl : R;
+      const int alen = a_hi > a_lo ? a_hi - a_lo : 0;
+      const int blen = rf + rl - R > o ? rf + rl - R - o : 0;
+      const int rfw = alen > 0 ? a_lo - o : 0, rlw = alen + blen;
+      rd.len0_w[tid] = a.mode == 0 ? l0w : l0;
+      rd.ring_first_w[tid] = rfw;
+      rd.ring_len_w[tid] = rlw;
+      chunks_w = (attn_num_tiles(a.mode == 0 ? l0w : l0, rfw, rlw, R - o) + a.tiles_per_item - 1) / a.tiles_per_item;
+    }
   }
   s_off[tid + 1] = chunks;
   if (tid == 0) s_off[0] = 0;
@@ -100,6 +126,10 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
       const int r = idx / half, i = idx - r * half;
       const float ang = float(s_pos[r]) / a.rope_timescale[i];
       rd.rope_cs[idx] = make_float2(bf16r(cosf(ang)), bf16r(sinf(ang)));
+      if (a.window > 0) {
+        const float angw = float(s_pos[r]) / a.rope_timescale_w[i];
+        rd.rope_cs_w[idx] = make_float2(bf16r(cosf(angw)), bf16r(sinf(angw)));
+      }
     }
   }
   if (a.grid_bar == nullptr) {  // the per-kernel path's attention work list (the persistent kernel cuts its own)
@@ -111,6 +141,20 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
       for (int c = 0; c < chunks; ++c) rd.work_items[base + c] = (tid << 16) | c;
     }
     if (tid == 0) *rd.work_count = s_off[a.rows];
+    if (a.window > 0) {  // the same list for the sliding-window layers
+      __syncthreads();
+      s_off[tid + 1] = chunks_w;
+      if (tid == 0) s_off[0] = 0;
+      __syncthreads();
+      if (tid == 0)
+        for (int i = 1; i <= 256; ++i) s_off[i] += s_off[i - 1];
+      __syncthreads();
+      if (tid < a.rows) {
+        const int base = s_off[tid];
+        for (int c = 0; c < chunks_w; ++c) rd.work_items_w[base + c] = (tid << 16) | c;
+      }
+      if (tid == 0) *rd.work_count_w = s_off[a.rows];
+    }
   }
   if (a.grid_bar != nullptr) {
     if (tid == 0) {

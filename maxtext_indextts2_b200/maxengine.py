@@ -33,6 +33,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import gemma3
 from . import parallel
 from . import params as params_lib
 from .common_types import DECODING_ACTIVE_SEQUENCE_INDICATOR
@@ -141,6 +142,8 @@ def pack_params(params: dict, config, device, vocab_shard: Optional[tuple] = Non
   bf = torch.bfloat16
   dev = lambda t: t.to(device=device, dtype=bf)
   wqkv, wo, w01, wout, an, mn = [], [], [], [], [], []
+  gemma3 = config.decoder_block == "gemma3"
+  qn, kn, pan, pfn = [], [], [], []
   for i in range(L):
     lp = p["decoder"][f"layers_{i}"]
     sa = lp["self_attention"]
@@ -153,8 +156,13 @@ def pack_params(params: dict, config, device, vocab_shard: Optional[tuple] = Non
     w1 = dev(lp["mlp"]["wi_1"]["kernel"]).t().reshape(M // 16, 16, E)
     w01.append(torch.stack([w0, w1], dim=1).reshape(2 * M, E).contiguous())
     wout.append(dev(lp["mlp"]["wo"]["kernel"]).t().contiguous())
-    an.append(dev(lp["pre_self_attention_layer_norm"]["scale"]))
+    an.append(dev(lp["pre_self_attention_norm" if gemma3 else "pre_self_attention_layer_norm"]["scale"]))
     mn.append(dev(lp["mlp"]["mlp_layer_norm"]["scale"]))
+    if gemma3:
+      qn.append(dev(sa["query_norm"]["scale"]))
+      kn.append(dev(sa["key_norm"]["scale"]))
+      pan.append(dev(lp["post_self_attention_norm"]["scale"]))
+      pfn.append(dev(lp["post_ffw_norm"]["scale"]))
   embedding = dev(p["token_embedder"]["embedding"]).contiguous()
   if config.logits_via_embedding:
     logits = embedding  # attend_on_embedding, embeddings.py:183-199
@@ -174,6 +182,9 @@ def pack_params(params: dict, config, device, vocab_shard: Optional[tuple] = Non
       final_norm=dev(p["decoder"]["decoder_norm"]["scale"]).contiguous(),
       logits=logits,
   )
+  if gemma3:
+    tensors.update(q_norm=torch.stack(qn).contiguous(), k_norm=torch.stack(kn).contiguous(),
+                   post_attn_norm=torch.stack(pan).contiguous(), post_ffw_norm=torch.stack(pfn).contiguous())
   return DeviceParams(tensors)
 
 
@@ -214,6 +225,8 @@ def random_device_params(config, device, seed: int = 0, norm_jitter: float = 0.0
       final_norm=scale((E,)),
       logits=embedding if config.logits_via_embedding else rn((V, E), 1.0 / math.sqrt(E)),
   )
+  if config.decoder_block == "gemma3":
+    tensors.update(q_norm=scale((L, D)), k_norm=scale((L, D)), post_attn_norm=scale((L, E)), post_ffw_norm=scale((L, E)))
   return DeviceParams(tensors)
 
 
@@ -282,6 +295,10 @@ class MaxEngine:
         embedding_rows=config.vocab_size,
         kv_quant=1 if config.quantize_kvcache else 0,
         norm_scales_folded=1 if config.fold_norm_scales else 0,
+        decoder_block=1 if config.decoder_block == "gemma3" else 0,
+        sliding_window=int(config.sliding_window_size) if config.decoder_block == "gemma3" else 0,
+        local_rope_max_timescale=float(config.local_rope_max_timescale),
+        query_scalar=float(gemma3.get_query_pre_attn_scalar(config)) if config.decoder_block == "gemma3" else 0.0,
     )
     _lib.check(self.lib.mtx_engine_create(ctypes.byref(self._cfg_struct), ctypes.byref(self._handle)))
     ws = self.lib.mtx_engine_workspace_bytes(self._handle)

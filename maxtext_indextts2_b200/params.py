@@ -1,4 +1,4 @@
-"""Parameter tree of the llama2-style decoder, with the reference's names and shapes.
+"""Parameter tree of the llama2-style decoder (and of the gemma3 block), with the reference's names and shapes.
 
 Tree (unscanned layout; SURVEY 5 "Checkpoint / resume", names from
 MaxText/layers/models.py:69, llama2.py:79,102,139, attentions.py:1865-1869,
@@ -16,6 +16,10 @@ linears.py:347,373,388, decoders.py:544,573)::
   params/decoder/layers_{i}/mlp/wo/kernel                [M, E]
   params/decoder/decoder_norm/scale                      [E]
   params/decoder/logits_dense/kernel                     [E, V]   (absent if logits_via_embedding)
+
+The gemma3 block (layers/gemma3.py:86-171, attentions.py:1872-1888) names its norms
+``pre_self_attention_norm`` / ``post_self_attention_norm`` / ``post_ffw_norm`` ([E] each; the MLP pre-norm stays
+``mlp/mlp_layer_norm``) and adds ``self_attention/query_norm`` and ``key_norm`` ([D]).
 
 Random init follows the reference's distributions (layers/initializers.py:31-43,
 models.py:68, linears.py:106, attentions.py:1510,1900-1904) but draws from
@@ -74,27 +78,42 @@ def init_params(config, seed: int | None = None) -> dict:
 
   params: dict = {"token_embedder": {"embedding": _normal(rng, (V, E), 1.0, dt)}}
   dec: dict = {}
+  gemma3 = config.decoder_block == "gemma3"
   for i in range(L):
     # attention kernels: variance_scaling(1.0, fan_in, normal); query additionally / sqrt(D)
     q = _normal(rng, (E, Hq, D), 1.0 / math.sqrt(E), torch.float32) / math.sqrt(D)
     k = _normal(rng, (E, Hkv, D), 1.0 / math.sqrt(E), dt)
     v = _normal(rng, (E, Hkv, D), 1.0 / math.sqrt(E), dt)
     o = _normal(rng, (Hq, D, E), 1.0 / math.sqrt(Hq * D), dt)
-    dec[f"layers_{i}"] = {
-        "pre_self_attention_layer_norm": {"scale": torch.ones(E, dtype=dt)},
-        "self_attention": {
-            "query": {"kernel": q.to(dt)},
-            "key": {"kernel": k},
-            "value": {"kernel": v},
-            "out": {"kernel": o},
-        },
-        "mlp": {
-            "mlp_layer_norm": {"scale": torch.ones(E, dtype=dt)},
-            "wi_0": {"kernel": _truncated_normal(rng, (E, M), 1.0 / math.sqrt(E), dt)},
-            "wi_1": {"kernel": _truncated_normal(rng, (E, M), 1.0 / math.sqrt(E), dt)},
-            "wo": {"kernel": _truncated_normal(rng, (M, E), 1.0 / math.sqrt(M), dt)},
-        },
+    attn = {
+        "query": {"kernel": q.to(dt)},
+        "key": {"kernel": k},
+        "value": {"kernel": v},
+        "out": {"kernel": o},
     }
+    mlp = {
+        "mlp_layer_norm": {"scale": torch.ones(E, dtype=dt)},
+        "wi_0": {"kernel": _truncated_normal(rng, (E, M), 1.0 / math.sqrt(E), dt)},
+        "wi_1": {"kernel": _truncated_normal(rng, (E, M), 1.0 / math.sqrt(E), dt)},
+        "wo": {"kernel": _truncated_normal(rng, (M, E), 1.0 / math.sqrt(M), dt)},
+    }
+    if gemma3:
+      # layers/gemma3.py:86-171: names of the four block norms; attentions.py:1872-1888: the q / k norms over head_dim
+      attn["query_norm"] = {"scale": torch.ones(D, dtype=dt)}
+      attn["key_norm"] = {"scale": torch.ones(D, dtype=dt)}
+      dec[f"layers_{i}"] = {
+          "pre_self_attention_norm": {"scale": torch.ones(E, dtype=dt)},
+          "self_attention": attn,
+          "post_self_attention_norm": {"scale": torch.ones(E, dtype=dt)},
+          "mlp": mlp,
+          "post_ffw_norm": {"scale": torch.ones(E, dtype=dt)},
+      }
+    else:
+      dec[f"layers_{i}"] = {
+          "pre_self_attention_layer_norm": {"scale": torch.ones(E, dtype=dt)},
+          "self_attention": attn,
+          "mlp": mlp,
+      }
   dec["decoder_norm"] = {"scale": torch.ones(E, dtype=dt)}
   if not config.logits_via_embedding:
     dec["logits_dense"] = {"kernel": _truncated_normal(rng, (E, V), 1.0 / math.sqrt(E), dt)}
@@ -171,6 +190,8 @@ def param_count(config) -> dict:
   E, Hq, Hkv, D = config.emb_dim, config.num_query_heads, config.num_kv_heads, config.head_dim
   M, V, L = config.mlp_dim, config.vocab_size, config.num_decoder_layers
   layer = E * Hq * D + 2 * E * Hkv * D + Hq * D * E + 3 * E * M + 2 * E
+  if config.decoder_block == "gemma3":
+    layer += 2 * E + 2 * D
   return {
       "layers": L * layer,
       "final_norm": E,

@@ -119,14 +119,32 @@ def _validate(keys: dict) -> None:
       raise ValueError("quantize_kvcache is implemented for head_dim=64")
   if keys["quantization"] not in ("", None):
     raise ValueError("quantization must be '' on this decode path (bf16 weights only)")
-  if keys["decoder_block"] != "llama2":
-    raise ValueError(f"decoder_block={keys['decoder_block']!r}: only the llama2 block is on this path")
+  if keys["decoder_block"] not in ("llama2", "gemma3"):
+    raise ValueError(f"decoder_block={keys['decoder_block']!r}: the llama2 and gemma3 blocks are on this path")
   if keys["dtype"] != "bfloat16":
     raise ValueError("dtype must be bfloat16 on this path")
   if keys["rope_type"] != "default":
     raise ValueError("only rope_type=default is on this path")
-  if keys["mlp_activations"] != ["silu", "linear"]:
-    raise ValueError("only mlp_activations=[silu, linear] is on this path")
+  if keys["decoder_block"] == "gemma3":
+    # layers/gemma3.py:45-197 + configs/models/gemma3-*.yml
+    if keys["mlp_activations"] != ["gelu", "linear"]:
+      raise ValueError("the gemma3 block is implemented with mlp_activations=[gelu, linear]")
+    if not (keys["use_post_attn_norm"] and keys["use_post_ffw_norm"]):
+      raise ValueError("the gemma3 block is implemented with use_post_attn_norm and use_post_ffw_norm (as every gemma3 model yml sets them)")
+    if keys["head_dim"] not in (64, 128):
+      raise ValueError(f"head_dim={keys['head_dim']}: the attention kernels of this path take head_dim 64 or 128 (gemma3-27b's geometry; "
+                       "gemma3-1b/4b/12b use 256)")
+    if keys["sliding_window_size"] <= 0:
+      raise ValueError("Sliding_window_size must be set if Local Sliding attention type")  # attentions.py:625-626
+    if not str(keys["model_name"]).startswith("gemma3"):
+      raise ValueError(f"Unsupported model name: {keys['model_name']}")  # gemma3.py:57 (query_pre_attn_scalar is chosen by model name)
+    if keys["quantize_kvcache"] or keys["scan_layers"] or int(keys["vocab_parallelism"]) != 1 or not keys["fold_norm_scales"]:
+      raise ValueError("the gemma3 block is implemented with a bf16 KV cache, scan_layers=False, vocab_parallelism=1 and fold_norm_scales=True")
+  else:
+    if keys["mlp_activations"] != ["silu", "linear"]:
+      raise ValueError("only mlp_activations=[silu, linear] is on this path")
+    if keys["use_post_attn_norm"] or keys["use_post_ffw_norm"] or keys["sliding_window_size"]:
+      raise ValueError("use_post_attn_norm / use_post_ffw_norm / sliding_window_size belong to the gemma3 block")
   if keys["max_target_length"] <= keys["max_prefill_predict_length"]:
     # inference/kvcache.py:408-412
     raise ValueError(

@@ -20,6 +20,11 @@ HyperBlaze456/maxtext-indextts2; the recipe is SURVEY.md Appendix A):
                           (local max/exp/sum), :1376-1397 (merge), :587-588 (AR mask),
                           :96-118 (mask application), :1399-1466 (two-segment call)
 * llama2 block            MaxText/layers/llama2.py:54-165
+* gemma3 block            MaxText/layers/gemma3.py:36-197 (5 local : 1 global pattern, post norms),
+                          attentions.py:2246-2265 (q/k RMSNorm before RoPE, query scalar after),
+                          :2085-2088 (local RoPE base), :604-631 (sliding-window mask; in
+                          AUTOREGRESSIVE mode the window is taken over CACHE INDICES of each segment,
+                          next_pos = kv_seq_len - 1), linears.py:40-51,460 (gelu = flax nn.gelu, tanh form)
 * gated MLP               MaxText/layers/linears.py:425-476
 * output head             MaxText/layers/decoders.py:537-589
 * sampling                MaxText/inference_utils.py:55-111
@@ -80,12 +85,13 @@ def prepare_weights(params: dict, config) -> OracleWeights:
   E, Hq, Hkv, D = config.emb_dim, config.num_query_heads, config.num_kv_heads, config.head_dim
   f = lambda t: t.to(torch.bfloat16).to(torch.float32)
   layers = []
+  gemma3 = config.decoder_block == "gemma3"
   for i in range(config.num_decoder_layers):
     lp = p["decoder"][f"layers_{i}"]
     sa = lp["self_attention"]
     layers.append(
         dict(
-            attn_scale=f(lp["pre_self_attention_layer_norm"]["scale"]),
+            attn_scale=f(lp["pre_self_attention_norm" if gemma3 else "pre_self_attention_layer_norm"]["scale"]),
             wq=f(sa["query"]["kernel"]).reshape(E, Hq * D),
             wk=f(sa["key"]["kernel"]).reshape(E, Hkv * D),
             wv=f(sa["value"]["kernel"]).reshape(E, Hkv * D),
@@ -96,6 +102,13 @@ def prepare_weights(params: dict, config) -> OracleWeights:
             wout=f(lp["mlp"]["wo"]["kernel"]),
         )
     )
+    if gemma3:
+      layers[-1].update(
+          q_norm=f(sa["query_norm"]["scale"]),
+          k_norm=f(sa["key_norm"]["scale"]),
+          post_attn_scale=f(lp["post_self_attention_norm"]["scale"]),
+          post_ffw_scale=f(lp["post_ffw_norm"]["scale"]),
+      )
   logits = None if config.logits_via_embedding else f(p["decoder"]["logits_dense"]["kernel"])
   return OracleWeights(
       embedding=f(p["token_embedder"]["embedding"]),
@@ -106,7 +119,24 @@ def prepare_weights(params: dict, config) -> OracleWeights:
 
 
 class DecodeOracle:
-  """Restates MaxEngine.prefill / insert / generate for the llama2 block."""
+  """Restates MaxEngine.prefill / insert / generate for the llama2 block and the gemma3 block."""
+
+  @property
+  def gemma3(self) -> bool:
+    return self.cfg.decoder_block == "gemma3"
+
+  def is_local(self, layer: int) -> bool:
+    """gemma3.py:36-48: five sliding-window layers, then one global layer."""
+    return self.gemma3 and layer % 6 != 5
+
+  def query_scalar(self) -> float:
+    """gemma3.py:51-58."""
+    cfg = self.cfg
+    if cfg.model_name in ("gemma3-4b", "gemma3-12b"):
+      return cfg.head_dim**-0.5
+    if cfg.model_name == "gemma3-27b":
+      return (cfg.base_emb_dim // cfg.base_num_query_heads) ** -0.5
+    raise ValueError(f"Unsupported model name: {cfg.model_name}")
 
   def __init__(self, config, params: dict, faithful: bool = True):
     self.cfg = config
@@ -147,14 +177,14 @@ class DecodeOracle:
     y = x @ w
     return y if out_f32 else self.r(y)
 
-  def rope(self, x, pos):
+  def rope(self, x, pos, max_timescale=None):
     """embeddings.py:270-315.  x [B,T,H,D]; pos [B,T] int."""
     D = x.shape[-1]
     half = D // 2
     # timescale = min * (max/min) ** (2i/D) (embeddings.py:270-275), evaluated in fp64 and
     # rounded once to fp32 so that every libm gives the same table
     fraction = 2 * torch.arange(0, half, dtype=torch.float64) / D
-    lo, hi = float(self.cfg.rope_min_timescale), float(self.cfg.rope_max_timescale)
+    lo, hi = float(self.cfg.rope_min_timescale), float(max_timescale or self.cfg.rope_max_timescale)
     timescale = (lo * (hi / lo) ** fraction).to(torch.float32)
     sinusoid = pos.to(torch.float32)[:, :, None, None] / timescale
     sin = self.r(torch.sin(sinusoid))
@@ -210,20 +240,61 @@ class DecodeOracle:
   # -- the block ----------------------------------------------------------------
 
   def _mlp(self, lw, h):
-    """linears.py:425-476 with mlp_activations [silu, linear]."""
+    """linears.py:425-476 with mlp_activations [silu, linear] (llama2) or [gelu, linear] (gemma3)."""
     n = self.rms_norm(h, lw["mlp_scale"])
     a = self.dense(n, lw["w0"])
-    a = self.r(a * self.r(torch.sigmoid(a)))  # jax.nn.silu on a bf16 array
+    if self.gemma3:
+      # flax nn.gelu = jax.nn.gelu(approximate=True): x * 0.5 * (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) on a bf16 array; the
+      # cdf factor is evaluated in fp32 and rounded once, then the product is rounded (as silu below)
+      cdf = 0.5 * (1.0 + torch.tanh(0.7978845608028654 * (a + 0.044715 * a * a * a)))
+      a = self.r(a * self.r(cdf))
+    else:
+      a = self.r(a * self.r(torch.sigmoid(a)))  # jax.nn.silu on a bf16 array
     b = self.dense(n, lw["w1"])
     return self.dense(self.r(a * b), lw["wout"])
 
-  def _qkv(self, lw, n, pos):
+  def _qkv(self, lw, n, pos, layer: int = 0):
     cfg = self.cfg
     B, T, _ = n.shape
     q = self.dense(n, lw["wq"]).reshape(B, T, cfg.num_query_heads, cfg.head_dim)
     k = self.dense(n, lw["wk"]).reshape(B, T, cfg.num_kv_heads, cfg.head_dim)
     v = self.dense(n, lw["wv"]).reshape(B, T, cfg.num_kv_heads, cfg.head_dim)
-    return self.rope(q, pos), self.rope(k, pos), v
+    if not self.gemma3:
+      return self.rope(q, pos), self.rope(k, pos), v
+    # attentions.py:2246-2265: RMSNorm over head_dim, RoPE (local layers: their own base, :2085-2088), query scalar
+    q, k = self.rms_norm(q, lw["q_norm"]), self.rms_norm(k, lw["k_norm"])
+    ts = None
+    if self.is_local(layer) and float(cfg.local_rope_max_timescale) > 0:
+      ts = float(cfg.local_rope_max_timescale)
+    q, k = self.rope(q, pos, ts), self.rope(k, pos, ts)
+    sc = self.query_scalar()
+    if sc and sc != 1.0:
+      q = self.r(q * sc)
+    return q, k, v
+
+  def _block(self, lw, x, a):
+    """Everything of a decoder layer after the attention op: llama2.py:139-165 / gemma3.py:132-176.  a [B,T,Hq*D]."""
+    o = self.dense(a, lw["wo"])
+    if self.gemma3:
+      o = self.rms_norm(o, lw["post_attn_scale"])
+    h = self.r(o + x)
+    m = self._mlp(lw, h)
+    if self.gemma3:
+      m = self.rms_norm(m, lw["post_ffw_scale"])
+    return self.r(m + h)
+
+  def _window_full(self, T: int):
+    """attentions.py:624-631 for a full sequence (next_pos = 0): col in (row - W, row]."""
+    W = int(self.cfg.sliding_window_size)
+    row, col = torch.arange(T)[:, None], torch.arange(T)[None, :]
+    return (col > row - W) & (col <= row)
+
+  def _window_ar(self, S: int):
+    """attentions.py:600-602,624-631 in AUTOREGRESSIVE mode: next_pos = kv_seq_len - 1 of the SEGMENT, so the window is the last
+    sliding_window_size cache indices of the prefill segment and of the AR ring, whatever the true positions are."""
+    W = int(self.cfg.sliding_window_size)
+    col = torch.arange(S)
+    return (col > S - 1 - W) & (col <= S - 1)
 
   def _output_head(self, x):
     """decoders.py:537-589."""
@@ -255,14 +326,14 @@ class DecodeOracle:
       mask = causal.expand(B, T, T)
     kvs = []
     rm = (lambda t: t) if self.softmax_f32 else self.r
-    for lw in self.w.layers:
+    for li, lw in enumerate(self.w.layers):
       n = self.rms_norm(x, lw["attn_scale"])
-      q, k, v = self._qkv(lw, n, pos)
+      q, k, v = self._qkv(lw, n, pos, li)
       kvs.append((k, v))
-      o, _, l = self._local_attention(q, k, v, mask)
+      lmask = mask & self._window_full(T)[None] if self.is_local(li) else mask
+      o, _, l = self._local_attention(q, k, v, lmask)
       a = rm(o / l)
-      h = self.r(x + self.dense(self.r(a).reshape(B, T, -1), lw["wo"]))
-      x = self.r(h + self._mlp(lw, h))
+      x = self._block(lw, x, self.r(a).reshape(B, T, -1))
     logits = self._output_head(x)
     return (logits, kvs) if return_kv else logits
 
@@ -349,14 +420,17 @@ class DecodeOracle:
     amask = (c["ar_segment_id"] == ACTIVE)[:, None, :]
     for l, lw in enumerate(self.w.layers):
       n = self.rms_norm(x, lw["attn_scale"])
-      q, k, v = self._qkv(lw, n, pos)
+      q, k, v = self._qkv(lw, n, pos, l)
       c["ar_key"][l][:, idx] = self.kv_quant(k[:, 0])  # kvcache.py:696-701 (quantised when quantize_kvcache: :658-718)
       c["ar_value"][l][:, idx] = self.kv_quant(v[:, 0])
-      o_p, m_p, l_p = self._local_attention(q, c["prefill_key"][l], c["prefill_value"][l], pmask)
-      o_a, m_a, l_a = self._local_attention(q, c["ar_key"][l], c["ar_value"][l], amask)
+      pm, am = pmask, amask
+      if self.is_local(l):
+        pm = pmask & self._window_ar(self.P)[None, None, :]
+        am = amask & self._window_ar(self.R)[None, None, :]
+      o_p, m_p, l_p = self._local_attention(q, c["prefill_key"][l], c["prefill_value"][l], pm)
+      o_a, m_a, l_a = self._local_attention(q, c["ar_key"][l], c["ar_value"][l], am)
       a = self._normalize_attention([o_p, o_a], [m_p, m_a], [l_p, l_a])
-      h = self.r(x + self.dense(self.r(a).reshape(B, 1, -1), lw["wo"]))
-      x = self.r(h + self._mlp(lw, h))
+      x = self._block(lw, x, self.r(a).reshape(B, 1, -1))
     c["ar_index"] = (idx + 1) % self.R  # kvcache.py:778
     c["ar_lengths"] += 1  # kvcache.py:779
     return self._output_head(x)

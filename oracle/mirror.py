@@ -43,6 +43,9 @@ def oracle_weights_from_device(dparams, cfg) -> ref.OracleWeights:
             wout=f(t["wout"][l]).t().contiguous(),
         )
     )
+    if cfg.decoder_block == "gemma3":
+      layers[-1].update(q_norm=f(t["q_norm"][l]), k_norm=f(t["k_norm"][l]), post_attn_scale=f(t["post_attn_norm"][l]),
+                        post_ffw_scale=f(t["post_ffw_norm"][l]))
   logits = None if cfg.logits_via_embedding else f(t["logits"]).t().contiguous()
   return ref.OracleWeights(embedding=f(t["embedding"]), layers=layers, final_scale=f(t["final_norm"]), logits=logits)
 

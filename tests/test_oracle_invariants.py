@@ -220,3 +220,58 @@ def test_log_prob_of_chosen_token():
   logits = torch.tensor([[[0.0, math.log(3.0)]]])
   lp = ref.log_prob_of_chosen_token(logits, torch.tensor([[1]]))
   assert abs(lp.item() - math.log(0.75)) < 1e-6
+
+
+# ---- gemma3 block (layers/gemma3.py:36-197) ----------------------------------------------------------------------
+
+
+def _gemma_cfg(**kw):
+  base = dict(model_name="gemma3-27b", base_num_decoder_layers=7, base_emb_dim=128, base_num_query_heads=4, base_num_kv_heads=2,
+              head_dim=64, base_mlp_dim=256, vocab_size=512, sliding_window_size=8, max_prefill_predict_length=16,
+              max_target_length=48, per_device_batch_size=2)
+  base.update(kw)
+  return small_config(**base)
+
+
+def test_gemma3_config_and_layer_pattern():
+  from maxtext_indextts2_b200 import gemma3, pyconfig
+
+  cfg = _gemma_cfg()
+  assert [gemma3.get_attention_type(i) for i in range(7)] == ["local_sliding"] * 5 + ["global", "local_sliding"]  # gemma3.py:36-48
+  assert gemma3.get_query_pre_attn_scalar(cfg) == (cfg.base_emb_dim // cfg.base_num_query_heads) ** -0.5         # gemma3.py:55-56
+  with pytest.raises(ValueError):
+    _gemma_cfg(model_name="default", decoder_block="gemma3", mlp_activations=["gelu", "linear"], use_post_attn_norm=True,
+               use_post_ffw_norm=True, logits_via_embedding=True)  # gemma3.py:57-58: the scalar is chosen by model name
+  with pytest.raises(ValueError):
+    pyconfig.initialize(None, model_name="gemma3-4b")  # head_dim 256
+
+
+def test_gemma3_ar_steps_equal_full_forward_when_the_window_covers_the_cache():
+  """tests/attention_test.py:361-406 for the gemma3 block.  With sliding_window_size >= the segment lengths the cache-index
+  window of AUTOREGRESSIVE mode (attentions.py:600-602) admits every valid row and equals the position window of the
+  full-sequence graph as long as the sequence is shorter than the window."""
+  cfg = _gemma_cfg(sliding_window_size=64)
+  params = make_params(cfg)
+  o = ref.DecodeOracle(cfg, params, faithful=False)
+  toks = random_tokens((1, 24), cfg.vocab_size, seed=9)
+  full = o.forward_full(toks)
+  state = o.init_decode_state()
+  prefix, _ = o.prefill(toks[0, :16], 16)
+  state = o.insert(prefix, state, 0)
+  torch.testing.assert_close(prefix["logits"][0, 0], full[0, 15], rtol=1e-4, atol=1e-4)
+  for t in range(16, 24):
+    state["tokens"][0] = int(toks[0, t])
+    logits = o.step_logits(state)
+    state["next_pos"] = state["next_pos"] + 1
+    torch.testing.assert_close(logits[0, 0], full[0, t], rtol=2e-4, atol=2e-4)
+
+
+def test_gemma3_local_layers_mask_by_cache_index_in_ar_mode():
+  """attentions.py:600-602,624-631: in AUTOREGRESSIVE mode next_pos = kv_seq_len - 1 of the segment, so a local layer sees the
+  last `sliding_window_size` INDICES of the prefill segment and of the ring."""
+  cfg = _gemma_cfg()
+  o = ref.DecodeOracle(cfg, make_params(cfg), faithful=False)
+  assert o._window_ar(16).nonzero()[:, 0].tolist() == list(range(8, 16))
+  assert o._window_ar(32).nonzero()[:, 0].tolist() == list(range(24, 32))
+  w = o._window_full(12)
+  assert w[11].nonzero()[:, 0].tolist() == list(range(4, 12)) and w[3].nonzero()[:, 0].tolist() == [0, 1, 2, 3]
