@@ -47,6 +47,7 @@ def parse_args():
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--batch", type=int, default=64, help="decode slots per GPU")
   ap.add_argument("--model", default="indextts2-t2s")
+  ap.add_argument("--layers", type=int, default=0, help="override base_num_decoder_layers (e.g. gemma3-27b geometry with 12 of its 62 layers)")
   ap.add_argument("--context-min", type=int, default=512)
   ap.add_argument("--context-max", type=int, default=1536)
   ap.add_argument("--prefill-len", type=int, default=0, help="override max_prefill_predict_length (BASELINE configs[3]: 4096)")
@@ -77,6 +78,8 @@ def make_config(args):
     kw["max_prefill_predict_length"] = args.prefill_len
   if args.target_len:
     kw["max_target_length"] = args.target_len
+  if args.layers:
+    kw["base_num_decoder_layers"] = args.layers
   if args.no_fold:
     kw["fold_norm_scales"] = False
   if args.kv_int8:
@@ -100,8 +103,9 @@ def context_lengths(args, cfg, rank=0):
   return prefill.astype(np.int64), ar.astype(np.int64)
 
 
-def algorithmic_bytes(cfg, batch, ctx_sum):
-  """weights once + valid KV rows + KV append + embedding rows + outputs."""
+def algorithmic_bytes(cfg, batch, ctx_sum, ctx_sum_local=None):
+  """weights once + valid KV rows + KV append + embedding rows + outputs.  `ctx_sum_local`: rows a sliding-window
+  layer reads (gemma3: five layers of six); the global layers read `ctx_sum`."""
   E, Hq, Hkv, D = cfg.emb_dim, cfg.num_query_heads, cfg.num_kv_heads, cfg.head_dim
   M, V, L = cfg.mlp_dim, cfg.vocab_size, cfg.num_decoder_layers
   w_layers = 2 * L * (E * Hq * D + 2 * E * Hkv * D + Hq * D * E + 3 * E * M)
@@ -110,13 +114,18 @@ def algorithmic_bytes(cfg, batch, ctx_sum):
   kv_row = L * 2 * Hkv * D * 2
   if cfg.quantize_kvcache:
     kv_row = L * 2 * Hkv * (D + 4)  # one byte per element + one fp32 scale per (token, kv head)
+  kv_read = int(ctx_sum) * kv_row
+  if cfg.decoder_block == "gemma3" and ctx_sum_local is not None:
+    n_local = sum(1 for l in range(L) if l % 6 != 5)
+    kv_read = (int(ctx_sum) * (L - n_local) + int(ctx_sum_local) * n_local) * (kv_row // L)
+    w_norm = 2 * (4 * L + 1) * E + 2 * 2 * L * D
   return {
       "weights": w_layers + w_norm + w_logits,
-      "kv_read": int(ctx_sum) * kv_row,
+      "kv_read": kv_read,
       "kv_write": batch * kv_row,
       "misc": batch * E * 2 + batch * 8,
       "logits_weights": w_logits,
-      "attention_per_layer": int(ctx_sum) * kv_row // L,
+      "attention_per_layer": kv_read // L,  # (mean over the layers: gemma3's local layers read fewer rows than its global ones)
   }
 
 
@@ -289,7 +298,9 @@ def workload_config(args, cfg, world=None):
   world = world or args.gpus
   per_gpu = args.batch // world if args.scaling == "strong" else args.batch
   return {
-      "workload": f"IndexTTS2-scale text-to-semantic GPT decode step (BASELINE configs[1]): L={cfg.num_decoder_layers} E={cfg.emb_dim} "
+      "workload": (f"IndexTTS2-scale text-to-semantic GPT decode step (BASELINE configs[1])" if cfg.decoder_block == "llama2" else
+                   f"{cfg.model_name} geometry, gemma3 block (not a BASELINE config), decode step") +
+                  f": L={cfg.num_decoder_layers} E={cfg.emb_dim} "
                   f"Hq={cfg.num_query_heads} Hkv={cfg.num_kv_heads} D={cfg.head_dim} M={cfg.mlp_dim} V={cfg.vocab_size}, greedy",
       "batch_per_gpu": per_gpu,
       "global_batch": per_gpu * world,
@@ -613,6 +624,18 @@ def main():
     prefill, ar = prefill[rank * B : (rank + 1) * B], ar[rank * B : (rank + 1) * B]
   state = engine.fill_synthetic_context(prefill, ar)
   ctx_sum = int((prefill + ar).sum()) + B  # the appended row is read too
+  ctx_sum_local = None
+  if cfg.decoder_block == "gemma3":
+    # rows inside the cache-index window of a local layer (attentions.py:600-602,624-631): prefill rows [P - W, P) and ring
+    # indices [R - W, R); the ring rows of slot s are the al[s] + 1 indices ending at the shared ring index
+    P_, R_, W_ = cfg.max_prefill_predict_length, cfg.max_target_length - cfg.max_prefill_predict_length, int(cfg.sliding_window_size)
+    idx = int(ar.max())
+    tot = 0
+    for s_ in range(B):
+      tot += max(0, int(prefill[s_]) - max(0, P_ - W_))
+      ring = (idx - np.arange(int(ar[s_]) + 1)) % R_
+      tot += int((ring >= max(0, R_ - W_)).sum())
+    ctx_sum_local = tot
   step_fn = lib.mtx_decode_step if args.no_graph else lib.mtx_decode_step_graph
   stream = torch.cuda.current_stream()
   sptr = ctypes.c_void_p(stream.cuda_stream)
@@ -689,7 +712,7 @@ def main():
       pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
-    ab = algorithmic_bytes(cfg, B, ctx_sum + B * args.steps / 2)
+    ab = algorithmic_bytes(cfg, B, ctx_sum + B * args.steps / 2, ctx_sum_local)
     step_bytes = ab["weights"] + ab["kv_read"] + ab["kv_write"] + ab["misc"]
     ms_per_step = elapsed_ms / args.steps
     tokens_per_s = world * B * args.steps / (elapsed_ms / 1e3)
