@@ -215,6 +215,9 @@ __device__ __forceinline__ void pk_grid_barrier(const PkParams& p, PkTail* tail,
   atomicAdd(p.grid_bar, 1u);
   const uint32_t target = k * gridDim.x;
   const long long t0 = clock64();
+  // (Neither polling harder nor polling less pays: four relaxed polls in flight per CTA, a quarter of a round trip apart, made
+  // every phase slower, 1.341 vs 1.280 ms/step -- the counter's L2 slice serves the arrivals and the polls -- and a pause of
+  // 128 / 384 clocks between polls gave 1.290 / 1.301 vs 1.284: profiles/r2ac_barrier_poll.txt, r2ad_barrier_pause.txt.)
   while (ld_acquire_gpu(p.grid_bar) < target) {
     if (clock64() - t0 > 4000000000LL) mtx_wait_timeout(2, int(k), 0);
   }
