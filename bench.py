@@ -670,18 +670,22 @@ def main():
   # ---- end to end through the public API with HOST buffers: this step's tokens in (pinned), result tokens out (pinned) ----
   host_in = torch.zeros(B, 1, dtype=torch.int32).pin_memory()
   host_out = torch.zeros(B, 3, dtype=torch.int32).pin_memory()
+  # The same workload as the device-timed loop: its contexts (a step gets ~0.2 us slower per step it has run at batch 64: every
+  # step appends a row to every slot), the same number of untimed steps before the timed ones.
+  state = engine.fill_synthetic_context(prefill, ar)
   host_in.copy_(state["tokens"].cpu())
-  for _ in range(2):
+  for _ in range(1 + max(3, args.warmup)):
     state, result = engine.generate_to_host(dparams, state, host_out, host_tokens=host_in)
     torch.cuda.synchronize()
   barrier()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record(stream)
+  hin, hout = host_in.numpy(), host_out.numpy()  # (views of the pinned buffers)
   for _ in range(args.steps):
-    # H2D of this step's input tokens, the step, D2H of the sampled tokens: one call, one stream sync per step
-    state, result = engine.generate_to_host(dparams, state, host_out, host_tokens=host_in)
-    stream.synchronize()  # the caller needs the tokens before the next step (detokenise / stop check)
-    host_in[:, 0] = host_out[:, 0]
+    # H2D of this step's input tokens, the step, D2H of the sampled tokens, and the wait for them: one call per step (the
+    # caller needs the tokens before the next step: detokenise / stop check)
+    state, result = engine.generate_to_host(dparams, state, host_out, host_tokens=host_in, sync=True)
+    hin[:, 0] = hout[:, 0]
   e1.record(stream)
   barrier()
   e2e_ms = e0.elapsed_time(e1)
@@ -780,7 +784,7 @@ def main():
             "ms_per_step": e2e_ms / args.steps,
             "h2d_bytes_per_step": B * 4,
             "d2h_bytes_per_step": B * 3 * 4,
-            "api": "MaxEngine.generate_to_host (mtx_decode_step_host): pinned host token buffer in, ResultTokens.data to a pinned host buffer, one stream sync per step",
+            "api": "MaxEngine.generate_to_host(sync=True) (mtx_decode_step_host_sync): pinned host token buffer in, ResultTokens.data to a pinned host buffer, the copies are nodes of the step's CUDA graph, one stream sync per step",
         },
         "gpu_launches": launches_per_step * args.steps,
         "launches_per_step": launches_per_step,

@@ -174,6 +174,9 @@ int mtx_decode_step_graph(mtx_engine* e, int rows, mtx_stream stream);
  * host, all enqueued on `stream`: the caller synchronises the stream once and reads result_host (offline_engine.py:612-614 copies
  * the result tokens to the host the same way). */
 int mtx_decode_step_host(mtx_engine* e, int rows, const int32_t* tokens_host, int32_t* result_host, float* log_prob_host, mtx_stream stream);
+/* With pinned buffers the copies are nodes of the step's graph (one graph per set of buffers: reuse them), so the call above is ONE
+ * driver call.  This variant also waits for the stream: result_host is valid on return. */
+int mtx_decode_step_host_sync(mtx_engine* e, int rows, const int32_t* tokens_host, int32_t* result_host, float* log_prob_host, mtx_stream stream);
 
 /* Vocab-parallel logits: this process holds `vocab_size` rows of the logits matrix starting
  * at `vocab_offset`.  mtx_decode_step_candidates runs the whole step but, instead of committing a token,

@@ -164,6 +164,8 @@ def _declare(lib) -> None:
   lib.mtx_decode_step_graph.argtypes = [vp, i32, vp]
   lib.mtx_decode_step_host.restype = i32
   lib.mtx_decode_step_host.argtypes = [vp, i32, vp, vp, vp, vp]
+  lib.mtx_decode_step_host_sync.restype = i32
+  lib.mtx_decode_step_host_sync.argtypes = [vp, i32, vp, vp, vp, vp]
   lib.mtx_decode_step_candidates.restype = i32
   lib.mtx_decode_step_candidates.argtypes = [vp, i32, vp, vp]
   lib.mtx_sample_logits.restype = i32

@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+#include <tuple>
+
 #include "../../include/mtx_b200.h"
 #include "attention.cuh"
 #include "gemm_rows.cuh"
@@ -358,6 +360,15 @@ struct mtx_engine {
   // graphs
   cudaStream_t cap_stream = nullptr;
   std::map<int, cudaGraphExec_t> graphs;
+  // mtx_decode_step_host: the step's graph with the host copies as nodes, keyed by (rows, tokens, result, log-prob pointers)
+  struct HostKey {
+    int rows;
+    const void *tok, *res, *lp;
+    bool operator<(const HostKey& o) const {
+      return std::tie(rows, tok, res, lp) < std::tie(o.rows, o.tok, o.res, o.lp);
+    }
+  };
+  std::map<HostKey, cudaGraphExec_t> host_graphs;
 };
 
 namespace {
@@ -1244,6 +1255,7 @@ int mtx_engine_create(const mtx_model_config* cfg, mtx_engine** out) {
 int mtx_engine_destroy(mtx_engine* e) {
   if (e == nullptr) return MTX_OK;
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : e->host_graphs) cudaGraphExecDestroy(kv.second);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   delete e;
   return MTX_OK;
@@ -1262,6 +1274,8 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   e->s = *s;
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   e->graphs.clear();
+  for (auto& kv : e->host_graphs) cudaGraphExecDestroy(kv.second);
+  e->host_graphs.clear();
   for (auto& m : e->xmaps) m.built = false;
   // (re)binding rewrites the workspace: wait for everything the device still runs, on any stream, before and after
   MTX_CUDA(cudaDeviceSynchronize());
@@ -1413,6 +1427,8 @@ int mtx_engine_set_sampling(mtx_engine* e, int strategy, int top_k, float nucleu
   e->temperature = temperature;
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   e->graphs.clear();
+  for (auto& kv : e->host_graphs) cudaGraphExecDestroy(kv.second);
+  e->host_graphs.clear();
   return MTX_OK;
 }
 
@@ -1451,11 +1467,64 @@ int mtx_decode_step_host(mtx_engine* e, int rows, const int32_t* tokens_host, in
   if (!e || !e->bound || !result_host) return fail(MTX_ERR_ARG, "engine is not bound / null result buffer");
   if (rows < 1 || rows > e->cfg.max_rows) return fail(MTX_ERR_ARG, "rows %d outside [1, %d]", rows, e->cfg.max_rows);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (tokens_host != nullptr) MTX_CUDA(cudaMemcpyAsync(e->s.tokens, tokens_host, size_t(rows) * 4, cudaMemcpyHostToDevice, st));
-  MTX_TRY(mtx_decode_step_graph(e, rows, stream));
-  MTX_CUDA(cudaMemcpyAsync(result_host, e->s.result, size_t(rows) * 12, cudaMemcpyDeviceToHost, st));
-  if (log_prob_host != nullptr && e->s.log_prob != nullptr)
-    MTX_CUDA(cudaMemcpyAsync(log_prob_host, e->s.log_prob, size_t(rows) * 4, cudaMemcpyDeviceToHost, st));
+  const bool want_lp = log_prob_host != nullptr && e->s.log_prob != nullptr;
+  auto copies_in = [&](cudaStream_t s2) -> int {
+    if (tokens_host != nullptr) MTX_CUDA(cudaMemcpyAsync(e->s.tokens, tokens_host, size_t(rows) * 4, cudaMemcpyHostToDevice, s2));
+    return MTX_OK;
+  };
+  auto copies_out = [&](cudaStream_t s2) -> int {
+    MTX_CUDA(cudaMemcpyAsync(result_host, e->s.result, size_t(rows) * 12, cudaMemcpyDeviceToHost, s2));
+    if (want_lp) MTX_CUDA(cudaMemcpyAsync(log_prob_host, e->s.log_prob, size_t(rows) * 4, cudaMemcpyDeviceToHost, s2));
+    return MTX_OK;
+  };
+  // Pinned buffers (what a serving loop reuses every step): ONE graph holds the copy in, the step's kernels and the copies
+  // out, so a step is one driver call.  Pageable buffers cannot be captured: three calls.
+  auto pinned = [](const void* ptr) {
+    if (ptr == nullptr) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+  };
+  const mtx_engine::HostKey key{rows, tokens_host, result_host, want_lp ? log_prob_host : nullptr};
+  auto it = e->host_graphs.find(key);
+  if (it == e->host_graphs.end()) {
+    if (!(pinned(tokens_host) && pinned(result_host) && (!want_lp || pinned(log_prob_host))) || env_int("MTX_HOST_GRAPH", 1) == 0) {
+      MTX_TRY(copies_in(st));
+      MTX_TRY(mtx_decode_step_graph(e, rows, stream));
+      return copies_out(st);
+    }
+    if (!e->cap_stream) MTX_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    MTX_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int rc = copies_in(e->cap_stream);
+    if (rc == MTX_OK) rc = enqueue_step(e, 0, rows, nullptr, 0, 0, 1, nullptr, nullptr, e->cap_stream);
+    if (rc == MTX_OK) rc = copies_out(e->cap_stream);
+    const cudaError_t end = cudaStreamEndCapture(e->cap_stream, &graph);
+    if (rc != MTX_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (end != cudaSuccess) return fail(MTX_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(end));
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t inst = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (inst != cudaSuccess) return fail(MTX_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(inst));
+    if (e->host_graphs.size() >= 16) {  // a caller cycling through buffers: do not grow without bound
+      for (auto& kv : e->host_graphs) cudaGraphExecDestroy(kv.second);
+      e->host_graphs.clear();
+    }
+    it = e->host_graphs.emplace(key, exec).first;
+  }
+  MTX_CUDA(cudaGraphLaunch(it->second, st));
+  return MTX_OK;
+}
+
+int mtx_decode_step_host_sync(mtx_engine* e, int rows, const int32_t* tokens_host, int32_t* result_host, float* log_prob_host, mtx_stream stream) {
+  MTX_TRY(mtx_decode_step_host(e, rows, tokens_host, result_host, log_prob_host, stream));
+  MTX_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   return MTX_OK;
 }
 
@@ -1940,6 +2009,8 @@ int mtx_engine_rebind_state(mtx_engine* e, const mtx_decode_state* s) {
   e->s = *s;
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   e->graphs.clear();
+  for (auto& kv : e->host_graphs) cudaGraphExecDestroy(kv.second);
+  e->host_graphs.clear();
   if (c.kv_quant) return fail(MTX_ERR_UNSUPPORTED, "mtx_engine_rebind_state with an int8 KV cache: bind again instead");
   if (kv_moved) {
     const uint64_t kv_rows = uint64_t(c.num_layers) * c.num_slots * c.num_kv_heads * c.max_target_len;

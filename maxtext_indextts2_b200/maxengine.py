@@ -612,27 +612,37 @@ class MaxEngine:
     return decode_state, result
 
   def generate_to_host(self, params: DeviceParams, decode_state: dict, host_result: torch.Tensor, host_tokens: Optional[torch.Tensor] = None,
-                       host_log_prob: Optional[torch.Tensor] = None):
+                       host_log_prob: Optional[torch.Tensor] = None, sync: bool = False):
     """``generate`` for a serving loop that holds its tokens on the host (JetStream / OfflineEngine copy every step's
-    ResultTokens to the host: offline_engine.py:612-614): one C call enqueues the host -> device copy of this step's input tokens
-    (`host_tokens` [B,1] int32 pinned, or None to continue from decode_state["tokens"]), the step's CUDA-graph replay and the
-    device -> host copy of ResultTokens.data into `host_result` [B,3] int32 pinned.  Nothing synchronises: the caller waits on the
-    current stream and reads `host_result`.  Returns (decode_state, ResultTokens over the host buffers)."""
+    ResultTokens to the host: offline_engine.py:612-614): one C call -- with pinned buffers one graph launch -- does the host ->
+    device copy of this step's input tokens (`host_tokens` [B,1] int32 pinned, or None to continue from decode_state["tokens"]),
+    the step, and the device -> host copy of ResultTokens.data into `host_result` [B,3] int32 pinned.  `sync=True` also waits
+    for the stream inside that call (`host_result` is valid on return); otherwise the caller waits on the current stream.
+    Returns (decode_state, ResultTokens over the host buffers)."""
     if decode_state is not self._state:
       raise ValueError("decode_state must be the dict returned by this engine's init_decode_state (it is donated)")
-    if self._vp_world > 1:
-      raise ValueError("generate_to_host is the batch-partitioned path; the vocab-parallel mode goes through generate()")
-    self._bind(params)
-    B = self.max_concurrent_decodes
-    for t, n in ((host_result, 3 * B), (host_tokens, B), (host_log_prob, B)):
-      if t is not None and (t.is_cuda or not t.is_contiguous() or t.numel() != n or t.element_size() != 4):
-        raise ValueError("host buffers must be contiguous 4-byte CPU tensors of B*3 (result), B (tokens), B (log-probs) elements")
-    _lib.check(
-        self.lib.mtx_decode_step_host(
-            self._handle, B, ctypes.c_void_p(host_tokens.data_ptr()) if host_tokens is not None else None,
-            ctypes.c_void_p(host_result.data_ptr()), ctypes.c_void_p(host_log_prob.data_ptr()) if host_log_prob is not None else None,
-            self._stream()))
-    return decode_state, ResultTokens(data=host_result, log_prob=host_log_prob)
+    key = (id(params), id(host_result), id(host_tokens), id(host_log_prob), sync)
+    call = self._host_call if getattr(self, "_host_call_key", None) == key and self._bound_params is params else None
+    if call is None:  # (validated once per set of buffers: a serving loop passes the same ones every step)
+      if self._vp_world > 1:
+        raise ValueError("generate_to_host is the batch-partitioned path; the vocab-parallel mode goes through generate()")
+      self._bind(params)
+      B = self.max_concurrent_decodes
+      for t, n in ((host_result, 3 * B), (host_tokens, B), (host_log_prob, B)):
+        if t is not None and (t.is_cuda or not t.is_contiguous() or t.numel() != n or t.element_size() != 4):
+          raise ValueError("host buffers must be contiguous 4-byte CPU tensors of B*3 (result), B (tokens), B (log-probs) elements")
+      fn = self.lib.mtx_decode_step_host_sync if sync else self.lib.mtx_decode_step_host
+      args = (self._handle, B, ctypes.c_void_p(host_tokens.data_ptr()) if host_tokens is not None else None,
+              ctypes.c_void_p(host_result.data_ptr()), ctypes.c_void_p(host_log_prob.data_ptr()) if host_log_prob is not None else None)
+      result = ResultTokens(data=host_result, log_prob=host_log_prob)
+      keep = (params, host_result, host_tokens, host_log_prob)  # the ids above stay unique while these are alive
+      call = (fn, args, result, keep)
+      self._host_call, self._host_call_key = call, key
+    fn, args, result, _ = call
+    rc = fn(*args, self._stream())
+    if rc != 0:
+      _lib.check(rc)
+    return decode_state, result
 
   def candidate_buffer(self, rows: int) -> torch.Tensor:
     """This rank's payload of the vocab-parallel all-gather: [5, rows] (greedy / weighted: the shard's winner per row) or

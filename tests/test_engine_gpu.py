@@ -324,21 +324,23 @@ def test_generate_to_host_matches_generate():
   params = make_params(cfg)
   prompts = random_tokens((3, 16), cfg.vocab_size, seed=8)
   runs = []
-  for use_host in (False, True):
+  for use_host in (False, True, "sync", "pageable"):
     engine = maxengine.MaxEngine(cfg)
     dparams = engine.load_params(params)
     state = engine.init_decode_state()
     for slot, n in enumerate((16, 4, 9)):
       prefix, _ = engine.prefill(params=dparams, padded_tokens=prompts[slot], true_length=n)
       state = engine.insert(prefix, state, slot)
-    host_out = torch.zeros(3, 3, dtype=torch.int32).pin_memory()
-    host_lp = torch.zeros(3, 1, dtype=torch.float32).pin_memory()
-    host_in = state["tokens"].cpu().pin_memory()
+    pin = (lambda t: t) if use_host == "pageable" else (lambda t: t.pin_memory())  # pinned: the copies are graph nodes
+    host_out = pin(torch.zeros(3, 3, dtype=torch.int32))
+    host_lp = pin(torch.zeros(3, 1, dtype=torch.float32))
+    host_in = pin(state["tokens"].cpu())
     toks = []
     for step in range(6):
       if use_host:
-        state, res = engine.generate_to_host(dparams, state, host_out, host_tokens=host_in, host_log_prob=host_lp)
-        torch.cuda.synchronize()
+        state, res = engine.generate_to_host(dparams, state, host_out, host_tokens=host_in, host_log_prob=host_lp, sync=use_host == "sync")
+        if use_host != "sync":
+          torch.cuda.synchronize()
         assert res.data is host_out
         host_in[:, 0] = host_out[:, 0]
         toks.append((host_out.clone(), host_lp.clone()))
@@ -348,6 +350,7 @@ def test_generate_to_host_matches_generate():
     runs.append(toks)
     with pytest.raises(ValueError):
       engine.generate_to_host(dparams, state, torch.zeros(2, 3, dtype=torch.int32))
-  for (da, la), (db, lb) in zip(*runs):
-    assert torch.equal(da, db)
-    torch.testing.assert_close(la, lb, rtol=0, atol=0)
+  for other in runs[1:]:
+    for (da, la), (db, lb) in zip(runs[0], other):
+      assert torch.equal(da, db)
+      torch.testing.assert_close(la, lb, rtol=0, atol=0)
