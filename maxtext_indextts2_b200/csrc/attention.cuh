@@ -56,6 +56,7 @@ struct AttnParams {
   int skip0;      // first prefill row of the window (0: no window)
   int ring_off;   // first ring index of the window (0: no window)
   int ring_size;  // ring indices in the window (0: the whole ring, T - P)
+  const int* skip0_rows;  // [rows] or null: per-row addition to skip0 (prefill positions run as decode rows: position window)
 };
 
 struct TileLoc { int p0, cnt; };
@@ -172,6 +173,7 @@ __device__ __forceinline__ void attn_process_items(const CUtensorMap& tm_k, cons
     const int h = item % p.hkv;
     const int r = packed >> 16, chunk = packed & 0xffff;
     const int len0 = p.len0[r], rf = p.ring_first[r], rl = p.ring_len[r];
+    const int skip0 = p.skip0 + (p.skip0_rows != nullptr ? p.skip0_rows[r] : 0);
     const int nt = attn_num_tiles(len0, rf, rl, R);
     const int n_chunks = (nt + TPI - 1) / TPI;
     const int t_begin = chunk * TPI, t_end = min(nt, t_begin + TPI);
@@ -181,7 +183,7 @@ __device__ __forceinline__ void attn_process_items(const CUtensorMap& tm_k, cons
 
     // first tile of this warp: start both loads before touching Q
     int t = t_begin + warp;
-    TileLoc loc = attn_tile(t < t_end ? t : nt, len0, rf, rl, p.P, R, p.skip0, p.ring_off);  // t >= nt gives an empty tile
+    TileLoc loc = attn_tile(t < t_end ? t : nt, len0, rf, rl, p.P, R, skip0, p.ring_off);  // t >= nt gives an empty tile
     if (t < t_end && lane == 0) {
       mbar_expect_tx(bar_k, kTileBytes);
 #pragma unroll
@@ -214,7 +216,7 @@ __device__ __forceinline__ void attn_process_items(const CUtensorMap& tm_k, cons
     for (; t < t_end; t += kAttnWarps) {
       const int cnt = loc.cnt;
       const int tn = t + kAttnWarps;
-      const TileLoc nloc = attn_tile(tn < t_end ? tn : nt, len0, rf, rl, p.P, R, p.skip0, p.ring_off);
+      const TileLoc nloc = attn_tile(tn < t_end ? tn : nt, len0, rf, rl, p.P, R, skip0, p.ring_off);
       // ---- S = Q K^T over the 64 rows of the tile ----
       float s[8][4];
 #pragma unroll

@@ -15,6 +15,7 @@
 
 #include "../../include/mtx_b200.h"
 #include "attention.cuh"
+#include "attention_wide.cuh"
 #include "gemm_rows.cuh"
 #include "gemm_umma.cuh"
 #include "gemma3_kernels.cuh"
@@ -376,6 +377,7 @@ namespace {
 struct WsLayout {
   size_t x, h, n, q, attn, act, attn_part_o, attn_part_ml, attn_tickets;
   size_t token, pos, plane, write_row, len0, ring_first, ring_len, rope_cs, work_items, work_count, rope_timescale;
+  size_t skip_w;
   size_t len0_w, ring_first_w, ring_len_w, rope_cs_w, work_items_w, work_count_w, rope_timescale_w, qkv_tmp;
   size_t part_score, part_idx, part_raw, part_max, part_sum, grid_bar;
   size_t pk_tables, pk_part_ws, pk_ss_x, pk_ss_h, pk_attn_part_o, pk_tile_prefix, pk_attn_info;
@@ -419,6 +421,7 @@ WsLayout layout_workspace(const mtx_engine* e) {
     L.len0_w = take(rt * 4);
     L.ring_first_w = take(rt * 4);
     L.ring_len_w = take(rt * 4);
+    L.skip_w = take(rt * 4);
     L.rope_cs_w = take(rt * (c.head_dim / 2) * 8);
     L.work_items_w = take(size_t(c.max_rows) * e->attn_max_chunks * 4);
     L.work_count_w = take(4);
@@ -478,7 +481,7 @@ int get_xmaps(mtx_engine* e, int r_tile, XMaps** out) {
 // gemma3.py:36-48: layers 0..4 of every six use sliding-window attention (and the local RoPE base), the sixth is global.
 bool layer_is_local(const mtx_engine* e, int layer) { return e->cfg.decoder_block == 1 && layer % 6 != 5; }
 
-int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st) {
+int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st, int mode = 0) {
   const mtx_model_config& c = e->cfg;
   AttnParams p;
   memset(&p, 0, sizeof(p));
@@ -497,9 +500,14 @@ int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st) {
     p.ring_len = e->rd.ring_len_w;
     p.work_items = e->rd.work_items_w;
     p.work_count = e->rd.work_count_w;
-    p.skip0 = c.max_prefill_len > W ? c.max_prefill_len - W : 0;
-    p.ring_off = R > W ? R - W : 0;
-    p.ring_size = R - p.ring_off;
+    if (mode == 0) {
+      p.skip0 = c.max_prefill_len > W ? c.max_prefill_len - W : 0;
+      p.ring_off = R > W ? R - W : 0;
+      p.ring_size = R - p.ring_off;
+    } else {
+      p.skip0_rows = e->rd.skip_w;  // prompt positions as decode rows: the window is by position
+      p.ring_size = R - (R > W ? R - W : 0);  // (no ring rows in prefill; the tile counts were made for this ring size)
+    }
   }
   p.part_o = e->attn_part_o;
   p.part_ml = e->attn_part_ml;
@@ -525,6 +533,16 @@ int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st) {
     if (grid_q > e->num_sms * 4) grid_q = e->num_sms * 4;
     return launch(decode_attn_q8_kernel, dim3(grid_q), dim3(kAttnThreads), smem_q, st, e->tm_kq, e->tm_vq, p, (const float*)e->s.k_scale,
                   (const float*)e->s.v_scale);
+  }
+  if (c.head_dim == 256) {  // wide heads: the transposed kernel (attention_wide.cuh), one CTA of three warps per SM
+    static bool attr_set = false;
+    if (!attr_set) {
+      MTX_CUDA(cudaFuncSetAttribute(decode_attn_wide_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_wide_smem_bytes(256))));
+      attr_set = true;
+    }
+    int grid_w = rows * c.num_kv_heads * attn_max_chunks(c.max_prefill_len, c.max_target_len, p.tiles_per_item);
+    if (grid_w > e->num_sms) grid_w = e->num_sms;
+    return launch(decode_attn_wide_kernel<256>, dim3(grid_w), dim3(kWideThreads), attn_wide_smem_bytes(256), st, e->tm_k, e->tm_v, p);
   }
   if (c.head_dim == 64) return launch(decode_attn_kernel<64>, dim3(grid), dim3(kAttnThreads), smem, st, e->tm_k, e->tm_v, p);
   return launch(decode_attn_kernel<128>, dim3(grid), dim3(kAttnThreads), smem, st, e->tm_k, e->tm_v, p);
@@ -890,8 +908,8 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
       // empty) gets no work item: its attention output is defined as zero.  (The reference softmaxes the all-masked scores, i.e.
       // averages every allocated cache row, valid or not: nothing a caller can rely on.)
       if (mode == 0 && local) MTX_CUDA(cudaMemsetAsync(e->attn, 0, size_t(rows) * HD * 2, st));
-      if (mode == 1) MTX_TRY(launch_prefill_attention(e, l, rows, start_pos, slot, st));
-      else MTX_TRY(launch_attention(e, l, rows, st));
+      if (mode == 1 && c.head_dim != 256) MTX_TRY(launch_prefill_attention(e, l, rows, start_pos, slot, st));
+      else MTX_TRY(launch_attention(e, l, rows, st, mode));  // (head_dim 256: prompt positions run as decode rows)
 
       // h = x + rms_norm(dense(attn))
       memset(&ea, 0, sizeof(ea));
@@ -1210,7 +1228,9 @@ uint64_t mtx_launch_count(void) { return g_launches.load(); }
 int mtx_engine_create(const mtx_model_config* cfg, mtx_engine** out) {
   if (cfg == nullptr || out == nullptr) return fail(MTX_ERR_ARG, "null argument");
   const mtx_model_config& c = *cfg;
-  if (c.head_dim != 64 && c.head_dim != 128) return fail(MTX_ERR_UNSUPPORTED, "head_dim %d: only 64 and 128", c.head_dim);
+  if (c.head_dim != 64 && c.head_dim != 128 && !(c.head_dim == 256 && c.decoder_block == 1))
+    return fail(MTX_ERR_UNSUPPORTED, "head_dim %d: 64 and 128 (and 256 for the gemma3 block)", c.head_dim);
+  if (c.head_dim == 256 && c.num_q_heads / c.num_kv_heads > 8) return fail(MTX_ERR_UNSUPPORTED, "head_dim 256 needs at most 8 query heads per kv head");
   if (c.num_q_heads % c.num_kv_heads != 0 || c.num_q_heads / c.num_kv_heads > 16)
     return fail(MTX_ERR_UNSUPPORTED, "query heads per kv head must divide evenly and be <= 16");
   if (c.emb_dim % 64 != 0 || c.mlp_dim % 64 != 0 || (c.num_q_heads * c.head_dim) % 64 != 0)
@@ -1306,6 +1326,7 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
     e->rd.len0_w = reinterpret_cast<int*>(b + L.len0_w);
     e->rd.ring_first_w = reinterpret_cast<int*>(b + L.ring_first_w);
     e->rd.ring_len_w = reinterpret_cast<int*>(b + L.ring_len_w);
+    e->rd.skip_w = reinterpret_cast<int*>(b + L.skip_w);
     e->rd.rope_cs_w = reinterpret_cast<float2*>(b + L.rope_cs_w);
     e->rd.work_items_w = reinterpret_cast<int*>(b + L.work_items_w);
     e->rd.work_count_w = reinterpret_cast<int*>(b + L.work_count_w);

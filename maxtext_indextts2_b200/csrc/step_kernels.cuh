@@ -24,6 +24,7 @@ struct RowDesc {
   int* len0_w;
   int* ring_first_w;
   int* ring_len_w;
+  int* skip_w;  // per-row first visible cache row of a prefill position (mode 1: position window), 0 for decode rows
   float2* rope_cs_w;
   int* work_items_w;
   int* work_count_w;
@@ -111,10 +112,14 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
       const int alen = a_hi > a_lo ? a_hi - a_lo : 0;
       const int blen = rf + rl - R > o ? rf + rl - R - o : 0;
       const int rfw = alen > 0 ? a_lo - o : 0, rlw = alen + blen;
-      rd.len0_w[tid] = a.mode == 0 ? l0w : l0;
+      // mode 1 (a prompt position run as a decode row: head_dim 256, which prefill_attn_kernel does not take): the window is by
+      // position, keys (pos - window, pos] = cache rows [l0 - min(l0, window), l0)
+      const int l0p = l0 < a.window ? l0 : a.window;
+      rd.len0_w[tid] = a.mode == 0 ? l0w : l0p;
+      rd.skip_w[tid] = a.mode == 0 ? 0 : l0 - l0p;
       rd.ring_first_w[tid] = rfw;
       rd.ring_len_w[tid] = rlw;
-      chunks_w = (attn_num_tiles(a.mode == 0 ? l0w : l0, rfw, rlw, R - o) + a.tiles_per_item - 1) / a.tiles_per_item;
+      chunks_w = (attn_num_tiles(a.mode == 0 ? l0w : l0p, rfw, rlw, R - o) + a.tiles_per_item - 1) / a.tiles_per_item;
     }
   }
   s_off[tid + 1] = chunks;

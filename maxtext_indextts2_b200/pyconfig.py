@@ -131,9 +131,10 @@ def _validate(keys: dict) -> None:
       raise ValueError("the gemma3 block is implemented with mlp_activations=[gelu, linear]")
     if not (keys["use_post_attn_norm"] and keys["use_post_ffw_norm"]):
       raise ValueError("the gemma3 block is implemented with use_post_attn_norm and use_post_ffw_norm (as every gemma3 model yml sets them)")
-    if keys["head_dim"] not in (64, 128):
-      raise ValueError(f"head_dim={keys['head_dim']}: the attention kernels of this path take head_dim 64 or 128 (gemma3-27b's geometry; "
-                       "gemma3-1b/4b/12b use 256)")
+    if keys["head_dim"] not in (64, 128, 256):
+      raise ValueError(f"head_dim={keys['head_dim']}: the attention kernels of this path take head_dim 64, 128 or 256")
+    if keys["head_dim"] == 256 and keys["base_num_query_heads"] // max(1, keys["base_num_kv_heads"]) > 8:
+      raise ValueError("head_dim 256 needs at most 8 query heads per kv head")
     if keys["sliding_window_size"] <= 0:
       raise ValueError("Sliding_window_size must be set if Local Sliding attention type")  # attentions.py:625-626
     if not str(keys["model_name"]).startswith("gemma3"):

@@ -35,9 +35,11 @@ def gemma_config(**kw):
   return small_config(**base)
 
 
-@pytest.mark.parametrize("head_dim", [64, 128])
-def test_gemma3_prefill_and_decode_match_oracle(head_dim):
-  cfg = gemma_config(head_dim=head_dim)
+@pytest.mark.parametrize("head_dim,model", [(64, "gemma3-27b"), (128, "gemma3-27b"), (256, "gemma3-4b")])
+def test_gemma3_prefill_and_decode_match_oracle(head_dim, model):
+  """head_dim 256 (gemma3-1b/4b/12b; query scalar head_dim ** -0.5) runs the transposed decode attention of
+  csrc/attention_wide.cuh, and its prompt positions go through the same kernel as decode rows."""
+  cfg = gemma_config(head_dim=head_dim, model_name=model)
   assert cfg.decoder_block == "gemma3" and cfg.logits_via_embedding
   params = make_params(cfg)
   oracle = ref.DecodeOracle(cfg, params, faithful=True)

@@ -242,8 +242,10 @@ def test_gemma3_config_and_layer_pattern():
   with pytest.raises(ValueError):
     _gemma_cfg(model_name="default", decoder_block="gemma3", mlp_activations=["gelu", "linear"], use_post_attn_norm=True,
                use_post_ffw_norm=True, logits_via_embedding=True)  # gemma3.py:57-58: the scalar is chosen by model name
+  cfg4 = pyconfig.initialize(None, model_name="gemma3-4b")  # head_dim 256
+  assert cfg4.head_dim == 256 and gemma3.get_query_pre_attn_scalar(cfg4) == 256**-0.5
   with pytest.raises(ValueError):
-    pyconfig.initialize(None, model_name="gemma3-4b")  # head_dim 256
+    pyconfig.initialize(None, model_name="gemma3-4b", head_dim=512)
 
 
 def test_gemma3_ar_steps_equal_full_forward_when_the_window_covers_the_cache():
