@@ -349,6 +349,7 @@ struct mtx_engine {
   unsigned long long *par_target = nullptr, *par_above = nullptr, *par_hist = nullptr;
   uint32_t* par_prefix = nullptr;
   int* par_found = nullptr;
+  int* par_cand_count = nullptr;
   int* par_eq = nullptr;
   float *rows_ss_x = nullptr, *rows_ss_h = nullptr;  // gemm_rows.cuh fused RMSNorm statistics: [E/128 rounded up][max_r_tile]
   int *pk_tile_prefix = nullptr, *pk_attn_info = nullptr;
@@ -382,7 +383,7 @@ struct WsLayout {
   size_t part_score, part_idx, part_raw, part_max, part_sum, grid_bar;
   size_t pk_tables, pk_part_ws, pk_ss_x, pk_ss_h, pk_attn_part_o, pk_tile_prefix, pk_attn_info;
   size_t rows_ss_x, rows_ss_h, cand_counters;
-  size_t par_M, par_Z, par_target, par_above, par_prefix, par_found, par_hist, par_eq;
+  size_t par_M, par_Z, par_target, par_above, par_prefix, par_found, par_hist, par_eq, par_cand_count;
   size_t total;
 };
 
@@ -451,6 +452,7 @@ WsLayout layout_workspace(const mtx_engine* e) {
     L.rows_ss_h = take(rt * ss_tiles * 4);
     L.cand_counters = take(64);
     L.par_M = take(size_t(c.max_rows) * 4);
+    L.par_cand_count = take(size_t(c.max_rows) * 4);
     L.par_Z = take(size_t(c.max_rows) * 4);
     L.par_target = take(size_t(c.max_rows) * 8);
     L.par_above = take(size_t(c.max_rows) * 8);
@@ -1076,7 +1078,9 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     float* lp_out = mode == 0 ? e->s.log_prob : first_log_prob;
     // decode steps with top-k / nucleus run the all-SM sampler, which starts from the per-tile (max, sum exp) partials
     const bool par_sampler = two_pass && mode == 0 && cand_out == nullptr && env_int("MTX_PAR_SAMPLER", 1) != 0;
-    ea.want_lse = (((lp_out != nullptr || cand_out != nullptr) && !two_pass) || par_sampler) ? 1 : 0;
+    // vocab-parallel top-k / nucleus: the shard's 64 candidates come from the same all-SM radix descent (par_collect_kernel)
+    const bool par_collect = two_pass && mode == 0 && cand_out != nullptr && env_int("MTX_PAR_COLLECT", 1) != 0;
+    ea.want_lse = (((lp_out != nullptr || cand_out != nullptr) && !two_pass) || par_sampler || par_collect) ? 1 : 0;
     ea.rng_state = e->s.rng_state;
     ea.row_offset = mode == 0 ? 0 : prefill_noise_row(e);
     gp.n = c.vocab_size;
@@ -1105,9 +1109,49 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     fa.stride_t = 1;
     fa.cand_out = cand_out;
     int finalize_rows = rows;
+    auto par_args = [&](ParSampleArgs& ps) {
+      memset(&ps, 0, sizeof(ps));
+      ps.logits = e->s.logits;
+      ps.ld = c.vocab_size;
+      ps.vocab = c.vocab_size;
+      ps.vocab_offset = c.vocab_offset;
+      ps.rows = rows;
+      ps.rng_state = e->s.rng_state;
+      ps.row_offset = 0;
+      ps.part_max = e->part_max;
+      ps.part_sum = e->part_sum;
+      ps.n_tiles = plan_logits.n_tiles;
+      ps.row_M = e->par_M;
+      ps.row_Z = e->par_Z;
+      ps.target = e->par_target;
+      ps.above = e->par_above;
+      ps.prefix = e->par_prefix;
+      ps.found = e->par_found;
+      ps.hist = e->par_hist;
+      ps.eq_count = e->par_eq;
+      ps.slices = par_slices(c.vocab_size);
+      ps.row_group = par_row_group(c.vocab_size, rows);
+    };
+    if (par_collect) {
+      // this shard's kCandK best logits per row + its (max, sum exp): the radix descent with top_k = kCandK, whatever the
+      // strategy; the selection happens after the all-gather (mtx_commit_candidates)
+      ParSampleArgs ps;
+      par_args(ps);
+      ps.mode = MTX_SAMPLE_TOPK;
+      ps.top_k = kCandK;
+      ps.cand = cand_out;
+      ps.cand_count = e->par_cand_count;
+      const dim3 sweep(ps.slices, (rows + ps.row_group - 1) / ps.row_group);
+      MTX_TRY(launch(par_stats_kernel, dim3(rows), dim3(kParThreads), 0, st, ps));
+      for (int level = 0; level < kParLevels; ++level) {
+        MTX_TRY(launch(par_hist_kernel, sweep, dim3(kParThreads), 0, st, ps, level));
+        MTX_TRY(launch(par_select_kernel, dim3(rows), dim3(256), 0, st, ps, level));
+      }
+      MTX_TRY(launch(par_eqcount_kernel, sweep, dim3(kParThreads), 0, st, ps));
+      return launch(par_collect_kernel, sweep, dim3(kParThreads), 0, st, ps);
+    }
     if (two_pass && cand_out != nullptr) {
-      // vocab-parallel top-k / nucleus: this shard's kCandK best logits per row + its (max, sum exp); the selection
-      // happens after the all-gather (mtx_commit_candidates)
+      // (MTX_PAR_COLLECT=0: the one-CTA-per-row extraction of round 1)
       ShardTopkArgs ta;
       memset(&ta, 0, sizeof(ta));
       ta.logits = e->s.logits;
@@ -1350,6 +1394,7 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   e->rows_ss_h = reinterpret_cast<float*>(b + L.rows_ss_h);
   e->cand_counters = reinterpret_cast<int*>(b + L.cand_counters);
   e->par_M = reinterpret_cast<float*>(b + L.par_M);
+  e->par_cand_count = reinterpret_cast<int*>(b + L.par_cand_count);
   e->par_Z = reinterpret_cast<float*>(b + L.par_Z);
   e->par_target = reinterpret_cast<unsigned long long*>(b + L.par_target);
   e->par_above = reinterpret_cast<unsigned long long*>(b + L.par_above);

@@ -442,8 +442,13 @@ __global__ void __launch_bounds__(kSampleThreads) commit_topk_kernel(const Commi
       cut = s_sv[idx < 0 ? 0 : idx];
       // a shard whose last candidate is still inside the nucleus may hold more logits that belong to it
       if (a.shard_vocab > kCandK)
-        for (int s = 0; s < a.n_shards; ++s)
-          trunc = trunc || a.gathered[((long long)s * a.rows + r) * kCandFloats + kCandK - 1] >= cut;
+        for (int s = 0; s < a.n_shards; ++s) {  // (the candidates of a shard come in any order: its smallest one)
+          float mn = INFINITY;
+          for (int j = lane; j < kCandK; j += 32) mn = fminf(mn, a.gathered[((long long)s * a.rows + r) * kCandFloats + j]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+          trunc = trunc || mn >= cut;
+        }
       if (lane == 0 && trunc) atomicAdd(a.truncated, 1);
     }
     if (lane == 0) s_cut = cut;
@@ -563,6 +568,8 @@ struct ParSampleArgs {
                                    // entries equal to the cut-off key are kept (top-k ties: rank them by index)
   unsigned long long* hist;        // [rows, kParBins] zero between levels (par_select_kernel clears what it reads)
   int* eq_count;                   // [rows, slices * kParWarps] entries equal to the cut-off per warp piece (rows with found == 2)
+  float* cand;                     // vocab-parallel (par_collect_kernel): [rows, kCandFloats] this shard's candidates, or null
+  int* cand_count;                 // [rows] candidates written so far (reset by par_stats_kernel)
   float* out_score;                // [rows, slices * kParWarps] partials for finalize_kernel
   int* out_idx;
   float* out_raw;
@@ -630,6 +637,13 @@ __global__ void __launch_bounds__(kParThreads) par_stats_kernel(const ParSampleA
     a.above[r] = 0ull;
     a.prefix[r] = 0u;
     a.found[r] = 1;
+    if (a.cand_count != nullptr) a.cand_count[r] = 0;
+  }
+  if (a.cand != nullptr) {  // empty candidate slots: -inf with an id past every vocabulary
+    for (int i = tid; i < kCandK; i += kParThreads) {
+      a.cand[(long long)r * kCandFloats + i] = -INFINITY;
+      a.cand[(long long)r * kCandFloats + kCandK + i] = __int_as_float(0x7fffffff);
+    }
   }
 }
 
@@ -959,6 +973,103 @@ __global__ void __launch_bounds__(kParThreads, 4) par_scan_kernel(const ParSampl
       a.out_sum[o] = piece == 0 ? a.row_Z[r0 + rr] : 0.0f;
     }
   }
+}
+
+// Vocab-parallel top-k / nucleus: this shard's kCandK best logits of every row as (value, global id) pairs in
+// any order, plus the shard's (max, sum exp) -- what shard_topk_kernel produces with one CTA per row, here from the radix
+// descent above with top_k = kCandK.  The kept set is exactly par_scan_kernel's (cut-off key, ties by index); a kept entry
+// takes the next free slot of its row (the merge on the gathered candidates, commit_topk_kernel, orders by value and id).
+__global__ void __launch_bounds__(kParThreads) par_collect_kernel(const ParSampleArgs a) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int piece = blockIdx.x * kParWarps + warp, pieces = a.slices * kParWarps;
+  int lo4, hi4, wlo, whi;
+  par_slice4(a.vocab, a.slices, blockIdx.x, lo4, hi4);
+  par_piece4(lo4, hi4, warp, wlo, whi);
+  const bool vec = (a.ld & 3) == 0 && (a.vocab & 3) == 0;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int r0 = blockIdx.y * a.row_group;
+  const int n_rows = min(a.row_group, a.rows - r0);
+  const int nb = (whi - wlo + 127) / 128;
+  const int total = n_rows * nb;
+  auto load = [&](int it, float4 (&x)[4]) {
+    const float* row = a.logits + (long long)(r0 + it / nb) * a.ld;
+    const int q0 = wlo + (it % nb) * 128;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * 32 + lane;
+      x[u] = q < whi ? par_load4(row, q, a.vocab, vec) : par_neg_inf4();
+    }
+  };
+  float4 cur[4], nxt[4];
+  if (total > 0) load(0, nxt);
+  int need = 0, before = 0;
+  uint32_t cut_key = 0u;
+  bool tied = false;
+  for (int it = 0; it < total; ++it) {
+    const int r = r0 + it / nb, b = it % nb;
+    if (b == 0) {
+      const int f = a.found[r];
+      tied = f == 2;
+      cut_key = f != 0 ? a.prefix[r] : 0u;
+      before = 0;
+      if (tied) {
+        need = int(a.target[r] - a.above[r]);
+        for (int p2 = lane; p2 < piece; p2 += 32) before += a.eq_count[(long long)r * pieces + p2];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+      }
+      if (piece == 0 && lane == 0) {
+        a.cand[(long long)r * kCandFloats + 2 * kCandK] = a.row_M[r];
+        a.cand[(long long)r * kCandFloats + 2 * kCandK + 1] = a.row_Z[r];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
+    if (it + 1 < total) load(it + 1, nxt);
+    const int q0 = wlo + b * 128;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * 32 + lane;
+      const bool in = q < whi;
+      const float xs[4] = {cur[u].x, cur[u].y, cur[u].z, cur[u].w};
+      bool keep[4];
+      if (!tied) {  // (warp-uniform)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) keep[j] = in && 4 * q + j < a.vocab && f32_order_key(xs[j]) >= cut_key;
+      } else {
+        bool eq[4];
+        uint32_t bal[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          eq[j] = in && 4 * q + j < a.vocab && f32_order_key(xs[j]) == cut_key;
+          bal[j] = __ballot_sync(0xffffffffu, eq[j]);
+        }
+        int rank = before + __popc(bal[0] & lt) + __popc(bal[1] & lt) + __popc(bal[2] & lt) + __popc(bal[3] & lt);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          keep[j] = in && 4 * q + j < a.vocab && (f32_order_key(xs[j]) > cut_key || (eq[j] && rank < need));
+          rank += eq[j] ? 1 : 0;
+        }
+        before += __popc(bal[0]) + __popc(bal[1]) + __popc(bal[2]) + __popc(bal[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!keep[j]) continue;
+        const int slot = atomicAdd(a.cand_count + r, 1);
+        if (slot < kCandK) {
+          a.cand[(long long)r * kCandFloats + slot] = xs[j];
+          a.cand[(long long)r * kCandFloats + kCandK + slot] = __int_as_float(a.vocab_offset + 4 * q + j);
+        }
+      }
+    }
+  }
+  if (total == 0 && piece == 0 && lane == 0)
+    for (int rr = 0; rr < n_rows; ++rr) {
+      a.cand[(long long)(r0 + rr) * kCandFloats + 2 * kCandK] = a.row_M[r0 + rr];
+      a.cand[(long long)(r0 + rr) * kCandFloats + 2 * kCandK + 1] = a.row_Z[r0 + rr];
+    }
 }
 
 }  // namespace mtx
