@@ -289,7 +289,8 @@ class MaxEngine:
         rope_min_timescale=float(config.rope_min_timescale),
         rope_max_timescale=float(config.rope_max_timescale),
         attn_softcap=float(config.attn_logits_soft_cap or 0.0),
-        final_softcap=float(config.final_logits_soft_cap or 0.0),
+        # (decoders.py:552-565: the final soft cap sits inside the logits_via_embedding branch; an untied head ignores the key)
+        final_softcap=float(config.final_logits_soft_cap or 0.0) if config.logits_via_embedding else 0.0,
         logits_scale=scale,
         logits_round_bf16=0 if config.logits_dot_in_fp32 else 1,
         embedding_rows=config.vocab_size,

@@ -354,3 +354,46 @@ def test_generate_to_host_matches_generate():
     for (da, la), (db, lb) in zip(runs[0], other):
       assert torch.equal(da, db)
       torch.testing.assert_close(la, lb, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize(
+    "kw",
+    [
+        dict(logits_via_embedding=True),                                  # tied logits, / sqrt(E) (decoders.py:552-562)
+        dict(logits_via_embedding=True, normalize_embedding_logits=False),
+        dict(final_logits_soft_cap=5.0),                                  # decoders.py:552-565: ignored by an untied head
+        dict(logits_via_embedding=True, final_logits_soft_cap=5.0),       # decoders.py:563-565
+        dict(attn_logits_soft_cap=8.0),                                   # attentions.py:1231-1236
+        dict(logits_dot_in_fp32=True),                                    # decoders.py:557,571
+        dict(logits_via_embedding=True, final_logits_soft_cap=5.0, attn_logits_soft_cap=8.0, logits_dot_in_fp32=True),
+    ],
+    ids=["tied", "tied-unnormalised", "final-softcap-untied", "final-softcap", "attn-softcap", "logits-fp32", "all"],
+)
+@pytest.mark.parametrize("batch", [3, 70])
+def test_output_head_and_softcap_variants_match_oracle(kw, batch):
+  """The output-head variants of decoders.py:537-589 and the attention soft cap, on the persistent kernel (batch 3) and on the
+  per-kernel path (batch 70), against the faithful oracle."""
+  cfg = small_config(per_device_batch_size=batch, max_prefill_predict_length=16, max_target_length=48, materialize_logits=True, **kw)
+  params = make_params(cfg)
+  slots = [0, 1, 2]
+  oracle = ref.DecodeOracle(small_config(per_device_batch_size=3, max_prefill_predict_length=16, max_target_length=48, **kw), params, faithful=True)
+  engine = maxengine.MaxEngine(cfg)
+  dparams = engine.load_params(params)
+  prompts = random_tokens((3, 16), cfg.vocab_size, seed=21)
+  ostate, state = oracle.init_decode_state(), engine.init_decode_state()
+  # (un-normalised tied logits are sqrt(E) times larger and so is their bf16 noise: compared on the normalised scale)
+  sc = cfg.emb_dim**-0.5 if cfg.logits_via_embedding and not cfg.normalize_embedding_logits else 1.0
+  for slot, n in zip(slots, (16, 7, 11)):
+    padded = torch.zeros(16, dtype=torch.int64)
+    padded[:n] = prompts[slot, :n]
+    oprefix, _ = oracle.prefill(padded, n)
+    ostate = oracle.insert(oprefix, ostate, slot)
+    prefix, _ = engine.prefill(params=dparams, padded_tokens=padded, true_length=n)
+    _assert_logits(prefix["logits"].cpu()[0] * sc, oprefix["logits"][0] * sc)
+    prefix["tokens"].fill_(int(oprefix["tokens"].item()))
+    state = engine.insert(prefix, state, slot)
+  for step in range(8):
+    ostate, odata = oracle.generate(ostate)
+    state, result = engine.generate(dparams, state)
+    _assert_logits(state["logits"].cpu()[:3] * sc, ostate["logits"] * sc)
+    state["tokens"][:3] = odata[:, :1].to(state["tokens"].device)  # teacher-force the oracle's tokens
