@@ -330,6 +330,7 @@ struct mtx_engine {
   float* rope_timescale = nullptr;
   float* rope_timescale_w = nullptr;  // gemma3: the local layers' RoPE base
   bf16* qkv_tmp = nullptr;            // gemma3: [max_r_tile, qkv_n] the QKV projection before q/k norm, RoPE and the cache append
+  bf16 *kv_tmp_k = nullptr, *kv_tmp_v = nullptr;  // kv_quant 2: [max_r_tile, Hkv, D] the step's keys / values before quantisation
   float *part_score = nullptr, *part_raw = nullptr, *part_max = nullptr, *part_sum = nullptr;
   int* part_idx = nullptr;
   std::vector<float> rope_timescale_host, rope_timescale_w_host;
@@ -378,7 +379,7 @@ namespace {
 struct WsLayout {
   size_t x, h, n, q, attn, act, attn_part_o, attn_part_ml, attn_tickets;
   size_t token, pos, plane, write_row, len0, ring_first, ring_len, rope_cs, work_items, work_count, rope_timescale;
-  size_t skip_w;
+  size_t skip_w, iota, tmp_row, kv_tmp_k, kv_tmp_v;
   size_t len0_w, ring_first_w, ring_len_w, rope_cs_w, work_items_w, work_count_w, rope_timescale_w, qkv_tmp;
   size_t part_score, part_idx, part_raw, part_max, part_sum, grid_bar;
   size_t pk_tables, pk_part_ws, pk_ss_x, pk_ss_h, pk_attn_part_o, pk_tile_prefix, pk_attn_info;
@@ -418,6 +419,12 @@ WsLayout layout_workspace(const mtx_engine* e) {
   L.work_items = take(size_t(c.max_rows) * e->attn_max_chunks * 4);
   L.work_count = take(4);
   L.rope_timescale = take((c.head_dim / 2) * 4);
+  if (c.kv_quant == 2) {
+    L.iota = take(rt * 4);
+    L.tmp_row = take(rt * 4);
+    L.kv_tmp_k = take(rt * c.num_kv_heads * c.head_dim * 2);
+    L.kv_tmp_v = take(rt * c.num_kv_heads * c.head_dim * 2);
+  }
   if (c.decoder_block == 1) {
     L.len0_w = take(rt * 4);
     L.ring_first_w = take(rt * 4);
@@ -979,11 +986,19 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     ea.hkv = c.num_kv_heads;
     ea.d = c.head_dim;
     ea.t_alloc = c.max_target_len;
-    if (c.kv_quant && mode == 0) {
+    if (c.kv_quant == 1 && mode == 0) {
       ea.kq_cache = static_cast<uint8_t*>(e->s.kq_cache) + kvq_layer * l;
       ea.vq_cache = static_cast<uint8_t*>(e->s.vq_cache) + kvq_layer * l;
       ea.k_scale = e->s.k_scale + kvs_layer * l;
       ea.v_scale = e->s.v_scale + kvs_layer * l;
+    } else if (c.kv_quant == 2 && mode == 0) {
+      // one scale per token over all kv heads (kv_quant_axis heads_and_dkv): the epilogue leaves the rotated keys / values as
+      // bf16 in [rows, Hkv, D] scratch matrices (plane = row, write row = 0), kv_quant_rows_kernel quantises and appends
+      ea.k_cache = e->kv_tmp_k;
+      ea.v_cache = e->kv_tmp_v;
+      ea.plane = e->rd.iota;
+      ea.write_row = e->rd.tmp_row;
+      ea.t_alloc = 1;
     }
     gp.n = e->qkv_n;
     gp.k = E;
@@ -994,6 +1009,21 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
       MTX_TRY(launch_rows<EPI_QKV_ROPE>(e->tm_wqkv[l], xmap(pl, fused_norm ? &XMaps::x : &XMaps::n), gp, ea, pl, st));
     }
     else MTX_TRY(launch_gemm<EPI_QKV_ROPE>(e->tm_wqkv[l], xm->n, gp, ea, plan_qkv, st));
+    if (c.kv_quant == 2 && mode == 0) {
+      KvQuantRowsArgs ka;
+      memset(&ka, 0, sizeof(ka));
+      ka.k_tmp = e->kv_tmp_k;
+      ka.v_tmp = e->kv_tmp_v;
+      ka.plane = e->rd.plane;
+      ka.write_row = e->rd.write_row;
+      ka.kq_cache = static_cast<uint8_t*>(e->s.kq_cache) + kvq_layer * l;
+      ka.vq_cache = static_cast<uint8_t*>(e->s.vq_cache) + kvq_layer * l;
+      ka.k_scale = e->s.k_scale + kvs_layer * l;
+      ka.v_scale = e->s.v_scale + kvs_layer * l;
+      ka.hkv = c.num_kv_heads;
+      ka.t_alloc = c.max_target_len;
+      MTX_TRY(launch(kv_quant_rows_kernel, dim3(rows, 2), dim3(c.num_kv_heads * 32), 0, st, ka));
+    }
 
     g_class = KC_ATTENTION;
     if (mode == 1 && (use_prefill_attention(e) || c.kv_quant)) MTX_TRY(launch_prefill_attention(e, l, rows, start_pos, slot, st));
@@ -1289,7 +1319,8 @@ int mtx_engine_create(const mtx_model_config* cfg, mtx_engine** out) {
   if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
     e->num_sms = sms;
   cudaGetLastError();
-  if (c.kv_quant != 0 && c.kv_quant != 1) return fail(MTX_ERR_ARG, "kv_quant must be 0 (bf16) or 1 (int8 per token and kv head)");
+  if (c.kv_quant < 0 || c.kv_quant > 2) return fail(MTX_ERR_ARG, "kv_quant must be 0 (bf16), 1 (int8, one scale per token and kv head) or 2 (int8, one scale per token)");
+  if (c.kv_quant == 2 && c.num_kv_heads > 32) return fail(MTX_ERR_UNSUPPORTED, "kv_quant 2: at most 32 kv heads");
   if (c.kv_quant && c.head_dim != 64) return fail(MTX_ERR_UNSUPPORTED, "the int8 KV cache is implemented for head_dim 64");
   if (c.decoder_block != 0 && c.decoder_block != 1) return fail(MTX_ERR_ARG, "decoder_block must be 0 (llama2) or 1 (gemma3)");
   if (c.decoder_block == 1 && (c.kv_quant || !c.norm_scales_folded || c.sliding_window <= 0))
@@ -1366,6 +1397,13 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   e->rd.work_items = reinterpret_cast<int*>(b + L.work_items);
   e->rd.work_count = reinterpret_cast<int*>(b + L.work_count);
   e->rope_timescale = reinterpret_cast<float*>(b + L.rope_timescale);
+  e->rd.iota = e->rd.tmp_row = nullptr;
+  if (c.kv_quant == 2) {
+    e->rd.iota = reinterpret_cast<int*>(b + L.iota);
+    e->rd.tmp_row = reinterpret_cast<int*>(b + L.tmp_row);
+    e->kv_tmp_k = reinterpret_cast<bf16*>(b + L.kv_tmp_k);
+    e->kv_tmp_v = reinterpret_cast<bf16*>(b + L.kv_tmp_v);
+  }
   if (c.decoder_block == 1) {
     e->rd.len0_w = reinterpret_cast<int*>(b + L.len0_w);
     e->rd.ring_first_w = reinterpret_cast<int*>(b + L.ring_first_w);
@@ -1788,9 +1826,11 @@ int mtx_insert_prefix(mtx_engine* e, const void* k_src, const void* v_src, int n
     q.vq_cache = static_cast<uint8_t*>(e->s.vq_cache);
     q.k_scale = e->s.k_scale;
     q.v_scale = e->s.v_scale;
-    const long long warps = (long long)c.num_layers * c.num_kv_heads * n_rows * 2;
+    q.shared_scale = c.kv_quant == 2 ? 1 : 0;
+    const long long warps = (long long)c.num_layers * (c.kv_quant == 2 ? 1 : c.num_kv_heads) * n_rows * 2;
     int grid_q = int((warps + 7) / 8);
     if (grid_q > e->num_sms * 8) grid_q = e->num_sms * 8;
+    if (c.kv_quant == 2) return launch(insert_prefix_q8_shared_kernel, dim3(grid_q), dim3(256), 0, static_cast<cudaStream_t>(stream), q);
     return launch(insert_prefix_q8_kernel, dim3(grid_q), dim3(256), 0, static_cast<cudaStream_t>(stream), q);
   }
   const long long vecs = (long long)c.num_layers * c.num_kv_heads * n_rows * (c.head_dim / 8);

@@ -19,6 +19,8 @@ struct RowDesc {
   float2* rope_cs;  // [max_rows, D/2] (cos, sin), bf16-rounded
   int* work_items;  // attention work list
   int* work_count;
+  int* iota;        // [max_rows] r            } "plane" / "write row" of a [rows, Hkv, D] scratch matrix for the QKV epilogue
+  int* tmp_row;     // [max_rows] 0, or -1 when the row appends nothing } (int8 cache with one scale per token: kv_quant_rows_kernel)
   // sliding-window layers (gemma3 local attention; PrepareArgs.window > 0): the valid rows INSIDE the window's two cache
   // sub-ranges (AttnParams.skip0 / ring_off / ring_size), their work list, and the RoPE table of the local base
   int* len0_w;
@@ -98,6 +100,10 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
     rd.len0[tid] = l0;
     rd.ring_first[tid] = rf;
     rd.ring_len[tid] = rl;
+    if (rd.iota != nullptr) {
+      rd.iota[tid] = tid;
+      rd.tmp_row[tid] = wr >= 0 ? 0 : -1;
+    }
     s_nt[tid] = attn_num_tiles(l0, rf, rl, R);
     chunks = (s_nt[tid] + a.tiles_per_item - 1) / a.tiles_per_item;
     s_pos[tid] = pos;
@@ -321,7 +327,86 @@ struct InsertQ8Args {
   uint8_t* vq_cache;
   float* k_scale;
   float* v_scale;
+  int shared_scale;  // kv_quant_axis heads_and_dkv: one scale per token, over all kv heads (stored once per head)
 };
+// kv_quant_axis "heads_and_dkv" (kvcache.py:69-72, the reference's default): scale = max|x| over the heads AND the head dims of a
+// token.  One warp per (layer, row, K|V) walks the kv heads twice.
+__global__ void __launch_bounds__(256) insert_prefix_q8_shared_kernel(const InsertQ8Args q) {
+  const InsertArgs& a = q.base;
+  griddep_launch_dependents();
+  griddep_wait();
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long total = (long long)a.L * a.n * 2;
+  for (long long i = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); i < total; i += warps) {
+    const int which = int(i & 1);
+    const long long j = i >> 1;
+    const int row = int(j % a.n), l = int(j / a.n);
+    const bf16* base = (which ? a.v_src : a.k_src);
+    float mx = 0.0f;
+    for (int h = 0; h < a.hkv; ++h) {
+      const uint32_t pk = *reinterpret_cast<const uint32_t*>(base + ((long long)(l * a.hkv + h) * a.n_src + row) * 64 + 2 * lane);
+      mx = fmaxf(mx, fmaxf(fabsf(bf16_lo(pk)), fabsf(bf16_hi(pk))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float inv = mx > 0.0f ? 127.5f / mx : 0.0f;
+    for (int h = 0; h < a.hkv; ++h) {
+      const uint32_t pk = *reinterpret_cast<const uint32_t*>(base + ((long long)(l * a.hkv + h) * a.n_src + row) * 64 + 2 * lane);
+      const int q0 = int(fminf(fmaxf(rintf(bf16_lo(pk) * inv), -128.0f), 127.0f)) + 128, q1 = int(fminf(fmaxf(rintf(bf16_hi(pk) * inv), -128.0f), 127.0f)) + 128;
+      const long long drow = ((long long)(l * a.planes + a.slot) * a.hkv + h) * a.T + row;
+      uint8_t* dst = (which ? q.vq_cache : q.kq_cache) + drow * 64;
+      *reinterpret_cast<uint16_t*>(dst + 2 * lane) = uint16_t(q0 | (q1 << 8));
+      if (lane == 0) (which ? q.v_scale : q.k_scale)[drow] = mx;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.prefill_len[a.slot] = a.n;
+    a.ar_lengths[a.slot] = 0;
+    a.next_pos_out[a.slot] = a.next_pos;
+    a.generated_out[a.slot] = a.generated;
+    a.tokens_out[a.slot] = a.token;
+  }
+}
+
+// The decode step's appended rows for kv_quant_axis "heads_and_dkv": the QKV epilogue leaves the (rotated) keys and values of
+// the step's rows as bf16 in [rows, Hkv, 64] scratch matrices; one CTA per (row, K|V), one warp per kv head, takes the
+// token's scale over all heads, quantises (KVQuant.quantize, kvcache.py:76-90) and appends to the int8 cache.
+struct KvQuantRowsArgs {
+  const bf16* k_tmp;  // [rows, Hkv, 64]
+  const bf16* v_tmp;
+  const int* plane;
+  const int* write_row;
+  uint8_t* kq_cache;  // this layer's [planes, Hkv, t_alloc, 64]
+  uint8_t* vq_cache;
+  float* k_scale;     // this layer's [planes, Hkv, t_alloc]
+  float* v_scale;
+  int hkv, t_alloc;
+};
+__global__ void __launch_bounds__(1024) kv_quant_rows_kernel(const KvQuantRowsArgs a) {
+  __shared__ float s_mx[32];
+  griddep_launch_dependents();
+  griddep_wait();
+  const int r = blockIdx.x, which = blockIdx.y, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wr = a.write_row[r];
+  const uint32_t pk = *reinterpret_cast<const uint32_t*>((which ? a.v_tmp : a.k_tmp) + ((long long)r * a.hkv + h) * 64 + 2 * lane);
+  const float x0 = bf16_lo(pk), x1 = bf16_hi(pk);
+  float mx = fmaxf(fabsf(x0), fabsf(x1));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) s_mx[h] = mx;
+  __syncthreads();
+  mx = 0.0f;
+  for (int w = 0; w < a.hkv; ++w) mx = fmaxf(mx, s_mx[w]);
+  if (wr < 0) return;
+  const float inv = mx > 0.0f ? 127.5f / mx : 0.0f;
+  const int q0 = int(fminf(fmaxf(rintf(x0 * inv), -128.0f), 127.0f)) + 128, q1 = int(fminf(fmaxf(rintf(x1 * inv), -128.0f), 127.0f)) + 128;
+  const long long drow = ((long long)a.plane[r] * a.hkv + h) * a.t_alloc + wr;
+  uint8_t* dst = (which ? a.vq_cache : a.kq_cache) + drow * 64;
+  *reinterpret_cast<uint16_t*>(dst + 2 * lane) = uint16_t(q0 | (q1 << 8));
+  if (lane == 0) (which ? a.v_scale : a.k_scale)[drow] = mx;
+}
+
 __global__ void __launch_bounds__(256) insert_prefix_q8_kernel(const InsertQ8Args q) {
   const InsertArgs& a = q.base;
   griddep_launch_dependents();

@@ -294,7 +294,7 @@ class MaxEngine:
         logits_scale=scale,
         logits_round_bf16=0 if config.logits_dot_in_fp32 else 1,
         embedding_rows=config.vocab_size,
-        kv_quant=1 if config.quantize_kvcache else 0,
+        kv_quant=(2 if config.kv_quant_axis == "heads_and_dkv" else 1) if config.quantize_kvcache else 0,
         norm_scales_folded=1 if config.fold_norm_scales else 0,
         decoder_block=1 if config.decoder_block == "gemma3" else 0,
         sliding_window=int(config.sliding_window_size) if config.decoder_block == "gemma3" else 0,

@@ -108,13 +108,12 @@ def _validate(keys: dict) -> None:
   if keys["decode_sampling_strategy"] not in _VALID_SAMPLING:
     raise ValueError(f"Sampling algorithm={keys['decode_sampling_strategy']!r} not supported!")
   if keys["quantize_kvcache"]:
-    # inference/kvcache.py:36-90.  Implemented: int8 with one scale per (token, kv head), i.e. kv_quant_axis "dkv" -- the
-    # reference's default "heads_and_dkv" shares one scale between the kv heads of a token, which the fused QKV epilogue
-    # (one head per thread) does not produce; "dkv" is the variant base.yml:108-110 describes as the more accurate one.
+    # inference/kvcache.py:36-90.  Implemented: int8 with kv_quant_axis "dkv" (one scale per token and kv head, fused into the QKV
+    # epilogue) and "heads_and_dkv" (the reference's default: one scale per token over all kv heads; a small kernel after the QKV GEMM).
     if keys["kv_quant_dtype"] != "int8":
       raise ValueError(f"Invalid kv_quant_dtype: {keys['kv_quant_dtype']} (this decode path implements int8)")
-    if keys["kv_quant_axis"] != "dkv":
-      raise ValueError(f"kv_quant_axis={keys['kv_quant_axis']!r}: this decode path implements kv_quant_axis=dkv (one scale per token and kv head)")
+    if keys["kv_quant_axis"] not in ("dkv", "heads_and_dkv"):
+      raise ValueError(f"Invalid KV quant axis cfg: {keys['kv_quant_axis']}")  # kvcache.py:73
     if keys["head_dim"] != 64:
       raise ValueError("quantize_kvcache is implemented for head_dim=64")
   if keys["quantization"] not in ("", None):

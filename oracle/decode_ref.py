@@ -156,7 +156,8 @@ class DecodeOracle:
     maps to rint(127.5) = 128 -> 127), cached value = q * scale / 127.5.  Identity unless quantize_kvcache."""
     if not getattr(self.cfg, "quantize_kvcache", False):
       return x
-    scale = x.abs().amax(dim=-1, keepdim=True)
+    # kvcache.py:66-73: "dkv" takes the maximum over the head's dims, "heads_and_dkv" over the kv heads as well (x [..., Hkv, D])
+    scale = x.abs().amax(dim=(-2, -1) if self.cfg.kv_quant_axis == "heads_and_dkv" else -1, keepdim=True)
     q = torch.where(scale > 0, torch.clamp(torch.round(x * (127.5 / scale.clamp(min=1e-30))), -128.0, 127.0), torch.zeros_like(x))
     return q * (scale / 127.5)
 

@@ -30,6 +30,7 @@ import pytest
 import torch
 
 from maxtext_indextts2_b200 import maxengine, pyconfig
+from oracle import decode_ref as ref
 from oracle import mirror
 
 pytestmark = pytest.mark.gpu
@@ -216,3 +217,40 @@ def test_near_tie_rate_tiny_config_320_greedy_steps():
     gstate["tokens"] = fdata[:, :1].clone()
   _record("C1_tiny_320_steps", stats)
   assert stats["mismatch"] <= max(3, 2 * stats["oracle_self_mismatch"])
+
+
+@pytest.mark.parametrize(
+    "strategy,kw",
+    [("topk", dict(decode_sampling_top_k=50)), ("nucleus", dict(decode_sampling_nucleus_p=0.9)), ("weighted", {})],
+)
+def test_sampling_at_the_expanded_vocabulary(strategy, kw):
+  """inference_utils.py:66-111 over the 264,192-entry vocabulary of BASELINE configs[1] (65 vocabulary slices per row in the
+  all-SM sampler, the fused Gumbel-max epilogue for `weighted`): every step's token against the oracle's sampler on the SAME
+  logits (the GPU's, so model noise plays no role) and the same Philox stream; a different token must be a near-tie of the
+  perturbed scores, and must lie inside the oracle's candidate set."""
+  temp = 0.8
+  cfg = pyconfig.initialize(None, model_name="indextts2-t2s", base_num_decoder_layers=2, per_device_batch_size=8,
+                            max_prefill_predict_length=32, max_target_length=64, decode_sampling_strategy=strategy,
+                            decode_sampling_temperature=temp, materialize_logits=True, return_log_prob=True, **kw)
+  engine = maxengine.MaxEngine(cfg)
+  dparams = engine.load_params(on_device_init=True)
+  state = engine.init_decode_state(rng=np.array([1234, 0], dtype=np.uint32))
+  rng = np.random.Generator(np.random.PCG64(3))
+  state = engine.fill_synthetic_context(rng.integers(4, 33, size=8), np.zeros(8, dtype=np.int64))
+  engine._seed(np.array([1234, 0], dtype=np.uint32))
+  k, p = int(cfg.decode_sampling_top_k), float(cfg.decode_sampling_nucleus_p)
+  differ = 0
+  for step in range(4):
+    state, result = engine.generate(dparams, state)
+    logits = state["logits"].cpu()
+    toks, scores = ref.sampling(logits, strategy, topk=k, nucleus_topp=p, temperature=temp, seed=1234, step=step, return_scores=True)
+    got = result.data.cpu()[:, 0]
+    for b in range(8):
+      g, w = int(got[b]), int(toks[b, 0])
+      assert scores[b][g] > -1e6, (strategy, step, b, g)  # inside the kept set (top-k: -inf outside; nucleus: -1e7 / temp)
+      if g != w:
+        differ += 1
+        assert abs(scores[b][g] - scores[b][w]) < 1e-3, (strategy, step, b, g, w, float(scores[b][g]), float(scores[b][w]))
+    lp = ref.log_prob_of_chosen_token(logits, got.reshape(8, 1).long())
+    torch.testing.assert_close(result.log_prob.cpu(), lp, rtol=1e-3, atol=1e-3)
+  assert differ <= 2

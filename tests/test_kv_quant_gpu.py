@@ -1,5 +1,6 @@
 """int8 KV cache (MaxText/inference/kvcache.py:36-90, 658-736; configs/base.yml:104-112) on the B200 against the
-oracle with the same quantiser: quantize_kvcache=True, kv_quant_dtype=int8, kv_quant_axis=dkv (one scale per token and kv head).
+oracle with the same quantiser: quantize_kvcache=True, kv_quant_dtype=int8, kv_quant_axis=dkv (one scale per token and kv head)
+or heads_and_dkv (the reference's default: one scale per token over all kv heads).
 
 Tolerances: logits vs the quantised dtype-faithful oracle rtol = atol = 1e-1 (the reference's ceiling, as for bf16); cache bytes
 equal to the oracle's quantiser up to one step of the int8 grid on isolated elements (fp32 product order)."""
@@ -16,18 +17,25 @@ from tests.helpers import make_params, random_tokens, small_config
 pytestmark = pytest.mark.gpu
 
 QUANT = dict(quantize_kvcache=True, kv_quant_dtype="int8", kv_quant_axis="dkv")
+AXES = ["dkv", "heads_and_dkv"]
+
+
+def _quant(axis):
+  return dict(QUANT, kv_quant_axis=axis)
 
 
 def test_config_accepts_only_the_implemented_quantiser():
   assert pyconfig.initialize(None, head_dim=64, **QUANT).quantize_kvcache
-  with pytest.raises(ValueError, match="kv_quant_axis"):
-    pyconfig.initialize(None, head_dim=64, quantize_kvcache=True)  # the reference default heads_and_dkv
+  assert pyconfig.initialize(None, head_dim=64, quantize_kvcache=True).kv_quant_axis == "heads_and_dkv"  # the reference default
+  with pytest.raises(ValueError, match="axis"):
+    pyconfig.initialize(None, head_dim=64, quantize_kvcache=True, kv_quant_axis="heads")
   with pytest.raises(ValueError, match="kv_quant_dtype"):
     pyconfig.initialize(None, head_dim=64, quantize_kvcache=True, kv_quant_axis="dkv", kv_quant_dtype="fp8")
 
 
-def test_prefill_insert_and_decode_with_int8_cache_match_the_quantised_oracle():
-  cfg = small_config(per_device_batch_size=3, max_prefill_predict_length=16, max_target_length=28, materialize_logits=True, **QUANT)
+@pytest.mark.parametrize("axis", AXES)
+def test_prefill_insert_and_decode_with_int8_cache_match_the_quantised_oracle(axis):
+  cfg = small_config(per_device_batch_size=3, max_prefill_predict_length=16, max_target_length=28, materialize_logits=True, **_quant(axis))
   params = make_params(cfg)
   oracle = ref.DecodeOracle(cfg, params, faithful=True)
   engine = maxengine.MaxEngine(cfg, use_cuda_graph=False)
@@ -46,6 +54,8 @@ def test_prefill_insert_and_decode_with_int8_cache_match_the_quantised_oracle():
     for name, src in (("key", prefix["cache"]["key"]), ("value", prefix["cache"]["value"])):
       x = src.float().cpu()  # [L, Hkv, n, D]
       scale = x.abs().amax(-1)
+      if axis == "heads_and_dkv":  # one scale per token: the maximum over the kv heads too, stored once per head
+        scale = scale.amax(1, keepdim=True).expand_as(scale)
       q = torch.clamp(torch.round(x * (127.5 / scale.clamp(min=1e-30))[..., None]), -128, 127)
       got_q = state["cache"][name][:, slot, :, :n].cpu().to(torch.int32) - 128
       got_s = state["cache"][name + "_scale"][:, slot, :, :n].cpu()
@@ -60,15 +70,16 @@ def test_prefill_insert_and_decode_with_int8_cache_match_the_quantised_oracle():
   assert int(state["cache"]["cache_ar_index"].item()) == 4
 
 
+@pytest.mark.parametrize("axis", AXES)
 @pytest.mark.parametrize("batch", [5, 64, 200])
-def test_int8_decode_on_a_synthetic_cache_against_the_oracle(batch):
+def test_int8_decode_on_a_synthetic_cache_against_the_oracle(batch, axis):
   """Ragged contexts on a random int8 cache (every step size runs the 128-row-block GEMM: padded to 128 rows, 128, 256), the oracle
   following a few slots through oracle/mirror.py on the dequantised cache; also the bf16 engine on the dequantised cache for
   reference: the two CUDA paths must agree far more tightly than either does with the CPU oracle."""
   cfg = pyconfig.initialize(
       None, base_num_decoder_layers=3, base_emb_dim=384, base_num_query_heads=10, base_num_kv_heads=2, head_dim=64, base_mlp_dim=768,
       vocab_size=5000, per_device_batch_size=batch, max_prefill_predict_length=192, max_target_length=448, weight_dtype="bfloat16",
-      attention="dot_product", scan_layers=False, materialize_logits=True, **QUANT)
+      attention="dot_product", scan_layers=False, materialize_logits=True, **_quant(axis))
   rng = np.random.Generator(np.random.PCG64(batch))
   pl = rng.integers(1, 193, size=batch)
   al = rng.integers(0, 240, size=batch)
@@ -91,4 +102,9 @@ def test_int8_decode_on_a_synthetic_cache_against_the_oracle(batch):
   idx = int(state["cache"]["cache_ar_index"].item())
   P = cfg.max_prefill_predict_length
   last = state["cache"]["key"][:, slots[0], :, P + idx - 1].cpu().to(torch.int32) - 128
-  assert (last.abs().amax(-1) >= 127).all()
+  if axis == "dkv":
+    assert (last.abs().amax(-1) >= 127).all()
+  else:  # one scale per token: the maximum sits in ONE of the heads, and the heads share the scale
+    assert (last.abs().amax(dim=(-2, -1)) >= 127).all()
+    sc = state["cache"]["key_scale"][:, slots[0], :, P + idx - 1].cpu()
+    assert (sc == sc[:, :1]).all() and (sc > 0).all()
