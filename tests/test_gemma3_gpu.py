@@ -69,3 +69,34 @@ def test_gemma3_window_wider_than_the_cache_is_full_attention():
     got = state["logits"].cpu()
     assert (got - want).abs().max() <= 2**-5 * max(1.0, float(want.abs().max()))
     state["tokens"].copy_(odata[:, :1].to(state["tokens"].device))
+
+
+@pytest.mark.parametrize("head_dim,model", [(64, "gemma3-27b"), (256, "gemma3-4b")])
+def test_gemma3_chunked_prefill_with_a_window_inside_the_chunks(head_dim, model):
+  """A 550-token prompt in three chunks of 256 positions with sliding_window_size 100: the position window
+  (attentions.py:624-631) cuts inside and across chunks, in prefill_attn_kernel (head_dim 64) and in the decode kernel
+  that runs prompt positions as rows (head_dim 256); then decode steps on the inserted prefix."""
+  cfg = gemma_config(head_dim=head_dim, model_name=model, sliding_window_size=100, max_prefill_predict_length=600,
+                     max_target_length=640, per_device_batch_size=2, base_num_decoder_layers=6, prefill_chunk_size=256)
+  params = make_params(cfg)
+  f32 = ref.DecodeOracle(cfg, params, faithful=False)
+  engine = maxengine.MaxEngine(cfg)
+  dparams = engine.load_params(params)
+  prompts = random_tokens((2, 600), cfg.vocab_size, seed=13)
+  ostate, state = f32.init_decode_state(), engine.init_decode_state()
+  for slot, n in enumerate((550, 300)):
+    padded = torch.zeros(600, dtype=torch.int64)
+    padded[:n] = prompts[slot, :n]
+    oprefix, ofirst = f32.prefill(padded, n)
+    ostate = f32.insert(oprefix, ostate, slot)
+    prefix, _ = engine.prefill(params=dparams, padded_tokens=padded, true_length=n)
+    want, got = oprefix["logits"][0], prefix["logits"].cpu()[0]
+    assert (got - want).abs().max() <= 2**-5 * max(1.0, float(want.abs().max()))
+    prefix["tokens"].fill_(int(ofirst))
+    state = engine.insert(prefix, state, slot)
+  for _ in range(4):
+    ostate, odata = f32.generate(ostate)
+    state, result = engine.generate(dparams, state)
+    want, got = ostate["logits"], state["logits"].cpu()
+    assert (got - want).abs().max() <= 2**-5 * max(1.0, float(want.abs().max()))
+    state["tokens"].copy_(odata[:, :1].to(state["tokens"].device))
