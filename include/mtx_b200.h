@@ -69,7 +69,8 @@ typedef struct {
   int32_t embedding_rows;    /* rows of the embedding table: token ids are clamped into [0, embedding_rows) as jnp indexing does
                                 (embeddings.py:154); 0 = do not clamp */
   int32_t kv_quant;          /* 0: bf16 KV cache.  2: as 1, with kv_quant_axis=heads_and_dkv (the reference's default): one scale per token over
-                                all kv heads, stored once per head.  1: int8 with one fp32 scale per (token, kv head) -- quantize_kvcache=True,
+                                all kv heads, stored once per head.  3 / 4: as 1 / 2 with kv_quant_dtype=fp8: float8_e4m3fn bytes,
+                                value = e4m3(x * 448 / scale) (kvcache.py:38,86-88).  1: int8 with one fp32 scale per (token, kv head) -- quantize_kvcache=True,
                                 kv_quant_dtype=int8, kv_quant_axis=dkv (inference/kvcache.py:36-90): decode_state.kq_cache / vq_cache /
                                 k_scale / v_scale hold the decode cache, k_cache / v_cache are ONE bf16 staging plane for prefill */
   int32_t norm_scales_folded; /* 1: wqkv / w01 already carry the per-feature RMSNorm scales of their input (W' = W * diag(scale),

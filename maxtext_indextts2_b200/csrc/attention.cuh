@@ -465,6 +465,7 @@ __host__ inline size_t attn_smem_bytes(int D, int G) {
 //     output columns come out permuted: element (n-block j, column c) is head dim 8 c + j).
 constexpr int kQ8WarpBytes = 9216;  // per warp: K tile 4 KB | V tile 4 KB | 64 K scales + 64 V scales (+ pad)
 constexpr float kQ8Inv = 1.0f / 127.5f;
+constexpr float kF8Inv = 1.0f / 448.0f;  // kv_quant_dtype fp8: value = e4m3(x * 448 / scale) (kvcache.py:38,86-88), x ~ value * scale / 448
 
 __device__ __forceinline__ void mma_m16n8k16_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -480,6 +481,17 @@ __device__ __forceinline__ uint32_t q8_pair_f16(uint32_t w, uint32_t sel) {
   asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(0x64806480u));
   return r;
 }
+// The same two bytes read as float8_e4m3fn values (kv_quant_dtype fp8): one permute to pair them, one packed conversion (exact).
+__device__ __forceinline__ uint32_t f8_pair_f16(uint32_t w, uint32_t sel) {
+  uint32_t t, r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(w), "r"(0u), "r"((sel & 0xFu) | ((sel >> 4) & 0xF0u)));
+  asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.rn.f16x2.e4m3x2 %0, lo; }" : "=r"(r) : "r"(t));
+  return r;
+}
+template <bool F8>
+__device__ __forceinline__ uint32_t kv8_pair_f16(uint32_t w, uint32_t sel) {
+  return F8 ? f8_pair_f16(w, sel) : q8_pair_f16(w, sel);
+}
 __device__ __forceinline__ uint32_t bf16x2_to_f16x2(uint32_t v) {
   const __half2 h = __floats2half2_rn(bf16_lo(v), bf16_hi(v));
   return *reinterpret_cast<const uint32_t*>(&h);
@@ -491,6 +503,7 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
 
 // The attention work loop of 128 threads (4 warps) over an int8 cache, head_dim 64.  Same contract as attn_process_items;
 // `tiles` = [warp][kQ8WarpBytes], k_scale / v_scale = fp32 per cache row, indexed like the rows of the K/V tensor maps.
+template <bool F8>
 __device__ __forceinline__ void attn_process_items_q8(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnParams& p, const float* k_scale,
                                                       const float* v_scale, uint8_t* tiles, float* sm_o_all, uint64_t* bars, float* sm_stat,
                                                       uint32_t& phase, int tid, int first_item, int item_stride) {
@@ -564,10 +577,10 @@ __device__ __forceinline__ void attn_process_items_q8(const CUtensorMap& tm_k, c
       {
         const long long row0 = (long long)plane_row + loc.p0;
         __syncwarp();
-        s_ks[lane] = lane < cnt ? __ldg(k_scale + row0 + lane) * kQ8Inv : 0.0f;
-        s_ks[lane + 32] = lane + 32 < cnt ? __ldg(k_scale + row0 + lane + 32) * kQ8Inv : 0.0f;
-        s_vs[lane] = lane < cnt ? __ldg(v_scale + row0 + lane) * kQ8Inv : 0.0f;
-        s_vs[lane + 32] = lane + 32 < cnt ? __ldg(v_scale + row0 + lane + 32) * kQ8Inv : 0.0f;
+        s_ks[lane] = lane < cnt ? __ldg(k_scale + row0 + lane) * (F8 ? kF8Inv : kQ8Inv) : 0.0f;
+        s_ks[lane + 32] = lane + 32 < cnt ? __ldg(k_scale + row0 + lane + 32) * (F8 ? kF8Inv : kQ8Inv) : 0.0f;
+        s_vs[lane] = lane < cnt ? __ldg(v_scale + row0 + lane) * (F8 ? kF8Inv : kQ8Inv) : 0.0f;
+        s_vs[lane + 32] = lane + 32 < cnt ? __ldg(v_scale + row0 + lane + 32) * (F8 ? kF8Inv : kQ8Inv) : 0.0f;
         __syncwarp();
       }
       // ---- S = Q K^T over the 64 rows of the tile: n-block j = kv rows 8 j .. 8 j + 7, one 16-byte load per row ----
@@ -582,7 +595,7 @@ __device__ __forceinline__ void attn_process_items_q8(const CUtensorMap& tm_k, c
         uint32_t w[4];
         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
 #pragma unroll
-        for (int tt = 0; tt < 4; ++tt) mma_m16n8k16_f16(s[j], qf[tt], q8_pair_f16(w[tt], 0x4140u), q8_pair_f16(w[tt], 0x4342u));
+        for (int tt = 0; tt < 4; ++tt) mma_m16n8k16_f16(s[j], qf[tt], kv8_pair_f16<F8>(w[tt], 0x4140u), kv8_pair_f16<F8>(w[tt], 0x4342u));
       }
       // K tile consumed: refill it with the next tile's keys while the softmax and P V run
       fence_proxy_async();
@@ -648,7 +661,7 @@ __device__ __forceinline__ void attn_process_items_q8(const CUtensorMap& tm_k, c
           const int row = 16 * u + 2 * tid4 + (q & 1) + 8 * (q >> 1);
           const uint32_t addr = vb + row * 64 + ((((gid >> 1) ^ ((row >> 1) & 3)) << 4) | ((gid & 1) << 3));
           asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(lo[q]), "=r"(hi[q]) : "r"(addr));
-          if (row >= cnt) lo[q] = hi[q] = 0x80808080u;  // rows past the valid count may hold anything: make them zero (u = 128)
+          if (row >= cnt) lo[q] = hi[q] = F8 ? 0u : 0x80808080u;  // rows past the valid count may hold anything: make them zero (u = 128; e4m3 +0)
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -658,7 +671,7 @@ __device__ __forceinline__ void attn_process_items_q8(const CUtensorMap& tm_k, c
           const uint32_t selg = 0x0040u + 0x0011u * uint32_t(j & 3);  // (byte j of the first word, byte j of the second word)
           asm("prmt.b32 %0, %1, %2, %3;" : "=r"(g0) : "r"(w0), "r"(w1), "r"(selg));
           asm("prmt.b32 %0, %1, %2, %3;" : "=r"(g1) : "r"(w2), "r"(w3), "r"(selg));
-          mma_m16n8k16_f16(o[j], pa[u], q8_pair_f16(g0, 0x4140u), q8_pair_f16(g1, 0x4140u));
+          mma_m16n8k16_f16(o[j], pa[u], kv8_pair_f16<F8>(g0, 0x4140u), kv8_pair_f16<F8>(g1, 0x4140u));
         }
       }
       // V tile consumed: refill
@@ -760,6 +773,7 @@ __device__ __forceinline__ void attn_process_items_q8(const CUtensorMap& tm_k, c
 }
 
 
+template <bool F8>
 __global__ void __launch_bounds__(kAttnThreads)
 decode_attn_q8_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnParams p, const float* k_scale,
                       const float* v_scale) {
@@ -785,7 +799,7 @@ decode_attn_q8_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
   __syncthreads();
   griddep_wait();
   uint32_t phase = 0;
-  attn_process_items_q8(tm_k, tm_v, p, k_scale, v_scale, smem, sm_o_all, bars, sm_stat, phase, threadIdx.x, blockIdx.x, gridDim.x);
+  attn_process_items_q8<F8>(tm_k, tm_v, p, k_scale, v_scale, smem, sm_o_all, bars, sm_stat, phase, threadIdx.x, blockIdx.x, gridDim.x);
   timeline_end(tl);
 }
 

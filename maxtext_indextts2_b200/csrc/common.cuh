@@ -22,6 +22,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 // Round an fp32 value to bf16 and back (round-to-nearest-even), the rounding the
 // reference applies wherever an activation is a bf16 array.
 __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// KVQuant.quantize (inference/kvcache.py:76-90) of two values with inv = MAX / scale: int8 -> the bytes u = clip(rint(x inv), -128, 127)
+// + 128 (MAX 127.5), fp8 -> float8_e4m3fn(x inv) (MAX 448; round to nearest even, |x inv| <= 448 by construction).
+__device__ __forceinline__ uint32_t kv_quant_pair(float x0, float x1, float inv, bool fp8) {
+  if (fp8) {
+    unsigned short r;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(x1 * inv), "f"(x0 * inv));
+    return r;
+  }
+  const int q0 = int(fminf(fmaxf(rintf(x0 * inv), -128.0f), 127.0f)) + 128, q1 = int(fminf(fmaxf(rintf(x1 * inv), -128.0f), 127.0f)) + 128;
+  return uint32_t(q0 | (q1 << 8));
+}
+__device__ __forceinline__ float kv_quant_max(bool fp8) { return fp8 ? 448.0f : 127.5f; }
 
 __device__ __forceinline__ float bf16_lo(uint32_t packed) { return __uint_as_float(packed << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }

@@ -388,6 +388,10 @@ struct WsLayout {
   size_t total;
 };
 
+// mtx_model_config.kv_quant: 1 / 2 = int8 with kv_quant_axis dkv / heads_and_dkv, 3 / 4 = the same with float8_e4m3fn bytes
+int kvq_axis(const mtx_model_config& c) { return c.kv_quant == 0 ? 0 : (c.kv_quant - 1) % 2 + 1; }
+bool kvq_fp8(const mtx_model_config& c) { return c.kv_quant >= 3; }
+
 WsLayout layout_workspace(const mtx_engine* e) {
   const mtx_model_config& c = e->cfg;
   const size_t rt = e->max_r_tile;
@@ -419,7 +423,7 @@ WsLayout layout_workspace(const mtx_engine* e) {
   L.work_items = take(size_t(c.max_rows) * e->attn_max_chunks * 4);
   L.work_count = take(4);
   L.rope_timescale = take((c.head_dim / 2) * 4);
-  if (c.kv_quant == 2) {
+  if (kvq_axis(c) == 2) {
     L.iota = take(rt * 4);
     L.tmp_row = take(rt * 4);
     L.kv_tmp_k = take(rt * c.num_kv_heads * c.head_dim * 2);
@@ -540,7 +544,10 @@ int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st, int mo
     const size_t smem_q = attn_q8_smem_bytes(c.num_q_heads / c.num_kv_heads);
     int grid_q = rows * c.num_kv_heads * attn_max_chunks(c.max_prefill_len, c.max_target_len, p.tiles_per_item);
     if (grid_q > e->num_sms * 4) grid_q = e->num_sms * 4;
-    return launch(decode_attn_q8_kernel, dim3(grid_q), dim3(kAttnThreads), smem_q, st, e->tm_kq, e->tm_vq, p, (const float*)e->s.k_scale,
+    if (kvq_fp8(c))
+      return launch(decode_attn_q8_kernel<true>, dim3(grid_q), dim3(kAttnThreads), smem_q, st, e->tm_kq, e->tm_vq, p, (const float*)e->s.k_scale,
+                    (const float*)e->s.v_scale);
+    return launch(decode_attn_q8_kernel<false>, dim3(grid_q), dim3(kAttnThreads), smem_q, st, e->tm_kq, e->tm_vq, p, (const float*)e->s.k_scale,
                   (const float*)e->s.v_scale);
   }
   if (c.head_dim == 256) {  // wide heads: the transposed kernel (attention_wide.cuh), one CTA of three warps per SM
@@ -986,12 +993,13 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
     ea.hkv = c.num_kv_heads;
     ea.d = c.head_dim;
     ea.t_alloc = c.max_target_len;
-    if (c.kv_quant == 1 && mode == 0) {
+    ea.kv_fp8 = kvq_fp8(c) ? 1 : 0;
+    if (kvq_axis(c) == 1 && mode == 0) {
       ea.kq_cache = static_cast<uint8_t*>(e->s.kq_cache) + kvq_layer * l;
       ea.vq_cache = static_cast<uint8_t*>(e->s.vq_cache) + kvq_layer * l;
       ea.k_scale = e->s.k_scale + kvs_layer * l;
       ea.v_scale = e->s.v_scale + kvs_layer * l;
-    } else if (c.kv_quant == 2 && mode == 0) {
+    } else if (kvq_axis(c) == 2 && mode == 0) {
       // one scale per token over all kv heads (kv_quant_axis heads_and_dkv): the epilogue leaves the rotated keys / values as
       // bf16 in [rows, Hkv, D] scratch matrices (plane = row, write row = 0), kv_quant_rows_kernel quantises and appends
       ea.k_cache = e->kv_tmp_k;
@@ -1009,7 +1017,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
       MTX_TRY(launch_rows<EPI_QKV_ROPE>(e->tm_wqkv[l], xmap(pl, fused_norm ? &XMaps::x : &XMaps::n), gp, ea, pl, st));
     }
     else MTX_TRY(launch_gemm<EPI_QKV_ROPE>(e->tm_wqkv[l], xm->n, gp, ea, plan_qkv, st));
-    if (c.kv_quant == 2 && mode == 0) {
+    if (kvq_axis(c) == 2 && mode == 0) {
       KvQuantRowsArgs ka;
       memset(&ka, 0, sizeof(ka));
       ka.k_tmp = e->kv_tmp_k;
@@ -1022,6 +1030,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
       ka.v_scale = e->s.v_scale + kvs_layer * l;
       ka.hkv = c.num_kv_heads;
       ka.t_alloc = c.max_target_len;
+      ka.fp8 = kvq_fp8(c) ? 1 : 0;
       MTX_TRY(launch(kv_quant_rows_kernel, dim3(rows, 2), dim3(c.num_kv_heads * 32), 0, st, ka));
     }
 
@@ -1319,8 +1328,9 @@ int mtx_engine_create(const mtx_model_config* cfg, mtx_engine** out) {
   if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
     e->num_sms = sms;
   cudaGetLastError();
-  if (c.kv_quant < 0 || c.kv_quant > 2) return fail(MTX_ERR_ARG, "kv_quant must be 0 (bf16), 1 (int8, one scale per token and kv head) or 2 (int8, one scale per token)");
-  if (c.kv_quant == 2 && c.num_kv_heads > 32) return fail(MTX_ERR_UNSUPPORTED, "kv_quant 2: at most 32 kv heads");
+  if (c.kv_quant < 0 || c.kv_quant > 4)
+    return fail(MTX_ERR_ARG, "kv_quant must be 0 (bf16), 1 / 2 (int8, one scale per token and kv head / per token) or 3 / 4 (the same with fp8 bytes)");
+  if (kvq_axis(c) == 2 && c.num_kv_heads > 32) return fail(MTX_ERR_UNSUPPORTED, "kv_quant 2: at most 32 kv heads");
   if (c.kv_quant && c.head_dim != 64) return fail(MTX_ERR_UNSUPPORTED, "the int8 KV cache is implemented for head_dim 64");
   if (c.decoder_block != 0 && c.decoder_block != 1) return fail(MTX_ERR_ARG, "decoder_block must be 0 (llama2) or 1 (gemma3)");
   if (c.decoder_block == 1 && (c.kv_quant || !c.norm_scales_folded || c.sliding_window <= 0))
@@ -1398,7 +1408,7 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   e->rd.work_count = reinterpret_cast<int*>(b + L.work_count);
   e->rope_timescale = reinterpret_cast<float*>(b + L.rope_timescale);
   e->rd.iota = e->rd.tmp_row = nullptr;
-  if (c.kv_quant == 2) {
+  if (kvq_axis(c) == 2) {
     e->rd.iota = reinterpret_cast<int*>(b + L.iota);
     e->rd.tmp_row = reinterpret_cast<int*>(b + L.tmp_row);
     e->kv_tmp_k = reinterpret_cast<bf16*>(b + L.kv_tmp_k);
@@ -1506,7 +1516,8 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
     MTX_TRY(make_map(&e->tm_v, s->v_cache, c.head_dim, stage_rows, kAttnTileRows));
     MTX_TRY(make_map_u8(&e->tm_kq, s->kq_cache, kv_rows));
     MTX_TRY(make_map_u8(&e->tm_vq, s->vq_cache, kv_rows));
-    MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_q8_smem_bytes(16))));
+    MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_q8_smem_bytes(16))));
+    MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_q8_smem_bytes(16))));
   } else {
   MTX_TRY(make_map(&e->tm_k, s->k_cache, c.head_dim, kv_rows, kAttnTileRows));
   MTX_TRY(make_map(&e->tm_v, s->v_cache, c.head_dim, kv_rows, kAttnTileRows));
@@ -1826,11 +1837,12 @@ int mtx_insert_prefix(mtx_engine* e, const void* k_src, const void* v_src, int n
     q.vq_cache = static_cast<uint8_t*>(e->s.vq_cache);
     q.k_scale = e->s.k_scale;
     q.v_scale = e->s.v_scale;
-    q.shared_scale = c.kv_quant == 2 ? 1 : 0;
-    const long long warps = (long long)c.num_layers * (c.kv_quant == 2 ? 1 : c.num_kv_heads) * n_rows * 2;
+    q.shared_scale = kvq_axis(c) == 2 ? 1 : 0;
+    q.fp8 = kvq_fp8(c) ? 1 : 0;
+    const long long warps = (long long)c.num_layers * (kvq_axis(c) == 2 ? 1 : c.num_kv_heads) * n_rows * 2;
     int grid_q = int((warps + 7) / 8);
     if (grid_q > e->num_sms * 8) grid_q = e->num_sms * 8;
-    if (c.kv_quant == 2) return launch(insert_prefix_q8_shared_kernel, dim3(grid_q), dim3(256), 0, static_cast<cudaStream_t>(stream), q);
+    if (kvq_axis(c) == 2) return launch(insert_prefix_q8_shared_kernel, dim3(grid_q), dim3(256), 0, static_cast<cudaStream_t>(stream), q);
     return launch(insert_prefix_q8_kernel, dim3(grid_q), dim3(256), 0, static_cast<cudaStream_t>(stream), q);
   }
   const long long vecs = (long long)c.num_layers * c.num_kv_heads * n_rows * (c.head_dim / 8);

@@ -228,7 +228,8 @@ __device__ __forceinline__ void rows_epi_qkv_q8(const EpiArgs& e, int N, int r, 
   for (int q = 0; q < 4; ++q)
 #pragma unroll
     for (int j = 0; j < 16; ++j) mx = fmaxf(mx, fabsf(part[q][j]));
-  const float inv = mx > 0.0f ? 127.5f / mx : 0.0f;
+  const bool fp8 = e.kv_fp8 != 0;
+  const float inv = mx > 0.0f ? kv_quant_max(fp8) / mx : 0.0f;
   const int kvh = is_k ? head - e.hq : head - e.hq - e.hkv;
   const long long row = ((long long)e.plane[r] * e.hkv + kvh) * e.t_alloc + wr;
   uint8_t* dst = (is_k ? e.kq_cache : e.vq_cache) + row * 64;
@@ -236,16 +237,8 @@ __device__ __forceinline__ void rows_epi_qkv_q8(const EpiArgs& e, int N, int r, 
   for (int q = 0; q < 4; ++q) {
     uint32_t w[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint32_t pk = 0;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        float v = rintf(part[q][4 * i + b] * inv);
-        v = fminf(fmaxf(v, -128.0f), 127.0f);
-        pk |= uint32_t(int(v) + 128) << (8 * b);
-      }
-      w[i] = pk;
-    }
+    for (int i = 0; i < 4; ++i)
+      w[i] = kv_quant_pair(part[q][4 * i], part[q][4 * i + 1], inv, fp8) | (kv_quant_pair(part[q][4 * i + 2], part[q][4 * i + 3], inv, fp8) << 16);
     *reinterpret_cast<uint4*>(dst + 16 * q) = make_uint4(w[0], w[1], w[2], w[3]);
   }
   (is_k ? e.k_scale : e.v_scale)[row] = mx;

@@ -91,6 +91,7 @@ struct EpiArgs {
   int ss_tiles, ss_pitch, ss_dim;
   float ss_eps;
   int act_gelu;  // gemm_rows.cuh, EPI_SWIGLU: 1 = the gate activation is gelu (tanh form) instead of silu (gemma3)
+  int kv_fp8;    // gemm_rows.cuh, quantising QKV epilogue: 1 = float8_e4m3fn bytes (kv_quant_dtype fp8) instead of int8
   // gemm_rows.cuh only: int8 KV cache (kvcache.py:36-90, kv_quant_axis dkv).  Non-null: key / value rows are appended as 64 bytes
   // u = clip(rint(x * 127.5 / scale), -128, 127) + 128 at the same row index of kq_cache / vq_cache, with scale = max|x| over the
   // head's dims in k_scale / v_scale [planes, Hkv, t_alloc]; k_cache / v_cache are then unused.

@@ -328,6 +328,7 @@ struct InsertQ8Args {
   float* k_scale;
   float* v_scale;
   int shared_scale;  // kv_quant_axis heads_and_dkv: one scale per token, over all kv heads (stored once per head)
+  int fp8;           // kv_quant_dtype fp8 (float8_e4m3fn bytes) instead of int8
 };
 // kv_quant_axis "heads_and_dkv" (kvcache.py:69-72, the reference's default): scale = max|x| over the heads AND the head dims of a
 // token.  One warp per (layer, row, K|V) walks the kv heads twice.
@@ -350,13 +351,12 @@ __global__ void __launch_bounds__(256) insert_prefix_q8_shared_kernel(const Inse
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const float inv = mx > 0.0f ? 127.5f / mx : 0.0f;
+    const float inv = mx > 0.0f ? kv_quant_max(q.fp8 != 0) / mx : 0.0f;
     for (int h = 0; h < a.hkv; ++h) {
       const uint32_t pk = *reinterpret_cast<const uint32_t*>(base + ((long long)(l * a.hkv + h) * a.n_src + row) * 64 + 2 * lane);
-      const int q0 = int(fminf(fmaxf(rintf(bf16_lo(pk) * inv), -128.0f), 127.0f)) + 128, q1 = int(fminf(fmaxf(rintf(bf16_hi(pk) * inv), -128.0f), 127.0f)) + 128;
       const long long drow = ((long long)(l * a.planes + a.slot) * a.hkv + h) * a.T + row;
       uint8_t* dst = (which ? q.vq_cache : q.kq_cache) + drow * 64;
-      *reinterpret_cast<uint16_t*>(dst + 2 * lane) = uint16_t(q0 | (q1 << 8));
+      *reinterpret_cast<uint16_t*>(dst + 2 * lane) = uint16_t(kv_quant_pair(bf16_lo(pk), bf16_hi(pk), inv, q.fp8 != 0));
       if (lane == 0) (which ? q.v_scale : q.k_scale)[drow] = mx;
     }
   }
@@ -382,6 +382,7 @@ struct KvQuantRowsArgs {
   float* k_scale;     // this layer's [planes, Hkv, t_alloc]
   float* v_scale;
   int hkv, t_alloc;
+  int fp8;
 };
 __global__ void __launch_bounds__(1024) kv_quant_rows_kernel(const KvQuantRowsArgs a) {
   __shared__ float s_mx[32];
@@ -399,11 +400,10 @@ __global__ void __launch_bounds__(1024) kv_quant_rows_kernel(const KvQuantRowsAr
   mx = 0.0f;
   for (int w = 0; w < a.hkv; ++w) mx = fmaxf(mx, s_mx[w]);
   if (wr < 0) return;
-  const float inv = mx > 0.0f ? 127.5f / mx : 0.0f;
-  const int q0 = int(fminf(fmaxf(rintf(x0 * inv), -128.0f), 127.0f)) + 128, q1 = int(fminf(fmaxf(rintf(x1 * inv), -128.0f), 127.0f)) + 128;
+  const float inv = mx > 0.0f ? kv_quant_max(a.fp8 != 0) / mx : 0.0f;
   const long long drow = ((long long)a.plane[r] * a.hkv + h) * a.t_alloc + wr;
   uint8_t* dst = (which ? a.vq_cache : a.kq_cache) + drow * 64;
-  *reinterpret_cast<uint16_t*>(dst + 2 * lane) = uint16_t(q0 | (q1 << 8));
+  *reinterpret_cast<uint16_t*>(dst + 2 * lane) = uint16_t(kv_quant_pair(x0, x1, inv, a.fp8 != 0));
   if (lane == 0) (which ? a.v_scale : a.k_scale)[drow] = mx;
 }
 
@@ -426,11 +426,10 @@ __global__ void __launch_bounds__(256) insert_prefix_q8_kernel(const InsertQ8Arg
     float mx = fmaxf(fabsf(x0), fabsf(x1));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const float inv = mx > 0.0f ? 127.5f / mx : 0.0f;
-    const int q0 = int(fminf(fmaxf(rintf(x0 * inv), -128.0f), 127.0f)) + 128, q1 = int(fminf(fmaxf(rintf(x1 * inv), -128.0f), 127.0f)) + 128;
+    const float inv = mx > 0.0f ? kv_quant_max(q.fp8 != 0) / mx : 0.0f;
     const long long drow = ((long long)(l * a.planes + a.slot) * a.hkv + h) * a.T + row;
     uint8_t* dst = (which ? q.vq_cache : q.kq_cache) + drow * 64;
-    *reinterpret_cast<uint16_t*>(dst + 2 * lane) = uint16_t(q0 | (q1 << 8));
+    *reinterpret_cast<uint16_t*>(dst + 2 * lane) = uint16_t(kv_quant_pair(x0, x1, inv, q.fp8 != 0));
     if (lane == 0) (which ? q.v_scale : q.k_scale)[drow] = mx;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {

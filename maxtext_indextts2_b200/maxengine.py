@@ -294,7 +294,7 @@ class MaxEngine:
         logits_scale=scale,
         logits_round_bf16=0 if config.logits_dot_in_fp32 else 1,
         embedding_rows=config.vocab_size,
-        kv_quant=(2 if config.kv_quant_axis == "heads_and_dkv" else 1) if config.quantize_kvcache else 0,
+        kv_quant=((2 if config.kv_quant_axis == "heads_and_dkv" else 1) + (2 if config.kv_quant_dtype == "fp8" else 0)) if config.quantize_kvcache else 0,
         norm_scales_folded=1 if config.fold_norm_scales else 0,
         decoder_block=1 if config.decoder_block == "gemma3" else 0,
         sliding_window=int(config.sliding_window_size) if config.decoder_block == "gemma3" else 0,
@@ -347,10 +347,13 @@ class MaxEngine:
     i32 = torch.int32
     z = lambda *shape, dtype=i32: torch.zeros(*shape, dtype=dtype, device=dev)
     self._kv_quant = bool(cfg.quantize_kvcache)
+    self._kv_fp8 = self._kv_quant and cfg.kv_quant_dtype == "fp8"
+    self._kv_zero = 0 if self._kv_fp8 else 128  # the byte of the value 0: e4m3 +0, or q + 128 with q = 0
     if self._kv_quant:
-      # int8 decode cache (u = q + 128) + one fp32 scale per (layer, slot, kv head, row); prefill writes ONE bf16 staging plane
-      self._kq = torch.full((L, S, Hkv, T, D), 128, dtype=torch.uint8, device=dev)
-      self._vq = torch.full((L, S, Hkv, T, D), 128, dtype=torch.uint8, device=dev)
+      # int8 decode cache (u = q + 128; or float8_e4m3fn bytes) + one fp32 scale per (layer, slot, kv head, row); prefill writes ONE
+      # bf16 staging plane
+      self._kq = torch.full((L, S, Hkv, T, D), self._kv_zero, dtype=torch.uint8, device=dev)
+      self._vq = torch.full((L, S, Hkv, T, D), self._kv_zero, dtype=torch.uint8, device=dev)
       self._k_scale = z(L, S, Hkv, T, dtype=torch.float32)
       self._v_scale = z(L, S, Hkv, T, dtype=torch.float32)
       self._k = z(L, 1, Hkv, T, D, dtype=torch.bfloat16)
@@ -463,8 +466,8 @@ class MaxEngine:
       t.zero_()
     self._rng_state[0:1].zero_()
     if self._kv_quant:
-      self._kq.fill_(128)
-      self._vq.fill_(128)
+      self._kq.fill_(self._kv_zero)
+      self._vq.fill_(self._kv_zero)
       self._k_scale.zero_()
       self._v_scale.zero_()
     if self._logits is not None:
@@ -675,8 +678,12 @@ class MaxEngine:
         step = 1 << 26
         for lo in range(0, flat.numel(), step):
           n = min(step, flat.numel() - lo)
-          flat[lo : lo + n] = torch.randint(1, 256, (n,), device=self.device, generator=g, dtype=torch.int32).to(torch.uint8)
-        buf[..., 0] = 255  # q = 127: the row's largest magnitude
+          if self._kv_fp8:  # finite e4m3 values in [-448, 448] (the byte patterns 0x7f / 0xff are NaN)
+            vals = (torch.rand(n, device=self.device, generator=g) * 2.0 - 1.0) * 448.0
+            flat[lo : lo + n] = vals.to(torch.float8_e4m3fn).view(torch.uint8)
+          else:
+            flat[lo : lo + n] = torch.randint(1, 256, (n,), device=self.device, generator=g, dtype=torch.int32).to(torch.uint8)
+        buf[..., 0] = 0x7E if self._kv_fp8 else 255  # the row's largest magnitude: e4m3 448, or q = 127
       for sc in (self._k_scale, self._v_scale):
         sc.copy_(torch.randn(sc.shape, device=self.device, generator=g).abs() + 2.0)
     for buf in (() if self._kv_quant else (self._k, self._v)):

@@ -110,8 +110,8 @@ def _validate(keys: dict) -> None:
   if keys["quantize_kvcache"]:
     # inference/kvcache.py:36-90.  Implemented: int8 with kv_quant_axis "dkv" (one scale per token and kv head, fused into the QKV
     # epilogue) and "heads_and_dkv" (the reference's default: one scale per token over all kv heads; a small kernel after the QKV GEMM).
-    if keys["kv_quant_dtype"] != "int8":
-      raise ValueError(f"Invalid kv_quant_dtype: {keys['kv_quant_dtype']} (this decode path implements int8)")
+    if keys["kv_quant_dtype"] not in ("int8", "fp8"):
+      raise ValueError(f"Invalid kv_quant_dtype: {keys['kv_quant_dtype']} (this decode path implements int8 and fp8)")
     if keys["kv_quant_axis"] not in ("dkv", "heads_and_dkv"):
       raise ValueError(f"Invalid KV quant axis cfg: {keys['kv_quant_axis']}")  # kvcache.py:73
     if keys["head_dim"] != 64:

@@ -151,13 +151,17 @@ class DecodeOracle:
     self.softmax_f32 = self.scores_f32 or bool(config.float32_logits)
 
   def kv_quant(self, x):
-    """KVQuant.quantize + dequantisation (inference/kvcache.py:76-90, int8, kv_quant_axis "dkv": one scale per token and kv
-    head): scale = max|x| over the head's dims, q = int8(rint(x * 127.5 / scale)) (the conversion saturates: the row's maximum
+    """KVQuant.quantize + dequantisation (inference/kvcache.py:76-90; int8 or fp8; kv_quant_axis "dkv": one scale per token and kv
+    head, or "heads_and_dkv"): scale = max|x| over the head's dims, q = int8(rint(x * 127.5 / scale)) (the conversion saturates: the row's maximum
     maps to rint(127.5) = 128 -> 127), cached value = q * scale / 127.5.  Identity unless quantize_kvcache."""
     if not getattr(self.cfg, "quantize_kvcache", False):
       return x
     # kvcache.py:66-73: "dkv" takes the maximum over the head's dims, "heads_and_dkv" over the kv heads as well (x [..., Hkv, D])
     scale = x.abs().amax(dim=(-2, -1) if self.cfg.kv_quant_axis == "heads_and_dkv" else -1, keepdim=True)
+    if self.cfg.kv_quant_dtype == "fp8":
+      # kvcache.py:38,86-88: value = float8_e4m3fn(x * (E4M3_MAX / scale)), E4M3_MAX = 448; dequantised value * scale / 448
+      q = torch.where(scale > 0, (x * (448.0 / scale.clamp(min=1e-30))).to(torch.float8_e4m3fn).to(torch.float32), torch.zeros_like(x))
+      return q * (scale / 448.0)
     q = torch.where(scale > 0, torch.clamp(torch.round(x * (127.5 / scale.clamp(min=1e-30))), -128.0, 127.0), torch.zeros_like(x))
     return q * (scale / 127.5)
 

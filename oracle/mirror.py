@@ -82,8 +82,12 @@ def mirror_state(engine, oracle: ref.DecodeOracle, slots) -> dict:
     if quant:  # int8 cache: the oracle holds the dequantised values q * scale / 127.5 (kvcache.py:76-90)
       ks = engine._k_scale[l].index_select(0, sl).to("cpu")[..., None]
       vs = engine._v_scale[l].index_select(0, sl).to("cpu")[..., None]
-      k = (engine._kq[l].index_select(0, sl).to("cpu").to(torch.float32) - 128.0) * (ks / 127.5)
-      v = (engine._vq[l].index_select(0, sl).to("cpu").to(torch.float32) - 128.0) * (vs / 127.5)
+      if getattr(engine, "_kv_fp8", False):  # float8_e4m3fn bytes: value * scale / 448
+        k = engine._kq[l].index_select(0, sl).to("cpu").view(torch.float8_e4m3fn).to(torch.float32) * (ks / 448.0)
+        v = engine._vq[l].index_select(0, sl).to("cpu").view(torch.float8_e4m3fn).to(torch.float32) * (vs / 448.0)
+      else:
+        k = (engine._kq[l].index_select(0, sl).to("cpu").to(torch.float32) - 128.0) * (ks / 127.5)
+        v = (engine._vq[l].index_select(0, sl).to("cpu").to(torch.float32) - 128.0) * (vs / 127.5)
     else:
       k = engine._k[l].index_select(0, sl).to("cpu").to(torch.float32)  # [n, Hkv, T, D]
       v = engine._v[l].index_select(0, sl).to("cpu").to(torch.float32)

@@ -17,10 +17,12 @@ from tests.helpers import make_params, random_tokens, small_config
 pytestmark = pytest.mark.gpu
 
 QUANT = dict(quantize_kvcache=True, kv_quant_dtype="int8", kv_quant_axis="dkv")
-AXES = ["dkv", "heads_and_dkv"]
+AXES = ["dkv", "heads_and_dkv", "fp8-dkv", "fp8-heads_and_dkv"]  # kv_quant_dtype int8 unless prefixed
 
 
 def _quant(axis):
+  if axis.startswith("fp8-"):
+    return dict(QUANT, kv_quant_axis=axis[4:], kv_quant_dtype="fp8")
   return dict(QUANT, kv_quant_axis=axis)
 
 
@@ -29,8 +31,9 @@ def test_config_accepts_only_the_implemented_quantiser():
   assert pyconfig.initialize(None, head_dim=64, quantize_kvcache=True).kv_quant_axis == "heads_and_dkv"  # the reference default
   with pytest.raises(ValueError, match="axis"):
     pyconfig.initialize(None, head_dim=64, quantize_kvcache=True, kv_quant_axis="heads")
+  assert pyconfig.initialize(None, head_dim=64, quantize_kvcache=True, kv_quant_axis="dkv", kv_quant_dtype="fp8").kv_quant_dtype == "fp8"
   with pytest.raises(ValueError, match="kv_quant_dtype"):
-    pyconfig.initialize(None, head_dim=64, quantize_kvcache=True, kv_quant_axis="dkv", kv_quant_dtype="fp8")
+    pyconfig.initialize(None, head_dim=64, quantize_kvcache=True, kv_quant_axis="dkv", kv_quant_dtype="int4")
 
 
 @pytest.mark.parametrize("axis", AXES)
@@ -54,12 +57,20 @@ def test_prefill_insert_and_decode_with_int8_cache_match_the_quantised_oracle(ax
     for name, src in (("key", prefix["cache"]["key"]), ("value", prefix["cache"]["value"])):
       x = src.float().cpu()  # [L, Hkv, n, D]
       scale = x.abs().amax(-1)
-      if axis == "heads_and_dkv":  # one scale per token: the maximum over the kv heads too, stored once per head
+      if axis.endswith("heads_and_dkv"):  # one scale per token: the maximum over the kv heads too, stored once per head
         scale = scale.amax(1, keepdim=True).expand_as(scale)
-      q = torch.clamp(torch.round(x * (127.5 / scale.clamp(min=1e-30))[..., None]), -128, 127)
-      got_q = state["cache"][name][:, slot, :, :n].cpu().to(torch.int32) - 128
       got_s = state["cache"][name + "_scale"][:, slot, :, :n].cpu()
       torch.testing.assert_close(got_s, scale, rtol=0, atol=0)
+      raw = state["cache"][name][:, slot, :, :n].cpu()
+      if axis.startswith("fp8-"):
+        want = (x * (448.0 / scale.clamp(min=1e-30))[..., None]).to(torch.float8_e4m3fn).to(torch.float32)
+        got = raw.view(torch.float8_e4m3fn).to(torch.float32)
+        d = (got - want).abs()
+        # (x * (448 / scale) lands within an fp32 ulp of a rounding boundary for a few elements: one e4m3 step, <= 1/8 relative)
+        assert (d <= 0.126 * want.abs().clamp(min=2.0**-6)).all() and (d > 0).float().mean() < 5e-3
+        continue
+      q = torch.clamp(torch.round(x * (127.5 / scale.clamp(min=1e-30))[..., None]), -128, 127)
+      got_q = raw.to(torch.int32) - 128
       d = (got_q - q.to(torch.int32)).abs()
       assert d.max() <= 1 and (d > 0).float().mean() < 5e-3  # x * (127.5 / scale) lands within an fp32 ulp of a .5 boundary for ~0.1 % of the elements
   for step in range(16):  # ring of 12 rows: wraps
@@ -101,8 +112,12 @@ def test_int8_decode_on_a_synthetic_cache_against_the_oracle(batch, axis):
   # the appended rows are quantised rows: every row written this run has its scale > 0 and a byte of magnitude 127 or 128
   idx = int(state["cache"]["cache_ar_index"].item())
   P = cfg.max_prefill_predict_length
-  last = state["cache"]["key"][:, slots[0], :, P + idx - 1].cpu().to(torch.int32) - 128
-  if axis == "dkv":
+  last = state["cache"]["key"][:, slots[0], :, P + idx - 1].cpu()
+  if axis.startswith("fp8-"):  # magnitude 448 (byte 0x7e / 0xfe) instead of 127 / 128
+    last = (last.view(torch.float8_e4m3fn).to(torch.float32).abs() >= 448).to(torch.int32) * 127
+  else:
+    last = last.to(torch.int32) - 128
+  if axis in ("dkv", "fp8-dkv"):
     assert (last.abs().amax(-1) >= 127).all()
   else:  # one scale per token: the maximum sits in ONE of the heads, and the heads share the scale
     assert (last.abs().amax(dim=(-2, -1)) >= 127).all()
