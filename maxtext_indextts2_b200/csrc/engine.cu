@@ -791,6 +791,7 @@ int launch_persistent(mtx_engine* e, int rows, const XMaps& xm, const EpiArgs& l
   p.trace = g_trace;
   p.trace_bars = pk_trace_bars(c.num_layers);
   p.variant = env_int("MTX_PK_VARIANT", 0);
+  p.attn_skew = float(env_int("MTX_PK_ATTN_SKEW", 0)) * 0.01f;  // percent
   p.fold = c.norm_scales_folded ? 1 : 0;
   // The kernel spins on a software grid barrier.  MTX_PK_COOPERATIVE=1 launches it cooperatively, so the driver guarantees that
   // all CTAs are resident together (or fails the launch) whatever else shares the device: the setting for a GPU shared with

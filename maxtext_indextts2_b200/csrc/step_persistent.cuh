@@ -140,6 +140,7 @@ struct PkParams {
   int trace_bars;          // barrier slots of the trace buffer (>= 2 + 5 L + 1, see mtx_step_trace_words)
   int variant;             // experiment switches (MTX_PK_VARIANT): bit 0 = L2 prefetch of the next layer's K/V tiles at the end of a
                            // warp's tile loop, bit 1 = L2 prefetch of this layer's K/V tiles at the start of the layer
+  float attn_skew;         // attention tile partition: see pk_cta_lo (0 = equal shares)
   int fold;                // 1: the RMSNorm scales are folded into wqkv / w01 (mtx_model_config.norm_scales_folded): no scale pass
 };
 
@@ -701,21 +702,36 @@ __device__ __forceinline__ void pk_attn_next(PkAttnPos& a, const PkParams& p, co
 }
 
 // CTA that owns flattened tile g when `nc` CTAs share `total` tiles.
-__device__ __forceinline__ int pk_cta_of(long long g, long long nc, long long total) { return int(((g + 1) * nc - 1) / total); }
+// First tile of CTA c when `nc` CTAs share `total` tiles.  skew = 0: equal shares.  skew > 0 (experiment, MTX_PK_ATTN_SKEW): CTA c's
+// share is proportional to 1 + skew (1/2 - c / nc) -- the CTAs with high indices finish their tile loops ~1 us later than the first
+// ones at equal shares (profiles/r2z_dataflow_trace.txt, per-decile loop ends).
+__device__ __forceinline__ int pk_cta_lo(int c, int nc, int total, float skew) {
+  if (c >= nc) return total;
+  if (skew == 0.0f) return int((long long)c * total / nc);
+  const double x = double(c) / double(nc);
+  return int((x * (1.0 + 0.5 * double(skew)) - 0.5 * double(skew) * x * x) * double(total));
+}
+__device__ __forceinline__ int pk_cta_of(long long g, long long nc, long long total, float skew) {
+  if (skew == 0.0f) return int(((g + 1) * nc - 1) / total);
+  int c = int(g * nc / total);
+  while (c > 0 && pk_cta_lo(c, int(nc), int(total), skew) > g) --c;
+  while (c + 1 < nc && pk_cta_lo(c + 1, int(nc), int(total), skew) <= g) ++c;
+  return c;
+}
 
 // Tiles [wlo, whi) of attention warp a of CTA c (equal contiguous runs per CTA, equal sub-runs per warp).
-__device__ __forceinline__ void pk_warp_range(int c, int a, int nc, int total, int& wlo, int& whi) {
-  const int clo = int((long long)c * total / nc), chi = int((long long)(c + 1) * total / nc);
+__device__ __forceinline__ void pk_warp_range(int c, int a, int nc, int total, float skew, int& wlo, int& whi) {
+  const int clo = pk_cta_lo(c, nc, total, skew), chi = pk_cta_lo(c + 1, nc, total, skew);
   wlo = clo + a * (chi - clo) / kPkAttnWarps;
   whi = clo + (a + 1) * (chi - clo) / kPkAttnWarps;
 }
 // Number of warps that hold tiles, from warp 0 of CTA c0 up to (not including) the first warp starting at or after g_stop.
-__device__ __noinline__ int pk_count_warps(int c0, int g_stop, int nc, int total) {
+__device__ __noinline__ int pk_count_warps(int c0, int g_stop, int nc, int total, float skew) {
   int count = 0;
   for (int c = c0; c < nc; ++c)
     for (int a = 0; a < kPkAttnWarps; ++a) {
       int wlo, whi;
-      pk_warp_range(c, a, nc, total, wlo, whi);
+      pk_warp_range(c, a, nc, total, skew, wlo, whi);
       if (wlo >= g_stop) return count;
       if (whi > wlo) ++count;
     }
@@ -734,7 +750,8 @@ __device__ __forceinline__ void pk_attn_build_list(const PkParams& p, PkTail* ta
   const int R = p.T - p.P;
   int n = 0, tail_slot = -1;
   if (cta < nc && total > 0) {
-    int clo = int((long long)cta * total / nc), chi = int((long long)(cta + 1) * total / nc);
+    const float skew = p.attn_skew;
+    int clo = pk_cta_lo(cta, nc, total, skew), chi = pk_cta_lo(cta + 1, nc, total, skew);
     if (pair_mode) {
       const int r = cta / p.hkv, h = cta - r * p.hkv;
       const int nt = attn_num_tiles(tail->r_len0[r], tail->r_rf[r], tail->r_rl[r], R);
@@ -751,8 +768,8 @@ __device__ __forceinline__ void pk_attn_build_list(const PkParams& p, PkTail* ta
       const int g_first = tail->r_prefix[pos.r] * p.hkv + pos.h * pos.nt;
       bool is_tail = !pair_mode && g_first < clo;
       if (is_tail) {
-        const int c_first = pk_cta_of(g_first, nc, total);
-        const int ordinal = pk_count_warps(c_first + 1, wlo, nc, total);
+        const int c_first = pk_cta_of(g_first, nc, total, skew);
+        const int ordinal = pk_count_warps(c_first + 1, wlo, nc, total, skew);
         if (ordinal >= kPkMaxParts) __trap();  // excluded by prepare_rows_kernel's choice of nc
         tail_slot = (pos.r * p.hkv + pos.h) * kPkMaxParts + ordinal;
       }
@@ -794,7 +811,7 @@ __device__ __forceinline__ void pk_attn_build_list(const PkParams& p, PkTail* ta
               if (wl >= g_end) break;
               if (wh > wl) jb.src[jb.n_src++] = wh <= g_end ? w : 8 + w;
             }
-            jb.n_parts = g_end > chi ? pk_count_warps(cta + 1, g_end, nc, total) : 0;
+            jb.n_parts = g_end > chi ? pk_count_warps(cta + 1, g_end, nc, total, skew) : 0;
             if (lane == 0) tail->a_jobs[nj] = jb;
             ++nj;
           }
