@@ -85,6 +85,13 @@ typedef struct {
   int32_t sliding_window;          /* sliding_window_size of the local layers (gemma3), 0 = none */
   float local_rope_max_timescale;  /* RoPE base of the local layers; <= 0: rope_max_timescale */
   float query_scalar;              /* query_pre_attn_scalar (gemma3.py:51-58); 0 or 1 = none */
+  /* attention=paged (configs/base.yml:737-746; inference/paged_attention.py, inference/page_manager.py).  paged_num_pages > 0: the
+   * decode cache is the page pools decode_state.k_pages / v_pages, addressed through decode_state.page_map etc. (the device copy of
+   * PageState); k_cache / v_cache are then ONE bf16 staging plane [L, 1, Hkv, T, D] that prefill writes (as with kv_quant) and
+   * mtx_insert_prefix copies a prefix into the pages of its group.  llama2 block, bf16 cache only. */
+  int32_t paged_num_pages;           /* pagedattn_num_pages, 0 = contiguous cache */
+  int32_t paged_tokens_per_page;     /* pagedattn_tokens_per_page: a power of two >= 8 */
+  int32_t paged_max_pages_per_group; /* pagedattn_max_pages_per_group (>= ceil(T / tokens_per_page)) */
 } mtx_model_config;
 
 /* Weights, repacked once at load time for K-major streaming (see DESIGN.md "Data layout").
@@ -144,6 +151,16 @@ typedef struct {
   void* vq_cache;
   float* k_scale;
   float* v_scale;
+  /* attention=paged only (else NULL): the page pools [L, Hkv, num_pages, tokens_per_page, D] bf16 (PagedAttentionOp.key_pages /
+   * value_pages, paged_attention.py:152-160, one pool for all layers) and the device copy of the PageState fields a step reads
+   * (page_manager.py:49-91), one page group per decode slot: the caller runs PageManager.update_decode_pages BEFORE the step
+   * (maxengine.py:847-849) and refreshes these arrays. */
+  void* k_pages;
+  void* v_pages;
+  int32_t* page_map;        /* [num_slots, max_pages_per_group] */
+  int32_t* page_lengths;    /* [num_slots] sequence_lengths (this step's token included) */
+  int32_t* active_page;     /* [num_slots] */
+  int32_t* active_page_pos; /* [num_slots] active_page_position */
 } mtx_decode_state;
 
 /* ---- engine ---------------------------------------------------------------------------- */
@@ -267,6 +284,28 @@ size_t mtx_ragged_attention_scratch_bytes(int rows, int num_kv_heads, int num_q_
 int mtx_ragged_attention(const void* q, const void* k, const void* v, const int32_t* lengths, void* out, float* out_max, float* out_sum,
                          int rows, int seq_len, int num_q_heads, int num_kv_heads, int head_dim, int seq_major, float softcap,
                          void* scratch, mtx_stream stream);
+
+/* ---- paged KV cache (attention=paged) as single ops ------------------------------------------------------------------------
+ * PagedAttentionOp in autoregressive mode (inference/paged_attention.py:348-401): update_decode_step_pages (:446-471) then
+ * paged_attention_v1_decode (:302-346; the kernel itself is jax.experimental.pallas.ops.tpu.paged_attention, third-party:
+ * softmax(q . K[:len]) V[:len] over the group's pages, no scaling of q).
+ *   k_pages, v_pages [Hkv, num_pages, tokens_per_page, D] bf16 (one layer); tokens_per_page a power of two >= 8;
+ *   page_map [groups, max_pages_per_group], lengths / active_page / active_pos [groups] int32: PageState.page_map,
+ *   sequence_lengths, active_page, active_page_position (page_manager.py:49-91); row r is page group r. */
+/* k_new, v_new [rows, Hkv, D] -> pages[h, active_page[r], active_pos[r]] for every row (inactive groups write page 0). */
+int mtx_paged_append(void* k_pages, void* v_pages, const void* k_new, const void* v_new, const int32_t* active_page,
+                     const int32_t* active_pos, int rows, int num_kv_heads, int head_dim, int num_pages, int tokens_per_page,
+                     mtx_stream stream);
+/* q, out [rows, Hq*D] bf16; a row of length 0 gets no output (its `out` row is left as it was). */
+size_t mtx_paged_attention_scratch_bytes(int rows, int num_kv_heads, int num_q_heads, int head_dim, int max_tokens);
+int mtx_paged_attention(const void* q, const void* k_pages, const void* v_pages, const int32_t* lengths, const int32_t* page_map,
+                        void* out, int rows, int num_q_heads, int num_kv_heads, int head_dim, int num_pages, int tokens_per_page,
+                        int max_pages_per_group, float softcap, void* scratch, mtx_stream stream);
+/* MaxEngine._insert_jit's `_copy_paged` (maxengine.py:1104-1131): the first n_tokens rows of a prefix (k_src / v_src
+ * [layers, Hkv, n_src_rows, D], i.e. the prefix's pages read as rows) into the pool pages page_map_row[i] (device, the group's row
+ * of PageState.page_map); pools [layers, Hkv, num_pages, tokens_per_page, D]. */
+int mtx_paged_insert(void* k_pages, void* v_pages, const void* k_src, const void* v_src, const int32_t* page_map_row, int layers,
+                     int num_kv_heads, int head_dim, int n_src_rows, int n_tokens, int num_pages, int tokens_per_page, mtx_stream stream);
 
 /* Attention.query/key/value projections + RotaryEmbedding + KVCache append of one decode step (attentions.py:1894-2030,
  * 2236-2265; embeddings.py:277-315; kvcache.py:626-718) as ONE GEMM with a fused epilogue:

@@ -60,6 +60,9 @@ class ModelConfig(ctypes.Structure):
       ("sliding_window", ctypes.c_int32),
       ("local_rope_max_timescale", ctypes.c_float),
       ("query_scalar", ctypes.c_float),
+      ("paged_num_pages", ctypes.c_int32),
+      ("paged_tokens_per_page", ctypes.c_int32),
+      ("paged_max_pages_per_group", ctypes.c_int32),
   ]
 
 
@@ -91,6 +94,12 @@ class DecodeState(ctypes.Structure):
           "vq_cache",
           "k_scale",
           "v_scale",
+          "k_pages",
+          "v_pages",
+          "page_map",
+          "page_lengths",
+          "active_page",
+          "active_page_pos",
       )
   ]
 
@@ -204,6 +213,14 @@ def _declare(lib) -> None:
   lib.mtx_qkv_rope_append_scratch_bytes.argtypes = [i32, i32]
   lib.mtx_qkv_rope_append.restype = i32
   lib.mtx_qkv_rope_append.argtypes = [vp] * 8 + [i32] * 6 + [f32, f32, vp, vp]
+  lib.mtx_paged_append.restype = i32
+  lib.mtx_paged_append.argtypes = [vp] * 6 + [i32] * 5 + [vp]
+  lib.mtx_paged_attention_scratch_bytes.restype = sz
+  lib.mtx_paged_attention_scratch_bytes.argtypes = [i32] * 5
+  lib.mtx_paged_attention.restype = i32
+  lib.mtx_paged_attention.argtypes = [vp] * 6 + [i32] * 7 + [f32, vp, vp]
+  lib.mtx_paged_insert.restype = i32
+  lib.mtx_paged_insert.argtypes = [vp] * 5 + [i32] * 7 + [vp]
   lib.mtx_jax_ffi_available.restype = i32
   lib.mtx_jax_ffi_available.argtypes = []
   lib.mtx_engine_rebind_state.restype = i32

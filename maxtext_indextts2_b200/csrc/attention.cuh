@@ -57,6 +57,14 @@ struct AttnParams {
   int ring_off;   // first ring index of the window (0: no window)
   int ring_size;  // ring indices in the window (0: the whole ring, T - P)
   const int* skip0_rows;  // [rows] or null: per-row addition to skip0 (prefill positions run as decode rows: position window)
+  // Paged KV cache (attention=paged: inference/paged_attention.py:302-346, page_manager.py:49-91).  page_map != null: K / V are page
+  // pools [Hkv, num_pages, tokens_per_page, D] (one layer at page_row_base rows into the tensor map), token i of the row's page
+  // group plane[r] lives in page page_map[plane[r]][i / tokens_per_page]; len0 is the group's sequence length, the ring is empty.
+  // The tensor maps' box is min(tokens_per_page, 64) rows: a 64-row tile is one slice of a page or 64 / tokens_per_page pages.
+  const int* page_map;   // [page groups, max_pages]
+  int tokens_per_page;   // power of two >= 8
+  int num_pages, max_pages;
+  long long page_row_base;
 };
 
 struct TileLoc { int p0, cnt; };
@@ -132,6 +140,38 @@ __global__ void attn_build_worklist_kernel(const int* len0, const int* ring_firs
   if (tid == 0) *work_count = s_off[rows];
 }
 
+// One thread requests 64-row tile `t` (physical row `row` when the cache is contiguous) of kv head `h` for row `r`: the whole tile,
+// or -- paged with pages shorter than the tile -- the pages that hold its `cnt` valid rows (the rest of the tile keeps stale
+// bytes: the scores of those rows are masked by selection and the value rows are zeroed before the P V product).
+template <int D>
+__device__ __forceinline__ void attn_issue_tile(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, const AttnParams& p, int r, int h, int t,
+                                                int cnt, int col0, int row) {
+  constexpr int kSub = D / 64;
+  if (p.page_map == nullptr) {
+    mbar_expect_tx(bar, 64 * D * 2);
+#pragma unroll
+    for (int s = 0; s < kSub; ++s) tma_load_2d(dst + s * 8192, tm, col0 + s * 64, row, bar, kEvictFirst);
+    return;
+  }
+  const int tpp = p.tokens_per_page;
+  const int* pm = p.page_map + (long long)p.plane[r] * p.max_pages;
+  const int tok = t * 64;
+  if (tpp >= 64) {
+    const long long prow = p.page_row_base + ((long long)h * p.num_pages + pm[tok / tpp]) * tpp + (tok & (tpp - 1));
+    mbar_expect_tx(bar, 64 * D * 2);
+#pragma unroll
+    for (int s = 0; s < kSub; ++s) tma_load_2d(dst + s * 8192, tm, s * 64, int(prow), bar, kEvictFirst);
+  } else {
+    const int nb = (cnt + tpp - 1) / tpp;
+    mbar_expect_tx(bar, nb * tpp * D * 2);
+    for (int j = 0; j < nb; ++j) {
+      const long long prow = p.page_row_base + ((long long)h * p.num_pages + pm[tok / tpp + j]) * tpp;
+#pragma unroll
+      for (int s = 0; s < kSub; ++s) tma_load_2d(dst + s * 8192 + j * tpp * 128, tm, s * 64, int(prow), bar, kEvictFirst);
+    }
+  }
+}
+
 // The attention work loop of 128 threads (4 warps).  `tiles` = [warp][K tile | V tile] (1024-byte
 // aligned), `sm_o_all` = merge buffer [warp][o_rows][D] fp32, `bars` = 2 initialised mbarriers per warp
 // (their current parity in `phase`, updated on return), `sm_stat` = 128 floats + 1 int.  Items are
@@ -185,12 +225,8 @@ __device__ __forceinline__ void attn_process_items(const CUtensorMap& tm_k, cons
     int t = t_begin + warp;
     TileLoc loc = attn_tile(t < t_end ? t : nt, len0, rf, rl, p.P, R, skip0, p.ring_off);  // t >= nt gives an empty tile
     if (t < t_end && lane == 0) {
-      mbar_expect_tx(bar_k, kTileBytes);
-#pragma unroll
-      for (int s = 0; s < kSub; ++s) tma_load_2d(k_tile + s * 8192, &tm_k, col0 + s * 64, plane_row + loc.p0, bar_k, kEvictFirst);
-      mbar_expect_tx(bar_v, kTileBytes);
-#pragma unroll
-      for (int s = 0; s < kSub; ++s) tma_load_2d(v_tile + s * 8192, &tm_v, col0 + s * 64, plane_row + loc.p0, bar_v, kEvictFirst);
+      attn_issue_tile<D>(k_tile, &tm_k, bar_k, p, r, h, t, loc.cnt, col0, plane_row + loc.p0);
+      attn_issue_tile<D>(v_tile, &tm_v, bar_v, p, r, h, t, loc.cnt, col0, plane_row + loc.p0);
     }
 
     // Q fragments (A operand, rows = query heads of the group, zero-padded to 16)
@@ -239,11 +275,7 @@ __device__ __forceinline__ void attn_process_items(const CUtensorMap& tm_k, cons
       // K tile consumed: refill it with the next tile's keys while the softmax and P V run
       fence_proxy_async();
       __syncwarp();
-      if (tn < t_end && lane == 0) {
-        mbar_expect_tx(bar_k, kTileBytes);
-#pragma unroll
-        for (int ss = 0; ss < kSub; ++ss) tma_load_2d(k_tile + ss * 8192, &tm_k, col0 + ss * 64, plane_row + nloc.p0, bar_k, kEvictFirst);
-      }
+      if (tn < t_end && lane == 0) attn_issue_tile<D>(k_tile, &tm_k, bar_k, p, r, h, tn, nloc.cnt, col0, plane_row + nloc.p0);
       // ---- mask + online softmax (quad shuffles) ----
       float tm0 = -INFINITY, tm1 = -INFINITY;
 #pragma unroll
@@ -313,11 +345,7 @@ __device__ __forceinline__ void attn_process_items(const CUtensorMap& tm_k, cons
       // V tile consumed: refill
       fence_proxy_async();
       __syncwarp();
-      if (tn < t_end && lane == 0) {
-        mbar_expect_tx(bar_v, kTileBytes);
-#pragma unroll
-        for (int ss = 0; ss < kSub; ++ss) tma_load_2d(v_tile + ss * 8192, &tm_v, col0 + ss * 64, plane_row + nloc.p0, bar_v, kEvictFirst);
-      }
+      if (tn < t_end && lane == 0) attn_issue_tile<D>(v_tile, &tm_v, bar_v, p, r, h, tn, nloc.cnt, col0, plane_row + nloc.p0);
       phase ^= 1;
       loc = nloc;
     }

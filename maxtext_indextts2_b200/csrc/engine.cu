@@ -19,6 +19,7 @@
 #include "gemm_rows.cuh"
 #include "gemm_umma.cuh"
 #include "gemma3_kernels.cuh"
+#include "paged_kv.cuh"
 #include "prefill_attention.cuh"
 #include "sampling.cuh"
 #include "step_kernels.cuh"
@@ -338,6 +339,7 @@ struct mtx_engine {
   std::vector<CUtensorMap> tm_wqkv, tm_wo, tm_w01, tm_wout;
   CUtensorMap tm_logits, tm_k, tm_v;
   CUtensorMap tm_kq, tm_vq;  // kv_quant: the int8 decode cache (tm_k / tm_v then address the bf16 prefill staging plane)
+  CUtensorMap tm_kp, tm_vp;  // attention=paged: the page pools as [L * Hkv * num_pages * tokens_per_page, D], box = min(page, 64) rows
   CUtensorMap tm_all_wqkv, tm_all_wo, tm_all_w01, tm_all_wout;  // all layers stacked: row = layer * N + n
   // persistent step kernel (step_persistent.cuh)
   int pk_ctas = 0;  // CTAs of the persistent grid (0 = unavailable)
@@ -391,6 +393,9 @@ struct WsLayout {
 // mtx_model_config.kv_quant: 1 / 2 = int8 with kv_quant_axis dkv / heads_and_dkv, 3 / 4 = the same with float8_e4m3fn bytes
 int kvq_axis(const mtx_model_config& c) { return c.kv_quant == 0 ? 0 : (c.kv_quant - 1) % 2 + 1; }
 bool kvq_fp8(const mtx_model_config& c) { return c.kv_quant >= 3; }
+// attention=paged: the decode cache is the page pools; like an int8 engine, prefill then writes ONE bf16 staging plane
+bool is_paged(const mtx_model_config& c) { return c.paged_num_pages > 0; }
+bool staged_prefill(const mtx_model_config& c) { return c.kv_quant != 0 || is_paged(c); }
 
 WsLayout layout_workspace(const mtx_engine* e) {
   const mtx_model_config& c = e->cfg;
@@ -423,7 +428,7 @@ WsLayout layout_workspace(const mtx_engine* e) {
   L.work_items = take(size_t(c.max_rows) * e->attn_max_chunks * 4);
   L.work_count = take(4);
   L.rope_timescale = take((c.head_dim / 2) * 4);
-  if (kvq_axis(c) == 2) {
+  if (kvq_axis(c) == 2 || is_paged(c)) {
     L.iota = take(rt * 4);
     L.tmp_row = take(rt * 4);
     L.kv_tmp_k = take(rt * c.num_kv_heads * c.head_dim * 2);
@@ -540,6 +545,15 @@ int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st, int mo
   int grid = rows * c.num_kv_heads * attn_max_chunks(c.max_prefill_len, c.max_target_len, p.tiles_per_item);
   const int cap = e->num_sms * ctas_per_sm;
   if (grid > cap) grid = cap;
+  if (is_paged(c) && mode == 0) {  // decode rows read the page pools through the group's row of the page map (row r = group r)
+    p.page_map = e->s.page_map;
+    p.tokens_per_page = c.paged_tokens_per_page;
+    p.num_pages = c.paged_num_pages;
+    p.max_pages = c.paged_max_pages_per_group;
+    p.page_row_base = (long long)layer * c.num_kv_heads * c.paged_num_pages * c.paged_tokens_per_page;
+    if (c.head_dim == 64) return launch(decode_attn_kernel<64>, dim3(grid), dim3(kAttnThreads), smem, st, e->tm_kp, e->tm_vp, p);
+    return launch(decode_attn_kernel<128>, dim3(grid), dim3(kAttnThreads), smem, st, e->tm_kp, e->tm_vp, p);
+  }
   if (c.kv_quant) {
     const size_t smem_q = attn_q8_smem_bytes(c.num_q_heads / c.num_kv_heads);
     int grid_q = rows * c.num_kv_heads * attn_max_chunks(c.max_prefill_len, c.max_target_len, p.tiles_per_item);
@@ -573,7 +587,7 @@ bool use_prefill_attention(const mtx_engine* e) {
 
 int launch_prefill_attention(mtx_engine* e, int layer, int rows, int start_pos, int slot, cudaStream_t st) {
   const mtx_model_config& c = e->cfg;
-  const int planes = c.kv_quant ? 1 : c.num_slots;  // an int8 engine prefills into its single bf16 staging plane
+  const int planes = staged_prefill(c) ? 1 : c.num_slots;  // an int8 / paged engine prefills into its single bf16 staging plane
   PrefillAttnParams p;
   memset(&p, 0, sizeof(p));
   p.q = e->q;
@@ -730,7 +744,7 @@ bool pk_fill_phase(std::vector<PkTable>& tabs, int ph, int n, int k, bool allow_
 int pk_trace_bars(int layers) { return 2 + 5 * layers + 2 > 200 ? 2 + 5 * layers + 2 : 200; }
 
 bool pk_usable(const mtx_engine* e, int rows) {
-  if (e->pk_ctas <= 0 || round_rows(rows) > kPkMaxRTile || e->cfg.kv_quant || e->cfg.decoder_block != 0) return false;
+  if (e->pk_ctas <= 0 || round_rows(rows) > kPkMaxRTile || e->cfg.kv_quant || e->cfg.decoder_block != 0 || is_paged(e->cfg)) return false;
   if (e->cfg.num_q_heads / e->cfg.num_kv_heads > 8) return false;  // the attention MMA carries the group's heads in its 8 columns
   // an attention warp's tile list holds kPkAttnListMax entries: bound the worst case (every context full)
   const mtx_model_config& c = e->cfg;
@@ -818,8 +832,8 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   XMaps* xm;
   MTX_TRY(get_xmaps(e, r_tile, &xm));
   // prefill (mode 1) of an int8 engine writes the ONE bf16 staging plane that k_cache / v_cache then are
-  const int planes = (c.kv_quant && mode == 1) ? 1 : c.num_slots;
-  if (c.kv_quant && mode == 1) slot = 0;
+  const int planes = (staged_prefill(c) && mode == 1) ? 1 : c.num_slots;
+  if (staged_prefill(c) && mode == 1) slot = 0;
   const int E = c.emb_dim, HD = c.num_q_heads * c.head_dim, M = c.mlp_dim, L = c.num_layers;
   const size_t kv_layer = size_t(planes) * c.num_kv_heads * c.max_target_len * c.head_dim;
   const size_t kvq_layer = size_t(c.num_slots) * c.num_kv_heads * c.max_target_len * c.head_dim;  // bytes of one layer of the int8 cache
@@ -844,6 +858,7 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   pa.emb_rows = c.embedding_rows;
   pa.rope_timescale = e->rope_timescale;
   pa.window = gemma3 ? c.sliding_window : 0;
+  pa.page_lengths = (is_paged(c) && mode == 0) ? e->s.page_lengths : nullptr;
   pa.rope_timescale_w = e->rope_timescale_w;
   const bool mega = mode == 0 && want_logits && pk_usable(e, rows);
   if (mega) {
@@ -1000,7 +1015,8 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
       ea.vq_cache = static_cast<uint8_t*>(e->s.vq_cache) + kvq_layer * l;
       ea.k_scale = e->s.k_scale + kvs_layer * l;
       ea.v_scale = e->s.v_scale + kvs_layer * l;
-    } else if (kvq_axis(c) == 2 && mode == 0) {
+    } else if ((kvq_axis(c) == 2 || is_paged(c)) && mode == 0) {
+      // (attention=paged: the same scratch matrices, paged_append_kernel then writes the rows into the groups' active pages)
       // one scale per token over all kv heads (kv_quant_axis heads_and_dkv): the epilogue leaves the rotated keys / values as
       // bf16 in [rows, Hkv, D] scratch matrices (plane = row, write row = 0), kv_quant_rows_kernel quantises and appends
       ea.k_cache = e->kv_tmp_k;
@@ -1033,6 +1049,22 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
       ka.t_alloc = c.max_target_len;
       ka.fp8 = kvq_fp8(c) ? 1 : 0;
       MTX_TRY(launch(kv_quant_rows_kernel, dim3(rows, 2), dim3(c.num_kv_heads * 32), 0, st, ka));
+    }
+    if (is_paged(c) && mode == 0) {  // update_decode_step_pages (paged_attention.py:446-471)
+      const size_t pool_layer = size_t(c.num_kv_heads) * c.paged_num_pages * c.paged_tokens_per_page * c.head_dim;
+      PagedAppendArgs pg;
+      memset(&pg, 0, sizeof(pg));
+      pg.k_new = e->kv_tmp_k;
+      pg.v_new = e->kv_tmp_v;
+      pg.k_pages = static_cast<bf16*>(e->s.k_pages) + pool_layer * l;
+      pg.v_pages = static_cast<bf16*>(e->s.v_pages) + pool_layer * l;
+      pg.active_page = e->s.active_page;
+      pg.active_pos = e->s.active_page_pos;
+      pg.hkv = c.num_kv_heads;
+      pg.d = c.head_dim;
+      pg.num_pages = c.paged_num_pages;
+      pg.tokens_per_page = c.paged_tokens_per_page;
+      MTX_TRY(launch(paged_append_kernel, dim3(rows), dim3(128), 0, st, pg));
     }
 
     g_class = KC_ATTENTION;
@@ -1336,6 +1368,18 @@ int mtx_engine_create(const mtx_model_config* cfg, mtx_engine** out) {
   if (c.decoder_block != 0 && c.decoder_block != 1) return fail(MTX_ERR_ARG, "decoder_block must be 0 (llama2) or 1 (gemma3)");
   if (c.decoder_block == 1 && (c.kv_quant || !c.norm_scales_folded || c.sliding_window <= 0))
     return fail(MTX_ERR_UNSUPPORTED, "the gemma3 block needs a bf16 KV cache, norm_scales_folded and a sliding_window");
+  if (is_paged(c)) {
+    const int tpp = c.paged_tokens_per_page;
+    if (c.kv_quant || c.decoder_block != 0) return fail(MTX_ERR_UNSUPPORTED, "attention=paged: bf16 cache and the llama2 block only");
+    if (c.head_dim != 64 && c.head_dim != 128) return fail(MTX_ERR_UNSUPPORTED, "attention=paged: head_dim 64 or 128");
+    if (tpp < 8 || (tpp & (tpp - 1)) != 0) return fail(MTX_ERR_UNSUPPORTED, "pagedattn_tokens_per_page must be a power of two >= 8");
+    if (c.paged_num_pages <= 1) return fail(MTX_ERR_ARG, "`pagedattn_num_pages` must be greater than 1.");
+    if (c.paged_max_pages_per_group < (c.max_target_len + tpp - 1) / tpp)
+      return fail(MTX_ERR_ARG, "`pagedattn_max_pages_per_group` (%d) is insufficient for `max_target_length` (%d). Needs %d.",
+                  c.paged_max_pages_per_group, c.max_target_len, (c.max_target_len + tpp - 1) / tpp);
+    if (uint64_t(c.num_layers) * c.num_kv_heads * c.paged_num_pages * tpp >= (1ull << 31))
+      return fail(MTX_ERR_UNSUPPORTED, "the page pools have too many rows for one tensor map");
+  }
   e->max_r_tile = round_rows(c.max_rows);
   if (c.kv_quant && e->max_r_tile < 128) e->max_r_tile = 128;  // every step of an int8 engine runs the 128-row-block GEMM
   if (c.decoder_block == 1 && e->max_r_tile < 128) e->max_r_tile = 128;  // and so does every step of the gemma3 block
@@ -1409,7 +1453,7 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   e->rd.work_count = reinterpret_cast<int*>(b + L.work_count);
   e->rope_timescale = reinterpret_cast<float*>(b + L.rope_timescale);
   e->rd.iota = e->rd.tmp_row = nullptr;
-  if (kvq_axis(c) == 2) {
+  if (kvq_axis(c) == 2 || is_paged(c)) {
     e->rd.iota = reinterpret_cast<int*>(b + L.iota);
     e->rd.tmp_row = reinterpret_cast<int*>(b + L.tmp_row);
     e->kv_tmp_k = reinterpret_cast<bf16*>(b + L.kv_tmp_k);
@@ -1519,6 +1563,16 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
     MTX_TRY(make_map_u8(&e->tm_vq, s->vq_cache, kv_rows));
     MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_q8_smem_bytes(16))));
     MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_q8_smem_bytes(16))));
+  } else if (is_paged(c)) {
+    if (!s->k_pages || !s->v_pages || !s->page_map || !s->page_lengths || !s->active_page || !s->active_page_pos)
+      return fail(MTX_ERR_ARG, "attention=paged: k_pages / v_pages / page_map / page_lengths / active_page / active_page_pos must be set");
+    const uint64_t stage_rows = uint64_t(L_) * c.num_kv_heads * c.max_target_len;  // one bf16 plane per layer
+    MTX_TRY(make_map(&e->tm_k, s->k_cache, c.head_dim, stage_rows, kAttnTileRows));
+    MTX_TRY(make_map(&e->tm_v, s->v_cache, c.head_dim, stage_rows, kAttnTileRows));
+    const uint64_t pool_rows = uint64_t(L_) * c.num_kv_heads * c.paged_num_pages * c.paged_tokens_per_page;
+    const uint32_t box = c.paged_tokens_per_page < kAttnTileRows ? c.paged_tokens_per_page : kAttnTileRows;
+    MTX_TRY(make_map(&e->tm_kp, s->k_pages, c.head_dim, pool_rows, box));
+    MTX_TRY(make_map(&e->tm_vp, s->v_pages, c.head_dim, pool_rows, box));
   } else {
   MTX_TRY(make_map(&e->tm_k, s->k_cache, c.head_dim, kv_rows, kAttnTileRows));
   MTX_TRY(make_map(&e->tm_v, s->v_cache, c.head_dim, kv_rows, kAttnTileRows));
@@ -1831,6 +1885,29 @@ int mtx_insert_prefix(mtx_engine* e, const void* k_src, const void* v_src, int n
   a.next_pos_out = e->s.next_pos;
   a.generated_out = e->s.generated;
   a.tokens_out = e->s.tokens;
+  if (is_paged(c)) {
+    // _copy_paged (maxengine.py:1104-1131): the prefix rows into the pages of group `slot`; then the slot's bookkeeping
+    PagedInsertArgs g;
+    memset(&g, 0, sizeof(g));
+    g.k_src = a.k_src;
+    g.v_src = a.v_src;
+    g.k_pages = static_cast<bf16*>(e->s.k_pages);
+    g.v_pages = static_cast<bf16*>(e->s.v_pages);
+    g.page_map_row = e->s.page_map + size_t(slot) * c.paged_max_pages_per_group;
+    g.layers = c.num_layers;
+    g.hkv = c.num_kv_heads;
+    g.d = c.head_dim;
+    g.src_rows = n_src_rows;
+    g.n_tokens = n_rows;
+    g.num_pages = c.paged_num_pages;
+    g.tokens_per_page = c.paged_tokens_per_page;
+    const long long vecs_p = (long long)c.num_layers * c.num_kv_heads * n_rows * (c.head_dim / 8);
+    int grid_p = int((vecs_p + 255) / 256);
+    if (grid_p > e->num_sms * 8) grid_p = e->num_sms * 8;
+    MTX_TRY(launch(paged_insert_kernel, dim3(grid_p), dim3(256), 0, static_cast<cudaStream_t>(stream), g));
+    a.n = 0;  // (no rows: only the bookkeeping of insert_prefix_kernel)
+    return launch(insert_prefix_kernel, dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream), a);
+  }
   if (c.kv_quant) {
     InsertQ8Args q;
     q.base = a;
@@ -2071,6 +2148,133 @@ int mtx_ragged_attention(const void* q, const void* k, const void* v, const int3
   }
   MTX_CUDA(cudaFuncSetAttribute(decode_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   return launch(decode_attn_kernel<128>, dim3(grid), dim3(kAttnThreads), smem, st, tk, tv, p);
+}
+
+// ---- paged KV cache as single ops (inference/paged_attention.py) ---------------------------------------
+
+int mtx_paged_append(void* k_pages, void* v_pages, const void* k_new, const void* v_new, const int32_t* active_page,
+                     const int32_t* active_pos, int rows, int num_kv_heads, int head_dim, int num_pages, int tokens_per_page,
+                     mtx_stream stream) {
+  if (!k_pages || !v_pages || !k_new || !v_new || !active_page || !active_pos) return fail(MTX_ERR_ARG, "null argument");
+  if (rows < 1 || num_kv_heads < 1 || head_dim % 8 != 0 || num_pages < 1 || tokens_per_page < 1) return fail(MTX_ERR_ARG, "bad paged append shape");
+  PagedAppendArgs a;
+  memset(&a, 0, sizeof(a));
+  a.k_new = static_cast<const bf16*>(k_new);
+  a.v_new = static_cast<const bf16*>(v_new);
+  a.k_pages = static_cast<bf16*>(k_pages);
+  a.v_pages = static_cast<bf16*>(v_pages);
+  a.active_page = active_page;
+  a.active_pos = active_pos;
+  a.hkv = num_kv_heads;
+  a.d = head_dim;
+  a.num_pages = num_pages;
+  a.tokens_per_page = tokens_per_page;
+  return launch(paged_append_kernel, dim3(rows), dim3(128), 0, static_cast<cudaStream_t>(stream), a);
+}
+
+size_t mtx_paged_attention_scratch_bytes(int rows, int num_kv_heads, int num_q_heads, int head_dim, int max_tokens) {
+  return mtx_attention_scratch_bytes(rows, num_kv_heads, num_q_heads, head_dim, max_tokens, max_tokens + 64) + align_up(size_t(rows) * 12, 1024);
+}
+
+int mtx_paged_attention(const void* q, const void* k_pages, const void* v_pages, const int32_t* lengths, const int32_t* page_map,
+                        void* out, int rows, int num_q_heads, int num_kv_heads, int head_dim, int num_pages, int tokens_per_page,
+                        int max_pages_per_group, float softcap, void* scratch, mtx_stream stream) {
+  if (!q || !k_pages || !v_pages || !lengths || !page_map || !out || !scratch) return fail(MTX_ERR_ARG, "null argument");
+  if (head_dim != 64 && head_dim != 128) return fail(MTX_ERR_UNSUPPORTED, "head_dim %d: only 64 and 128", head_dim);
+  if (rows < 1 || rows > 256) return fail(MTX_ERR_ARG, "rows must be in [1, 256]");
+  if (num_q_heads % num_kv_heads != 0 || num_q_heads / num_kv_heads > 16) return fail(MTX_ERR_UNSUPPORTED, "bad head grouping");
+  if (tokens_per_page < 8 || (tokens_per_page & (tokens_per_page - 1)) != 0)
+    return fail(MTX_ERR_UNSUPPORTED, "tokens_per_page must be a power of two >= 8");
+  if (num_pages < 1 || max_pages_per_group < 1) return fail(MTX_ERR_ARG, "bad page counts");
+  const uint64_t pool_rows = uint64_t(num_kv_heads) * num_pages * tokens_per_page;
+  if (pool_rows >= (1ull << 31)) return fail(MTX_ERR_UNSUPPORTED, "the page pool has too many rows for one tensor map");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // a group's tokens are addressed as a "prefill segment" of up to max_tokens rows with an empty ring behind it
+  const int P = max_pages_per_group * tokens_per_page, T = P + 64;
+  const size_t mc = attn_max_chunks(P, T);
+  const size_t G = num_q_heads / num_kv_heads;
+  uint8_t* b = static_cast<uint8_t*>(scratch);
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  int* work_items = reinterpret_cast<int*>(b);
+  b += align_up(size_t(rows) * mc * 4, 1024);
+  int* work_count = reinterpret_cast<int*>(b);
+  b += 1024;
+  p.tickets = reinterpret_cast<int*>(b);
+  const size_t ticket_bytes = align_up(size_t(rows) * num_kv_heads * 4, 1024);
+  b += ticket_bytes;
+  p.part_ml = reinterpret_cast<float*>(b);
+  b += align_up(size_t(rows) * num_kv_heads * mc * G * 2 * 4, 1024);
+  p.part_o = reinterpret_cast<float*>(b);
+  b += align_up(size_t(rows) * num_kv_heads * mc * G * head_dim * 4, 1024);
+  int* plane = reinterpret_cast<int*>(b);
+  int* zeros_a = plane + rows;
+  int* zeros_b = zeros_a + rows;
+  MTX_CUDA(cudaMemsetAsync(p.tickets, 0, ticket_bytes, st));
+  ragged_rows_kernel<<<(rows + 127) / 128, 128, 0, st>>>(plane, zeros_a, zeros_b, rows);
+  const int tpi = attn_tiles_per_item(rows, num_kv_heads, P, T, 148);
+  MTX_TRY(launch(attn_build_worklist_kernel, dim3(1), dim3(256), 0, st, (const int*)lengths, (const int*)zeros_a, (const int*)zeros_b, rows, P, T, tpi,
+                 work_items, work_count));
+  CUtensorMap tk, tv;
+  const uint32_t box = tokens_per_page < kAttnTileRows ? tokens_per_page : kAttnTileRows;
+  MTX_TRY(make_map(&tk, k_pages, head_dim, pool_rows, box));
+  MTX_TRY(make_map(&tv, v_pages, head_dim, pool_rows, box));
+  p.q = static_cast<const bf16*>(q);
+  p.out = static_cast<bf16*>(out);
+  p.plane = plane;
+  p.len0 = lengths;
+  p.ring_first = zeros_a;
+  p.ring_len = zeros_b;
+  p.work_items = work_items;
+  p.work_count = work_count;
+  p.rows = rows;
+  p.hq = num_q_heads;
+  p.hkv = num_kv_heads;
+  p.P = P;
+  p.T = T;
+  p.tiles_per_item = tpi;
+  p.max_chunks = int(mc);
+  p.softcap = softcap;
+  p.page_map = page_map;
+  p.tokens_per_page = tokens_per_page;
+  p.num_pages = num_pages;
+  p.max_pages = max_pages_per_group;
+  p.page_row_base = 0;
+  const size_t smem = attn_smem_bytes(head_dim, int(G));
+  int grid = rows * num_kv_heads * attn_max_chunks(P, T, tpi);
+  const int cap = 148 * (head_dim == 64 ? 3 : 1);
+  if (grid > cap) grid = cap;
+  if (head_dim == 64) {
+    MTX_CUDA(cudaFuncSetAttribute(decode_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    return launch(decode_attn_kernel<64>, dim3(grid), dim3(kAttnThreads), smem, st, tk, tv, p);
+  }
+  MTX_CUDA(cudaFuncSetAttribute(decode_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  return launch(decode_attn_kernel<128>, dim3(grid), dim3(kAttnThreads), smem, st, tk, tv, p);
+}
+
+int mtx_paged_insert(void* k_pages, void* v_pages, const void* k_src, const void* v_src, const int32_t* page_map_row, int layers,
+                     int num_kv_heads, int head_dim, int n_src_rows, int n_tokens, int num_pages, int tokens_per_page, mtx_stream stream) {
+  if (!k_pages || !v_pages || !k_src || !v_src || !page_map_row) return fail(MTX_ERR_ARG, "null argument");
+  if (layers < 1 || num_kv_heads < 1 || head_dim % 8 != 0 || n_tokens < 1 || n_tokens > n_src_rows || num_pages < 1 || tokens_per_page < 1)
+    return fail(MTX_ERR_ARG, "bad paged insert shape");
+  PagedInsertArgs g;
+  memset(&g, 0, sizeof(g));
+  g.k_src = static_cast<const bf16*>(k_src);
+  g.v_src = static_cast<const bf16*>(v_src);
+  g.k_pages = static_cast<bf16*>(k_pages);
+  g.v_pages = static_cast<bf16*>(v_pages);
+  g.page_map_row = page_map_row;
+  g.layers = layers;
+  g.hkv = num_kv_heads;
+  g.d = head_dim;
+  g.src_rows = n_src_rows;
+  g.n_tokens = n_tokens;
+  g.num_pages = num_pages;
+  g.tokens_per_page = tokens_per_page;
+  const long long vecs = (long long)layers * num_kv_heads * n_tokens * (head_dim / 8);
+  int grid = int((vecs + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  return launch(paged_insert_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), g);
 }
 
 // ---- fused QKV projection + RoPE + KV append ------------------------------------------------------

@@ -48,6 +48,10 @@ struct PrepareArgs {
   const float* rope_timescale;  // [D/2] min * (max/min)^(2i/D), embeddings.py:270-275
   int window;                     // sliding_window_size of the local layers (0: the model has none)
   const float* rope_timescale_w;  // [D/2] the same table for local_rope_max_timescale (attentions.py:2085-2088)
+  // attention=paged, decode: [B] PageState.sequence_lengths after update_decode_pages (page_manager.py:332-412), else null.  The
+  // row then attends tokens [0, length) of its page group (no prefill segment / ring) and its key / value go to scratch rows
+  // (paged_append_kernel places them).
+  const int* page_lengths;
   // persistent step kernel (step_persistent.cuh): counters reset here, attention tile partition
   unsigned int* grid_bar;  // grid-barrier arrival counter
   int* tile_prefix;        // [rows + 1] exclusive prefix of the per-row 64-row tile counts
@@ -83,6 +87,11 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
       const int n = a.ar_lengths[tid] + 1;  // rows marked active since insert, this one included
       rl = n < R ? n : R;
       rf = ((idx + 1 - rl) % R + R) % R;
+      if (a.page_lengths != nullptr) {
+        l0 = a.page_lengths[tid];
+        rl = rf = 0;
+        wr = 0;
+      }
     } else {
       token = a.chunk_tokens[tid];
       pos = a.start_pos + tid;

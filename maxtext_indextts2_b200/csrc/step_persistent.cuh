@@ -829,6 +829,96 @@ __device__ __forceinline__ void pk_attn_build_list(const PkParams& p, PkTail* ta
   }
 }
 
+// Phase 2 of the CTA's attention: the merge jobs of the static plan (pk_attn_build_list).  Partials are [head][64] fp32 arrays
+// followed by (m, l) per head, whatever arithmetic layout produced them.
+__device__ __forceinline__ void pk_attention_merge(const PkParams& p, PkTail* tail, uint8_t* attn_tiles, int aw, int lane, PkEv& ev) {
+  constexpr int D = 64;
+  constexpr float kLog2e = 1.4426950408889634f;
+  const int G = p.hq / p.hkv;
+  // ---- phase 2: the CTA's merge jobs (static plan, see pk_attn_build_list) ----
+  if (lane == 0) pk_ev(ev, 610);
+  named_bar_sync(3, kPkAttnWarps * 32);
+  if (lane == 0) pk_ev(ev, 611);
+  // One thread per (head, 4 dims) unit of a job, so 160 / (16 G) jobs run side by side; a thread folds the job's
+  // on-chip partials, then the parts of later CTAs' warps from L2 (flag-in-data: a word is the sentinel or data;
+  // they were written during those warps' tile loops, so normally all are present), four parts per round trip.
+  // Fixed order: deterministic.  A thread puts the words it has read back to the sentinel.
+  const int n_units = G * (D / 4);
+  const int t = aw * 32 + lane;
+  const int lanes = (kPkAttnWarps * 32) / n_units;  // jobs in flight
+  const int jl = t / n_units, unit = t - jl * n_units;
+  const int gq = unit / (D / 4), d4 = unit - gq * (D / 4);
+  const int stride = (G * D + 2 * G + 3) & ~3;
+  const float sent = __uint_as_float(kPkSentinel);
+  const uint32_t head_mask = 0xFFFFu << (lane & 16);  // the 16 threads of a head sit in one half warp
+  if (jl < lanes) {
+    for (int j = jl; j < tail->a_njobs; j += lanes) {
+      const int n_src = tail->a_jobs[j].n_src, n_parts = tail->a_jobs[j].n_parts, pair = tail->a_jobs[j].pair;
+      float M = -INFINITY, Ls = 0.0f;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto fold = [&](const float2 ml, const float4 o4) {
+        const float Mn = fmaxf(M, ml.x);
+        const float so = ex2_approx((M - Mn) * kLog2e), sn = ex2_approx((ml.x - Mn) * kLog2e);
+        Ls = Ls * so + ml.y * sn;
+        acc.x = acc.x * so + o4.x * sn; acc.y = acc.y * so + o4.y * sn;
+        acc.z = acc.z * so + o4.z * sn; acc.w = acc.w * so + o4.w * sn;
+        M = Mn;
+      };
+      float* gbase = p.attn_part_o + (long long)pair * kPkMaxParts * stride;
+      // the first round of remote parts is requested before the on-chip partials are folded
+      float2 ml[4];
+      float4 o4[4];
+      auto request = [&](int c0) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+          if (c0 + cc < n_parts) {
+            const float* part = gbase + (long long)(c0 + cc) * stride;
+            ml[cc] = ld_poll_f2(part + G * D + gq * 2);
+            o4[cc] = ld_poll_f4(part + gq * D + d4 * 4);
+          }
+      };
+      request(0);
+      for (int c = 0; c < n_src; ++c) {  // on-chip partials, folded like the remote ones (online rescaling)
+        const int code = tail->a_jobs[j].src[c];
+        const float* src = code < 8 ? reinterpret_cast<const float*>(attn_tiles + code * 2 * 8192) : tail->a_slot[code - 8];
+        fold(*reinterpret_cast<const float2*>(src + G * D + gq * 2), *reinterpret_cast<const float4*>(src + gq * D + d4 * 4));
+      }
+      for (int c0 = 0; c0 < n_parts; c0 += 4) {
+        const long long t_spin = clock64();
+        for (;;) {
+          bool ok = true;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc)
+            if (c0 + cc < n_parts)
+              ok = ok && __float_as_uint(ml[cc].x) != kPkSentinel && __float_as_uint(ml[cc].y) != kPkSentinel &&
+                   __float_as_uint(o4[cc].x) != kPkSentinel && __float_as_uint(o4[cc].y) != kPkSentinel &&
+                   __float_as_uint(o4[cc].z) != kPkSentinel && __float_as_uint(o4[cc].w) != kPkSentinel;
+          if (ok) break;
+          pk_backoff();
+          if (clock64() - t_spin > 4000000000LL) mtx_wait_timeout(4, pair, c0);
+          request(c0);
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+          if (c0 + cc < n_parts) {
+            *reinterpret_cast<float4*>(gbase + (long long)(c0 + cc) * stride + gq * D + d4 * 4) = make_float4(sent, sent, sent, sent);
+            fold(ml[cc], o4[cc]);
+          }
+        if (c0 + 4 < n_parts) request(c0 + 4);
+      }
+      const float inv = 1.0f / Ls;
+      *reinterpret_cast<uint2*>(p.attn + (long long)tail->a_jobs[j].row * p.hq * D + (long long)tail->a_jobs[j].head * G * D + gq * D + d4 * 4) =
+          pack_bf16x4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+      if (n_parts > 0) {
+        __syncwarp(head_mask);  // all 16 threads of the head have read its (m, l) words
+        if (d4 == 0)
+          for (int c = 0; c < n_parts; ++c) *reinterpret_cast<float2*>(gbase + (long long)c * stride + G * D + gq * 2) = make_float2(sent, sent);
+      }
+    }
+  }
+  if (lane == 0) pk_ev(ev, 691);
+}
+
 // The whole CTA's attention for one layer, executed by the attention warps.
 //   phase 1: every warp walks its tile list (TMA K/V tiles -> S = Q K^T -> online softmax -> O += P V)
 //   phase 2: partial segments are merged in shared memory; pairs shared with other CTAs go through L2
@@ -1046,88 +1136,7 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
       tma_prefetch_l2_2d(&tm_v, 0, next_layer_row + list[i].x);
     }
   }
-  // ---- phase 2: the CTA's merge jobs (static plan, see pk_attn_build_list) ----
-  if (lane == 0) pk_ev(ev, 610);
-  named_bar_sync(3, kPkAttnWarps * 32);
-  if (lane == 0) pk_ev(ev, 611);
-  // One thread per (head, 4 dims) unit of a job, so 160 / (16 G) jobs run side by side; a thread folds the job's
-  // on-chip partials, then the parts of later CTAs' warps from L2 (flag-in-data: a word is the sentinel or data;
-  // they were written during those warps' tile loops, so normally all are present), four parts per round trip.
-  // Fixed order: deterministic.  A thread puts the words it has read back to the sentinel.
-  const int n_units = G * (D / 4);
-  const int t = aw * 32 + lane;
-  const int lanes = (kPkAttnWarps * 32) / n_units;  // jobs in flight
-  const int jl = t / n_units, unit = t - jl * n_units;
-  const int gq = unit / (D / 4), d4 = unit - gq * (D / 4);
-  const int stride = (G * D + 2 * G + 3) & ~3;
-  const float sent = __uint_as_float(kPkSentinel);
-  const uint32_t head_mask = 0xFFFFu << (lane & 16);  // the 16 threads of a head sit in one half warp
-  if (jl < lanes) {
-    for (int j = jl; j < tail->a_njobs; j += lanes) {
-      const int n_src = tail->a_jobs[j].n_src, n_parts = tail->a_jobs[j].n_parts, pair = tail->a_jobs[j].pair;
-      float M = -INFINITY, Ls = 0.0f;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      auto fold = [&](const float2 ml, const float4 o4) {
-        const float Mn = fmaxf(M, ml.x);
-        const float so = ex2_approx((M - Mn) * kLog2e), sn = ex2_approx((ml.x - Mn) * kLog2e);
-        Ls = Ls * so + ml.y * sn;
-        acc.x = acc.x * so + o4.x * sn; acc.y = acc.y * so + o4.y * sn;
-        acc.z = acc.z * so + o4.z * sn; acc.w = acc.w * so + o4.w * sn;
-        M = Mn;
-      };
-      float* gbase = p.attn_part_o + (long long)pair * kPkMaxParts * stride;
-      // the first round of remote parts is requested before the on-chip partials are folded
-      float2 ml[4];
-      float4 o4[4];
-      auto request = [&](int c0) {
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-          if (c0 + cc < n_parts) {
-            const float* part = gbase + (long long)(c0 + cc) * stride;
-            ml[cc] = ld_poll_f2(part + G * D + gq * 2);
-            o4[cc] = ld_poll_f4(part + gq * D + d4 * 4);
-          }
-      };
-      request(0);
-      for (int c = 0; c < n_src; ++c) {  // on-chip partials, folded like the remote ones (online rescaling)
-        const int code = tail->a_jobs[j].src[c];
-        const float* src = code < 8 ? reinterpret_cast<const float*>(attn_tiles + code * 2 * 8192) : tail->a_slot[code - 8];
-        fold(*reinterpret_cast<const float2*>(src + G * D + gq * 2), *reinterpret_cast<const float4*>(src + gq * D + d4 * 4));
-      }
-      for (int c0 = 0; c0 < n_parts; c0 += 4) {
-        const long long t_spin = clock64();
-        for (;;) {
-          bool ok = true;
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc)
-            if (c0 + cc < n_parts)
-              ok = ok && __float_as_uint(ml[cc].x) != kPkSentinel && __float_as_uint(ml[cc].y) != kPkSentinel &&
-                   __float_as_uint(o4[cc].x) != kPkSentinel && __float_as_uint(o4[cc].y) != kPkSentinel &&
-                   __float_as_uint(o4[cc].z) != kPkSentinel && __float_as_uint(o4[cc].w) != kPkSentinel;
-          if (ok) break;
-          pk_backoff();
-          if (clock64() - t_spin > 4000000000LL) mtx_wait_timeout(4, pair, c0);
-          request(c0);
-        }
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-          if (c0 + cc < n_parts) {
-            *reinterpret_cast<float4*>(gbase + (long long)(c0 + cc) * stride + gq * D + d4 * 4) = make_float4(sent, sent, sent, sent);
-            fold(ml[cc], o4[cc]);
-          }
-        if (c0 + 4 < n_parts) request(c0 + 4);
-      }
-      const float inv = 1.0f / Ls;
-      *reinterpret_cast<uint2*>(p.attn + (long long)tail->a_jobs[j].row * p.hq * D + (long long)tail->a_jobs[j].head * G * D + gq * D + d4 * 4) =
-          pack_bf16x4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-      if (n_parts > 0) {
-        __syncwarp(head_mask);  // all 16 threads of the head have read its (m, l) words
-        if (d4 == 0)
-          for (int c = 0; c < n_parts; ++c) *reinterpret_cast<float2*>(gbase + (long long)c * stride + G * D + gq * 2) = make_float2(sent, sent);
-      }
-    }
-  }
-  if (lane == 0) pk_ev(ev, 691);
+  pk_attention_merge(p, tail, attn_tiles, aw, lane, ev);
 }
 
 // ---- the kernel --------------------------------------------------------------------------

@@ -34,6 +34,7 @@ import torch
 
 from . import _lib
 from . import gemma3
+from . import page_manager
 from . import parallel
 from . import params as params_lib
 from .common_types import DECODING_ACTIVE_SEQUENCE_INDICATOR
@@ -254,6 +255,14 @@ class MaxEngine:
     self._num_slots = B + 1
     if config.quantize_kvcache:  # the int8 cache holds the decode slots only; prefill has its own bf16 plane (index 0)
       self._staging, self._num_slots = 0, B
+    # attention=paged (maxengine.py:131-136): the decode cache is the page pools, one page group per slot; prefill writes a
+    # bf16 staging plane (index 0) like the int8 engine's
+    self._paged = config.attention == "paged"
+    self.page_manager, self.page_state = None, None
+    if self._paged:
+      self._staging, self._num_slots = 0, B
+      self.page_manager = page_manager.PageManager(config)
+      self.page_state = self.page_manager.get_initial_page_state()
     self._vp_world, self._vp_rank, self._gather = 1, 0, gather
     if vocab_shard is not None:
       self._vp_rank, self._vp_world = int(vocab_shard[0]), int(vocab_shard[1])
@@ -300,6 +309,9 @@ class MaxEngine:
         sliding_window=int(config.sliding_window_size) if config.decoder_block == "gemma3" else 0,
         local_rope_max_timescale=float(config.local_rope_max_timescale),
         query_scalar=float(gemma3.get_query_pre_attn_scalar(config)) if config.decoder_block == "gemma3" else 0.0,
+        paged_num_pages=int(config.pagedattn_num_pages) if self._paged else 0,
+        paged_tokens_per_page=int(config.pagedattn_tokens_per_page) if self._paged else 0,
+        paged_max_pages_per_group=int(config.pagedattn_max_pages_per_group) if self._paged else 0,
     )
     _lib.check(self.lib.mtx_engine_create(ctypes.byref(self._cfg_struct), ctypes.byref(self._handle)))
     ws = self.lib.mtx_engine_workspace_bytes(self._handle)
@@ -359,6 +371,17 @@ class MaxEngine:
       self._k = z(L, 1, Hkv, T, D, dtype=torch.bfloat16)
       self._v = z(L, 1, Hkv, T, D, dtype=torch.bfloat16)
       self._staging = 0
+    elif self._paged:
+      # PagedAttentionOp.key_pages / value_pages (paged_attention.py:152-160), all layers in one pool, + the device copy of the
+      # PageState fields a step reads: [page_map | sequence_lengths | active_page | active_page_position] in one int32 buffer
+      self._kq = self._vq = self._k_scale = self._v_scale = None
+      NP, TPP, MP = int(cfg.pagedattn_num_pages), int(cfg.pagedattn_tokens_per_page), int(cfg.pagedattn_max_pages_per_group)
+      self._k_pages = z(L, Hkv, NP, TPP, D, dtype=torch.bfloat16)
+      self._v_pages = z(L, Hkv, NP, TPP, D, dtype=torch.bfloat16)
+      self._page_dev = z(B * MP + 3 * B)
+      self._k = z(L, 1, Hkv, T, D, dtype=torch.bfloat16)
+      self._v = z(L, 1, Hkv, T, D, dtype=torch.bfloat16)
+      self._staging = 0
     else:
       self._kq = self._vq = self._k_scale = self._v_scale = None
       self._k = z(L, S, Hkv, T, D, dtype=torch.bfloat16)
@@ -395,6 +418,28 @@ class MaxEngine:
         k_scale=self._k_scale.data_ptr() if self._k_scale is not None else None,
         v_scale=self._v_scale.data_ptr() if self._v_scale is not None else None,
     )
+    if self._paged:
+      MP = int(cfg.pagedattn_max_pages_per_group)
+      base = self._page_dev.data_ptr()
+      self._state_struct.k_pages = self._k_pages.data_ptr()
+      self._state_struct.v_pages = self._v_pages.data_ptr()
+      self._state_struct.page_map = base
+      self._state_struct.page_lengths = base + 4 * B * MP
+      self._state_struct.active_page = base + 4 * (B * MP + B)
+      self._state_struct.active_page_pos = base + 4 * (B * MP + 2 * B)
+
+  def _upload_page_state(self) -> None:
+    """The PageState fields a step reads, host -> device (the reference passes page_state into the jitted step,
+    maxengine.py:856-864).  The source is pageable memory, so the copy has left the host buffer when the call returns."""
+    ps = self.page_state
+    packed = np.concatenate((ps.page_map.reshape(-1), ps.sequence_lengths, ps.active_page, ps.active_page_position)).astype(np.int32)
+    self._page_dev.copy_(torch.from_numpy(packed))
+
+  def release_pages(self, slot: int) -> None:
+    """maxengine.py:1320-1328: hand the slot's pages back to the pool."""
+    if not self._paged:
+      return
+    self.page_state = self.page_manager.release_pages(page_state=self.page_state, page_group_id=int(slot))
 
   def _apply_sampling(self) -> None:
     cfg = self.config
@@ -472,14 +517,22 @@ class MaxEngine:
       self._v_scale.zero_()
     if self._logits is not None:
       self._logits.zero_()
+    if self._paged:
+      self._k_pages.zero_()
+      self._v_pages.zero_()
+      self.page_state = self.page_manager.get_initial_page_state()  # maxengine.py:1379-1381
+      self._upload_page_state()
     self._seed(rng)
     self._state = {
         "logits": self._logits,
         "cache": {
             # [L, slots, Hkv, T, D]: rows [0,P) = cached_prefill_key, [P,T) = cached_ar_key (uint8 q + 128 with "key_scale" /
             # "value_scale" [L, slots, Hkv, T] when quantize_kvcache: KVTensor's qvalue / scale, kvcache.py:658-736)
+            # (attention=paged: "key_pages" / "value_pages" [L, Hkv, num_pages, tokens_per_page, D], paged_attention.py:152-160)
             "key": self._kq if self._kv_quant else self._k,
             "value": self._vq if self._kv_quant else self._v,
+            "key_pages": self._k_pages if self._paged else None,
+            "value_pages": self._v_pages if self._paged else None,
             "key_scale": self._k_scale,
             "value_scale": self._v_scale,
             "prefill_length": self._prefill_len,  # == cache_prefill_segment_id.sum(-1)
@@ -515,6 +568,10 @@ class MaxEngine:
     self._seed(rng)
     cfg = self.config
     true_length = int(true_length)
+    if self._paged:  # maxengine.py:549-554: the slot's pages are reserved before the prefill runs
+      if slot is None:
+        raise ValueError("attention=paged: prefill needs the slot (page group) the sequence will be inserted into")
+      self.page_state = self.page_manager.update_prefill_pages(page_state=self.page_state, page_group_id=int(slot), true_length=true_length)
     toks = torch.as_tensor(padded_tokens).reshape(-1)
     if true_length < 1 or true_length > toks.numel() or toks.numel() > cfg.max_prefill_predict_length:
       raise ValueError(f"true_length={true_length}, {toks.numel()} padded tokens, max_prefill_predict_length={cfg.max_prefill_predict_length}")
@@ -575,11 +632,21 @@ class MaxEngine:
     k_src, v_src = prefix["cache"]["key"], prefix["cache"]["value"]  # [L, Hkv, n_src, D]
     if not (k_src.is_contiguous() and v_src.is_contiguous()):
       k_src, v_src = k_src.contiguous(), v_src.contiguous()
+    if self._paged:
+      # maxengine.py:1104-1131, 1189-1191: the prefix goes to the pages reserved for the slot (none if the pool was exhausted: the
+      # group then stays empty, as in the reference) and the group is marked active
+      ps = self.page_state
+      active = ps.has_active_page.copy()
+      active[slot] = True
+      self.page_state = ps.replace(has_active_page=active)
+      self._upload_page_state()
+      n = min(n, int(ps.num_pages_used[slot]) * self.page_manager.tokens_per_page)
     # token / position ride along as launch arguments when they are host values; device tensors (the usual case) are copied
-    _lib.check(
-        self.lib.mtx_insert_prefix(
-            self._handle, ctypes.c_void_p(k_src.data_ptr()), ctypes.c_void_p(v_src.data_ptr()), n, int(k_src.shape[2]), int(slot),
-            n, 0, 0, self._stream()))
+    if n > 0:
+      _lib.check(
+          self.lib.mtx_insert_prefix(
+              self._handle, ctypes.c_void_p(k_src.data_ptr()), ctypes.c_void_p(v_src.data_ptr()), n, int(k_src.shape[2]), int(slot),
+              n, 0, 0, self._stream()))
     self._next_pos[slot].copy_(prefix["next_pos"][0])
     self._generated[slot].copy_(prefix["generated_tokens"][0])
     self._tokens[slot].copy_(prefix["tokens"][0])
@@ -600,6 +667,9 @@ class MaxEngine:
     self._bind(params)
     self._seed(rng)
     B = self.max_concurrent_decodes
+    if self._paged:  # maxengine.py:847-849: page state advances outside the step
+      self.page_state = self.page_manager.update_decode_pages(self.page_state)
+      self._upload_page_state()
     if self._vp_world > 1:
       # each rank scores its vocabulary shard; one all-gather of 5*B floats; identical commit everywhere
       cand = self.candidate_buffer(B)
@@ -643,6 +713,9 @@ class MaxEngine:
       call = (fn, args, result, keep)
       self._host_call, self._host_call_key = call, key
     fn, args, result, _ = call
+    if self._paged:
+      self.page_state = self.page_manager.update_decode_pages(self.page_state)
+      self._upload_page_state()
     rc = fn(*args, self._stream())
     if rc != 0:
       _lib.check(rc)
@@ -671,6 +744,19 @@ class MaxEngine:
     P, R = cfg.max_prefill_predict_length, cfg.max_target_length - cfg.max_prefill_predict_length
     state = self.init_decode_state()
     g = torch.Generator(device=self.device).manual_seed(seed)
+    if self._paged:
+      # every slot gets the pages of a (prefill + generated)-token sequence; the pools hold random-normal rows
+      for slot in range(B):
+        self.page_state = self.page_manager.update_prefill_pages(self.page_state, slot, int(prefill_lengths[slot]) + int(ar_lengths[slot]))
+        if not self.page_state.has_active_page[slot]:
+          raise ValueError("pagedattn_num_pages is too small for the synthetic contexts")
+      self._upload_page_state()
+      for buf in (self._k_pages, self._v_pages):
+        flat = buf.view(-1)
+        step = 1 << 26
+        for lo in range(0, flat.numel(), step):
+          n = min(step, flat.numel() - lo)
+          flat[lo : lo + n] = torch.randn(n, device=self.device, generator=g).to(torch.bfloat16)
     if self._kv_quant:
       # random int8 rows that are consistent with KVQuant.quantize: every row holds a +-127 (its max) and has scale ~ |N(0,1)| + 2
       for buf in (self._kq, self._vq):
@@ -686,7 +772,7 @@ class MaxEngine:
         buf[..., 0] = 0x7E if self._kv_fp8 else 255  # the row's largest magnitude: e4m3 448, or q = 127
       for sc in (self._k_scale, self._v_scale):
         sc.copy_(torch.randn(sc.shape, device=self.device, generator=g).abs() + 2.0)
-    for buf in (() if self._kv_quant else (self._k, self._v)):
+    for buf in (() if (self._kv_quant or self._paged) else (self._k, self._v)):
       flat = buf.view(-1)
       step = 1 << 26
       for lo in range(0, flat.numel(), step):

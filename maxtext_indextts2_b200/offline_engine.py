@@ -4,8 +4,9 @@ Mirrors the scheduling of the reference's ``InferenceWorker`` (MaxText/inference
 prompts, `max_concurrent_decodes` decode slots, prefill + insert whenever a slot is free (`prefill_done`, :565-597), batched
 generate steps (`decode`, :599-631), token emission with EOS / length termination that frees the slot (`emit_token`,
 `background_token_emission`, :637-715).  Differences: one thread (the reference emits from a background thread to overlap the
-host work of a JAX dispatch; here a step is one C call and the tokens come back through pinned memory), and dense slots only:
-the paged KV cache (`inference/page_manager.py`) is not built.
+host work of a JAX dispatch; here a step is one C call and the tokens come back through pinned memory).  With
+`attention=paged` a slot is a page group (`inference/page_manager.py`): prefill reserves the group's pages, and they go back to
+the pool when the sequence ends (`MaxEngine.release_pages`, maxengine.py:1320-1328).
 
 Host-side scheduling only: every token comes from MaxEngine (sm_100a kernels); nothing here computes on the CPU.
 """
@@ -86,11 +87,12 @@ class OfflineEngine:
           raise ValueError(f"prompt {pid}: {ids.size} tokens, max_prefill_predict_length={P}")
         padded = torch.zeros(P, dtype=torch.int64)
         padded[: ids.size] = torch.from_numpy(ids)
-        prefix, first = self.engine.prefill(params=self.params, padded_tokens=padded, true_length=int(ids.size))
+        prefix, first = self.engine.prefill(params=self.params, padded_tokens=padded, true_length=int(ids.size), slot=slot)
         self.decode_state = self.engine.insert(prefix, self.decode_state, slot)
         self.prefills_run += 1
         lp = float(first.log_prob.reshape(-1)[0]) if first.log_prob is not None else None
         if emit(pid, int(first.data.reshape(-1)[0]), lp):
+          self.engine.release_pages(slot)
           empty.append(slot)
         else:
           slot_to_id[slot] = pid
@@ -108,6 +110,7 @@ class OfflineEngine:
             continue
           if emit(pid, int(out[slot, 0]), float(lps[slot, 0]) if lps is not None else None):
             slot_to_id[slot] = None
+            self.engine.release_pages(slot)
             empty.append(slot)
     return [
         CompletionOutput(i, np.array([t.token for t in seq], dtype=np.int32),

@@ -151,6 +151,15 @@ def _validate(keys: dict) -> None:
         f"max_target_length: {keys['max_target_length']} should be greater than max_prefill_length:"
         f" {keys['max_prefill_predict_length']}!"
     )
+  if keys["attention"] == "paged":
+    # inference/paged_attention.py + inference/page_manager.py: bf16 pages, llama2 block, one page group per decode slot
+    tpp = int(keys["pagedattn_tokens_per_page"])
+    if tpp < 8 or tpp & (tpp - 1):
+      raise ValueError("pagedattn_tokens_per_page must be a power of two >= 8 on this path")
+    if keys["quantize_kvcache"] or keys["decoder_block"] != "llama2" or int(keys["vocab_parallelism"]) != 1:
+      raise ValueError("attention=paged is implemented for the llama2 block with a bf16 cache and vocab_parallelism=1")
+    if keys["head_dim"] not in (64, 128):
+      raise ValueError("attention=paged takes head_dim 64 or 128")
   for k in ("use_qk_norm", "use_iota_embed", "use_untrainable_positional_embedding", "fused_qkv", "fused_mlp"):
     if keys[k]:
       raise ValueError(f"{k}=True is outside this decode path")
@@ -213,6 +222,9 @@ def initialize(argv=None, **kwargs) -> HyperParameters:
     keys["attn_logits_soft_cap"] = None
   if keys["final_logits_soft_cap"] == 0.0:
     keys["final_logits_soft_cap"] = None
+
+  if keys["pagedattn_max_pages_per_group"] <= 0:  # pyconfig.py:611-614
+    keys["pagedattn_max_pages_per_group"] = (keys["max_target_length"] + keys["pagedattn_tokens_per_page"] - 1) // keys["pagedattn_tokens_per_page"]
 
   emb_scale, num_head_scale, mlp_dim_scale, layer_scale = get_individual_scales(keys["global_parameter_scale"])
   keys["emb_dim"] = 2**emb_scale * keys["base_emb_dim"]

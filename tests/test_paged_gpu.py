@@ -1,0 +1,279 @@
+"""Paged KV cache (attention=paged) on the B200, through the C ABI, against oracle/paged_ref.py and oracle/decode_ref.py.
+
+* mtx_paged_attention vs the fp32 restatement of paged_attention_v1_decode (inference/paged_attention.py:302-346):
+  |d| <= 2^-7 * max|out| (one bf16 output rounding + bf16 probabilities, the bound of tests/test_kernels_gpu.py) and the
+  reference's own attention ceiling rtol = atol = 1e-2 (MaxText/tests/attention_test.py:406);
+* mtx_paged_append / mtx_paged_insert vs update_decode_step_pages / _copy_paged: copies, bit-exact;
+* MaxEngine with attention=paged vs the dense-cache oracle in lock step: a sequence's keys and values are the same rows
+  wherever they are stored, so the logits obey the engine tests' tolerance (rtol = atol = 1e-1, model_test.py:191) and greedy
+  ids are exact up to documented near-ties.
+"""
+
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from maxtext_indextts2_b200 import _lib, maxengine, offline_engine
+from oracle import decode_ref as ref
+from oracle import paged_ref
+from tests.helpers import make_params, random_tokens, small_config
+from tests.test_engine_gpu import _assert_logits, _assert_near_tie
+
+pytestmark = pytest.mark.gpu
+
+
+def _stream():
+  return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+  return ctypes.c_void_p(t.data_ptr())
+
+
+def _random_pages(rng, lengths, tpp, num_pages, max_pages):
+  """A page map that hands every sequence distinct pages >= 1 in shuffled order (what a long-running pool looks like)."""
+  need = [(n + tpp - 1) // tpp for n in lengths]
+  perm = rng.permutation(np.arange(1, num_pages))[: sum(need)]
+  page_map = np.zeros((len(lengths), max_pages), dtype=np.int32)
+  at = 0
+  for b, k in enumerate(need):
+    page_map[b, :k] = perm[at : at + k]
+    at += k
+  return page_map
+
+
+@pytest.mark.parametrize(
+    "B,Hq,Hkv,D,tpp,lengths",
+    [
+        (4, 20, 4, 64, 32, [1, 33, 64, 700]),            # the model's head grouping, the reference's default page size
+        (6, 8, 2, 64, 8, [0, 7, 8, 9, 129, 1000]),       # smallest pages (8 boxes per tile), an empty group
+        (3, 8, 8, 64, 16, [63, 65, 2048]),               # G = 1, long sequence cut over several CTAs
+        (5, 16, 2, 64, 64, [64, 1, 127, 128, 3000]),     # page = tile
+        (4, 20, 4, 64, 128, [5, 128, 129, 1500]),        # a tile is half a page
+        (3, 8, 2, 128, 32, [31, 100, 900]),              # head_dim 128 (two 64-wide sub-tiles per box)
+        (64, 20, 4, 64, 32, None),                       # batch 64, lengths 512..1536 (BASELINE configs[1] contexts)
+    ],
+)
+def test_paged_attention_matches_oracle(B, Hq, Hkv, D, tpp, lengths):
+  lib = _lib.load()
+  rng = np.random.default_rng(B * 1000 + tpp)
+  if lengths is None:
+    lengths = rng.integers(512, 1537, size=B).tolist()
+  max_pages = (max(lengths) + tpp - 1) // tpp + 2
+  num_pages = sum((n + tpp - 1) // tpp for n in lengths) + 5
+  g = torch.Generator().manual_seed(tpp)
+  q = torch.randn(B, Hq, D, generator=g).to(torch.bfloat16)
+  k_pages = torch.randn(Hkv, num_pages, tpp, D, generator=g).to(torch.bfloat16)
+  v_pages = torch.randn(Hkv, num_pages, tpp, D, generator=g).to(torch.bfloat16)
+  # what lies past a sequence's end inside its last page must not matter: poison it
+  page_map = _random_pages(rng, lengths, tpp, num_pages, max_pages)
+  for b, n in enumerate(lengths):
+    if n % tpp:
+      last = page_map[b, (n - 1) // tpp]
+      k_pages[:, last, n % tpp :] = float("nan")
+      v_pages[:, last, n % tpp :] = float("nan")
+  want = paged_ref.paged_attention(q, k_pages, v_pages, lengths, page_map)
+  qd, kd, vd = q.cuda(), k_pages.cuda(), v_pages.cuda()
+  ld, pd = torch.tensor(lengths, dtype=torch.int32).cuda(), torch.from_numpy(page_map).cuda()
+  out = torch.zeros(B, Hq * D, dtype=torch.bfloat16, device="cuda")
+  scratch = torch.empty(lib.mtx_paged_attention_scratch_bytes(B, Hkv, Hq, D, max_pages * tpp), dtype=torch.uint8, device="cuda")
+  _lib.check(lib.mtx_paged_attention(_ptr(qd), _ptr(kd), _ptr(vd), _ptr(ld), _ptr(pd), _ptr(out), B, Hq, Hkv, D, num_pages, tpp, max_pages,
+                                     0.0, _ptr(scratch), _stream()))
+  torch.cuda.synchronize()
+  got = out.cpu().float().reshape(B, Hq, D)
+  assert torch.isfinite(got).all()
+  assert (got - want).abs().max() <= 2**-7 * want.abs().max()
+  torch.testing.assert_close(got, want, rtol=1e-2, atol=1e-2)
+
+
+def test_paged_attention_softcap_and_argument_errors():
+  lib = _lib.load()
+  B, Hq, Hkv, D, tpp, num_pages, max_pages = 2, 8, 2, 64, 32, 16, 4
+  g = torch.Generator().manual_seed(3)
+  q = (torch.randn(B, Hq, D, generator=g) * 2).to(torch.bfloat16)
+  k_pages = torch.randn(Hkv, num_pages, tpp, D, generator=g).to(torch.bfloat16)
+  v_pages = torch.randn(Hkv, num_pages, tpp, D, generator=g).to(torch.bfloat16)
+  lengths, page_map = [100, 37], np.array([[3, 1, 7, 9], [2, 5, 0, 0]], dtype=np.int32)
+  want = paged_ref.paged_attention(q, k_pages, v_pages, lengths, page_map, softcap=5.0)
+  qd, kd, vd = q.cuda(), k_pages.cuda(), v_pages.cuda()
+  ld, pd = torch.tensor(lengths, dtype=torch.int32).cuda(), torch.from_numpy(page_map).cuda()
+  out = torch.zeros(B, Hq * D, dtype=torch.bfloat16, device="cuda")
+  scratch = torch.empty(lib.mtx_paged_attention_scratch_bytes(B, Hkv, Hq, D, max_pages * tpp), dtype=torch.uint8, device="cuda")
+  args = [_ptr(qd), _ptr(kd), _ptr(vd), _ptr(ld), _ptr(pd), _ptr(out), B, Hq, Hkv, D, num_pages, tpp, max_pages, 5.0, _ptr(scratch), _stream()]
+  _lib.check(lib.mtx_paged_attention(*args))
+  torch.cuda.synchronize()
+  got = out.cpu().float().reshape(B, Hq, D)
+  assert (got - want).abs().max() <= 2**-7 * want.abs().max()
+  for pos, bad in ((11, 24), (11, 4), (9, 96), (0, None)):  # page size not a power of two / too small, head_dim, null pointer
+    a = list(args)
+    a[pos] = bad
+    assert lib.mtx_paged_attention(*a) in (_lib.MTX_ERR_ARG, _lib.MTX_ERR_UNSUPPORTED)
+
+
+def test_paged_append_and_insert_match_oracle():
+  lib = _lib.load()
+  L, Hkv, D, tpp, num_pages, B = 3, 4, 64, 16, 40, 5
+  g = torch.Generator().manual_seed(11)
+  pools = [torch.randn(L, Hkv, num_pages, tpp, D, generator=g).to(torch.bfloat16) for _ in range(2)]
+  # ---- append: one layer, every row writes (inactive groups hit page 0, position 0) ----
+  state = paged_ref.initialize_page_state(num_pages, B, 8)
+  for grp, n in ((0, 5), (1, 16), (3, 33)):
+    state = paged_ref.update_prefill_pages(state, grp, n, tpp, 8)
+  state = paged_ref.update_decode_pages(state, tpp, 8)
+  k_new, v_new = (torch.randn(B, Hkv, D, generator=g).to(torch.bfloat16) for _ in range(2))
+  want_k, want_v = pools[0][1].clone(), pools[1][1].clone()
+  paged_ref.update_decode_step_pages(want_k, want_v, k_new, v_new, state)
+  kd, vd = pools[0].cuda(), pools[1].cuda()
+  ap = torch.tensor(state["active_page"], dtype=torch.int32).cuda()
+  apos = torch.tensor(state["active_page_position"], dtype=torch.int32).cuda()
+  knd, vnd = k_new.cuda(), v_new.cuda()
+  _lib.check(lib.mtx_paged_append(_ptr(kd[1]), _ptr(vd[1]), _ptr(knd), _ptr(vnd), _ptr(ap), _ptr(apos), B, Hkv, D, num_pages, tpp, _stream()))
+  torch.cuda.synchronize()
+  # groups 2 and 4 have no active page: both write (page 0, position 0), the never-allocated page -- which of them lands last is
+  # unspecified (duplicate indices of the reference's scatter, paged_attention.py:467-468); every other page is exact
+  assert torch.equal(kd[1].cpu()[:, 1:], want_k[:, 1:]) and torch.equal(vd[1].cpu()[:, 1:], want_v[:, 1:])
+  assert any(torch.equal(kd[1].cpu()[:, 0, 0], k_new[b]) for b in (2, 4))
+  want_k[:, 0], want_v[:, 0] = kd[1].cpu()[:, 0], vd[1].cpu()[:, 0]
+  assert torch.equal(kd[0].cpu(), pools[0][0]) and torch.equal(kd[2].cpu(), pools[0][2])  # other layers untouched
+  # ---- insert: a 33-token prefix (rows of [L, Hkv, 48, D] = 3 prefix pages per head) into group 3's pages ----
+  n_src = 48
+  k_src, v_src = (torch.randn(L, Hkv, n_src, D, generator=g).to(torch.bfloat16) for _ in range(2))
+  want_k, want_v = kd.cpu().clone(), vd.cpu().clone()
+  for l in range(L):
+    paged_ref.copy_prefix_pages(want_k[l], want_v[l], k_src[l].reshape(Hkv, n_src // tpp, tpp, D), v_src[l].reshape(Hkv, n_src // tpp, tpp, D), state, 3)
+  row = torch.tensor(state["page_map"][3], dtype=torch.int32).cuda()
+  ksd, vsd = k_src.cuda(), v_src.cuda()
+  n_tokens = state["num_pages_used"][3] * tpp  # whole pages, as the reference copies them
+  _lib.check(lib.mtx_paged_insert(_ptr(kd), _ptr(vd), _ptr(ksd), _ptr(vsd), _ptr(row), L, Hkv, D, n_src, n_tokens, num_pages, tpp, _stream()))
+  torch.cuda.synchronize()
+  assert torch.equal(kd.cpu(), want_k) and torch.equal(vd.cpu(), want_v)
+
+
+def _paged_config(**kw):
+  base = dict(attention="paged", pagedattn_tokens_per_page=8, pagedattn_num_pages=40, materialize_logits=True)
+  base.update(kw)
+  return small_config(**base)
+
+
+@pytest.mark.parametrize("use_graph,tpp", [(False, 8), (True, 16), (True, 64)])
+def test_paged_engine_matches_dense_oracle(use_graph, tpp):
+  """Prefill + insert + 24 lock-step greedy steps for three sequences (their pages interleave in the pool and every sequence
+  crosses page boundaries), then one slot is released and refilled with a new prompt that reuses the freed pages."""
+  cfg = _paged_config(per_device_batch_size=3, max_prefill_predict_length=16, max_target_length=64, pagedattn_tokens_per_page=tpp)
+  dense = small_config(per_device_batch_size=3, max_prefill_predict_length=16, max_target_length=64, materialize_logits=True)
+  params = make_params(cfg)
+  oracle = ref.DecodeOracle(dense, params, faithful=True)
+  engine = maxengine.MaxEngine(cfg, use_cuda_graph=use_graph)
+  dparams = engine.load_params(params)
+  prompts = random_tokens((4, 16), cfg.vocab_size, seed=21)
+  ostate, state = oracle.init_decode_state(), engine.init_decode_state()
+
+  def add(slot, toks, n):
+    nonlocal ostate, state
+    padded = torch.zeros(16, dtype=torch.int64)
+    padded[:n] = toks[:n]
+    oprefix, ofirst = oracle.prefill(padded, n)
+    ostate = oracle.insert(oprefix, ostate, slot)
+    prefix, _ = engine.prefill(params=dparams, padded_tokens=padded, true_length=n, slot=slot)
+    _assert_logits(prefix["logits"].cpu()[0], oprefix["logits"][0])
+    prefix["tokens"].fill_(int(ofirst))
+    state = engine.insert(prefix, state, slot)
+
+  def steps(n, live):
+    nonlocal ostate, state
+    near = 0
+    for _ in range(n):
+      ostate, odata = oracle.generate(ostate)
+      state, result = engine.generate(dparams, state)
+      data = result.data.cpu()
+      got, want = state["logits"].cpu(), ostate["logits"]
+      for b in live:
+        torch.testing.assert_close(got[b], want[b], rtol=1e-1, atol=1e-1)
+        if data[b, 0] != odata[b, 0]:
+          _assert_near_tie(want[b, 0], int(data[b, 0]), int(odata[b, 0]))
+          near += 1
+      state["tokens"].copy_(odata[:, :1])
+    return near
+
+  for slot, n in enumerate((16, 5, 1)):
+    add(slot, prompts[slot], n)
+  ps = engine.page_state
+  assert ps.has_active_page.all() and ps.sequence_lengths.tolist() == [16, 5, 1]
+  near = steps(24, (0, 1, 2))
+  ps = engine.page_state
+  assert ps.sequence_lengths.tolist() == [40, 29, 25]
+  assert ps.num_pages_used.tolist() == [(n + tpp - 1) // tpp for n in (40, 29, 25)]
+  freed = set(ps.page_map[1, : ps.num_pages_used[1]].tolist())
+  engine.release_pages(1)
+  assert int(engine.page_state.num_pages_used[1]) == 0 and not engine.page_state.has_active_page[1]
+  add(1, prompts[3], 11)
+  assert set(engine.page_state.page_map[1, : engine.page_state.num_pages_used[1]].tolist()) <= freed  # lowest free pages first
+  near += steps(8, (0, 1, 2))
+  assert near <= 3, f"{near} near-ties in 96 tokens"
+
+
+def test_paged_engine_head_grouping_of_the_model():
+  """G = 5 (20 query heads over 4 kv heads, the IndexTTS2-scale grouping), 32-token pages, 6 slots of ragged prompts."""
+  kw = dict(base_num_query_heads=20, base_num_kv_heads=4, base_emb_dim=256, per_device_batch_size=6, max_prefill_predict_length=64,
+            max_target_length=160, materialize_logits=True)
+  cfg = _paged_config(pagedattn_tokens_per_page=32, pagedattn_num_pages=64, **kw)
+  dense = small_config(**kw)
+  params = make_params(cfg)
+  oracle = ref.DecodeOracle(dense, params, faithful=True)
+  engine = maxengine.MaxEngine(cfg)
+  dparams = engine.load_params(params)
+  prompts = random_tokens((6, 64), cfg.vocab_size, seed=5)
+  ostate, state = oracle.init_decode_state(), engine.init_decode_state()
+  for slot, n in enumerate((64, 33, 32, 31, 2, 50)):
+    padded = torch.zeros(64, dtype=torch.int64)
+    padded[:n] = prompts[slot][:n]
+    oprefix, ofirst = oracle.prefill(padded, n)
+    ostate = oracle.insert(oprefix, ostate, slot)
+    prefix, _ = engine.prefill(params=dparams, padded_tokens=padded, true_length=n, slot=slot)
+    prefix["tokens"].fill_(int(ofirst))
+    state = engine.insert(prefix, state, slot)
+  for _ in range(40):
+    ostate, odata = oracle.generate(ostate)
+    state, result = engine.generate(dparams, state)
+    torch.testing.assert_close(state["logits"].cpu(), ostate["logits"], rtol=1e-1, atol=1e-1)
+    state["tokens"].copy_(odata[:, :1])
+  assert engine.page_state.sequence_lengths.tolist() == [n + 40 for n in (64, 33, 32, 31, 2, 50)]
+
+
+def test_paged_engine_errors():
+  cfg = _paged_config()
+  engine = maxengine.MaxEngine(cfg)
+  dparams = engine.load_params(make_params(cfg))
+  with pytest.raises(ValueError, match="slot"):
+    engine.prefill(params=dparams, padded_tokens=torch.arange(8), true_length=8)
+  with pytest.raises(ValueError, match="page_group_id"):
+    engine.prefill(params=dparams, padded_tokens=torch.arange(8), true_length=8, slot=7)
+  with pytest.raises(ValueError, match="power of two"):
+    _paged_config(pagedattn_tokens_per_page=24)
+  with pytest.raises(ValueError, match="insufficient"):
+    maxengine.MaxEngine(_paged_config(pagedattn_max_pages_per_group=2))
+
+
+def test_offline_engine_over_pages_matches_dense_slots():
+  """Continuous batching with page groups: 7 prompts through 3 slots with a pool too small to hold 7 sequences at once (pages
+  must come back when a sequence ends); greedy completions equal those of the dense-cache engine."""
+  kw = dict(per_device_batch_size=3, max_prefill_predict_length=16, max_target_length=48)
+  dense_cfg = small_config(**kw)
+  paged_cfg = _paged_config(pagedattn_tokens_per_page=8, pagedattn_num_pages=19, materialize_logits=False, **kw)  # 18 usable pages = 3 x 6
+  params = make_params(dense_cfg)
+  rng = np.random.default_rng(3)
+  prompts = [rng.integers(0, dense_cfg.vocab_size, size=int(n)).tolist() for n in (16, 3, 9, 1, 12, 7, 16)]
+  outs = []
+  for cfg in (dense_cfg, paged_cfg):
+    eng = offline_engine.OfflineEngine(cfg, params)
+    outs.append(eng.batch_inference(prompts, max_decode_length=20))
+    if cfg is paged_cfg:
+      ps = eng.engine.page_state
+      assert int(ps.page_status.sum()) == 1 and int(ps.num_pages_used.sum()) == 0  # everything returned to the pool
+  agree = sum(int(np.array_equal(a.token_ids, b.token_ids)) for a, b in zip(*outs))
+  # the two engines run different attention kernels (persistent vs per-kernel): a near-tie may flip a token and the rest of that
+  # completion; the oracle comparison above is the parity test, this one checks the scheduling
+  assert agree >= len(prompts) - 1, f"{agree} of {len(prompts)} completions identical"
+  assert all(len(o.token_ids) == 20 for o in outs[1])
