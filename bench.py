@@ -56,6 +56,8 @@ def parse_args():
   ap.add_argument("--kv-int8", action="store_true", help="quantize_kvcache=True, kv_quant_dtype=int8, kv_quant_axis=dkv (SURVEY 8f-2; not the judged line)")
   ap.add_argument("--kv-fp8", action="store_true", help="quantize_kvcache=True, kv_quant_dtype=fp8 (float8_e4m3fn bytes)")
   ap.add_argument("--kv-axis", default="dkv", choices=["dkv", "heads_and_dkv"], help="kv_quant_axis of --kv-int8 / --kv-fp8")
+  ap.add_argument("--paged", type=int, default=0, help="attention=paged with this many tokens per page (SURVEY 8f-4; not the judged line): "
+                  "the page manager runs on the host before every step and its state is uploaded, inside the timed region")
   ap.add_argument("--no-fold", action="store_true", help="keep the RMSNorm scales out of the weights (fold_norm_scales=False)")
   ap.add_argument("--skip-cpu-baseline", action="store_true")
   ap.add_argument("--cpu-slots", type=int, default=0, help="slots in the CPU baseline sample (0 = all slots of the batch)")
@@ -86,6 +88,9 @@ def make_config(args):
     kw["fold_norm_scales"] = False
   if args.kv_int8 or args.kv_fp8:
     kw.update(quantize_kvcache=True, kv_quant_dtype="fp8" if args.kv_fp8 else "int8", kv_quant_axis=args.kv_axis)
+  if args.paged:
+    T = kw.get("max_target_length", 0) or 3072
+    kw.update(attention="paged", pagedattn_tokens_per_page=args.paged, pagedattn_num_pages=args.batch * ((T + args.paged - 1) // args.paged) + 1)
   if args.sampling != "greedy":
     kw["decode_sampling_strategy"] = args.sampling
     kw["decode_sampling_top_k"] = 64
@@ -318,7 +323,9 @@ def workload_config(args, cfg, world=None):
       "global_batch": per_gpu * world,
       "context": f"uniform[{args.context_min},{args.context_max}] valid rows per slot, P={cfg.max_prefill_predict_length} T={cfg.max_target_length}",
       "parallelism": f"request-batch partitioned x{world}, no collective",
-      "kv_cache": f"{cfg.kv_quant_dtype} + fp32 scale ({cfg.kv_quant_axis})" if cfg.quantize_kvcache else "bf16",
+      "kv_cache": (f"{cfg.kv_quant_dtype} + fp32 scale ({cfg.kv_quant_axis})" if cfg.quantize_kvcache else "bf16") +
+                  (f", paged: {cfg.pagedattn_num_pages} pages of {cfg.pagedattn_tokens_per_page} tokens, host page manager + state upload "
+                   f"every step inside the timed region" if cfg.attention == "paged" else ""),
       "l2": "working set per step (weights 1.81 GB + KV 1.6 GB) exceeds the 126 MB L2; no flush needed",
   }
 
@@ -648,9 +655,14 @@ def main():
       ring = (idx - np.arange(int(ar[s_]) + 1)) % R_
       tot += int((ring >= max(0, R_ - W_)).sum())
     ctx_sum_local = tot
-  step_fn = lib.mtx_decode_step if args.no_graph else lib.mtx_decode_step_graph
+  step_c = lib.mtx_decode_step if args.no_graph else lib.mtx_decode_step_graph
   stream = torch.cuda.current_stream()
   sptr = ctypes.c_void_p(stream.cuda_stream)
+
+  def step_fn(handle, rows, sp):
+    if args.paged:  # what MaxEngine.generate does before the step: PageManager.update_decode_pages + upload of the page state
+      engine._advance_pages()
+    return step_c(handle, rows, sp)
 
   def barrier():
     torch.cuda.synchronize()
@@ -662,6 +674,8 @@ def main():
   sampler.start()  # (early: see ClockSampler.mark)
   # ---- kernel launches per step (counted on one eager step) and per-class times ----
   n0 = lib.mtx_launch_count()
+  if args.paged:
+    engine._advance_pages()
   _lib.check(lib.mtx_decode_step(engine._handle, B, sptr))
   torch.cuda.synchronize()
   launches_per_step = int(lib.mtx_launch_count() - n0)
@@ -720,6 +734,8 @@ def main():
   acc = np.zeros(NCLS)
   prof_steps = 3
   for _ in range(prof_steps):
+    if args.paged:
+      engine._advance_pages()
     _lib.check(lib.mtx_profile_decode_step(engine._handle, B, sptr, class_ms, class_n))
     acc += np.array(list(class_ms))
   acc /= prof_steps
@@ -781,7 +797,7 @@ def main():
                       for k in per_launch_bytes if acc[KERNEL_CLASSES.index(k)] > 0},
     }
     verify = None
-    if not args.no_verify:
+    if not args.no_verify and not args.paged:  # (the oracle mirror reads the dense cache; the paged engine's parity: tests/test_paged_gpu.py)
       verify = verify_step(engine, dparams, cfg, B)
     cpu = None
     if not args.skip_cpu_baseline and world == 1:

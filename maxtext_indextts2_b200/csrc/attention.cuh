@@ -58,8 +58,8 @@ struct AttnParams {
   int ring_size;  // ring indices in the window (0: the whole ring, T - P)
   const int* skip0_rows;  // [rows] or null: per-row addition to skip0 (prefill positions run as decode rows: position window)
   // Paged KV cache (attention=paged: inference/paged_attention.py:302-346, page_manager.py:49-91).  page_map != null: K / V are page
-  // pools [Hkv, num_pages, tokens_per_page, D] (one layer at page_row_base rows into the tensor map), token i of the row's page
-  // group plane[r] lives in page page_map[plane[r]][i / tokens_per_page]; len0 is the group's sequence length, the ring is empty.
+  // pools [Hkv, num_pages, tokens_per_page, D] (one layer at page_row_base rows into the tensor map), token i of row r (= page
+  // group r) lives in page page_map[r][i / tokens_per_page]; len0 is the group's sequence length, the ring is empty.
   // The tensor maps' box is min(tokens_per_page, 64) rows: a 64-row tile is one slice of a page or 64 / tokens_per_page pages.
   const int* page_map;   // [page groups, max_pages]
   int tokens_per_page;   // power of two >= 8
@@ -154,7 +154,7 @@ __device__ __forceinline__ void attn_issue_tile(uint8_t* dst, const CUtensorMap*
     return;
   }
   const int tpp = p.tokens_per_page;
-  const int* pm = p.page_map + (long long)p.plane[r] * p.max_pages;
+  const int* pm = p.page_map + (long long)r * p.max_pages;
   const int tok = t * 64;
   if (tpp >= 64) {
     const long long prow = p.page_row_base + ((long long)h * p.num_pages + pm[tok / tpp]) * tpp + (tok & (tpp - 1));

@@ -428,7 +428,7 @@ WsLayout layout_workspace(const mtx_engine* e) {
   L.work_items = take(size_t(c.max_rows) * e->attn_max_chunks * 4);
   L.work_count = take(4);
   L.rope_timescale = take((c.head_dim / 2) * 4);
-  if (kvq_axis(c) == 2 || is_paged(c)) {
+  if (kvq_axis(c) == 2) {
     L.iota = take(rt * 4);
     L.tmp_row = take(rt * 4);
     L.kv_tmp_k = take(rt * c.num_kv_heads * c.head_dim * 2);
@@ -744,7 +744,9 @@ bool pk_fill_phase(std::vector<PkTable>& tabs, int ph, int n, int k, bool allow_
 int pk_trace_bars(int layers) { return 2 + 5 * layers + 2 > 200 ? 2 + 5 * layers + 2 : 200; }
 
 bool pk_usable(const mtx_engine* e, int rows) {
-  if (e->pk_ctas <= 0 || round_rows(rows) > kPkMaxRTile || e->cfg.kv_quant || e->cfg.decoder_block != 0 || is_paged(e->cfg)) return false;
+  if (e->pk_ctas <= 0 || round_rows(rows) > kPkMaxRTile || e->cfg.kv_quant || e->cfg.decoder_block != 0) return false;
+  // (paged: a 64-row tile is one slice of a page or two whole pages; smaller pages take the per-kernel path)
+  if (is_paged(e->cfg) && (e->cfg.paged_tokens_per_page < 32 || env_int("MTX_PK_PAGED", 1) == 0)) return false;
   if (e->cfg.num_q_heads / e->cfg.num_kv_heads > 8) return false;  // the attention MMA carries the group's heads in its 8 columns
   // an attention warp's tile list holds kPkAttnListMax entries: bound the worst case (every context full)
   const mtx_model_config& c = e->cfg;
@@ -786,6 +788,18 @@ int launch_persistent(mtx_engine* e, int rows, const XMaps& xm, const EpiArgs& l
   p.k_cache = static_cast<bf16*>(e->s.k_cache);
   p.v_cache = static_cast<bf16*>(e->s.v_cache);
   p.kv_layer_elems = (long long)c.num_slots * c.num_kv_heads * c.max_target_len * c.head_dim;
+  p.kv_layer_rows = c.num_slots * c.num_kv_heads * c.max_target_len;
+  if (is_paged(c)) {  // the page pools: one "plane" of num_pages * tokens_per_page rows per kv head and layer (prepare_rows_kernel)
+    p.k_cache = static_cast<bf16*>(e->s.k_pages);
+    p.v_cache = static_cast<bf16*>(e->s.v_pages);
+    p.t_alloc = c.paged_num_pages * c.paged_tokens_per_page;
+    p.kv_layer_rows = c.num_kv_heads * p.t_alloc;
+    p.kv_layer_elems = (long long)p.kv_layer_rows * c.head_dim;
+    p.page_map = e->s.page_map;
+    p.page_tokens = c.paged_tokens_per_page;
+    p.num_pages = c.paged_num_pages;
+    p.max_pages = c.paged_max_pages_per_group;
+  }
   p.token = e->rd.token;
   p.plane = e->rd.plane;
   p.write_row = e->rd.write_row;
@@ -814,7 +828,8 @@ int launch_persistent(mtx_engine* e, int rows, const XMaps& xm, const EpiArgs& l
   // launch against the prepare kernel and 45 us per CUDA-graph replay end to end (profiles/r2k_cooperative_ab.txt).
   g_cooperative = env_int("MTX_PK_COOPERATIVE", 0) != 0;
   const int rc = launch(step_persistent_kernel, dim3(e->pk_ctas), dim3(kPkThreads), pk_smem_bytes(), st, e->tm_all_wqkv, e->tm_all_wo, e->tm_all_w01,
-                        e->tm_all_wout, e->tm_logits, xm.x, xm.attn, xm.h, xm.act, xm.n, e->tm_k, e->tm_v, p);
+                        e->tm_all_wout, e->tm_logits, xm.x, xm.attn, xm.h, xm.act, xm.n, is_paged(c) ? e->tm_kp : e->tm_k,
+                        is_paged(c) ? e->tm_vp : e->tm_v, p);
   g_cooperative = false;
   return rc;
 }
@@ -859,6 +874,9 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   pa.rope_timescale = e->rope_timescale;
   pa.window = gemma3 ? c.sliding_window : 0;
   pa.page_lengths = (is_paged(c) && mode == 0) ? e->s.page_lengths : nullptr;
+  pa.active_page = e->s.active_page;
+  pa.active_pos = e->s.active_page_pos;
+  pa.tokens_per_page = c.paged_tokens_per_page;
   pa.rope_timescale_w = e->rope_timescale_w;
   const bool mega = mode == 0 && want_logits && pk_usable(e, rows);
   if (mega) {
@@ -1015,8 +1033,14 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
       ea.vq_cache = static_cast<uint8_t*>(e->s.vq_cache) + kvq_layer * l;
       ea.k_scale = e->s.k_scale + kvs_layer * l;
       ea.v_scale = e->s.v_scale + kvs_layer * l;
-    } else if ((kvq_axis(c) == 2 || is_paged(c)) && mode == 0) {
-      // (attention=paged: the same scratch matrices, paged_append_kernel then writes the rows into the groups' active pages)
+    } else if (is_paged(c) && mode == 0) {
+      // update_decode_step_pages (paged_attention.py:446-471): the layer's pool is one plane of num_pages * tokens_per_page rows
+      // per kv head, the row descriptors address (active page, position) in it (prepare_rows_kernel)
+      const size_t pool_layer = size_t(c.num_kv_heads) * c.paged_num_pages * c.paged_tokens_per_page * c.head_dim;
+      ea.k_cache = static_cast<bf16*>(e->s.k_pages) + pool_layer * l;
+      ea.v_cache = static_cast<bf16*>(e->s.v_pages) + pool_layer * l;
+      ea.t_alloc = c.paged_num_pages * c.paged_tokens_per_page;
+    } else if (kvq_axis(c) == 2 && mode == 0) {
       // one scale per token over all kv heads (kv_quant_axis heads_and_dkv): the epilogue leaves the rotated keys / values as
       // bf16 in [rows, Hkv, D] scratch matrices (plane = row, write row = 0), kv_quant_rows_kernel quantises and appends
       ea.k_cache = e->kv_tmp_k;
@@ -1049,22 +1073,6 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
       ka.t_alloc = c.max_target_len;
       ka.fp8 = kvq_fp8(c) ? 1 : 0;
       MTX_TRY(launch(kv_quant_rows_kernel, dim3(rows, 2), dim3(c.num_kv_heads * 32), 0, st, ka));
-    }
-    if (is_paged(c) && mode == 0) {  // update_decode_step_pages (paged_attention.py:446-471)
-      const size_t pool_layer = size_t(c.num_kv_heads) * c.paged_num_pages * c.paged_tokens_per_page * c.head_dim;
-      PagedAppendArgs pg;
-      memset(&pg, 0, sizeof(pg));
-      pg.k_new = e->kv_tmp_k;
-      pg.v_new = e->kv_tmp_v;
-      pg.k_pages = static_cast<bf16*>(e->s.k_pages) + pool_layer * l;
-      pg.v_pages = static_cast<bf16*>(e->s.v_pages) + pool_layer * l;
-      pg.active_page = e->s.active_page;
-      pg.active_pos = e->s.active_page_pos;
-      pg.hkv = c.num_kv_heads;
-      pg.d = c.head_dim;
-      pg.num_pages = c.paged_num_pages;
-      pg.tokens_per_page = c.paged_tokens_per_page;
-      MTX_TRY(launch(paged_append_kernel, dim3(rows), dim3(128), 0, st, pg));
     }
 
     g_class = KC_ATTENTION;
@@ -1453,7 +1461,7 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   e->rd.work_count = reinterpret_cast<int*>(b + L.work_count);
   e->rope_timescale = reinterpret_cast<float*>(b + L.rope_timescale);
   e->rd.iota = e->rd.tmp_row = nullptr;
-  if (kvq_axis(c) == 2 || is_paged(c)) {
+  if (kvq_axis(c) == 2) {
     e->rd.iota = reinterpret_cast<int*>(b + L.iota);
     e->rd.tmp_row = reinterpret_cast<int*>(b + L.tmp_row);
     e->kv_tmp_k = reinterpret_cast<bf16*>(b + L.kv_tmp_k);

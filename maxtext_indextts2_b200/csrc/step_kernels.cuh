@@ -49,9 +49,14 @@ struct PrepareArgs {
   int window;                     // sliding_window_size of the local layers (0: the model has none)
   const float* rope_timescale_w;  // [D/2] the same table for local_rope_max_timescale (attentions.py:2085-2088)
   // attention=paged, decode: [B] PageState.sequence_lengths after update_decode_pages (page_manager.py:332-412), else null.  The
-  // row then attends tokens [0, length) of its page group (no prefill segment / ring) and its key / value go to scratch rows
-  // (paged_append_kernel places them).
+  // row then attends tokens [0, length) of its page group (no prefill segment / ring).  Its key / value go to
+  // pages[h, active_page, active_page_position] (update_decode_step_pages, paged_attention.py:446-471): with the pool of a layer
+  // read as ONE plane of Hkv heads x (num_pages * tokens_per_page) rows that is row active_page * tokens_per_page + position of
+  // plane 0, so the QKV epilogues append to a page exactly as they append to a dense cache.
   const int* page_lengths;
+  const int* active_page;
+  const int* active_pos;
+  int tokens_per_page;
   // persistent step kernel (step_persistent.cuh): counters reset here, attention tile partition
   unsigned int* grid_bar;  // grid-barrier arrival counter
   int* tile_prefix;        // [rows + 1] exclusive prefix of the per-row 64-row tile counts
@@ -90,7 +95,8 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
       if (a.page_lengths != nullptr) {
         l0 = a.page_lengths[tid];
         rl = rf = 0;
-        wr = 0;
+        plane = 0;
+        wr = a.active_page[tid] * a.tokens_per_page + a.active_pos[tid];
       }
     } else {
       token = a.chunk_tokens[tid];

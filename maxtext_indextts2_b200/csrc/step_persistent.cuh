@@ -105,6 +105,7 @@ struct PkTail {
     int n_parts;               // partials of later CTAs' warps in the pair's L2 workspace
   } a_jobs[kPkAttnWarps + 1];
   int2 a_list[kPkAttnWarps][kPkAttnListMax];  // .x = cache row of the tile (layer 0), .y = PkAttnMeta bits
+  int a_row2[kPkAttnWarps][kPkAttnListMax];   // paged, 32-token pages: cache row of the tile's second page
   alignas(16) float a_slot[kPkAttnWarps][kPkAttnSlotFloats];  // partial of a warp's first segment (its K/V buffers stay busy)
   PkTable tab;
 };
@@ -122,6 +123,12 @@ struct PkParams {
   const bf16 *embedding, *attn_norm, *mlp_norm, *final_norm;
   bf16 *k_cache, *v_cache;
   long long kv_layer_elems;
+  int kv_layer_rows;  // rows of one layer in the K/V tensor maps
+  // attention=paged (page_map != null): k_cache / v_cache are the page pools [L, Hkv, num_pages, page_tokens, 64], a layer being one
+  // plane of t_alloc = num_pages * page_tokens rows per kv head; row r is page group r, its token i lives in page
+  // page_map[r][i / page_tokens].  page_tokens >= 32: a 64-row tile is a slice of one page, or two whole pages (4 KB boxes).
+  const int* page_map;
+  int page_tokens, num_pages, max_pages;
   // row descriptors (prepare_rows_kernel)
   const int *token, *plane, *write_row, *len0, *ring_first, *ring_len;
   const float2* rope_cs;
@@ -788,6 +795,25 @@ __device__ __forceinline__ void pk_attn_build_list(const PkParams& p, PkTail* ta
         pk_attn_next(pos, p, tail, R);
       }
     }
+    if (p.page_map != nullptr) {
+      // Paged: .x so far is kv head * T + the tile's first token; turn it into the pool row of the page that holds the token,
+      // one tile per lane.  Once per step: the pages of a sequence are the same in every layer.
+      __syncwarp();
+      if (lane < n) {
+        const int2 e = tail->a_list[aw][lane];
+        const int h = pka_head(e.y), tok = e.x - h * p.T;  // (group rows are plane 0: plane_row = h * T)
+        const int* pm = p.page_map + (long long)pka_row(e.y) * p.max_pages;
+        const int pt = p.page_tokens;
+        const int first = pm[tok / pt];
+        const int row = (h * p.num_pages + first) * pt + (tok & (pt - 1));
+        // (a tile whose valid rows end inside its first 32-token page loads that page twice: entries of the page map past the
+        //  sequence's pages are not valid)
+        const int second = (pt == 32 && pka_cnt(e.y) > 32) ? pm[tok / pt + 1] : first;
+        tail->a_list[aw][lane].x = row;
+        tail->a_row2[aw][lane] = (h * p.num_pages + second) * pt;
+      }
+      __syncwarp();
+    }
     if (aw == 0) {
       // Merge plan.  Walk the pairs that start inside [clo, chi); a pair that leaves the warp it starts in needs a
       // merge.  Its partial in warp w is w's last segment (parked in w's K buffer) when it runs to the end of w's
@@ -919,6 +945,18 @@ __device__ __forceinline__ void pk_attention_merge(const PkParams& p, PkTail* ta
   if (lane == 0) pk_ev(ev, 691);
 }
 
+// One thread requests a 64-row K (or V) tile: cache row `row` of the layer, or -- 32-token pages -- the two pages at `row`, `row2`.
+__device__ __forceinline__ void pk_issue_tile(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, const PkParams& p, int layer_row, int row,
+                                              int row2) {
+  mbar_expect_tx(bar, 8192);
+  if (p.page_map != nullptr && p.page_tokens == 32) {
+    tma_load_2d(dst, tm, 0, layer_row + row, bar, kEvictFirst);
+    tma_load_2d(dst + 4096, tm, 0, layer_row + row2, bar, kEvictFirst);
+  } else {
+    tma_load_2d(dst, tm, 0, layer_row + row, bar, kEvictFirst);
+  }
+}
+
 // The whole CTA's attention for one layer, executed by the attention warps.
 //   phase 1: every warp walks its tile list (TMA K/V tiles -> S = Q K^T -> online softmax -> O += P V)
 //   phase 2: partial segments are merged in shared memory; pairs shared with other CTAs go through L2
@@ -926,10 +964,10 @@ __device__ __forceinline__ void pk_attention_merge(const PkParams& p, PkTail* ta
 __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const PkParams& p, PkTail* tail, int layer,
                                                  uint8_t* attn_tiles, uint32_t& phase, int cta, int aw, int lane, bool primed, PkEv& ev) {
   constexpr int D = 64;
-  constexpr int kTileBytes = 64 * D * 2;
   constexpr float kLog2e = 1.4426950408889634f;
   const int G = p.hq / p.hkv;
-  const int layer_row = layer * p.num_slots * p.hkv * p.T;
+  const int layer_row = layer * p.kv_layer_rows;
+  const int* list2 = tail->a_row2[aw];
   const int gid = lane >> 2, tid4 = lane & 3;
   uint8_t* k_tile = attn_tiles + aw * 2 * 8192;
   uint8_t* v_tile = k_tile + 8192;
@@ -941,11 +979,8 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
 
   if (n > 0 && !primed && lane == 0) {
     fence_proxy_async_all();  // K/V rows appended by the QKV epilogue (generic stores) are read through TMA
-    const int row0 = layer_row + list[0].x;
-    mbar_expect_tx(bar_k, kTileBytes);
-    tma_load_2d(k_tile, &tm_k, 0, row0, bar_k, kEvictFirst);
-    mbar_expect_tx(bar_v, kTileBytes);
-    tma_load_2d(v_tile, &tm_v, 0, row0, bar_v, kEvictFirst);
+    pk_issue_tile(k_tile, &tm_k, bar_k, p, layer_row, list[0].x, list2[0]);
+    pk_issue_tile(v_tile, &tm_v, bar_v, p, layer_row, list[0].x, list2[0]);
   }
 
   // Transposed formulation: S^T = K Q^T and O^T = V^T P^T, so the 16-row MMA dimension carries KV rows / head
@@ -979,7 +1014,6 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
       seg_first = (meta & PKA_PAIR_FIRST) != 0;
     }
     const bool more = i + 1 < n;
-    const int next_row = more ? layer_row + list[i + 1].x : 0;
 
     // ---- S^T = K Q^T over the 64 rows of the tile ----
     float s[4][4];
@@ -1000,10 +1034,7 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
     // K tile consumed: refill it with the next tile's keys while the softmax and P V run
     fence_proxy_async();
     __syncwarp();
-    if (more && lane == 0) {
-      mbar_expect_tx(bar_k, kTileBytes);
-      tma_load_2d(k_tile, &tm_k, 0, next_row, bar_k, kEvictFirst);
-    }
+    if (more && lane == 0) pk_issue_tile(k_tile, &tm_k, bar_k, p, layer_row, list[i + 1].x, list2[i + 1]);
     // ---- mask + online softmax: a head's scores live in the 8 threads of equal tid4 ----
     if (p.softcap != 0.0f) {
 #pragma unroll
@@ -1075,10 +1106,7 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
     }
     fence_proxy_async();
     __syncwarp();
-    if (more && lane == 0) {
-      mbar_expect_tx(bar_v, kTileBytes);
-      tma_load_2d(v_tile, &tm_v, 0, next_row, bar_v, kEvictFirst);
-    }
+    if (more && lane == 0) pk_issue_tile(v_tile, &tm_v, bar_v, p, layer_row, list[i + 1].x, list2[i + 1]);
     phase ^= 1;
 
     if (meta & PKA_SEG_END) {
@@ -1129,8 +1157,8 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
 
   // The HBM is idle for most of the GEMM phases that follow: ask for the next layer's K/V tiles of this warp now, so that its
   // next tile loop streams from L2 (the list is the same for every layer; a tile is 8 KB, a warp holds ~6).
-  if ((p.variant & 1) && layer + 1 < p.L) {
-    const int next_layer_row = layer_row + p.num_slots * p.hkv * p.T;
+  if ((p.variant & 1) && layer + 1 < p.L && p.page_map == nullptr) {
+    const int next_layer_row = layer_row + p.kv_layer_rows;
     for (int i = lane; i < n; i += 32) {
       tma_prefetch_l2_2d(&tm_k, 0, next_layer_row + list[i].x);
       tma_prefetch_l2_2d(&tm_v, 0, next_layer_row + list[i].x);
@@ -1756,9 +1784,9 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
       ev.on = ev.brief ? (l & 1) == 0 && l < 32 : l == 1;
 #pragma unroll 1  // one copy of the duty code
       for (int ph = 0; ph < 4; ++ph) {
-        if (ph == PK_QKV && ((p.variant & 2) || ((p.variant & 1) && l == 0))) {
+        if (ph == PK_QKV && ((p.variant & 2) || ((p.variant & 1) && l == 0)) && p.page_map == nullptr) {
           // this layer's K/V tiles towards L2 while the QKV phase runs (the row appended by that phase is written later: L2 stays coherent)
-          const int lrow = l * p.num_slots * p.hkv * p.T;
+          const int lrow = l * p.kv_layer_rows;
           const int n_own = tail->a_count[aw];
           for (int i = lane; i < n_own; i += 32) {
             tma_prefetch_l2_2d(&tm_k, 0, lrow + tail->a_list[aw][i].x);
@@ -1778,12 +1806,9 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
         __syncwarp();
         // ---- attention over the valid rows of both cache segments ----
         if (may_prime && lane == 0) {
-          const int row0 = l * p.num_slots * p.hkv * p.T + tail->a_list[aw][0].x;
           uint8_t* kt = attn_tiles + aw * 2 * 8192;
-          mbar_expect_tx(&tail->attn_bars[2 * aw], 8192);
-          tma_load_2d(kt, &tm_k, 0, row0, &tail->attn_bars[2 * aw], kEvictFirst);
-          mbar_expect_tx(&tail->attn_bars[2 * aw + 1], 8192);
-          tma_load_2d(kt + 8192, &tm_v, 0, row0, &tail->attn_bars[2 * aw + 1], kEvictFirst);
+          pk_issue_tile(kt, &tm_k, &tail->attn_bars[2 * aw], p, l * p.kv_layer_rows, tail->a_list[aw][0].x, tail->a_row2[aw][0]);
+          pk_issue_tile(kt + 8192, &tm_v, &tail->attn_bars[2 * aw + 1], p, l * p.kv_layer_rows, tail->a_list[aw][0].x, tail->a_row2[aw][0]);
         }
         pk_wait_flag(&tail->bar_done, uint32_t(2 + 5 * l));
         if (lane == 0) pk_ev(ev, 500);

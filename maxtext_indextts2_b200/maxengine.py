@@ -435,6 +435,12 @@ class MaxEngine:
     packed = np.concatenate((ps.page_map.reshape(-1), ps.sequence_lengths, ps.active_page, ps.active_page_position)).astype(np.int32)
     self._page_dev.copy_(torch.from_numpy(packed))
 
+  def _advance_pages(self) -> None:
+    """maxengine.py:847-849: the page state advances outside the step (one more token per active group, a new page for the
+    groups that crossed a boundary), then the step reads it."""
+    self.page_state = self.page_manager.update_decode_pages(self.page_state)
+    self._upload_page_state()
+
   def release_pages(self, slot: int) -> None:
     """maxengine.py:1320-1328: hand the slot's pages back to the pool."""
     if not self._paged:
@@ -667,9 +673,8 @@ class MaxEngine:
     self._bind(params)
     self._seed(rng)
     B = self.max_concurrent_decodes
-    if self._paged:  # maxengine.py:847-849: page state advances outside the step
-      self.page_state = self.page_manager.update_decode_pages(self.page_state)
-      self._upload_page_state()
+    if self._paged:
+      self._advance_pages()
     if self._vp_world > 1:
       # each rank scores its vocabulary shard; one all-gather of 5*B floats; identical commit everywhere
       cand = self.candidate_buffer(B)
@@ -714,8 +719,7 @@ class MaxEngine:
       self._host_call, self._host_call_key = call, key
     fn, args, result, _ = call
     if self._paged:
-      self.page_state = self.page_manager.update_decode_pages(self.page_state)
-      self._upload_page_state()
+      self._advance_pages()
     rc = fn(*args, self._stream())
     if rc != 0:
       _lib.check(rc)
