@@ -797,7 +797,7 @@ def main():
                       for k in per_launch_bytes if acc[KERNEL_CLASSES.index(k)] > 0},
     }
     verify = None
-    if not args.no_verify and not args.paged:  # (the oracle mirror reads the dense cache; the paged engine's parity: tests/test_paged_gpu.py)
+    if not args.no_verify:  # (attention=paged: the mirror gathers the slots' rows from the page pools)
       verify = verify_step(engine, dparams, cfg, B)
     cpu = None
     if not args.skip_cpu_baseline and world == 1:

@@ -329,7 +329,7 @@ int mtx_engine_rebind_state(mtx_engine* e, const mtx_decode_state* s);
 size_t mtx_step_trace_words(const mtx_engine* e); /* sized for the engine's grid and layer count (NULL: 148 CTAs, 24 layers) */
 
 /* 1 when the library was built with jaxlib's headers and exports the XLA FFI handler symbols of csrc/mtx_jax_ffi.cc
- * (MtxRaggedAttention, MtxDecodeAttention, MtxQkvRopeAppend, MtxDecodeStep), else 0. */
+ * (MtxRaggedAttention, MtxDecodeAttention, MtxQkvRopeAppend, MtxDecodeStep, MtxPagedAppend, MtxPagedAttention), else 0. */
 int mtx_jax_ffi_available(void);
 
 const char* mtx_last_error(void);

@@ -12,6 +12,8 @@
 //   MtxDecodeAttention  -- AttentionOp.__call__ in autoregressive mode over this library's two-segment cache
 //   MtxQkvRopeAppend    -- Attention.query/key/value + RotaryEmbedding + KVCache append (in-place cache: input_output_aliases)
 //   MtxDecodeStep       -- MaxEngine._generate_jit (MaxText/maxengine.py:868-936): the whole step on a bound engine
+//   MtxPagedAppend      -- PagedAttentionOp.update_decode_step_pages (MaxText/inference/paged_attention.py:446-471), pools donated
+//   MtxPagedAttention   -- PagedAttentionOp.paged_attention_v1_decode (:302-346) on the reference's pools and PageState arrays
 //
 // COMPILE GUARD.  jaxlib's headers (xla/ffi/api/ffi.h) are not in this image and jax cannot be installed (no network), so
 // this translation unit compiles to the single symbol mtx_jax_ffi_available() == 0 here; with the headers on the include
@@ -105,7 +107,7 @@ ffi::Error DecodeStepImpl(cudaStream_t stream, ffi::Buffer<ffi::BF16> k_cache, f
                           int64_t engine, int32_t rows) {
   if (k_out->untyped_data() != k_cache.untyped_data() || tokens_out->untyped_data() != tokens.untyped_data())
     return ffi::Error(ffi::ErrorCode::kInvalidArgument, "decode state must be donated (input_output_aliases for operands 0..8)");
-  mtx_decode_state s;
+  mtx_decode_state s = {};  // (quantised-cache and page-pool fields stay null: the dense bf16 cache)
   s.k_cache = k_out->untyped_data();
   s.v_cache = v_out->untyped_data();
   s.tokens = tokens_out->typed_data();
@@ -124,7 +126,62 @@ ffi::Error DecodeStepImpl(cudaStream_t stream, ffi::Buffer<ffi::BF16> k_cache, f
   return Status(mtx_decode_step(e, rows, stream));
 }
 
+// (key_pages, value_pages [Hkv, num_pages, tokens_per_page, D] (donated), key, value [B, Hkv, D] or [B, 1, Hkv, D], active_page [B],
+// active_page_position [B]) -> (key_pages, value_pages)
+ffi::Error PagedAppendImpl(cudaStream_t stream, ffi::Buffer<ffi::BF16> k_pages, ffi::Buffer<ffi::BF16> v_pages, ffi::Buffer<ffi::BF16> key,
+                           ffi::Buffer<ffi::BF16> value, ffi::Buffer<ffi::S32> active_page, ffi::Buffer<ffi::S32> active_pos,
+                           ffi::ResultBuffer<ffi::BF16> k_out, ffi::ResultBuffer<ffi::BF16> v_out) {
+  const auto pd = k_pages.dimensions();
+  if (pd.size() != 4) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "pools must be [Hkv, num_pages, tokens_per_page, D]");
+  if (k_out->untyped_data() != k_pages.untyped_data() || v_out->untyped_data() != v_pages.untyped_data())
+    return ffi::Error(ffi::ErrorCode::kInvalidArgument, "the page pools must be donated (input_output_aliases {0: 0, 1: 1})");
+  const int rows = int(active_page.element_count());
+  return Status(mtx_paged_append(k_out->untyped_data(), v_out->untyped_data(), key.untyped_data(), value.untyped_data(), active_page.typed_data(),
+                                 active_pos.typed_data(), rows, int(pd[0]), int(pd[3]), int(pd[1]), int(pd[2]), stream));
+}
+
+// (q [B, Hq*D] or [B, 1, Hq, D], key_pages, value_pages, sequence_lengths [B], page_map [B, max_pages_per_group], scratch u8[...]) -> out like q
+ffi::Error PagedAttentionImpl(cudaStream_t stream, ffi::Buffer<ffi::BF16> q, ffi::Buffer<ffi::BF16> k_pages, ffi::Buffer<ffi::BF16> v_pages,
+                              ffi::Buffer<ffi::S32> lengths, ffi::Buffer<ffi::S32> page_map, ffi::Buffer<ffi::U8> scratch,
+                              ffi::ResultBuffer<ffi::BF16> out, int32_t num_q_heads, float softcap) {
+  const auto pd = k_pages.dimensions();
+  const auto md = page_map.dimensions();
+  if (pd.size() != 4 || md.size() != 2) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "pools must be rank 4, page_map [groups, max_pages]");
+  const int rows = int(lengths.element_count());
+  const int hkv = int(pd[0]), num_pages = int(pd[1]), tpp = int(pd[2]), d = int(pd[3]), max_pages = int(md[1]);
+  if (scratch.element_count() < mtx_paged_attention_scratch_bytes(rows, hkv, num_q_heads, d, max_pages * tpp))
+    return ffi::Error(ffi::ErrorCode::kInvalidArgument, "scratch smaller than mtx_paged_attention_scratch_bytes()");
+  return Status(mtx_paged_attention(q.untyped_data(), k_pages.untyped_data(), v_pages.untyped_data(), lengths.typed_data(), page_map.typed_data(),
+                                    out->untyped_data(), rows, num_q_heads, hkv, d, num_pages, tpp, max_pages, softcap, scratch.untyped_data(),
+                                    stream));
+}
+
 }  // namespace
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(MtxPagedAppend, PagedAppendImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Ret<ffi::Buffer<ffi::BF16>>()
+                                  .Ret<ffi::Buffer<ffi::BF16>>());
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(MtxPagedAttention, PagedAttentionImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::S32>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Ret<ffi::Buffer<ffi::BF16>>()
+                                  .Attr<int32_t>("num_q_heads")
+                                  .Attr<float>("softcap"));
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(MtxRaggedAttention, RaggedAttentionImpl,
                               ffi::Ffi::Bind()

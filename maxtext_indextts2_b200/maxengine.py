@@ -373,12 +373,14 @@ class MaxEngine:
       self._staging = 0
     elif self._paged:
       # PagedAttentionOp.key_pages / value_pages (paged_attention.py:152-160), all layers in one pool, + the device copy of the
-      # PageState fields a step reads: [page_map | sequence_lengths | active_page | active_page_position] in one int32 buffer
+      # PageState fields a step reads: [sequence_lengths | active_page | active_page_position | page_map] in one int32 buffer
       self._kq = self._vq = self._k_scale = self._v_scale = None
       NP, TPP, MP = int(cfg.pagedattn_num_pages), int(cfg.pagedattn_tokens_per_page), int(cfg.pagedattn_max_pages_per_group)
       self._k_pages = z(L, Hkv, NP, TPP, D, dtype=torch.bfloat16)
       self._v_pages = z(L, Hkv, NP, TPP, D, dtype=torch.bfloat16)
-      self._page_dev = z(B * MP + 3 * B)
+      self._page_dev = z(3 * B + B * MP)
+      self._page_dev_small, self._page_dev_map = self._page_dev[: 3 * B], self._page_dev[3 * B :]
+      self._uploaded_map = None
       self._k = z(L, 1, Hkv, T, D, dtype=torch.bfloat16)
       self._v = z(L, 1, Hkv, T, D, dtype=torch.bfloat16)
       self._staging = 0
@@ -423,17 +425,20 @@ class MaxEngine:
       base = self._page_dev.data_ptr()
       self._state_struct.k_pages = self._k_pages.data_ptr()
       self._state_struct.v_pages = self._v_pages.data_ptr()
-      self._state_struct.page_map = base
-      self._state_struct.page_lengths = base + 4 * B * MP
-      self._state_struct.active_page = base + 4 * (B * MP + B)
-      self._state_struct.active_page_pos = base + 4 * (B * MP + 2 * B)
+      self._state_struct.page_lengths = base
+      self._state_struct.active_page = base + 4 * B
+      self._state_struct.active_page_pos = base + 8 * B
+      self._state_struct.page_map = base + 12 * B
 
   def _upload_page_state(self) -> None:
     """The PageState fields a step reads, host -> device (the reference passes page_state into the jitted step,
     maxengine.py:856-864).  The source is pageable memory, so the copy has left the host buffer when the call returns."""
     ps = self.page_state
-    packed = np.concatenate((ps.page_map.reshape(-1), ps.sequence_lengths, ps.active_page, ps.active_page_position)).astype(np.int32)
-    self._page_dev.copy_(torch.from_numpy(packed))
+    small = np.concatenate((ps.sequence_lengths, ps.active_page, ps.active_page_position))
+    self._page_dev_small.copy_(torch.from_numpy(small))
+    if ps.page_map is not self._uploaded_map:  # (the page manager returns the same array while no page was handed out)
+      self._page_dev_map.copy_(torch.from_numpy(ps.page_map.reshape(-1)))
+      self._uploaded_map = ps.page_map
 
   def _advance_pages(self) -> None:
     """maxengine.py:847-849: the page state advances outside the step (one more token per active group, a new page for the

@@ -103,14 +103,14 @@ def _update_decode_pages_global(state: PageState, tokens_per_page: int, max_page
   """page_manager.py:332-412: one more token for every active group; groups that crossed a page boundary get the lowest
   free page, in group order, while free pages last."""
   active = state.has_active_page
-  lengths = state.sequence_lengths + active.astype(np.int32)
-  position = np.where(active, (lengths - 1) % tokens_per_page, state.active_page_position).astype(np.int32)
-  required = (lengths + tokens_per_page - 1) // tokens_per_page
+  lengths = state.sequence_lengths + active  # (int32 + bool stays int32)
+  position = np.where(active, (lengths - 1) % tokens_per_page, state.active_page_position)
+  required = (lengths + (tokens_per_page - 1)) // tokens_per_page
   needs = active & (required > state.num_pages_used) & (required <= max_pages_per_group)
-  groups = np.flatnonzero(needs)
   status, page_map = state.page_status, state.page_map
   used, active_page = state.num_pages_used, state.active_page
-  if groups.size:
+  if needs.any():
+    groups = np.flatnonzero(needs)
     free = np.flatnonzero(status[1:] == 0) + 1
     n = min(groups.size, free.size)  # later groups find no free page and keep their state (can_allocate false)
     groups, take = groups[:n], free[:n].astype(np.int32)
@@ -119,8 +119,8 @@ def _update_decode_pages_global(state: PageState, tokens_per_page: int, max_page
     page_map[groups, used[groups]] = take
     used[groups] += 1
     active_page[groups] = take
-  return state.replace(page_status=status, page_map=page_map, num_pages_used=used, sequence_lengths=lengths.astype(np.int32),
-                       active_page=active_page, active_page_position=position)
+  # (the common step hands out no page: page_status / page_map / num_pages_used / active_page are then the SAME arrays)
+  return PageState(status, page_map, used, lengths, active_page, active, position)
 
 
 class PageManager:

@@ -76,6 +76,8 @@ def mirror_state(engine, oracle: ref.DecodeOracle, slots) -> dict:
   P, R, L = oracle.P, oracle.R, oracle.cfg.num_decoder_layers
   state = oracle.init_decode_state()
   c = state["cache"]
+  if getattr(engine, "_paged", False):
+    return _mirror_paged(engine, oracle, slots, state)
   sl = torch.as_tensor(slots, device=engine._k.device)
   quant = bool(getattr(engine, "_kv_quant", False))
   for l in range(L):
@@ -108,6 +110,42 @@ def mirror_state(engine, oracle: ref.DecodeOracle, slots) -> dict:
   c["ar_segment_id"] = seg
   c["ar_index"] = idx
   c["ar_lengths"] = alen.to(torch.int32)
+  state["next_pos"] = engine._next_pos.cpu()[slots].clone()
+  state["generated_tokens"] = engine._generated.cpu()[slots].clone()
+  state["tokens"] = engine._tokens.cpu()[slots].clone()
+  return state
+
+
+def _mirror_paged(engine, oracle: ref.DecodeOracle, slots, state: dict) -> dict:
+  """attention=paged: a sequence is the tokens [0, sequence_lengths[s]) of page group s, gathered from the pools
+  [L, Hkv, num_pages, tokens_per_page, D] through page_map (inference/page_manager.py:49-91).  The dense-cache oracle attends the
+  same keys wherever they are stored: the first P tokens go to its prefill segment, the rest to ring rows ending at a shared
+  ring index (no wrap: the caller keeps sequence_lengths - P below the ring size)."""
+  P, R, L = oracle.P, oracle.R, oracle.cfg.num_decoder_layers
+  c = state["cache"]
+  ps = engine.page_state
+  tpp = engine.page_manager.tokens_per_page
+  lengths = [int(ps.sequence_lengths[s]) for s in slots]
+  extra = [max(0, n - P) for n in lengths]
+  idx = max(extra)
+  assert idx < R, "the mirrored sequences do not fit the oracle's ring"
+  for i, (s, n) in enumerate(zip(slots, lengths)):
+    pages = torch.as_tensor(ps.page_map[s, : (n + tpp - 1) // tpp].astype(np.int64), device=engine._k_pages.device)
+    k = engine._k_pages.index_select(2, pages).to("cpu").to(torch.float32)  # [L, Hkv, pages, tpp, D]
+    v = engine._v_pages.index_select(2, pages).to("cpu").to(torch.float32)
+    k = k.reshape(L, k.shape[1], -1, k.shape[-1])[:, :, :n].permute(0, 2, 1, 3)  # [L, n, Hkv, D]
+    v = v.reshape(L, v.shape[1], -1, v.shape[-1])[:, :, :n].permute(0, 2, 1, 3)
+    n0 = min(n, P)
+    for l in range(L):
+      c["prefill_key"][l][i, :n0] = k[l, :n0]
+      c["prefill_value"][l][i, :n0] = v[l, :n0]
+      if n > P:
+        c["ar_key"][l][i, idx - extra[i] : idx] = k[l, P:]
+        c["ar_value"][l][i, idx - extra[i] : idx] = v[l, P:]
+    c["prefill_segment_id"][i, :n0] = ref.ACTIVE
+    c["ar_segment_id"][i, idx - extra[i] : idx] = ref.ACTIVE
+  c["ar_index"] = idx
+  c["ar_lengths"] = torch.as_tensor(extra, dtype=torch.int32)
   state["next_pos"] = engine._next_pos.cpu()[slots].clone()
   state["generated_tokens"] = engine._generated.cpu()[slots].clone()
   state["tokens"] = engine._tokens.cpu()[slots].clone()
