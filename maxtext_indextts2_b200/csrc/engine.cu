@@ -744,7 +744,10 @@ bool pk_fill_phase(std::vector<PkTable>& tabs, int ph, int n, int k, bool allow_
 int pk_trace_bars(int layers) { return 2 + 5 * layers + 2 > 200 ? 2 + 5 * layers + 2 : 200; }
 
 bool pk_usable(const mtx_engine* e, int rows) {
-  if (e->pk_ctas <= 0 || round_rows(rows) > kPkMaxRTile || e->cfg.kv_quant || e->cfg.decoder_block != 0) return false;
+  if (e->pk_ctas <= 0 || round_rows(rows) > kPkMaxRTile || e->cfg.decoder_block != 0) return false;
+  // (a quantised cache with one scale per token and kv head is quantised by the QKV epilogue; heads_and_dkv needs the maximum over
+  //  heads that sit in different CTAs: per-kernel path)
+  if (e->cfg.kv_quant && (kvq_axis(e->cfg) != 1 || env_int("MTX_PK_KVQ", 1) == 0)) return false;
   // (paged: a 64-row tile is one slice of a page or two whole pages; smaller pages take the per-kernel path)
   if (is_paged(e->cfg) && (e->cfg.paged_tokens_per_page < 32 || env_int("MTX_PK_PAGED", 1) == 0)) return false;
   if (e->cfg.num_q_heads / e->cfg.num_kv_heads > 8) return false;  // the attention MMA carries the group's heads in its 8 columns
@@ -827,9 +830,20 @@ int launch_persistent(mtx_engine* e, int rows, const XMaps& xm, const EpiArgs& l
   // deployed) passes the occupancy check of mtx_engine_bind once, and the cooperative launch costs programmatic dependent
   // launch against the prepare kernel and 45 us per CUDA-graph replay end to end (profiles/r2k_cooperative_ab.txt).
   g_cooperative = env_int("MTX_PK_COOPERATIVE", 0) != 0;
-  const int rc = launch(step_persistent_kernel, dim3(e->pk_ctas), dim3(kPkThreads), pk_smem_bytes(), st, e->tm_all_wqkv, e->tm_all_wo, e->tm_all_w01,
-                        e->tm_all_wout, e->tm_logits, xm.x, xm.attn, xm.h, xm.act, xm.n, is_paged(c) ? e->tm_kp : e->tm_k,
-                        is_paged(c) ? e->tm_vp : e->tm_v, p);
+  int rc;
+  if (c.kv_quant) {  // kv_quant_axis dkv only (pk_usable): the byte caches, quantising QKV epilogue, fp16 attention over byte tiles
+    p.kq_cache = static_cast<uint8_t*>(e->s.kq_cache);
+    p.vq_cache = static_cast<uint8_t*>(e->s.vq_cache);
+    p.k_scale = e->s.k_scale;
+    p.v_scale = e->s.v_scale;
+    auto kern = kvq_fp8(c) ? step_persistent_kernel<2> : step_persistent_kernel<1>;
+    rc = launch(kern, dim3(e->pk_ctas), dim3(kPkThreads), pk_smem_bytes(), st, e->tm_all_wqkv, e->tm_all_wo, e->tm_all_w01, e->tm_all_wout,
+                e->tm_logits, xm.x, xm.attn, xm.h, xm.act, xm.n, e->tm_kq, e->tm_vq, p);
+  } else {
+    rc = launch(step_persistent_kernel<0>, dim3(e->pk_ctas), dim3(kPkThreads), pk_smem_bytes(), st, e->tm_all_wqkv, e->tm_all_wo, e->tm_all_w01,
+                e->tm_all_wout, e->tm_logits, xm.x, xm.attn, xm.h, xm.act, xm.n, is_paged(c) ? e->tm_kp : e->tm_k,
+                is_paged(c) ? e->tm_vp : e->tm_v, p);
+  }
   g_cooperative = false;
   return rc;
 }
@@ -843,7 +857,8 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   const mtx_model_config& c = e->cfg;
   // (an int8 cache is appended to by the row-major GEMM's epilogue only: steps of any size run it, padded to 128 rows)
   const bool gemma3 = c.decoder_block == 1;
-  const int r_tile = (c.kv_quant || gemma3) && round_rows(rows) < 128 ? 128 : round_rows(rows);
+  const bool mega = mode == 0 && want_logits && pk_usable(e, rows);  // the persistent step kernel (up to 64 rows)
+  const int r_tile = (c.kv_quant || gemma3) && !mega && round_rows(rows) < 128 ? 128 : round_rows(rows);
   XMaps* xm;
   MTX_TRY(get_xmaps(e, r_tile, &xm));
   // prefill (mode 1) of an int8 engine writes the ONE bf16 staging plane that k_cache / v_cache then are
@@ -878,7 +893,6 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   pa.active_pos = e->s.active_page_pos;
   pa.tokens_per_page = c.paged_tokens_per_page;
   pa.rope_timescale_w = e->rope_timescale_w;
-  const bool mega = mode == 0 && want_logits && pk_usable(e, rows);
   if (mega) {
     pa.grid_bar = e->grid_bar;
     pa.tile_prefix = e->pk_tile_prefix;
@@ -1527,8 +1541,9 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   if (c.head_dim == 64 && env_int("MTX_PERSISTENT", 1) != 0) {
     // one CTA per SM, all co-resident (the grid barrier spins): needs the full shared-memory carve-out
     int blocks = 0;
-    if (cudaFuncSetAttribute(step_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pk_smem_bytes())) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, step_persistent_kernel, kPkThreads, pk_smem_bytes()) == cudaSuccess && blocks >= 1) {
+    auto pk_kernel = c.kv_quant == 0 ? step_persistent_kernel<0> : kvq_fp8(c) ? step_persistent_kernel<2> : step_persistent_kernel<1>;
+    if (cudaFuncSetAttribute(pk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pk_smem_bytes())) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, pk_kernel, kPkThreads, pk_smem_bytes()) == cudaSuccess && blocks >= 1) {
       int ctas = e->num_sms;
       const int cap = env_int("MTX_PERSISTENT_CTAS", 0);
       if (cap > 0 && cap < ctas) ctas = cap;

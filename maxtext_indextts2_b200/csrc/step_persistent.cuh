@@ -106,6 +106,7 @@ struct PkTail {
   } a_jobs[kPkAttnWarps + 1];
   int2 a_list[kPkAttnWarps][kPkAttnListMax];  // .x = cache row of the tile (layer 0), .y = PkAttnMeta bits
   int a_row2[kPkAttnWarps][kPkAttnListMax];   // paged, 32-token pages: cache row of the tile's second page
+  float a_scales[kPkAttnWarps][128];          // quantised cache: the current tile's 64 K scales | 64 V scales
   alignas(16) float a_slot[kPkAttnWarps][kPkAttnSlotFloats];  // partial of a warp's first segment (its K/V buffers stay busy)
   PkTable tab;
 };
@@ -124,6 +125,11 @@ struct PkParams {
   bf16 *k_cache, *v_cache;
   long long kv_layer_elems;
   int kv_layer_rows;  // rows of one layer in the K/V tensor maps
+  // step_persistent_kernel<KVQ != 0>: quantised decode cache (quantize_kvcache with kv_quant_axis=dkv, inference/kvcache.py:36-90):
+  // bytes [L, slots, Hkv, T, 64] (u = q + 128, or float8_e4m3fn) with one fp32 scale = max|x| per row in k_scale / v_scale
+  // [L, slots, Hkv, T]; tm_k / tm_v then address the byte caches (64-byte rows, SWIZZLE_64B)
+  uint8_t *kq_cache, *vq_cache;
+  float *k_scale, *v_scale;
   // attention=paged (page_map != null): k_cache / v_cache are the page pools [L, Hkv, num_pages, page_tokens, 64], a layer being one
   // plane of t_alloc = num_pages * page_tokens rows per kv head; row r is page group r, its token i lives in page
   // page_map[r][i / page_tokens].  page_tokens >= 32: a 64-row tile is a slice of one page, or two whole pages (4 KB boxes).
@@ -359,8 +365,9 @@ __device__ __forceinline__ PkQkvSide pk_qkv_side(const PkParams& p, int r, int t
 
 // embeddings.py:304-315 (half-split rotation in bf16) + kvcache.py:626-718 (append).  D = 64: the rotation partner
 // of feature d is d +- 32, eight lanes away.
+template <int KVQ>
 __device__ __forceinline__ void pk_epi_qkv(const float4 a, const PkQkvSide& sd, int r, int tile, int lane, const PkParams& p, bf16* k_layer,
-                                           bf16* v_layer) {
+                                           bf16* v_layer, int layer) {
   float own[4], oth[4];
   bf16r2(a.x, a.y, own[0], own[1]);
   bf16r2(a.z, a.w, own[2], own[3]);
@@ -385,6 +392,23 @@ __device__ __forceinline__ void pk_epi_qkv(const float4 a, const PkQkvSide& sd, 
   const uint2 packed = pack_bf16x4(val[0], val[1], val[2], val[3]);
   if (is_q) {
     *reinterpret_cast<uint2*>(p.q + (long long)r * p.HD + n0) = packed;
+  } else if (KVQ != 0) {
+    // KVQuant.quantize over the head's 64 dims (kvcache.py:76-90), on the bf16 values the reference would have cached: the 16
+    // lanes of the head agree on max|x|, every lane quantises its four values
+    const float x0 = bf16_lo(packed.x), x1 = bf16_hi(packed.x), x2 = bf16_lo(packed.y), x3 = bf16_hi(packed.y);
+    float mx = fmaxf(fmaxf(fabsf(x0), fabsf(x1)), fmaxf(fabsf(x2), fabsf(x3)));
+    const uint32_t group = 0xFFFFu << (lane & 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(group, mx, o));
+    if (sd.wr >= 0) {
+      constexpr bool fp8 = KVQ == 2;
+      const float inv = mx > 0.0f ? kv_quant_max(fp8) / mx : 0.0f;
+      const int kvh = is_k ? head - p.hq : head - p.hq - p.hkv;
+      const long long row = (long long)layer * p.kv_layer_rows + ((long long)sd.plane * p.hkv + kvh) * p.t_alloc + sd.wr;
+      uint8_t* dst = (is_k ? p.kq_cache : p.vq_cache) + row * 64 + d0;
+      *reinterpret_cast<uint32_t*>(dst) = kv_quant_pair(x0, x1, inv, fp8) | (kv_quant_pair(x2, x3, inv, fp8) << 16);
+      if (d0 == 0) (is_k ? p.k_scale : p.v_scale)[row] = mx;
+    }
   } else if (sd.wr >= 0) {
     const int kvh = is_k ? head - p.hq : head - p.hq - p.hkv;
     const long long off = (((long long)sd.plane * p.hkv + kvh) * p.t_alloc + sd.wr) * 64 + d0;
@@ -947,8 +971,8 @@ __device__ __forceinline__ void pk_attention_merge(const PkParams& p, PkTail* ta
 
 // One thread requests a 64-row K (or V) tile: cache row `row` of the layer, or -- 32-token pages -- the two pages at `row`, `row2`.
 __device__ __forceinline__ void pk_issue_tile(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, const PkParams& p, int layer_row, int row,
-                                              int row2) {
-  mbar_expect_tx(bar, 8192);
+                                              int row2, uint32_t bytes = 8192) {
+  mbar_expect_tx(bar, bytes);
   if (p.page_map != nullptr && p.page_tokens == 32) {
     tma_load_2d(dst, tm, 0, layer_row + row, bar, kEvictFirst);
     tma_load_2d(dst + 4096, tm, 0, layer_row + row2, bar, kEvictFirst);
@@ -1167,8 +1191,259 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
   pk_attention_merge(p, tail, attn_tiles, aw, lane, ev);
 }
 
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 ld_shared_v2(uint32_t addr) {
+  uint2 v;
+  asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+
+// The same phase over a quantised cache (step_persistent_kernel<KVQ != 0>; F8: float8_e4m3fn bytes, else u = q + 128).  The tile
+// walk, segment bookkeeping and merge plan are those of pk_attention_cta; the arithmetic of a tile is attn_process_items_q8's
+// (attention.cuh) -- 4 KB byte tiles (SWIZZLE_64B), bytes converted exactly to fp16 in registers, fp16 MMAs, permuted head dims,
+// k_scale / v_scale folded into the scores / probabilities -- in the transposed form of pk_attention_cta (half the MMAs).  Byte tiles are half
+// the size, so a warp's 16 KB buffer is TWO stages of [K tile 4 KB | V tile 4 KB]: tile i + 2 is requested when tile i has been
+// consumed and the whole buffer stays in flight (with one stage the loop was latency-bound: 30 us per layer against 18 for bf16).
+// One mbarrier per stage (the K and the V tile of a stage complete together); bit s of `phase` is the parity of stage s.
+// Partials are parked over stage 0.
+template <bool F8>
+__device__ __forceinline__ void pk_attention_cta_q8(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const PkParams& p, PkTail* tail, int layer,
+                                                    uint8_t* attn_tiles, uint32_t& phase, int cta, int aw, int lane, bool primed, PkEv& ev) {
+  constexpr int D = 64;
+  constexpr uint32_t kTileBytes = 64 * D;
+  constexpr float kLog2e = 1.4426950408889634f;
+  constexpr float kInv = F8 ? kF8Inv : kQ8Inv;
+  const int G = p.hq / p.hkv;
+  const int layer_row = layer * p.kv_layer_rows;
+  const int gid = lane >> 2, tid4 = lane & 3;
+  uint8_t* stage0 = attn_tiles + aw * 2 * 8192;
+  float* s_ks = tail->a_scales[aw];
+  float* s_vs = s_ks + 64;
+  uint64_t* bars = &tail->attn_bars[2 * aw];  // [stage]
+  const int n = tail->a_count[aw];
+  const int2* list = tail->a_list[aw];
+
+  auto issue = [&](int i) {  // one thread: K and V tile i into stage i & 1
+    uint8_t* st = stage0 + (i & 1) * 8192;
+    mbar_expect_tx(&bars[i & 1], 2 * kTileBytes);
+    tma_load_2d(st, &tm_k, 0, layer_row + list[i].x, &bars[i & 1], kEvictFirst);
+    tma_load_2d(st + kTileBytes, &tm_v, 0, layer_row + list[i].x, &bars[i & 1], kEvictFirst);
+  };
+  if (lane == 0) {
+    fence_proxy_async_all();  // rows appended by the QKV epilogue (generic stores) are read through TMA
+    if (n > 0 && !primed) issue(0);
+    if (n > 1) issue(1);
+  }
+  // The scales of a tile (two K and two V rows per lane) are requested TWO tiles ahead, when the tile's bytes are: an L2 round trip
+  // under load is longer than one tile's arithmetic.  L2 loads (ld.cg): this step's row was written by another SM.
+  struct Scales { float k0, k1, v0, v1; };
+  auto request_scales = [&](int i) {
+    Scales sc;
+    const long long row0 = (long long)layer_row + list[i].x;
+    const int c = pka_cnt(list[i].y);
+    sc.k0 = lane < c ? __ldcg(p.k_scale + row0 + lane) : 0.0f;
+    sc.k1 = lane + 32 < c ? __ldcg(p.k_scale + row0 + lane + 32) : 0.0f;
+    sc.v0 = lane < c ? __ldcg(p.v_scale + row0 + lane) : 0.0f;
+    sc.v1 = lane + 32 < c ? __ldcg(p.v_scale + row0 + lane + 32) : 0.0f;
+    return sc;
+  };
+  Scales sc_cur = {0.f, 0.f, 0.f, 0.f}, sc_next = sc_cur;
+  if (n > 0) sc_cur = request_scales(0);
+  if (n > 1) sc_next = request_scales(1);
+
+  // Transposed products, as in pk_attention_cta: S^T = K Q^T and O^T = V^T P^T, the 16-row MMA dimension carrying kv rows /
+  // head dims and the 8-column dimension the (up to 8) heads of the group.
+  //   thread (gid, tid4) owns heads h0 = 2 tid4, h1 = h0 + 1
+  //   s[mb][0..3] = S^T[kv = 16 mb + gid (+8 for 2,3)][h0, h1]
+  //   o[db][0..3] = O^T[d = 8 gid + 2 db (+1 for 2,3)][h0, h1]   (head dims permuted: a thread holds 8 consecutive dims)
+  // K as the A operand: k-slots (2 tid4, 2 tid4 + 1, 2 tid4 + 8, 2 tid4 + 9) of k-step kk are head dims 16 tid4 + 4 kk + (0..3),
+  // i.e. bytes 4 kk .. 4 kk + 3 of ONE 16-byte load per kv row; the query fragments are gathered with the same permutation.
+  uint32_t qb[4][2];
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+  float o[4][4];
+  bool seg_first = false;
+
+  for (int i = 0; i < n; ++i) {
+    const int meta = list[i].y;
+    const int r = pka_row(meta), h = pka_head(meta), cnt = pka_cnt(meta);
+    if (meta & PKA_SEG_START) {
+      const bf16* qrow = p.q + (long long)r * p.hq * D + (long long)h * G * D + gid * D + 16 * tid4;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        qb[kk][0] = gid < G ? bf16x2_to_f16x2(__ldcg(reinterpret_cast<const uint32_t*>(qrow + 4 * kk))) : 0u;
+        qb[kk][1] = gid < G ? bf16x2_to_f16x2(__ldcg(reinterpret_cast<const uint32_t*>(qrow + 4 * kk + 2))) : 0u;
+      }
+      m0 = m1 = -INFINITY;
+      l0 = l1 = 0.0f;
+#pragma unroll
+      for (int db = 0; db < 4; ++db) o[db][0] = o[db][1] = o[db][2] = o[db][3] = 0.0f;
+      seg_first = (meta & PKA_PAIR_FIRST) != 0;
+    }
+    const bool more = i + 1 < n;
+    const uint32_t kb = smem_u32(stage0 + (i & 1) * 8192), vb = kb + kTileBytes;
+    // this tile's scales to shared memory (per-row reads below), the next tile's requested
+    __syncwarp();
+    s_ks[lane] = sc_cur.k0 * kInv;
+    s_ks[lane + 32] = sc_cur.k1 * kInv;
+    s_vs[lane] = sc_cur.v0 * kInv;
+    s_vs[lane + 32] = sc_cur.v1 * kInv;
+    __syncwarp();
+    sc_cur = sc_next;
+    if (i + 2 < n) sc_next = request_scales(i + 2);
+
+    // ---- S^T = K Q^T over the 64 rows of the tile ----
+    float s[4][4];
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) s[mb][0] = s[mb][1] = s[mb][2] = s[mb][3] = 0.0f;
+    mbar_wait(&bars[i & 1], (phase >> (i & 1)) & 1u);
+    phase ^= 1u << (i & 1);
+    {
+      uint4 wa[4], wb[4];  // the thread's 16 bytes of kv rows 16 mb + gid and 16 mb + gid + 8
+#pragma unroll
+      for (int mb = 0; mb < 4; ++mb) {
+        const int ra = 16 * mb + gid, rb = ra + 8;
+        wa[mb] = ld_shared_v4(kb + ra * 64 + ((tid4 ^ ((ra >> 1) & 3)) << 4));
+        wb[mb] = ld_shared_v4(kb + rb * 64 + ((tid4 ^ ((rb >> 1) & 3)) << 4));
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {  // (independent accumulators back to back)
+          const uint32_t xa = kk == 0 ? wa[mb].x : kk == 1 ? wa[mb].y : kk == 2 ? wa[mb].z : wa[mb].w;
+          const uint32_t xb = kk == 0 ? wb[mb].x : kk == 1 ? wb[mb].y : kk == 2 ? wb[mb].z : wb[mb].w;
+          const uint32_t a[4] = {kv8_pair_f16<F8>(xa, 0x4140u), kv8_pair_f16<F8>(xb, 0x4140u), kv8_pair_f16<F8>(xa, 0x4342u),
+                                 kv8_pair_f16<F8>(xb, 0x4342u)};
+          mma_m16n8k16_f16(s[mb], a, qb[kk][0], qb[kk][1]);
+        }
+      }
+    }
+    // ---- dequantise the scores (per kv row), mask, online softmax: a head's scores live in the 8 threads of equal tid4 ----
+    float vsr[4][2];
+    float tm0 = -INFINITY, tm1 = -INFINITY;
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+      const float ka = s_ks[16 * mb + gid], kc = s_ks[16 * mb + gid + 8];
+      vsr[mb][0] = s_vs[16 * mb + gid];
+      vsr[mb][1] = s_vs[16 * mb + gid + 8];
+      s[mb][0] *= ka;
+      s[mb][1] *= ka;
+      s[mb][2] *= kc;
+      s[mb][3] *= kc;
+      if (p.softcap != 0.0f) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s[mb][q] = tanhf(s[mb][q] / p.softcap) * p.softcap;
+      }
+      if (16 * mb + gid >= cnt) s[mb][0] = s[mb][1] = -INFINITY;
+      if (16 * mb + gid + 8 >= cnt) s[mb][2] = s[mb][3] = -INFINITY;
+      tm0 = fmaxf(tm0, fmaxf(s[mb][0], s[mb][2]));
+      tm1 = fmaxf(tm1, fmaxf(s[mb][1], s[mb][3]));
+    }
+#pragma unroll
+    for (int sh = 4; sh < 32; sh <<= 1) {
+      tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, sh));
+      tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, sh));
+    }
+    const float nm0 = fmaxf(m0, tm0), nm1 = fmaxf(m1, tm1);
+    const float a0 = ex2_approx((m0 - nm0) * kLog2e), a1 = ex2_approx((m1 - nm1) * kLog2e);  // ex2(-inf) = 0 on the first tile
+    m0 = nm0;
+    m1 = nm1;
+    l0 *= a0;
+    l1 *= a1;
+    const float ms0 = m0 * kLog2e, ms1 = m1 * kLog2e;
+    uint32_t pb[4][2];  // P^T (times the V scale of its kv row) as the fp16 B operand, one k-step per 16 kv rows
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+      const float p0 = ex2_approx(fmaf(s[mb][0], kLog2e, -ms0)), p1 = ex2_approx(fmaf(s[mb][1], kLog2e, -ms1));
+      const float p2 = ex2_approx(fmaf(s[mb][2], kLog2e, -ms0)), p3 = ex2_approx(fmaf(s[mb][3], kLog2e, -ms1));
+      l0 += p0 + p2;
+      l1 += p1 + p3;
+      pb[mb][0] = movmatrix_trans(pack_f16x2(p0 * vsr[mb][0], p1 * vsr[mb][0]));
+      pb[mb][1] = movmatrix_trans(pack_f16x2(p2 * vsr[mb][1], p3 * vsr[mb][1]));
+    }
+#pragma unroll
+    for (int db = 0; db < 4; ++db) {
+      o[db][0] *= a0;
+      o[db][1] *= a1;
+      o[db][2] *= a0;
+      o[db][3] *= a1;
+    }
+    // ---- O^T += V^T P^T: a thread reads the 8 bytes V[row][8 gid .. 8 gid + 7] of kv rows 16 mb + 2 tid4 (+1, +8, +9); m-block db
+    // takes bytes 2 db (row gid of the fragment) and 2 db + 1 (row gid + 8) ----
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+      uint2 w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int row = 16 * mb + 2 * tid4 + (q & 1) + 8 * (q >> 1);
+        w[q] = ld_shared_v2(vb + row * 64 + ((((gid >> 1) ^ ((row >> 1) & 3)) << 4) | ((gid & 1) << 3)));
+        if (cnt < 64 && row >= cnt) w[q].x = w[q].y = F8 ? 0u : 0x80808080u;  // rows past the valid count may hold anything: make them zero
+      }
+#pragma unroll
+      for (int db = 0; db < 4; ++db) {
+        const uint32_t w0 = db < 2 ? w[0].x : w[0].y, w1 = db < 2 ? w[1].x : w[1].y, w2 = db < 2 ? w[2].x : w[2].y, w3 = db < 2 ? w[3].x : w[3].y;
+        // bytes (2 db, 2 db + 1) mod 4 of the two rows of a pair -> (row0[b], row1[b], row0[b + 1], row1[b + 1])
+        const uint32_t selg = (db & 1) ? 0x7362u : 0x5140u;
+        uint32_t g01, g23;
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(g01) : "r"(w0), "r"(w1), "r"(selg));
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(g23) : "r"(w2), "r"(w3), "r"(selg));
+        const uint32_t a[4] = {kv8_pair_f16<F8>(g01, 0x4140u), kv8_pair_f16<F8>(g01, 0x4342u), kv8_pair_f16<F8>(g23, 0x4140u),
+                               kv8_pair_f16<F8>(g23, 0x4342u)};
+        mma_m16n8k16_f16(o[db], a, pb[mb][0], pb[mb][1]);
+      }
+    }
+    // the stage is consumed: refill it with tile i + 2
+    fence_proxy_async();
+    __syncwarp();
+    if (i + 2 < n && lane == 0) issue(i + 2);
+
+    if (meta & PKA_SEG_END) {
+#pragma unroll
+      for (int sh = 4; sh < 32; sh <<= 1) {
+        l0 += __shfl_xor_sync(0xffffffffu, l0, sh);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, sh);
+      }
+      const int h0 = tid4 * 2;
+      // head h0: dims 8 gid .. 8 gid + 7 = o[0][0], o[0][2], o[1][0], o[1][2], ...; head h0 + 1: o[.][1], o[.][3]
+      if (seg_first && (meta & PKA_PAIR_LAST)) {
+        bf16* dst = p.attn + (long long)r * p.hq * D + (long long)h * G * D + 8 * gid;
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        if (h0 < G)
+          *reinterpret_cast<uint4*>(dst + h0 * D) = make_uint4(pack_bf16x2(o[0][0] * i0, o[0][2] * i0), pack_bf16x2(o[1][0] * i0, o[1][2] * i0),
+                                                               pack_bf16x2(o[2][0] * i0, o[2][2] * i0), pack_bf16x2(o[3][0] * i0, o[3][2] * i0));
+        if (h0 + 1 < G)
+          *reinterpret_cast<uint4*>(dst + (h0 + 1) * D) = make_uint4(pack_bf16x2(o[0][1] * i1, o[0][3] * i1), pack_bf16x2(o[1][1] * i1, o[1][3] * i1),
+                                                                     pack_bf16x2(o[2][1] * i1, o[2][3] * i1), pack_bf16x2(o[3][1] * i1, o[3][3] * i1));
+      } else {
+        const bool final_seg = !more, to_l2 = (meta & PKA_TAIL) != 0;
+        const int stride = (G * D + 2 * G + 3) & ~3;
+        float* dst = to_l2 ? p.attn_part_o + (long long)tail->a_tail[aw] * stride : final_seg ? reinterpret_cast<float*>(stage0) : tail->a_slot[aw];
+        if (h0 < G) {
+          float* row = dst + h0 * D + 8 * gid;
+          *reinterpret_cast<float4*>(row) = make_float4(o[0][0], o[0][2], o[1][0], o[1][2]);
+          *reinterpret_cast<float4*>(row + 4) = make_float4(o[2][0], o[2][2], o[3][0], o[3][2]);
+          if (gid == 0) *reinterpret_cast<float2*>(dst + G * D + h0 * 2) = make_float2(m0, l0);
+        }
+        if (h0 + 1 < G) {
+          float* row = dst + (h0 + 1) * D + 8 * gid;
+          *reinterpret_cast<float4*>(row) = make_float4(o[0][1], o[0][3], o[1][1], o[1][3]);
+          *reinterpret_cast<float4*>(row + 4) = make_float4(o[2][1], o[2][3], o[3][1], o[3][3]);
+          if (gid == 0) *reinterpret_cast<float2*>(dst + G * D + (h0 + 1) * 2) = make_float2(m1, l1);
+        }
+      }
+    }
+  }
+  pk_attention_merge(p, tail, attn_tiles, aw, lane, ev);
+}
+
 // ---- the kernel --------------------------------------------------------------------------
 
+// KVQ: 0 = bf16 KV cache, 1 = int8, 2 = float8_e4m3fn (kv_quant_axis dkv) -- separate instantiations, so the bf16 kernel's
+// code and register allocation do not change with the quantised attention path.
+template <int KVQ>
 __global__ void __launch_bounds__(kPkThreads, 1)
 step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid_constant__ CUtensorMap tm_wo,
                        const __grid_constant__ CUtensorMap tm_w01, const __grid_constant__ CUtensorMap tm_wout,
@@ -1406,7 +1681,7 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
           const float rs = tail->rstd[r];
           a.x *= rs; a.y *= rs; a.z *= rs; a.w *= rs;
         }
-        if (ph == PK_QKV) pk_epi_qkv(a, sd.q, r, tile, lane, p, k_layer, v_layer);
+        if (ph == PK_QKV) pk_epi_qkv<KVQ>(a, sd.q, r, tile, lane, p, k_layer, v_layer, layer);
         else if (ph == PK_UP) pk_epi_swiglu(a, r, tile, lane, N, p.M, p.act);
         else pk_epi_residual(a, sd.rv, r, tile, lane, N, res_out, ss_out, ss_tiles);
       };
@@ -1807,12 +2082,20 @@ step_persistent_kernel(const __grid_constant__ CUtensorMap tm_wqkv, const __grid
         // ---- attention over the valid rows of both cache segments ----
         if (may_prime && lane == 0) {
           uint8_t* kt = attn_tiles + aw * 2 * 8192;
-          pk_issue_tile(kt, &tm_k, &tail->attn_bars[2 * aw], p, l * p.kv_layer_rows, tail->a_list[aw][0].x, tail->a_row2[aw][0]);
-          pk_issue_tile(kt + 8192, &tm_v, &tail->attn_bars[2 * aw + 1], p, l * p.kv_layer_rows, tail->a_list[aw][0].x, tail->a_row2[aw][0]);
+          if constexpr (KVQ != 0) {  // byte tiles: K and V of the first tile into stage 0, one barrier (pk_attention_cta_q8)
+            const int row0 = l * p.kv_layer_rows + tail->a_list[aw][0].x;
+            mbar_expect_tx(&tail->attn_bars[2 * aw], 8192);
+            tma_load_2d(kt, &tm_k, 0, row0, &tail->attn_bars[2 * aw], kEvictFirst);
+            tma_load_2d(kt + 4096, &tm_v, 0, row0, &tail->attn_bars[2 * aw], kEvictFirst);
+          } else {
+            pk_issue_tile(kt, &tm_k, &tail->attn_bars[2 * aw], p, l * p.kv_layer_rows, tail->a_list[aw][0].x, tail->a_row2[aw][0]);
+            pk_issue_tile(kt + 8192, &tm_v, &tail->attn_bars[2 * aw + 1], p, l * p.kv_layer_rows, tail->a_list[aw][0].x, tail->a_row2[aw][0]);
+          }
         }
         pk_wait_flag(&tail->bar_done, uint32_t(2 + 5 * l));
         if (lane == 0) pk_ev(ev, 500);
-        pk_attention_cta(tm_k, tm_v, p, tail, l, attn_tiles, kv_phase, cta, aw, lane, may_prime, ev);
+        if constexpr (KVQ != 0) pk_attention_cta_q8<KVQ == 2>(tm_k, tm_v, p, tail, l, attn_tiles, kv_phase, cta, aw, lane, may_prime, ev);
+        else pk_attention_cta(tm_k, tm_v, p, tail, l, attn_tiles, kv_phase, cta, aw, lane, may_prime, ev);
         if (lane == 0) pk_ev(ev, 501);
         fence_proxy_async_all();
         named_bar_sync(3, kPkAttnWarps * 32);

@@ -84,7 +84,7 @@ def test_prefill_insert_and_decode_with_int8_cache_match_the_quantised_oracle(ax
 @pytest.mark.parametrize("axis", AXES)
 @pytest.mark.parametrize("batch", [5, 64, 200])
 def test_int8_decode_on_a_synthetic_cache_against_the_oracle(batch, axis):
-  """Ragged contexts on a random int8 cache (every step size runs the 128-row-block GEMM: padded to 128 rows, 128, 256), the oracle
+  """Ragged contexts on a random int8 cache (the persistent kernel, or the 128-row-block GEMMs padded to 128 rows, 128, 256), the oracle
   following a few slots through oracle/mirror.py on the dequantised cache; also the bf16 engine on the dequantised cache for
   reference: the two CUDA paths must agree far more tightly than either does with the CPU oracle."""
   cfg = pyconfig.initialize(
@@ -105,7 +105,12 @@ def test_int8_decode_on_a_synthetic_cache_against_the_oracle(batch, axis):
   ostate = mirror.mirror_state(engine, oracle, slots)
   sl = torch.as_tensor(slots)
   for step in range(3):
+    n0 = engine.lib.mtx_launch_count()
     state, result = engine.generate(dparams, state)
+    launches = int(engine.lib.mtx_launch_count() - n0)
+    # up to 64 rows with one scale per token and kv head run the persistent step kernel (step_persistent_kernel<1 / 2>: quantising
+    # QKV epilogue, fp16 attention over byte tiles); heads_and_dkv and larger steps take the per-kernel path
+    assert (launches == 3) == (batch <= 64 and axis in ("dkv", "fp8-dkv")), launches
     ostate, odata = oracle.generate(ostate)
     torch.testing.assert_close(state["logits"].cpu()[sl], ostate["logits"], rtol=1e-1, atol=1e-1)
     state["tokens"][sl.to(state["tokens"].device)] = odata[:, :1].to(state["tokens"].device)
