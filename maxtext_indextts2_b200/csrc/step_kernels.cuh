@@ -94,6 +94,7 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
       rf = ((idx + 1 - rl) % R + R) % R;
       if (a.page_lengths != nullptr) {
         l0 = a.page_lengths[tid];
+        l0 = l0 < a.T ? l0 : a.T;  // (the page manager keeps counting past max_target_length; a group holds at most T tokens)
         rl = rf = 0;
         plane = 0;
         wr = a.active_page[tid] * a.tokens_per_page + a.active_pos[tid];
