@@ -83,6 +83,15 @@ class ResultTokens:
     )
 
 
+@dataclasses.dataclass
+class ExistingPrefix:
+  """maxengine.py:66-77: a prefix that has already been processed -- its cache (``prefix["cache"]`` of an earlier ``prefill``)
+  and its tokens without padding."""
+
+  cache: Any
+  common_prefix_tokens: Any
+
+
 class DeviceParams:
   """Weights in the layout of ``mtx_weights`` (include/mtx_b200.h), resident in HBM.
 
@@ -571,8 +580,11 @@ class MaxEngine:
       return_prompt_logp: bool = False,
   ):
     """maxengine.py:533-574.  Returns (prefix, ResultTokens) for one sequence."""
-    if existing_prefix is not None:
-      raise ValueError("Using chunked prefill is needed for existing_prefix.")  # maxengine.py:436-437
+    start_position = 0
+    if existing_prefix is not None:  # maxengine.py:434-440: this call continues a prefix processed by earlier calls
+      if not self.use_chunked_prefill:
+        raise ValueError("Using chunked prefill is needed for existing_prefix.")
+      start_position = int(torch.as_tensor(existing_prefix.common_prefix_tokens).reshape(-1).numel())
     if return_prompt_logp:
       raise NotImplementedError("return_prompt_logp is outside the decode path")
     self._bind(params)
@@ -582,12 +594,22 @@ class MaxEngine:
     if self._paged:  # maxengine.py:549-554: the slot's pages are reserved before the prefill runs
       if slot is None:
         raise ValueError("attention=paged: prefill needs the slot (page group) the sequence will be inserted into")
-      self.page_state = self.page_manager.update_prefill_pages(page_state=self.page_state, page_group_id=int(slot), true_length=true_length)
+      self.page_state = self.page_manager.update_prefill_pages(page_state=self.page_state, page_group_id=int(slot),
+                                                               true_length=start_position + true_length)
     toks = torch.as_tensor(padded_tokens).reshape(-1)
-    if true_length < 1 or true_length > toks.numel() or toks.numel() > cfg.max_prefill_predict_length:
-      raise ValueError(f"true_length={true_length}, {toks.numel()} padded tokens, max_prefill_predict_length={cfg.max_prefill_predict_length}")
+    if true_length < 1 or true_length > toks.numel() or start_position + toks.numel() > cfg.max_prefill_predict_length:
+      raise ValueError(f"true_length={true_length}, {toks.numel()} padded tokens after {start_position} prefix tokens, "
+                       f"max_prefill_predict_length={cfg.max_prefill_predict_length}")
     n = toks.numel()
     self._prefill_tokens[:n].copy_(toks.to(torch.int32), non_blocking=True)
+    if start_position:
+      # the prefix's cache rows go back to the staging plane (a no-op copy when the previous call left them there); the new
+      # positions [start_position, start_position + true_length) attend to them causally (kvcache.py:584-624 with previous_chunk)
+      pk, pv = existing_prefix.cache["key"], existing_prefix.cache["value"]  # [L, Hkv, >= start_position, D]
+      if int(pk.shape[2]) < start_position:
+        raise ValueError(f"existing_prefix.cache holds {int(pk.shape[2])} rows for {start_position} common_prefix_tokens")
+      self._k[:, self._staging, :, :start_position].copy_(pk[:, :, :start_position])
+      self._v[:, self._staging, :, :start_position].copy_(pv[:, :, :start_position])
     want_logits = self._logits is not None or self._vp_world > 1
     for start in range(0, true_length, self._chunk):
       count = min(self._chunk, true_length - start)
@@ -597,7 +619,7 @@ class MaxEngine:
               self._handle,
               ctypes.c_void_p(self._prefill_tokens.data_ptr() + 4 * start),
               count,
-              start,
+              start_position + start,
               self._staging,
               1 if last else 0,
               ctypes.c_void_p(self._first_token.data_ptr()),
@@ -616,14 +638,15 @@ class MaxEngine:
                                             ctypes.c_void_p(self._first_log_prob.data_ptr()) if self._first_log_prob is not None else None,
                                             self._stream()))
     first = self._first_token.clone().reshape(1, 1)
+    full_true_length = start_position + true_length  # maxengine.py:442
     prefix = {
         "logits": self._prefill_logits.clone().reshape(1, 1, -1) if want_logits else None,
         "cache": {
-            "key": self._k[:, self._staging, :, :true_length].clone(),  # [L, Hkv, len, D]
-            "value": self._v[:, self._staging, :, :true_length].clone(),
-            "prefill_length": true_length,
+            "key": self._k[:, self._staging, :, :full_true_length].clone(),  # [L, Hkv, len, D]
+            "value": self._v[:, self._staging, :, :full_true_length].clone(),
+            "prefill_length": full_true_length,
         },
-        "next_pos": torch.full((1, 1), true_length, dtype=torch.int32, device=self.device),
+        "next_pos": torch.full((1, 1), full_true_length, dtype=torch.int32, device=self.device),
         "generated_tokens": torch.zeros((1, 1), dtype=torch.int32, device=self.device),
         "tokens": first,
     }

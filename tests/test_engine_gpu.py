@@ -397,3 +397,49 @@ def test_output_head_and_softcap_variants_match_oracle(kw, batch):
     state, result = engine.generate(dparams, state)
     _assert_logits(state["logits"].cpu()[:3] * sc, ostate["logits"] * sc)
     state["tokens"][:3] = odata[:, :1].to(state["tokens"].device)  # teacher-force the oracle's tokens
+
+
+def test_chunked_prefill_with_existing_prefix_matches_one_call():
+  """maxengine.py:434-440: a prompt processed by three prefill calls (existing_prefix carrying the cache and the tokens done so far)
+  against the same prompt in one call and against the oracle's prefill: same cache rows and last-position logits up to the
+  summation order of the attention (different chunk boundaries), same next_pos; the prefix decodes like the one-call prefix."""
+  cfg = small_config(per_device_batch_size=2, max_prefill_predict_length=32, max_target_length=48, materialize_logits=True,
+                     use_chunked_prefill=True, prefill_chunk_size=8)
+  params = make_params(cfg)
+  oracle = ref.DecodeOracle(cfg, params, faithful=True)
+  engine = maxengine.MaxEngine(cfg)
+  dparams = engine.load_params(params)
+  toks = random_tokens((1, 32), cfg.vocab_size, seed=77)[0]
+  n = 27
+  whole, _ = engine.prefill(params=dparams, padded_tokens=toks, true_length=n)
+  # 11 + 9 + 7 tokens, the middle chunk padded
+  prefix, _ = engine.prefill(params=dparams, padded_tokens=toks[:11], true_length=11)
+  assert int(prefix["next_pos"]) == 11 and prefix["cache"]["key"].shape[2] == 11
+  padded = torch.zeros(12, dtype=torch.int64)
+  padded[:9] = toks[11:20]
+  prefix, _ = engine.prefill(params=dparams, padded_tokens=padded, true_length=9,
+                             existing_prefix=maxengine.ExistingPrefix(cache=prefix["cache"], common_prefix_tokens=toks[:11]))
+  assert int(prefix["next_pos"]) == 20
+  prefix, result = engine.prefill(params=dparams, padded_tokens=toks[20:27], true_length=7,
+                                  existing_prefix=maxengine.ExistingPrefix(cache=prefix["cache"], common_prefix_tokens=toks[:20]))
+  assert int(prefix["next_pos"]) == n and int(prefix["cache"]["prefill_length"]) == n and result.data.shape == (1, 3)
+  for name in ("key", "value"):
+    a, b = prefix["cache"][name].float().cpu(), whole["cache"][name].float().cpu()
+    assert a.shape == b.shape
+    assert (a - b).abs().max() <= 2**-6 * b.abs().max()
+  oprefix, ofirst = oracle.prefill(toks, n)
+  _assert_logits(prefix["logits"].cpu()[0], oprefix["logits"][0])
+  _assert_logits(whole["logits"].cpu()[0], oprefix["logits"][0])
+  # and it decodes: insert + 4 lock-step steps
+  prefix["tokens"].fill_(int(ofirst))
+  state = engine.insert(prefix, engine.init_decode_state(), 1)
+  ostate = oracle.insert(oprefix, oracle.init_decode_state(), 1)
+  for _ in range(4):
+    ostate, odata = oracle.generate(ostate)
+    state, _ = engine.generate(dparams, state)
+    torch.testing.assert_close(state["logits"].cpu()[1], ostate["logits"][1], rtol=1e-1, atol=1e-1)
+    state["tokens"].copy_(odata[:, :1])
+  with pytest.raises(ValueError, match="chunked prefill"):
+    plain = maxengine.MaxEngine(small_config())
+    plain.prefill(params=plain.load_params(make_params(small_config())), padded_tokens=toks[:4], true_length=4,
+                  existing_prefix=maxengine.ExistingPrefix(cache=prefix["cache"], common_prefix_tokens=toks[:4]))
