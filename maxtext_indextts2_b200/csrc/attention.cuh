@@ -529,9 +529,148 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// Transposes an 8x8 matrix of 16-bit elements held one row pair per thread (thread (gid, tid4) holds M[gid][2 tid4 .. +1]).
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 ld_shared_v2(uint32_t addr) {
+  uint2 v;
+  asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+
+// ---- the same tile in TRANSPOSED form, for groups of up to 8 heads: S^T = K Q^T and O^T = V^T P^T, the 16-row MMA dimension
+// carrying kv rows / head dims and the 8-column dimension the heads (no padding of the group to 16 rows: half the MMAs).
+//   thread (gid, tid4) owns heads h0 = 2 tid4, h1 = h0 + 1;  m / l: running max and (this thread's rows of the) sum per head
+//   qb[kk][0..1] = fp16 Q[head gid][16 tid4 + 4 kk + (0,1)], [.. + (2,3)]   (zero for gid >= G)
+//   o[db][0..3]  = O^T[d = 8 gid + 2 db (+1 for 2,3)][h0, h1]: a thread holds 8 consecutive dims of its two heads
+// K as the A operand: k-slots (2 tid4, 2 tid4 + 1, 2 tid4 + 8, 2 tid4 + 9) of k-step kk are head dims 16 tid4 + 4 kk + (0..3), i.e.
+// bytes 4 kk .. 4 kk + 3 of ONE 16-byte load per kv row (the query fragments carry the same permutation).
+// kv8t_scores: scores of the tile at shared address kb (64 rows x 64 bytes, SWIZZLE_64B), dequantised with s_ks[row], masked past
+// `cnt`, online-softmax update of (m, l, o); returns P^T (times s_vs[row]) as the fp16 B operand pb of the P V product.
+template <bool F8>
+__device__ __forceinline__ void kv8t_scores(uint32_t kb, const float* s_ks, const float* s_vs, int cnt, float softcap, const uint32_t (&qb)[4][2],
+                                            float& m0, float& m1, float& l0, float& l1, float (&o)[4][4], uint32_t (&pb)[4][2], int gid, int tid4) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  float s[4][4];
+#pragma unroll
+  for (int mb = 0; mb < 4; ++mb) s[mb][0] = s[mb][1] = s[mb][2] = s[mb][3] = 0.0f;
+  {
+    uint4 wa[4], wb[4];  // the thread's 16 bytes of kv rows 16 mb + gid and 16 mb + gid + 8
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+      const int ra = 16 * mb + gid, rb = ra + 8;
+      wa[mb] = ld_shared_v4(kb + ra * 64 + ((tid4 ^ ((ra >> 1) & 3)) << 4));
+      wb[mb] = ld_shared_v4(kb + rb * 64 + ((tid4 ^ ((rb >> 1) & 3)) << 4));
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int mb = 0; mb < 4; ++mb) {  // (independent accumulators back to back)
+        const uint32_t xa = kk == 0 ? wa[mb].x : kk == 1 ? wa[mb].y : kk == 2 ? wa[mb].z : wa[mb].w;
+        const uint32_t xb = kk == 0 ? wb[mb].x : kk == 1 ? wb[mb].y : kk == 2 ? wb[mb].z : wb[mb].w;
+        const uint32_t a[4] = {kv8_pair_f16<F8>(xa, 0x4140u), kv8_pair_f16<F8>(xb, 0x4140u), kv8_pair_f16<F8>(xa, 0x4342u),
+                               kv8_pair_f16<F8>(xb, 0x4342u)};
+        mma_m16n8k16_f16(s[mb], a, qb[kk][0], qb[kk][1]);
+      }
+    }
+  }
+  // dequantise (per kv row), mask, online softmax: a head's scores live in the 8 threads of equal tid4
+  float vsr[4][2];
+  float tm0 = -INFINITY, tm1 = -INFINITY;
+#pragma unroll
+  for (int mb = 0; mb < 4; ++mb) {
+    const float ka = s_ks[16 * mb + gid], kc = s_ks[16 * mb + gid + 8];
+    vsr[mb][0] = s_vs[16 * mb + gid];
+    vsr[mb][1] = s_vs[16 * mb + gid + 8];
+    s[mb][0] *= ka;
+    s[mb][1] *= ka;
+    s[mb][2] *= kc;
+    s[mb][3] *= kc;
+    if (softcap != 0.0f) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[mb][q] = tanhf(s[mb][q] / softcap) * softcap;
+    }
+    if (16 * mb + gid >= cnt) s[mb][0] = s[mb][1] = -INFINITY;
+    if (16 * mb + gid + 8 >= cnt) s[mb][2] = s[mb][3] = -INFINITY;
+    tm0 = fmaxf(tm0, fmaxf(s[mb][0], s[mb][2]));
+    tm1 = fmaxf(tm1, fmaxf(s[mb][1], s[mb][3]));
+  }
+#pragma unroll
+  for (int sh = 4; sh < 32; sh <<= 1) {
+    tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, sh));
+    tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, sh));
+  }
+  const float nm0 = fmaxf(m0, tm0), nm1 = fmaxf(m1, tm1);
+  const float a0 = ex2_approx((m0 - nm0) * kLog2e), a1 = ex2_approx((m1 - nm1) * kLog2e);  // ex2(-inf) = 0 on the first tile
+  m0 = nm0;
+  m1 = nm1;
+  l0 *= a0;
+  l1 *= a1;
+  const float ms0 = m0 * kLog2e, ms1 = m1 * kLog2e;
+#pragma unroll
+  for (int mb = 0; mb < 4; ++mb) {
+    const float p0 = ex2_approx(fmaf(s[mb][0], kLog2e, -ms0)), p1 = ex2_approx(fmaf(s[mb][1], kLog2e, -ms1));
+    const float p2 = ex2_approx(fmaf(s[mb][2], kLog2e, -ms0)), p3 = ex2_approx(fmaf(s[mb][3], kLog2e, -ms1));
+    l0 += p0 + p2;
+    l1 += p1 + p3;
+    pb[mb][0] = movmatrix_trans(pack_f16x2(p0 * vsr[mb][0], p1 * vsr[mb][0]));
+    pb[mb][1] = movmatrix_trans(pack_f16x2(p2 * vsr[mb][1], p3 * vsr[mb][1]));
+  }
+#pragma unroll
+  for (int db = 0; db < 4; ++db) {
+    o[db][0] *= a0;
+    o[db][1] *= a1;
+    o[db][2] *= a0;
+    o[db][3] *= a1;
+  }
+}
+
+// O^T += V^T P^T over the tile at shared address vb: a thread reads the 8 bytes V[row][8 gid .. 8 gid + 7] of kv rows
+// 16 mb + 2 tid4 (+1, +8, +9); m-block db takes bytes 2 db (row gid of the fragment) and 2 db + 1 (row gid + 8).
+template <bool F8>
+__device__ __forceinline__ void kv8t_pv(uint32_t vb, int cnt, const uint32_t (&pb)[4][2], float (&o)[4][4], int gid, int tid4) {
+#pragma unroll
+  for (int mb = 0; mb < 4; ++mb) {
+    uint2 w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int row = 16 * mb + 2 * tid4 + (q & 1) + 8 * (q >> 1);
+      w[q] = ld_shared_v2(vb + row * 64 + ((((gid >> 1) ^ ((row >> 1) & 3)) << 4) | ((gid & 1) << 3)));
+      if (cnt < 64 && row >= cnt) w[q].x = w[q].y = F8 ? 0u : 0x80808080u;  // rows past the valid count may hold anything: make them zero
+    }
+#pragma unroll
+    for (int db = 0; db < 4; ++db) {
+      const uint32_t w0 = db < 2 ? w[0].x : w[0].y, w1 = db < 2 ? w[1].x : w[1].y, w2 = db < 2 ? w[2].x : w[2].y, w3 = db < 2 ? w[3].x : w[3].y;
+      // bytes (2 db, 2 db + 1) mod 4 of the two rows of a pair -> (row0[b], row1[b], row0[b + 1], row1[b + 1])
+      const uint32_t selg = (db & 1) ? 0x7362u : 0x5140u;
+      uint32_t g01, g23;
+      asm("prmt.b32 %0, %1, %2, %3;" : "=r"(g01) : "r"(w0), "r"(w1), "r"(selg));
+      asm("prmt.b32 %0, %1, %2, %3;" : "=r"(g23) : "r"(w2), "r"(w3), "r"(selg));
+      const uint32_t a[4] = {kv8_pair_f16<F8>(g01, 0x4140u), kv8_pair_f16<F8>(g01, 0x4342u), kv8_pair_f16<F8>(g23, 0x4140u),
+                             kv8_pair_f16<F8>(g23, 0x4342u)};
+      mma_m16n8k16_f16(o[db], a, pb[mb][0], pb[mb][1]);
+    }
+  }
+}
+
 // The attention work loop of 128 threads (4 warps) over an int8 cache, head_dim 64.  Same contract as attn_process_items;
 // `tiles` = [warp][kQ8WarpBytes], k_scale / v_scale = fp32 per cache row, indexed like the rows of the K/V tensor maps.
-template <bool F8>
+// TR: groups of up to 8 heads run the tile in the transposed form (kv8t_scores / kv8t_pv): half the MMAs and half the
+// accumulator registers of the heads-in-rows form below, which stays for wider groups.
+template <bool F8, bool TR>
 __device__ __forceinline__ void attn_process_items_q8(const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnParams& p, const float* k_scale,
                                                       const float* v_scale, uint8_t* tiles, float* sm_o_all, uint64_t* bars, float* sm_stat,
                                                       uint32_t& phase, int tid, int first_item, int item_stride) {
@@ -577,6 +716,85 @@ __device__ __forceinline__ void attn_process_items_q8(const CUtensorMap& tm_k, c
       tma_load_2d(v_tile, &tm_v, 0, plane_row + loc.p0, bar_v, kEvictFirst);
     }
 
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+    if constexpr (TR) {
+      uint32_t qb[4][2];
+      {
+        const bf16* qrow = p.q + (long long)r * p.hq * D + (long long)h * G * D + gid * D + 16 * tid4;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          qb[kk][0] = gid < G ? bf16x2_to_f16x2(*reinterpret_cast<const uint32_t*>(qrow + 4 * kk)) : 0u;
+          qb[kk][1] = gid < G ? bf16x2_to_f16x2(*reinterpret_cast<const uint32_t*>(qrow + 4 * kk + 2)) : 0u;
+        }
+      }
+      float o[4][4];
+#pragma unroll
+      for (int db = 0; db < 4; ++db) o[db][0] = o[db][1] = o[db][2] = o[db][3] = 0.0f;
+      // a tile's scales (two K and two V rows per lane) are requested one tile ahead, with the tile's bytes
+      float sk0, sk1, sv0, sv1;
+      auto request_scales = [&](const TileLoc& tl) {
+        const long long row0 = (long long)plane_row + tl.p0;
+        sk0 = lane < tl.cnt ? __ldg(k_scale + row0 + lane) : 0.0f;
+        sk1 = lane + 32 < tl.cnt ? __ldg(k_scale + row0 + lane + 32) : 0.0f;
+        sv0 = lane < tl.cnt ? __ldg(v_scale + row0 + lane) : 0.0f;
+        sv1 = lane + 32 < tl.cnt ? __ldg(v_scale + row0 + lane + 32) : 0.0f;
+      };
+      request_scales(loc);
+      for (; t < t_end; t += kAttnWarps) {
+        const int cnt = loc.cnt;
+        const int tn = t + kAttnWarps;
+        const TileLoc nloc = attn_tile(tn < t_end ? tn : nt, len0, rf, rl, p.P, R);
+        __syncwarp();
+        s_ks[lane] = sk0 * (F8 ? kF8Inv : kQ8Inv);
+        s_ks[lane + 32] = sk1 * (F8 ? kF8Inv : kQ8Inv);
+        s_vs[lane] = sv0 * (F8 ? kF8Inv : kQ8Inv);
+        s_vs[lane + 32] = sv1 * (F8 ? kF8Inv : kQ8Inv);
+        __syncwarp();
+        if (tn < t_end) request_scales(nloc);
+        uint32_t pb[4][2];
+        mbar_wait(bar_k, phase);
+        kv8t_scores<F8>(kb, s_ks, s_vs, cnt, p.softcap, qb, m0, m1, l0, l1, o, pb, gid, tid4);
+        fence_proxy_async();
+        __syncwarp();
+        if (tn < t_end && lane == 0) {
+          mbar_expect_tx(bar_k, kTileBytes);
+          tma_load_2d(k_tile, &tm_k, 0, plane_row + nloc.p0, bar_k, kEvictFirst);
+        }
+        mbar_wait(bar_v, phase);
+        kv8t_pv<F8>(vb, cnt, pb, o, gid, tid4);
+        fence_proxy_async();
+        __syncwarp();
+        if (tn < t_end && lane == 0) {
+          mbar_expect_tx(bar_v, kTileBytes);
+          tma_load_2d(v_tile, &tm_v, 0, plane_row + nloc.p0, bar_v, kEvictFirst);
+        }
+        phase ^= 1;
+        loc = nloc;
+      }
+#pragma unroll
+      for (int sh = 4; sh < 32; sh <<= 1) {
+        l0 += __shfl_xor_sync(0xffffffffu, l0, sh);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, sh);
+      }
+      // the warp's partial to the merge buffer: head h0 = 2 tid4 holds dims 8 gid .. 8 gid + 7 in o[.][0], o[.][2]; h0 + 1 in o[.][1], o[.][3]
+      const int h0 = 2 * tid4;
+      if (h0 < G) {
+        float* row = sm_o + h0 * D + 8 * gid;
+        *reinterpret_cast<float4*>(row) = make_float4(o[0][0], o[0][2], o[1][0], o[1][2]);
+        *reinterpret_cast<float4*>(row + 4) = make_float4(o[2][0], o[2][2], o[3][0], o[3][2]);
+      }
+      if (h0 + 1 < G) {
+        float* row = sm_o + (h0 + 1) * D + 8 * gid;
+        *reinterpret_cast<float4*>(row) = make_float4(o[0][1], o[0][3], o[1][1], o[1][3]);
+        *reinterpret_cast<float4*>(row + 4) = make_float4(o[2][1], o[2][3], o[3][1], o[3][3]);
+      }
+      if (gid == 0) {
+        sm_m[warp * 16 + h0] = m0;
+        sm_m[warp * 16 + h0 + 1] = m1;
+        sm_l[warp * 16 + h0] = l0;
+        sm_l[warp * 16 + h0 + 1] = l1;
+      }
+    } else {
     // Q fragments (A operand: rows = query heads of the group, zero-padded to 16) as fp16, head dims gathered with the K
     // permutation: k-slot (2 tid4 + e) of k-step tt is head dim 16 tid4 + 4 tt + e, k-slot (2 tid4 + 8 + e) is dim 16 tid4 + 4 tt + 2 + e
     uint32_t qf[4][4];
@@ -592,7 +810,6 @@ __device__ __forceinline__ void attn_process_items_q8(const CUtensorMap& tm_k, c
       }
     }
 
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
     float o[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.0f;
@@ -732,6 +949,7 @@ __device__ __forceinline__ void attn_process_items_q8(const CUtensorMap& tm_k, c
       sm_l[warp * 16 + gid] = l0;
       sm_l[warp * 16 + gid + 8] = l1;
     }
+    }  // (heads-in-rows form)
     epi_bar_sync();
 
     const long long out_base = (long long)r * p.hq * D + (long long)h * G * D;
@@ -801,7 +1019,7 @@ __device__ __forceinline__ void attn_process_items_q8(const CUtensorMap& tm_k, c
 }
 
 
-template <bool F8>
+template <bool F8, bool TR>
 __global__ void __launch_bounds__(kAttnThreads)
 decode_attn_q8_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnParams p, const float* k_scale,
                       const float* v_scale) {
@@ -827,7 +1045,7 @@ decode_attn_q8_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
   __syncthreads();
   griddep_wait();
   uint32_t phase = 0;
-  attn_process_items_q8<F8>(tm_k, tm_v, p, k_scale, v_scale, smem, sm_o_all, bars, sm_stat, phase, threadIdx.x, blockIdx.x, gridDim.x);
+  attn_process_items_q8<F8, TR>(tm_k, tm_v, p, k_scale, v_scale, smem, sm_o_all, bars, sm_stat, phase, threadIdx.x, blockIdx.x, gridDim.x);
   timeline_end(tl);
 }
 

@@ -558,10 +558,11 @@ int launch_attention(mtx_engine* e, int layer, int rows, cudaStream_t st, int mo
     const size_t smem_q = attn_q8_smem_bytes(c.num_q_heads / c.num_kv_heads);
     int grid_q = rows * c.num_kv_heads * attn_max_chunks(c.max_prefill_len, c.max_target_len, p.tiles_per_item);
     if (grid_q > e->num_sms * 4) grid_q = e->num_sms * 4;
-    if (kvq_fp8(c))
-      return launch(decode_attn_q8_kernel<true>, dim3(grid_q), dim3(kAttnThreads), smem_q, st, e->tm_kq, e->tm_vq, p, (const float*)e->s.k_scale,
-                    (const float*)e->s.v_scale);
-    return launch(decode_attn_q8_kernel<false>, dim3(grid_q), dim3(kAttnThreads), smem_q, st, e->tm_kq, e->tm_vq, p, (const float*)e->s.k_scale,
+    // groups of up to 8 heads: the transposed tile arithmetic (half the MMAs, fewer registers: four CTAs per SM)
+    const bool tr = c.num_q_heads / c.num_kv_heads <= 8 && env_int("MTX_Q8_TRANSPOSED", 1) != 0;
+    auto kern = kvq_fp8(c) ? (tr ? decode_attn_q8_kernel<true, true> : decode_attn_q8_kernel<true, false>)
+                           : (tr ? decode_attn_q8_kernel<false, true> : decode_attn_q8_kernel<false, false>);
+    return launch(kern, dim3(grid_q), dim3(kAttnThreads), smem_q, st, e->tm_kq, e->tm_vq, p, (const float*)e->s.k_scale,
                   (const float*)e->s.v_scale);
   }
   if (c.head_dim == 256) {  // wide heads: the transposed kernel (attention_wide.cuh), one CTA of three warps per SM
@@ -1584,8 +1585,10 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
     MTX_TRY(make_map(&e->tm_v, s->v_cache, c.head_dim, stage_rows, kAttnTileRows));
     MTX_TRY(make_map_u8(&e->tm_kq, s->kq_cache, kv_rows));
     MTX_TRY(make_map_u8(&e->tm_vq, s->vq_cache, kv_rows));
-    MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_q8_smem_bytes(16))));
-    MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_q8_smem_bytes(16))));
+    MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_q8_smem_bytes(16))));
+    MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_q8_smem_bytes(16))));
+    MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_q8_smem_bytes(16))));
+    MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_q8_smem_bytes(16))));
   } else if (is_paged(c)) {
     if (!s->k_pages || !s->v_pages || !s->page_map || !s->page_lengths || !s->active_page || !s->active_page_pos)
       return fail(MTX_ERR_ARG, "attention=paged: k_pages / v_pages / page_map / page_lengths / active_page / active_page_pos must be set");

@@ -198,17 +198,6 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
   return v;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-// Transposes an 8x8 matrix of 16-bit elements held one row pair per thread (thread (gid, tid4) holds M[gid][2 tid4 .. +1]).
-__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
-  uint32_t d;
-  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
-  return d;
-}
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 __device__ __forceinline__ void pk_wait_flag(volatile uint32_t* flag, uint32_t want) {
   if (*flag >= want) return;
@@ -1191,17 +1180,6 @@ __device__ __forceinline__ void pk_attention_cta(const CUtensorMap& tm_k, const 
   pk_attention_merge(p, tail, attn_tiles, aw, lane, ev);
 }
 
-__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
-  uint4 v;
-  asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint2 ld_shared_v2(uint32_t addr) {
-  uint2 v;
-  asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
-  return v;
-}
-
 // The same phase over a quantised cache (step_persistent_kernel<KVQ != 0>; F8: float8_e4m3fn bytes, else u = q + 128).  The tile
 // walk, segment bookkeeping and merge plan are those of pk_attention_cta; the arithmetic of a tile is attn_process_items_q8's
 // (attention.cuh) -- 4 KB byte tiles (SWIZZLE_64B), bytes converted exactly to fp16 in registers, fp16 MMAs, permuted head dims,
@@ -1295,106 +1273,11 @@ __device__ __forceinline__ void pk_attention_cta_q8(const CUtensorMap& tm_k, con
     sc_cur = sc_next;
     if (i + 2 < n) sc_next = request_scales(i + 2);
 
-    // ---- S^T = K Q^T over the 64 rows of the tile ----
-    float s[4][4];
-#pragma unroll
-    for (int mb = 0; mb < 4; ++mb) s[mb][0] = s[mb][1] = s[mb][2] = s[mb][3] = 0.0f;
     mbar_wait(&bars[i & 1], (phase >> (i & 1)) & 1u);
     phase ^= 1u << (i & 1);
-    {
-      uint4 wa[4], wb[4];  // the thread's 16 bytes of kv rows 16 mb + gid and 16 mb + gid + 8
-#pragma unroll
-      for (int mb = 0; mb < 4; ++mb) {
-        const int ra = 16 * mb + gid, rb = ra + 8;
-        wa[mb] = ld_shared_v4(kb + ra * 64 + ((tid4 ^ ((ra >> 1) & 3)) << 4));
-        wb[mb] = ld_shared_v4(kb + rb * 64 + ((tid4 ^ ((rb >> 1) & 3)) << 4));
-      }
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-        for (int mb = 0; mb < 4; ++mb) {  // (independent accumulators back to back)
-          const uint32_t xa = kk == 0 ? wa[mb].x : kk == 1 ? wa[mb].y : kk == 2 ? wa[mb].z : wa[mb].w;
-          const uint32_t xb = kk == 0 ? wb[mb].x : kk == 1 ? wb[mb].y : kk == 2 ? wb[mb].z : wb[mb].w;
-          const uint32_t a[4] = {kv8_pair_f16<F8>(xa, 0x4140u), kv8_pair_f16<F8>(xb, 0x4140u), kv8_pair_f16<F8>(xa, 0x4342u),
-                                 kv8_pair_f16<F8>(xb, 0x4342u)};
-          mma_m16n8k16_f16(s[mb], a, qb[kk][0], qb[kk][1]);
-        }
-      }
-    }
-    // ---- dequantise the scores (per kv row), mask, online softmax: a head's scores live in the 8 threads of equal tid4 ----
-    float vsr[4][2];
-    float tm0 = -INFINITY, tm1 = -INFINITY;
-#pragma unroll
-    for (int mb = 0; mb < 4; ++mb) {
-      const float ka = s_ks[16 * mb + gid], kc = s_ks[16 * mb + gid + 8];
-      vsr[mb][0] = s_vs[16 * mb + gid];
-      vsr[mb][1] = s_vs[16 * mb + gid + 8];
-      s[mb][0] *= ka;
-      s[mb][1] *= ka;
-      s[mb][2] *= kc;
-      s[mb][3] *= kc;
-      if (p.softcap != 0.0f) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) s[mb][q] = tanhf(s[mb][q] / p.softcap) * p.softcap;
-      }
-      if (16 * mb + gid >= cnt) s[mb][0] = s[mb][1] = -INFINITY;
-      if (16 * mb + gid + 8 >= cnt) s[mb][2] = s[mb][3] = -INFINITY;
-      tm0 = fmaxf(tm0, fmaxf(s[mb][0], s[mb][2]));
-      tm1 = fmaxf(tm1, fmaxf(s[mb][1], s[mb][3]));
-    }
-#pragma unroll
-    for (int sh = 4; sh < 32; sh <<= 1) {
-      tm0 = fmaxf(tm0, __shfl_xor_sync(0xffffffffu, tm0, sh));
-      tm1 = fmaxf(tm1, __shfl_xor_sync(0xffffffffu, tm1, sh));
-    }
-    const float nm0 = fmaxf(m0, tm0), nm1 = fmaxf(m1, tm1);
-    const float a0 = ex2_approx((m0 - nm0) * kLog2e), a1 = ex2_approx((m1 - nm1) * kLog2e);  // ex2(-inf) = 0 on the first tile
-    m0 = nm0;
-    m1 = nm1;
-    l0 *= a0;
-    l1 *= a1;
-    const float ms0 = m0 * kLog2e, ms1 = m1 * kLog2e;
-    uint32_t pb[4][2];  // P^T (times the V scale of its kv row) as the fp16 B operand, one k-step per 16 kv rows
-#pragma unroll
-    for (int mb = 0; mb < 4; ++mb) {
-      const float p0 = ex2_approx(fmaf(s[mb][0], kLog2e, -ms0)), p1 = ex2_approx(fmaf(s[mb][1], kLog2e, -ms1));
-      const float p2 = ex2_approx(fmaf(s[mb][2], kLog2e, -ms0)), p3 = ex2_approx(fmaf(s[mb][3], kLog2e, -ms1));
-      l0 += p0 + p2;
-      l1 += p1 + p3;
-      pb[mb][0] = movmatrix_trans(pack_f16x2(p0 * vsr[mb][0], p1 * vsr[mb][0]));
-      pb[mb][1] = movmatrix_trans(pack_f16x2(p2 * vsr[mb][1], p3 * vsr[mb][1]));
-    }
-#pragma unroll
-    for (int db = 0; db < 4; ++db) {
-      o[db][0] *= a0;
-      o[db][1] *= a1;
-      o[db][2] *= a0;
-      o[db][3] *= a1;
-    }
-    // ---- O^T += V^T P^T: a thread reads the 8 bytes V[row][8 gid .. 8 gid + 7] of kv rows 16 mb + 2 tid4 (+1, +8, +9); m-block db
-    // takes bytes 2 db (row gid of the fragment) and 2 db + 1 (row gid + 8) ----
-#pragma unroll
-    for (int mb = 0; mb < 4; ++mb) {
-      uint2 w[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int row = 16 * mb + 2 * tid4 + (q & 1) + 8 * (q >> 1);
-        w[q] = ld_shared_v2(vb + row * 64 + ((((gid >> 1) ^ ((row >> 1) & 3)) << 4) | ((gid & 1) << 3)));
-        if (cnt < 64 && row >= cnt) w[q].x = w[q].y = F8 ? 0u : 0x80808080u;  // rows past the valid count may hold anything: make them zero
-      }
-#pragma unroll
-      for (int db = 0; db < 4; ++db) {
-        const uint32_t w0 = db < 2 ? w[0].x : w[0].y, w1 = db < 2 ? w[1].x : w[1].y, w2 = db < 2 ? w[2].x : w[2].y, w3 = db < 2 ? w[3].x : w[3].y;
-        // bytes (2 db, 2 db + 1) mod 4 of the two rows of a pair -> (row0[b], row1[b], row0[b + 1], row1[b + 1])
-        const uint32_t selg = (db & 1) ? 0x7362u : 0x5140u;
-        uint32_t g01, g23;
-        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(g01) : "r"(w0), "r"(w1), "r"(selg));
-        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(g23) : "r"(w2), "r"(w3), "r"(selg));
-        const uint32_t a[4] = {kv8_pair_f16<F8>(g01, 0x4140u), kv8_pair_f16<F8>(g01, 0x4342u), kv8_pair_f16<F8>(g23, 0x4140u),
-                               kv8_pair_f16<F8>(g23, 0x4342u)};
-        mma_m16n8k16_f16(o[db], a, pb[mb][0], pb[mb][1]);
-      }
-    }
+    uint32_t pb[4][2];
+    kv8t_scores<F8>(kb, s_ks, s_vs, cnt, p.softcap, qb, m0, m1, l0, l1, o, pb, gid, tid4);
+    kv8t_pv<F8>(vb, cnt, pb, o, gid, tid4);
     // the stage is consumed: refill it with tile i + 2
     fence_proxy_async();
     __syncwarp();
