@@ -92,6 +92,10 @@ typedef struct {
   int32_t paged_num_pages;           /* pagedattn_num_pages, 0 = contiguous cache */
   int32_t paged_tokens_per_page;     /* pagedattn_tokens_per_page: a power of two >= 8 */
   int32_t paged_max_pages_per_group; /* pagedattn_max_pages_per_group (>= ceil(T / tokens_per_page)) */
+  int32_t paged_device_state;        /* 1: the whole PageState lives in decode_state (page_status, num_pages_used, has_active_page
+                                        too) and every decode step begins with PageManager.update_decode_pages ON THE DEVICE
+                                        (page_manager.py:332-412; in the step's first kernel), as the reference's jitted update does;
+                                        0: the caller advances the page state and refreshes page_map etc. before the step */
 } mtx_model_config;
 
 /* Weights, repacked once at load time for K-major streaming (see DESIGN.md "Data layout").
@@ -161,6 +165,10 @@ typedef struct {
   int32_t* page_lengths;    /* [num_slots] sequence_lengths (this step's token included) */
   int32_t* active_page;     /* [num_slots] */
   int32_t* active_page_pos; /* [num_slots] active_page_position */
+  /* paged_device_state = 1 only: the rest of PageState, updated in place by the step */
+  int32_t* page_status;     /* [num_pages] */
+  int32_t* num_pages_used;  /* [num_slots] */
+  int32_t* has_active_page; /* [num_slots] 0 / 1 */
 } mtx_decode_state;
 
 /* ---- engine ---------------------------------------------------------------------------- */
@@ -301,6 +309,13 @@ size_t mtx_paged_attention_scratch_bytes(int rows, int num_kv_heads, int num_q_h
 int mtx_paged_attention(const void* q, const void* k_pages, const void* v_pages, const int32_t* lengths, const int32_t* page_map,
                         void* out, int rows, int num_q_heads, int num_kv_heads, int head_dim, int num_pages, int tokens_per_page,
                         int max_pages_per_group, float softcap, void* scratch, mtx_stream stream);
+/* PageManager.update_decode_pages (page_manager.py:538-563, `_update_decode_pages_global` :332-412) on device arrays, in place: one more
+ * token for every active group, a new page (the lowest free index >= 1, in group order, while free pages last) for the groups that
+ * crossed a page boundary.  All arrays int32 (has_active_page 0 / 1); groups <= 256. */
+int mtx_page_update_decode(int32_t* page_status, int32_t* page_map, int32_t* num_pages_used, int32_t* sequence_lengths, int32_t* active_page,
+                           const int32_t* has_active_page, int32_t* active_page_position, int num_pages, int groups, int max_pages_per_group,
+                           int tokens_per_page, mtx_stream stream);
+
 /* MaxEngine._insert_jit's `_copy_paged` (maxengine.py:1104-1131): the first n_tokens rows of a prefix (k_src / v_src
  * [layers, Hkv, n_src_rows, D], i.e. the prefix's pages read as rows) into the pool pages page_map_row[i] (device, the group's row
  * of PageState.page_map); pools [layers, Hkv, num_pages, tokens_per_page, D]. */

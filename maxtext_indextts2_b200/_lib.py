@@ -63,6 +63,7 @@ class ModelConfig(ctypes.Structure):
       ("paged_num_pages", ctypes.c_int32),
       ("paged_tokens_per_page", ctypes.c_int32),
       ("paged_max_pages_per_group", ctypes.c_int32),
+      ("paged_device_state", ctypes.c_int32),
   ]
 
 
@@ -100,6 +101,9 @@ class DecodeState(ctypes.Structure):
           "page_lengths",
           "active_page",
           "active_page_pos",
+          "page_status",
+          "num_pages_used",
+          "has_active_page",
       )
   ]
 
@@ -219,6 +223,8 @@ def _declare(lib) -> None:
   lib.mtx_paged_attention_scratch_bytes.argtypes = [i32] * 5
   lib.mtx_paged_attention.restype = i32
   lib.mtx_paged_attention.argtypes = [vp] * 6 + [i32] * 7 + [f32, vp, vp]
+  lib.mtx_page_update_decode.restype = i32
+  lib.mtx_page_update_decode.argtypes = [vp] * 7 + [i32] * 4 + [vp]
   lib.mtx_paged_insert.restype = i32
   lib.mtx_paged_insert.argtypes = [vp] * 5 + [i32] * 7 + [vp]
   lib.mtx_jax_ffi_available.restype = i32

@@ -893,6 +893,20 @@ int enqueue_step(mtx_engine* e, int mode, int rows, const int32_t* chunk_tokens,
   pa.active_page = e->s.active_page;
   pa.active_pos = e->s.active_page_pos;
   pa.tokens_per_page = c.paged_tokens_per_page;
+  if (is_paged(c) && c.paged_device_state && mode == 0) {  // update_decode_pages at the head of the step (maxengine.py:847-849)
+    pa.page_update = 1;
+    pa.page_state.page_status = e->s.page_status;
+    pa.page_state.page_map = e->s.page_map;
+    pa.page_state.num_pages_used = e->s.num_pages_used;
+    pa.page_state.sequence_lengths = e->s.page_lengths;
+    pa.page_state.active_page = e->s.active_page;
+    pa.page_state.has_active_page = e->s.has_active_page;
+    pa.page_state.active_page_position = e->s.active_page_pos;
+    pa.page_state.num_pages = c.paged_num_pages;
+    pa.page_state.groups = c.num_slots;
+    pa.page_state.max_pages_per_group = c.paged_max_pages_per_group;
+    pa.page_state.tokens_per_page = c.paged_tokens_per_page;
+  }
   pa.rope_timescale_w = e->rope_timescale_w;
   if (mega) {
     pa.grid_bar = e->grid_bar;
@@ -1592,6 +1606,8 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
   } else if (is_paged(c)) {
     if (!s->k_pages || !s->v_pages || !s->page_map || !s->page_lengths || !s->active_page || !s->active_page_pos)
       return fail(MTX_ERR_ARG, "attention=paged: k_pages / v_pages / page_map / page_lengths / active_page / active_page_pos must be set");
+    if (c.paged_device_state && (!s->page_status || !s->num_pages_used || !s->has_active_page))
+      return fail(MTX_ERR_ARG, "paged_device_state: page_status / num_pages_used / has_active_page must be set");
     const uint64_t stage_rows = uint64_t(L_) * c.num_kv_heads * c.max_target_len;  // one bf16 plane per layer
     MTX_TRY(make_map(&e->tm_k, s->k_cache, c.head_dim, stage_rows, kAttnTileRows));
     MTX_TRY(make_map(&e->tm_v, s->v_cache, c.head_dim, stage_rows, kAttnTileRows));
@@ -2276,6 +2292,27 @@ int mtx_paged_attention(const void* q, const void* k_pages, const void* v_pages,
   }
   MTX_CUDA(cudaFuncSetAttribute(decode_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   return launch(decode_attn_kernel<128>, dim3(grid), dim3(kAttnThreads), smem, st, tk, tv, p);
+}
+
+int mtx_page_update_decode(int32_t* page_status, int32_t* page_map, int32_t* num_pages_used, int32_t* sequence_lengths, int32_t* active_page,
+                           const int32_t* has_active_page, int32_t* active_page_position, int num_pages, int groups, int max_pages_per_group,
+                           int tokens_per_page, mtx_stream stream) {
+  if (!page_status || !page_map || !num_pages_used || !sequence_lengths || !active_page || !has_active_page || !active_page_position)
+    return fail(MTX_ERR_ARG, "null argument");
+  if (groups < 1 || groups > 256 || num_pages < 2 || max_pages_per_group < 1 || tokens_per_page < 1) return fail(MTX_ERR_ARG, "bad page state shape");
+  PageStateDev a;
+  a.page_status = page_status;
+  a.page_map = page_map;
+  a.num_pages_used = num_pages_used;
+  a.sequence_lengths = sequence_lengths;
+  a.active_page = active_page;
+  a.has_active_page = has_active_page;
+  a.active_page_position = active_page_position;
+  a.num_pages = num_pages;
+  a.groups = groups;
+  a.max_pages_per_group = max_pages_per_group;
+  a.tokens_per_page = tokens_per_page;
+  return launch(page_update_decode_kernel, dim3(1), dim3(256), 0, static_cast<cudaStream_t>(stream), a);
 }
 
 int mtx_paged_insert(void* k_pages, void* v_pages, const void* k_src, const void* v_src, const int32_t* page_map_row, int layers,

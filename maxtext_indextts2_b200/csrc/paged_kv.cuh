@@ -68,4 +68,80 @@ __global__ void paged_insert_kernel(const PagedInsertArgs a) {
   }
 }
 
+// PageManager.update_decode_pages on the device (page_manager.py:332-412 `_update_decode_pages_global`; the reference runs it as a
+// jitted function on device arrays too): every active group gets one more token; the groups that crossed a page boundary get, in
+// group order, the lowest free pages (index >= 1) while free pages last.  ONE CTA of 256 threads, all of them calling; at most
+// 256 groups.  The arrays are PageState's (has_active_page as int32 0 / 1) and are updated in place.
+struct PageStateDev {
+  int* page_status;           // [num_pages]
+  int* page_map;              // [groups, max_pages_per_group]
+  int* num_pages_used;        // [groups]
+  int* sequence_lengths;      // [groups]
+  int* active_page;           // [groups]
+  const int* has_active_page; // [groups]
+  int* active_page_position;  // [groups]
+  int num_pages, groups, max_pages_per_group, tokens_per_page;
+};
+
+__device__ __forceinline__ int page_block_exclusive_scan(int v, int* s_warp, int& total) {
+  // exclusive prefix sum over the 256 threads of the CTA (8 warps); s_warp: 9 ints of shared memory
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // (s_warp may still be read from a previous scan)
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < warp; ++w) base += s_warp[w];
+  total = 0;
+  for (int w = 0; w < 8; ++w) total += s_warp[w];
+  return base + inc - v;
+}
+
+__device__ __forceinline__ void page_update_decode(const PageStateDev& a, int* s_warp, int* s_free) {
+  const int g = threadIdx.x;
+  const int tpp = a.tokens_per_page;
+  bool need = false;
+  int used = 0;
+  if (g < a.groups) {
+    const int active = a.has_active_page[g] != 0 ? 1 : 0;
+    const int len = a.sequence_lengths[g] + active;
+    used = a.num_pages_used[g];
+    const int required = (len + tpp - 1) / tpp;
+    need = active && required > used && required <= a.max_pages_per_group;
+    a.sequence_lengths[g] = len;
+    if (active) a.active_page_position[g] = (len - 1) % tpp;
+  }
+  int n_need;
+  const int rank = page_block_exclusive_scan(need ? 1 : 0, s_warp, n_need);
+  if (n_need == 0) return;  // (uniform: every thread holds the same total)
+  // the first n_need free pages, ascending: every thread owns a contiguous run of pages [lo, hi) of [1, num_pages)
+  const int per = (a.num_pages - 1 + 255) / 256;
+  const int lo = 1 + threadIdx.x * per, hi = min(a.num_pages, lo + per);
+  int n_free = 0;
+  for (int pg = lo; pg < hi; ++pg) n_free += a.page_status[pg] == 0 ? 1 : 0;
+  int total_free;
+  int k = page_block_exclusive_scan(n_free, s_warp, total_free);
+  for (int pg = lo; pg < hi && k < n_need; ++pg)
+    if (a.page_status[pg] == 0) s_free[k++] = pg;
+  __syncthreads();
+  if (need && rank < total_free) {  // later groups find no free page and keep their state
+    const int pg = s_free[rank];
+    a.page_status[pg] = 1;
+    a.page_map[(long long)g * a.max_pages_per_group + used] = pg;
+    a.num_pages_used[g] = used + 1;
+    a.active_page[g] = pg;
+  }
+}
+
+__global__ void __launch_bounds__(256) page_update_decode_kernel(const PageStateDev a) {
+  __shared__ int s_warp[9];
+  __shared__ int s_free[256];
+  page_update_decode(a, s_warp, s_free);
+}
+
 }  // namespace mtx

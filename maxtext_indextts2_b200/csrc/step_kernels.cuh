@@ -4,6 +4,7 @@
 
 #include "attention.cuh"
 #include "common.cuh"
+#include "paged_kv.cuh"
 
 namespace mtx {
 
@@ -57,6 +58,9 @@ struct PrepareArgs {
   const int* active_page;
   const int* active_pos;
   int tokens_per_page;
+  // paged_device_state: the step itself runs PageManager.update_decode_pages first (paged_kv.cuh), on these arrays
+  int page_update;
+  PageStateDev page_state;
   // persistent step kernel (step_persistent.cuh): counters reset here, attention tile partition
   unsigned int* grid_bar;  // grid-barrier arrival counter
   int* tile_prefix;        // [rows + 1] exclusive prefix of the per-row 64-row tile counts
@@ -80,6 +84,11 @@ __global__ void prepare_rows_kernel(const PrepareArgs a, const RowDesc rd) {
   const int tid = threadIdx.x;
   const int R = a.T - a.P;
   int chunks = 0, chunks_w = 0;
+  if (a.page_update) {  // (uniform)
+    __shared__ int s_free[256];
+    page_update_decode(a.page_state, s_off, s_free);  // (s_off: scratch until the work list below)
+    __syncthreads();
+  }
   if (tid < a.rows) {
     int token, pos, plane, wr, l0, rf, rl;
     if (a.mode == 0) {

@@ -267,7 +267,10 @@ class MaxEngine:
     # attention=paged (maxengine.py:131-136): the decode cache is the page pools, one page group per slot; prefill writes a
     # bf16 staging plane (index 0) like the int8 engine's
     self._paged = config.attention == "paged"
-    self.page_manager, self.page_state = None, None
+    self.page_manager, self._page_state, self._page_host_stale = None, None, False
+    # pagedattn_device_state (a key of this implementation): the PageState lives on the device and every decode step begins with
+    # update_decode_pages there (as the reference's jitted update does); the host copy is refreshed when somebody looks
+    self._page_on_device = self._paged and bool(config.pagedattn_device_state)
     if self._paged:
       self._staging, self._num_slots = 0, B
       self.page_manager = page_manager.PageManager(config)
@@ -321,6 +324,7 @@ class MaxEngine:
         paged_num_pages=int(config.pagedattn_num_pages) if self._paged else 0,
         paged_tokens_per_page=int(config.pagedattn_tokens_per_page) if self._paged else 0,
         paged_max_pages_per_group=int(config.pagedattn_max_pages_per_group) if self._paged else 0,
+        paged_device_state=1 if self._page_on_device else 0,
     )
     _lib.check(self.lib.mtx_engine_create(ctypes.byref(self._cfg_struct), ctypes.byref(self._handle)))
     ws = self.lib.mtx_engine_workspace_bytes(self._handle)
@@ -382,13 +386,14 @@ class MaxEngine:
       self._staging = 0
     elif self._paged:
       # PagedAttentionOp.key_pages / value_pages (paged_attention.py:152-160), all layers in one pool, + the device copy of the
-      # PageState fields a step reads: [sequence_lengths | active_page | active_page_position | page_map] in one int32 buffer
+      # PageState in one int32 buffer: [sequence_lengths | active_page | active_page_position | num_pages_used | has_active_page |
+      # page_map | page_status] (the step reads the first three and the map; with pagedattn_device_state it updates all of it)
       self._kq = self._vq = self._k_scale = self._v_scale = None
       NP, TPP, MP = int(cfg.pagedattn_num_pages), int(cfg.pagedattn_tokens_per_page), int(cfg.pagedattn_max_pages_per_group)
       self._k_pages = z(L, Hkv, NP, TPP, D, dtype=torch.bfloat16)
       self._v_pages = z(L, Hkv, NP, TPP, D, dtype=torch.bfloat16)
-      self._page_dev = z(3 * B + B * MP)
-      self._page_dev_small, self._page_dev_map = self._page_dev[: 3 * B], self._page_dev[3 * B :]
+      self._page_dev = z(5 * B + B * MP + NP)
+      self._page_dev_small, self._page_dev_map = self._page_dev[: 3 * B], self._page_dev[5 * B : 5 * B + B * MP]
       self._uploaded_map = None
       self._k = z(L, 1, Hkv, T, D, dtype=torch.bfloat16)
       self._v = z(L, 1, Hkv, T, D, dtype=torch.bfloat16)
@@ -437,21 +442,50 @@ class MaxEngine:
       self._state_struct.page_lengths = base
       self._state_struct.active_page = base + 4 * B
       self._state_struct.active_page_pos = base + 8 * B
-      self._state_struct.page_map = base + 12 * B
+      self._state_struct.num_pages_used = base + 12 * B
+      self._state_struct.has_active_page = base + 16 * B
+      self._state_struct.page_map = base + 20 * B
+      self._state_struct.page_status = base + 4 * (5 * B + B * MP)
 
   def _upload_page_state(self) -> None:
     """The PageState fields a step reads, host -> device (the reference passes page_state into the jitted step,
     maxengine.py:856-864).  The source is pageable memory, so the copy has left the host buffer when the call returns."""
     ps = self.page_state
+    if self._page_on_device:  # the whole state (request boundaries only: prefill, insert, release)
+      packed = np.concatenate((ps.sequence_lengths, ps.active_page, ps.active_page_position, ps.num_pages_used,
+                               ps.has_active_page.astype(np.int32), ps.page_map.reshape(-1), ps.page_status))
+      self._page_dev.copy_(torch.from_numpy(packed))
+      return
     small = np.concatenate((ps.sequence_lengths, ps.active_page, ps.active_page_position))
     self._page_dev_small.copy_(torch.from_numpy(small))
     if ps.page_map is not self._uploaded_map:  # (the page manager returns the same array while no page was handed out)
       self._page_dev_map.copy_(torch.from_numpy(ps.page_map.reshape(-1)))
       self._uploaded_map = ps.page_map
 
+  @property
+  def page_state(self):
+    """maxengine.py:133-136 `self.page_state`.  With the state on the device this reads it back (a stream synchronisation) if
+    decode steps have run since the host copy was made."""
+    if self._page_host_stale:
+      B, MP, NP = self.max_concurrent_decodes, self.page_manager.max_pages_per_group, self.page_manager.num_pages
+      flat = self._page_dev.cpu().numpy()
+      f = lambda i: flat[i * B : (i + 1) * B].copy()
+      self._page_state = page_manager.PageState(
+          page_status=flat[5 * B + B * MP :].copy(), page_map=flat[5 * B : 5 * B + B * MP].reshape(B, MP).copy(), num_pages_used=f(3),
+          sequence_lengths=f(0), active_page=f(1), has_active_page=f(4).astype(bool), active_page_position=f(2))
+      self._page_host_stale = False
+    return self._page_state
+
+  @page_state.setter
+  def page_state(self, value) -> None:
+    self._page_state, self._page_host_stale = value, False
+
   def _advance_pages(self) -> None:
-    """maxengine.py:847-849: the page state advances outside the step (one more token per active group, a new page for the
-    groups that crossed a boundary), then the step reads it."""
+    """maxengine.py:847-849: the page state advances before the step reads it (one more token per active group, a new page for
+    the groups that crossed a boundary): on the device, in the step's first kernel, or here on the host followed by an upload."""
+    if self._page_on_device:
+      self._page_host_stale = True
+      return
     self.page_state = self.page_manager.update_decode_pages(self.page_state)
     self._upload_page_state()
 
@@ -460,6 +494,8 @@ class MaxEngine:
     if not self._paged:
       return
     self.page_state = self.page_manager.release_pages(page_state=self.page_state, page_group_id=int(slot))
+    if self._page_on_device:
+      self._upload_page_state()
 
   def _apply_sampling(self) -> None:
     cfg = self.config
@@ -596,6 +632,8 @@ class MaxEngine:
         raise ValueError("attention=paged: prefill needs the slot (page group) the sequence will be inserted into")
       self.page_state = self.page_manager.update_prefill_pages(page_state=self.page_state, page_group_id=int(slot),
                                                                true_length=start_position + true_length)
+      if self._page_on_device:
+        self._upload_page_state()
     toks = torch.as_tensor(padded_tokens).reshape(-1)
     if true_length < 1 or true_length > toks.numel() or start_position + toks.numel() > cfg.max_prefill_predict_length:
       raise ValueError(f"true_length={true_length}, {toks.numel()} padded tokens after {start_position} prefix tokens, "

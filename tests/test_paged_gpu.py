@@ -152,17 +152,55 @@ def test_paged_append_and_insert_match_oracle():
   assert torch.equal(kd.cpu(), want_k) and torch.equal(vd.cpu(), want_v)
 
 
+@pytest.mark.parametrize("seed,num_pages,groups", [(0, 128, 4), (1, 24, 4), (2, 12, 4), (3, 300, 64), (4, 40, 256)])
+def test_device_page_update_matches_the_host_page_manager(seed, num_pages, groups):
+  """mtx_page_update_decode (PageManager.update_decode_pages in one CTA) against the host page manager on random prefill / decode /
+  release sequences, with pools small enough to run dry: every PageState field equal after every decode update.  Prefill and
+  release stay host operations (request boundaries); their result is uploaded."""
+  from maxtext_indextts2_b200 import page_manager as pm_lib
+  from maxtext_indextts2_b200 import pyconfig
+
+  lib = _lib.load()
+  tpp, t = 8, 64
+  max_pages = t // tpp
+  pm = pm_lib.PageManager(pyconfig.initialize(None, per_device_batch_size=groups, max_prefill_predict_length=32, max_target_length=t,
+                                              pagedattn_num_pages=num_pages, pagedattn_tokens_per_page=tpp, pagedattn_max_pages_per_group=max_pages))
+  rng = np.random.default_rng(seed)
+  state = pm.get_initial_page_state()
+  fields = ("page_status", "page_map", "num_pages_used", "sequence_lengths", "active_page", "has_active_page", "active_page_position")
+
+  def upload(st):
+    return {f: torch.from_numpy(np.ascontiguousarray(getattr(st, f)).astype(np.int32)).cuda() for f in fields}
+
+  dev = upload(state)
+  for step in range(300):
+    op = rng.integers(0, 10)
+    if op < 2:
+      state = pm.update_prefill_pages(state, int(rng.integers(0, groups)), int(rng.integers(1, 33)))
+      dev = upload(state)
+    elif op < 3:
+      state = pm.release_pages(state, int(rng.integers(0, groups)))
+      dev = upload(state)
+    else:
+      state = pm.update_decode_pages(state)
+      _lib.check(lib.mtx_page_update_decode(*[_ptr(dev[f]) for f in fields], num_pages, groups, max_pages, tpp, _stream()))
+      torch.cuda.synchronize()
+      for f in fields:
+        assert np.array_equal(dev[f].cpu().numpy(), np.asarray(getattr(state, f)).astype(np.int32)), (step, f)
+
+
 def _paged_config(**kw):
   base = dict(attention="paged", pagedattn_tokens_per_page=8, pagedattn_num_pages=40, materialize_logits=True)
   base.update(kw)
   return small_config(**base)
 
 
-@pytest.mark.parametrize("use_graph,tpp", [(False, 8), (True, 16), (True, 64)])
-def test_paged_engine_matches_dense_oracle(use_graph, tpp):
+@pytest.mark.parametrize("use_graph,tpp,device_state", [(False, 8, True), (True, 16, False), (True, 64, True), (True, 32, False)])
+def test_paged_engine_matches_dense_oracle(use_graph, tpp, device_state):
   """Prefill + insert + 24 lock-step greedy steps for three sequences (their pages interleave in the pool and every sequence
   crosses page boundaries), then one slot is released and refilled with a new prompt that reuses the freed pages."""
-  cfg = _paged_config(per_device_batch_size=3, max_prefill_predict_length=16, max_target_length=64, pagedattn_tokens_per_page=tpp)
+  cfg = _paged_config(per_device_batch_size=3, max_prefill_predict_length=16, max_target_length=64, pagedattn_tokens_per_page=tpp,
+                      pagedattn_device_state=device_state)
   dense = small_config(per_device_batch_size=3, max_prefill_predict_length=16, max_target_length=64, materialize_logits=True)
   params = make_params(cfg)
   oracle = ref.DecodeOracle(dense, params, faithful=True)
