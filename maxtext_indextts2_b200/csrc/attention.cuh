@@ -1020,7 +1020,7 @@ __device__ __forceinline__ void attn_process_items_q8(const CUtensorMap& tm_k, c
 
 
 template <bool F8, bool TR>
-__global__ void __launch_bounds__(kAttnThreads)
+__global__ void __launch_bounds__(kAttnThreads, TR ? 4 : 3)  // (transposed form: 128 registers, four CTAs = 16 warps per SM; else 168, three)
 decode_attn_q8_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const AttnParams p, const float* k_scale,
                       const float* v_scale) {
   constexpr int D = 64;

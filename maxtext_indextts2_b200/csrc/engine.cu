@@ -1603,6 +1603,9 @@ int mtx_engine_bind(mtx_engine* e, const mtx_weights* w, const mtx_decode_state*
     MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_q8_smem_bytes(16))));
     MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_q8_smem_bytes(16))));
     MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(attn_q8_smem_bytes(16))));
+    // four CTAs of 46 KB per SM need the large shared-memory carve-out
+    MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    MTX_CUDA(cudaFuncSetAttribute(decode_attn_q8_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   } else if (is_paged(c)) {
     if (!s->k_pages || !s->v_pages || !s->page_map || !s->page_lengths || !s->active_page || !s->active_page_pos)
       return fail(MTX_ERR_ARG, "attention=paged: k_pages / v_pages / page_map / page_lengths / active_page / active_page_pos must be set");
