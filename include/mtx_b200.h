@@ -157,8 +157,9 @@ typedef struct {
   float* v_scale;
   /* attention=paged only (else NULL): the page pools [L, Hkv, num_pages, tokens_per_page, D] bf16 (PagedAttentionOp.key_pages /
    * value_pages, paged_attention.py:152-160, one pool for all layers) and the device copy of the PageState fields a step reads
-   * (page_manager.py:49-91), one page group per decode slot: the caller runs PageManager.update_decode_pages BEFORE the step
-   * (maxengine.py:847-849) and refreshes these arrays. */
+   * (page_manager.py:49-91), one page group per decode slot.  paged_device_state = 0: the caller runs
+   * PageManager.update_decode_pages BEFORE the step (maxengine.py:847-849) and refreshes these arrays; = 1: the step does it
+   * itself on the full state (the three arrays at the end of this struct included). */
   void* k_pages;
   void* v_pages;
   int32_t* page_map;        /* [num_slots, max_pages_per_group] */
