@@ -128,3 +128,35 @@ def test_int8_decode_on_a_synthetic_cache_against_the_oracle(batch, axis):
     assert (last.abs().amax(dim=(-2, -1)) >= 127).all()
     sc = state["cache"]["key_scale"][:, slots[0], :, P + idx - 1].cpu()
     assert (sc == sc[:, :1]).all() and (sc > 0).all()
+
+
+@pytest.mark.parametrize("hq,hkv", [(8, 1), (4, 4), (6, 2)])
+@pytest.mark.parametrize("fp8", [False, True])
+def test_quantised_persistent_kernel_head_groupings(hq, hkv, fp8):
+  """step_persistent_kernel<1 / 2> (quantising QKV epilogue, transposed fp16 attention over byte tiles) with 8, 1 and 3 query heads
+  per kv head, ragged contexts that wrap the ring, against the oracle with the same quantiser."""
+  cfg = pyconfig.initialize(
+      None, base_num_decoder_layers=2, base_emb_dim=256, base_num_query_heads=hq, base_num_kv_heads=hkv, head_dim=64, base_mlp_dim=512,
+      vocab_size=3000, per_device_batch_size=24, max_prefill_predict_length=128, max_target_length=256, weight_dtype="bfloat16",
+      attention="dot_product", scan_layers=False, materialize_logits=True, quantize_kvcache=True, kv_quant_axis="dkv",
+      kv_quant_dtype="fp8" if fp8 else "int8")
+  rng = np.random.Generator(np.random.PCG64(hq * 10 + hkv))
+  pl = rng.integers(1, 129, size=24)
+  al = rng.integers(0, 127, size=24)
+  al[pl < 128] = 0
+  pl[0], al[0] = 128, 126
+  engine = maxengine.MaxEngine(cfg, use_cuda_graph=False)  # (launches are counted when they are enqueued, not when a graph replays)
+  dparams = engine.load_params(make_params(cfg))
+  state = engine.fill_synthetic_context(pl, al, seed=9)
+  slots = [0, 7, 23]
+  weights = mirror.oracle_weights_from_device(dparams, cfg)
+  oracle = mirror.make_oracle(cfg, weights, len(slots), faithful=True)
+  ostate = mirror.mirror_state(engine, oracle, slots)
+  sl = torch.as_tensor(slots)
+  for step in range(4):
+    n0 = engine.lib.mtx_launch_count()
+    state, result = engine.generate(dparams, state)
+    assert int(engine.lib.mtx_launch_count() - n0) == 3
+    ostate, odata = oracle.generate(ostate)
+    torch.testing.assert_close(state["logits"].cpu()[sl], ostate["logits"], rtol=1e-1, atol=1e-1)
+    state["tokens"][sl.to(state["tokens"].device)] = odata[:, :1].to(state["tokens"].device)

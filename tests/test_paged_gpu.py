@@ -316,3 +316,38 @@ def test_offline_engine_over_pages_matches_dense_slots():
   # completion; the oracle comparison above is the parity test, this one checks the scheduling
   assert agree >= len(prompts) - 1, f"{agree} of {len(prompts)} completions identical"
   assert all(len(o.token_ids) == 20 for o in outs[1])
+
+
+def test_paged_engine_more_than_64_slots_and_a_full_group():
+  """80 page groups (steps of 65..256 rows take the per-kernel path: row-major GEMMs, decode_attn_kernel over pages) against the
+  dense-cache oracle on a slot subset (rows gathered through the page map); one group is one token short of max_target_length
+  and fills its last page during the run."""
+  from maxtext_indextts2_b200 import pyconfig
+  from oracle import mirror
+
+  kw = dict(base_num_decoder_layers=2, base_emb_dim=256, base_num_query_heads=8, base_num_kv_heads=2, head_dim=64, base_mlp_dim=512,
+            vocab_size=2048, per_device_batch_size=80, max_prefill_predict_length=64, max_target_length=160, weight_dtype="bfloat16",
+            scan_layers=False, materialize_logits=True)
+  cfg = pyconfig.initialize(None, attention="paged", pagedattn_tokens_per_page=16, pagedattn_num_pages=80 * 10 + 1, **kw)
+  engine = maxengine.MaxEngine(cfg, use_cuda_graph=False)
+  dparams = engine.load_params(make_params(cfg))
+  rng = np.random.default_rng(8)
+  total = rng.integers(1, 150, size=80)
+  total[5] = 157  # reaches 160 = max_target_length at the third step
+  prefill, ar = np.minimum(total, 64), total - np.minimum(total, 64)
+  state = engine.fill_synthetic_context(prefill, ar, seed=5)
+  slots = [0, 5, 17, 40, 64, 79]
+  weights = mirror.oracle_weights_from_device(dparams, cfg)
+  oracle = mirror.make_oracle(cfg, weights, len(slots), faithful=True)
+  ostate = mirror.mirror_state(engine, oracle, slots)
+  sl = torch.as_tensor(slots)
+  for step in range(3):
+    n0 = engine.lib.mtx_launch_count()
+    state, result = engine.generate(dparams, state)
+    assert int(engine.lib.mtx_launch_count() - n0) > 3  # not the persistent kernel
+    ostate, odata = oracle.generate(ostate)
+    torch.testing.assert_close(state["logits"].cpu()[sl], ostate["logits"], rtol=1e-1, atol=1e-1)
+    state["tokens"][sl.to(state["tokens"].device)] = odata[:, :1].to(state["tokens"].device)
+  ps = engine.page_state
+  assert ps.sequence_lengths.tolist() == (total + 3).tolist()
+  assert int(ps.num_pages_used[5]) == 10 and int(ps.active_page_position[5]) == 15
