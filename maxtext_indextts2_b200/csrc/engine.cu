@@ -2394,13 +2394,15 @@ int mtx_engine_rebind_state(mtx_engine* e, const mtx_decode_state* s) {
   if (!e || !e->bound || !s) return fail(MTX_ERR_ARG, "engine is not bound / null state");
   if (memcmp(&e->s, s, sizeof(*s)) == 0) return MTX_OK;
   const mtx_model_config& c = e->cfg;
+  // (checked before anything is changed: a quantised or paged engine has more tensor maps than the two rebuilt below)
+  if (c.kv_quant) return fail(MTX_ERR_UNSUPPORTED, "mtx_engine_rebind_state with an int8 KV cache: bind again instead");
+  if (is_paged(c)) return fail(MTX_ERR_UNSUPPORTED, "mtx_engine_rebind_state with a paged KV cache: bind again instead");
   const bool kv_moved = e->s.k_cache != s->k_cache || e->s.v_cache != s->v_cache;
   e->s = *s;
   for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
   e->graphs.clear();
   for (auto& kv : e->host_graphs) cudaGraphExecDestroy(kv.second);
   e->host_graphs.clear();
-  if (c.kv_quant) return fail(MTX_ERR_UNSUPPORTED, "mtx_engine_rebind_state with an int8 KV cache: bind again instead");
   if (kv_moved) {
     const uint64_t kv_rows = uint64_t(c.num_layers) * c.num_slots * c.num_kv_heads * c.max_target_len;
     MTX_TRY(make_map(&e->tm_k, s->k_cache, c.head_dim, kv_rows, kAttnTileRows));
