@@ -443,3 +443,42 @@ def test_chunked_prefill_with_existing_prefix_matches_one_call():
     plain = maxengine.MaxEngine(small_config())
     plain.prefill(params=plain.load_params(make_params(small_config())), padded_tokens=toks[:4], true_length=4,
                   existing_prefix=maxengine.ExistingPrefix(cache=prefix["cache"], common_prefix_tokens=toks[:4]))
+
+
+def test_rebind_state_follows_moved_buffers():
+  """mtx_engine_rebind_state (what an XLA FFI handler calls when its operand buffers moved): a no-op for the same buffers; after
+  the KV cache has moved to new allocations the next steps continue bit-identically; quantised / paged engines refuse."""
+  import ctypes
+
+  from maxtext_indextts2_b200 import _lib
+
+  cfg = small_config(per_device_batch_size=2, materialize_logits=True)
+  params = make_params(cfg)
+  prompts = random_tokens((2, 16), cfg.vocab_size, seed=4)
+
+  def run(move):
+    engine = maxengine.MaxEngine(cfg, use_cuda_graph=False)
+    dparams = engine.load_params(params)
+    state = engine.init_decode_state()
+    for slot, n in enumerate((9, 16)):
+      prefix, _ = engine.prefill(params=dparams, padded_tokens=prompts[slot], true_length=n)
+      state = engine.insert(prefix, state, slot)
+    out = []
+    for step in range(6):
+      if step == 3:
+        _lib.check(engine.lib.mtx_engine_rebind_state(engine._handle, ctypes.byref(engine._state_struct)))  # nothing moved
+        if move:
+          engine._k, engine._v = engine._k.clone(), engine._v.clone()
+          engine._state_struct.k_cache, engine._state_struct.v_cache = engine._k.data_ptr(), engine._v.data_ptr()
+          _lib.check(engine.lib.mtx_engine_rebind_state(engine._handle, ctypes.byref(engine._state_struct)))
+      state, result = engine.generate(dparams, state)
+      out.append((result.data.cpu().clone(), state["logits"].cpu().clone()))
+    return out
+
+  for (d0, l0), (d1, l1) in zip(run(False), run(True)):
+    assert torch.equal(d0, d1) and torch.equal(l0, l1)
+  quant = maxengine.MaxEngine(small_config(quantize_kvcache=True, kv_quant_axis="dkv"))
+  quant.load_params(make_params(cfg))
+  assert quant.lib.mtx_engine_rebind_state(quant._handle, ctypes.byref(quant._state_struct)) == 0  # unchanged: still a no-op
+  quant._state_struct.tokens = quant._next_pos.data_ptr()
+  assert quant.lib.mtx_engine_rebind_state(quant._handle, ctypes.byref(quant._state_struct)) == _lib.MTX_ERR_UNSUPPORTED
