@@ -195,7 +195,7 @@ def _paged_config(**kw):
   return small_config(**base)
 
 
-@pytest.mark.parametrize("use_graph,tpp,device_state", [(False, 8, True), (True, 16, False), (True, 64, True), (True, 32, False)])
+@pytest.mark.parametrize("use_graph,tpp,device_state", [(False, 8, True), (True, 16, False), (True, 64, True), (True, 32, False), (True, 128, True)])
 def test_paged_engine_matches_dense_oracle(use_graph, tpp, device_state):
   """Prefill + insert + 24 lock-step greedy steps for three sequences (their pages interleave in the pool and every sequence
   crosses page boundaries), then one slot is released and refilled with a new prompt that reuses the freed pages."""
