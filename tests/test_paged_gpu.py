@@ -253,11 +253,13 @@ def test_paged_engine_matches_dense_oracle(use_graph, tpp, device_state):
   assert near <= 3, f"{near} near-ties in 96 tokens"
 
 
-def test_paged_engine_head_grouping_of_the_model():
-  """G = 5 (20 query heads over 4 kv heads, the IndexTTS2-scale grouping), 32-token pages, 6 slots of ragged prompts."""
+@pytest.mark.parametrize("tpp", [32, 128])
+def test_paged_engine_head_grouping_of_the_model(tpp):
+  """G = 5 (20 query heads over 4 kv heads, the IndexTTS2-scale grouping), 32- / 128-token pages (two whole pages, or half a page,
+  per 64-row tile of the persistent kernel), 6 slots of ragged prompts; sequences cross page boundaries during the run."""
   kw = dict(base_num_query_heads=20, base_num_kv_heads=4, base_emb_dim=256, per_device_batch_size=6, max_prefill_predict_length=64,
             max_target_length=160, materialize_logits=True)
-  cfg = _paged_config(pagedattn_tokens_per_page=32, pagedattn_num_pages=64, **kw)
+  cfg = _paged_config(pagedattn_tokens_per_page=tpp, pagedattn_num_pages=64, **kw)
   dense = small_config(**kw)
   params = make_params(cfg)
   oracle = ref.DecodeOracle(dense, params, faithful=True)
