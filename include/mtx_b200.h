@@ -268,6 +268,20 @@ int mtx_rmsnorm(const void* x, const void* scale, void* out, int rows, int emb_d
  * weight tile; the partial tiles are reduced over distributed shared memory. */
 int mtx_linear(const void* x, const void* w, void* out, int rows, int n, int k, int splits, mtx_stream stream);
 
+/* The two remaining fused blocks of a decoder layer as single ops, on the GEMM kernels of the per-kernel path.  `rows`
+ * 1..256; activation inputs must be allocated with the rows rounded up to 16/32/64/128/256, as for mtx_linear.
+ *
+ * Attention.out + the residual add (attentions.py:2017-2030 `out_projection`, llama2.py:139-140):
+ *   out[rows, E] = bf16(x + bf16(attn[rows, Hq*D] . wo[E, Hq*D]^T)), wo = mtx_weights.wo of one layer.  x and out may alias. */
+int mtx_outproj_residual(const void* attn, const void* wo, const void* x, void* out, int rows, int emb_dim, int q_dim, mtx_stream stream);
+/* MlpBlock with its pre-norm + the residual add (linears.py:425-476, llama2.py:150-163):
+ *   n = RMSNorm(h) * norm_scale;  out[rows, E] = bf16(h + bf16(bf16(silu(n . w0) * (n . w1)) . wout^T)),
+ *   w01 [2M, E] = mtx_weights.w01 of one layer (wi_0 / wi_1 rows interleaved in groups of 16), wout [E, M].
+ * scratch: mtx_mlp_scratch_bytes(); h must be padded like an activation input (it is read as n's source only up to `rows`). */
+size_t mtx_mlp_scratch_bytes(int rows, int emb_dim, int mlp_dim);
+int mtx_mlp(const void* h, const void* norm_scale, const void* w01, const void* wout, void* out, int rows, int emb_dim, int mlp_dim, float eps,
+            void* scratch, mtx_stream stream);
+
 /* GQA decode attention over the valid rows of both cache segments: AttentionOp.__call__ in
  * autoregressive mode (attentions.py:1399-1466: two apply_attention_dot calls merged by
  * normalize_attention).  q,out [rows, Hq*D] bf16; k_cache/v_cache one layer [num_slots,Hkv,T,D];
@@ -345,7 +359,8 @@ int mtx_engine_rebind_state(mtx_engine* e, const mtx_decode_state* s);
 size_t mtx_step_trace_words(const mtx_engine* e); /* sized for the engine's grid and layer count (NULL: 148 CTAs, 24 layers) */
 
 /* 1 when the library was built with jaxlib's headers and exports the XLA FFI handler symbols of csrc/mtx_jax_ffi.cc
- * (MtxRaggedAttention, MtxDecodeAttention, MtxQkvRopeAppend, MtxDecodeStep, MtxPagedAppend, MtxPagedAttention), else 0. */
+ * (MtxRaggedAttention, MtxDecodeAttention, MtxQkvRopeAppend, MtxOutprojResidual, MtxMlp, MtxDecodeStep, MtxPagedAppend,
+ * MtxPagedAttention), else 0. */
 int mtx_jax_ffi_available(void);
 
 const char* mtx_last_error(void);

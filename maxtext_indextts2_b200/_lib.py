@@ -205,6 +205,12 @@ def _declare(lib) -> None:
   lib.mtx_rmsnorm.argtypes = [vp, vp, vp, i32, i32, f32, vp]
   lib.mtx_linear.restype = i32
   lib.mtx_linear.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+  lib.mtx_outproj_residual.restype = i32
+  lib.mtx_outproj_residual.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+  lib.mtx_mlp_scratch_bytes.restype = sz
+  lib.mtx_mlp_scratch_bytes.argtypes = [i32, i32, i32]
+  lib.mtx_mlp.restype = i32
+  lib.mtx_mlp.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, f32, vp, vp]
   lib.mtx_attention_scratch_bytes.restype = sz
   lib.mtx_attention_scratch_bytes.argtypes = [i32] * 6
   lib.mtx_decode_attention.restype = i32

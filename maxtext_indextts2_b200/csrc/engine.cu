@@ -298,6 +298,28 @@ bool use_rows_kernel(int r_tile) {
   return on != 0 && r_tile >= 128;
 }
 
+// (plan_gemm / launch_gemm are declared above)
+// out = EPI(x[rows, k] . w[n, k]^T) on whichever tcgen05 GEMM serves the row count (gemm_umma.cuh up to 64 rows, gemm_rows.cuh above)
+template <int EPI>
+int single_gemm(const void* x, const void* w, int rows, int n, int k, EpiArgs ea, cudaStream_t st) {
+  const int r_tile = round_rows(rows);
+  CUtensorMap tw, tx;
+  MTX_TRY(make_map(&tw, w, k, n, kTileN));
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = n;
+  p.k = k;
+  p.rows = rows;
+  p.r_tile = r_tile;
+  if (use_rows_kernel(r_tile)) {
+    const RowsPlan pl = plan_rows(n, k, r_tile, 148, EPI);
+    MTX_TRY(make_map(&tx, x, k, r_tile, pl.splits > 1 ? 128 : r_tile));
+    return launch_rows<EPI>(tw, tx, p, ea, pl, st);
+  }
+  MTX_TRY(make_map(&tx, x, k, r_tile, r_tile));
+  return launch_gemm<EPI>(tw, tx, p, ea, plan_gemm(n, k, r_tile, 148, EPI), st);
+}
+
 struct XMaps {
   bool built = false;
   CUtensorMap n, attn, act, x, h;
@@ -2019,6 +2041,46 @@ int mtx_linear(const void* x, const void* w, void* out, int rows, int n, int k, 
   e.out = static_cast<bf16*>(out);
   e.ld_out = n;
   return launch_gemm<EPI_STORE_BF16>(tw, tx, p, e, g, static_cast<cudaStream_t>(stream));
+}
+
+int mtx_outproj_residual(const void* attn, const void* wo, const void* x, void* out, int rows, int emb_dim, int q_dim, mtx_stream stream) {
+  if (!attn || !wo || !x || !out || rows < 1 || rows > 256 || emb_dim < 8 || emb_dim % 8 != 0 || q_dim < 64 || q_dim % 64 != 0)
+    return fail(MTX_ERR_ARG, "bad out-projection arguments");
+  EpiArgs ea;
+  memset(&ea, 0, sizeof(ea));
+  ea.out = static_cast<bf16*>(out);
+  ea.resid = static_cast<const bf16*>(x);
+  ea.ld_out = emb_dim;
+  return single_gemm<EPI_RESIDUAL>(attn, wo, rows, emb_dim, q_dim, ea, static_cast<cudaStream_t>(stream));
+}
+
+size_t mtx_mlp_scratch_bytes(int rows, int emb_dim, int mlp_dim) {
+  const size_t rt = size_t(round_rows(rows < 1 ? 1 : rows));
+  return align_up(rt * emb_dim * 2, 1024) + align_up(rt * mlp_dim * 2, 1024);
+}
+
+int mtx_mlp(const void* h, const void* norm_scale, const void* w01, const void* wout, void* out, int rows, int emb_dim, int mlp_dim, float eps,
+            void* scratch, mtx_stream stream) {
+  if (!h || !norm_scale || !w01 || !wout || !out || !scratch || rows < 1 || rows > 256) return fail(MTX_ERR_ARG, "bad MLP arguments");
+  if (emb_dim < 64 || emb_dim % 64 != 0 || mlp_dim < 64 || mlp_dim % 64 != 0) return fail(MTX_ERR_UNSUPPORTED, "emb_dim and mlp_dim must be multiples of 64");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t rt = size_t(round_rows(rows));
+  bf16* n = static_cast<bf16*>(scratch);
+  bf16* act = reinterpret_cast<bf16*>(static_cast<uint8_t*>(scratch) + align_up(rt * emb_dim * 2, 1024));
+  // the rows past `rows` of the two scratch matrices feed MMA rows whose results are never stored; keep them finite
+  MTX_CUDA(cudaMemsetAsync(scratch, 0, mtx_mlp_scratch_bytes(rows, emb_dim, mlp_dim), st));
+  MTX_TRY(launch(rmsnorm_kernel<false>, dim3(rows), dim3(128), 0, st, static_cast<const bf16*>(h), (const int*)nullptr, (const bf16*)nullptr,
+                 static_cast<const bf16*>(norm_scale), (bf16*)nullptr, n, emb_dim, eps));
+  EpiArgs ea;
+  memset(&ea, 0, sizeof(ea));
+  ea.out = act;
+  ea.ld_out = mlp_dim;
+  MTX_TRY(single_gemm<EPI_SWIGLU>(n, w01, rows, 2 * mlp_dim, emb_dim, ea, st));
+  memset(&ea, 0, sizeof(ea));
+  ea.out = static_cast<bf16*>(out);
+  ea.resid = static_cast<const bf16*>(h);
+  ea.ld_out = emb_dim;
+  return single_gemm<EPI_RESIDUAL>(act, wout, rows, emb_dim, mlp_dim, ea, st);
 }
 
 size_t mtx_attention_scratch_bytes(int rows, int num_kv_heads, int num_q_heads, int head_dim, int max_prefill_len, int max_target_len) {

@@ -12,6 +12,8 @@
 //   MtxDecodeAttention  -- AttentionOp.__call__ in autoregressive mode over this library's two-segment cache
 //   MtxQkvRopeAppend    -- Attention.query/key/value + RotaryEmbedding + KVCache append (in-place cache: input_output_aliases)
 //   MtxDecodeStep       -- MaxEngine._generate_jit (MaxText/maxengine.py:868-936): the whole step on a bound engine
+//   MtxOutprojResidual  -- Attention.out projection + the residual add (attentions.py:2017-2030, llama2.py:139-140)
+//   MtxMlp              -- MlpBlock with its pre-norm + the residual add (linears.py:425-476, llama2.py:150-163)
 //   MtxPagedAppend      -- PagedAttentionOp.update_decode_step_pages (MaxText/inference/paged_attention.py:446-471), pools donated
 //   MtxPagedAttention   -- PagedAttentionOp.paged_attention_v1_decode (:302-346) on the reference's pools and PageState arrays
 //
@@ -156,7 +158,49 @@ ffi::Error PagedAttentionImpl(cudaStream_t stream, ffi::Buffer<ffi::BF16> q, ffi
                                     stream));
 }
 
+// (attn [rows padded, Hq*D], wo [E, Hq*D], x [rows, E]) -> out [rows, E];  rows = the leading dimension of x
+ffi::Error OutprojResidualImpl(cudaStream_t stream, ffi::Buffer<ffi::BF16> attn, ffi::Buffer<ffi::BF16> wo, ffi::Buffer<ffi::BF16> x,
+                               ffi::ResultBuffer<ffi::BF16> out) {
+  const auto wd = wo.dimensions();
+  const auto xd = x.dimensions();
+  if (wd.size() != 2 || xd.size() != 2) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "wo must be [E, Hq*D], x [rows, E]");
+  return Status(mtx_outproj_residual(attn.untyped_data(), wo.untyped_data(), x.untyped_data(), out->untyped_data(), int(xd[0]), int(wd[0]),
+                                     int(wd[1]), stream));
+}
+
+// (h [rows padded, E], norm_scale [E], w01 [2M, E], wout [E, M], scratch u8[...]) -> out [rows, E];  rows = the leading dimension of out
+ffi::Error MlpImpl(cudaStream_t stream, ffi::Buffer<ffi::BF16> h, ffi::Buffer<ffi::BF16> norm_scale, ffi::Buffer<ffi::BF16> w01,
+                   ffi::Buffer<ffi::BF16> wout, ffi::Buffer<ffi::U8> scratch, ffi::ResultBuffer<ffi::BF16> out, float eps) {
+  const auto wd = wout.dimensions();
+  const auto od = out->dimensions();
+  if (wd.size() != 2 || od.size() != 2) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "wout must be [E, M], out [rows, E]");
+  const int rows = int(od[0]), emb = int(wd[0]), mlp = int(wd[1]);
+  if (scratch.element_count() < mtx_mlp_scratch_bytes(rows, emb, mlp))
+    return ffi::Error(ffi::ErrorCode::kInvalidArgument, "scratch smaller than mtx_mlp_scratch_bytes()");
+  return Status(mtx_mlp(h.untyped_data(), norm_scale.untyped_data(), w01.untyped_data(), wout.untyped_data(), out->untyped_data(), rows, emb, mlp,
+                        eps, scratch.untyped_data(), stream));
+}
+
 }  // namespace
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(MtxOutprojResidual, OutprojResidualImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Ret<ffi::Buffer<ffi::BF16>>());
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(MtxMlp, MlpImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::BF16>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Ret<ffi::Buffer<ffi::BF16>>()
+                                  .Attr<float>("eps"));
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(MtxPagedAppend, PagedAppendImpl,
                               ffi::Ffi::Bind()

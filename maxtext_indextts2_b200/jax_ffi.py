@@ -19,6 +19,8 @@ TARGETS = {
     "mtx_decode_attention": "MtxDecodeAttention",
     "mtx_qkv_rope_append": "MtxQkvRopeAppend",
     "mtx_decode_step": "MtxDecodeStep",
+    "mtx_outproj_residual": "MtxOutprojResidual",
+    "mtx_mlp": "MtxMlp",
     "mtx_paged_append": "MtxPagedAppend",
     "mtx_paged_attention": "MtxPagedAttention",
 }

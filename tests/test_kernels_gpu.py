@@ -264,3 +264,66 @@ def test_qkv_rope_append_op(rows, E, Hq, Hkv, D):
     torch.testing.assert_close(kcc[plane[r], :, write_row[r]], k[r], **tol)
     torch.testing.assert_close(vcc[plane[r], :, write_row[r]], v[r], **tol)
   assert kcc.permute(0, 2, 1, 3)[~written].abs().max() == 0 and vcc.permute(0, 2, 1, 3)[~written].abs().max() == 0  # nothing else touched
+
+
+class _OracleOps:
+  """DecodeOracle's rounding rules (faithful mode) without a model around them."""
+
+  def __init__(self, eps=1e-5):
+    class C:
+      normalization_layer_epsilon = eps
+      decoder_block = "llama2"
+
+    self.o = ref.DecodeOracle.__new__(ref.DecodeOracle)
+    self.o.cfg, self.o.faithful, self.o.scores_f32, self.o.softmax_f32 = C, True, True, True
+
+
+@pytest.mark.parametrize("rows,E,HD", [(1, 256, 256), (37, 1280, 1280), (64, 1280, 1280), (200, 1280, 1280), (256, 640, 512)])
+def test_outproj_residual_matches_oracle(rows, E, HD):
+  """mtx_outproj_residual: out = x + dense(attn, wo) (attentions.py out projection + llama2.py:139-140), bf16 roundings as the oracle's."""
+  lib = _lib.load()
+  g = torch.Generator().manual_seed(rows + E)
+  rt = _round_rows(rows)
+  attn = torch.zeros(rt, HD, dtype=torch.bfloat16)
+  attn[:rows] = torch.randn(rows, HD, generator=g).to(torch.bfloat16)
+  wo = (torch.randn(E, HD, generator=g) / np.sqrt(HD)).to(torch.bfloat16)
+  x = torch.randn(rows, E, generator=g).to(torch.bfloat16)
+  ad, wd, xd = attn.cuda(), wo.cuda(), x.cuda()
+  out = torch.zeros(rows, E, dtype=torch.bfloat16, device="cuda")
+  _lib.check(lib.mtx_outproj_residual(_ptr(ad), _ptr(wd), _ptr(xd), _ptr(out), rows, E, HD, _stream()))
+  torch.cuda.synchronize()
+  o = _OracleOps().o
+  want = o.r(x.float() + o.dense(attn[:rows].float(), wo.float().t()))
+  got = out.cpu().float()
+  err = (got - want).abs()
+  assert err.max() <= 2**-6 * want.abs().max()  # two bf16 roundings (projection, sum), fp32 sums in another order
+  assert (err > 2**-8 * want.abs().clamp(min=1.0)).float().mean() < 0.02
+
+
+@pytest.mark.parametrize("rows,E,M", [(3, 256, 512), (64, 1280, 5120), (130, 1280, 5120), (256, 384, 768)])
+def test_mlp_block_matches_oracle(rows, E, M):
+  """mtx_mlp: out = h + MlpBlock(RMSNorm(h)) (linears.py:425-476, llama2.py:150-163) against DecodeOracle._mlp on the same weights."""
+  lib = _lib.load()
+  g = torch.Generator().manual_seed(rows * 7 + M)
+  rt = _round_rows(rows)
+  h = torch.zeros(rt, E, dtype=torch.bfloat16)
+  h[:rows] = torch.randn(rows, E, generator=g).to(torch.bfloat16)
+  scale = (1 + 0.1 * torch.randn(E, generator=g)).to(torch.bfloat16)
+  w0 = (torch.randn(E, M, generator=g) / np.sqrt(E)).to(torch.bfloat16)  # [E, M] as the reference's wi_0 kernel
+  w1 = (torch.randn(E, M, generator=g) / np.sqrt(E)).to(torch.bfloat16)
+  wout = (torch.randn(M, E, generator=g) / np.sqrt(M)).to(torch.bfloat16)
+  # mtx_weights.w01: rows of wi_0^T / wi_1^T interleaved in groups of 16; wout^T
+  w01 = torch.stack([w0.t().reshape(M // 16, 16, E), w1.t().reshape(M // 16, 16, E)], dim=1).reshape(2 * M, E).contiguous()
+  hd, sd, w01d, woutd = h.cuda(), scale.cuda(), w01.cuda(), wout.t().contiguous().cuda()
+  out = torch.zeros(rows, E, dtype=torch.bfloat16, device="cuda")
+  scratch = torch.empty(lib.mtx_mlp_scratch_bytes(rows, E, M), dtype=torch.uint8, device="cuda")
+  _lib.check(lib.mtx_mlp(_ptr(hd), _ptr(sd), _ptr(w01d), _ptr(woutd), _ptr(out), rows, E, M, 1e-5, _ptr(scratch), _stream()))
+  torch.cuda.synchronize()
+  o = _OracleOps().o
+  lw = dict(mlp_scale=scale.float(), w0=w0.float(), w1=w1.float(), wout=wout.float())
+  hf = h[:rows].float()
+  want = o.r(hf + o._mlp(lw, hf))
+  got = out.cpu().float()
+  err = (got - want).abs()
+  assert err.max() <= 2**-5 * want.abs().max()  # four bf16 roundings deep, hardware exp in the sigmoid
+  assert err.mean() <= 2**-9 * want.abs().mean() + 1e-3
